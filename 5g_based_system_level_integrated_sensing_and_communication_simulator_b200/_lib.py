@@ -1,0 +1,154 @@
+"""ctypes binding of lib/libisac_b200.so (C ABI: include/isac_b200.h).
+
+No fallback of any kind: a missing library or a missing CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libisac_b200.so")
+
+_lib = None
+_lock = threading.Lock()
+_ctxs = {}
+
+
+class IsacError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"isac status {status}: {msg}")
+        self.status = status
+
+
+STATUS = {
+    0: "OK", 1: "INVALID_ARG", 2: "CUDA", 3: "NO_DEVICE", 4: "UNSUPPORTED", 5: "CFAR_WINDOW",
+    6: "NO_LOS_TARGET", 7: "NUM_DETS_ZERO", 8: "CAPACITY",
+}
+
+
+class RdmConfig(C.Structure):
+    _fields_ = [
+        ("nSc", C.c_int32), ("nSym", C.c_int32), ("nAnts", C.c_int32),
+        ("nIFFT", C.c_int32), ("nFFT", C.c_int32),
+        ("cutRow0", C.c_int32), ("cutRow1", C.c_int32), ("cutCol0", C.c_int32), ("cutCol1", C.c_int32),
+        ("guardRows", C.c_int32), ("guardCols", C.c_int32), ("trainRows", C.c_int32), ("trainCols", C.c_int32),
+        ("maxBatch", C.c_int32),
+        ("pfa", C.c_double), ("kaiserBeta", C.c_double),
+    ]
+
+
+def _declare(lib):
+    vp, i32, f64 = C.c_void_p, C.c_int32, C.c_double
+    P = C.POINTER
+    sigs = {
+        "isac_create": ([P(vp), C.c_int], C.c_int),
+        "isac_destroy": ([vp], C.c_int),
+        "isac_last_error": ([vp], C.c_char_p),
+        "isac_set_stream": ([vp, vp], C.c_int),
+        "isac_synchronize": ([vp], C.c_int),
+        "isac_version": ([], C.c_char_p),
+        "isac_rdm_plan_create": ([vp, P(RdmConfig), P(vp)], C.c_int),
+        "isac_rdm_plan_destroy": ([vp], C.c_int),
+        "isac_rdm_plan_info": ([vp, P(f64), P(i32), P(i32)], C.c_int),
+        "isac_rdm_cfar_dev": ([vp, vp, vp, i32, vp], C.c_int),
+        "isac_cfar2d_dev": ([vp, vp, i32], C.c_int),
+        "isac_rdm_get_detections": ([vp, i32, i32, vp, vp, vp], C.c_int),
+        "isac_rdm_get_power": ([vp, i32, vp], C.c_int),
+        "isac_rdm_cfar_host": ([vp, vp, vp, i32, i32, vp, vp, vp, vp], C.c_int),
+    }
+    for name, (args, res) in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    return sigs
+
+
+def exported_symbols():
+    """Names the header declares (used by the CPU-only symbol test)."""
+    import re
+    hdr = os.path.join(os.path.dirname(PKG_DIR), "include", "isac_b200.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(isac_[a-z0-9_]+)\s*\(", txt, flags=re.M)))
+
+
+def load():
+    """Load the shared library (raises if it has not been built)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                    "(python -m 5g_..._b200.build). There is no CPU fallback.")
+            lib = C.CDLL(LIB_PATH)
+            _declare(lib)
+            _lib = lib
+    return _lib
+
+
+def check(status, ctx_handle=None):
+    if status != 0:
+        lib = load()
+        msg = lib.isac_last_error(ctx_handle)
+        raise IsacError(status, f"{STATUS.get(status, '?')}: {msg.decode() if msg else ''}")
+
+
+class Context:
+    """One library context (device + stream)."""
+
+    def __init__(self, device=0):
+        lib = load()
+        h = C.c_void_p()
+        st = lib.isac_create(C.byref(h), int(device))
+        if st != 0:
+            msg = lib.isac_last_error(None)
+            raise IsacError(st, f"{STATUS.get(st, '?')}: {msg.decode() if msg else ''}")
+        self.handle = h
+        self.device = int(device)
+        self.lib = lib
+
+    def set_stream(self, cuda_stream_ptr):
+        check(self.lib.isac_set_stream(self.handle, C.c_void_p(cuda_stream_ptr or 0)), self.handle)
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self):
+        check(self.lib.isac_synchronize(self.handle), self.handle)
+
+    def close(self):
+        if self.handle:
+            self.lib.isac_destroy(self.handle)
+            self.handle = None
+
+
+def get_context(device=None) -> Context:
+    """Process-wide context for a device (default: LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    with _lock:
+        ctx = _ctxs.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        with _lock:
+            _ctxs[device] = ctx
+    return ctx
+
+
+def as_c64(a):
+    """Host complex64, Fortran (MATLAB column-major) order, no copy when already so."""
+    return np.asfortranarray(np.asarray(a, dtype=np.complex64))
+
+
+def ptr(a):
+    """Raw pointer of a numpy array / torch tensor (device or host) / None."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())

@@ -1,0 +1,27 @@
+// Library context: device, stream, error string, twiddle table, reusable staging buffers.
+#pragma once
+#include "isac_common.cuh"
+
+namespace isac {
+
+struct Ctx {
+    static constexpr int kPinnedSlots = 8;
+    static constexpr int kScratchSlots = 16;
+    int device = 0;
+    int numSMs = 0;
+    int ccMajor = 0;
+    cudaStream_t ownStream = nullptr;
+    cudaStream_t stream = nullptr;  // stream every launch / copy is enqueued on
+    float2* d_twiddle = nullptr;    // exp(+2*pi*i*m/4096)
+    std::string err;
+    void* pinned[kPinnedSlots] = {};
+    size_t pinnedBytes[kPinnedSlots] = {};
+    void* scratch[kScratchSlots] = {};
+    size_t scratchBytes[kScratchSlots] = {};
+};
+
+// grow-only pinned host / device scratch buffers owned by the context
+int ctx_pinned(Ctx* ctx, int slot, size_t bytes, void** out);
+int ctx_scratch(Ctx* ctx, int slot, size_t bytes, void** out);
+
+}  // namespace isac

@@ -1,0 +1,187 @@
+// In-register radix-2/4/8/16 DFTs and a shared-memory block FFT (N = R1*R2*16, N <= 4096).
+//
+// Every thread keeps 16 complex values in registers; passes exchange data through shared
+// memory.  The decomposition is decimation-in-frequency so that
+//   * the first pass reads the input at stride N/R1 with consecutive threads on consecutive
+//     elements  (coalesced float2 global loads, natural order), and
+//   * the last pass leaves X[tf + (N/16)*d] in register d of thread tf
+//     (coalesced natural-order global stores straight from registers).
+// `RT` FFT instances can be interleaved in shared memory (element e of instance nl lives at
+// smem[pad(e)*RT + nl]); with RT == 1 the layout is padded so that all three passes are
+// bank-conflict free for 8-byte accesses.
+#pragma once
+#include "isac_common.cuh"
+
+namespace isac {
+
+// multiply by SIGN*j
+template <int SIGN>
+__device__ __forceinline__ float2 mulj(float2 a) {
+    return SIGN > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+template <int SIGN>
+__device__ __forceinline__ void dft2(float2& a, float2& b) {
+    float2 t = csub(a, b);
+    a = cadd(a, b);
+    b = t;
+}
+
+// y_k = sum_n x_n exp(SIGN*2*pi*i*n*k/4)
+template <int SIGN>
+__device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    float2 t0 = cadd(x0, x2), t1 = csub(x0, x2);
+    float2 t2 = cadd(x1, x3), t3 = mulj<SIGN>(csub(x1, x3));
+    x0 = cadd(t0, t2);
+    x2 = csub(t0, t2);
+    x1 = cadd(t1, t3);
+    x3 = csub(t1, t3);
+}
+
+template <int SIGN>
+__device__ __forceinline__ void dft8(float2* v) {
+    // n = 4*n1 + n2, k = k1 + 2*k2
+    constexpr float c = 0.70710678118654752440f;
+    float2 A0[4], A1[4];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        A0[n2] = cadd(v[n2], v[4 + n2]);
+        A1[n2] = csub(v[n2], v[4 + n2]);
+    }
+    // twiddles w8^{n2}, w8 = exp(SIGN*2*pi*i/8)
+    A1[1] = cmul(A1[1], make_float2(c, SIGN * c));
+    A1[2] = mulj<SIGN>(A1[2]);
+    A1[3] = cmul(A1[3], make_float2(-c, SIGN * c));
+    dft4<SIGN>(A0[0], A0[1], A0[2], A0[3]);
+    dft4<SIGN>(A1[0], A1[1], A1[2], A1[3]);
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+        v[2 * k2] = A0[k2];
+        v[2 * k2 + 1] = A1[k2];
+    }
+}
+
+template <int SIGN>
+__device__ __forceinline__ void dft16(float2* v) {
+    // n = 4*n1 + n2, k = k1 + 4*k2
+    constexpr float c1 = 0.92387953251128675613f;  // cos(pi/8)
+    constexpr float s1 = 0.38268343236508977173f;  // sin(pi/8)
+    constexpr float c2 = 0.70710678118654752440f;  // cos(pi/4)
+    float2 A[4][4];  // A[k1][n2]
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        float2 a = v[n2], b = v[4 + n2], c = v[8 + n2], d = v[12 + n2];
+        dft4<SIGN>(a, b, c, d);
+        A[0][n2] = a;
+        A[1][n2] = b;
+        A[2][n2] = c;
+        A[3][n2] = d;
+    }
+    // twiddle w16^{n2*k1}, w16 = exp(SIGN*2*pi*i/16): exponent m -> (cos(pi m/8), SIGN sin(pi m/8))
+    A[1][1] = cmul(A[1][1], make_float2(c1, SIGN * s1));    // m=1
+    A[1][2] = cmul(A[1][2], make_float2(c2, SIGN * c2));    // m=2
+    A[1][3] = cmul(A[1][3], make_float2(s1, SIGN * c1));    // m=3
+    A[2][1] = cmul(A[2][1], make_float2(c2, SIGN * c2));    // m=2
+    A[2][2] = mulj<SIGN>(A[2][2]);                          // m=4
+    A[2][3] = cmul(A[2][3], make_float2(-c2, SIGN * c2));   // m=6
+    A[3][1] = cmul(A[3][1], make_float2(s1, SIGN * c1));    // m=3
+    A[3][2] = cmul(A[3][2], make_float2(-c2, SIGN * c2));   // m=6
+    A[3][3] = cmul(A[3][3], make_float2(-c1, -SIGN * s1));  // m=9
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        dft4<SIGN>(A[k1][0], A[k1][1], A[k1][2], A[k1][3]);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) v[k1 + 4 * k2] = A[k1][k2];
+    }
+}
+
+template <int R, int SIGN>
+__device__ __forceinline__ void dftR(float2* v) {
+    if constexpr (R == 2) dft2<SIGN>(v[0], v[1]);
+    if constexpr (R == 4) dft4<SIGN>(v[0], v[1], v[2], v[3]);
+    if constexpr (R == 8) dft8<SIGN>(v);
+    if constexpr (R == 16) dft16<SIGN>(v);
+}
+
+// master twiddle table tw[m] = exp(+2*pi*i*m/4096) lives in global memory (context-owned,
+// computed in float64 on the host) and is passed to every FFT kernel as a pointer.
+template <int SIGN>
+__device__ __forceinline__ float2 twiddle(const float2* __restrict__ tw, int idx) {
+    float2 w = __ldg(tw + (idx & (kTwiddleN - 1)));
+    if (SIGN < 0) w.y = -w.y;
+    return w;
+}
+
+// Shared-memory geometry of one block FFT.
+template <int R1, int R2, bool PAD>
+struct FftGeom {
+    static constexpr int N = R1 * R2 * 16;
+    static constexpr int NT = N / 16;  // threads per FFT instance
+    static constexpr int N2 = R2 * 16;
+    static constexpr int S2 = (PAD && R1 < 16) ? 16 + R1 : 16;
+    static constexpr int S1raw = R2 * S2;
+    static constexpr int S1 = (PAD && R1 > 1) ? (S1raw + ((17 - (S1raw % 16)) % 16)) : S1raw;  // == 1 (mod 16)
+    static constexpr int kElems = R1 * S1;  // float2 slots per instance
+    __device__ __forceinline__ static int addr(int k1, int mid, int lo) { return k1 * S1 + mid * S2 + lo; }
+};
+
+// Block FFT.  `v` receives X[tf + NT*d] in v[d].  `load(n)` returns input element n.
+// smem points at this instance's slot 0 (already offset by nl); RT = interleave stride.
+template <int R1, int R2, int SIGN, bool PAD, class Load>
+__device__ __forceinline__ void block_fft(float2 (&v)[16], float2* smem, const int RT, const int tf,
+                                          const float2* __restrict__ tw, Load load) {
+    using G = FftGeom<R1, R2, PAD>;
+    constexpr int N = G::N, NT = G::NT, N2 = G::N2;
+    if constexpr (R1 > 1) {
+#pragma unroll
+        for (int i = 0; i < 16 / R1; ++i) {
+            const int m = tf + NT * i;  // 0..N2-1
+#pragma unroll
+            for (int j = 0; j < R1; ++j) v[i * R1 + j] = load(N2 * j + m);
+            dftR<R1, SIGN>(&v[i * R1]);
+#pragma unroll
+            for (int k1 = 1; k1 < R1; ++k1)
+                v[i * R1 + k1] = cmul(v[i * R1 + k1], twiddle<SIGN>(tw, (m * k1) * (kTwiddleN / N)));
+#pragma unroll
+            for (int k1 = 0; k1 < R1; ++k1) smem[G::addr(k1, m >> 4, m & 15) * RT] = v[i * R1 + k1];
+        }
+        __syncthreads();
+    }
+    if constexpr (R2 > 1) {
+#pragma unroll
+        for (int i = 0; i < 16 / R2; ++i) {
+            const int g = tf + NT * i;  // 0..R1*16-1
+            const int k1 = g >> 4, b = g & 15;
+#pragma unroll
+            for (int a = 0; a < R2; ++a) {
+                if constexpr (R1 > 1) v[i * R2 + a] = smem[G::addr(k1, a, b) * RT];
+                else v[i * R2 + a] = load(a * 16 + b);
+            }
+            dftR<R2, SIGN>(&v[i * R2]);
+#pragma unroll
+            for (int c = 1; c < R2; ++c)
+                v[i * R2 + c] = cmul(v[i * R2 + c], twiddle<SIGN>(tw, (b * c) * (kTwiddleN / N2)));
+#pragma unroll
+            for (int c = 0; c < R2; ++c) smem[G::addr(k1, c, b) * RT] = v[i * R2 + c];
+        }
+        __syncthreads();
+    }
+    {
+        const int k1 = tf % R1, c = tf / R1;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            if constexpr (R1 * R2 > 1) v[b] = smem[G::addr(k1, c, b) * RT];
+            else v[b] = load(b);
+        }
+        dft16<SIGN>(v);
+    }
+}
+
+// log2 helpers for dispatch
+inline int ilog2(int n) {
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return l;
+}
+
+}  // namespace isac

@@ -1,0 +1,66 @@
+// Shared device/host helpers for the ISAC B200 hot-path library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace isac {
+
+constexpr int kTwiddleN = 4096;  // master twiddle table: tw[m] = exp(+2*pi*i*m/4096)
+
+// ---- complex helpers (float2 = interleaved complex, MATLAB mxComplexSingle layout) ----
+__host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+__host__ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+
+__host__ __device__ __forceinline__ double2 zmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ double2 zmulc(double2 a, double2 b) {  // a*conj(b)
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__host__ __device__ __forceinline__ double2 zadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ double2 zsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+
+// streaming (read-once) global load: ld.global.cs (evict-first in L1/L2)
+__device__ __forceinline__ float2 ld_stream(const float2* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+// ---- status codes of the C ABI (mirrored in include/isac_b200.h) ----
+enum Status : int {
+    kOk = 0,
+    kErrInvalidArg = 1,
+    kErrCuda = 2,
+    kErrNoDevice = 3,
+    kErrUnsupported = 4,
+    kErrCfarWindow = 5,   // a CUT's training window leaves the RD map (reference: CFARDetector2D errors)
+    kErrNoLosTarget = 6,  // every target NLoS (reference: empty waveform, basicRadarChannel.m:59)
+    kErrNumDetsZero = 7,  // MUSIC asked for zero sources (reference: findpeaks NPeaks=0 errors)
+    kErrCapacity = 8,
+};
+
+struct Ctx;  // defined in capi.cu
+
+void set_error(Ctx* ctx, const std::string& msg);
+const float2* ctx_twiddle(Ctx* ctx);  // device pointer to exp(+2*pi*i*m/4096), m < 4096
+
+#define ISAC_CUDA_CHECK(ctx, expr)                                                          \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ::isac::set_error((ctx), std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+            return ::isac::kErrCuda;                                                        \
+        }                                                                                   \
+    } while (0)
+
+}  // namespace isac

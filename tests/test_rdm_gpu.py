@@ -1,0 +1,151 @@
+"""GPU parity: 2D-FFT range-Doppler map + 2D CA-CFAR (csrc/rdm.cu) vs the float64 oracle.
+
+Tolerances (north_star): CFAR detection indices bit-exact; |RDM|^2 within 1e-5 relative (fp32),
+measured relative to the map's peak and, cell-wise, on the cells within 40 dB of the peak
+(an fp32 FFT cannot hold 1e-5 on cells 70 dB under the peak).
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import sensing as S
+
+PKG = "5g_based_system_level_integrated_sensing_and_communication_simulator_b200"
+pytestmark = pytest.mark.gpu
+
+
+def _scenario(workloads, name, seed=1):
+    cell, car, wave = workloads.cell_config(name)
+    rp = S.radar_params(cell, car, wave)
+    grid, txw = workloads.sensing_tx(name, seed)
+    noise = workloads.std_normal_complex(txw.shape, seed + 1)
+    rx = S.mono_static_sensing(txw, grid.shape, car, rp, cell["targetLoSConditions"], noise)
+    cf = S.cfar2d_config(rp)
+    return rp, cf, rx.astype(np.complex64), grid.astype(np.complex64)
+
+
+def _plan(rp, cf, shape, **kw):
+    rdm = importlib.import_module(PKG + ".sensing._rdm")
+    return rdm.RangeDopplerPlan(shape[0], shape[1], shape[2], rp["nIFFT"], rp["nFFT"],
+                                cf["rngIdx"], cf["dopIdx"], rp["Pfa"], **kw)
+
+
+def _to_dev(a):
+    import torch
+    # MATLAB [nSc x nSym x nAnts] column-major == C-contiguous [nAnts][nSym][nSc]
+    return torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0))).cuda()
+
+
+def _check_power(P_gpu, P_ref):
+    peak = P_ref.max()
+    err_peak = np.abs(P_gpu - P_ref).max() / peak
+    strong = P_ref >= peak * 1e-4
+    err_strong = (np.abs(P_gpu - P_ref)[strong] / P_ref[strong]).max()
+    err_l2 = np.linalg.norm((P_gpu - P_ref).ravel()) / np.linalg.norm(P_ref.ravel())
+    print(f"power err: rel-to-peak {err_peak:.3e}  strong-cells {err_strong:.3e}  l2 {err_l2:.3e}")
+    assert err_peak <= 1e-5
+    assert err_strong <= 1e-5
+    assert err_l2 <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg1"])
+def test_rdm_power_and_cfar_match_oracle(gpu, workloads, name):
+    rp, cf, rx, tx = _scenario(workloads, name)
+    plan = _plan(rp, cf, rx.shape)
+    plan.run_dev(_to_dev(rx), _to_dev(tx), 1)
+    P_gpu = plan.power(1)[..., 0].astype(np.float64)
+    ref = S.fft2d(rp, cf, rx, tx)
+    P_ref = np.abs(ref["rdm"]) ** 2
+    _check_power(P_gpu, P_ref)
+    cnt, dets = plan.detections(1)
+    # (1) bit-exact against the float64 detector applied to the SAME fp32 map
+    for r in range(rx.shape[2]):
+        exp = S.cfar2d_detect_exact(P_gpu[:, :, r], cf)
+        assert np.array_equal(dets[0][r][0], exp), f"antenna {r}"
+        assert np.array_equal(dets[0][r][1], P_gpu[exp[0] - 1, exp[1] - 1, r].astype(np.float32))
+    # (2) identical to the all-float64 reference chain
+    for r in range(rx.shape[2]):
+        assert np.array_equal(dets[0][r][0], ref["detections"][r]), f"antenna {r} vs f64 chain"
+    assert cnt.sum() > 0
+    assert abs(plan.alpha - S.cfar_threshold_factor(24, rp["Pfa"])) < 1e-12 * plan.alpha
+    plan.close()
+
+
+def test_rdm_truncating_doppler_fft_and_odd_sizes(gpu, workloads):
+    """nSym > nFFT (MATLAB fft truncates, fft2D.m:46), odd nSym and odd nAnts (all-dim shifts)."""
+    rng = np.random.default_rng(5)
+    nSc, nSym, nAnts = 300, 77, 3
+    rp = {"nIFFT": 512, "nFFT": 64, "rRes": 1.0, "vRes": 1.0, "Pfa": 1e-3,
+          "cfarEstZone": np.array([[10.0, 200.0], [-20.0, 20.0]])}
+    cf = S.cfar2d_config(rp)
+    rx = (rng.standard_normal((nSc, nSym, nAnts)) + 1j * rng.standard_normal((nSc, nSym, nAnts))).astype(np.complex64)
+    tx = (rng.standard_normal((nSc, nSym, nAnts)) + 1j * rng.standard_normal((nSc, nSym, nAnts))).astype(np.complex64)
+    plan = _plan(rp, cf, rx.shape)
+    plan.run_dev(_to_dev(rx), _to_dev(tx), 1)
+    P_gpu = plan.power(1)[..., 0].astype(np.float64)
+    P_ref = np.abs(S.rdm_2dfft(rp, rx, tx)) ** 2
+    err = np.abs(P_gpu - P_ref).max() / P_ref.max()
+    print("noise-map err rel-to-peak", err)
+    assert err <= 1e-5
+    _, dets = plan.detections(1)
+    for r in range(nAnts):
+        assert np.array_equal(dets[0][r][0], S.cfar2d_detect_exact(P_gpu[:, :, r], cf))
+    plan.close()
+
+
+@pytest.mark.parametrize("nfft_sym", [(256, 16, 10), (2048, 128, 100), (4096, 256, 168), (1024, 2048, 1100)])
+def test_rdm_fft_sizes(gpu, nfft_sym):
+    """Every supported (nIFFT, nFFT) radix decomposition against numpy."""
+    nIFFT, nFFT, nSym = nfft_sym
+    rng = np.random.default_rng(nIFFT + nFFT)
+    nSc, nAnts = nIFFT - 52, 2
+    rp = {"nIFFT": nIFFT, "nFFT": nFFT, "rRes": 1.0, "vRes": 1.0, "Pfa": 1e-4,
+          "cfarEstZone": np.array([[10.0, 100.0], [-4.0, 3.0]])}
+    cf = S.cfar2d_config(rp)
+    rx = (rng.standard_normal((nSc, nSym, nAnts)) + 1j * rng.standard_normal((nSc, nSym, nAnts))).astype(np.complex64)
+    tx = np.exp(2j * np.pi * rng.random((nSc, nSym, nAnts))).astype(np.complex64)
+    plan = _plan(rp, cf, rx.shape)
+    plan.run_dev(_to_dev(rx), _to_dev(tx), 1)
+    P_gpu = plan.power(1)[..., 0].astype(np.float64)
+    P_ref = np.abs(S.rdm_2dfft(rp, rx, tx)) ** 2
+    err = np.abs(P_gpu - P_ref).max() / P_ref.max()
+    print(nfft_sym, "err rel-to-peak", err)
+    assert err <= 1e-5
+    plan.close()
+
+
+def test_rdm_batch_and_host_path(gpu, workloads):
+    """A batch of map-sets equals the per-map results; host-pointer entry equals device entry."""
+    import torch
+    rp, cf, rx, tx = _scenario(workloads, "tiny")
+    rng = np.random.default_rng(9)
+    B = 3
+    rxs = np.stack([rx * np.exp(1j * rng.random()) + 0.01 * b for b in range(B)], axis=3).astype(np.complex64)
+    txs = np.stack([tx] * B, axis=3).astype(np.complex64)
+    plan = _plan(rp, cf, rx.shape, max_batch=B)
+    rx_d = torch.from_numpy(np.ascontiguousarray(rxs.transpose(3, 2, 1, 0))).cuda()
+    tx_d = torch.from_numpy(np.ascontiguousarray(txs.transpose(3, 2, 1, 0))).cuda()
+    plan.run_dev(rx_d, tx_d, B)
+    P_b = plan.power(B).copy()
+    cnt_b, det_b = plan.detections(B)
+    for b in range(B):
+        plan.run_dev(_to_dev(rxs[..., b]), _to_dev(txs[..., b]), 1)
+        assert np.array_equal(plan.power(1)[..., 0], P_b[..., b])
+        c1, d1 = plan.detections(1)
+        assert np.array_equal(c1[0], cnt_b[b])
+        for r in range(rx.shape[2]):
+            assert np.array_equal(d1[0][r][0], det_b[b][r][0])
+    cnt_h, det_h, P_h = plan.run_host(np.asfortranarray(rxs), np.asfortranarray(txs), B, want_power=True)
+    assert np.array_equal(P_h, P_b)
+    assert np.array_equal(cnt_h, cnt_b)
+    plan.close()
+
+
+def test_cfar_window_outside_map_is_an_error(gpu):
+    """phased.CFARDetector2D errors when a CUT's training window leaves the matrix."""
+    _lib = importlib.import_module(PKG + "._lib")
+    rdm = importlib.import_module(PKG + ".sensing._rdm")
+    with pytest.raises(_lib.IsacError) as e:
+        rdm.RangeDopplerPlan(288, 42, 4, 512, 64, (2, 27), (28, 38), 1e-9)
+    assert e.value.status == 5
