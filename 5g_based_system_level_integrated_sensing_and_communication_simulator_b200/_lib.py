@@ -49,6 +49,7 @@ def _declare(lib):
         "isac_destroy": ([vp], C.c_int),
         "isac_last_error": ([vp], C.c_char_p),
         "isac_set_stream": ([vp, vp], C.c_int),
+        "isac_use_own_stream": ([vp], C.c_int),
         "isac_synchronize": ([vp], C.c_int),
         "isac_version": ([], C.c_char_p),
         "isac_rdm_plan_create": ([vp, P(RdmConfig), P(vp)], C.c_int),
@@ -113,6 +114,9 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         check(self.lib.isac_set_stream(self.handle, C.c_void_p(cuda_stream_ptr or 0)), self.handle)
+
+    def use_own_stream(self):
+        check(self.lib.isac_use_own_stream(self.handle), self.handle)
 
     def use_torch_stream(self):
         import torch

@@ -132,7 +132,13 @@ const char* isac_last_error(const isac_ctx* h) {
 
 int isac_set_stream(isac_ctx* h, void* s) {
     if (!h) return ISAC_ERR_INVALID_ARG;
-    h->c.stream = s ? (cudaStream_t)s : h->c.ownStream;
+    h->c.stream = (cudaStream_t)s;  // NULL == the CUDA legacy default stream
+    return ISAC_OK;
+}
+
+int isac_use_own_stream(isac_ctx* h) {
+    if (!h) return ISAC_ERR_INVALID_ARG;
+    h->c.stream = h->c.ownStream;
     return ISAC_OK;
 }
 

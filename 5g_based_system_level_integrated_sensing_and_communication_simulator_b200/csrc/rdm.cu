@@ -17,7 +17,7 @@
 //   N-point inverse FFT in shared memory, w2/sqrt(N)/(-1)^s' epilogue, coalesced float2 stores.
 // Kernel B (Doppler): one CTA per tile of RT consecutive range rows of one antenna page; loads are
 //   coalesced along the range axis, the F-point FFTs run interleaved in shared memory, the
-//   epilogue writes |.|^2 with the Doppler fftshift folded into the store index.
+//   epilogue writes |.|^2 (the Doppler fftshift is the (-1)^s' modulation applied by kernel A).
 // Kernel C (CFAR): one thread per cell under test, float64 training sum in a fixed order,
 //   strict `>` against alpha*mean, flags + detected-row bitmap.
 // Kernel D (compaction): one CTA per (antenna, map): ordered stream compaction of the flags into
@@ -102,10 +102,10 @@ rdm_doppler_fft_kernel(const RdmDev p, const int RT, const float invF) {
     float2 v[16];
     block_fft<R1, R2, -1, false>(v, smem + nl, RT, tf, p.tw, load);
     float* __restrict__ out = p.pow + page * (long long)p.nFFT * nIFFT + n;
-    constexpr int F = G::N;
 #pragma unroll
     for (int d = 0; d < 16; ++d) {
-        const int q = (tf + G::NT * d + F / 2) & (F - 1);  // fftshift on the Doppler axis (fft2D.m:46)
+        // Doppler-axis fftshift (fft2D.m:46) already applied: kernel A modulated symbol s' by (-1)^s'
+        const int q = tf + G::NT * d;
         out[(long long)q * nIFFT] = (v[d].x * v[d].x + v[d].y * v[d].y) * invF;  // abs(rdm).^2 (fft2D.m:61)
     }
 }

@@ -85,7 +85,7 @@ class RangeDopplerPlan:
         pk = np.zeros((nA * batch, max_det), dtype=np.float32)
         nI, nF, _ = self.shape_rdm
         pw = np.zeros(nI * nF * nA * batch, dtype=np.float32) if want_power else None
-        self.ctx.set_stream(None)
+        self.ctx.use_own_stream()
         _lib.check(self.lib.isac_rdm_cfar_host(self.handle, _lib.ptr(rx), _lib.ptr(tx), batch, max_det,
                                                _lib.ptr(cnt), _lib.ptr(rc), _lib.ptr(pk), _lib.ptr(pw)),
                    self.ctx.handle)

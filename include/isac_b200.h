@@ -45,8 +45,10 @@ typedef struct isac_rdm_plan isac_rdm_plan;
 int isac_create(isac_ctx** ctx, int device);
 int isac_destroy(isac_ctx* ctx);
 const char* isac_last_error(const isac_ctx* ctx);
-/* Use an existing cudaStream_t (e.g. torch's current stream); NULL restores the context's own stream. */
+/* Enqueue on an existing cudaStream_t (e.g. torch's current stream); NULL = CUDA legacy default stream. */
 int isac_set_stream(isac_ctx* ctx, void* cuda_stream);
+/* Go back to the context's private non-blocking stream (the default after isac_create). */
+int isac_use_own_stream(isac_ctx* ctx);
 int isac_synchronize(isac_ctx* ctx);
 const char* isac_version(void);
 
