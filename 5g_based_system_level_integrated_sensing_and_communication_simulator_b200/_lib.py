@@ -41,6 +41,39 @@ class RdmConfig(C.Structure):
     ]
 
 
+class DoaConfig(C.Structure):
+    _fields_ = [
+        ("isUpa", C.c_int32), ("nAnts", C.c_int32), ("nX", C.c_int32), ("nY", C.c_int32),
+        ("d", C.c_double), ("aGran", C.c_double), ("aMax", C.c_double),
+        ("eGran", C.c_double), ("eMax", C.c_double),
+    ]
+
+
+class Music2dConfig(C.Structure):
+    _fields_ = [
+        ("nSc", C.c_int32), ("nSym", C.c_int32), ("nAnts", C.c_int32),
+        ("scsHz", C.c_double), ("fc", C.c_double), ("Tsri", C.c_double),
+        ("rMax", C.c_double), ("vZone", C.c_double),
+        ("doa", DoaConfig),
+        ("numDetsOverride", C.c_int32),
+    ]
+
+
+class EchoConfig(C.Structure):
+    _fields_ = [
+        ("T", C.c_int64), ("nTx", C.c_int32), ("nTargets", C.c_int32),
+        ("fc", C.c_double), ("fs", C.c_double), ("N0", C.c_double),
+        ("range", C.c_void_p), ("velocity", C.c_void_p), ("largeScaleFading", C.c_void_p),
+        ("steeringVec", C.c_void_p), ("los", C.c_void_p),
+        ("nfft", C.c_int32), ("nSc", C.c_int32), ("nSymTx", C.c_int32), ("symbolsPerSubframe", C.c_int32),
+        ("cpLengths", C.c_void_p),
+    ]
+
+
+NOISE_NONE, NOISE_TENSOR, NOISE_PHILOX = 0, 1, 2
+MAX_PEAKS = 64
+
+
 def _declare(lib):
     vp, i32, f64 = C.c_void_p, C.c_int32, C.c_double
     P = C.POINTER
@@ -60,6 +93,20 @@ def _declare(lib):
         "isac_rdm_get_detections": ([vp, i32, i32, vp, vp, vp], C.c_int),
         "isac_rdm_get_power": ([vp, i32, vp], C.c_int),
         "isac_rdm_cfar_host": ([vp, vp, vp, i32, i32, vp, vp, vp, vp], C.c_int),
+        "isac_music_doa_host": ([vp, P(DoaConfig), vp, i32, P(i32), vp, P(i32), vp, vp], C.c_int),
+        "isac_sense_plan_create": ([vp, P(RdmConfig), P(DoaConfig), f64, f64, P(vp)], C.c_int),
+        "isac_sense_plan_destroy": ([vp], C.c_int),
+        "isac_sense_plan_rdm": ([vp], vp),
+        "isac_fft2d_dev": ([vp, vp, vp, i32, vp], C.c_int),
+        "isac_fft2d_collect": ([vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp], C.c_int),
+        "isac_fft2d_get_spectrum": ([vp, i32, vp], C.c_int),
+        "isac_fft2d_host": ([vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp], C.c_int),
+        "isac_music2d_dev": ([vp, P(Music2dConfig), vp, vp, P(i32), vp, P(i32), vp, P(i32), vp, P(i32), vp, vp,
+                              P(i32)], C.c_int),
+        "isac_antenna_covariance_dev": ([vp, vp, C.c_int64, i32, vp], C.c_int),
+        "isac_radar_channel_dev": ([vp, P(EchoConfig), vp, vp, i32, C.c_uint64, vp], C.c_int),
+        "isac_mono_static_sensing_dev": ([vp, P(EchoConfig), vp, vp, i32, C.c_uint64, vp, P(i32)], C.c_int),
+        "isac_mono_static_sensing_host": ([vp, P(EchoConfig), vp, vp, i32, C.c_uint64, vp, P(i32)], C.c_int),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(lib, name)
@@ -73,7 +120,7 @@ def exported_symbols():
     import re
     hdr = os.path.join(os.path.dirname(PKG_DIR), "include", "isac_b200.h")
     txt = open(hdr).read()
-    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(isac_[a-z0-9_]+)\s*\(", txt, flags=re.M)))
+    return sorted(set(re.findall(r"^(?:int|const char\*|isac_[a-z0-9_]+\s*\*)\s*(isac_[a-z0-9_]+)\s*\(", txt, flags=re.M)))
 
 
 def load():

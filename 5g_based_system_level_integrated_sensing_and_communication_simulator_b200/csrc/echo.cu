@@ -1,0 +1,367 @@
+// K1 + K2: mono-static radar echo synthesis fused with CP-OFDM demodulation.
+//
+// Replaces sensing.channelModels.basicRadarChannel (+sensing/+channelModels/basicRadarChannel.m:8-74)
+// and the nrOFDMDemodulate call of sensing.monoStaticSensing (+sensing/monoStaticSensing.m:13-21).
+//
+// basicRadarChannel, restated analytically (the up-converted waveform never exists):
+//   rx[n,r] = sum_i a_i[r] * w_i[n] + sqrt(N0/2) * z[n,r],                        0 <= n < T
+//   w_i[n]  = beta_i * exp(2 pi j fd_i Ts n) * u_i[n - s_i],   u_i[m] = sum_t tx[m,t] a_i[t]  (0 for m < 0)
+//   s_i = ceil(2 R_i / (c Ts)) (:21-22), fd_i = 2 v_i / lambda (:25),
+//   beta_i = largeScaleFading_i * exp(-2 pi j fc Ts s_i): the carrier terms of :30, :42, :73 cancel to
+//   this constant, evaluated in float64 on the host (2 pi fc t itself does not fit float32).
+// OFDM demodulation is linear, so per OFDM symbol the kernel transforms the nTargets streams w_i
+// (not the nAnts antenna streams) and combines them per antenna in the frequency domain:
+//   echoGrid[k,s,r] = ramp_s[k] * ( sum_i a_i[r] FFT{w_i}[bin(k)] + noise term ).
+// Noise: (a) explicit time-domain standard-normal tensor z (parity mode; one extra FFT per antenna),
+//        (b) counter-based Philox generated directly in the frequency domain (white Gaussian noise is
+//            invariant under the unitary DFT up to the sqrt(Nfft) scale), or (c) none.
+#include "echo.cuh"
+#include "ctx.cuh"
+#include "fft_core.cuh"
+#include <cmath>
+#include <vector>
+
+namespace isac {
+
+struct EchoDev {
+    const float2* tx;      // [T x nTx]
+    const float2* noise;   // [T x nAnts] standard normals, or nullptr
+    const float2* steer;   // [nAnts x nTgt] float2 (device)
+    const int* symStart;   // [nSymRx] first CP sample of each symbol
+    const int* cpLen;      // [nSymRx]
+    const float2* tw;
+    float2* out;           // [nSc x nSymOut x nAnts]
+    long long T;
+    int nTx, nAnts, nTgt, nSymRx, nSymOut, nfft, nSc;
+    int noiseMode;         // 0 none, 1 explicit time-domain tensor, 2 generated (frequency domain)
+    float noiseSigma;      // sqrt(N0/2)
+    unsigned long long seed;
+    int shift[kEchoMaxTargets];
+    float2 beta[kEchoMaxTargets];
+    double fdTs[kEchoMaxTargets];
+};
+
+// Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float2 gauss_pair(unsigned a, unsigned b) {
+    const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;  // (0,1)
+    const float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    return make_float2(r * c, r * s);
+}
+
+// stream sample w_i[n] (see file header)
+__device__ __forceinline__ float2 target_sample(const EchoDev& p, int i, long long n, long long n0, double base,
+                                                const float2* __restrict__ a /*steer column i*/) {
+    const long long m = n - p.shift[i];
+    if (n >= p.T || m < 0) return make_float2(0.f, 0.f);
+    float2 u = make_float2(0.f, 0.f);
+    for (int t = 0; t < p.nTx; ++t) {
+        const float2 x = __ldg(p.tx + (long long)t * p.T + m);
+        const float2 at = a[t];
+        u.x += x.x * at.x - x.y * at.y;
+        u.y += x.x * at.y + x.y * at.x;
+    }
+    const float ph = (float)base + (float)p.fdTs[i] * (float)(n - n0);  // cycles
+    float s, c;
+    sincospif(2.0f * ph, &s, &c);
+    return cmul(cmul(u, make_float2(c, s)), p.beta[i]);
+}
+
+template <int R1, int R2>
+__global__ void __launch_bounds__((R1 * R2 >= 256 ? R1 * R2 : 256))
+echo_demod_kernel(const EchoDev p) {
+    using G = FftGeom<R1, R2, true>;
+    constexpr int NT = G::NT, NF = G::N;
+    extern __shared__ float2 smem[];
+    const int groups = blockDim.x / NT;
+    const int grp = threadIdx.x / NT, tf = threadIdx.x % NT;
+    float2* fftbuf = smem + grp * G::kElems;
+    float2* Wf = smem + groups * G::kElems;                       // [nTgt][nSc]
+    float2* steerS = Wf + (size_t)p.nTgt * p.nSc;                  // [nAnts x nTgt]
+    __shared__ double baseCycles[kEchoMaxTargets];
+    const int s = blockIdx.x;
+    for (int i = threadIdx.x; i < p.nAnts * p.nTgt; i += blockDim.x) steerS[i] = p.steer[i];
+    if (s >= p.nSymRx) {  // zero padding up to txDimension(2) (monoStaticSensing.m:19-21)
+        for (int r = 0; r < p.nAnts; ++r)
+            for (int k = threadIdx.x; k < p.nSc; k += blockDim.x)
+                p.out[((long long)r * p.nSymOut + s) * p.nSc + k] = make_float2(0.f, 0.f);
+        return;
+    }
+    const int cp = p.cpLen[s];
+    const int off = cp / 2;                       // fix(cp * CyclicPrefixFraction), fraction 0.5
+    const long long n0 = (long long)p.symStart[s] + off;
+    if (threadIdx.x < p.nTgt) {
+        const double c = p.fdTs[threadIdx.x] * (double)n0;
+        baseCycles[threadIdx.x] = c - floor(c);
+    }
+    __syncthreads();
+    const int half = p.nSc / 2;
+    // ---- targets: FFT{w_i} -> Wf[i][k] ----
+    for (int j0 = 0; j0 < p.nTgt; j0 += groups) {
+        const int i = j0 + grp;
+        const bool act = i < p.nTgt;
+        const float2* a = steerS + (act ? i : 0) * p.nAnts;  // a_t == a_r (basicRadarChannel.m:36)
+        const double base = act ? baseCycles[i] : 0.0;
+        auto load = [&](int n) -> float2 {
+            if (!act) return make_float2(0.f, 0.f);
+            return target_sample(p, i, n0 + n, n0, base, a);
+        };
+        float2 v[16];
+        block_fft<R1, R2, -1, true>(v, fftbuf, 1, tf, p.tw, load);
+        if (act) {
+#pragma unroll
+            for (int d = 0; d < 16; ++d) {
+                const int bin = tf + NT * d;
+                int k = -1;
+                if (bin < p.nSc - half) k = bin + half;
+                else if (bin >= NF - half) k = bin - (NF - half);
+                if (k >= 0) Wf[(size_t)i * p.nSc + k] = v[d];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- antennas: combine, add noise, phase ramp, store ----
+    const float rampStep = (float)(cp - off) / (float)NF;  // cycles per subcarrier index
+    for (int r0 = 0; r0 < p.nAnts; r0 += groups) {
+        const int r = r0 + grp;
+        const bool act = r < p.nAnts;
+        float2 v[16];
+        if (p.noiseMode == 1) {
+            const float2* __restrict__ z = p.noise + (long long)(act ? r : 0) * p.T;
+            auto load = [&](int n) -> float2 {
+                const long long nn = n0 + n;
+                if (!act || nn >= p.T) return make_float2(0.f, 0.f);
+                return __ldg(z + nn);
+            };
+            block_fft<R1, R2, -1, true>(v, fftbuf, 1, tf, p.tw, load);
+        }
+        if (act) {
+#pragma unroll
+            for (int d = 0; d < 16; ++d) {
+                const int bin = tf + NT * d;
+                int k = -1;
+                if (bin < p.nSc - half) k = bin + half;
+                else if (bin >= NF - half) k = bin - (NF - half);
+                if (k < 0) continue;
+                float2 acc = make_float2(0.f, 0.f);
+                for (int i = 0; i < p.nTgt; ++i) {
+                    const float2 w = Wf[(size_t)i * p.nSc + k];
+                    const float2 ar = steerS[i * p.nAnts + r];
+                    acc.x += w.x * ar.x - w.y * ar.y;
+                    acc.y += w.x * ar.y + w.y * ar.x;
+                }
+                if (p.noiseMode == 1) {
+                    acc.x += p.noiseSigma * v[d].x;
+                    acc.y += p.noiseSigma * v[d].y;
+                } else if (p.noiseMode == 2) {
+                    const uint4 ctr = make_uint4((unsigned)k, (unsigned)s, (unsigned)r, 0x15ACu);
+                    const uint4 rn = philox4x32(ctr, make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
+                    const float2 g = gauss_pair(rn.x, rn.y);
+                    const float sc = p.noiseSigma * sqrtf((float)NF);
+                    acc.x += sc * g.x;
+                    acc.y += sc * g.y;
+                }
+                // undo the early FFT window start: exp(+2 pi j kk (cp - off)/Nfft), kk = k - nSc/2
+                float sn, cs;
+                sincospif(2.0f * rampStep * (float)(k - half), &sn, &cs);
+                p.out[((long long)r * p.nSymOut + s) * p.nSc + k] = cmul(acc, make_float2(cs, sn));
+            }
+        }
+        if (p.noiseMode == 1) __syncthreads();
+    }
+}
+
+// basicRadarChannel alone: rxWaveform [T x nAnts]
+__global__ void __launch_bounds__(256)
+radar_channel_kernel(const EchoDev p, float2* __restrict__ rxWave) {
+    extern __shared__ float2 steerS[];
+    for (int i = threadIdx.x; i < p.nAnts * p.nTgt; i += blockDim.x) steerS[i] = p.steer[i];
+    __syncthreads();
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.T) return;
+    float2 w[kEchoMaxTargets];
+    for (int i = 0; i < p.nTgt; ++i) {
+        const double c = p.fdTs[i] * (double)n;
+        w[i] = target_sample(p, i, n, n, c - floor(c), steerS + i * p.nAnts);
+    }
+    for (int r = 0; r < p.nAnts; ++r) {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int i = 0; i < p.nTgt; ++i) {
+            const float2 ar = steerS[i * p.nAnts + r];
+            acc.x += w[i].x * ar.x - w[i].y * ar.y;
+            acc.y += w[i].x * ar.y + w[i].y * ar.x;
+        }
+        if (p.noiseMode == 1) {
+            const float2 z = __ldg(p.noise + (long long)r * p.T + n);
+            acc.x += p.noiseSigma * z.x;
+            acc.y += p.noiseSigma * z.y;
+        } else if (p.noiseMode == 2) {
+            const uint4 ctr = make_uint4((unsigned)(n & 0xffffffffu), (unsigned)(n >> 32), (unsigned)r, 0x7D0Au);
+            const uint4 rn = philox4x32(ctr, make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
+            const float2 g = gauss_pair(rn.x, rn.y);
+            acc.x += p.noiseSigma * g.x;
+            acc.y += p.noiseSigma * g.y;
+        }
+        rxWave[(long long)r * p.T + n] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int fill_targets(Ctx* ctx, const EchoConfig& c, EchoDev& d, std::vector<float2>& steerHost) {
+    const double kC = 299792458.0;
+    const double lambda = kC / c.fc, Ts = 1.0 / c.fs;
+    int nT = 0;
+    steerHost.clear();
+    for (int i = 0; i < c.nTargets; ++i) {
+        if (c.los && c.los[i] != 1) continue;  // NLoS targets reflect nothing (basicRadarChannel.m:57-58)
+        if (nT >= kEchoMaxTargets) {
+            set_error(ctx, "echo: more LoS targets than kEchoMaxTargets");
+            return kErrCapacity;
+        }
+        const double delay = 2.0 * c.range[i] / kC;                    // :21
+        const long long sh = (long long)std::ceil(delay / Ts);         // :22
+        const double fd = 2.0 * c.velocity[i] / lambda;                // :25
+        double cyc = c.fc * Ts * (double)sh;                           // carrier phase of the delay, in cycles
+        cyc -= std::floor(cyc);
+        const double ang = -2.0 * M_PI * cyc;
+        d.shift[nT] = (int)sh;
+        d.beta[nT] = make_float2((float)(c.largeScaleFading[i] * std::cos(ang)), (float)(c.largeScaleFading[i] * std::sin(ang)));
+        d.fdTs[nT] = fd * Ts;
+        for (int a = 0; a < c.nTx; ++a)
+            steerHost.push_back(make_float2((float)c.steeringVec[2 * ((size_t)i * c.nTx + a)],
+                                            (float)c.steeringVec[2 * ((size_t)i * c.nTx + a) + 1]));
+        ++nT;
+    }
+    d.nTgt = nT;
+    if (nT == 0) {
+        set_error(ctx, "basicRadarChannel: no LoS target (the reference produces an empty waveform)");
+        return kErrNoLosTarget;
+    }
+    return kOk;
+}
+
+static int common_dev(Ctx* ctx, const EchoConfig& c, const float2* tx, const float2* noise, int noiseMode,
+                      unsigned long long seed, EchoDev& d, cudaStream_t st) {
+    if (!tx || c.T < 1 || c.nTx < 1 || c.nTargets < 0) {
+        set_error(ctx, "echo: invalid argument");
+        return kErrInvalidArg;
+    }
+    if (noiseMode == 1 && !noise) {
+        set_error(ctx, "echo: noise mode 1 needs the standard-normal tensor");
+        return kErrInvalidArg;
+    }
+    d = EchoDev{};
+    std::vector<float2> steerHost;
+    int s = fill_targets(ctx, c, d, steerHost);
+    if (s) return s;
+    void* dSteer = nullptr;
+    if ((s = ctx_scratch(ctx, 15, sizeof(float2) * steerHost.size(), &dSteer))) return s;
+    void* pin = nullptr;
+    if ((s = ctx_pinned(ctx, 7, sizeof(float2) * steerHost.size(), &pin))) return s;
+    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));  // the pinned staging buffer may still be in flight
+    std::memcpy(pin, steerHost.data(), sizeof(float2) * steerHost.size());
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(dSteer, pin, sizeof(float2) * steerHost.size(), cudaMemcpyHostToDevice, st));
+    d.tx = tx;
+    d.noise = noise;
+    d.steer = (const float2*)dSteer;
+    d.tw = ctx_twiddle(ctx);
+    d.T = c.T;
+    d.nTx = c.nTx;
+    d.nAnts = c.nTx;  // Rx and Tx share the array (radarParams.m:88,105)
+    d.noiseMode = noiseMode;
+    d.noiseSigma = (float)std::sqrt(c.N0 / 2.0);  // basicRadarChannel.m:67
+    d.seed = seed;
+    return kOk;
+}
+
+int radar_channel_run(Ctx* ctx, const EchoConfig& c, const float2* tx, const float2* noise, int noiseMode,
+                      unsigned long long seed, float2* rxWave, cudaStream_t st) {
+    EchoDev d;
+    int s = common_dev(ctx, c, tx, noise, noiseMode, seed, d, st);
+    if (s) return s;
+    const size_t smem = sizeof(float2) * (size_t)d.nAnts * d.nTgt;
+    radar_channel_kernel<<<(unsigned)((c.T + 255) / 256), 256, smem, st>>>(d, rxWave);
+    ISAC_CUDA_CHECK(ctx, cudaGetLastError());
+    return kOk;
+}
+
+template <int R1, int R2>
+static cudaError_t launch_echo(const EchoDev& d, cudaStream_t st) {
+    using G = FftGeom<R1, R2, true>;
+    const int groups = G::NT >= 256 ? 1 : 256 / G::NT;
+    const int threads = G::NT * groups;
+    const size_t smem = sizeof(float2) * ((size_t)groups * G::kElems + (size_t)d.nTgt * d.nSc + (size_t)d.nAnts * d.nTgt);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;  // too many LoS targets for one pass
+    auto k = echo_demod_kernel<R1, R2>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<d.nSymOut, threads, smem, st>>>(d);
+    return cudaGetLastError();
+}
+
+int mono_static_sensing_run(Ctx* ctx, const EchoConfig& c, const float2* tx, const float2* noise, int noiseMode,
+                            unsigned long long seed, float2* echoGrid, int* nSymRxOut, cudaStream_t st) {
+    if (c.nfft < 128 || c.nfft > 4096 || (c.nfft & (c.nfft - 1)) || c.nSc < 2 || c.nSc > c.nfft || c.symbolsPerSubframe < 1) {
+        set_error(ctx, "monoStaticSensing: unsupported numerology");
+        return kErrUnsupported;
+    }
+    // whole symbols contained in the waveform (nrOFDMDemodulate)
+    std::vector<int> start, cp;
+    long long acc = 0;
+    for (int s = 0;; ++s) {
+        const int len = c.cpLengths[s % c.symbolsPerSubframe] + c.nfft;
+        if (acc + len > c.T) break;
+        start.push_back((int)acc);
+        cp.push_back(c.cpLengths[s % c.symbolsPerSubframe]);
+        acc += len;
+    }
+    const int nSymRx = (int)start.size();
+    const int nSymOut = nSymRx > c.nSymTx ? nSymRx : c.nSymTx;  // pad up to txDimension(2) (:19-21)
+    if (nSymRxOut) *nSymRxOut = nSymOut;
+    if (!echoGrid) return kOk;  // size query
+    EchoDev d;
+    int s = common_dev(ctx, c, tx, noise, noiseMode, seed, d, st);
+    if (s) return s;
+    void *dStart = nullptr, *pin = nullptr;
+    if ((s = ctx_scratch(ctx, 14, sizeof(int) * 2 * (size_t)(nSymRx + 1), &dStart))) return s;
+    if ((s = ctx_pinned(ctx, 6, sizeof(int) * 2 * (size_t)(nSymRx + 1), &pin))) return s;
+    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    std::memcpy(pin, start.data(), sizeof(int) * nSymRx);
+    std::memcpy((int*)pin + nSymRx, cp.data(), sizeof(int) * nSymRx);
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(dStart, pin, sizeof(int) * 2 * (size_t)nSymRx, cudaMemcpyHostToDevice, st));
+    d.symStart = (const int*)dStart;
+    d.cpLen = (const int*)dStart + nSymRx;
+    d.nSymRx = nSymRx;
+    d.nSymOut = nSymOut;
+    d.nfft = c.nfft;
+    d.nSc = c.nSc;
+    d.out = echoGrid;
+    cudaError_t e;
+    switch (c.nfft) {
+        case 128: e = launch_echo<1, 8>(d, st); break;
+        case 256: e = launch_echo<1, 16>(d, st); break;
+        case 512: e = launch_echo<2, 16>(d, st); break;
+        case 1024: e = launch_echo<4, 16>(d, st); break;
+        case 2048: e = launch_echo<8, 16>(d, st); break;
+        default: e = launch_echo<16, 16>(d, st); break;
+    }
+    ISAC_CUDA_CHECK(ctx, e);
+    return kOk;
+}
+
+}  // namespace isac

@@ -1,0 +1,103 @@
+"""K1+K2 host mirror: basicRadarChannel / monoStaticSensing (csrc/echo.cu)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from ..workloads import ofdm_numerology
+
+
+class _EchoArgs:
+    """Keeps the host arrays referenced by an isac_echo_config alive for the duration of a call."""
+
+    def __init__(self, T, nTx, radarParams, los, carrierInfo=None, nSymTx=0):
+        nT = int(radarParams["nTargets"])
+        self.range = np.ascontiguousarray(radarParams["range"], dtype=np.float64).reshape(nT)
+        self.vel = np.ascontiguousarray(radarParams["velocity"], dtype=np.float64).reshape(nT)
+        self.lsf = np.ascontiguousarray(radarParams["largeScaleFading"], dtype=np.float64).reshape(nT)
+        self.steer = np.asfortranarray(np.asarray(radarParams["RxSteeringVec"], dtype=np.complex128).reshape(nTx, nT))
+        self.los = np.ascontiguousarray(los, dtype=np.int32).reshape(nT)
+        if carrierInfo is not None:
+            num = ofdm_numerology(int(carrierInfo["NRBsDL"]), float(carrierInfo["SubcarrierSpacing"]))
+            self.cp = np.ascontiguousarray(num["CyclicPrefixLengths"], dtype=np.int32)
+            nfft, nSc = int(num["Nfft"]), 12 * int(carrierInfo["NRBsDL"])
+        else:
+            self.cp = np.zeros(1, dtype=np.int32)
+            nfft, nSc = 0, 0
+        self.cfg = _lib.EchoConfig(
+            T=int(T), nTx=int(nTx), nTargets=nT, fc=float(radarParams["fc"]), fs=float(radarParams["fs"]),
+            N0=float(radarParams["N0"]), range=self.range.ctypes.data, velocity=self.vel.ctypes.data,
+            largeScaleFading=self.lsf.ctypes.data, steeringVec=self.steer.ctypes.data, los=self.los.ctypes.data,
+            nfft=nfft, nSc=nSc, nSymTx=int(nSymTx), symbolsPerSubframe=int(self.cp.size), cpLengths=self.cp.ctypes.data)
+
+
+def _noise_args(noise, seed):
+    if noise is None:
+        return None, (_lib.NOISE_PHILOX if seed is not None else _lib.NOISE_NONE), int(seed or 0)
+    return noise, _lib.NOISE_TENSOR, 0
+
+
+def _is_dev(a):
+    return hasattr(a, "is_cuda") and a.is_cuda
+
+
+def basicRadarChannel(txWaveform, radarParams, targetLoSConditions, noise=None, seed=None):
+    """``rxWaveform = sensing.channelModels.basicRadarChannel(txWaveform, radarParams, targetLoSConditions)``
+    (reference +sensing/+channelModels/basicRadarChannel.m:1).
+
+    ``noise``: the ``randn(size)+1j*randn(size)`` draw of :68 as an explicit [T x nTx] complex tensor
+    (MATLAB's generator cannot be reproduced); ``noise=None, seed=k`` draws it on the device (Philox);
+    ``noise=None, seed=None`` is noiseless.  torch CUDA tensors are laid out [nTx][T]."""
+    import torch
+    ctx = _lib.get_context(None)
+    if _is_dev(txWaveform):
+        tx_d = txWaveform
+        nTx, T = tx_d.shape
+        nz_d = noise
+    else:
+        tx = np.asarray(txWaveform)
+        T, nTx = tx.shape
+        tx_d = torch.from_numpy(np.ascontiguousarray(tx.astype(np.complex64).T)).cuda()
+        nz_d = None if noise is None else torch.from_numpy(np.ascontiguousarray(np.asarray(noise).astype(np.complex64).T)).cuda()
+    nz_d, mode, sd = _noise_args(nz_d, seed)
+    args = _EchoArgs(T, nTx, radarParams, targetLoSConditions)
+    out = torch.empty((nTx, T), dtype=torch.complex64, device=tx_d.device)
+    ctx.use_torch_stream()
+    _lib.check(ctx.lib.isac_radar_channel_dev(ctx.handle, C.byref(args.cfg), _lib.ptr(tx_d), _lib.ptr(nz_d), mode, sd,
+                                              _lib.ptr(out)), ctx.handle)
+    if _is_dev(txWaveform):
+        return out
+    return out.cpu().numpy().T.copy()
+
+
+def monoStaticSensing(txWaveform, txDimension, carrierInfo, radarParams, targetLoSConditions, noise=None, seed=None):
+    """``echoGrid = sensing.monoStaticSensing(txWaveform, txDimension, carrierInfo, radarParams, targetLoSConditions)``
+    (reference +sensing/monoStaticSensing.m:1): echo synthesis + nrOFDMDemodulate + zero padding, fused in
+    one kernel.  Returns [nSc x nSym x nAnts] complex64 (NumPy in, NumPy out; torch CUDA [nTx][T] in,
+    torch CUDA [nAnts][nSym][nSc] out).  See ``basicRadarChannel`` for ``noise`` / ``seed``."""
+    import torch
+    ctx = _lib.get_context(None)
+    dev_in = _is_dev(txWaveform)
+    if dev_in:
+        tx_d = txWaveform
+        nTx, T = tx_d.shape
+        nz_d = noise
+    else:
+        tx = np.asarray(txWaveform)
+        T, nTx = tx.shape
+        tx_d = torch.from_numpy(np.ascontiguousarray(tx.astype(np.complex64).T)).cuda()
+        nz_d = None if noise is None else torch.from_numpy(np.ascontiguousarray(np.asarray(noise).astype(np.complex64).T)).cuda()
+    nz_d, mode, sd = _noise_args(nz_d, seed)
+    args = _EchoArgs(T, nTx, radarParams, targetLoSConditions, carrierInfo, int(txDimension[1]))
+    nsym = C.c_int32()
+    ctx.use_torch_stream()
+    _lib.check(ctx.lib.isac_mono_static_sensing_dev(ctx.handle, C.byref(args.cfg), None, None, 0, 0, None,
+                                                    C.byref(nsym)), ctx.handle)
+    out = torch.empty((nTx, nsym.value, args.cfg.nSc), dtype=torch.complex64, device=tx_d.device)
+    _lib.check(ctx.lib.isac_mono_static_sensing_dev(ctx.handle, C.byref(args.cfg), _lib.ptr(tx_d), _lib.ptr(nz_d), mode, sd,
+                                                    _lib.ptr(out), C.byref(nsym)), ctx.handle)
+    if dev_in:
+        return out
+    return out.cpu().numpy().transpose(2, 1, 0).copy()

@@ -94,6 +94,102 @@ int isac_rdm_cfar_host(isac_rdm_plan* plan, const void* rxGridHost, const void* 
                        int32_t batch, int32_t maxDet, int32_t* detCount, int32_t* detRowCol,
                        float* peaks, float* rdPowerHost);
 
+/* ---- K5+K6: MUSIC DoA / fft2D estimator / music2D --------------------------------------------- */
+typedef struct {
+    int32_t isUpa;          /* isa(array,'parameters.baseStation.antenna.upa')   music.m:31 */
+    int32_t nAnts;          /* ULA: array.numElements                             music.m:76 */
+    int32_t nX, nY;         /* UPA: array.nV, array.nH                            music.m:34-35 */
+    double d;               /* element spacing / lambda = 0.5                     music.m:12 */
+    double aGran, aMax;     /* azimuthScanGranularity / azimuthScanScale          radarParams.m:120,122 */
+    double eGran, eMax;     /* elevationScanGranularity / elevationScanScale      radarParams.m:121,123 */
+} isac_doa_config;
+
+#define ISAC_MAX_PEAKS 64   /* capacity of findpeaks(...,'NPeaks',L) outputs */
+
+/* [L, aziEst, eleEst] = sensing.estimation.doaEstimation.music(numDets, radarEstParams, Ra)
+ * (+sensing/+estimation/+doaEstimation/music.m:1).  Ra: host complex128 [n x n] column-major.
+ * numDets < 0 means [] (eigen-gap rule, music.m:109-125).  ULA: aziEst[<=ISAC_MAX_PEAKS] degrees,
+ * PmusicdB[aSteps].  UPA: the reference's peak picker does not exist (tools.find2DPeaks), so only
+ * PmusicdB[eSteps x aSteps] (column-major) is returned and *nAzi = 0.  Pmusic may be NULL. */
+int isac_music_doa_host(isac_ctx* ctx, const isac_doa_config* doa, const double* Ra, int32_t numDets,
+                        int32_t* L, double* aziEst, int32_t* nAzi, double* PmusicdB, double* Pmusic);
+
+typedef struct isac_sense_plan isac_sense_plan;
+/* estResults = sensing.estimation.fft2D(radarEstParams, cfar, rxGrid, txGrid)
+ * (+sensing/+estimation/fft2D.m:1): RDM + CFAR (above) + Ra (fft2D.m:106-107) + MUSIC (fft2D.m:111). */
+int isac_sense_plan_create(isac_ctx* ctx, const isac_rdm_config* rdm, const isac_doa_config* doa,
+                           double rRes, double vRes, isac_sense_plan** plan);
+int isac_sense_plan_destroy(isac_sense_plan* plan);
+/* the embedded RDM plan (for isac_rdm_get_detections / isac_rdm_get_power); owned by the sense plan */
+isac_rdm_plan* isac_sense_plan_rdm(isac_sense_plan* plan);
+/* enqueue the chain on device grids [nSc x nSym x nAnts x batch]; no host sync for ULA arrays */
+int isac_fft2d_dev(isac_sense_plan* plan, const void* rxGrid, const void* txGrid, int32_t batch, float* rdPower);
+/* fetch estResults of the last run: for map-set b, rngEst[b*maxOut + i], i < nRng[b] (unique,'stable'
+ * of the per-antenna peak-sorted lists, fft2D.m:89-102); velEst likewise; aziEst[b*ISAC_MAX_PEAKS+i];
+ * status[b] = ISAC_ERR_NUM_DETS_ZERO when nothing was detected (reference: error -> senResults = NaN). */
+int isac_fft2d_collect(isac_sense_plan* plan, int32_t batch, int32_t maxOut, double* rngEst, int32_t* nRng,
+                       double* velEst, int32_t* nVel, double* aziEst, int32_t* nAzi, int32_t* L,
+                       int32_t* status);
+/* copy the DoA pseudo-spectrum (dB) of the last run: [specLen x batch], specLen = aSteps (ULA) or eSteps*aSteps */
+int isac_fft2d_get_spectrum(isac_sense_plan* plan, int32_t batch, double* PmusicdB);
+/* host-buffer convenience: H2D, isac_fft2d_dev, isac_fft2d_collect */
+int isac_fft2d_host(isac_sense_plan* plan, const void* rxGridHost, const void* txGridHost, int32_t batch,
+                    int32_t maxOut, double* rngEst, int32_t* nRng, double* velEst, int32_t* nVel,
+                    double* aziEst, int32_t* nAzi, int32_t* L, int32_t* status);
+
+typedef struct {
+    int32_t nSc, nSym, nAnts;   /* size(rxGrid)                               music2D.m:34 */
+    double scsHz;               /* bsParams.scs*1e3                           music2D.m:35 */
+    double fc, Tsri;            /* rdrEstParams.fc, .Tsri                     music2D.m:37,39 */
+    double rMax, vZone;         /* cfarEstZone(1,2), cfarEstZone(2,2)         music2D.m:42-43 */
+    isac_doa_config doa;
+    int32_t numDetsOverride;    /* <= 0: reference behaviour (L from the eigen-gap rule on Ra) */
+} isac_music2d_config;
+/* estResults = sensing.estimation.music2D(rdrEstParams, bsParams, rxGrid, txGrid) (music2D.m:1).
+ * rx/tx: device complex64 [nSc x nSym x nAnts].  Outputs (host): L, aziEst/rngEst/velEst
+ * [<=ISAC_MAX_PEAKS each], PrmusicdB[rSteps], PvmusicdB[vSteps] (may be NULL). */
+int isac_music2d_dev(isac_ctx* ctx, const isac_music2d_config* cfg, const void* rxGrid, const void* txGrid,
+                     int32_t* L, double* aziEst, int32_t* nAzi, double* rngEst, int32_t* nRng, double* velEst,
+                     int32_t* nVel, double* PrmusicdB, double* PvmusicdB, int32_t* sweeps);
+/* antenna covariance Ra (fft2D.m:106-107) of a device grid -> host complex128 [nAnts x nAnts] */
+int isac_antenna_covariance_dev(isac_ctx* ctx, const void* rxGrid, int64_t nScSym, int32_t nAnts, double* RaHost);
+
+/* ---- K1+K2: mono-static echo synthesis + OFDM demodulation --------------------------------------
+ * rxWaveform = sensing.channelModels.basicRadarChannel(txWaveform, radarParams, targetLoSConditions)
+ *   (+sensing/+channelModels/basicRadarChannel.m:1) and
+ * echoGrid = sensing.monoStaticSensing(txWaveform, txDimension, carrierInfo, radarParams, targetLoSConditions)
+ *   (+sensing/monoStaticSensing.m:1; nrOFDMDemodulate at :16, zero padding at :19-21). */
+typedef struct {
+    int64_t T;                      /* size(txWaveform,1)                         basicRadarChannel.m:9 */
+    int32_t nTx;                    /* size(txWaveform,2); Rx array == Tx array   radarParams.m:88,105 */
+    int32_t nTargets;               /* radarParams.nTargets                       basicRadarChannel.m:18 */
+    double fc, fs, N0;              /* radarParams.fc / .fs / .N0                 :13,:15,:67 */
+    const double* range;            /* [nTargets] radarParams.range               :21 */
+    const double* velocity;         /* [nTargets] radarParams.velocity            :25 */
+    const double* largeScaleFading; /* [nTargets]                                 :34 */
+    const double* steeringVec;      /* complex128 [nTx x nTargets] RxSteeringVec  :35 */
+    const int32_t* los;             /* [nTargets] targetLoSConditions (NULL = all 1) :40 */
+    int32_t nfft, nSc;              /* nrOFDMInfo.Nfft, 12*NRBsDL                 monoStaticSensing.m:9-11 */
+    int32_t nSymTx;                 /* txDimension(2)                             monoStaticSensing.m:19 */
+    int32_t symbolsPerSubframe;     /* length of cpLengths */
+    const int32_t* cpLengths;       /* nrOFDMInfo.CyclicPrefixLengths of one subframe */
+} isac_echo_config;
+
+enum { ISAC_NOISE_NONE = 0,    /* noiseless */
+       ISAC_NOISE_TENSOR = 1,  /* noise = randn+1j*randn supplied by the caller, complex64 [T x nTx] (:68) */
+       ISAC_NOISE_PHILOX = 2   /* generated on the device from `seed` (statistically equivalent) */ };
+
+int isac_radar_channel_dev(isac_ctx* ctx, const isac_echo_config* cfg, const void* txWaveform, const void* noise,
+                           int32_t noiseMode, uint64_t seed, void* rxWaveform);
+/* echoGrid: device complex64 [nSc x nSymOut x nTx]; *nSymOut = max(whole symbols in T, nSymTx).
+ * Call with echoGrid == NULL to query nSymOut. */
+int isac_mono_static_sensing_dev(isac_ctx* ctx, const isac_echo_config* cfg, const void* txWaveform,
+                                 const void* noise, int32_t noiseMode, uint64_t seed, void* echoGrid,
+                                 int32_t* nSymOut);
+int isac_mono_static_sensing_host(isac_ctx* ctx, const isac_echo_config* cfg, const void* txWaveformHost,
+                                  const void* noiseHost, int32_t noiseMode, uint64_t seed, void* echoGridHost,
+                                  int32_t* nSymOut);
+
 #ifdef __cplusplus
 }
 #endif
