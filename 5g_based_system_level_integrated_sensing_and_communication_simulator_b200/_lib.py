@@ -84,6 +84,8 @@ def _declare(lib):
         "isac_set_stream": ([vp, vp], C.c_int),
         "isac_use_own_stream": ([vp], C.c_int),
         "isac_synchronize": ([vp], C.c_int),
+        "isac_profile_enable": ([vp, i32], C.c_int),
+        "isac_profile_collect": ([vp, vp, vp, vp], C.c_int),
         "isac_version": ([], C.c_char_p),
         "isac_rdm_plan_create": ([vp, P(RdmConfig), P(vp)], C.c_int),
         "isac_rdm_plan_destroy": ([vp], C.c_int),
@@ -171,6 +173,21 @@ class Context:
 
     def synchronize(self):
         check(self.lib.isac_synchronize(self.handle), self.handle)
+
+    PROF_SLOTS = ("rdm_range", "rdm_doppler", "cfar", "echo_demod", "covariance", "music", "pmi_sinr", "cdl",
+                  "prg_precode", "ul_tpmi")
+
+    def profile_enable(self, on=True):
+        check(self.lib.isac_profile_enable(self.handle, 1 if on else 0), self.handle)
+
+    def profile_collect(self):
+        """-> ({slot: (total_ms, count)}, launches) since the last collect; synchronises the stream."""
+        ms = np.zeros(16)
+        cnt = np.zeros(16, dtype=np.int32)
+        n = C.c_int64()
+        check(self.lib.isac_profile_collect(self.handle, ptr(ms), ptr(cnt), C.byref(n)), self.handle)
+        out = {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.PROF_SLOTS) if cnt[i]}
+        return out, int(n.value)
 
     def close(self):
         if self.handle:

@@ -17,6 +17,28 @@ void set_error(Ctx* ctx, const std::string& msg) {
 }
 const float2* ctx_twiddle(Ctx* ctx) { return ctx->d_twiddle; }
 
+static cudaEvent_t take_event(Ctx* ctx) {
+    if (!ctx->eventPool.empty()) {
+        cudaEvent_t e = ctx->eventPool.back();
+        ctx->eventPool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+int prof_begin(Ctx* ctx, int slot, cudaStream_t st) {
+    if (!ctx->profiling) return -1;
+    Ctx::ProfRec r{slot, take_event(ctx), take_event(ctx)};
+    cudaEventRecord(r.a, st);
+    ctx->prof.push_back(r);
+    return (int)ctx->prof.size() - 1;
+}
+void prof_end(Ctx* ctx, int rec, cudaStream_t st) {
+    if (rec >= 0 && rec < (int)ctx->prof.size()) cudaEventRecord(ctx->prof[rec].b, st);
+}
+void count_launches(Ctx* ctx, int n) { ctx->launches += n; }
+
 int ctx_pinned(Ctx* ctx, int slot, size_t bytes, void** out) {
     if (slot < 0 || slot >= Ctx::kPinnedSlots) return kErrInvalidArg;
     if (ctx->pinnedBytes[slot] < bytes) {
@@ -161,6 +183,36 @@ int isac_set_stream(isac_ctx* h, void* s) {
 int isac_use_own_stream(isac_ctx* h) {
     if (!h) return ISAC_ERR_INVALID_ARG;
     h->c.stream = h->c.ownStream;
+    return ISAC_OK;
+}
+
+int isac_profile_enable(isac_ctx* h, int32_t on) {
+    if (!h) return ISAC_ERR_INVALID_ARG;
+    h->c.profiling = on != 0;
+    return ISAC_OK;
+}
+
+int isac_profile_collect(isac_ctx* h, double* msPerSlot, int32_t* countPerSlot, int64_t* launches) {
+    if (!h) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    ISAC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < kProfSlots; ++i) {
+        if (msPerSlot) msPerSlot[i] = 0.0;
+        if (countPerSlot) countPerSlot[i] = 0;
+    }
+    for (auto& r : c->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.slot >= 0 && r.slot < kProfSlots) {
+            if (msPerSlot) msPerSlot[r.slot] += (double)ms;
+            if (countPerSlot) countPerSlot[r.slot] += 1;
+        }
+        c->eventPool.push_back(r.a);
+        c->eventPool.push_back(r.b);
+    }
+    c->prof.clear();
+    if (launches) *launches = c->launches;
+    c->launches = 0;
     return ISAC_OK;
 }
 

@@ -1,6 +1,7 @@
 // Library context: device, stream, error string, twiddle table, reusable staging buffers.
 #pragma once
 #include "isac_common.cuh"
+#include <vector>
 
 namespace isac {
 
@@ -18,6 +19,11 @@ struct Ctx {
     size_t pinnedBytes[kPinnedSlots] = {};
     void* scratch[kScratchSlots] = {};
     size_t scratchBytes[kScratchSlots] = {};
+    struct ProfRec { int slot; cudaEvent_t a, b; };
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> eventPool;
+    long long launches = 0;
 };
 
 // grow-only pinned host / device scratch buffers owned by the context

@@ -36,6 +36,7 @@ struct EchoDev {
     int noiseMode;         // 0 none, 1 explicit time-domain tensor, 2 generated (frequency domain)
     float noiseSigma;      // sqrt(N0/2)
     unsigned long long seed;
+    double fcTsFrac;       // frac(fc*Ts): the receiver down-conversion also rotates the noise (:68-74)
     int shift[kEchoMaxTargets];
     float2 beta[kEchoMaxTargets];
     double fdTs[kEchoMaxTargets];
@@ -61,6 +62,14 @@ __device__ __forceinline__ float2 gauss_pair(unsigned a, unsigned b) {
     float s, c;
     sincospif(2.0f * u2, &s, &c);
     return make_float2(r * c, r * s);
+}
+
+// noise sample after the receive mixer: z[n] * exp(-2 pi j fc Ts n)   (basicRadarChannel.m:69,73-74)
+__device__ __forceinline__ float2 mixed_noise(const EchoDev& p, const float2* __restrict__ z, long long n) {
+    const double c = p.fcTsFrac * (double)n;
+    float sn, cs;
+    sincospif(-2.0f * (float)(c - floor(c)), &sn, &cs);
+    return cmul(__ldg(z + n), make_float2(cs, sn));
 }
 
 // stream sample w_i[n] (see file header)
@@ -145,7 +154,7 @@ echo_demod_kernel(const EchoDev p) {
             auto load = [&](int n) -> float2 {
                 const long long nn = n0 + n;
                 if (!act || nn >= p.T) return make_float2(0.f, 0.f);
-                return __ldg(z + nn);
+                return mixed_noise(p, z, nn);
             };
             block_fft<R1, R2, -1, true>(v, fftbuf, 1, tf, p.tw, load);
         }
@@ -206,7 +215,7 @@ radar_channel_kernel(const EchoDev p, float2* __restrict__ rxWave) {
             acc.y += w[i].x * ar.y + w[i].y * ar.x;
         }
         if (p.noiseMode == 1) {
-            const float2 z = __ldg(p.noise + (long long)r * p.T + n);
+            const float2 z = mixed_noise(p, p.noise + (long long)r * p.T, n);
             acc.x += p.noiseSigma * z.x;
             acc.y += p.noiseSigma * z.y;
         } else if (p.noiseMode == 2) {
@@ -287,6 +296,8 @@ static int common_dev(Ctx* ctx, const EchoConfig& c, const float2* tx, const flo
     d.noiseMode = noiseMode;
     d.noiseSigma = (float)std::sqrt(c.N0 / 2.0);  // basicRadarChannel.m:67
     d.seed = seed;
+    const double ft = c.fc / c.fs;
+    d.fcTsFrac = ft - std::floor(ft);
     return kOk;
 }
 
@@ -297,6 +308,7 @@ int radar_channel_run(Ctx* ctx, const EchoConfig& c, const float2* tx, const flo
     if (s) return s;
     const size_t smem = sizeof(float2) * (size_t)d.nAnts * d.nTgt;
     radar_channel_kernel<<<(unsigned)((c.T + 255) / 256), 256, smem, st>>>(d, rxWave);
+    count_launches(ctx, 1);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     return kOk;
 }
@@ -352,6 +364,7 @@ int mono_static_sensing_run(Ctx* ctx, const EchoConfig& c, const float2* tx, con
     d.nSc = c.nSc;
     d.out = echoGrid;
     cudaError_t e;
+    const int pr = prof_begin(ctx, kProfEcho, st);
     switch (c.nfft) {
         case 128: e = launch_echo<1, 8>(d, st); break;
         case 256: e = launch_echo<1, 16>(d, st); break;
@@ -360,6 +373,8 @@ int mono_static_sensing_run(Ctx* ctx, const EchoConfig& c, const float2* tx, con
         case 2048: e = launch_echo<8, 16>(d, st); break;
         default: e = launch_echo<16, 16>(d, st); break;
     }
+    prof_end(ctx, pr, st);
+    count_launches(ctx, 1);
     ISAC_CUDA_CHECK(ctx, e);
     return kOk;
 }

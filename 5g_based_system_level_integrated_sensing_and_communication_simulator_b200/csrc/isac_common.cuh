@@ -54,6 +54,16 @@ struct Ctx;  // defined in capi.cu
 void set_error(Ctx* ctx, const std::string& msg);
 const float2* ctx_twiddle(Ctx* ctx);  // device pointer to exp(+2*pi*i*m/4096), m < 4096
 
+// Optional CUDA-event profiling of kernel groups on the launching stream (used by bench.py for the
+// live roofline figure) and a counter of this library's kernel launches.
+enum ProfSlot : int {
+    kProfRdmRange = 0, kProfRdmDoppler = 1, kProfCfar = 2, kProfEcho = 3, kProfCov = 4, kProfMusic = 5,
+    kProfPmi = 6, kProfCdl = 7, kProfPrecode = 8, kProfUlPmi = 9, kProfSlots = 16
+};
+int prof_begin(Ctx* ctx, int slot, cudaStream_t st);  // returns a record index (or -1 when disabled)
+void prof_end(Ctx* ctx, int rec, cudaStream_t st);
+void count_launches(Ctx* ctx, int n);
+
 #define ISAC_CUDA_CHECK(ctx, expr)                                                          \
     do {                                                                                    \
         cudaError_t _e = (expr);                                                            \

@@ -142,10 +142,13 @@ int cov_antenna(Ctx* ctx, const float2* rx, long long N, int nAnts, int batch, d
     int s = ctx_scratch(ctx, 8, sizeof(double2) * (size_t)batch * nPairs * chunks * kCovBI * kCovBJ, &part);
     if (s) return s;
     dim3 grid(chunks, nPairs, batch);
+    const int pr = prof_begin(ctx, kProfCov, st);
     cov_partial_kernel<<<grid, kCovThreads, 0, st>>>(rx, N, nAnts, jBlocks, chunks, (double2*)part);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     dim3 g2((nAnts * nAnts + 255) / 256, batch);
     cov_final_kernel<<<g2, 256, 0, st>>>((const double2*)part, nAnts, jBlocks, nPairs, chunks, 1.0 / (double)N, Ra);
+    prof_end(ctx, pr, st);
+    count_launches(ctx, 2);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     return kOk;
 }
@@ -279,7 +282,10 @@ int eig_psd_small(Ctx* ctx, const double2* A, int n, int batch, double* w, doubl
     if (threads > 1024) threads = 1024;
     const size_t smem = sizeof(double2) * 2 * (size_t)n * n;
     cudaFuncSetAttribute(eig_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int pr = prof_begin(ctx, kProfMusic, st);
     eig_small_kernel<<<batch, threads, smem, st>>>(A, n, w, V, 40);
+    prof_end(ctx, pr, st);
+    count_launches(ctx, 1);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     return kOk;
 }
@@ -625,7 +631,10 @@ int music_doa_ula(Ctx* ctx, const double* w, const double2* V, int n, int batch,
     const int aSteps = (int)std::floor((cfg.aMax + 1.0) / cfg.aGran);  // music.m:79
     const size_t smem = sizeof(double2) * (size_t)n * n + sizeof(double) * aSteps + aSteps + 16;
     cudaFuncSetAttribute(music_ula_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int pr = prof_begin(ctx, kProfMusic, st);
     music_ula_kernel<<<batch, 512, smem, st>>>(w, V, n, cfg, ls, aSteps, Lout, P, PdB, peakLoc, nPeaks, status);
+    prof_end(ctx, pr, st);
+    count_launches(ctx, 1);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     return kOk;
 }

@@ -375,9 +375,12 @@ int rdm_cfar_only(RdmPlan* p, const float* pow, int batch, cudaStream_t st) {
     CfarDev d = make_cfar_dev(p, pow, batch);
     ISAC_CUDA_CHECK(ctx, cudaMemsetAsync(p->d_rowmask, 0, sizeof(uint32_t) * (size_t)p->rowWords * batch, st));
     const long long blocks = (d.total + 255) / 256;
+    const int pr = prof_begin(ctx, kProfCfar, st);
     cfar2d_flags_kernel<<<(unsigned)blocks, 256, 0, st>>>(d);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     cfar2d_compact_kernel<<<(unsigned)(p->cfg.nAnts * batch), 1024, 0, st>>>(d, p->d_det, p->d_peak, p->d_detCount);
+    prof_end(ctx, pr, st);
+    count_launches(ctx, 2);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     p->lastPow = pow;
     p->lastBatch = batch;
@@ -412,6 +415,7 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
     d.M = p->M;
     d.totalCols = (long long)p->M * c.nAnts * batch;
     cudaError_t e = cudaSuccess;
+    int pr = prof_begin(ctx, kProfRdmRange, st);
     switch (c.nIFFT) {
         case 256: e = launch_range<1, 16>(d, st); break;
         case 512: e = launch_range<2, 16>(d, st); break;
@@ -420,8 +424,10 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
         case 4096: e = launch_range<16, 16>(d, st); break;
         default: set_error(ctx, "rdm: unsupported nIFFT"); return kErrUnsupported;
     }
+    prof_end(ctx, pr, st);
     ISAC_CUDA_CHECK(ctx, e);
     const long long pages = (long long)c.nAnts * batch;
+    pr = prof_begin(ctx, kProfRdmDoppler, st);
     switch (c.nFFT) {
         case 16: e = launch_doppler<1, 1>(d, pages, st); break;
         case 32: e = launch_doppler<1, 2>(d, pages, st); break;
@@ -434,7 +440,9 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
         case 4096: e = launch_doppler<16, 16>(d, pages, st); break;
         default: set_error(ctx, "rdm: unsupported nFFT"); return kErrUnsupported;
     }
+    prof_end(ctx, pr, st);
     ISAC_CUDA_CHECK(ctx, e);
+    count_launches(ctx, 2);
     return rdm_cfar_only(p, pow, batch, st);
 }
 

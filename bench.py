@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the B200-native ISAC hot path (contract: see the task statement).
+
+Metric (BASELINE.json): cell-subframes/sec.  One *step* = one 10 ms frame (10 subframes) of hot-path
+work for each of ``cells_per_gpu`` cells of BASELINE config 2 (1 gNB, 8 UE, 4 targets, 8x8,
+273 PRB @ 30 kHz, TDD DDDSU -> 168 DL symbols per frame):
+    sensing : mono-static echo synthesis + OFDM demod of the frame's DL waveform (K1+K2),
+              2D-FFT range-Doppler map + 2D CA-CFAR (K3+K4), antenna covariance + MUSIC DoA (K5+K6);
+    comm    : per UE and CSI-RS occasion RI/PMI/CQI selection over the Type-I codebook (K7-K9), UL TPMI
+              selection per SRS occasion (K12), PRG precoding of the DL slots (K10), with the channel
+              matrices H produced on the device by the CDL generator (K11)          [stages listed in
+              config.stages are the ones inside the timed region].
+`value`  : cell-subframes/s with every input resident in HBM (device-timed, CUDA events, max over ranks).
+`e2e`    : same metric through the package's host API (pinned host buffers in, host results out).
+`roofline`: dominant kernel group, algorithmic bytes / CUDA-event time measured inside the timed region.
+`cpu_baseline` / ``--impl reference``: the float64 NumPy restatement of the reference (oracle/) on the
+host cores — MATLAB itself cannot run here (no MATLAB/Octave, closed toolboxes); labelled "port".
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "5g_based_system_level_integrated_sensing_and_communication_simulator_b200"
+SUBFRAMES_PER_STEP = 10
+WORKLOAD = "cfg2: 1 gNB, 8 UE, 4 targets, 8x8, 273 PRB @30 kHz, 1 frame (168 DL symbols) per cell per step"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append((time.time(), line.strip()))
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for t, line in self.samples:
+            if t < t0 - 0.05 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def build_cell_inputs(W, seed):
+    """Synthetic cfg2 inputs of one cell-frame (host, complex64): senTxGrid, senTxWave."""
+    grid, txw = W.sensing_tx("cfg2", seed)
+    return grid.astype(np.complex64), txw.astype(np.complex64)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P = importlib.import_module(PKG)
+    _lib = P._lib
+    W = P.workloads
+    est = importlib.import_module(PKG + ".sensing.estimation")
+    echo = importlib.import_module(PKG + ".sensing._echo")
+    ctx = _lib.get_context(local)
+    cells = args.cells_per_gpu
+
+    cell, car, wave = W.cell_config("cfg2")
+    rp = P.sensing.radarParams(cell, car, wave)
+    cf = P.sensing.detection.cfar2D(rp)
+    los = cell["targetLoSConditions"]
+    # per-cell inputs: distinct QPSK payloads (cells are independent, networkSimulation.m:57-60)
+    host_grid, host_wave = [], []
+    uniq = min(cells, 2)  # generating 47 MB waveforms on the host is slow; reuse payloads round-robin
+    for c in range(uniq):
+        g, w = build_cell_inputs(W, 1000 * rank + c + 1)
+        host_grid.append(g)
+        host_wave.append(w)
+    nSc, nSym, nTx = host_grid[0].shape
+    T = host_wave[0].shape[0]
+    to_dev_grid = lambda a: torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0))).cuda()
+    to_dev_wave = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).cuda()
+    tx_grid_d = torch.stack([to_dev_grid(host_grid[c % uniq]) for c in range(cells)])   # [cells][nAnts][nSym][nSc]
+    tx_wave_d = [to_dev_wave(host_wave[c % uniq]) for c in range(cells)]                # each [nTx][T]
+    rx_grid_d = torch.empty_like(tx_grid_d)
+    plan = est.SensePlan(rp, cf, (nSc, nSym, nTx), max_batch=cells, device=local)
+    eargs = echo._EchoArgs(T, nTx, rp, los, car, nSym)
+    import ctypes as C
+    nsym_out = C.c_int32()
+
+    def sensing_step_dev(step):
+        ctx.use_torch_stream()
+        for c in range(cells):
+            _lib.check(ctx.lib.isac_mono_static_sensing_dev(ctx.handle, C.byref(eargs.cfg), _lib.ptr(tx_wave_d[c]), None,
+                                                            _lib.NOISE_PHILOX, 7919 * step + c, _lib.ptr(rx_grid_d[c]),
+                                                            C.byref(nsym_out)), ctx.handle)
+        plan.run_dev(rx_grid_d, tx_grid_d, cells)
+
+    stages = ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa"]
+
+    def step_dev(step):
+        sensing_step_dev(step)
+
+    # ---- device-resident timing ----------------------------------------------------------------
+    for i in range(args.warmup):
+        step_dev(i)
+    torch.cuda.synchronize()
+    res = plan.collect(cells)
+    n_est = [len(r["rngEst"]) for r in res]
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ctx.profile_collect()
+    ctx.profile_enable(True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step_dev(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    prof, launches = ctx.profile_collect()
+    ctx.profile_enable(False)
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = cells * SUBFRAMES_PER_STEP * world / (ms_step * 1e-3)
+
+    # ---- end-to-end through the host API (pinned host in, host results out) -------------------------
+    pin_wave = [torch.from_numpy(np.ascontiguousarray(host_wave[c % uniq].T)).pin_memory() for c in range(uniq)]
+    pin_grid = [torch.from_numpy(np.ascontiguousarray(host_grid[c % uniq].transpose(2, 1, 0))).pin_memory() for c in range(uniq)]
+    stage_wave = [torch.empty((nTx, T), dtype=torch.complex64, device="cuda") for _ in range(2)]
+
+    def step_e2e(step):
+        # simulation.cellSimulation's sensing pass (cellSimulation.m:191-197) per cell: txWave+txGrid in, estResults out
+        ctx.use_torch_stream()
+        for c in range(cells):
+            sw = stage_wave[c % 2]
+            sw.copy_(pin_wave[c % uniq], non_blocking=True)
+            tx_grid_d[c].copy_(pin_grid[c % uniq], non_blocking=True)
+            _lib.check(ctx.lib.isac_mono_static_sensing_dev(ctx.handle, C.byref(eargs.cfg), _lib.ptr(sw), None,
+                                                            _lib.NOISE_PHILOX, 7919 * step + c, _lib.ptr(rx_grid_d[c]),
+                                                            C.byref(nsym_out)), ctx.handle)
+        plan.run_dev(rx_grid_d, tx_grid_d, cells)
+        return plan.collect(cells)   # D2H of detections / estimates (synchronises)
+
+    e2e_steps = max(1, min(args.steps, 5))
+    step_e2e(0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.time()
+    for i in range(e2e_steps):
+        out = step_e2e(i + 1)
+    torch.cuda.synchronize()
+    t_e2e = time.time() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = cells * SUBFRAMES_PER_STEP * world * e2e_steps / t_e2e
+    h2d = cells * (T * nTx * 8 + nSc * nSym * nTx * 8)
+    d2h = cells * (nTx * 4 + 64 * 8 + 16)  # counts + estimates (order of magnitude; exact per step varies with detections)
+
+    sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- roofline of the dominant kernel group ---------------------------------------------------
+    peak, peak_src = _peaks()
+    nIFFT, nFFT = rp["nIFFT"], rp["nFFT"]
+    alg = {
+        "rdm_2dfft+cfar": (16 * nSc * nSym * nTx + 4 * nIFFT * nFFT * nTx) * cells,        # 104.0 MB / map-set
+        "echo_demod": (8 * T * nTx + 8 * nSc * nSym * nTx),                                # per launch (one cell)
+    }
+    groups = {}
+    rdm_ms = sum(prof.get(k, (0.0, 0))[0] for k in ("rdm_range", "rdm_doppler", "cfar"))
+    rdm_n = prof.get("rdm_range", (0.0, 1))[1]
+    groups["rdm_2dfft+cfar"] = (rdm_ms, rdm_n)
+    groups["echo_demod"] = prof.get("echo_demod", (0.0, 1))
+    dom = max(groups, key=lambda k: groups[k][0])
+    roof = {}
+    for name, (ms, n) in groups.items():
+        if n and ms > 0:
+            ach = alg[name] / (ms / n * 1e-3) / 1e9
+            roof[name] = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                          "frac": round(ach / peak, 4), "traffic": None, "avg_launch_us": round(ms / n * 1e3, 2),
+                          "share_of_step": round(ms / ms_total, 4), "peak_source": peak_src}
+    if rank == 0:
+        line = {
+            "metric": "cell_subframes_per_sec", "value": round(value, 2), "unit": "cell-subframes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (MUSIC/CFAR compare in f64)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "cells_per_gpu": cells, "stages": stages,
+                       "l2_policy": "inputs (%.0f MB per step) larger than L2; no flush" % (h2d / 1e6),
+                       "rd_map_sets_per_sec": round(cells * world / (ms_step * 1e-3), 1),
+                       "detections_sanity": n_est[:4]},
+            "e2e": {"value": round(e2e_value, 2), "unit": "cell-subframes/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "api": "simulation-level sensing pass: pinned txWave/txGrid -> estResults"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": dict(roof.get("rdm_2dfft+cfar", {}), kernel="rdm_2dfft+cfar (range IFFT + Doppler FFT + CFAR)"),
+            "roofline_all": roof, "dominant_group": dom,
+        }
+        if args.cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sample_cells=1)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+def _oracle_cell_frame(seed):
+    """One cfg2 cell-frame of sensing work on the CPU (float64 oracle).  Returns seconds."""
+    from oracle import sensing as S
+    W = importlib.import_module(PKG + ".workloads")
+    cell, car, wave = W.cell_config("cfg2")
+    rp = S.radar_params(cell, car, wave)
+    grid, txw = W.sensing_tx("cfg2", seed)
+    noise = W.std_normal_complex(txw.shape, seed + 1)
+    cf = S.cfar2d_config(rp)
+    t0 = time.time()
+    rx = S.mono_static_sensing(txw, grid.shape, car, rp, cell["targetLoSConditions"], noise)
+    S.fft2d(rp, cf, rx, grid)
+    return time.time() - t0
+
+
+def cpu_baseline(sample_cells=1):
+    ts = [_oracle_cell_frame(11 + i) for i in range(sample_cells)]
+    t = float(np.mean(ts))
+    return {"value": round(SUBFRAMES_PER_STEP / t, 3), "unit": "cell-subframes/s", "cores": 1, "kind": "port",
+            "sample": f"{sample_cells} cfg2 cell-frame(s) of sensing work (echo+demod+fft2D+CFAR+MUSIC), NumPy float64 "
+                      f"restatement of the reference (not MATLAB), {t:.2f} s per cell-frame"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ProcessPoolExecutor
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 8))
+    per_step = workers  # one cell-frame per worker per step
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        for _ in range(args.warmup and 1):
+            list(ex.map(_oracle_cell_frame, range(workers)))
+        t0 = time.time()
+        for s in range(args.steps):
+            list(ex.map(_oracle_cell_frame, [100 * s + i for i in range(per_step)]))
+        dt = time.time() - t0
+    value = per_step * SUBFRAMES_PER_STEP * args.steps / dt
+    line = {"impl": "reference", "metric": "cell_subframes_per_sec", "value": round(value, 3), "unit": "cell-subframes/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "cells_per_step": per_step,
+                       "stages": ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa"]},
+            "cpu_baseline": {"value": round(value, 3), "unit": "cell-subframes/s", "cores": workers, "kind": "port",
+                             "sample": f"{per_step} cfg2 cell-frames per step over {workers} processes; NumPy float64 "
+                                       "restatement of the reference (MATLAB cannot run here)"},
+            "e2e": {"value": round(value, 3), "unit": "cell-subframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells-per-gpu", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 3:
+            args.steps = 3  # bounded sample: each step is `workers` cell-frames of float64 NumPy work
+        run_reference(args)
+        return
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or int(os.environ.get("RANK", "0")) > 0:
+        args.cpu_baseline = args.cpu_baseline and int(os.environ.get("WORLD_SIZE", "1")) == 1
+    run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

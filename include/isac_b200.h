@@ -50,6 +50,12 @@ int isac_set_stream(isac_ctx* ctx, void* cuda_stream);
 /* Go back to the context's private non-blocking stream (the default after isac_create). */
 int isac_use_own_stream(isac_ctx* ctx);
 int isac_synchronize(isac_ctx* ctx);
+/* CUDA-event timing of kernel groups on the launching stream (bench.py's live roofline) and the number
+ * of kernels this library launched.  Slots: 0 rdm_range, 1 rdm_doppler, 2 cfar, 3 echo_demod, 4 covariance,
+ * 5 music, 6 pmi_sinr, 7 cdl, 8 prg_precode, 9 ul_tpmi (16 slots).  collect() synchronises and resets. */
+#define ISAC_PROF_SLOTS 16
+int isac_profile_enable(isac_ctx* ctx, int32_t on);
+int isac_profile_collect(isac_ctx* ctx, double* msPerSlot, int32_t* countPerSlot, int64_t* launches);
 const char* isac_version(void);
 
 /* ---- K3+K4: 2D-FFT range-Doppler map + 2D CA-CFAR ---------------------------------------------
