@@ -26,7 +26,7 @@ struct RdmPlan {
     // device buffers (plan-owned)
     float* d_win1 = nullptr;     // kaiser(nSc)                         (fft2D.m:43)
     float* d_win2 = nullptr;     // kaiser(nIFFT)[(n-N/2) mod N]/sqrt(N) (fft2D.m:44-45 folded)
-    float2* d_inter = nullptr;   // range profiles [nIFFT x M x nAnts x maxBatch]
+    float2* d_inter = nullptr;   // range profiles [nIFFT x M x nAnts]: ONE map-set, reused so it stays in L2
     float* d_pow = nullptr;      // |RDM|^2 [nIFFT x nFFT x nAnts x maxBatch]
     uint8_t* d_flags = nullptr;  // CFAR decisions [nCut x nAnts x maxBatch]
     uint32_t* d_rowmask = nullptr;  // [rowWords x maxBatch]
