@@ -70,6 +70,16 @@ class EchoConfig(C.Structure):
     ]
 
 
+class CsiConfig(C.Structure):
+    _fields_ = [
+        ("nPorts", C.c_int32), ("N1", C.c_int32), ("N2", C.c_int32), ("O1", C.c_int32), ("O2", C.c_int32),
+        ("codebookMode", C.c_int32), ("nSizeBWP", C.c_int32), ("nStartBWP", C.c_int32), ("subbandSize", C.c_int32),
+        ("pmiSubband", C.c_int32), ("cqiSubband", C.c_int32), ("K", C.c_int32), ("L", C.c_int32), ("nRx", C.c_int32),
+        ("subsetRestriction", C.c_void_p), ("i2Restriction", C.c_void_p), ("riRestriction", C.c_uint8 * 8),
+        ("nRE", C.c_int32), ("reK", C.c_void_p), ("reL", C.c_void_p),
+    ]
+
+
 NOISE_NONE, NOISE_TENSOR, NOISE_PHILOX = 0, 1, 2
 MAX_PEAKS = 64
 
@@ -106,6 +116,22 @@ def _declare(lib):
         "isac_music2d_dev": ([vp, P(Music2dConfig), vp, vp, P(i32), vp, P(i32), vp, P(i32), vp, P(i32), vp, vp,
                               P(i32)], C.c_int),
         "isac_antenna_covariance_dev": ([vp, vp, C.c_int64, i32, vp], C.c_int),
+        "isac_type1sp_codebook": ([P(CsiConfig), i32, i32, P(i32), vp], C.c_int),
+        "isac_pusch_codebook": ([i32, i32, P(i32), vp], C.c_int),
+        "isac_pmi_plan_create": ([vp, P(CsiConfig), i32, i32, P(vp)], C.c_int),
+        "isac_pmi_plan_destroy": ([vp], C.c_int),
+        "isac_pmi_plan_info": ([vp, P(i32), P(i32), P(i32), P(i32), vp, vp], C.c_int),
+        "isac_dl_pmi_select_dev": ([vp, vp, vp, i32], C.c_int),
+        "isac_dl_pmi_collect": ([vp, i32, vp, vp, vp], C.c_int),
+        "isac_dl_pmi_get_info": ([vp, i32, vp, vp], C.c_int),
+        "isac_csi_plan_create": ([vp, P(CsiConfig), i32, P(vp)], C.c_int),
+        "isac_csi_plan_destroy": ([vp], C.c_int),
+        "isac_ri_select_dev": ([vp, vp, vp, i32, vp, vp, vp], C.c_int),
+        "isac_cqi_select_dev": ([vp, i32, vp, vp, i32, vp, i32, vp, P(i32), vp, vp, vp], C.c_int),
+        "isac_csi_report_dev": ([vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, P(i32)], C.c_int),
+        "isac_ul_pmi_select_dev": ([vp, i32, vp, i32, i32, i32, i32, f64, i32, i32, vp, vp, vp, P(i32), P(i32), P(i32)],
+                                   C.c_int),
+        "isac_prg_precode_dev": ([vp, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, vp, vp], C.c_int),
         "isac_radar_channel_dev": ([vp, P(EchoConfig), vp, vp, i32, C.c_uint64, vp], C.c_int),
         "isac_mono_static_sensing_dev": ([vp, P(EchoConfig), vp, vp, i32, C.c_uint64, vp, P(i32)], C.c_int),
         "isac_mono_static_sensing_host": ([vp, P(EchoConfig), vp, vp, i32, C.c_uint64, vp, P(i32)], C.c_int),

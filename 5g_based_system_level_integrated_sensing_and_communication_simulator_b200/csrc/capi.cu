@@ -5,6 +5,7 @@
 #include "rdm.cuh"
 #include "sense.cuh"
 #include "echo.cuh"
+#include "comm.cuh"
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -590,6 +591,316 @@ int isac_mono_static_sensing_host(isac_ctx* h, const isac_echo_config* cfg, cons
     ISAC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     if (nSymOut) *nSymOut = n;
     return ISAC_OK;
+}
+
+// ---- codebooks / PMI / RI / CQI / UL TPMI / PRG precoding --------------------------------------
+struct isac_pmi_plan {
+    PmiPlan* p;
+};
+struct isac_csi_plan {
+    Ctx* ctx;
+    CsiConfig cfg;
+    std::vector<uint8_t> csr, i2r;
+    std::vector<int> reK, reL;
+    int maxBatch;
+    PmiPlan* byRank[kMaxLayers];
+};
+
+static CsiConfig to_csi_config(const isac_csi_config* c) {
+    CsiConfig o{};
+    o.nPorts = c->nPorts; o.N1 = c->N1; o.N2 = c->N2; o.O1 = c->O1; o.O2 = c->O2; o.codebookMode = c->codebookMode;
+    o.nSizeBWP = c->nSizeBWP; o.nStartBWP = c->nStartBWP; o.subbandSize = c->subbandSize;
+    o.pmiSubband = c->pmiSubband; o.cqiSubband = c->cqiSubband; o.K = c->K; o.L = c->L; o.nRx = c->nRx;
+    o.subsetRestriction = c->subsetRestriction; o.i2Restriction = c->i2Restriction;
+    std::memcpy(o.riRestriction, c->riRestriction, 8);
+    o.nRE = c->nRE; o.reK = c->reK; o.reL = c->reL;
+    return o;
+}
+
+int isac_type1sp_codebook(const isac_csi_config* cfg, int32_t nLayers, int32_t variant, int32_t dims[4], double* W) {
+    if (!cfg || !dims) return ISAC_ERR_INVALID_ARG;
+    CodebookTable t;
+    int st = build_type1sp_table(nullptr, to_csi_config(cfg), nLayers, variant, t);
+    if (st) return st;
+    dims[0] = t.n2; dims[1] = t.n11; dims[2] = t.n12; dims[3] = t.n13;
+    if (W) {
+        std::vector<std::complex<double>> w;
+        materialize_codebook(t, w);
+        std::memcpy(W, w.data(), sizeof(std::complex<double>) * w.size());
+    }
+    return ISAC_OK;
+}
+
+int isac_pusch_codebook(int32_t nLayers, int32_t nPorts, int32_t* nTPMI, double* W) {
+    if (!nTPMI) return ISAC_ERR_INVALID_ARG;
+    CodebookTable t;
+    int st = build_pusch_table(nullptr, nLayers, nPorts, t);
+    if (st) return st;
+    *nTPMI = t.n2;
+    if (W) {
+        std::vector<std::complex<double>> w;
+        materialize_codebook(t, w);
+        std::memcpy(W, w.data(), sizeof(std::complex<double>) * w.size());
+    }
+    return ISAC_OK;
+}
+
+int isac_pmi_plan_create(isac_ctx* h, const isac_csi_config* cfg, int32_t nLayers, int32_t maxBatch, isac_pmi_plan** out) {
+    if (!h || !cfg || !out) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(h->c.device);
+    PmiPlan* p = nullptr;
+    int st = pmi_plan_create(&h->c, to_csi_config(cfg), nLayers, maxBatch, &p);
+    if (st) return st;
+    *out = new isac_pmi_plan{p};
+    return ISAC_OK;
+}
+
+int isac_pmi_plan_destroy(isac_pmi_plan* pl) {
+    if (!pl) return ISAC_OK;
+    if (pl->p) {
+        cudaSetDevice(pl->p->ctx->device);
+        cudaStreamSynchronize(pl->p->ctx->stream);
+        pmi_plan_destroy(pl->p);
+    }
+    delete pl;
+    return ISAC_OK;
+}
+
+int isac_pmi_plan_info(const isac_pmi_plan* pl, int32_t dims[4], int32_t* nSB, int32_t* nCqiSB, int32_t* nRE, int32_t* reKs,
+                       int32_t* reLs) {
+    if (!pl || !pl->p) return ISAC_ERR_INVALID_ARG;
+    const PmiPlan* p = pl->p;
+    if (dims) { dims[0] = p->tab.n2; dims[1] = p->tab.n11; dims[2] = p->tab.n12; dims[3] = p->tab.n13; }
+    if (nSB) *nSB = p->nSB;
+    if (nCqiSB) *nCqiSB = p->nCqiSB;
+    if (nRE) *nRE = (int32_t)p->reK.size();
+    if (reKs) std::memcpy(reKs, p->reK.data(), sizeof(int) * p->reK.size());
+    if (reLs) std::memcpy(reLs, p->reL.data(), sizeof(int) * p->reL.size());
+    return ISAC_OK;
+}
+
+int isac_dl_pmi_select_dev(isac_pmi_plan* pl, const void* H, const double* nVar, int32_t batch) {
+    if (!pl || !pl->p) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = pl->p->ctx;
+    cudaSetDevice(c->device);
+    return pmi_select_run(pl->p, (const float2*)H, nVar, batch, c->stream);
+}
+
+static void put_pmi(const PmiResult& r, int nSB, int nu, double* i1, double* i2, double* sinrAt) {
+    if (i1) for (int q = 0; q < 3; ++q) i1[q] = r.allNaN ? NAN : (double)r.i1[q];
+    if (i2) for (int sb = 0; sb < nSB; ++sb) i2[sb] = r.i2[sb];
+    if (sinrAt) std::memcpy(sinrAt, r.sinrSel.data(), sizeof(double) * (size_t)nSB * nu);
+}
+
+int isac_dl_pmi_collect(isac_pmi_plan* pl, int32_t batch, double* i1, double* i2, double* sinrAt) {
+    if (!pl || !pl->p) return ISAC_ERR_INVALID_ARG;
+    PmiPlan* p = pl->p;
+    cudaSetDevice(p->ctx->device);
+    std::vector<PmiResult> res;
+    int st = pmi_select_collect(p, batch, res);
+    if (st) return st;
+    for (int b = 0; b < batch; ++b)
+        put_pmi(res[b], p->nSB, p->nLayers, i1 ? i1 + 3 * b : nullptr, i2 ? i2 + (size_t)p->nSB * b : nullptr,
+                sinrAt ? sinrAt + (size_t)p->nSB * p->nLayers * b : nullptr);
+    return ISAC_OK;
+}
+
+int isac_dl_pmi_get_info(isac_pmi_plan* pl, int32_t batch, double* sinrPerRE, double* sinrPerSubband) {
+    if (!pl || !pl->p) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(pl->p->ctx->device);
+    return pmi_get_sinr_arrays(pl->p, batch, sinrPerRE, sinrPerSubband);
+}
+
+int isac_csi_plan_create(isac_ctx* h, const isac_csi_config* cfg, int32_t maxBatch, isac_csi_plan** out) {
+    if (!h || !cfg || !out) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(h->c.device);
+    isac_csi_plan* pl = new isac_csi_plan();
+    pl->ctx = &h->c;
+    pl->cfg = to_csi_config(cfg);
+    pl->maxBatch = maxBatch;
+    for (int r = 0; r < kMaxLayers; ++r) pl->byRank[r] = nullptr;
+    const int maxRank = pl->cfg.nRx < pl->cfg.nPorts ? pl->cfg.nRx : pl->cfg.nPorts;  // riSelect.m:222
+    for (int r = 1; r <= maxRank && r <= kMaxLayers; ++r) {
+        int st = pmi_plan_create(&h->c, pl->cfg, r, maxBatch, &pl->byRank[r - 1]);
+        if (st) {
+            isac_csi_plan_destroy(pl);
+            return st;
+        }
+    }
+    *out = pl;
+    return ISAC_OK;
+}
+
+int isac_csi_plan_destroy(isac_csi_plan* pl) {
+    if (!pl) return ISAC_OK;
+    cudaSetDevice(pl->ctx->device);
+    cudaStreamSynchronize(pl->ctx->stream);
+    for (int r = 0; r < kMaxLayers; ++r)
+        if (pl->byRank[r]) pmi_plan_destroy(pl->byRank[r]);
+    delete pl;
+    return ISAC_OK;
+}
+
+// riSelect.m:254-294 for a batch; keeps every evaluated rank's results for the fused report
+static int ri_select_batch(isac_csi_plan* pl, const float2* H, const double* nVar, int batch, std::vector<double>& RI,
+                           std::vector<PmiResult>& chosen, std::vector<std::vector<PmiResult>>& all) {
+    Ctx* c = pl->ctx;
+    const int maxRank = pl->cfg.nRx < pl->cfg.nPorts ? pl->cfg.nRx : pl->cfg.nPorts;
+    all.assign(kMaxLayers, {});
+    std::vector<int> valid;
+    for (int r = 1; r <= maxRank && r <= kMaxLayers; ++r)
+        if (pl->cfg.riRestriction[r - 1]) valid.push_back(r);
+    RI.assign(batch, NAN);
+    chosen.assign(batch, PmiResult());
+    const int nSB = pl->byRank[0] ? pl->byRank[0]->nSB : 1;
+    if (valid.empty() || (pl->byRank[0] && pl->byRank[0]->reK.empty())) {  // riSelect.m:235-245
+        for (auto& r : chosen) { r.allNaN = true; r.i2.assign(nSB, NAN); }
+        return kOk;
+    }
+    for (int r : valid) {
+        int st = pmi_select_run(pl->byRank[r - 1], H, nVar, batch, c->stream);
+        if (st) return st;
+    }
+    for (int r : valid) {
+        int st = pmi_select_collect(pl->byRank[r - 1], batch, all[r - 1]);
+        if (st) return st;
+    }
+    for (int b = 0; b < batch; ++b) {
+        double best = -INFINITY;
+        bool allNaNTotals = true;
+        for (int r : valid) {
+            const PmiResult& pr = all[r - 1][b];
+            const double total = ri_total_sinr(pr, nSB, r);
+            if (!std::isnan(total)) allNaNTotals = false;
+            if (total > best + 0.1) {  // riSelect.m:284
+                best = total;
+                RI[b] = r;
+                chosen[b] = pr;
+            }
+        }
+        if (allNaNTotals) {  // riSelect.m:289-292
+            RI[b] = NAN;
+            chosen[b] = all[valid.back() - 1][b];
+        }
+    }
+    return kOk;
+}
+
+int isac_ri_select_dev(isac_csi_plan* pl, const void* H, const double* nVar, int32_t batch, double* RI, double* i1, double* i2) {
+    if (!pl || !H || !nVar || !RI) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(pl->ctx->device);
+    if (batch < 1 || batch > pl->maxBatch) { set_error(pl->ctx, "riSelect: batch out of range"); return ISAC_ERR_INVALID_ARG; }
+    std::vector<double> ri;
+    std::vector<PmiResult> chosen;
+    std::vector<std::vector<PmiResult>> all;
+    int st = ri_select_batch(pl, (const float2*)H, nVar, batch, ri, chosen, all);
+    if (st) return st;
+    const int nSB = pl->byRank[0]->nSB;
+    for (int b = 0; b < batch; ++b) {
+        RI[b] = ri[b];
+        put_pmi(chosen[b], nSB, 0, i1 ? i1 + 3 * b : nullptr, i2 ? i2 + (size_t)nSB * b : nullptr, nullptr);
+    }
+    return ISAC_OK;
+}
+
+static void put_cqi(const CsiReport& rep, int rowsOut, double* cqi, double* sbcw, int rowsFull) {
+    if (cqi) {
+        for (int i = 0; i < rowsOut * 2; ++i) cqi[i] = NAN;
+        for (int c = 0; c < rep.nCW; ++c)
+            for (int s = 0; s < rep.nCqiRows; ++s) cqi[(size_t)c * rowsOut + s] = rep.cqi[(size_t)c * rep.nCqiRows + s];
+    }
+    if (sbcw) {
+        for (int i = 0; i < rowsFull * 2; ++i) sbcw[i] = NAN;
+        const int rows = (int)(rep.sinrPerSubbandPerCW.size() / (rep.nCW ? rep.nCW : 1));
+        for (int c = 0; c < rep.nCW; ++c)
+            for (int s = 0; s < rows && s < rowsFull; ++s) sbcw[(size_t)c * rowsFull + s] = rep.sinrPerSubbandPerCW[(size_t)c * rows + s];
+    }
+}
+
+int isac_cqi_select_dev(isac_csi_plan* pl, int32_t nLayers, const void* H, const double* nVar, int32_t batch,
+                        const double* table, int32_t tableLen, double* cqi, int32_t* cqiRows, double* i1, double* i2,
+                        double* sbcw) {
+    if (!pl || !H || !nVar || !table) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = pl->ctx;
+    cudaSetDevice(c->device);
+    if (nLayers < 1 || nLayers > kMaxLayers || !pl->byRank[nLayers - 1]) { set_error(c, "cqiSelect: invalid nLayers"); return ISAC_ERR_INVALID_ARG; }
+    if (batch < 1 || batch > pl->maxBatch) { set_error(c, "cqiSelect: batch out of range"); return ISAC_ERR_INVALID_ARG; }
+    PmiPlan* p = pl->byRank[nLayers - 1];
+    int st = pmi_select_run(p, (const float2*)H, nVar, batch, c->stream);  // cqiSelect.m:507
+    if (st) return st;
+    std::vector<PmiResult> res;
+    if ((st = pmi_select_collect(p, batch, res))) return st;
+    const int rowsOut = (pl->cfg.cqiSubband && p->nCqiSB > 1) ? p->nCqiSB + 1 : 1;
+    const int rowsFull = p->nCqiSB > 1 ? p->nCqiSB + 1 : 1;
+    if (cqiRows) *cqiRows = rowsOut;
+    for (int b = 0; b < batch; ++b) {
+        CsiReport rep;
+        cqi_from_pmi(pl->cfg, nLayers, res[b], p->nSB, p->nCqiSB, table, tableLen, rep);
+        put_cqi(rep, rowsOut, cqi ? cqi + (size_t)2 * rowsOut * b : nullptr, sbcw ? sbcw + (size_t)2 * rowsFull * b : nullptr, rowsFull);
+        put_pmi(res[b], p->nSB, nLayers, i1 ? i1 + 3 * b : nullptr, i2 ? i2 + (size_t)p->nSB * b : nullptr, nullptr);
+    }
+    return ISAC_OK;
+}
+
+int isac_csi_report_dev(isac_csi_plan* pl, const void* H, const double* nVar, int32_t batch, const double* table,
+                        int32_t tableLen, int32_t rankCap, double* RI, double* i1, double* i2, double* cqi, int32_t* cqiRows) {
+    if (!pl || !H || !nVar || !table || !RI) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = pl->ctx;
+    cudaSetDevice(c->device);
+    if (batch < 1 || batch > pl->maxBatch) { set_error(c, "csi report: batch out of range"); return ISAC_ERR_INVALID_ARG; }
+    std::vector<double> ri;
+    std::vector<PmiResult> chosen;
+    std::vector<std::vector<PmiResult>> all;
+    int st = ri_select_batch(pl, (const float2*)H, nVar, batch, ri, chosen, all);
+    if (st) return st;
+    PmiPlan* p0 = pl->byRank[0];
+    const int rowsOut = (pl->cfg.cqiSubband && p0->nCqiSB > 1) ? p0->nCqiSB + 1 : 1;
+    if (cqiRows) *cqiRows = rowsOut;
+    for (int b = 0; b < batch; ++b) {
+        RI[b] = ri[b];
+        int rank = std::isnan(ri[b]) ? 1 : (int)ri[b];
+        if (rankCap > 0 && rank > rankCap) rank = rankCap;  // uePhy.m:901
+        if (std::isnan(ri[b])) RI[b] = NAN; else RI[b] = rank;
+        if (all[rank - 1].empty()) {  // rank not scored by the RI loop (restricted): evaluate it now
+            std::vector<PmiResult> tmp;
+            if ((st = pmi_select_run(pl->byRank[rank - 1], (const float2*)H, nVar, batch, c->stream))) return st;
+            if ((st = pmi_select_collect(pl->byRank[rank - 1], batch, all[rank - 1]))) return st;
+        }
+        const PmiResult& pr = all[rank - 1][b];
+        CsiReport rep;
+        cqi_from_pmi(pl->cfg, rank, pr, p0->nSB, p0->nCqiSB, table, tableLen, rep);
+        put_cqi(rep, rowsOut, cqi ? cqi + (size_t)2 * rowsOut * b : nullptr, nullptr, 0);
+        put_pmi(pr, p0->nSB, rank, i1 ? i1 + 3 * b : nullptr, i2 ? i2 + (size_t)p0->nSB * b : nullptr, nullptr);
+    }
+    return ISAC_OK;
+}
+
+int isac_ul_pmi_select_dev(isac_ctx* h, int32_t nLayers, const void* hest, int32_t K, int32_t nSym, int32_t nRx, int32_t nPorts,
+                           double noiseEst, int32_t bandSize, int32_t maxSB, double* pmi, double* sinr, int32_t* sbIdx,
+                           int32_t* nSB, int32_t* nTPMI, int32_t* none) {
+    if (!h || !hest || !nSB || !nTPMI || !none) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    UlPmiResult r;
+    int st = ul_pmi_select_run(c, nLayers, (const float2*)hest, K, nSym, nRx, nPorts, noiseEst, bandSize, r, c->stream);
+    if (st) return st;
+    *nSB = r.nSB; *nTPMI = r.nTPMI; *none = r.none ? 1 : 0;
+    if (r.nSB > maxSB) { set_error(c, "pmiSelect: maxSB too small"); return ISAC_ERR_CAPACITY; }
+    if (sbIdx) std::memcpy(sbIdx, r.subbandIndices.data(), sizeof(int) * r.subbandIndices.size());
+    if (!r.none) {
+        if (pmi) std::memcpy(pmi, r.pmi.data(), sizeof(double) * r.pmi.size());
+        if (sinr) std::memcpy(sinr, r.sinr.data(), sizeof(double) * r.sinr.size());
+    }
+    return ISAC_OK;
+}
+
+int isac_prg_precode_dev(isac_ctx* h, int32_t K, int32_t Lsym, int32_t nStartGrid, const void* portsym, const int32_t* portind,
+                         int32_t NRE, int32_t nLayers, const void* F, int32_t P, int32_t NPRG, void* antsym, int32_t* antind) {
+    if (!h) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    return prg_precode_run(c, K, Lsym, nStartGrid, (const float2*)portsym, portind, NRE, nLayers, (const float2*)F, P, NPRG,
+                           (float2*)antsym, antind, c->stream);
 }
 
 }  // extern "C"

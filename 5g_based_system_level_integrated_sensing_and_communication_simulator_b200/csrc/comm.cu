@@ -1,0 +1,876 @@
+// K8 + K9 (+K12, K10): per-RE LMMSE SINR of every Type-I precoder candidate, wideband / subband PMI
+// selection, UL TPMI selection and PRG precoding.
+//
+// Replaces the interpreted loop nest of communication.phyLayer.dlPMISelect (dlPMISelect.m:385-428 calling
+// getPrecodedSINR :1825-1834, selection :444-501), pmiSelect (pmiSelect.m:44-59, precodedSINR.m:11-18,
+// sinrPerSubband.m:26-34) and prgPrecode (prgPrecode.m:103-144).
+//
+// K8 (the dense H*W contraction): every Type-I precoder column is [c0 v ; c1 v (; c2 v ; c3 v)] with v a DFT
+// beam, so H*W for ALL candidates follows from the beam responses  B[blk][beam] = H[:, block blk] * v_beam,
+// computed once per RE into shared memory (R x P/2 x nBeams complex MACs; P/2 <= 16 is far too short a
+// contraction to feed tcgen05 — K = 2..16 would idle the tensor pipe — so it runs on the FP64 pipe with the
+// rest of the SINR arithmetic).  K9: per candidate A = (HW)'(HW) + nVar I in registers (float64: A squares the
+// conditioning of HW, float32 cannot hold 1e-5 here), Cholesky, diag(A^-1), sinr_l = 1/(nVar [A^-1]_ll) - 1.
+#include "comm.cuh"
+#include "ctx.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace isac {
+
+struct PmiDev {
+    const float2* H;
+    const double2* beams;
+    const int* layerBeam;
+    const double2* layerCoef;
+    const double* candScale;
+    const uint8_t* valid;
+    const int* reK;
+    const int* reL;
+    const double* nVar;   // device [batch]
+    double* S;
+    int K, L, R, P, NB, Pb, nBeams, nCand, nRE;
+    double scale;
+};
+
+__device__ __forceinline__ double round4(double x) { return copysign(floor(fabs(x) * 1e4 + 0.5) / 1e4, x); }
+
+template <int NU>
+__global__ void __launch_bounds__(128)
+pmi_sinr_kernel(const PmiDev p) {
+    extern __shared__ double2 sm[];
+    double2* Hs = sm;                  // [R][P]
+    double2* Bf = sm + p.R * p.P;      // [NB][nBeams][R]
+    const int e = blockIdx.x, b = blockIdx.y;
+    const int R = p.R, P = p.P;
+    const long long kk = p.reK[e] - 1, ll = p.reL[e] - 1;
+    const float2* __restrict__ Hb = p.H + (long long)b * p.K * p.L * R * P;
+    for (int i = threadIdx.x; i < R * P; i += blockDim.x) {
+        const int r = i % R, pp = i / R;
+        const float2 h = __ldg(Hb + kk + p.K * (ll + (long long)p.L * (r + (long long)R * pp)));
+        Hs[r * P + pp] = make_double2((double)h.x, (double)h.y);
+    }
+    __syncthreads();
+    const int nB = p.NB * p.nBeams * R;
+    for (int i = threadIdx.x; i < nB; i += blockDim.x) {
+        const int r = i % R, bm = (i / R) % p.nBeams, blk = i / (R * p.nBeams);
+        double2 acc = make_double2(0.0, 0.0);
+        for (int q = 0; q < p.Pb; ++q) acc = zadd(acc, zmul(Hs[r * P + blk * p.Pb + q], p.beams[bm * p.Pb + q]));
+        Bf[i] = acc;  // index (blk*nBeams + bm)*R + r
+    }
+    __syncthreads();
+    const double nVar = p.nVar[b];
+    double* __restrict__ Sout = p.S + ((long long)b * p.nRE + e) * NU * (long long)p.nCand;
+    for (int c = threadIdx.x; c < p.nCand; c += blockDim.x) {
+        if (!p.valid[c]) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) Sout[(long long)j * p.nCand + c] = NAN;  // restricted precoder (dlPMISelect.m:418)
+            continue;
+        }
+        const double sc = p.candScale ? p.candScale[c] : p.scale;
+        double2 A[NU][NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i)
+#pragma unroll
+            for (int j = 0; j < NU; ++j) A[i][j] = make_double2(0.0, 0.0);
+        int beamOf[NU];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) beamOf[j] = p.layerBeam[c * NU + j];
+        for (int r = 0; r < R; ++r) {
+            double2 g[NU];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+                double2 acc = make_double2(0.0, 0.0);
+                for (int blk = 0; blk < p.NB; ++blk)
+                    acc = zadd(acc, zmul(p.layerCoef[(c * NU + j) * p.NB + blk], Bf[(blk * p.nBeams + beamOf[j]) * R + r]));
+                g[j] = make_double2(acc.x * sc, acc.y * sc);
+            }
+#pragma unroll
+            for (int i = 0; i < NU; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) A[i][j] = zadd(A[i][j], zmulc(g[j], g[i]));  // conj(g_i) g_j
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) A[i][i].x += nVar;  // (W'H')HW + noise  (dlPMISelect.m:1831-1832)
+        // Cholesky A = L L^H (lower triangle in place)
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+            double d = A[j][j].x;
+#pragma unroll
+            for (int k = 0; k < j; ++k) d -= A[j][k].x * A[j][k].x + A[j][k].y * A[j][k].y;
+            const double ljj = sqrt(d);
+            A[j][j] = make_double2(ljj, 0.0);
+            const double inv = 1.0 / ljj;
+#pragma unroll
+            for (int i = j + 1; i < NU; ++i) {
+                double2 s = A[i][j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) s = zsub(s, zmulc(A[i][k], A[j][k]));
+                A[i][j] = make_double2(s.x * inv, s.y * inv);
+            }
+        }
+        // [A^-1]_cc = || L^-1 e_c ||^2 ; sinr = 1/(nVar*[A^-1]_cc) - 1   (dlPMISelect.m:1832-1833)
+#pragma unroll
+        for (int cc = 0; cc < NU; ++cc) {
+            double2 x[NU];
+            x[cc] = make_double2(1.0 / A[cc][cc].x, 0.0);
+            double nrm = x[cc].x * x[cc].x;
+#pragma unroll
+            for (int i = cc + 1; i < NU; ++i) {
+                double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int k = cc; k < i; ++k) s = zadd(s, zmul(A[i][k], x[k]));
+                const double inv = -1.0 / A[i][i].x;
+                x[i] = make_double2(s.x * inv, s.y * inv);
+                nrm += x[i].x * x[i].x + x[i].y * x[i].y;
+            }
+            Sout[(long long)cc * p.nCand + c] = 1.0 / (nVar * nrm) - 1.0;
+        }
+    }
+}
+
+// totals over REs and layers per candidate (dlPMISelect.m:444)
+__global__ void pmi_total_kernel(const double* __restrict__ S, int nCand, int nu, int nRE, double* __restrict__ total) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (c >= nCand) return;
+    const double* __restrict__ s = S + (long long)b * nRE * nu * nCand + c;
+    double acc = 0.0;
+    for (int i = 0; i < nRE * nu; ++i) {
+        const double v = s[(long long)i * nCand];
+        if (!isnan(v)) acc += v;  // 'omitnan'
+    }
+    total[(long long)b * nCand + c] = acc;
+}
+
+// subband means (dlPMISelect.m:481): REs are sorted by subband; weight = mean-of-means weight
+__global__ void pmi_subband_kernel(const double* __restrict__ S, int nCand, int nu, int nRE, int nSB,
+                                   const int* __restrict__ sbStart, const double* __restrict__ reW,
+                                   double* __restrict__ sub) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCand) return;
+    const int l = blockIdx.y % nu, sb = blockIdx.y / nu, b = blockIdx.z;
+    const double* __restrict__ s = S + (long long)b * nRE * nu * nCand + c;
+    double acc = 0.0;
+    bool any = false;
+    for (int e = sbStart[sb]; e < sbStart[sb + 1]; ++e) {
+        const double v = s[((long long)e * nu + l) * nCand];
+        if (!isnan(v)) {
+            acc += reW[e] * v;
+            any = true;
+        }
+    }
+    sub[(((long long)b * nSB + sb) * nu + l) * nCand + c] = any ? acc : NAN;
+}
+
+struct SelDev {
+    const double* total;
+    const double* sub;
+    const double* S;
+    const int* sbStart;
+    const int* cqiStart;
+    const double* cqiW;
+    int* sel;
+    double* sinrSel;
+    double* sinrWb;
+    int nCand, nu, nRE, nSB, nCqiSB, n2, n11, n12, n13;
+};
+
+__global__ void __launch_bounds__(256) pmi_select_kernel(const SelDev p) {
+    __shared__ double bv[8];
+    __shared__ int bi[8];
+    __shared__ int best;
+    const int b = blockIdx.x;
+    const double* __restrict__ tot = p.total + (long long)b * p.nCand;
+    double v = -INFINITY;
+    int ix = -1;
+    for (int c = threadIdx.x; c < p.nCand; c += blockDim.x) {
+        const double t = round4(tot[c]);  // dlPMISelect.m:449
+        if (ix < 0 || t > v) {
+            v = t;
+            ix = c;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+        if (oi >= 0 && (ix < 0 || ov > v || (ov == v && oi < ix))) {
+            v = ov;
+            ix = oi;
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        bv[threadIdx.x >> 5] = v;
+        bi[threadIdx.x >> 5] = ix;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = -INFINITY;
+        int mi = -1;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+            if (bi[w] >= 0 && (mi < 0 || bv[w] > m || (bv[w] == m && bi[w] < mi))) {
+                m = bv[w];
+                mi = bi[w];
+            }
+        best = mi;  // first linear index of the maximum (find(...,1), dlPMISelect.m:453)
+    }
+    __syncthreads();
+    const int lin = best;
+    const int i2wb = lin % p.n2, i11 = (lin / p.n2) % p.n11, i12 = (lin / (p.n2 * p.n11)) % p.n12,
+              i13 = lin / (p.n2 * p.n11 * p.n12);
+    int* __restrict__ sel = p.sel + (long long)b * (4 + p.nSB);
+    if (threadIdx.x == 0) {
+        sel[0] = i2wb;
+        sel[1] = i11;
+        sel[2] = i12;
+        sel[3] = i13;
+    }
+    const long long base1 = (long long)p.n2 * (i11 + (long long)p.n11 * (i12 + (long long)p.n12 * i13));
+    for (int sb = threadIdx.x; sb < p.nSB; sb += blockDim.x) {
+        int pick = -1;
+        if (p.sbStart[sb + 1] > p.sbStart[sb]) {  // CSI-RS present in the subband
+            double bestT = -INFINITY;
+            for (int i2 = 0; i2 < p.n2; ++i2) {
+                double acc = 0.0;
+                for (int l = 0; l < p.nu; ++l) {
+                    const double x = p.sub[(((long long)b * p.nSB + sb) * p.nu + l) * p.nCand + base1 + i2];
+                    if (!isnan(x)) acc += x;  // sum(...,2,'omitnan')  (dlPMISelect.m:492)
+                }
+                const double t = round4(acc);
+                if (pick < 0 || t > bestT) {  // [~,i2] = max(...) -> first maximum (dlPMISelect.m:496)
+                    bestT = t;
+                    pick = i2;
+                }
+            }
+        }
+        sel[4 + sb] = pick;
+        for (int l = 0; l < p.nu; ++l)
+            p.sinrSel[((long long)b * p.nSB + sb) * p.nu + l] =
+                pick >= 0 ? p.sub[(((long long)b * p.nSB + sb) * p.nu + l) * p.nCand + base1 + pick] : NAN;
+    }
+    __syncthreads();
+    // CQI-subband SINR with one wideband i2 (cqiSelect.m:586-596 -> getSubbandSINR :768-800)
+    const int i2first = sel[4];
+    for (int idx = threadIdx.x; idx < p.nCqiSB * p.nu; idx += blockDim.x) {
+        const int l = idx % p.nu, cs = idx / p.nu;
+        double acc = NAN;
+        if (i2first >= 0 && p.cqiStart[cs + 1] > p.cqiStart[cs]) {
+            acc = 0.0;
+            for (int e = p.cqiStart[cs]; e < p.cqiStart[cs + 1]; ++e)
+                acc += p.cqiW[e] * p.S[(((long long)b * p.nRE + e) * p.nu + l) * p.nCand + base1 + i2first];
+        }
+        p.sinrWb[((long long)b * p.nCqiSB + cs) * p.nu + l] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+template <class T>
+static int upload(Ctx* ctx, T** dst, const std::vector<T>& v) {
+    const size_t n = v.empty() ? 1 : v.size();
+    ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)dst, sizeof(T) * n));
+    if (!v.empty()) ISAC_CUDA_CHECK(ctx, cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    return kOk;
+}
+
+// sort REs by (k,l), assign subbands and mean-of-means weights (mean over k per symbol, then over symbols)
+static void partition_res(const std::vector<int>& k, const std::vector<int>& l, const std::vector<int>& sizes,
+                          std::vector<int>& start, std::vector<double>& w) {
+    const int nSB = (int)sizes.size(), n = (int)k.size();
+    start.assign(nSB + 1, 0);
+    w.assign(n, 0.0);
+    int prb0 = 0, e = 0;
+    for (int sb = 0; sb < nSB; ++sb) {
+        const int lo = prb0 * 12 + 1, hi = (prb0 + sizes[sb]) * 12;
+        start[sb] = e;
+        while (e < n && k[e] >= lo && k[e] <= hi) ++e;
+        prb0 += sizes[sb];
+        // weights
+        std::vector<int> syms;
+        for (int i = start[sb]; i < e; ++i)
+            if (std::find(syms.begin(), syms.end(), l[i]) == syms.end()) syms.push_back(l[i]);
+        for (int i = start[sb]; i < e; ++i) {
+            int cnt = 0;
+            for (int q = start[sb]; q < e; ++q) cnt += (l[q] == l[i]);
+            w[i] = 1.0 / ((double)cnt * (double)syms.size());
+        }
+    }
+    start[nSB] = e;
+}
+
+int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, PmiPlan** out) {
+    if (maxBatch < 1 || cin.nRx < 1 || cin.nPorts < 1 || cin.K < 12 || cin.L < 1 || cin.nRE < 0) {
+        set_error(ctx, "pmi_plan_create: invalid configuration");
+        return kErrInvalidArg;
+    }
+    if (nLayers > cin.nRx || nLayers > cin.nPorts) {
+        set_error(ctx, "nr5g:hDLPMISelect:InvalidNumLayers");
+        return kErrInvalidArg;
+    }
+    PmiPlan* p = new PmiPlan();
+    p->ctx = ctx;
+    p->cfg = cin;
+    p->nLayers = nLayers;
+    p->maxBatch = maxBatch;
+    if (cin.subsetRestriction) {
+        const int n = cin.nPorts > 2 ? cin.N1 * cin.O1 * cin.N2 * cin.O2 : 6;
+        p->csr.assign(cin.subsetRestriction, cin.subsetRestriction + n);
+        p->cfg.subsetRestriction = p->csr.data();
+    }
+    if (cin.i2Restriction) {
+        p->i2r.assign(cin.i2Restriction, cin.i2Restriction + 16);
+        p->cfg.i2Restriction = p->i2r.data();
+    }
+    // RE list sorted by (k, l) (only the summation order depends on it)
+    std::vector<int> order(cin.nRE);
+    for (int i = 0; i < cin.nRE; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        return cin.reK[a] != cin.reK[b] ? cin.reK[a] < cin.reK[b] : cin.reL[a] < cin.reL[b];
+    });
+    for (int i : order) {
+        if (cin.reK[i] < 1 || cin.reK[i] > cin.nSizeBWP * 12 || cin.reL[i] < 1 || cin.reL[i] > cin.L) continue;  // :352-353
+        p->reK.push_back(cin.reK[i]);
+        p->reL.push_back(cin.reL[i]);
+    }
+    p->cfg.nRE = (int)p->reK.size();
+    p->cfg.reK = p->reK.data();
+    p->cfg.reL = p->reL.data();
+    int s = build_type1sp_table(ctx, p->cfg, nLayers, kVariantUE, p->tab);
+    if (s) { delete p; return s; }
+    subband_info(p->cfg.pmiSubband != 0, p->cfg.nStartBWP, p->cfg.nSizeBWP, p->cfg.subbandSize, p->sbSizes);
+    subband_info(p->cfg.cqiSubband != 0, p->cfg.nStartBWP, p->cfg.nSizeBWP, p->cfg.subbandSize, p->cqiSbSizes);
+    p->nSB = (int)p->sbSizes.size();
+    p->nCqiSB = (int)p->cqiSbSizes.size();
+    std::vector<int> sbStart, cqiStart;
+    std::vector<double> w, cw;
+    partition_res(p->reK, p->reL, p->sbSizes, sbStart, w);
+    partition_res(p->reK, p->reL, p->cqiSbSizes, cqiStart, cw);
+    p->sbHasRE.resize(p->nSB);
+    for (int i = 0; i < p->nSB; ++i) p->sbHasRE[i] = sbStart[i + 1] > sbStart[i];
+    p->cqiSbHasRE.resize(p->nCqiSB);
+    for (int i = 0; i < p->nCqiSB; ++i) p->cqiSbHasRE[i] = cqiStart[i + 1] > cqiStart[i];
+    const CodebookTable& t = p->tab;
+    const int nCand = t.nCand(), nu = nLayers;
+    std::vector<double2> beams(t.beams.size()), coef((size_t)nCand * nu * t.NB);
+    for (size_t i = 0; i < t.beams.size(); ++i) beams[i] = make_double2(t.beams[i].real(), t.beams[i].imag());
+    std::vector<int> lb((size_t)nCand * nu);
+    for (int c = 0; c < nCand; ++c)
+        for (int j = 0; j < nu; ++j) {
+            const LayerDesc& d = t.layers[(size_t)c * nu + j];
+            lb[(size_t)c * nu + j] = d.beam;
+            for (int b = 0; b < t.NB; ++b) coef[((size_t)c * nu + j) * t.NB + b] = make_double2(d.coef[b].real(), d.coef[b].imag());
+        }
+    PmiPlan* ex = p;
+#define UP(dst, vec)                                   \
+    if ((s = upload(ctx, &(dst), vec))) {              \
+        pmi_plan_destroy(p);                           \
+        return s;                                      \
+    }
+    UP(p->d_beams, beams);
+    UP(p->d_layerBeam, lb);
+    UP(p->d_layerCoef, coef);
+    UP(p->d_valid, t.valid);
+    UP(p->d_reK, p->reK);
+    UP(p->d_reL, p->reL);
+    UP(p->d_reW, w);
+    UP(p->d_reCqiW, cw);
+    UP(ex->d_sbStart, sbStart);
+    UP(ex->d_cqiStart, cqiStart);
+#undef UP
+    const size_t B = maxBatch, nRE = p->reK.size() ? p->reK.size() : 1;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 8); };
+    A((void**)&p->d_S, sizeof(double) * nCand * nu * nRE * B);
+    A((void**)&p->d_total, sizeof(double) * nCand * B);
+    A((void**)&p->d_sub, sizeof(double) * nCand * nu * p->nSB * B);
+    A((void**)&p->d_sel, sizeof(int) * (4 + p->nSB) * B);
+    A((void**)&p->d_sinrSel, sizeof(double) * nu * p->nSB * B);
+    A((void**)&p->d_sinrWb, sizeof(double) * nu * p->nCqiSB * B);
+    A((void**)&ex->d_nVar, sizeof(double) * B);
+    if (e != cudaSuccess) {
+        set_error(ctx, std::string("pmi_plan_create: cudaMalloc: ") + cudaGetErrorString(e));
+        pmi_plan_destroy(p);
+        return kErrCuda;
+    }
+    *out = p;
+    return kOk;
+}
+
+void pmi_plan_destroy(PmiPlan* p) {
+    if (!p) return;
+    cudaFree(p->d_sbStart); cudaFree(p->d_cqiStart); cudaFree(p->d_nVar);
+    cudaFree(p->d_beams); cudaFree(p->d_layerBeam); cudaFree(p->d_layerCoef); cudaFree(p->d_candScale);
+    cudaFree(p->d_valid); cudaFree(p->d_reK); cudaFree(p->d_reL); cudaFree(p->d_reSb); cudaFree(p->d_reW);
+    cudaFree(p->d_reCqiSb); cudaFree(p->d_reCqiW); cudaFree(p->d_S); cudaFree(p->d_total); cudaFree(p->d_sub);
+    cudaFree(p->d_sel); cudaFree(p->d_sinrSel); cudaFree(p->d_sinrWb);
+    delete p;
+}
+
+template <int NU>
+static cudaError_t launch_sinr(const PmiDev& d, int batch, cudaStream_t st) {
+    const size_t smem = sizeof(double2) * ((size_t)d.R * d.P + (size_t)d.NB * d.nBeams * d.R);
+    auto k = pmi_sinr_kernel<NU>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(d.nRE, batch);
+    k<<<grid, 128, smem, st>>>(d);
+    return cudaGetLastError();
+}
+
+int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, cudaStream_t st) {
+    Ctx* ctx = p->ctx;
+    if (batch < 1 || batch > p->maxBatch || !H || !nVar) {
+        set_error(ctx, "pmi_select_run: invalid argument");
+        return kErrInvalidArg;
+    }
+    const int nRE = (int)p->reK.size();
+    if (nRE == 0) return kOk;  // everything NaN (dlPMISelect.m:362-379), decided at collect time
+    PmiPlan* ex = p;
+    std::vector<double> nv(batch);
+    for (int b = 0; b < batch; ++b) {
+        if (!(nVar[b] >= 0.0) || !std::isfinite(nVar[b])) {
+            set_error(ctx, "dlPMISelect: NVAR must be real, nonnegative and finite");
+            return kErrInvalidArg;
+        }
+        nv[b] = nVar[b] < 1e-10 ? 1e-10 : nVar[b];  // dlPMISelect.m:846-848
+    }
+    void* pin = nullptr;
+    int s = ctx_pinned(ctx, 5, sizeof(double) * batch, &pin);
+    if (s) return s;
+    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    std::memcpy(pin, nv.data(), sizeof(double) * batch);
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(ex->d_nVar, pin, sizeof(double) * batch, cudaMemcpyHostToDevice, st));
+    const CodebookTable& t = p->tab;
+    PmiDev d{};
+    d.H = H; d.beams = p->d_beams; d.layerBeam = p->d_layerBeam; d.layerCoef = p->d_layerCoef;
+    d.candScale = nullptr; d.valid = p->d_valid; d.reK = p->d_reK; d.reL = p->d_reL; d.nVar = ex->d_nVar; d.S = p->d_S;
+    d.K = p->cfg.K; d.L = p->cfg.L; d.R = p->cfg.nRx; d.P = t.P; d.NB = t.NB; d.Pb = t.Pb; d.nBeams = t.nBeams;
+    d.nCand = t.nCand(); d.nRE = nRE; d.scale = t.scale;
+    const int pr = prof_begin(ctx, kProfPmi, st);
+    cudaError_t e;
+    switch (p->nLayers) {
+        case 1: e = launch_sinr<1>(d, batch, st); break;
+        case 2: e = launch_sinr<2>(d, batch, st); break;
+        case 3: e = launch_sinr<3>(d, batch, st); break;
+        case 4: e = launch_sinr<4>(d, batch, st); break;
+        case 5: e = launch_sinr<5>(d, batch, st); break;
+        case 6: e = launch_sinr<6>(d, batch, st); break;
+        case 7: e = launch_sinr<7>(d, batch, st); break;
+        default: e = launch_sinr<8>(d, batch, st); break;
+    }
+    ISAC_CUDA_CHECK(ctx, e);
+    const int nCand = d.nCand, nu = p->nLayers;
+    dim3 g1((nCand + 127) / 128, batch);
+    pmi_total_kernel<<<g1, 128, 0, st>>>(p->d_S, nCand, nu, nRE, p->d_total);
+    dim3 g2((nCand + 127) / 128, nu * p->nSB, batch);
+    pmi_subband_kernel<<<g2, 128, 0, st>>>(p->d_S, nCand, nu, nRE, p->nSB, ex->d_sbStart, p->d_reW, p->d_sub);
+    SelDev sd{};
+    sd.total = p->d_total; sd.sub = p->d_sub; sd.S = p->d_S; sd.sbStart = ex->d_sbStart; sd.cqiStart = ex->d_cqiStart;
+    sd.cqiW = p->d_reCqiW; sd.sel = p->d_sel; sd.sinrSel = p->d_sinrSel; sd.sinrWb = p->d_sinrWb;
+    sd.nCand = nCand; sd.nu = nu; sd.nRE = nRE; sd.nSB = p->nSB; sd.nCqiSB = p->nCqiSB;
+    sd.n2 = t.n2; sd.n11 = t.n11; sd.n12 = t.n12; sd.n13 = t.n13;
+    pmi_select_kernel<<<batch, 256, 0, st>>>(sd);
+    prof_end(ctx, pr, st);
+    count_launches(ctx, 4);
+    ISAC_CUDA_CHECK(ctx, cudaGetLastError());
+    return kOk;
+}
+
+int pmi_select_collect(PmiPlan* p, int batch, std::vector<PmiResult>& out) {
+    Ctx* ctx = p->ctx;
+    cudaStream_t st = ctx->stream;
+    const int nu = p->nLayers, nSB = p->nSB, nC = p->nCqiSB;
+    out.assign(batch, PmiResult());
+    bool anyValid = false;
+    for (uint8_t v : p->tab.valid) anyValid |= (v != 0);
+    if (p->reK.empty() || !anyValid) {  // dlPMISelect.m:362-379
+        for (auto& r : out) {
+            r.allNaN = true;
+            r.i2.assign(nSB, NAN);
+            r.sinrSel.assign((size_t)nSB * nu, NAN);
+            r.sinrWbSel.assign((size_t)nC * nu, NAN);
+        }
+        return kOk;
+    }
+    std::vector<int> sel((size_t)(4 + nSB) * batch);
+    std::vector<double> ss((size_t)nu * nSB * batch), sw((size_t)nu * nC * batch);
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(sel.data(), p->d_sel, sizeof(int) * sel.size(), cudaMemcpyDeviceToHost, st));
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(ss.data(), p->d_sinrSel, sizeof(double) * ss.size(), cudaMemcpyDeviceToHost, st));
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(sw.data(), p->d_sinrWb, sizeof(double) * sw.size(), cudaMemcpyDeviceToHost, st));
+    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    for (int b = 0; b < batch; ++b) {
+        PmiResult& r = out[b];
+        const int* s = sel.data() + (size_t)b * (4 + nSB);
+        r.i1[0] = s[1] + 1; r.i1[1] = s[2] + 1; r.i1[2] = s[3] + 1;
+        r.i2.resize(nSB);
+        for (int sb = 0; sb < nSB; ++sb) r.i2[sb] = s[4 + sb] >= 0 ? (double)(s[4 + sb] + 1) : NAN;
+        r.sinrSel.resize((size_t)nSB * nu);
+        for (int sb = 0; sb < nSB; ++sb)
+            for (int l = 0; l < nu; ++l) r.sinrSel[(size_t)l * nSB + sb] = ss[((size_t)b * nSB + sb) * nu + l];  // [nSB x nu] col-major
+        r.sinrWbSel.resize((size_t)nC * nu);
+        for (int cs = 0; cs < nC; ++cs)
+            for (int l = 0; l < nu; ++l) r.sinrWbSel[(size_t)l * nC + cs] = sw[((size_t)b * nC + cs) * nu + l];
+    }
+    return kOk;
+}
+
+int pmi_get_sinr_arrays(PmiPlan* p, int batch, double* sinrPerRE, double* sinrPerSubband) {
+    Ctx* ctx = p->ctx;
+    cudaStream_t st = ctx->stream;
+    const size_t nCand = p->tab.nCand(), nu = p->nLayers, nRE = p->reK.size();
+    // device layout [cand][layer][RE|SB][batch] -> host MATLAB layout [RE|SB x layer x cand x batch]
+    auto fetch = [&](const double* dsrc, size_t n3, double* dst) -> int {
+        std::vector<double> tmp(nCand * nu * n3 * batch);
+        ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(tmp.data(), dsrc, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, st));
+        ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+        for (size_t b = 0; b < (size_t)batch; ++b)
+            for (size_t e = 0; e < n3; ++e)
+                for (size_t l = 0; l < nu; ++l)
+                    for (size_t c = 0; c < nCand; ++c)
+                        dst[e + n3 * (l + nu * (c + nCand * b))] = tmp[c + nCand * (l + nu * (e + n3 * b))];
+        return kOk;
+    };
+    int s = kOk;
+    if (sinrPerRE && nRE) s = fetch(p->d_S, nRE, sinrPerRE);
+    if (!s && sinrPerSubband && nRE) s = fetch(p->d_sub, (size_t)p->nSB, sinrPerSubband);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// host tails: riSelect / cqiSelect
+// ------------------------------------------------------------------------------------------
+double ri_total_sinr(const PmiResult& r, int nSB, int rank) {
+    if (r.allNaN) return NAN;
+    double total = 0.0;
+    for (int l = 0; l < rank; ++l) {
+        double acc = 0.0;
+        int cnt = 0;
+        for (int sb = 0; sb < nSB; ++sb) {
+            if (std::isnan(r.i2[sb])) continue;                               // riSelect.m:263
+            const double v = r.sinrSel[(size_t)l * nSB + sb] * rank;         // :265
+            if (!std::isnan(v)) { acc += v; ++cnt; }
+        }
+        const double mean = cnt ? acc / cnt : NAN;                            // :278
+        if (mean >= 1.0) total += mean;                                       // :282
+    }
+    return total;
+}
+
+static double get_cqi(double lin, const double* table, int n) {  // cqiSelect.m:697-722
+    if (std::isnan(lin)) return NAN;
+    const double db = 10.0 * std::log10(lin);
+    int last = -1;
+    for (int i = 0; i < n; ++i)
+        if (table[i] <= db) last = i;
+    return last < 0 ? 0.0 : (double)(last + 1);
+}
+
+void cqi_from_pmi(const CsiConfig& cfg, int nu, const PmiResult& r, int nSB, int nCqiSB, const double* table, int tableLen,
+                  CsiReport& rep) {
+    const int nCW = (nu + 3) / 4;
+    rep.nCW = nCW;
+    std::vector<double> sbl((size_t)nCqiSB * nu, NAN);  // SINRperSubband [nCqiSB x nu]
+    if (!r.allNaN) {
+        if (!cfg.pmiSubband || nSB == 1) sbl = r.sinrWbSel;                   // cqiSelect.m:586-596
+        else sbl = r.sinrSel;                                                 // :604-614 (PMI subbands == CQI subbands)
+    }
+    std::vector<double> cw((size_t)nCqiSB * nCW);
+    for (int s = 0; s < nCqiSB; ++s) {                                        // :610-627
+        bool nan = false;
+        for (int l = 0; l < nu; ++l) nan |= std::isnan(sbl[(size_t)l * nCqiSB + s]);
+        for (int c = 0; c < nCW; ++c) {
+            if (nan) { cw[(size_t)c * nCqiSB + s] = NAN; continue; }
+            int lo = 0, hi = nu;
+            if (nCW == 2) { lo = c == 0 ? 0 : nu / 2; hi = c == 0 ? nu / 2 : nu; }  // nrLayerDemap (TS 38.211 Table 7.3.1.3-1)
+            double a = 0.0;
+            for (int l = lo; l < hi; ++l) a += sbl[(size_t)l * nCqiSB + s];
+            cw[(size_t)c * nCqiSB + s] = a;
+        }
+    }
+    std::vector<double> full;  // [rows x nCW]
+    int rows = nCqiSB;
+    if (nCqiSB > 1) {                                                         // :631-633 wideband row = omitnan mean
+        rows = nCqiSB + 1;
+        full.assign((size_t)rows * nCW, NAN);
+        for (int c = 0; c < nCW; ++c) {
+            double a = 0.0; int n = 0;
+            for (int s = 0; s < nCqiSB; ++s) { const double v = cw[(size_t)c * nCqiSB + s]; if (!std::isnan(v)) { a += v; ++n; } }
+            full[(size_t)c * rows] = n ? a / n : NAN;
+            for (int s = 0; s < nCqiSB; ++s) full[(size_t)c * rows + 1 + s] = cw[(size_t)c * nCqiSB + s];
+        }
+    } else full = cw;
+    if (r.allNaN) {                                                           // :636-650
+        const int ns = nCqiSB == 1 ? 0 : nCqiSB;
+        rep.nCqiRows = ns + 1;
+        rep.cqi.assign((size_t)(ns + 1) * nCW, NAN);
+        rep.sinrPerSubbandPerCW.assign((size_t)(ns + 1) * nCW, NAN);
+        return;
+    }
+    std::vector<double> cqAll(full.size());
+    for (size_t i = 0; i < full.size(); ++i) cqAll[i] = get_cqi(full[i], table, tableLen);   // :653
+    rep.sinrPerSubbandPerCW = full;
+    if (cfg.cqiSubband) {                                                     // :656-677
+        rep.nCqiRows = rows;
+        rep.cqi.assign((size_t)rows * nCW, NAN);
+        for (int c = 0; c < nCW; ++c) {
+            rep.cqi[(size_t)c * rows] = cqAll[(size_t)c * rows];
+            for (int s = 1; s < rows; ++s) {
+                const double d = cqAll[(size_t)c * rows + s] - cqAll[(size_t)c * rows];
+                double off = NAN;
+                if (d == 0) off = 0; else if (d == 1) off = 1; else if (d >= 2) off = 2; else if (d <= -1) off = 3;
+                rep.cqi[(size_t)c * rows + s] = off;
+            }
+        }
+    } else {
+        rep.nCqiRows = 1;
+        rep.cqi.resize(nCW);
+        for (int c = 0; c < nCW; ++c) rep.cqi[c] = cqAll[(size_t)c * rows];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// UL TPMI selection (pmiSelect.m:28-66)
+// ------------------------------------------------------------------------------------------
+template <int NU>
+__global__ void __launch_bounds__(128)
+ul_sinr_kernel(const float2* __restrict__ hest, int K, int nSym, int R, int P, const double2* __restrict__ W /*[P][NU][nT]*/,
+               int nT, double nVar, double* __restrict__ sinr /*[K*nSym][nT]*/) {
+    const long long re = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (re >= (long long)K * nSym) return;
+    double2 h[16 * 4];  // R <= 16, P <= 4
+    double sr = 0.0, si = 0.0;
+    for (int r = 0; r < R; ++r)
+        for (int p = 0; p < P; ++p) {
+            const float2 v = __ldg(hest + re + (long long)K * nSym * (r + (long long)R * p));
+            h[r * 4 + p] = make_double2((double)v.x, (double)v.y);
+            sr += v.x;
+            si += v.y;
+        }
+    const bool has = (sr != 0.0 || si != 0.0);  // find(sum(hest,3:4) ~= 0)  (pmiSelect.m:35)
+    for (int t = 0; t < nT; ++t) {
+        double out = 0.0;
+        if (has) {
+            double2 A[NU][NU];
+#pragma unroll
+            for (int i = 0; i < NU; ++i)
+#pragma unroll
+                for (int j = 0; j < NU; ++j) A[i][j] = make_double2(0.0, 0.0);
+            for (int r = 0; r < R; ++r) {
+                double2 g[NU];
+#pragma unroll
+                for (int j = 0; j < NU; ++j) {
+                    double2 acc = make_double2(0.0, 0.0);
+                    for (int p = 0; p < P; ++p) acc = zadd(acc, zmul(h[r * 4 + p], W[(t * NU + j) * P + p]));
+                    g[j] = acc;
+                }
+#pragma unroll
+                for (int i = 0; i < NU; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) A[i][j] = zadd(A[i][j], zmulc(g[j], g[i]));
+            }
+#pragma unroll
+            for (int i = 0; i < NU; ++i) A[i][i].x += nVar;
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+                double d = A[j][j].x;
+#pragma unroll
+                for (int k = 0; k < j; ++k) d -= A[j][k].x * A[j][k].x + A[j][k].y * A[j][k].y;
+                const double ljj = sqrt(d);
+                A[j][j] = make_double2(ljj, 0.0);
+                const double inv = 1.0 / ljj;
+#pragma unroll
+                for (int i = j + 1; i < NU; ++i) {
+                    double2 s = A[i][j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) s = zsub(s, zmulc(A[i][k], A[j][k]));
+                    A[i][j] = make_double2(s.x * inv, s.y * inv);
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < NU; ++cc) {
+                double2 x[NU];
+                x[cc] = make_double2(1.0 / A[cc][cc].x, 0.0);
+                double nrm = x[cc].x * x[cc].x;
+#pragma unroll
+                for (int i = cc + 1; i < NU; ++i) {
+                    double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int k = cc; k < i; ++k) s = zadd(s, zmul(A[i][k], x[k]));
+                    const double inv = -1.0 / A[i][i].x;
+                    x[i] = make_double2(s.x * inv, s.y * inv);
+                    nrm += x[i].x * x[i].x + x[i].y * x[i].y;
+                }
+                out += 1.0 / (nVar * nrm) - 1.0;  // sum over layers (precodedSINR.m:16)
+            }
+        }
+        sinr[re * nT + t] = out;
+    }
+}
+
+// sinrPerSubband (sinrPerSubband.m:26-34): one CTA per (band, tpmi)
+__global__ void __launch_bounds__(256)
+ul_band_kernel(const double* __restrict__ sinr, int K, int nSym, int nT, const int* __restrict__ bandLo,
+               const int* __restrict__ bandHi, double* __restrict__ out /*[nSB][nT]*/) {
+    const int sb = blockIdx.x, t = blockIdx.y;
+    double acc = 0.0;
+    long long cnt = 0;
+    const int lo = bandLo[sb] - 1, hi = bandHi[sb];  // 0-based [lo, hi)
+    for (long long i = threadIdx.x; i < (long long)(hi - lo) * nSym; i += blockDim.x) {
+        const int k = lo + (int)(i % (hi - lo)), l = (int)(i / (hi - lo));
+        const double* __restrict__ row = sinr + ((long long)k + (long long)K * l) * nT;
+        acc += row[t];
+        double s = 0.0;
+        for (int q = 0; q < nT; ++q) s += row[q];
+        cnt += (s != 0.0);
+    }
+    __shared__ double ra[8];
+    __shared__ long long rc[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) { ra[threadIdx.x >> 5] = acc; rc[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0; long long c = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += ra[w]; c += rc[w]; }
+        out[(long long)sb * nT + t] = a / (double)c;  // 0/0 -> NaN like MATLAB
+    }
+}
+
+int ul_pmi_select_run(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int R, int P, double noiseEst, int bandSize,
+                      UlPmiResult& out, cudaStream_t st) {
+    if (!hest || K < 12 || nSym < 1 || R < 1 || R > 16 || bandSize < 1) {
+        set_error(ctx, "pmiSelect: invalid argument");
+        return kErrInvalidArg;
+    }
+    CodebookTable t;
+    int s = build_pusch_table(ctx, nu, P, t);
+    if (s) return s;
+    const int nT = t.n2;
+    out = UlPmiResult();
+    out.nTPMI = nT;
+    const double nrb = K / 12.0, r = nrb / bandSize;
+    const int nSB = (int)std::ceil(r);
+    out.nSB = nSB;
+    std::vector<int> lo(nSB), hi(nSB);
+    for (int i = 0; i < nSB; ++i) {  // sinrPerSubband.m:20-21
+        lo[i] = 12 * bandSize * i + 1;
+        hi[i] = i < (int)std::floor(r) ? 12 * bandSize * (i + 1) : (int)(12 * bandSize * r);
+    }
+    out.subbandIndices.resize((size_t)nSB * 2);
+    for (int i = 0; i < nSB; ++i) { out.subbandIndices[i] = lo[i]; out.subbandIndices[nSB + i] = hi[i]; }
+    if (noiseEst == 0.0) { out.none = true; return kOk; }  // pmiSelect.m:39
+    std::vector<std::complex<double>> Wc;
+    materialize_codebook(t, Wc);  // [P][nu][nT]
+    std::vector<double2> Wd(Wc.size());
+    for (size_t i = 0; i < Wc.size(); ++i) Wd[i] = make_double2(Wc[i].real(), Wc[i].imag());
+    void *dW = nullptr, *dS = nullptr, *dB = nullptr, *dIdx = nullptr, *pin = nullptr;
+    if ((s = ctx_scratch(ctx, 2, sizeof(double2) * Wd.size(), &dW))) return s;
+    if ((s = ctx_scratch(ctx, 3, sizeof(double) * (size_t)K * nSym * nT, &dS))) return s;
+    if ((s = ctx_scratch(ctx, 4, sizeof(double) * (size_t)nSB * nT, &dB))) return s;
+    if ((s = ctx_scratch(ctx, 5, sizeof(int) * 2 * (size_t)nSB, &dIdx))) return s;
+    const size_t pinBytes = sizeof(double2) * Wd.size() + sizeof(int) * 2 * nSB;
+    if ((s = ctx_pinned(ctx, 4, pinBytes, &pin))) return s;
+    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    std::memcpy(pin, Wd.data(), sizeof(double2) * Wd.size());
+    int* pidx = (int*)((char*)pin + sizeof(double2) * Wd.size());
+    std::memcpy(pidx, lo.data(), sizeof(int) * nSB);
+    std::memcpy(pidx + nSB, hi.data(), sizeof(int) * nSB);
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(dW, pin, sizeof(double2) * Wd.size(), cudaMemcpyHostToDevice, st));
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(dIdx, pidx, sizeof(int) * 2 * nSB, cudaMemcpyHostToDevice, st));
+    const long long nre = (long long)K * nSym;
+    const unsigned blocks = (unsigned)((nre + 127) / 128);
+    const int pr = prof_begin(ctx, kProfUlPmi, st);
+    switch (nu) {
+        case 1: ul_sinr_kernel<1><<<blocks, 128, 0, st>>>(hest, K, nSym, R, P, (const double2*)dW, nT, noiseEst, (double*)dS); break;
+        case 2: ul_sinr_kernel<2><<<blocks, 128, 0, st>>>(hest, K, nSym, R, P, (const double2*)dW, nT, noiseEst, (double*)dS); break;
+        case 3: ul_sinr_kernel<3><<<blocks, 128, 0, st>>>(hest, K, nSym, R, P, (const double2*)dW, nT, noiseEst, (double*)dS); break;
+        default: ul_sinr_kernel<4><<<blocks, 128, 0, st>>>(hest, K, nSym, R, P, (const double2*)dW, nT, noiseEst, (double*)dS); break;
+    }
+    ISAC_CUDA_CHECK(ctx, cudaGetLastError());
+    dim3 g(nSB, nT);
+    ul_band_kernel<<<g, 256, 0, st>>>((const double*)dS, K, nSym, nT, (const int*)dIdx, (const int*)dIdx + nSB, (double*)dB);
+    prof_end(ctx, pr, st);
+    count_launches(ctx, 2);
+    ISAC_CUDA_CHECK(ctx, cudaGetLastError());
+    std::vector<double> bands((size_t)nSB * nT);
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(bands.data(), dB, sizeof(double) * bands.size(), cudaMemcpyDeviceToHost, st));
+    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    // "no channel estimates" <=> every band is 0/0 (pmiSelect.m:39,60-64)
+    bool any = false;
+    for (double v : bands) any |= !std::isnan(v);
+    if (!any) { out.none = true; return kOk; }
+    out.pmi.resize(nSB);
+    out.sinr.resize((size_t)nSB * nT);
+    for (int sb = 0; sb < nSB; ++sb) {
+        int best = 0;
+        for (int tt = 0; tt < nT; ++tt) {
+            out.sinr[(size_t)tt * nSB + sb] = bands[(size_t)sb * nT + tt];
+            if (bands[(size_t)sb * nT + tt] > bands[(size_t)sb * nT + best]) best = tt;  // first max (pmiSelect.m:56)
+        }
+        out.pmi[sb] = std::isnan(bands[(size_t)sb * nT]) ? NAN : (double)best;           // :57-58 (0-based)
+    }
+    return kOk;
+}
+
+// ------------------------------------------------------------------------------------------
+// PRG precoding (prgPrecode.m:53-144)
+// ------------------------------------------------------------------------------------------
+__global__ void prg_scatter_kernel(const float2* __restrict__ sym, const int* __restrict__ ind, long long n, long long plane,
+                                   int nu, float2* __restrict__ portgrid /*[plane][nu]*/) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long lin = (long long)ind[i] - 1;
+    const long long pos = lin % plane, layer = lin / plane;
+    if (layer < nu) portgrid[pos * nu + layer] = sym[i];  // portgrid(indin) = symin (prgPrecode.m:131)
+}
+
+__global__ void prg_apply_kernel(const float2* __restrict__ portgrid, const int* __restrict__ ind, int NRE, long long plane,
+                                 int K, int nu, const float2* __restrict__ F, int P, int NPRG, int nStartGrid, int Pd,
+                                 float2* __restrict__ antsym, int* __restrict__ antind) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)NRE * P) return;
+    const int i = (int)(gid % NRE), p = (int)(gid / NRE);
+    const long long pos = ((long long)ind[i] - 1) % plane;  // RE position of the first layer's index
+    const int k = (int)(pos % K);
+    const int prg = (nStartGrid + k / 12) / Pd;             // getPRGSet (prgPrecode.m:94-100), 0-based
+    float2 acc = make_float2(0.f, 0.f);
+    for (int l = 0; l < nu; ++l) {
+        const float2 x = portgrid[pos * nu + l], f = __ldg(F + l + nu * (p + (long long)P * prg));
+        acc.x += x.x * f.x - x.y * f.y;                     // portgrid * F(:,:,prg) (prgPrecode.m:134)
+        acc.y += x.x * f.y + x.y * f.x;
+    }
+    antsym[gid] = acc;
+    antind[gid] = (int)(pos + 1 + plane * p);
+}
+
+int prg_precode_run(Ctx* ctx, int K, int Lsym, int nStartGrid, const float2* portsym, const int* portind, int NRE, int nu,
+                    const float2* F, int P, int NPRG, float2* antsym, int* antind, cudaStream_t st) {
+    if (!portsym || !portind || !F || !antsym || !antind || K < 12 || K % 12 || Lsym < 1 || nu < 1 || P < 1 || NPRG < 1 || NRE < 0) {
+        set_error(ctx, "prgPrecode: invalid argument");
+        return kErrInvalidArg;
+    }
+    if (NRE == 0) return kOk;
+    const long long plane = (long long)K * Lsym;
+    void* grid = nullptr;
+    int s = ctx_scratch(ctx, 6, sizeof(float2) * plane * nu, &grid);
+    if (s) return s;
+    const int nrb = K / 12;
+    const int Pd = (nrb + nStartGrid + NPRG - 1) / NPRG;  // Pd_BWP = ceil((NRB+nstartgrid)/NPRG)
+    const int pr = prof_begin(ctx, kProfPrecode, st);
+    ISAC_CUDA_CHECK(ctx, cudaMemsetAsync(grid, 0, sizeof(float2) * plane * nu, st));
+    const long long n = (long long)NRE * nu;
+    prg_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(portsym, portind, n, plane, nu, (float2*)grid);
+    const long long m = (long long)NRE * P;
+    prg_apply_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>((const float2*)grid, portind, NRE, plane, K, nu, F, P, NPRG,
+                                                                nStartGrid, Pd, antsym, antind);
+    prof_end(ctx, pr, st);
+    count_launches(ctx, 2);
+    ISAC_CUDA_CHECK(ctx, cudaGetLastError());
+    return kOk;
+}
+
+}  // namespace isac

@@ -1,0 +1,86 @@
+// K8-K10, K12: Type-I PMI / RI / CQI selection, UL TPMI selection, PRG precoding.
+#pragma once
+#include "codebook.cuh"
+#include <vector>
+
+namespace isac {
+
+// results of one dlPMISelect evaluation for one UE (host side)
+struct PmiResult {
+    bool allNaN = false;             // no CSI-RS RE in the BWP / everything restricted
+    int i1[3] = {0, 0, 0};           // 1-based [i11 i12 i13]
+    std::vector<double> i2;          // per subband, 1-based, NaN where CSI-RS is absent
+    std::vector<double> sinrSel;     // [nSB x nLayers] SINRPerSubband at the reported PMI (NaN rows as above)
+    std::vector<double> sinrWbSel;   // [nCqiSB x nLayers] per-CQI-subband SINR with a single (wideband) i2 (cqiSelect.m:586-596)
+};
+
+// Device plan for one (report configuration, rank): codebook tables + work buffers for `maxBatch` UEs.
+struct PmiPlan {
+    Ctx* ctx = nullptr;
+    CsiConfig cfg{};
+    std::vector<int> reK, reL;
+    std::vector<uint8_t> csr, i2r;
+    int nLayers = 0, maxBatch = 0;
+    CodebookTable tab;
+    std::vector<int> sbSizes, cqiSbSizes;  // PMI / CQI subband sizes in PRBs
+    int nSB = 0, nCqiSB = 0;
+    // device
+    double2* d_beams = nullptr;
+    int* d_layerBeam = nullptr;     // [nCand*nLayers]
+    double2* d_layerCoef = nullptr; // [nCand*nLayers*NB]
+    double* d_candScale = nullptr;  // [nCand]
+    uint8_t* d_valid = nullptr;     // [nCand]
+    int* d_reK = nullptr; int* d_reL = nullptr;
+    int* d_reSb = nullptr;          // PMI subband of each RE
+    double* d_reW = nullptr;        // mean-of-means weight of each RE within its PMI subband
+    int* d_reCqiSb = nullptr;       // CQI subband of each RE
+    double* d_reCqiW = nullptr;
+    double* d_S = nullptr;          // SINRPerRE compact [nCand][nLayers][nRE][batch]
+    double* d_total = nullptr;      // [nCand][batch]
+    double* d_sub = nullptr;        // SINRPerSubband [nCand][nLayers][nSB][batch]
+    int* d_sel = nullptr;           // [4 + nSB][batch]: allNaN flag, i11, i12, i13 (0-based), i2 per subband (0-based, -1 = NaN)
+    double* d_sinrSel = nullptr;    // [nLayers][nSB][batch]
+    double* d_sinrWb = nullptr;     // [nLayers][nCqiSB][batch]
+    int* d_sbStart = nullptr;       // [nSB+1] RE ranges of the PMI subbands (REs sorted by subcarrier)
+    int* d_cqiStart = nullptr;      // [nCqiSB+1]
+    double* d_nVar = nullptr;       // [batch]
+    std::vector<uint8_t> sbHasRE, cqiSbHasRE;
+};
+
+int pmi_plan_create(Ctx* ctx, const CsiConfig& cfg, int nLayers, int maxBatch, PmiPlan** out);
+void pmi_plan_destroy(PmiPlan* p);
+// H: device complex64 [K x L x nRx x P x batch]; nVar: host [batch]
+int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, cudaStream_t st);
+int pmi_select_collect(PmiPlan* p, int batch, std::vector<PmiResult>& out);   // synchronises
+// optional big outputs of the last run (host): SINRPerRE [nRE x nLayers x nCand x batch], SINRPerSubband [nSB x nLayers x nCand x batch]
+int pmi_get_sinr_arrays(PmiPlan* p, int batch, double* sinrPerRE, double* sinrPerSubband);
+
+// riSelect (riSelect.m:254-294) and cqiSelect tail (cqiSelect.m:610-695) on the host from PmiResults
+struct CsiReport {
+    double RI = NAN;
+    PmiResult pmi;                   // at the reported rank
+    std::vector<double> cqi;         // [(nCqiSB+1 or 1) x nCW] column-major
+    std::vector<double> sinrPerSubbandPerCW;
+    int nCqiRows = 0, nCW = 0;
+};
+double ri_total_sinr(const PmiResult& r, int nSB, int rank);   // totalSINR(rankIdx) of riSelect.m:266-282
+void cqi_from_pmi(const CsiConfig& cfg, int nLayers, const PmiResult& r, int nSB, int nCqiSB, const double* sinrTable,
+                  int tableLen, CsiReport& rep);
+
+// UL: pmiSelect (pmiSelect.m:28-66).  hest device complex64 [K x nSym x nRx x P]
+struct UlPmiResult {
+    bool none = false;               // no estimates / zero noise -> NaN outputs
+    std::vector<double> pmi;         // [nSB] 0-based TPMI or NaN
+    std::vector<double> sinr;        // [nSB x nTPMI] column-major
+    std::vector<int> subbandIndices; // [nSB x 2] column-major, 1-based subcarriers
+    int nSB = 0, nTPMI = 0;
+};
+int ul_pmi_select_run(Ctx* ctx, int nLayers, const float2* hest, int K, int nSym, int nRx, int P, double noiseEst,
+                      int bandSize, UlPmiResult& out, cudaStream_t st);
+
+// prgPrecode (prgPrecode.m:53-144): portsym/portind [NRE x nLayers], F [nLayers x P x NPRG] (device);
+// antsym [NRE x P] complex64, antind [NRE x P] int32 (1-based).  scratch grid owned by ctx.
+int prg_precode_run(Ctx* ctx, int K, int Lsym, int nStartGrid, const float2* portsym, const int* portind, int NRE,
+                    int nLayers, const float2* F, int P, int NPRG, float2* antsym, int* antind, cudaStream_t st);
+
+}  // namespace isac

@@ -196,6 +196,82 @@ int isac_mono_static_sensing_host(isac_ctx* ctx, const isac_echo_config* cfg, co
                                   const void* noiseHost, int32_t noiseMode, uint64_t seed, void* echoGridHost,
                                   int32_t* nSymOut);
 
+/* ---- K7-K10, K12: Type-I codebook, PMI / RI / CQI selection, UL TPMI selection, PRG precoding --------- */
+typedef struct {
+    int32_t nPorts;                    /* csirs.NumCSIRSPorts                                  dlPMISelect.m:326 */
+    int32_t N1, N2, O1, O2;            /* PanelDimensions, OverSamplingFactors (TS 38.214 Table 5.2.2.2.1-2)  :604-644 */
+    int32_t codebookMode;              /* reportConfig.CodebookMode (1|2)                       :583-590 */
+    int32_t nSizeBWP, nStartBWP;       /* reportConfig.NSizeBWP / NStartBWP (relative to the carrier start)  :536-569 */
+    int32_t subbandSize;               /* reportConfig.SubbandSize (0 when not applicable)      :705-742 */
+    int32_t pmiSubband, cqiSubband;    /* PMIMode / CQIMode == 'Subband'                         :683-688, cqiSelect.m:865 */
+    int32_t K, L;                      /* carrier.NSizeGrid*12, carrier.SymbolsPerSlot          :829-831 */
+    int32_t nRx;                       /* size(H,3) */
+    const uint8_t* subsetRestriction;  /* CodebookSubsetRestriction bits, NULL = all ones       :744-764 */
+    const uint8_t* i2Restriction;      /* 16 bits, NULL = all ones                              :766-775 */
+    uint8_t riRestriction[8];          /* RIRestriction                                         riSelect.m:440-447 */
+    int32_t nRE;                       /* CSI-RS REs kept by validateInputs (port 1, lowest RE of each CDM group)  :797-833 */
+    const int32_t* reK;                /* 1-based subcarrier subscripts relative to the BWP     :352-356 */
+    const int32_t* reL;                /* 1-based OFDM symbol subscripts */
+} isac_csi_config;
+
+/* W = getPMIType1SinglePanelCodebook(reportConfig,nLayers) (dlPMISelect.m:853; variant 0) or
+ * communication.pmiType1SinglePanelCodebook(reportConfig,nLayers) (pmiType1SinglePanelCodebook.m:1; variant 1,
+ * including that copy's deviations).  dims = [i2 i11 i12 i13] lengths; W complex128 [P x nLayers x prod(dims)]
+ * (NULL to query dims).  Pure host code: works without a GPU. */
+int isac_type1sp_codebook(const isac_csi_config* cfg, int32_t nLayers, int32_t variant, int32_t dims[4], double* W);
+/* nrPUSCHCodebook(nlayers,nports,tpmi).' for tpmi = 0..maxTPMI (pmiSelect.m:45; TS 38.211 Tables 6.3.1.5-1..7);
+ * W complex128 [nPorts x nLayers x nTPMI] (NULL to query nTPMI). */
+int isac_pusch_codebook(int32_t nLayers, int32_t nPorts, int32_t* nTPMI, double* W);
+
+typedef struct isac_pmi_plan isac_pmi_plan;
+/* [PMISet,info] = communication.phyLayer.dlPMISelect(carrier,csirs,reportConfig,nLayers,H,nVar) (dlPMISelect.m:1) */
+int isac_pmi_plan_create(isac_ctx* ctx, const isac_csi_config* cfg, int32_t nLayers, int32_t maxBatch, isac_pmi_plan** plan);
+int isac_pmi_plan_destroy(isac_pmi_plan* plan);
+/* dims = [i2 i11 i12 i13]; REs sorted by subcarrier as the plan stores them (reKs/reLs may be NULL) */
+int isac_pmi_plan_info(const isac_pmi_plan* plan, int32_t dims[4], int32_t* nSB, int32_t* nCqiSB, int32_t* nRE,
+                       int32_t* reKs, int32_t* reLs);
+/* H: device complex64 [K x L x nRx x nPorts x batch]; nVar: host double[batch] */
+int isac_dl_pmi_select_dev(isac_pmi_plan* plan, const void* H, const double* nVar, int32_t batch);
+/* PMISet of the last run: i1 [3 x batch], i2 [nSB x batch] (1-based, NaN = not reported);
+ * sinrAtPmi [nSB x nLayers x batch] = info.SINRPerSubband at the reported indices (may be NULL) */
+int isac_dl_pmi_collect(isac_pmi_plan* plan, int32_t batch, double* i1, double* i2, double* sinrAtPmi);
+/* info.SINRPerRE at the CSI-RS REs [nRE x nLayers x nCand x batch] and info.SINRPerSubband
+ * [nSB x nLayers x nCand x batch] (nCand = prod(dims), MATLAB index order); either may be NULL */
+int isac_dl_pmi_get_info(isac_pmi_plan* plan, int32_t batch, double* sinrPerRE, double* sinrPerSubband);
+
+typedef struct isac_csi_plan isac_csi_plan;
+/* One plan per report configuration: holds the per-rank PMI plans (riSelect.m:254 loops over the valid ranks). */
+int isac_csi_plan_create(isac_ctx* ctx, const isac_csi_config* cfg, int32_t maxBatch, isac_csi_plan** plan);
+int isac_csi_plan_destroy(isac_csi_plan* plan);
+/* [RI,PMISet] = communication.phyLayer.riSelect(carrier,csirs,reportConfig,H,nVar) (riSelect.m:1).
+ * RI [batch] (NaN when nothing is reportable), i1 [3 x batch], i2 [nSB x batch]. */
+int isac_ri_select_dev(isac_csi_plan* plan, const void* H, const double* nVar, int32_t batch, double* RI, double* i1,
+                       double* i2);
+/* [CQI,PMISet,..] = communication.phyLayer.cqiSelect(carrier,csirs,reportConfig,nLayers,H,nVar,SINRTable)
+ * (cqiSelect.m:1).  cqi [cqiRows x 2 x batch] (second codeword column NaN when nLayers <= 4), *cqiRows =
+ * nCqiSB+1 in subband CQI mode else 1; sinrPerSubbandPerCW same shape with (nCqiSB+1) rows when nCqiSB > 1. */
+int isac_cqi_select_dev(isac_csi_plan* plan, int32_t nLayers, const void* H, const double* nVar, int32_t batch,
+                        const double* sinrTable, int32_t tableLen, double* cqi, int32_t* cqiRows, double* i1, double* i2,
+                        double* sinrPerSubbandPerCW);
+/* Fused UE CSI report (uePhy.m:900-907): rank = min(riSelect(..), rankCap) then cqiSelect at that rank, without
+ * re-evaluating the rank already scored by the RI loop.  rankCap <= 0 disables the cap. */
+int isac_csi_report_dev(isac_csi_plan* plan, const void* H, const double* nVar, int32_t batch, const double* sinrTable,
+                        int32_t tableLen, int32_t rankCap, double* RI, double* i1, double* i2, double* cqi,
+                        int32_t* cqiRows);
+
+/* [pmi,sinr,subbandIndices] = communication.phyLayer.pmiSelect(nlayers,hest,noiseest,bandSize) (pmiSelect.m:28).
+ * hest: device complex64 [K x nSym x nRx x nPorts].  pmi [nSB] 0-based TPMI (NaN), sinr [nSB x nTPMI],
+ * subbandIndices [nSB x 2].  *none = 1 reproduces the reference's scalar-NaN outputs (pmiSelect.m:60-64). */
+int isac_ul_pmi_select_dev(isac_ctx* ctx, int32_t nLayers, const void* hest, int32_t K, int32_t nSym, int32_t nRx,
+                           int32_t nPorts, double noiseEst, int32_t bandSize, int32_t maxSB, double* pmi, double* sinr,
+                           int32_t* subbandIndices, int32_t* nSB, int32_t* nTPMI, int32_t* none);
+/* [antsym,antind] = communication.phyLayer.prgPrecode(siz,nstartgrid,portsym,portind,F) (prgPrecode.m:53).
+ * portsym complex64 / portind int32 (1-based) [NRE x nLayers], F complex64 [nLayers x P x NPRG] (device);
+ * antsym complex64 / antind int32 [NRE x P] (device). */
+int isac_prg_precode_dev(isac_ctx* ctx, int32_t K, int32_t Lsym, int32_t nStartGrid, const void* portsym,
+                         const int32_t* portind, int32_t NRE, int32_t nLayers, const void* F, int32_t P, int32_t NPRG,
+                         void* antsym, int32_t* antind);
+
 #ifdef __cplusplus
 }
 #endif
