@@ -80,6 +80,14 @@ class CsiConfig(C.Structure):
     ]
 
 
+class CdlConfig(C.Structure):
+    _fields_ = [
+        ("profile", C.c_int32), ("delaySpread", C.c_double), ("fc", C.c_double), ("maxDoppler", C.c_double),
+        ("txSize", C.c_int32 * 3), ("rxSize", C.c_int32 * 3), ("txPattern38901", C.c_int32),
+        ("rxPattern38901", C.c_int32), ("seed", C.c_uint64),
+    ]
+
+
 NOISE_NONE, NOISE_TENSOR, NOISE_PHILOX = 0, 1, 2
 MAX_PEAKS = 64
 
@@ -132,6 +140,10 @@ def _declare(lib):
         "isac_ul_pmi_select_dev": ([vp, i32, vp, i32, i32, i32, i32, f64, i32, i32, vp, vp, vp, P(i32), P(i32), P(i32)],
                                    C.c_int),
         "isac_prg_precode_dev": ([vp, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, vp, vp], C.c_int),
+        "isac_cdl_create": ([vp, P(CdlConfig), P(vp)], C.c_int),
+        "isac_cdl_destroy": ([vp], C.c_int),
+        "isac_cdl_get_rays": ([vp, P(i32), P(i32), P(i32), P(i32), vp, vp, vp, vp], C.c_int),
+        "isac_cdl_generate_dev": ([vp, i32, f64, i32, vp, f64, vp], C.c_int),
         "isac_radar_channel_dev": ([vp, P(EchoConfig), vp, vp, i32, C.c_uint64, vp], C.c_int),
         "isac_mono_static_sensing_dev": ([vp, P(EchoConfig), vp, vp, i32, C.c_uint64, vp, P(i32)], C.c_int),
         "isac_mono_static_sensing_host": ([vp, P(EchoConfig), vp, vp, i32, C.c_uint64, vp, P(i32)], C.c_int),

@@ -6,6 +6,7 @@
 #include "sense.cuh"
 #include "echo.cuh"
 #include "comm.cuh"
+#include "cdl.cuh"
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -901,6 +902,53 @@ int isac_prg_precode_dev(isac_ctx* h, int32_t K, int32_t Lsym, int32_t nStartGri
     cudaSetDevice(c->device);
     return prg_precode_run(c, K, Lsym, nStartGrid, (const float2*)portsym, portind, NRE, nLayers, (const float2*)F, P, NPRG,
                            (float2*)antsym, antind, c->stream);
+}
+
+// ---- CDL channel ---------------------------------------------------------------------------------
+struct isac_cdl_channel {
+    Ctx* ctx;
+    CdlRays rays;
+};
+
+int isac_cdl_create(isac_ctx* h, const isac_cdl_config* cfg, isac_cdl_channel** out) {
+    if (!h || !cfg || !out) return ISAC_ERR_INVALID_ARG;
+    CdlConfig c{};
+    c.profile = cfg->profile; c.delaySpread = cfg->delaySpread; c.fc = cfg->fc; c.maxDoppler = cfg->maxDoppler;
+    for (int i = 0; i < 3; ++i) { c.txSize[i] = cfg->txSize[i]; c.rxSize[i] = cfg->rxSize[i]; }
+    c.txPattern38901 = cfg->txPattern38901; c.rxPattern38901 = cfg->rxPattern38901; c.seed = cfg->seed;
+    isac_cdl_channel* ch = new isac_cdl_channel();
+    ch->ctx = &h->c;
+    int st = cdl_build_rays(&h->c, c, ch->rays);
+    if (st) { delete ch; return st; }
+    *out = ch;
+    return ISAC_OK;
+}
+
+int isac_cdl_destroy(isac_cdl_channel* ch) {
+    delete ch;
+    return ISAC_OK;
+}
+
+int isac_cdl_get_rays(const isac_cdl_channel* ch, int32_t* nCl, int32_t* nRays, int32_t* nRx, int32_t* nTx, double* tau,
+                      double* nu, int32_t* cluster, double* g) {
+    if (!ch) return ISAC_ERR_INVALID_ARG;
+    const CdlRays& r = ch->rays;
+    if (nCl) *nCl = r.nCl;
+    if (nRays) *nRays = (int32_t)r.nu.size();
+    if (nRx) *nRx = r.nRx;
+    if (nTx) *nTx = r.nTx;
+    if (tau) std::memcpy(tau, r.tau.data(), sizeof(double) * r.tau.size());
+    if (nu) std::memcpy(nu, r.nu.data(), sizeof(double) * r.nu.size());
+    if (cluster) std::memcpy(cluster, r.cluster.data(), sizeof(int) * r.cluster.size());
+    if (g) std::memcpy(g, r.g.data(), sizeof(std::complex<double>) * r.g.size());
+    return ISAC_OK;
+}
+
+int isac_cdl_generate_dev(isac_cdl_channel* ch, int32_t K, double scsHz, int32_t L, const double* symTime, double t0, void* H) {
+    if (!ch || !H || !symTime) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = ch->ctx;
+    cudaSetDevice(c->device);
+    return cdl_generate(c, ch->rays, K, scsHz, L, symTime, t0, (float2*)H, c->stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,273 @@
+// K11: CDL frequency-response generator (TR 38.901 7.7.1, steps of 7.5 for fixed angles).
+//
+// The reference filters time-domain waveforms through the toolbox's nrCDLChannel (uePhy.m:731, gNBPhy.m:840,
+// objects built at +parameters/+channelModels/+communication/cdl.m:48-88) and recovers H with
+// nrChannelEstimate (uePhy.m:897).  This kernel produces the channel matrix H[K x L x nRx x nTx] directly in
+// the frequency domain.  PARITY: statistical only — the toolbox's source and its mt19937 ray-coupling /
+// initial-phase draws are not reproducible here; tables are TR 38.901 Tables 7.7.1-1/-3/-4 and 7.5-3.
+//
+// Host (float64, tiny): per-ray static coefficients g_m[u,s] (field patterns, XPR matrix, array phases, power)
+// and Dopplers.  Device: (1) C_n[l,u,s] = sum_{m in n} g_m[u,s] e^{2 pi j nu_m t_l}; (2) the write-bound
+// contraction H[k,(l,u,s)] = sum_n e^{-2 pi j f_k tau_n} C_n[(l,u,s)] (contraction length = #clusters <= 24).
+#include "cdl.cuh"
+#include "ctx.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace isac {
+
+namespace {
+struct Row { double delay, powerdB, aod, aoa, zod, zoa; };
+struct Profile { std::vector<Row> rows; double cASD, cASA, cZSD, cZSA, xprdB; bool los; double losPowerdB; };
+
+const Profile& profile_table(int id) {
+    static const Profile A{{{0.0000,-13.4,-178.1,51.3,50.2,125.4},{0.3819,0,-4.2,-152.7,93.2,91.3},{0.4025,-2.2,-4.2,-152.7,93.2,91.3},
+        {0.5868,-4,-4.2,-152.7,93.2,91.3},{0.4610,-6,90.2,76.6,122,94},{0.5375,-8.2,90.2,76.6,122,94},{0.6708,-9.9,90.2,76.6,122,94},
+        {0.5750,-10.5,121.5,-1.8,150.2,47.1},{0.7618,-7.5,-81.7,-41.9,55.2,56},{1.5375,-15.9,158.4,94.2,26.4,30.1},
+        {1.8978,-6.6,-83,51.9,126.4,58.8},{2.2242,-16.7,134.8,-115.9,171.6,26},{2.1718,-12.4,-153,26.6,151.4,49.2},
+        {2.4942,-15.2,-172,76.6,157.2,143.1},{2.5119,-10.8,-129.9,-7,47.2,117.4},{3.0582,-11.3,-136,-23,40.4,122.7},
+        {4.0810,-12.7,165.4,-47.2,43.3,123.2},{4.4579,-16.2,148.4,110.4,161.8,32.6},{4.5695,-18.3,132.7,144.5,10.8,27.2},
+        {4.7966,-18.9,-118.6,155.3,16.7,15.2},{5.0066,-16.6,-154.1,102,171.7,146},{5.3043,-19.9,126.5,-151.8,22.7,150.7},
+        {9.6586,-29.7,-56.2,55.2,144.9,156.1}}, 5, 11, 3, 3, 10, false, 0};
+    static const Profile Cc{{{0,-4.4,-46.6,-101,97.2,87.6},{0.2099,-1.2,-22.8,120,98.6,72.1},{0.2219,-3.5,-22.8,120,98.6,72.1},
+        {0.2329,-5.2,-22.8,120,98.6,72.1},{0.2176,-2.5,-40.7,-127.5,100.6,70.1},{0.6366,0,0.3,170.4,99.2,75.3},
+        {0.6448,-2.2,0.3,170.4,99.2,75.3},{0.6560,-3.9,0.3,170.4,99.2,75.3},{0.6584,-7.4,73.1,55.4,105.2,67.4},
+        {0.7935,-7.1,-64.5,66.5,95.3,63.8},{0.8213,-10.7,80.2,-48.1,106.1,71.4},{0.9336,-11.1,-97.1,46.9,93.5,60.5},
+        {1.2285,-5.1,-55.3,68.1,103.7,90.6},{1.3083,-6.8,-64.3,-68.7,104.2,60.1},{2.1704,-8.7,-78.5,81.5,93.0,61.0},
+        {2.7105,-13.2,102.7,30.7,104.2,100.7},{4.2589,-13.9,99.2,-16.4,94.9,62.3},{4.6003,-13.9,88.8,3.8,93.1,66.7},
+        {5.4902,-15.8,-101.9,-13.7,92.2,52.9},{5.6077,-17.1,92.2,9.7,106.7,61.8},{6.3065,-16,93.3,5.6,93.0,51.9},
+        {6.6374,-15.7,106.6,0.7,92.9,61.7},{7.0427,-21.6,119.5,-21.9,105.2,58},{8.6523,-22.8,-123.8,33.6,107.8,57}},
+        2, 15, 3, 7, 7, false, 0};
+    static const Profile D{{{0,-13.5,0,-180,98.5,81.5},{0.035,-18.8,89.2,89.2,85.5,86.9},{0.612,-21,89.2,89.2,85.5,86.9},
+        {1.363,-22.8,89.2,89.2,85.5,86.9},{1.405,-17.9,13,163,97.5,79.4},{1.804,-20.1,13,163,97.5,79.4},{2.596,-21.9,13,163,97.5,79.4},
+        {1.775,-22.9,34.6,-137,98.5,78.2},{4.042,-27.8,-64.5,74.5,88.4,73.6},{7.937,-23.6,-32.9,127.7,91.3,78.3},
+        {9.424,-24.8,52.6,-119.6,103.8,87},{9.708,-30.0,-132.1,-9.1,80.3,70.6},{12.525,-27.7,77.2,-83.8,86.5,72.9}},
+        5, 8, 3, 3, 11, true, -0.2};
+    return id == 0 ? A : (id == 2 ? Cc : D);
+}
+
+// splitmix64: the documented generator of the ray coupling / initial phases (restated in oracle/cdl.py)
+struct SplitMix {
+    unsigned long long s;
+    unsigned long long next() {
+        unsigned long long z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }  // [0,1)
+};
+
+// TR 38.901 Table 7.3-1 element power pattern (linear), theta = zenith, phi = azimuth in degrees
+double pattern38901(double theta, double phi) {
+    auto wrap = [](double a) { a = std::fmod(a + 180.0, 360.0); if (a < 0) a += 360.0; return a - 180.0; };
+    const double ph = wrap(phi);
+    const double av = -std::min(12.0 * ((theta - 90.0) / 65.0) * ((theta - 90.0) / 65.0), 30.0);
+    const double ah = -std::min(12.0 * (ph / 65.0) * (ph / 65.0), 30.0);
+    const double a = -std::min(-(av + ah), 30.0) + 8.0;  // 8 dBi maximum gain
+    return std::pow(10.0, a / 10.0);
+}
+}  // namespace
+
+int cdl_build_rays(Ctx* ctx, const CdlConfig& c, CdlRays& r) {
+    if (!(c.profile == 0 || c.profile == 2 || c.profile == 3)) {
+        set_error(ctx, "CDL: only CDL-A, CDL-C and CDL-D are tabulated");
+        return kErrUnsupported;
+    }
+    for (int i = 0; i < 3; ++i)
+        if (c.txSize[i] < 1 || c.rxSize[i] < 1 || (i == 2 && (c.txSize[i] > 2 || c.rxSize[i] > 2))) {
+            set_error(ctx, "CDL: invalid antenna array size");
+            return kErrInvalidArg;
+        }
+    const Profile& p = profile_table(c.profile);
+    static const double alpha[20] = {0.0447, -0.0447, 0.1413, -0.1413, 0.2492, -0.2492, 0.3715, -0.3715, 0.5129, -0.5129,
+                                     0.6797, -0.6797, 0.8844, -0.8844, 1.1481, -1.1481, 1.5195, -1.5195, 2.1551, -2.1551};
+    const int nCl = (int)p.rows.size(), M = 20;
+    const int nTx = c.txSize[0] * c.txSize[1] * c.txSize[2], nRx = c.rxSize[0] * c.rxSize[1] * c.rxSize[2];
+    r = CdlRays();
+    r.nCl = nCl; r.nRay = M; r.nRx = nRx; r.nTx = nTx; r.los = p.los;
+    // powers, normalised so that all path gains sum to 1 (NormalizePathGains)
+    std::vector<double> pw(nCl);
+    double tot = 0.0, plos = p.los ? std::pow(10.0, p.losPowerdB / 10.0) : 0.0;
+    for (int n = 0; n < nCl; ++n) { pw[n] = std::pow(10.0, p.rows[n].powerdB / 10.0); tot += pw[n]; }
+    tot += plos;
+    for (int n = 0; n < nCl; ++n) pw[n] /= tot;
+    plos /= tot;
+    r.power = pw;
+    r.tau.resize(nCl);
+    for (int n = 0; n < nCl; ++n) r.tau[n] = p.rows[n].delay * c.delaySpread;
+    const double kappa = std::pow(10.0, p.xprdB / 10.0);
+    const double deg = M_PI / 180.0;
+    auto elemPos = [](const int size[3], int e, double& y, double& z, int& pol) {
+        const int m = e % size[0], n = (e / size[0]) % size[1];
+        pol = e / (size[0] * size[1]);
+        y = 0.5 * n;  // columns along y, rows along z, half-wavelength spacing (toolbox default [0.5 0.5 1 1])
+        z = 0.5 * m;
+    };
+    auto field = [&](bool pat, int npol, int pol, double theta, double phi, double& Ft, double& Fp) {
+        const double a = pat ? std::sqrt(pattern38901(theta, phi)) : 1.0;
+        const double zeta = npol == 2 ? (pol == 0 ? 45.0 : -45.0) : 0.0;  // PolarizationAngles [45 -45]; single pol: vertical
+        Ft = a * std::cos(zeta * deg);  // polarisation model 2 (TR 38.901 7.3.2)
+        Fp = a * std::sin(zeta * deg);
+    };
+    SplitMix rng{c.seed};
+    const int nRaysTot = nCl * M + (p.los ? 1 : 0);
+    r.g.assign((size_t)nRaysTot * nRx * nTx, 0.0);
+    r.nu.assign(nRaysTot, 0.0);
+    r.cluster.assign(nRaysTot, 0);
+    auto ray = [&](int idx, int cl, double amp, double aod, double aoa, double zod, double zoa, const std::complex<double> X[4]) {
+        r.cluster[idx] = cl;
+        r.nu[idx] = c.maxDoppler * std::sin(zoa * deg) * std::cos(aoa * deg);  // UT travels along +x (UTDirectionOfTravel [0;90])
+        const double rxv[3] = {std::sin(zoa * deg) * std::cos(aoa * deg), std::sin(zoa * deg) * std::sin(aoa * deg), std::cos(zoa * deg)};
+        const double txv[3] = {std::sin(zod * deg) * std::cos(aod * deg), std::sin(zod * deg) * std::sin(aod * deg), std::cos(zod * deg)};
+        for (int u = 0; u < nRx; ++u) {
+            double yu, zu; int pu;
+            elemPos(c.rxSize, u, yu, zu, pu);
+            double Frt, Frp;
+            field(c.rxPattern38901 != 0, c.rxSize[2], pu, zoa, aoa, Frt, Frp);
+            const double phr = 2.0 * M_PI * (rxv[1] * yu + rxv[2] * zu);
+            for (int s = 0; s < nTx; ++s) {
+                double ys, zs; int ps;
+                elemPos(c.txSize, s, ys, zs, ps);
+                double Ftt, Ftp;
+                field(c.txPattern38901 != 0, c.txSize[2], ps, zod, aod, Ftt, Ftp);
+                const double pht = 2.0 * M_PI * (txv[1] * ys + txv[2] * zs);
+                const std::complex<double> pol = Frt * (X[0] * Ftt + X[1] * Ftp) + Frp * (X[2] * Ftt + X[3] * Ftp);
+                r.g[((size_t)idx * nRx + u) * nTx + s] = amp * pol * std::polar(1.0, phr + pht) / std::sqrt((double)nRx);  // NormalizeChannelOutputs
+            }
+        }
+    };
+    for (int n = 0; n < nCl; ++n) {
+        // random coupling of the rays within the cluster (TR 38.901 7.5 step 8): permutations for AOA, ZOD, ZOA
+        int perm[3][20];
+        for (int q = 0; q < 3; ++q) {
+            for (int m = 0; m < M; ++m) perm[q][m] = m;
+            for (int m = M - 1; m > 0; --m) {
+                const int j = (int)(rng.uniform() * (m + 1));
+                std::swap(perm[q][m], perm[q][j]);
+            }
+        }
+        for (int m = 0; m < M; ++m) {
+            std::complex<double> X[4];
+            for (int q = 0; q < 4; ++q) X[q] = std::polar(1.0, (2.0 * rng.uniform() - 1.0) * M_PI);  // initial phases (step 10)
+            X[1] *= std::sqrt(1.0 / kappa);
+            X[2] *= std::sqrt(1.0 / kappa);
+            const Row& row = p.rows[n];
+            ray(n * M + m, n, std::sqrt(pw[n] / M), row.aod + p.cASD * alpha[m], row.aoa + p.cASA * alpha[perm[0][m]],
+                row.zod + p.cZSD * alpha[perm[1][m]], row.zoa + p.cZSA * alpha[perm[2][m]], X);
+        }
+    }
+    if (p.los) {  // specular ray of cluster 1: XPR matrix diag(1,-1) (TR 38.901 eq. 7.5-29)
+        const std::complex<double> X[4] = {1.0, 0.0, 0.0, -1.0};
+        const Row& row = p.rows[0];
+        ray(nCl * M, 0, std::sqrt(plos), row.aod, row.aoa, row.zod, row.zoa, X);
+    }
+    return kOk;
+}
+
+// C_n[l,u,s] = sum_{m in n} g_m[u,s] exp(2 pi j nu_m t_l)
+__global__ void cdl_cluster_kernel(const double2* __restrict__ g, const double* __restrict__ nu, const int* __restrict__ cl,
+                                   int nRays, int nCl, int nRx, int nTx, int L, const double* __restrict__ tl,
+                                   float2* __restrict__ C /*[nCl][L*RT]*/) {
+    const int RT = nRx * nTx;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nCl * L * RT) return;
+    const int us = idx % RT, l = (idx / RT) % L, n = idx / (RT * L);
+    const int u = us / nTx, sx = us % nTx;
+    double re = 0.0, im = 0.0;
+    for (int m = 0; m < nRays; ++m) {
+        if (cl[m] != n) continue;
+        double s, c;
+        sincospi(2.0 * nu[m] * tl[l], &s, &c);
+        const double2 gv = g[(size_t)m * RT + us];
+        re += gv.x * c - gv.y * s;
+        im += gv.x * s + gv.y * c;
+    }
+    // MATLAB order of H(k,l,u,s): j = l + L*(u + nRx*s)
+    C[(size_t)n * L * RT + l + (size_t)L * (u + (size_t)nRx * sx)] = make_float2((float)re, (float)im);
+}
+
+// H[k, j] = sum_n E[k,n] C[n, j],  E[k,n] = exp(-2 pi j f_k tau_n);  j = (l,u,s) flattened, output [K x J]
+constexpr int kCdlTK = 64, kCdlTJ = 64, kCdlMaxCl = 24;
+__global__ void __launch_bounds__(256)
+cdl_response_kernel(const float2* __restrict__ C, const double* __restrict__ tau, int nCl, int K, long long J, double scs,
+                    float2* __restrict__ H) {
+    __shared__ float2 Es[kCdlMaxCl][kCdlTK];
+    __shared__ float2 Cs[kCdlMaxCl][kCdlTJ];
+    const int k0 = blockIdx.x * kCdlTK;
+    const long long j0 = (long long)blockIdx.y * kCdlTJ;
+    for (int i = threadIdx.x; i < nCl * kCdlTK; i += blockDim.x) {
+        const int n = i / kCdlTK, kk = i % kCdlTK;
+        const double f = ((double)(k0 + kk) - (double)(K / 2)) * scs;
+        double s, c;
+        sincospi(-2.0 * f * tau[n], &s, &c);
+        Es[n][kk] = make_float2((float)c, (float)s);
+    }
+    for (int i = threadIdx.x; i < nCl * kCdlTJ; i += blockDim.x) {
+        const int n = i / kCdlTJ, jj = i % kCdlTJ;
+        Cs[n][jj] = (j0 + jj < J) ? C[(size_t)n * J + j0 + jj] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    // thread -> k = tid % 64 (coalesced stores along k), 16 j's each
+    const int kk = threadIdx.x % kCdlTK, jg = threadIdx.x / kCdlTK;  // jg in 0..3
+    float2 acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = make_float2(0.f, 0.f);
+    for (int n = 0; n < nCl; ++n) {
+        const float2 e = Es[n][kk];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float2 c = Cs[n][jg * 16 + q];
+            acc[q].x += e.x * c.x - e.y * c.y;
+            acc[q].y += e.x * c.y + e.y * c.x;
+        }
+    }
+    if (k0 + kk < K) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const long long j = j0 + jg * 16 + q;
+            if (j < J) H[j * K + k0 + kk] = acc[q];
+        }
+    }
+}
+
+int cdl_generate(Ctx* ctx, const CdlRays& rays, int K, double scsHz, int L, const double* symTime, double t0, float2* H,
+                 cudaStream_t st) {
+    if (!H || K < 1 || L < 1 || !symTime || rays.nCl < 1 || rays.nCl > kCdlMaxCl) {
+        set_error(ctx, "cdl_generate: invalid argument");
+        return kErrInvalidArg;
+    }
+    const int nRays = (int)rays.nu.size(), RT = rays.nRx * rays.nTx;
+    const size_t gB = sizeof(double2) * rays.g.size(), nuB = sizeof(double) * nRays, clB = sizeof(int) * nRays,
+                 tauB = sizeof(double) * rays.nCl, tlB = sizeof(double) * L;
+    const size_t total = gB + nuB + clB + tauB + tlB + 64;
+    void *dev = nullptr, *pin = nullptr, *dC = nullptr;
+    int s;
+    if ((s = ctx_scratch(ctx, 9, total, &dev))) return s;
+    if ((s = ctx_pinned(ctx, 3, total, &pin))) return s;
+    if ((s = ctx_scratch(ctx, 10, sizeof(float2) * (size_t)rays.nCl * L * RT, &dC))) return s;
+    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    char* h = (char*)pin;
+    size_t off = 0;
+    auto put = [&](const void* src, size_t b) { std::memcpy(h + off, src, b); size_t o = off; off += (b + 15) / 16 * 16; return o; };
+    const size_t oG = put(rays.g.data(), gB), oNu = put(rays.nu.data(), nuB), oCl = put(rays.cluster.data(), clB),
+                 oTau = put(rays.tau.data(), tauB);
+    std::vector<double> tl(L);
+    for (int l = 0; l < L; ++l) tl[l] = t0 + symTime[l];
+    const size_t oTl = put(tl.data(), tlB);
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(dev, pin, off, cudaMemcpyHostToDevice, st));
+    char* d = (char*)dev;
+    const int pr = prof_begin(ctx, kProfCdl, st);
+    const int tot1 = rays.nCl * L * RT;
+    cdl_cluster_kernel<<<(tot1 + 255) / 256, 256, 0, st>>>((const double2*)(d + oG), (const double*)(d + oNu), (const int*)(d + oCl),
+                                                          nRays, rays.nCl, rays.nRx, rays.nTx, L, (const double*)(d + oTl), (float2*)dC);
+    const long long J = (long long)L * RT;
+    dim3 grid((K + kCdlTK - 1) / kCdlTK, (unsigned)((J + kCdlTJ - 1) / kCdlTJ));
+    cdl_response_kernel<<<grid, 256, 0, st>>>((const float2*)dC, (const double*)(d + oTau), rays.nCl, K, J, scsHz, H);
+    prof_end(ctx, pr, st);
+    count_launches(ctx, 2);
+    ISAC_CUDA_CHECK(ctx, cudaGetLastError());
+    return kOk;
+}
+
+}  // namespace isac

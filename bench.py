@@ -104,6 +104,108 @@ def build_cell_inputs(W, seed):
     return grid.astype(np.complex64), txw.astype(np.complex64)
 
 
+class CommWorkload:
+    """COMM share of one cfg2 cell-frame (20 slots @30 kHz, 8 UEs, 8x8, 273 PRB, CDL-C):
+    4 CSI-RS occasions (period 5 slots, setupCSIRS.m:11) x 8 UEs: CDL channel matrix + fused RI/PMI/CQI report;
+    20 SRS occasions (period 8 slots, setupSRS.m:13; 2.5 per UE per frame): UL CDL + TPMI selection;
+    12 DL slots: PRG precoding of a full-band 2-layer PDSCH (12 symbols) and its DM-RS."""
+
+    N_UE, NRB, SCS = 8, 273, 30e3
+
+    def __init__(self, P, cells, device):
+        import ctypes as C
+        import torch
+        self.C, self.torch, self.P, self.cells = C, torch, P, cells
+        self._lib = P._lib
+        ph = importlib.import_module(PKG + ".communication.phyLayer")
+        cm = importlib.import_module(PKG + ".communication.channelModels")
+        self.ctx = self._lib.get_context(device)
+        K = self.NRB * 12
+        self.K = K
+        self.carrier = {"NSizeGrid": self.NRB, "NStartGrid": 0, "SymbolsPerSlot": 14}
+        self.csirs = {"NumCSIRSPorts": 8, "NumRB": self.NRB, "RBOffset": 0, "SubcarrierLocations": 1, "SymbolLocations": 0,
+                      "Density": "one"}
+        self.rc = {"NSizeBWP": self.NRB, "NStartBWP": 0, "PanelDimensions": (2, 2), "CodebookMode": 1, "PMIMode": "Subband",
+                   "CQIMode": "Subband", "SubbandSize": 16}
+        self.cs = ph._csi_struct(self.carrier, self.csirs, self.rc, 8)
+        _, self.csi_plan = ph._csi_plan(self.cs, self.N_UE)
+        self.table = np.ascontiguousarray(P.communication.setupSINRtoCQIMappingTable()["downlinkSINR90pc"], dtype=np.float64)
+        num = P.workloads.ofdm_numerology(self.NRB, 30)
+        starts = P.workloads.symbol_starts(num, 14) / num["SampleRate"]
+        self.sym_t = np.ascontiguousarray(starts, dtype=np.float64)
+        self.sym13 = np.ascontiguousarray(starts[13:14], dtype=np.float64)
+        self.dl = [[cm.CDLChannel("CDL-C", TransmitAntennaArraySize=(1, 4, 2), ReceiveAntennaArraySize=(2, 2, 2),
+                                  Seed=1000 * c + u, device=device) for u in range(self.N_UE)] for c in range(cells)]
+        self.ul = [[cm.CDLChannel("CDL-C", TransmitAntennaArraySize=(1, 1, 2), ReceiveAntennaArraySize=(1, 4, 2),
+                                  Seed=5000 + 1000 * c + u, device=device) for u in range(self.N_UE)] for c in range(cells)]
+        dev = f"cuda:{device}"
+        self.H = torch.empty((self.N_UE, 8, 8, 14, K), dtype=torch.complex64, device=dev)       # [ue][P][R][L][K]
+        self.hest = torch.empty((2, 8, 1, K), dtype=torch.complex64, device=dev)                # [P][R][1][K]
+        comb = torch.zeros(K, dtype=torch.complex64, device=dev)
+        comb[1::4] = 1.0
+        self.comb = comb
+        self.nvar = np.full(self.N_UE, 10 ** (-15 / 10))
+        nSB = (self.NRB + 15) // 16
+        self.RI = np.zeros(self.N_UE)
+        self.i1 = np.zeros((3, self.N_UE), order="F")
+        self.i2 = np.zeros((nSB, self.N_UE), order="F")
+        self.cqi = np.zeros((nSB + 1) * 2 * self.N_UE)
+        self.rows = C.c_int32()
+        self.ul_pmi = np.zeros(nSB + 1)
+        self.ul_sinr = np.zeros((nSB + 1) * 3)
+        self.ul_idx = np.zeros((nSB + 1) * 2, dtype=np.int32)
+        self.ul_n = (C.c_int32(), C.c_int32(), C.c_int32())
+        # PDSCH: full band, symbols 2..13 (12 symbols), 2 layers, PRG size 2 -> 137 PRGs; DM-RS: symbol 2, 6 REs/PRB
+        L, nu, Pp = 14, 2, 8
+        self.nprg = (self.NRB + 1) // 2
+        g = torch.Generator(device=dev).manual_seed(5)
+        k = torch.arange(K, device=dev)
+        def alloc(syms, ksel):
+            pos = (ksel[:, None] + K * torch.tensor(syms, device=dev)[None, :]).T.reshape(-1)
+            ind = torch.stack([pos + 1 + K * L * j for j in range(nu)], dim=0).to(torch.int32).contiguous()   # [nu][NRE] == MATLAB [NRE x nu]
+            sym = torch.view_as_complex(torch.randn(nu, pos.numel(), 2, device=dev, generator=g)).contiguous()
+            return sym, ind, pos.numel()
+        self.pdsch = alloc(list(range(2, 14)), k)
+        self.dmrs = alloc([2], k[::2])
+        self.F = torch.view_as_complex(torch.randn(self.nprg, Pp, nu, 2, device=dev, generator=g)).contiguous()  # == MATLAB [nu x P x NPRG]
+        self.out_sym = torch.empty(self.pdsch[2] * Pp, dtype=torch.complex64, device=dev)
+        self.out_ind = torch.empty(self.pdsch[2] * Pp, dtype=torch.int32, device=dev)
+        self.slot_t = 0.5e-3
+
+    def step(self, step):
+        lib, ctx, C = self.ctx.lib, self.ctx, self.C
+        ptr, check = self._lib.ptr, self._lib.check
+        ctx.use_torch_stream()
+        frame_t0 = 0.010 * step
+        for c in range(self.cells):
+            for occ in range(4):                                            # CSI-RS occasions of the frame
+                t0 = frame_t0 + (5 * occ + 2) * self.slot_t
+                for u in range(self.N_UE):
+                    self.dl[c][u].generate(self.K, self.SCS, self.sym_t, t0, out=self.H[u])
+                check(lib.isac_csi_report_dev(self.csi_plan, ptr(self.H), ptr(self.nvar), self.N_UE, ptr(self.table),
+                                              self.table.size, 4, ptr(self.RI), ptr(self.i1), ptr(self.i2), ptr(self.cqi),
+                                              C.byref(self.rows)), ctx.handle)
+            for i in range(20):                                             # SRS occasions (2.5 per UE per frame)
+                u = i % self.N_UE
+                t0 = frame_t0 + (8 * (i // self.N_UE) + 3 + u // 4) * self.slot_t
+                self.ul[c][u].generate(self.K, self.SCS, self.sym13, t0, out=self.hest)
+                self.hest.mul_(self.comb)                                   # comb-4 SRS REs only (setupSRS.m:11-18)
+                check(lib.isac_ul_pmi_select_dev(ctx.handle, 2, ptr(self.hest), self.K, 1, 8, 2, 0.05, 16, self.ul_pmi.size,
+                                                 ptr(self.ul_pmi), ptr(self.ul_sinr), ptr(self.ul_idx), C.byref(self.ul_n[0]),
+                                                 C.byref(self.ul_n[1]), C.byref(self.ul_n[2])), ctx.handle)
+            for slot in range(12):                                          # DL slots: PDSCH + DM-RS precoding (gNBPhy.m:822,826)
+                for sym, ind, nre in (self.pdsch, self.dmrs):
+                    check(lib.isac_prg_precode_dev(ctx.handle, self.K, 14, 0, ptr(sym), ptr(ind), nre, 2, ptr(self.F), 8, self.nprg,
+                                                   ptr(self.out_sym), ptr(self.out_ind)), ctx.handle)
+
+    def d2h_bytes_per_step(self):
+        return self.cells * (4 * (self.RI.nbytes + self.i1.nbytes + self.i2.nbytes + self.cqi.nbytes) + 20 * (self.ul_pmi.nbytes + self.ul_sinr.nbytes))
+
+    def algorithmic_bytes(self):
+        K = self.K
+        return {"cdl": 8 * K * 14 * 8 * 8}   # bytes written per DL H (SURVEY 8(d)); UL launches are smaller (reported with the same slot)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -153,10 +255,13 @@ def run_b200(args):
                                                             C.byref(nsym_out)), ctx.handle)
         plan.run_dev(rx_grid_d, tx_grid_d, cells)
 
-    stages = ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa"]
+    stages = ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa",
+              "cdl_dl_generate", "csi_report(ri+pmi+cqi)", "cdl_ul_generate", "ul_tpmi_select", "prg_precode"]
+    comm = CommWorkload(P, cells, local)
 
     def step_dev(step):
         sensing_step_dev(step)
+        comm.step(step)
 
     # ---- device-resident timing ----------------------------------------------------------------
     for i in range(args.warmup):
@@ -197,6 +302,7 @@ def run_b200(args):
     stage_wave = [torch.empty((nTx, T), dtype=torch.complex64, device="cuda") for _ in range(2)]
 
     def step_e2e(step):
+        comm.step(step)   # COMM results already land on the host (PMI/RI/CQI/TPMI); H is generated on the device
         # simulation.cellSimulation's sensing pass (cellSimulation.m:191-197) per cell: txWave+txGrid in, estResults out
         ctx.use_torch_stream()
         for c in range(cells):
@@ -225,7 +331,7 @@ def run_b200(args):
         t_e2e = float(t.item())
     e2e_value = cells * SUBFRAMES_PER_STEP * world * e2e_steps / t_e2e
     h2d = cells * (T * nTx * 8 + nSc * nSym * nTx * 8)
-    d2h = cells * (nTx * 4 + 64 * 8 + 16)  # counts + estimates (order of magnitude; exact per step varies with detections)
+    d2h = cells * (nTx * 4 + 64 * 8 + 16) + comm.d2h_bytes_per_step()  # detections/estimates + CSI / TPMI reports
 
     sampler.stop()
     clocks = sampler.summary(t_wall0, t_wall1)
@@ -242,9 +348,16 @@ def run_b200(args):
     rdm_n = prof.get("rdm_range", (0.0, 1))[1]
     groups["rdm_2dfft+cfar"] = (rdm_ms, rdm_n)
     groups["echo_demod"] = prof.get("echo_demod", (0.0, 1))
+    for name in ("pmi_sinr", "cdl", "ul_tpmi", "prg_precode", "covariance", "music"):
+        if name in prof:
+            groups[name] = prof[name]
+    alg.update(comm.algorithmic_bytes())
     dom = max(groups, key=lambda k: groups[k][0])
     roof = {}
     for name, (ms, n) in groups.items():
+        if n and ms > 0 and name not in alg:
+            roof[name] = {"bound": "latency/alu", "avg_launch_us": round(ms / n * 1e3, 2), "share_of_step": round(ms / ms_total, 4)}
+            continue
         if n and ms > 0:
             ach = alg[name] / (ms / n * 1e-3) / 1e9
             roof[name] = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
@@ -275,6 +388,32 @@ def run_b200(args):
 
 
 # ----------------------------------------------------------------------------------------------
+def _oracle_comm_sample(seed, n_reports=2):
+    """`n_reports` UE CSI reports (+ proportional UL/precoding work) of the cfg2 COMM share on the CPU.
+    Uses the vectorised NumPy restatement (best-effort CPU variant of BASELINE.md).  Returns seconds."""
+    from oracle import comm as OCm
+    from oracle import cdl as OCd
+    rng = np.random.default_rng(seed)
+    nrb, K = 273, 273 * 12
+    cfg = OCm.report_config(8, (2, 2), nrb, 0, 1, "Subband", "Subband", 16)
+    re_k, re_l = OCm.csirs_first_port_res(nrb, 1, 0)
+    table = np.array([-3.46, 1.54, 6.54, 11.05, 13.54, 16.04, 17.54, 20.04, 22.04, 24.43, 26.93, 27.43, 29.43, 32.43, 35.43])
+    t_sym = np.arange(14) * 35.7e-6
+    t0 = time.time()
+    for i in range(n_reports):
+        rays = OCd.build_rays(2, 300e-9, 5.0, (1, 4, 2), (2, 2, 2), True, False, seed * 100 + i)
+        H = OCd.frequency_response(rays, K, 30e3, t_sym)
+        OCm.csi_report_vectorized(cfg, re_k, re_l, H, 10 ** -1.5, table)
+    # UL: 20/32 SRS occasions per CSI report
+    for i in range(max(1, round(n_reports * 20 / 32))):
+        rays = OCd.build_rays(2, 300e-9, 5.0, (1, 1, 2), (1, 4, 2), True, False, seed * 100 + 50 + i)
+        h = OCd.frequency_response(rays, K, 30e3, t_sym[13:14])
+        mask = np.zeros(K)
+        mask[1::4] = 1
+        OCm.pmi_select(2, h * mask[:, None, None, None], 0.05, 16)
+    return time.time() - t0
+
+
 def _oracle_cell_frame(seed):
     """One cfg2 cell-frame of sensing work on the CPU (float64 oracle).  Returns seconds."""
     from oracle import sensing as S
@@ -290,12 +429,19 @@ def _oracle_cell_frame(seed):
     return time.time() - t0
 
 
+def _cell_frame_seconds(seed, n_reports=2):
+    """Bounded CPU sample of one cfg2 cell-frame: the whole sensing share + n_reports of the 32 CSI reports (and the
+    proportional SRS work), the COMM part extrapolated linearly to the full frame."""
+    ts = _oracle_cell_frame(seed)
+    tc = _oracle_comm_sample(seed, n_reports) * (32.0 / n_reports)
+    return ts + tc, ts, tc
+
+
 def cpu_baseline(sample_cells=1):
-    ts = [_oracle_cell_frame(11 + i) for i in range(sample_cells)]
-    t = float(np.mean(ts))
+    t, ts, tc = _cell_frame_seconds(11)
     return {"value": round(SUBFRAMES_PER_STEP / t, 3), "unit": "cell-subframes/s", "cores": 1, "kind": "port",
-            "sample": f"{sample_cells} cfg2 cell-frame(s) of sensing work (echo+demod+fft2D+CFAR+MUSIC), NumPy float64 "
-                      f"restatement of the reference (not MATLAB), {t:.2f} s per cell-frame"}
+            "sample": f"1 cfg2 cell-frame: full sensing share ({ts:.1f} s) + 2 of its 32 UE CSI reports and 1 of its 20 SRS "
+                      f"reports, extrapolated linearly ({tc:.1f} s); NumPy float64 restatement of the reference (not MATLAB)"}
 
 
 def run_reference(args):
@@ -308,18 +454,23 @@ def run_reference(args):
     per_step = workers  # one cell-frame per worker per step
     with ProcessPoolExecutor(max_workers=workers) as ex:
         for _ in range(args.warmup and 1):
-            list(ex.map(_oracle_cell_frame, range(workers)))
+            list(ex.map(_cell_frame_seconds, range(workers)))
         t0 = time.time()
+        est = []
         for s in range(args.steps):
-            list(ex.map(_oracle_cell_frame, [100 * s + i for i in range(per_step)]))
-        dt = time.time() - t0
+            est += [r[0] for r in ex.map(_cell_frame_seconds, [100 * s + i for i in range(per_step)])]
+        wall = time.time() - t0
+        # every worker ran one (partly extrapolated) cell-frame; throughput = workers / mean extrapolated seconds
+        dt = float(np.mean(est)) * args.steps
     value = per_step * SUBFRAMES_PER_STEP * args.steps / dt
     line = {"impl": "reference", "metric": "cell_subframes_per_sec", "value": round(value, 3), "unit": "cell-subframes/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "cells_per_step": per_step,
-                       "stages": ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa"]},
+                       "stages": ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa", "cdl_dl_generate",
+                                  "csi_report(ri+pmi+cqi)", "cdl_ul_generate", "ul_tpmi_select"],
+                       "note": "COMM share sampled (2 of 32 CSI reports per cell-frame) and extrapolated; wall %.1f s" % wall},
             "cpu_baseline": {"value": round(value, 3), "unit": "cell-subframes/s", "cores": workers, "kind": "port",
                              "sample": f"{per_step} cfg2 cell-frames per step over {workers} processes; NumPy float64 "
                                        "restatement of the reference (MATLAB cannot run here)"},

@@ -272,6 +272,32 @@ int isac_prg_precode_dev(isac_ctx* ctx, int32_t K, int32_t Lsym, int32_t nStartG
                          const int32_t* portind, int32_t NRE, int32_t nLayers, const void* F, int32_t P, int32_t NPRG,
                          void* antsym, int32_t* antind);
 
+/* ---- K11: CDL channel (TR 38.901 7.7.1) as a frequency-domain channel matrix ---------------------
+ * Replaces nrCDLChannel filtering + nrChannelEstimate (uePhy.m:731,897; gNBPhy.m:840,1030; objects
+ * configured at +parameters/+channelModels/+communication/cdl.m:48-88, profile chosen by
+ * communication.channelModels.updateCDLModels.m:7-15).  Statistical parity only (toolbox RNG stream). */
+typedef struct {
+    int32_t profile;         /* 0 CDL-A, 2 CDL-C, 3 CDL-D                    cdl.m:58 / updateCDLModels.m:11-13 */
+    double delaySpread;      /* channel.DelaySpread = 300e-9                 cdl.m:59 */
+    double fc;               /* channel.CarrierFrequency                     cdl.m:60 */
+    double maxDoppler;       /* MaximumDopplerShift (toolbox default 5 Hz) */
+    int32_t txSize[3];       /* TransmitAntennaArray.Size(1:3) = [M N P]     cdl.m:61 */
+    int32_t rxSize[3];       /* ReceiveAntennaArray.Size(1:3)                cdl.m:62 */
+    int32_t txPattern38901;  /* 1: '38.901' element (toolbox Tx default), 0: isotropic */
+    int32_t rxPattern38901;  /* toolbox Rx default: isotropic (0) */
+    uint64_t seed;
+} isac_cdl_config;
+typedef struct isac_cdl_channel isac_cdl_channel;
+int isac_cdl_create(isac_ctx* ctx, const isac_cdl_config* cfg, isac_cdl_channel** ch);
+int isac_cdl_destroy(isac_cdl_channel* ch);
+/* ray tables of the channel: nClusters, nRays (incl. the LOS ray), tau[nClusters], nu[nRays], cluster[nRays],
+ * g complex128 [nTx x nRx x nRays] (s fastest); any pointer may be NULL */
+int isac_cdl_get_rays(const isac_cdl_channel* ch, int32_t* nClusters, int32_t* nRays, int32_t* nRx, int32_t* nTx,
+                      double* tau, double* nu, int32_t* cluster, double* g);
+/* H: device complex64 [K x L x nRx x nTx] for subcarrier spacing scsHz, symbol times t0 + symTime[l] (seconds) */
+int isac_cdl_generate_dev(isac_cdl_channel* ch, int32_t K, double scsHz, int32_t L, const double* symTime, double t0,
+                          void* H);
+
 #ifdef __cplusplus
 }
 #endif

@@ -628,8 +628,70 @@ def prg_precode(siz, nstartgrid, portsym, portind, F):
         if not sel.any():
             continue
         port = np.zeros((K * Lsym, nu), complex)
-        port.reshape(-1, order="F")[portind[sel] - 1] = portsym[sel]
+        lin = portind[sel] - 1                                                            # portgrid(indin(thisprg)) = symin(thisprg)
+        port[lin % (K * Lsym), lin // (K * Lsym)] = portsym[sel]
         ant += port @ F[:, :, g - 1]
     pos = re[:, 0] if re.ndim == 2 else re
     antind = pos[:, None] + 1 + (K * Lsym) * np.arange(P)[None, :]
     return ant[pos, :], antind
+
+
+# ----------------------------------------------------------------------------------------------
+# vectorised variants (same arithmetic, batched linear algebra) — used as the best-effort CPU baseline
+# ----------------------------------------------------------------------------------------------
+def sinr_per_re_vectorized(cfg, re_k, re_l, n_layers, H, n_var):
+    """SINRPerRE [nRE, nLayers, i2, i11, i12, i13] with stacked np.linalg.inv instead of the loop nest."""
+    n_var = max(float(n_var), 1e-10)
+    P = cfg["NumCSIRSPorts"]
+    W = np.ones((1, 1, 1, 1, 1, 1), complex) if P == 1 else type1_single_panel_codebook(cfg, n_layers, "ue")
+    sizes = W.shape[2:]
+    Wf = W.reshape(W.shape[0], n_layers, -1, order="F")                      # [P, nu, nCand] (MATLAB linear order)
+    valid = np.abs(Wf).sum(axis=(0, 1)) > 0
+    Hs = np.asarray(H)[np.asarray(re_k) - 1, np.asarray(re_l) - 1]           # [nRE, R, P]
+    G = np.einsum("erp,pvc->ecrv", Hs.astype(complex), Wf[:, :, valid])
+    A = np.einsum("ecrv,ecrw->ecvw", G.conj(), G) + n_var * np.eye(n_layers)
+    d = np.real(np.diagonal(np.linalg.inv(A), axis1=2, axis2=3))             # [nRE, nValid, nu]
+    S = np.full((Hs.shape[0], n_layers, Wf.shape[2]), np.nan)
+    S[:, :, valid] = np.transpose(1.0 / (n_var * d) - 1.0, (0, 2, 1))
+    return S.reshape((Hs.shape[0], n_layers) + sizes, order="F"), W
+
+
+def csi_report_vectorized(cfg, re_k, re_l, H, n_var, sinr_table, rank_cap=4):
+    """riSelect + cqiSelect (uePhy.m:900-907) using the vectorised SINR kernel; selection logic identical to
+    dl_pmi_select / ri_select / cqi_select above (they are re-used through a monkey-patched SINR array)."""
+    re_k = np.asarray(re_k, int)
+    re_l = np.asarray(re_l, int)
+    n_sb, sb_sizes = subband_info(cfg["PMIMode"], cfg["NStartBWP"], cfg["NSizeBWP"], cfg["SubbandSize"])
+    R, P = H.shape[2], H.shape[3]
+    best, RI, keep = -np.inf, np.nan, {}
+    for r in range(1, min(R, P) + 1):
+        if not cfg["RIRestriction"][r - 1]:
+            continue
+        S, W = sinr_per_re_vectorized(cfg, re_k, re_l, r, H, n_var)
+        sizes = S.shape[2:]
+        total = matlab_round4(np.nansum(S, axis=(0, 1)))
+        lin = int(np.flatnonzero(total.reshape(-1, order="F") == total.max())[0])
+        i2, i11, i12, i13 = np.unravel_index(lin, sizes, order="F")
+        i2s, sel = np.full(n_sb, np.nan), np.full((n_sb, r), np.nan)
+        start = 0
+        for sb in range(n_sb):
+            m = (re_k >= start * 12 + 1) & (re_k <= (start + sb_sizes[sb]) * 12)
+            if m.any():
+                sub = np.nanmean(S[m][:, :, :, i11, i12, i13], axis=0)           # [nu, n2] (single CSI-RS symbol)
+                t = matlab_round4(np.nansum(sub, axis=0))
+                i2s[sb] = int(np.argmax(t)) + 1
+                sel[sb] = sub[:, int(i2s[sb]) - 1]
+            start += sb_sizes[sb]
+        with np.errstate(invalid="ignore"):
+            layer = np.nanmean(sel * r, axis=0)
+        tot_r = np.sum(layer[layer >= 1])
+        keep[r] = ({"i1": np.array([i11 + 1, i12 + 1, i13 + 1.0]), "i2": i2s}, sel)
+        if tot_r > best + 0.1:
+            best, RI = tot_r, r
+    rank = int(min(RI, rank_cap))
+    pm, sel = keep[rank]
+    n_cw = int(math.ceil(rank / 4))
+    cw = np.stack([layer_demap_sums(sel[s]) if not np.any(np.isnan(sel[s])) else np.full(n_cw, np.nan) for s in range(n_sb)])
+    full = np.vstack([np.nanmean(cw, axis=0), cw]) if n_sb > 1 else cw
+    cq = np.vectorize(lambda x: get_cqi(x, sinr_table))(full)
+    return rank, pm, cq
