@@ -763,7 +763,12 @@ static int ri_select_batch(isac_csi_plan* pl, const float2* H, const double* nVa
         if (st) return st;
     }
     for (int r : valid) {
-        int st = pmi_select_collect(pl->byRank[r - 1], batch, all[r - 1]);
+        int st = pmi_select_collect_enqueue(pl->byRank[r - 1], batch, c->stream);
+        if (st) return st;
+    }
+    ISAC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));  // one synchronisation for all ranks
+    for (int r : valid) {
+        int st = pmi_select_collect_finish(pl->byRank[r - 1], batch, all[r - 1]);
         if (st) return st;
     }
     for (int b = 0; b < batch; ++b) {
@@ -925,6 +930,11 @@ int isac_cdl_create(isac_ctx* h, const isac_cdl_config* cfg, isac_cdl_channel** 
 }
 
 int isac_cdl_destroy(isac_cdl_channel* ch) {
+    if (ch) {
+        cudaSetDevice(ch->ctx->device);
+        cudaStreamSynchronize(ch->ctx->stream);
+        cdl_free(ch->rays);
+    }
     delete ch;
     return ISAC_OK;
 }

@@ -165,20 +165,27 @@ int cdl_build_rays(Ctx* ctx, const CdlConfig& c, CdlRays& r) {
     return kOk;
 }
 
-// C_n[l,u,s] = sum_{m in n} g_m[u,s] exp(2 pi j nu_m t_l)
-__global__ void cdl_cluster_kernel(const double2* __restrict__ g, const double* __restrict__ nu, const int* __restrict__ cl,
-                                   int nRays, int nCl, int nRx, int nTx, int L, const double* __restrict__ tl,
-                                   float2* __restrict__ C /*[nCl][L*RT]*/) {
+constexpr int kCdlMaxSym = 16;
+struct CdlTimes { double t[kCdlMaxSym]; };
+
+// C_n[l,u,s] = sum_{m in n} g_m[u,s] exp(2 pi j nu_m t_l); rays of cluster n are [n*nRay, (n+1)*nRay) (+ the LOS ray)
+__global__ void cdl_cluster_kernel(const double2* __restrict__ g, const double* __restrict__ nu, int nRay, int losRay,
+                                   int nCl, int nRx, int nTx, int L, const CdlTimes tl, float2* __restrict__ C /*[nCl][J]*/) {
     const int RT = nRx * nTx;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nCl * L * RT) return;
     const int us = idx % RT, l = (idx / RT) % L, n = idx / (RT * L);
     const int u = us / nTx, sx = us % nTx;
     double re = 0.0, im = 0.0;
-    for (int m = 0; m < nRays; ++m) {
-        if (cl[m] != n) continue;
+    const double t = tl.t[l];
+    for (int q = 0; q <= nRay; ++q) {
+        int m = n * nRay + q;
+        if (q == nRay) {
+            if (n != 0 || losRay < 0) break;
+            m = losRay;  // specular ray belongs to cluster 1
+        }
         double s, c;
-        sincospi(2.0 * nu[m] * tl[l], &s, &c);
+        sincospi(2.0 * nu[m] * t, &s, &c);
         const double2 gv = g[(size_t)m * RT + us];
         re += gv.x * c - gv.y * s;
         im += gv.x * s + gv.y * c;
@@ -187,8 +194,9 @@ __global__ void cdl_cluster_kernel(const double2* __restrict__ g, const double* 
     C[(size_t)n * L * RT + l + (size_t)L * (u + (size_t)nRx * sx)] = make_float2((float)re, (float)im);
 }
 
-// H[k, j] = sum_n E[k,n] C[n, j],  E[k,n] = exp(-2 pi j f_k tau_n);  j = (l,u,s) flattened, output [K x J]
-constexpr int kCdlTK = 64, kCdlTJ = 64, kCdlMaxCl = 24;
+// H[k, j] = sum_n E[k,n] C[n, j],  E[k,n] = exp(-2 pi j f_k tau_n);  j = (l,u,s) flattened, output [K x J].
+// 64(k) x 128(j) tile per CTA, 4 x 8 register tile per thread, contraction over <= 24 clusters from shared memory.
+constexpr int kCdlTK = 64, kCdlTJ = 128, kCdlMaxCl = 24;
 __global__ void __launch_bounds__(256)
 cdl_response_kernel(const float2* __restrict__ C, const double* __restrict__ tau, int nCl, int K, long long J, double scs,
                     float2* __restrict__ H) {
@@ -208,62 +216,80 @@ cdl_response_kernel(const float2* __restrict__ C, const double* __restrict__ tau
         Cs[n][jj] = (j0 + jj < J) ? C[(size_t)n * J + j0 + jj] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    // thread -> k = tid % 64 (coalesced stores along k), 16 j's each
-    const int kk = threadIdx.x % kCdlTK, jg = threadIdx.x / kCdlTK;  // jg in 0..3
-    float2 acc[16];
+    const int tk = threadIdx.x % 16, tj = threadIdx.x / 16;  // k = tk + 16*a (a<4), j = tj + 16*b (b<8)
+    float2 acc[4][8];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) acc[q] = make_float2(0.f, 0.f);
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = make_float2(0.f, 0.f);
     for (int n = 0; n < nCl; ++n) {
-        const float2 e = Es[n][kk];
+        float2 e[4], c[8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const float2 c = Cs[n][jg * 16 + q];
-            acc[q].x += e.x * c.x - e.y * c.y;
-            acc[q].y += e.x * c.y + e.y * c.x;
-        }
+        for (int a = 0; a < 4; ++a) e[a] = Es[n][tk + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) c[b] = Cs[n][tj + 16 * b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                acc[a][b].x += e[a].x * c[b].x - e[a].y * c[b].y;
+                acc[a][b].y += e[a].x * c[b].y + e[a].y * c[b].x;
+            }
     }
-    if (k0 + kk < K) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const long long j = j0 + jg * 16 + q;
-            if (j < J) H[j * K + k0 + kk] = acc[q];
+    for (int b = 0; b < 8; ++b) {
+        const long long j = j0 + tj + 16 * b;
+        if (j >= J) continue;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int k = k0 + tk + 16 * a;
+            if (k < K) H[j * K + k] = acc[a][b];
         }
     }
 }
 
-int cdl_generate(Ctx* ctx, const CdlRays& rays, int K, double scsHz, int L, const double* symTime, double t0, float2* H,
+// upload the ray tables once (they do not change between calls)
+int cdl_upload(Ctx* ctx, CdlRays& rays) {
+    if (rays.d_g) return kOk;
+    std::vector<double2> g(rays.g.size());
+    for (size_t i = 0; i < g.size(); ++i) g[i] = make_double2(rays.g[i].real(), rays.g[i].imag());
+    ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)&rays.d_g, sizeof(double2) * g.size()));
+    ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)&rays.d_nu, sizeof(double) * rays.nu.size()));
+    ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)&rays.d_tau, sizeof(double) * rays.tau.size()));
+    ISAC_CUDA_CHECK(ctx, cudaMemcpy(rays.d_g, g.data(), sizeof(double2) * g.size(), cudaMemcpyHostToDevice));
+    ISAC_CUDA_CHECK(ctx, cudaMemcpy(rays.d_nu, rays.nu.data(), sizeof(double) * rays.nu.size(), cudaMemcpyHostToDevice));
+    ISAC_CUDA_CHECK(ctx, cudaMemcpy(rays.d_tau, rays.tau.data(), sizeof(double) * rays.tau.size(), cudaMemcpyHostToDevice));
+    return kOk;
+}
+
+void cdl_free(CdlRays& rays) {
+    cudaFree(rays.d_g);
+    cudaFree(rays.d_nu);
+    cudaFree(rays.d_tau);
+    rays.d_g = nullptr; rays.d_nu = nullptr; rays.d_tau = nullptr;
+}
+
+int cdl_generate(Ctx* ctx, CdlRays& rays, int K, double scsHz, int L, const double* symTime, double t0, float2* H,
                  cudaStream_t st) {
-    if (!H || K < 1 || L < 1 || !symTime || rays.nCl < 1 || rays.nCl > kCdlMaxCl) {
-        set_error(ctx, "cdl_generate: invalid argument");
+    if (!H || K < 1 || L < 1 || L > kCdlMaxSym || !symTime || rays.nCl < 1 || rays.nCl > kCdlMaxCl) {
+        set_error(ctx, "cdl_generate: invalid argument (L <= 16 symbols per call)");
         return kErrInvalidArg;
     }
-    const int nRays = (int)rays.nu.size(), RT = rays.nRx * rays.nTx;
-    const size_t gB = sizeof(double2) * rays.g.size(), nuB = sizeof(double) * nRays, clB = sizeof(int) * nRays,
-                 tauB = sizeof(double) * rays.nCl, tlB = sizeof(double) * L;
-    const size_t total = gB + nuB + clB + tauB + tlB + 64;
-    void *dev = nullptr, *pin = nullptr, *dC = nullptr;
-    int s;
-    if ((s = ctx_scratch(ctx, 9, total, &dev))) return s;
-    if ((s = ctx_pinned(ctx, 3, total, &pin))) return s;
+    int s = cdl_upload(ctx, rays);
+    if (s) return s;
+    const int RT = rays.nRx * rays.nTx;
+    void* dC = nullptr;
     if ((s = ctx_scratch(ctx, 10, sizeof(float2) * (size_t)rays.nCl * L * RT, &dC))) return s;
-    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    char* h = (char*)pin;
-    size_t off = 0;
-    auto put = [&](const void* src, size_t b) { std::memcpy(h + off, src, b); size_t o = off; off += (b + 15) / 16 * 16; return o; };
-    const size_t oG = put(rays.g.data(), gB), oNu = put(rays.nu.data(), nuB), oCl = put(rays.cluster.data(), clB),
-                 oTau = put(rays.tau.data(), tauB);
-    std::vector<double> tl(L);
-    for (int l = 0; l < L; ++l) tl[l] = t0 + symTime[l];
-    const size_t oTl = put(tl.data(), tlB);
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(dev, pin, off, cudaMemcpyHostToDevice, st));
-    char* d = (char*)dev;
+    CdlTimes tl{};
+    for (int l = 0; l < L; ++l) tl.t[l] = t0 + symTime[l];
     const int pr = prof_begin(ctx, kProfCdl, st);
     const int tot1 = rays.nCl * L * RT;
-    cdl_cluster_kernel<<<(tot1 + 255) / 256, 256, 0, st>>>((const double2*)(d + oG), (const double*)(d + oNu), (const int*)(d + oCl),
-                                                          nRays, rays.nCl, rays.nRx, rays.nTx, L, (const double*)(d + oTl), (float2*)dC);
+    const int losRay = rays.los ? rays.nCl * rays.nRay : -1;
+    cdl_cluster_kernel<<<(tot1 + 255) / 256, 256, 0, st>>>(rays.d_g, rays.d_nu, rays.nRay, losRay, rays.nCl, rays.nRx, rays.nTx, L, tl,
+                                                          (float2*)dC);
     const long long J = (long long)L * RT;
     dim3 grid((K + kCdlTK - 1) / kCdlTK, (unsigned)((J + kCdlTJ - 1) / kCdlTJ));
-    cdl_response_kernel<<<grid, 256, 0, st>>>((const float2*)dC, (const double*)(d + oTau), rays.nCl, K, J, scsHz, H);
+    cdl_response_kernel<<<grid, 256, 0, st>>>((const float2*)dC, rays.d_tau, rays.nCl, K, J, scsHz, H);
     prof_end(ctx, pr, st);
     count_launches(ctx, 2);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());

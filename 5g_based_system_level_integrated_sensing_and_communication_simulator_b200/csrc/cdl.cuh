@@ -28,13 +28,17 @@ struct CdlRays {
     std::vector<double> nu;                    // [nCl*nRay (+1 LOS)] Doppler of each ray (Hz)
     std::vector<int> cluster;                  // cluster of each ray
     std::vector<std::complex<double>> g;       // [ray][u][s] static coefficient
+    double2* d_g = nullptr;                    // device copies (uploaded on first use)
+    double* d_nu = nullptr;
+    double* d_tau = nullptr;
 };
 
 int cdl_build_rays(Ctx* ctx, const CdlConfig& c, CdlRays& r);
 
 // H[k,l,u,s] = sum_n exp(-2 pi j f_k tau_n) * sum_{m in n} g_m[u,s] exp(2 pi j nu_m t_l),
 // f_k = (k - K/2)*scs, t_l = t0 + symTime[l].  H: device complex64 [K x L x nRx x nTx].
-int cdl_generate(Ctx* ctx, const CdlRays& rays, int K, double scsHz, int L, const double* symTime, double t0, float2* H,
+void cdl_free(CdlRays& rays);
+int cdl_generate(Ctx* ctx, CdlRays& rays, int K, double scsHz, int L, const double* symTime, double t0, float2* H,
                  cudaStream_t st);
 
 }  // namespace isac

@@ -8,6 +8,7 @@
 namespace isac {
 
 constexpr int kMaxLayers = 8;
+constexpr int kMaxPmiBatch = 32;  // UEs per PMI launch (their noise variances travel as kernel parameters)
 constexpr int kMaxBlocks = 4;  // column blocks of a precoder: 2 (v_lm ; phi v_lm), 4 (vbar: 1, theta, phi, phi*theta) or P (explicit W, P <= 4)
 
 // Mirrors isac_csi_config of include/isac_b200.h (validated reportConfig of dlPMISelect.m:511-851)

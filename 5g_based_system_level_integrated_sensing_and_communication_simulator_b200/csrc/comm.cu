@@ -28,10 +28,10 @@ struct PmiDev {
     const uint8_t* valid;
     const int* reK;
     const int* reL;
-    const double* nVar;   // device [batch]
     double* S;
     int K, L, R, P, NB, Pb, nBeams, nCand, nRE;
     double scale;
+    double nVar[kMaxPmiBatch];  // per UE, already clipped at 1e-10 (dlPMISelect.m:846-848)
 };
 
 __device__ __forceinline__ double round4(double x) { return copysign(floor(fabs(x) * 1e4 + 0.5) / 1e4, x); }
@@ -69,64 +69,71 @@ pmi_sinr_kernel(const PmiDev p) {
             continue;
         }
         const double sc = p.candScale ? p.candScale[c] : p.scale;
-        double2 A[NU][NU];
+        constexpr int NT = NU * (NU + 1) / 2;
+#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))   /* packed lower triangle, i >= j: stays in registers */
+        double2 A[NT];
 #pragma unroll
-        for (int i = 0; i < NU; ++i)
-#pragma unroll
-            for (int j = 0; j < NU; ++j) A[i][j] = make_double2(0.0, 0.0);
+        for (int i = 0; i < NT; ++i) A[i] = make_double2(0.0, 0.0);
         int beamOf[NU];
+        double2 cf[NU][2];
 #pragma unroll
-        for (int j = 0; j < NU; ++j) beamOf[j] = p.layerBeam[c * NU + j];
+        for (int j = 0; j < NU; ++j) {
+            beamOf[j] = p.layerBeam[c * NU + j];
+            cf[j][0] = p.layerCoef[(c * NU + j) * p.NB];
+            cf[j][1] = p.NB > 1 ? p.layerCoef[(c * NU + j) * p.NB + 1] : make_double2(0.0, 0.0);
+        }
         for (int r = 0; r < R; ++r) {
             double2 g[NU];
 #pragma unroll
             for (int j = 0; j < NU; ++j) {
-                double2 acc = make_double2(0.0, 0.0);
-                for (int blk = 0; blk < p.NB; ++blk)
+                double2 acc = zmul(cf[j][0], Bf[(0 * p.nBeams + beamOf[j]) * R + r]);
+                if (p.NB > 1) acc = zadd(acc, zmul(cf[j][1], Bf[(1 * p.nBeams + beamOf[j]) * R + r]));
+                for (int blk = 2; blk < p.NB; ++blk)
                     acc = zadd(acc, zmul(p.layerCoef[(c * NU + j) * p.NB + blk], Bf[(blk * p.nBeams + beamOf[j]) * R + r]));
                 g[j] = make_double2(acc.x * sc, acc.y * sc);
             }
 #pragma unroll
             for (int i = 0; i < NU; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j) A[i][j] = zadd(A[i][j], zmulc(g[j], g[i]));  // conj(g_i) g_j
+                for (int j = 0; j <= i; ++j) A[TRI(i, j)] = zadd(A[TRI(i, j)], zmulc(g[j], g[i]));  // conj(g_i) g_j
         }
 #pragma unroll
-        for (int i = 0; i < NU; ++i) A[i][i].x += nVar;  // (W'H')HW + noise  (dlPMISelect.m:1831-1832)
+        for (int i = 0; i < NU; ++i) A[TRI(i, i)].x += nVar;  // (W'H')HW + noise  (dlPMISelect.m:1831-1832)
         // Cholesky A = L L^H (lower triangle in place)
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
-            double d = A[j][j].x;
+            double d = A[TRI(j, j)].x;
 #pragma unroll
-            for (int k = 0; k < j; ++k) d -= A[j][k].x * A[j][k].x + A[j][k].y * A[j][k].y;
+            for (int k = 0; k < j; ++k) d -= A[TRI(j, k)].x * A[TRI(j, k)].x + A[TRI(j, k)].y * A[TRI(j, k)].y;
             const double ljj = sqrt(d);
-            A[j][j] = make_double2(ljj, 0.0);
+            A[TRI(j, j)] = make_double2(ljj, 0.0);
             const double inv = 1.0 / ljj;
 #pragma unroll
             for (int i = j + 1; i < NU; ++i) {
-                double2 s = A[i][j];
+                double2 s = A[TRI(i, j)];
 #pragma unroll
-                for (int k = 0; k < j; ++k) s = zsub(s, zmulc(A[i][k], A[j][k]));
-                A[i][j] = make_double2(s.x * inv, s.y * inv);
+                for (int k = 0; k < j; ++k) s = zsub(s, zmulc(A[TRI(i, k)], A[TRI(j, k)]));
+                A[TRI(i, j)] = make_double2(s.x * inv, s.y * inv);
             }
         }
         // [A^-1]_cc = || L^-1 e_c ||^2 ; sinr = 1/(nVar*[A^-1]_cc) - 1   (dlPMISelect.m:1832-1833)
 #pragma unroll
         for (int cc = 0; cc < NU; ++cc) {
             double2 x[NU];
-            x[cc] = make_double2(1.0 / A[cc][cc].x, 0.0);
+            x[cc] = make_double2(1.0 / A[TRI(cc, cc)].x, 0.0);
             double nrm = x[cc].x * x[cc].x;
 #pragma unroll
             for (int i = cc + 1; i < NU; ++i) {
                 double2 s = make_double2(0.0, 0.0);
 #pragma unroll
-                for (int k = cc; k < i; ++k) s = zadd(s, zmul(A[i][k], x[k]));
-                const double inv = -1.0 / A[i][i].x;
+                for (int k = cc; k < i; ++k) s = zadd(s, zmul(A[TRI(i, k)], x[k]));
+                const double inv = -1.0 / A[TRI(i, i)].x;
                 x[i] = make_double2(s.x * inv, s.y * inv);
                 nrm += x[i].x * x[i].x + x[i].y * x[i].y;
             }
             Sout[(long long)cc * p.nCand + c] = 1.0 / (nVar * nrm) - 1.0;
         }
+#undef TRI
     }
 }
 
@@ -401,6 +408,7 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
 void pmi_plan_destroy(PmiPlan* p) {
     if (!p) return;
     cudaFree(p->d_sbStart); cudaFree(p->d_cqiStart); cudaFree(p->d_nVar);
+    if (p->pin) cudaFreeHost(p->pin);
     cudaFree(p->d_beams); cudaFree(p->d_layerBeam); cudaFree(p->d_layerCoef); cudaFree(p->d_candScale);
     cudaFree(p->d_valid); cudaFree(p->d_reK); cudaFree(p->d_reL); cudaFree(p->d_reSb); cudaFree(p->d_reW);
     cudaFree(p->d_reCqiSb); cudaFree(p->d_reCqiW); cudaFree(p->d_S); cudaFree(p->d_total); cudaFree(p->d_sub);
@@ -426,25 +434,20 @@ int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, c
     }
     const int nRE = (int)p->reK.size();
     if (nRE == 0) return kOk;  // everything NaN (dlPMISelect.m:362-379), decided at collect time
-    PmiPlan* ex = p;
-    std::vector<double> nv(batch);
-    for (int b = 0; b < batch; ++b) {
+    if (batch > kMaxPmiBatch) {
+        set_error(ctx, "pmi_select_run: batch exceeds kMaxPmiBatch");
+        return kErrCapacity;
+    }
+    for (int b = 0; b < batch; ++b)
         if (!(nVar[b] >= 0.0) || !std::isfinite(nVar[b])) {
             set_error(ctx, "dlPMISelect: NVAR must be real, nonnegative and finite");
             return kErrInvalidArg;
         }
-        nv[b] = nVar[b] < 1e-10 ? 1e-10 : nVar[b];  // dlPMISelect.m:846-848
-    }
-    void* pin = nullptr;
-    int s = ctx_pinned(ctx, 5, sizeof(double) * batch, &pin);
-    if (s) return s;
-    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    std::memcpy(pin, nv.data(), sizeof(double) * batch);
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(ex->d_nVar, pin, sizeof(double) * batch, cudaMemcpyHostToDevice, st));
     const CodebookTable& t = p->tab;
     PmiDev d{};
     d.H = H; d.beams = p->d_beams; d.layerBeam = p->d_layerBeam; d.layerCoef = p->d_layerCoef;
-    d.candScale = nullptr; d.valid = p->d_valid; d.reK = p->d_reK; d.reL = p->d_reL; d.nVar = ex->d_nVar; d.S = p->d_S;
+    d.candScale = nullptr; d.valid = p->d_valid; d.reK = p->d_reK; d.reL = p->d_reL; d.S = p->d_S;
+    for (int b = 0; b < batch; ++b) d.nVar[b] = nVar[b] < 1e-10 ? 1e-10 : nVar[b];  // dlPMISelect.m:846-848
     d.K = p->cfg.K; d.L = p->cfg.L; d.R = p->cfg.nRx; d.P = t.P; d.NB = t.NB; d.Pb = t.Pb; d.nBeams = t.nBeams;
     d.nCand = t.nCand(); d.nRE = nRE; d.scale = t.scale;
     const int pr = prof_begin(ctx, kProfPmi, st);
@@ -464,9 +467,9 @@ int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, c
     dim3 g1((nCand + 127) / 128, batch);
     pmi_total_kernel<<<g1, 128, 0, st>>>(p->d_S, nCand, nu, nRE, p->d_total);
     dim3 g2((nCand + 127) / 128, nu * p->nSB, batch);
-    pmi_subband_kernel<<<g2, 128, 0, st>>>(p->d_S, nCand, nu, nRE, p->nSB, ex->d_sbStart, p->d_reW, p->d_sub);
+    pmi_subband_kernel<<<g2, 128, 0, st>>>(p->d_S, nCand, nu, nRE, p->nSB, p->d_sbStart, p->d_reW, p->d_sub);
     SelDev sd{};
-    sd.total = p->d_total; sd.sub = p->d_sub; sd.S = p->d_S; sd.sbStart = ex->d_sbStart; sd.cqiStart = ex->d_cqiStart;
+    sd.total = p->d_total; sd.sub = p->d_sub; sd.S = p->d_S; sd.sbStart = p->d_sbStart; sd.cqiStart = p->d_cqiStart;
     sd.cqiW = p->d_reCqiW; sd.sel = p->d_sel; sd.sinrSel = p->d_sinrSel; sd.sinrWb = p->d_sinrWb;
     sd.nCand = nCand; sd.nu = nu; sd.nRE = nRE; sd.nSB = p->nSB; sd.nCqiSB = p->nCqiSB;
     sd.n2 = t.n2; sd.n11 = t.n11; sd.n12 = t.n12; sd.n13 = t.n13;
@@ -477,14 +480,37 @@ int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, c
     return kOk;
 }
 
-int pmi_select_collect(PmiPlan* p, int batch, std::vector<PmiResult>& out) {
-    Ctx* ctx = p->ctx;
-    cudaStream_t st = ctx->stream;
-    const int nu = p->nLayers, nSB = p->nSB, nC = p->nCqiSB;
-    out.assign(batch, PmiResult());
+static bool plan_all_nan(const PmiPlan* p) {
     bool anyValid = false;
     for (uint8_t v : p->tab.valid) anyValid |= (v != 0);
-    if (p->reK.empty() || !anyValid) {  // dlPMISelect.m:362-379
+    return p->reK.empty() || !anyValid;  // dlPMISelect.m:362-379
+}
+
+// enqueue the D2H copies of the selection results into the plan's pinned staging buffer (no synchronisation)
+int pmi_select_collect_enqueue(PmiPlan* p, int batch, cudaStream_t st) {
+    Ctx* ctx = p->ctx;
+    if (plan_all_nan(p)) return kOk;
+    const size_t nu = p->nLayers, nSB = p->nSB, nC = p->nCqiSB;
+    const size_t bSel = sizeof(int) * (4 + nSB) * batch, bSs = sizeof(double) * nu * nSB * batch, bSw = sizeof(double) * nu * nC * batch;
+    const size_t need = bSel + bSs + bSw + 64;
+    if (p->pinBytes < need) {
+        if (p->pin) cudaFreeHost(p->pin);
+        p->pin = nullptr;
+        ISAC_CUDA_CHECK(ctx, cudaMallocHost(&p->pin, need));
+        p->pinBytes = need;
+    }
+    char* h = (char*)p->pin;
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(h, p->d_sel, bSel, cudaMemcpyDeviceToHost, st));
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(h + ((bSel + 15) / 16) * 16, p->d_sinrSel, bSs, cudaMemcpyDeviceToHost, st));
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(h + ((bSel + 15) / 16) * 16 + ((bSs + 15) / 16) * 16, p->d_sinrWb, bSw, cudaMemcpyDeviceToHost, st));
+    return kOk;
+}
+
+// parse the staged results; the caller has synchronised the stream after pmi_select_collect_enqueue
+int pmi_select_collect_finish(PmiPlan* p, int batch, std::vector<PmiResult>& out) {
+    const int nu = p->nLayers, nSB = p->nSB, nC = p->nCqiSB;
+    out.assign(batch, PmiResult());
+    if (plan_all_nan(p)) {
         for (auto& r : out) {
             r.allNaN = true;
             r.i2.assign(nSB, NAN);
@@ -493,15 +519,14 @@ int pmi_select_collect(PmiPlan* p, int batch, std::vector<PmiResult>& out) {
         }
         return kOk;
     }
-    std::vector<int> sel((size_t)(4 + nSB) * batch);
-    std::vector<double> ss((size_t)nu * nSB * batch), sw((size_t)nu * nC * batch);
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(sel.data(), p->d_sel, sizeof(int) * sel.size(), cudaMemcpyDeviceToHost, st));
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(ss.data(), p->d_sinrSel, sizeof(double) * ss.size(), cudaMemcpyDeviceToHost, st));
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(sw.data(), p->d_sinrWb, sizeof(double) * sw.size(), cudaMemcpyDeviceToHost, st));
-    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    const size_t bSel = sizeof(int) * (4 + nSB) * batch, bSs = sizeof(double) * nu * nSB * batch;
+    const char* h = (const char*)p->pin;
+    const int* sel = (const int*)h;
+    const double* ss = (const double*)(h + ((bSel + 15) / 16) * 16);
+    const double* sw = (const double*)(h + ((bSel + 15) / 16) * 16 + ((bSs + 15) / 16) * 16);
     for (int b = 0; b < batch; ++b) {
         PmiResult& r = out[b];
-        const int* s = sel.data() + (size_t)b * (4 + nSB);
+        const int* s = sel + (size_t)b * (4 + nSB);
         r.i1[0] = s[1] + 1; r.i1[1] = s[2] + 1; r.i1[2] = s[3] + 1;
         r.i2.resize(nSB);
         for (int sb = 0; sb < nSB; ++sb) r.i2[sb] = s[4 + sb] >= 0 ? (double)(s[4 + sb] + 1) : NAN;
@@ -513,6 +538,14 @@ int pmi_select_collect(PmiPlan* p, int batch, std::vector<PmiResult>& out) {
             for (int l = 0; l < nu; ++l) r.sinrWbSel[(size_t)l * nC + cs] = sw[((size_t)b * nC + cs) * nu + l];
     }
     return kOk;
+}
+
+int pmi_select_collect(PmiPlan* p, int batch, std::vector<PmiResult>& out) {
+    Ctx* ctx = p->ctx;
+    int s = pmi_select_collect_enqueue(p, batch, ctx->stream);
+    if (s) return s;
+    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return pmi_select_collect_finish(p, batch, out);
 }
 
 int pmi_get_sinr_arrays(PmiPlan* p, int batch, double* sinrPerRE, double* sinrPerSubband) {
@@ -763,24 +796,30 @@ int ul_pmi_select_run(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int
     out.subbandIndices.resize((size_t)nSB * 2);
     for (int i = 0; i < nSB; ++i) { out.subbandIndices[i] = lo[i]; out.subbandIndices[nSB + i] = hi[i]; }
     if (noiseEst == 0.0) { out.none = true; return kOk; }  // pmiSelect.m:39
-    std::vector<std::complex<double>> Wc;
-    materialize_codebook(t, Wc);  // [P][nu][nT]
-    std::vector<double2> Wd(Wc.size());
-    for (size_t i = 0; i < Wc.size(); ++i) Wd[i] = make_double2(Wc[i].real(), Wc[i].imag());
-    void *dW = nullptr, *dS = nullptr, *dB = nullptr, *dIdx = nullptr, *pin = nullptr;
-    if ((s = ctx_scratch(ctx, 2, sizeof(double2) * Wd.size(), &dW))) return s;
+    // the PUSCH codebook of (nu, P) and the band limits are uploaded once per context and cached
+    struct UlCache { Ctx* ctx; int nu, P, K, band; double2* dW; int* dIdx; };
+    static std::vector<UlCache> cache;
+    UlCache* uc = nullptr;
+    for (auto& e : cache)
+        if (e.ctx == ctx && e.nu == nu && e.P == P && e.K == K && e.band == bandSize) uc = &e;
+    if (!uc) {
+        std::vector<std::complex<double>> Wc;
+        materialize_codebook(t, Wc);  // [P][nu][nT]
+        std::vector<double2> Wd(Wc.size());
+        for (size_t i = 0; i < Wc.size(); ++i) Wd[i] = make_double2(Wc[i].real(), Wc[i].imag());
+        UlCache e{ctx, nu, P, K, bandSize, nullptr, nullptr};
+        ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)&e.dW, sizeof(double2) * Wd.size()));
+        ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)&e.dIdx, sizeof(int) * 2 * nSB));
+        ISAC_CUDA_CHECK(ctx, cudaMemcpy(e.dW, Wd.data(), sizeof(double2) * Wd.size(), cudaMemcpyHostToDevice));
+        std::vector<int> lohi(lo);
+        lohi.insert(lohi.end(), hi.begin(), hi.end());
+        ISAC_CUDA_CHECK(ctx, cudaMemcpy(e.dIdx, lohi.data(), sizeof(int) * 2 * nSB, cudaMemcpyHostToDevice));
+        cache.push_back(e);
+        uc = &cache.back();
+    }
+    void *dW = uc->dW, *dIdx = uc->dIdx, *dS = nullptr, *dB = nullptr;
     if ((s = ctx_scratch(ctx, 3, sizeof(double) * (size_t)K * nSym * nT, &dS))) return s;
     if ((s = ctx_scratch(ctx, 4, sizeof(double) * (size_t)nSB * nT, &dB))) return s;
-    if ((s = ctx_scratch(ctx, 5, sizeof(int) * 2 * (size_t)nSB, &dIdx))) return s;
-    const size_t pinBytes = sizeof(double2) * Wd.size() + sizeof(int) * 2 * nSB;
-    if ((s = ctx_pinned(ctx, 4, pinBytes, &pin))) return s;
-    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    std::memcpy(pin, Wd.data(), sizeof(double2) * Wd.size());
-    int* pidx = (int*)((char*)pin + sizeof(double2) * Wd.size());
-    std::memcpy(pidx, lo.data(), sizeof(int) * nSB);
-    std::memcpy(pidx + nSB, hi.data(), sizeof(int) * nSB);
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(dW, pin, sizeof(double2) * Wd.size(), cudaMemcpyHostToDevice, st));
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(dIdx, pidx, sizeof(int) * 2 * nSB, cudaMemcpyHostToDevice, st));
     const long long nre = (long long)K * nSym;
     const unsigned blocks = (unsigned)((nre + 127) / 128);
     const int pr = prof_begin(ctx, kProfUlPmi, st);

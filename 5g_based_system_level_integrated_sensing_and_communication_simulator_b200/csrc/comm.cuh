@@ -43,7 +43,9 @@ struct PmiPlan {
     double* d_sinrWb = nullptr;     // [nLayers][nCqiSB][batch]
     int* d_sbStart = nullptr;       // [nSB+1] RE ranges of the PMI subbands (REs sorted by subcarrier)
     int* d_cqiStart = nullptr;      // [nCqiSB+1]
-    double* d_nVar = nullptr;       // [batch]
+    double* d_nVar = nullptr;       // [batch] (unused: nVar travels as a kernel parameter)
+    void* pin = nullptr;            // pinned staging of the selection results
+    size_t pinBytes = 0;
     std::vector<uint8_t> sbHasRE, cqiSbHasRE;
 };
 
@@ -52,6 +54,9 @@ void pmi_plan_destroy(PmiPlan* p);
 // H: device complex64 [K x L x nRx x P x batch]; nVar: host [batch]
 int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, cudaStream_t st);
 int pmi_select_collect(PmiPlan* p, int batch, std::vector<PmiResult>& out);   // synchronises
+// split form: enqueue the D2H copies for several plans, synchronise once, then parse
+int pmi_select_collect_enqueue(PmiPlan* p, int batch, cudaStream_t st);
+int pmi_select_collect_finish(PmiPlan* p, int batch, std::vector<PmiResult>& out);
 // optional big outputs of the last run (host): SINRPerRE [nRE x nLayers x nCand x batch], SINRPerSubband [nSB x nLayers x nCand x batch]
 int pmi_get_sinr_arrays(PmiPlan* p, int batch, double* sinrPerRE, double* sinrPerSubband);
 

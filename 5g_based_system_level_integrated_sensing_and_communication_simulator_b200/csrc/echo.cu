@@ -26,9 +26,7 @@ namespace isac {
 struct EchoDev {
     const float2* tx;      // [T x nTx]
     const float2* noise;   // [T x nAnts] standard normals, or nullptr
-    const float2* steer;   // [nAnts x nTgt] float2 (device)
-    const int* symStart;   // [nSymRx] first CP sample of each symbol
-    const int* cpLen;      // [nSymRx]
+    const float2* steer;   // [nAnts x nTgt] float2 (device) when it does not fit the inline table
     const float2* tw;
     float2* out;           // [nSc x nSymOut x nAnts]
     long long T;
@@ -40,6 +38,12 @@ struct EchoDev {
     int shift[kEchoMaxTargets];
     float2 beta[kEchoMaxTargets];
     double fdTs[kEchoMaxTargets];
+    // symbol timing is periodic per subframe: start(s) = (s / symPer) * subframeLen + startTab[s % symPer]
+    int symPer, subframeLen;
+    int cpTab[kEchoMaxSymPerSubframe];
+    int startTab[kEchoMaxSymPerSubframe];
+    int steerInline;       // 1: steering vectors travel in steerTab (no upload, no synchronisation)
+    float2 steerTab[kEchoInlineSteer];
 };
 
 // Philox4x32-10
@@ -103,16 +107,16 @@ echo_demod_kernel(const EchoDev p) {
     float2* steerS = Wf + (size_t)p.nTgt * p.nSc;                  // [nAnts x nTgt]
     __shared__ double baseCycles[kEchoMaxTargets];
     const int s = blockIdx.x;
-    for (int i = threadIdx.x; i < p.nAnts * p.nTgt; i += blockDim.x) steerS[i] = p.steer[i];
+    for (int i = threadIdx.x; i < p.nAnts * p.nTgt; i += blockDim.x) steerS[i] = p.steerInline ? p.steerTab[i] : p.steer[i];
     if (s >= p.nSymRx) {  // zero padding up to txDimension(2) (monoStaticSensing.m:19-21)
         for (int r = 0; r < p.nAnts; ++r)
             for (int k = threadIdx.x; k < p.nSc; k += blockDim.x)
                 p.out[((long long)r * p.nSymOut + s) * p.nSc + k] = make_float2(0.f, 0.f);
         return;
     }
-    const int cp = p.cpLen[s];
+    const int cp = p.cpTab[s % p.symPer];
     const int off = cp / 2;                       // fix(cp * CyclicPrefixFraction), fraction 0.5
-    const long long n0 = (long long)p.symStart[s] + off;
+    const long long n0 = (long long)(s / p.symPer) * p.subframeLen + p.startTab[s % p.symPer] + off;
     if (threadIdx.x < p.nTgt) {
         const double c = p.fdTs[threadIdx.x] * (double)n0;
         baseCycles[threadIdx.x] = c - floor(c);
@@ -198,7 +202,7 @@ echo_demod_kernel(const EchoDev p) {
 __global__ void __launch_bounds__(256)
 radar_channel_kernel(const EchoDev p, float2* __restrict__ rxWave) {
     extern __shared__ float2 steerS[];
-    for (int i = threadIdx.x; i < p.nAnts * p.nTgt; i += blockDim.x) steerS[i] = p.steer[i];
+    for (int i = threadIdx.x; i < p.nAnts * p.nTgt; i += blockDim.x) steerS[i] = p.steerInline ? p.steerTab[i] : p.steer[i];
     __syncthreads();
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= p.T) return;
@@ -279,16 +283,23 @@ static int common_dev(Ctx* ctx, const EchoConfig& c, const float2* tx, const flo
     std::vector<float2> steerHost;
     int s = fill_targets(ctx, c, d, steerHost);
     if (s) return s;
-    void* dSteer = nullptr;
-    if ((s = ctx_scratch(ctx, 15, sizeof(float2) * steerHost.size(), &dSteer))) return s;
-    void* pin = nullptr;
-    if ((s = ctx_pinned(ctx, 7, sizeof(float2) * steerHost.size(), &pin))) return s;
-    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));  // the pinned staging buffer may still be in flight
-    std::memcpy(pin, steerHost.data(), sizeof(float2) * steerHost.size());
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(dSteer, pin, sizeof(float2) * steerHost.size(), cudaMemcpyHostToDevice, st));
+    if (steerHost.size() <= (size_t)kEchoInlineSteer) {
+        d.steerInline = 1;
+        for (size_t i = 0; i < steerHost.size(); ++i) d.steerTab[i] = steerHost[i];
+        d.steer = nullptr;
+    } else {
+        void* dSteer = nullptr;
+        if ((s = ctx_scratch(ctx, 15, sizeof(float2) * steerHost.size(), &dSteer))) return s;
+        void* pin = nullptr;
+        if ((s = ctx_pinned(ctx, 7, sizeof(float2) * steerHost.size(), &pin))) return s;
+        ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));  // the pinned staging buffer may still be in flight
+        std::memcpy(pin, steerHost.data(), sizeof(float2) * steerHost.size());
+        ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(dSteer, pin, sizeof(float2) * steerHost.size(), cudaMemcpyHostToDevice, st));
+        d.steerInline = 0;
+        d.steer = (const float2*)dSteer;
+    }
     d.tx = tx;
     d.noise = noise;
-    d.steer = (const float2*)dSteer;
     d.tw = ctx_twiddle(ctx);
     d.T = c.T;
     d.nTx = c.nTx;
@@ -332,32 +343,33 @@ int mono_static_sensing_run(Ctx* ctx, const EchoConfig& c, const float2* tx, con
         set_error(ctx, "monoStaticSensing: unsupported numerology");
         return kErrUnsupported;
     }
+    if (c.symbolsPerSubframe > kEchoMaxSymPerSubframe) {
+        set_error(ctx, "monoStaticSensing: more than 56 symbols per subframe (subcarrier spacing > 60 kHz) is not supported");
+        return kErrUnsupported;
+    }
     // whole symbols contained in the waveform (nrOFDMDemodulate)
-    std::vector<int> start, cp;
+    int nSymRx = 0;
     long long acc = 0;
     for (int s = 0;; ++s) {
         const int len = c.cpLengths[s % c.symbolsPerSubframe] + c.nfft;
         if (acc + len > c.T) break;
-        start.push_back((int)acc);
-        cp.push_back(c.cpLengths[s % c.symbolsPerSubframe]);
         acc += len;
+        ++nSymRx;
     }
-    const int nSymRx = (int)start.size();
     const int nSymOut = nSymRx > c.nSymTx ? nSymRx : c.nSymTx;  // pad up to txDimension(2) (:19-21)
     if (nSymRxOut) *nSymRxOut = nSymOut;
     if (!echoGrid) return kOk;  // size query
     EchoDev d;
     int s = common_dev(ctx, c, tx, noise, noiseMode, seed, d, st);
     if (s) return s;
-    void *dStart = nullptr, *pin = nullptr;
-    if ((s = ctx_scratch(ctx, 14, sizeof(int) * 2 * (size_t)(nSymRx + 1), &dStart))) return s;
-    if ((s = ctx_pinned(ctx, 6, sizeof(int) * 2 * (size_t)(nSymRx + 1), &pin))) return s;
-    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    std::memcpy(pin, start.data(), sizeof(int) * nSymRx);
-    std::memcpy((int*)pin + nSymRx, cp.data(), sizeof(int) * nSymRx);
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(dStart, pin, sizeof(int) * 2 * (size_t)nSymRx, cudaMemcpyHostToDevice, st));
-    d.symStart = (const int*)dStart;
-    d.cpLen = (const int*)dStart + nSymRx;
+    d.symPer = c.symbolsPerSubframe;
+    int off = 0;
+    for (int q = 0; q < c.symbolsPerSubframe; ++q) {
+        d.cpTab[q] = c.cpLengths[q];
+        d.startTab[q] = off;
+        off += c.cpLengths[q] + c.nfft;
+    }
+    d.subframeLen = off;
     d.nSymRx = nSymRx;
     d.nSymOut = nSymOut;
     d.nfft = c.nfft;

@@ -5,7 +5,9 @@
 
 namespace isac {
 
-constexpr int kEchoMaxTargets = 16;  // LoS targets per call (bounded further by shared memory: nTgt*nSc*8 B)
+constexpr int kEchoMaxTargets = 16;
+constexpr int kEchoMaxSymPerSubframe = 56;  // symbols per subframe up to 60 kHz subcarrier spacing
+constexpr int kEchoInlineSteer = 128;        // nAnts*nTargets steering entries carried as kernel parameters  // LoS targets per call (bounded further by shared memory: nTgt*nSc*8 B)
 
 // host-side description (mirrors isac_echo_config of include/isac_b200.h)
 struct EchoConfig {
