@@ -1,0 +1,47 @@
+/* estResults = isac_fft2d_mex(cfg, rxGrid, txGrid)
+ *   cfg   : struct nIFFT,nFFT,rRes,vRes,cutRows[2],cutCols[2],Pfa,isUpa,nAnts,nX,nY,aGran,aMax,eGran,eMax
+ *   grids : single complex [nSc x nSym x nAnts]
+ * Marshals sensing.estimation.fft2D (+sensing/+estimation/fft2D.m:1) onto isac_fft2d_host. */
+#include "isac_mex_common.h"
+#include <vector>
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs != 3) mexErrMsgIdAndTxt("isac:fft2d:nargin", "three inputs required");
+    const mxArray *cfg = prhs[0], *rx = prhs[1], *tx = prhs[2];
+    if (!mxIsSingle(rx) || !mxIsComplex(rx) || !mxIsSingle(tx) || !mxIsComplex(tx))
+        mexErrMsgIdAndTxt("isac:fft2d:type", "grids must be complex single");
+    const mwSize* d = mxGetDimensions(rx);
+    const int nd = (int)mxGetNumberOfDimensions(rx);
+    isac_rdm_config r = {};
+    r.nSc = (int32_t)d[0]; r.nSym = (int32_t)d[1]; r.nAnts = nd > 2 ? (int32_t)d[2] : 1;
+    r.nIFFT = (int32_t)field_scalar(cfg, "nIFFT"); r.nFFT = (int32_t)field_scalar(cfg, "nFFT");
+    const double* cr = mxGetDoubles(mxGetField(cfg, 0, "cutRows"));
+    const double* cc = mxGetDoubles(mxGetField(cfg, 0, "cutCols"));
+    r.cutRow0 = (int32_t)cr[0]; r.cutRow1 = (int32_t)cr[1]; r.cutCol0 = (int32_t)cc[0]; r.cutCol1 = (int32_t)cc[1];
+    r.guardRows = r.guardCols = 2; r.trainRows = r.trainCols = 1;      /* cfar2D.m:32-33 */
+    r.maxBatch = 1; r.pfa = field_scalar(cfg, "Pfa"); r.kaiserBeta = 3.0;   /* fft2D.m:135 */
+    isac_doa_config a = {};
+    a.isUpa = (int32_t)field_scalar(cfg, "isUpa"); a.nAnts = (int32_t)field_scalar(cfg, "nAnts");
+    a.nX = (int32_t)field_scalar(cfg, "nX"); a.nY = (int32_t)field_scalar(cfg, "nY"); a.d = 0.5;
+    a.aGran = field_scalar(cfg, "aGran"); a.aMax = field_scalar(cfg, "aMax");
+    a.eGran = field_scalar(cfg, "eGran"); a.eMax = field_scalar(cfg, "eMax");
+    isac_sense_plan* plan = nullptr;   /* a production gateway caches the plan per configuration */
+    isac_mex_check(isac_sense_plan_create(isac_mex_ctx(), &r, &a, field_scalar(cfg, "rRes"), field_scalar(cfg, "vRes"), &plan), "fft2D");
+    const int maxOut = 4096;
+    std::vector<double> rng(maxOut), vel(maxOut), azi(ISAC_MAX_PEAKS);
+    int32_t nR = 0, nV = 0, nA = 0, L = 0, st = 0;
+    int rc = isac_fft2d_host(plan, mxGetComplexSingles(rx), mxGetComplexSingles(tx), 1, maxOut, rng.data(), &nR, vel.data(), &nV,
+                             azi.data(), &nA, &L, &st);
+    isac_sense_plan_destroy(plan);
+    isac_mex_check(rc, "fft2D");
+    isac_mex_check(st, "fft2D");   /* zero detections -> error, like findpeaks(...,'NPeaks',0) (music.m:102) */
+    const char* names[] = {"rngEst", "velEst", "aziEst", "eleEst"};
+    plhs[0] = mxCreateStructMatrix(1, 1, 4, names);
+    auto row = [](const double* v, int n) { mxArray* m = mxCreateDoubleMatrix(1, n, mxREAL); for (int i = 0; i < n; ++i) mxGetDoubles(m)[i] = v[i]; return m; };
+    mxSetField(plhs[0], 0, "rngEst", row(rng.data(), nR));
+    mxSetField(plhs[0], 0, "velEst", row(vel.data(), nV));
+    mxSetField(plhs[0], 0, "aziEst", row(azi.data(), nA));
+    mxArray* ele = mxCreateDoubleMatrix(1, nA, mxREAL);
+    for (int i = 0; i < nA; ++i) mxGetDoubles(ele)[i] = mxGetNaN();   /* music.m:104 */
+    mxSetField(plhs[0], 0, "eleEst", ele);
+}

@@ -1,0 +1,121 @@
+"""CPU-only known-answer tests that pin the float64 oracle (oracle/sensing.py): the reference ships no golden
+vectors, so the restatement is anchored on closed forms and on independent SciPy code."""
+import importlib
+import math
+
+import numpy as np
+import pytest
+import scipy.signal
+
+from oracle import sensing as S
+
+PKG = "5g_based_system_level_integrated_sensing_and_communication_simulator_b200"
+W = importlib.import_module(PKG + ".workloads")
+
+
+def test_kaiser_matches_scipy():
+    for n in (1, 2, 17, 624, 4096):
+        assert np.allclose(S.kaiser(n, 3.0), scipy.signal.windows.kaiser(n, 3.0, sym=True), rtol=1e-13, atol=1e-15)
+
+
+def test_findpeaks_semantics():
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(500)
+    pk, loc = S.findpeaks(y, 7)
+    ref, _ = scipy.signal.find_peaks(y)
+    top = ref[np.argsort(-y[ref], kind="stable")][:7]
+    assert np.array_equal(loc - 1, top) and np.array_equal(pk, y[top])
+    # plateau -> first sample; end points never peaks; fewer than NPeaks available
+    assert np.array_equal(S.findpeaks([0, 1, 3, 3, 3, 1, 5], 4)[1], [3])
+    assert np.array_equal(S.findpeaks([5, 1, 2, 1, 4], 3)[1], [3])
+    with pytest.raises(ValueError):
+        S.findpeaks(y, 0)
+
+
+def test_sind_exact_and_unique_stable():
+    assert S.sind(180.0) == 0 and S.sind(-180.0) == 0 and S.sind(90.0) == 1 and S.cosd(90.0) == 0 and S.sind(360.0) == 0
+    assert abs(S.sind(30.0) - 0.5) < 1e-15
+    assert np.array_equal(S.unique_stable(np.array([3.0, 1.0, 3.0, 2.0, 1.0])), [3.0, 1.0, 2.0])
+
+
+def test_cfar_threshold_and_strict_compare():
+    assert abs(S.cfar_threshold_factor(24, 1e-9) - 32.91296893587972) < 1e-10
+    P = np.ones((40, 30))
+    cf = {"CUTIdx": np.array([[10, 11], [12, 12]]), "GuardBandSize": (2, 2), "TrainingBandSize": (1, 1), "Pfa": 1e-9}
+    assert S.cfar2d_detect(P, cf).shape[1] == 0
+    a = S.cfar_threshold_factor(24, 1e-9)
+    P[9, 11] = a * (1 + 1e-9)          # CUT (10,12): just above -> detected
+    P[10, 11] = a                       # CUT (11,12): equal to threshold*noise?  its guard cell (10,12) is excluded
+    d = S.cfar2d_detect(P, cf)
+    assert d.tolist() == [[10], [12]]
+    assert np.array_equal(S.cfar2d_detect_exact(P, cf), d)
+    with pytest.raises(ValueError):
+        S.cfar2d_detect(P, dict(cf, CUTIdx=np.array([[2], [12]])))
+    rng = np.random.default_rng(1)
+    Q = rng.exponential(size=(64, 48))
+    Q[rng.integers(5, 59, 12), rng.integers(5, 43, 12)] *= 200
+    rr, cc = np.meshgrid(np.arange(5, 60), np.arange(5, 44), indexing="ij")
+    cf2 = dict(cf, CUTIdx=np.stack([rr.reshape(-1, order="F"), cc.reshape(-1, order="F")]), Pfa=1e-4)
+    assert np.array_equal(S.cfar2d_detect(Q, cf2), S.cfar2d_detect_exact(Q, cf2))
+
+
+def test_rdm_closed_form():
+    """The kernels' closed form equals the literal restatement of fft2D.m:37-46."""
+    rng = np.random.default_rng(0)
+    for (nSc, nSym, nA, N, F) in [(300, 77, 3, 512, 64), (288, 42, 4, 512, 64), (200, 10, 2, 256, 16)]:
+        rx = rng.standard_normal((nSc, nSym, nA)) + 1j * rng.standard_normal((nSc, nSym, nA))
+        tx = rng.standard_normal((nSc, nSym, nA)) + 1j * rng.standard_normal((nSc, nSym, nA))
+        ref = S.rdm_2dfft({"nIFFT": N, "nFFT": F}, rx, tx)
+        y = np.fft.ifft(rx * np.conj(tx) * S.kaiser(nSc, 3.0)[:, None, None], N, axis=0) * math.sqrt(N)
+        M = min(nSym, F)
+        sp = np.arange(M)
+        ys = y[:, (sp + nSym // 2) % nSym, :] * ((-1.0) ** sp)[None, :, None]
+        Z = np.fft.fft(ys, F, axis=1) / math.sqrt(F) * S.kaiser(N, 3.0)[(np.arange(N) - N // 2) % N][:, None, None]
+        assert np.abs(Z - ref).max() <= 1e-14 * np.abs(ref).max()
+
+
+def test_ofdm_roundtrip_and_numerology():
+    for nrb, scs, nfft, fs in ((52, 15, 1024, 15.36e6), (273, 30, 4096, 122.88e6), (24, 15, 512, 7.68e6)):
+        info = S.ofdm_info(nrb, scs)
+        assert info["Nfft"] == nfft and info["SampleRate"] == fs
+        assert info["SymbolLengths"].sum() == fs / 1000                # one subframe
+        num = W.ofdm_numerology(nrb, scs)
+        assert np.array_equal(num["CyclicPrefixLengths"], info["CyclicPrefixLengths"])
+    grid = W.qpsk_grid(288, 28, 2, 3)
+    wave = W.ofdm_modulate(grid, 24, 15)
+    back = S.ofdm_demodulate(24, 15, wave)
+    assert back.shape == grid.shape
+    assert np.abs(back - grid).max() < 1e-12                              # plain fft(ifft(.)) with the CP-fraction ramp undone
+
+
+def test_single_target_lands_in_the_predicted_bins():
+    """Noiseless target: peak row = s*nIFFT/Nfft + 1; echo passes through every stage."""
+    cell, car, wave = W.cell_config("tiny")
+    rp = S.radar_params(cell, car, wave)
+    grid, txw = W.sensing_tx("tiny", 1)
+    rx = S.mono_static_sensing(txw, grid.shape, car, rp, [1], np.zeros(txw.shape, complex))
+    P = np.abs(S.rdm_2dfft(rp, rx, grid)[:, :, 0]) ** 2
+    r, c = np.unravel_index(np.argmax(P), P.shape)
+    s = math.ceil(2 * rp["range"][0] / S.LIGHTSPEED * rp["fs"])
+    assert r == s * rp["nIFFT"] // wave["Nfft"]
+    # the symbol-axis rotation before the zero-padded Doppler FFT and the mis-stated Tsri (radarParams.m:34-35) bias
+    # the velocity axis: only require the right neighbourhood
+    assert abs((c - rp["nFFT"] / 2) * rp["vRes"] - rp["velocity"][0]) <= 2 * rp["vRes"]
+    assert abs(rp["rRes"] - S.LIGHTSPEED / (2 * 15e3 * 512)) < 1e-9 and rp["nIFFT"] == 512 and rp["nFFT"] == 64
+
+
+def test_music_on_exact_covariance():
+    n = 16
+    rp = {"antennaType": {"type": "ula", "nV": 8, "p": 2, "d": 0.5}, "azimuthScanScale": 360, "azimuthScanGranularity": 1}
+    angs = np.array([-50.0, 20.0])
+    A = np.exp(-2j * np.pi * np.arange(n)[:, None] * 0.5 * S.sind(angs)[None, :])
+    Ra = A @ np.diag([2.0, 1.0]) @ A.conj().T + 0.1 * np.eye(n)
+    L, azi, ele, PdB = S.music_doa(2, rp, Ra)
+    assert L == 2 and np.all(np.isnan(ele))
+    # +-180 scan of a ULA is mirror ambiguous: sin(x) = sin(180-x)
+    assert set(azi.tolist()) <= {-50.0, -130.0, 20.0, 160.0}
+    assert S.determine_num_targets(np.array([0.1, 0.1, 0.1, 0.1, 5.0, 9.0])) >= 1
+    # on-grid steering vector is orthogonal to the noise subspace: P = 1/eps at the true angle
+    Uann, _ = S.noise_projector(Ra, 2)
+    a = np.exp(-2j * np.pi * np.arange(n) * 0.5 * S.sind(20.0))
+    assert abs(np.vdot(a, Uann @ a)) < 1e-10
