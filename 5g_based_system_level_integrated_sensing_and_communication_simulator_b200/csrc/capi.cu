@@ -17,7 +17,12 @@ namespace isac {
 void set_error(Ctx* ctx, const std::string& msg) {
     if (ctx) ctx->err = msg;
 }
-const float2* ctx_twiddle(Ctx* ctx) { return ctx->d_twiddle; }
+void ctx_fft_tw(Ctx* ctx, int N, const float2** tw1, const float2** tw2) {
+    int i = 0;
+    while ((16 << i) < N) ++i;
+    *tw1 = ctx->d_twiddle + ctx->tw1Off[i];
+    *tw2 = ctx->d_twiddle + ctx->tw2Off[i];
+}
 
 static cudaEvent_t take_event(Ctx* ctx) {
     if (!ctx->eventPool.empty()) {
@@ -141,13 +146,27 @@ int isac_create(isac_ctx** out, int device) {
         return ISAC_ERR_CUDA;
     }
     c->stream = c->ownStream;
-    std::vector<float2> tw(kTwiddleN);
-    for (int m = 0; m < kTwiddleN; ++m) {
-        const double a = 2.0 * M_PI * (double)m / (double)kTwiddleN;
-        tw[m] = make_float2((float)std::cos(a), (float)std::sin(a));
+    // twiddle tables for N = 16..4096 (N = R1*R2*16: N <= 256 -> R1 = 1, R2 = N/16; else R1 = N/256, R2 = 16)
+    std::vector<float2> tw;
+    for (int i = 0; i < 9; ++i) {
+        const int N = 16 << i;
+        const int R1 = N <= 256 ? 1 : N / 256, R2 = N <= 256 ? N / 16 : 16, N2 = N / R1;
+        c->tw1Off[i] = tw.size();
+        for (int k1 = 1; k1 < R1; ++k1)
+            for (int m = 0; m < N2; ++m) {
+                const double a = 2.0 * M_PI * (double)m * (double)k1 / (double)N;
+                tw.push_back(make_float2((float)std::cos(a), (float)std::sin(a)));
+            }
+        c->tw2Off[i] = tw.size();
+        for (int cc = 1; cc < R2; ++cc)
+            for (int b = 0; b < 16; ++b) {
+                const double a = 2.0 * M_PI * (double)b * (double)cc / (double)N2;
+                tw.push_back(make_float2((float)std::cos(a), (float)std::sin(a)));
+            }
+        tw.push_back(make_float2(1.f, 0.f));  // keep the table pointers valid when a pass has no twiddles
     }
-    if (cudaMalloc((void**)&c->d_twiddle, sizeof(float2) * kTwiddleN) != cudaSuccess ||
-        cudaMemcpy(c->d_twiddle, tw.data(), sizeof(float2) * kTwiddleN, cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (cudaMalloc((void**)&c->d_twiddle, sizeof(float2) * tw.size()) != cudaSuccess ||
+        cudaMemcpy(c->d_twiddle, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         g_createError = "isac_create: twiddle table upload failed";
         delete h;
         return ISAC_ERR_CUDA;

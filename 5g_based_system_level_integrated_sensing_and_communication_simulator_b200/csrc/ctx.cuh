@@ -13,7 +13,8 @@ struct Ctx {
     int ccMajor = 0;
     cudaStream_t ownStream = nullptr;
     cudaStream_t stream = nullptr;  // stream every launch / copy is enqueued on
-    float2* d_twiddle = nullptr;    // exp(+2*pi*i*m/4096)
+    float2* d_twiddle = nullptr;    // packed per-size twiddle tables (see fft_core.cuh)
+    size_t tw1Off[9] = {}, tw2Off[9] = {};  // offsets for N = 16 << i
     std::string err;
     void* pinned[kPinnedSlots] = {};
     size_t pinnedBytes[kPinnedSlots] = {};

@@ -27,7 +27,7 @@ struct EchoDev {
     const float2* tx;      // [T x nTx]
     const float2* noise;   // [T x nAnts] standard normals, or nullptr
     const float2* steer;   // [nAnts x nTgt] float2 (device) when it does not fit the inline table
-    const float2* tw;
+    FftTw tw;
     float2* out;           // [nSc x nSymOut x nAnts]
     long long T;
     int nTx, nAnts, nTgt, nSymRx, nSymOut, nfft, nSc;
@@ -300,7 +300,6 @@ static int common_dev(Ctx* ctx, const EchoConfig& c, const float2* tx, const flo
     }
     d.tx = tx;
     d.noise = noise;
-    d.tw = ctx_twiddle(ctx);
     d.T = c.T;
     d.nTx = c.nTx;
     d.nAnts = c.nTx;  // Rx and Tx share the array (radarParams.m:88,105)
@@ -375,6 +374,7 @@ int mono_static_sensing_run(Ctx* ctx, const EchoConfig& c, const float2* tx, con
     d.nfft = c.nfft;
     d.nSc = c.nSc;
     d.out = echoGrid;
+    ctx_fft_tw(ctx, c.nfft, &d.tw.tw1, &d.tw.tw2);
     cudaError_t e;
     const int pr = prof_begin(ctx, kProfEcho, st);
     switch (c.nfft) {

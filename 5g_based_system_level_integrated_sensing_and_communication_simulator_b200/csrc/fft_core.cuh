@@ -103,11 +103,17 @@ __device__ __forceinline__ void dftR(float2* v) {
     if constexpr (R == 16) dft16<SIGN>(v);
 }
 
-// master twiddle table tw[m] = exp(+2*pi*i*m/4096) lives in global memory (context-owned,
-// computed in float64 on the host) and is passed to every FFT kernel as a pointer.
+// Per-size twiddle tables (context-owned, computed in float64 on the host), laid out in the order the passes
+// consume them so that every warp-wide load is a contiguous 128/256-byte segment:
+//   tw1[(k1-1)*N2 + m] = exp(+2 pi i m k1 / N)     m < N2 = N/R1, k1 = 1..R1-1   (pass 1, lanes = consecutive m)
+//   tw2[(c-1)*16 + b]  = exp(+2 pi i b c / N2)     b < 16,        c  = 1..R2-1   (pass 2, lanes = consecutive b)
+struct FftTw {
+    const float2* tw1;
+    const float2* tw2;
+};
 template <int SIGN>
-__device__ __forceinline__ float2 twiddle(const float2* __restrict__ tw, int idx) {
-    float2 w = __ldg(tw + (idx & (kTwiddleN - 1)));
+__device__ __forceinline__ float2 tw_load(const float2* __restrict__ p) {
+    float2 w = __ldg(p);
     if (SIGN < 0) w.y = -w.y;
     return w;
 }
@@ -129,9 +135,9 @@ struct FftGeom {
 // smem points at this instance's slot 0 (already offset by nl); RT = interleave stride.
 template <int R1, int R2, int SIGN, bool PAD, class Load>
 __device__ __forceinline__ void block_fft(float2 (&v)[16], float2* smem, const int RT, const int tf,
-                                          const float2* __restrict__ tw, Load load) {
+                                          const FftTw tw, Load load) {
     using G = FftGeom<R1, R2, PAD>;
-    constexpr int N = G::N, NT = G::NT, N2 = G::N2;
+    constexpr int NT = G::NT, N2 = G::N2;
     if constexpr (R1 > 1) {
 #pragma unroll
         for (int i = 0; i < 16 / R1; ++i) {
@@ -141,7 +147,7 @@ __device__ __forceinline__ void block_fft(float2 (&v)[16], float2* smem, const i
             dftR<R1, SIGN>(&v[i * R1]);
 #pragma unroll
             for (int k1 = 1; k1 < R1; ++k1)
-                v[i * R1 + k1] = cmul(v[i * R1 + k1], twiddle<SIGN>(tw, (m * k1) * (kTwiddleN / N)));
+                v[i * R1 + k1] = cmul(v[i * R1 + k1], tw_load<SIGN>(tw.tw1 + (k1 - 1) * N2 + m));
 #pragma unroll
             for (int k1 = 0; k1 < R1; ++k1) smem[G::addr(k1, m >> 4, m & 15) * RT] = v[i * R1 + k1];
         }
@@ -160,7 +166,7 @@ __device__ __forceinline__ void block_fft(float2 (&v)[16], float2* smem, const i
             dftR<R2, SIGN>(&v[i * R2]);
 #pragma unroll
             for (int c = 1; c < R2; ++c)
-                v[i * R2 + c] = cmul(v[i * R2 + c], twiddle<SIGN>(tw, (b * c) * (kTwiddleN / N2)));
+                v[i * R2 + c] = cmul(v[i * R2 + c], tw_load<SIGN>(tw.tw2 + (c - 1) * 16 + b));
 #pragma unroll
             for (int c = 0; c < R2; ++c) smem[G::addr(k1, c, b) * RT] = v[i * R2 + c];
         }

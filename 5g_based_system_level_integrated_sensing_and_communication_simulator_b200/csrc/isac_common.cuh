@@ -52,7 +52,9 @@ enum Status : int {
 struct Ctx;  // defined in capi.cu
 
 void set_error(Ctx* ctx, const std::string& msg);
-const float2* ctx_twiddle(Ctx* ctx);  // device pointer to exp(+2*pi*i*m/4096), m < 4096
+struct FftTw;
+// per-size twiddle tables for block_fft (N = 16 << log2N16); see fft_core.cuh
+void ctx_fft_tw(Ctx* ctx, int N, const float2** tw1, const float2** tw2);
 
 // Optional CUDA-event profiling of kernel groups on the launching stream (used by bench.py for the
 // live roofline figure) and a counter of this library's kernel launches.

@@ -34,7 +34,8 @@ struct RdmDev {
     const float2* tx;
     const float* win1;
     const float* win2;
-    const float2* tw;
+    FftTw twR;  // tables of the range IFFT size
+    FftTw twD;  // tables of the Doppler FFT size
     float2* inter;
     float* pow;
     int nSc, nSym, nAnts, nIFFT, nFFT, M;
@@ -69,7 +70,7 @@ rdm_range_ifft_kernel(const RdmDev p) {
         return make_float2(0.f, 0.f);
     };
     float2 v[16];
-    block_fft<R1, R2, +1, true>(v, smem + local * G::kElems, 1, tf, p.tw, load);
+    block_fft<R1, R2, +1, true>(v, smem + local * G::kElems, 1, tf, p.twR, load);
     if (active) {
         float2* __restrict__ out = p.inter + (page * p.M + sp) * (long long)p.nIFFT;
         const float sgn = (sp & 1) ? -1.f : 1.f;  // e^{+i pi s'}: Doppler fftshift folded in
@@ -100,7 +101,7 @@ rdm_doppler_fft_kernel(const RdmDev p, const int RT, const float invF) {
         return make_float2(0.f, 0.f);
     };
     float2 v[16];
-    block_fft<R1, R2, -1, false>(v, smem + nl, RT, tf, p.tw, load);
+    block_fft<R1, R2, -1, false>(v, smem + nl, RT, tf, p.twD, load);
     float* __restrict__ out = p.pow + page * (long long)p.nFFT * nIFFT + n;
 #pragma unroll
     for (int d = 0; d < 16; ++d) {
@@ -411,7 +412,8 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
         d.tx = tx + b * gridElems;
         d.win1 = p->d_win1;
         d.win2 = p->d_win2;
-        d.tw = ctx_twiddle(ctx);
+        ctx_fft_tw(ctx, c.nIFFT, &d.twR.tw1, &d.twR.tw2);
+        ctx_fft_tw(ctx, c.nFFT, &d.twD.tw1, &d.twD.tw2);
         d.inter = p->d_inter;
         d.pow = pow + b * powElems;
         d.nSc = c.nSc;
