@@ -53,11 +53,13 @@ pmi_sinr_kernel(const PmiDev p) {
     }
     __syncthreads();
     const int nB = p.NB * p.nBeams * R;
+    // Bf[(r*NB + blk)*nBeams + beam]: for a fixed (r, blk) the lanes of a warp (consecutive candidates = consecutive
+    // beams in the host-chosen storage order) read consecutive 16-byte words -> no shared-memory bank conflicts
     for (int i = threadIdx.x; i < nB; i += blockDim.x) {
-        const int r = i % R, bm = (i / R) % p.nBeams, blk = i / (R * p.nBeams);
+        const int bm = i % p.nBeams, blk = (i / p.nBeams) % p.NB, r = i / (p.nBeams * p.NB);
         double2 acc = make_double2(0.0, 0.0);
         for (int q = 0; q < p.Pb; ++q) acc = zadd(acc, zmul(Hs[r * P + blk * p.Pb + q], p.beams[bm * p.Pb + q]));
-        Bf[i] = acc;  // index (blk*nBeams + bm)*R + r
+        Bf[i] = acc;
     }
     __syncthreads();
     const double nVar = p.nVar[b];
@@ -86,10 +88,11 @@ pmi_sinr_kernel(const PmiDev p) {
             double2 g[NU];
 #pragma unroll
             for (int j = 0; j < NU; ++j) {
-                double2 acc = zmul(cf[j][0], Bf[(0 * p.nBeams + beamOf[j]) * R + r]);
-                if (p.NB > 1) acc = zadd(acc, zmul(cf[j][1], Bf[(1 * p.nBeams + beamOf[j]) * R + r]));
+                const double2* __restrict__ Br = Bf + (size_t)r * p.NB * p.nBeams + beamOf[j];
+                double2 acc = zmul(cf[j][0], Br[0]);
+                if (p.NB > 1) acc = zadd(acc, zmul(cf[j][1], Br[p.nBeams]));
                 for (int blk = 2; blk < p.NB; ++blk)
-                    acc = zadd(acc, zmul(p.layerCoef[(c * NU + j) * p.NB + blk], Bf[(blk * p.nBeams + beamOf[j]) * R + r]));
+                    acc = zadd(acc, zmul(p.layerCoef[(c * NU + j) * p.NB + blk], Br[blk * p.nBeams]));
                 g[j] = make_double2(acc.x * sc, acc.y * sc);
             }
 #pragma unroll
@@ -105,9 +108,10 @@ pmi_sinr_kernel(const PmiDev p) {
             double d = A[TRI(j, j)].x;
 #pragma unroll
             for (int k = 0; k < j; ++k) d -= A[TRI(j, k)].x * A[TRI(j, k)].x + A[TRI(j, k)].y * A[TRI(j, k)].y;
-            const double ljj = sqrt(d);
-            A[TRI(j, j)] = make_double2(ljj, 0.0);
-            const double inv = 1.0 / ljj;
+            // store 1/L_jj on the diagonal (one rsqrt + one Newton step instead of sqrt and two divisions)
+            double inv = rsqrt(d);
+            inv = inv * (1.5 - 0.5 * d * inv * inv);
+            A[TRI(j, j)] = make_double2(inv, 0.0);
 #pragma unroll
             for (int i = j + 1; i < NU; ++i) {
                 double2 s = A[TRI(i, j)];
@@ -120,14 +124,14 @@ pmi_sinr_kernel(const PmiDev p) {
 #pragma unroll
         for (int cc = 0; cc < NU; ++cc) {
             double2 x[NU];
-            x[cc] = make_double2(1.0 / A[TRI(cc, cc)].x, 0.0);
+            x[cc] = make_double2(A[TRI(cc, cc)].x, 0.0);  // diagonal holds 1/L_cc
             double nrm = x[cc].x * x[cc].x;
 #pragma unroll
             for (int i = cc + 1; i < NU; ++i) {
                 double2 s = make_double2(0.0, 0.0);
 #pragma unroll
                 for (int k = cc; k < i; ++k) s = zadd(s, zmul(A[TRI(i, k)], x[k]));
-                const double inv = -1.0 / A[TRI(i, i)].x;
+                const double inv = -A[TRI(i, i)].x;
                 x[i] = make_double2(s.x * inv, s.y * inv);
                 nrm += x[i].x * x[i].x + x[i].y * x[i].y;
             }
@@ -360,13 +364,21 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
     for (int i = 0; i < p->nCqiSB; ++i) p->cqiSbHasRE[i] = cqiStart[i + 1] > cqiStart[i];
     const CodebookTable& t = p->tab;
     const int nCand = t.nCand(), nu = nLayers;
+    // storage order of the beams in shared memory: beam (l, m) = l*L2 + m is stored at m*L1 + l so that candidates that
+    // are consecutive in the index order (i2 fastest, then i11 = l) touch consecutive shared-memory words
+    const int L2 = t.nBeams > 1 ? p->cfg.N2 * p->cfg.O2 : 1, L1 = t.nBeams / L2;
+    auto store_idx = [&](int beam) { return t.nBeams > 1 ? (beam % L2) * L1 + beam / L2 : 0; };
     std::vector<double2> beams(t.beams.size()), coef((size_t)nCand * nu * t.NB);
-    for (size_t i = 0; i < t.beams.size(); ++i) beams[i] = make_double2(t.beams[i].real(), t.beams[i].imag());
+    for (int bm = 0; bm < t.nBeams; ++bm)
+        for (int q = 0; q < t.Pb; ++q) {
+            const std::complex<double> v = t.beams[(size_t)bm * t.Pb + q];
+            beams[(size_t)store_idx(bm) * t.Pb + q] = make_double2(v.real(), v.imag());
+        }
     std::vector<int> lb((size_t)nCand * nu);
     for (int c = 0; c < nCand; ++c)
         for (int j = 0; j < nu; ++j) {
             const LayerDesc& d = t.layers[(size_t)c * nu + j];
-            lb[(size_t)c * nu + j] = d.beam;
+            lb[(size_t)c * nu + j] = store_idx(d.beam);
             for (int b = 0; b < t.NB; ++b) coef[((size_t)c * nu + j) * t.NB + b] = make_double2(d.coef[b].real(), d.coef[b].imag());
         }
     PmiPlan* ex = p;
