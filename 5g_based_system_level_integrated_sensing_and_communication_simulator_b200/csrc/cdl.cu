@@ -168,30 +168,34 @@ int cdl_build_rays(Ctx* ctx, const CdlConfig& c, CdlRays& r) {
 constexpr int kCdlMaxSym = 16;
 struct CdlTimes { double t[kCdlMaxSym]; };
 
-// C_n[l,u,s] = sum_{m in n} g_m[u,s] exp(2 pi j nu_m t_l); rays of cluster n are [n*nRay, (n+1)*nRay) (+ the LOS ray)
-__global__ void cdl_cluster_kernel(const double2* __restrict__ g, const double* __restrict__ nu, int nRay, int losRay,
-                                   int nCl, int nRx, int nTx, int L, const CdlTimes tl, float2* __restrict__ C /*[nCl][J]*/) {
-    const int RT = nRx * nTx;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nCl * L * RT) return;
-    const int us = idx % RT, l = (idx / RT) % L, n = idx / (RT * L);
-    const int u = us / nTx, sx = us % nTx;
-    double re = 0.0, im = 0.0;
-    const double t = tl.t[l];
-    for (int q = 0; q <= nRay; ++q) {
-        int m = n * nRay + q;
-        if (q == nRay) {
-            if (n != 0 || losRay < 0) break;
-            m = losRay;  // specular ray belongs to cluster 1
-        }
+// C_n[l,u,s] = sum_{m in n} g_m[u,s] exp(2 pi j nu_m t_l); rays of cluster n are [n*nRay, (n+1)*nRay) (+ the LOS ray).
+// One CTA per (cluster, symbol): the <= 21 ray phasors are computed once, then threads sweep the antenna pairs.
+__global__ void __launch_bounds__(128)
+cdl_cluster_kernel(const double2* __restrict__ g, const double* __restrict__ nu, int nRay, int losRay, int nCl, int nRx,
+                   int nTx, int L, const CdlTimes tl, float2* __restrict__ C /*[nCl][J]*/) {
+    __shared__ double2 ph[32];
+    __shared__ int rayIdx[32];
+    const int n = blockIdx.x, l = blockIdx.y, RT = nRx * nTx;
+    const int cnt = nRay + ((n == 0 && losRay >= 0) ? 1 : 0);
+    if ((int)threadIdx.x < cnt) {
+        const int m = (int)threadIdx.x < nRay ? n * nRay + threadIdx.x : losRay;
         double s, c;
-        sincospi(2.0 * nu[m] * t, &s, &c);
-        const double2 gv = g[(size_t)m * RT + us];
-        re += gv.x * c - gv.y * s;
-        im += gv.x * s + gv.y * c;
+        sincospi(2.0 * nu[m] * tl.t[l], &s, &c);
+        ph[threadIdx.x] = make_double2(c, s);
+        rayIdx[threadIdx.x] = m;
     }
-    // MATLAB order of H(k,l,u,s): j = l + L*(u + nRx*s)
-    C[(size_t)n * L * RT + l + (size_t)L * (u + (size_t)nRx * sx)] = make_float2((float)re, (float)im);
+    __syncthreads();
+    for (int us = threadIdx.x; us < RT; us += blockDim.x) {
+        const int u = us / nTx, sx = us % nTx;
+        double re = 0.0, im = 0.0;
+        for (int q = 0; q < cnt; ++q) {
+            const double2 gv = g[(size_t)rayIdx[q] * RT + us], p = ph[q];
+            re += gv.x * p.x - gv.y * p.y;
+            im += gv.x * p.y + gv.y * p.x;
+        }
+        // MATLAB order of H(k,l,u,s): j = l + L*(u + nRx*s)
+        C[(size_t)n * L * RT + l + (size_t)L * (u + (size_t)nRx * sx)] = make_float2((float)re, (float)im);
+    }
 }
 
 // H[k, j] = sum_n E[k,n] C[n, j],  E[k,n] = exp(-2 pi j f_k tau_n);  j = (l,u,s) flattened, output [K x J].
@@ -283,10 +287,9 @@ int cdl_generate(Ctx* ctx, CdlRays& rays, int K, double scsHz, int L, const doub
     CdlTimes tl{};
     for (int l = 0; l < L; ++l) tl.t[l] = t0 + symTime[l];
     const int pr = prof_begin(ctx, kProfCdl, st);
-    const int tot1 = rays.nCl * L * RT;
     const int losRay = rays.los ? rays.nCl * rays.nRay : -1;
-    cdl_cluster_kernel<<<(tot1 + 255) / 256, 256, 0, st>>>(rays.d_g, rays.d_nu, rays.nRay, losRay, rays.nCl, rays.nRx, rays.nTx, L, tl,
-                                                          (float2*)dC);
+    dim3 g1(rays.nCl, L);
+    cdl_cluster_kernel<<<g1, 128, 0, st>>>(rays.d_g, rays.d_nu, rays.nRay, losRay, rays.nCl, rays.nRx, rays.nTx, L, tl, (float2*)dC);
     const long long J = (long long)L * RT;
     dim3 grid((K + kCdlTK - 1) / kCdlTK, (unsigned)((J + kCdlTJ - 1) / kCdlTJ));
     cdl_response_kernel<<<grid, 256, 0, st>>>((const float2*)dC, rays.d_tau, rays.nCl, K, J, scsHz, H);

@@ -141,41 +141,32 @@ pmi_sinr_kernel(const PmiDev p) {
     }
 }
 
-// totals over REs and layers per candidate (dlPMISelect.m:444)
-__global__ void pmi_total_kernel(const double* __restrict__ S, int nCand, int nu, int nRE, double* __restrict__ total) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (c >= nCand) return;
-    const double* __restrict__ s = S + (long long)b * nRE * nu * nCand + c;
-    double acc = 0.0;
-    for (int i = 0; i < nRE * nu; ++i) {
-        const double v = s[(long long)i * nCand];
-        if (!isnan(v)) acc += v;  // 'omitnan'
-    }
-    total[(long long)b * nCand + c] = acc;
-}
-
 // subband means (dlPMISelect.m:481): REs are sorted by subband; weight = mean-of-means weight
 __global__ void pmi_subband_kernel(const double* __restrict__ S, int nCand, int nu, int nRE, int nSB,
                                    const int* __restrict__ sbStart, const double* __restrict__ reW,
-                                   double* __restrict__ sub) {
+                                   double* __restrict__ sub, double* __restrict__ psum) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nCand) return;
     const int l = blockIdx.y % nu, sb = blockIdx.y / nu, b = blockIdx.z;
     const double* __restrict__ s = S + (long long)b * nRE * nu * nCand + c;
-    double acc = 0.0;
+    double acc = 0.0, plain = 0.0;
     bool any = false;
+#pragma unroll 4
     for (int e = sbStart[sb]; e < sbStart[sb + 1]; ++e) {
         const double v = s[((long long)e * nu + l) * nCand];
         if (!isnan(v)) {
             acc += reW[e] * v;
+            plain += v;   // un-weighted partial of sum(SINRPerRE,[1 2 3],'omitnan') (dlPMISelect.m:444)
             any = true;
         }
     }
-    sub[(((long long)b * nSB + sb) * nu + l) * nCand + c] = any ? acc : NAN;
+    const long long o = (((long long)b * nSB + sb) * nu + l) * nCand + c;
+    sub[o] = any ? acc : NAN;
+    psum[o] = plain;
 }
 
 struct SelDev {
-    const double* total;
+    const double* psum;
     const double* sub;
     const double* S;
     const int* sbStart;
@@ -192,11 +183,13 @@ __global__ void __launch_bounds__(256) pmi_select_kernel(const SelDev p) {
     __shared__ int bi[8];
     __shared__ int best;
     const int b = blockIdx.x;
-    const double* __restrict__ tot = p.total + (long long)b * p.nCand;
+    const double* __restrict__ ps = p.psum + (long long)b * p.nSB * p.nu * p.nCand;
     double v = -INFINITY;
     int ix = -1;
     for (int c = threadIdx.x; c < p.nCand; c += blockDim.x) {
-        const double t = round4(tot[c]);  // dlPMISelect.m:449
+        double tot = 0.0;  // totalSINR: fixed summation order (subband-major, then layer)
+        for (int q = 0; q < p.nSB * p.nu; ++q) tot += ps[(long long)q * p.nCand + c];
+        const double t = round4(tot);  // dlPMISelect.m:449
         if (ix < 0 || t > v) {
             v = t;
             ix = c;
@@ -402,7 +395,7 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
     cudaError_t e = cudaSuccess;
     auto A = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 8); };
     A((void**)&p->d_S, sizeof(double) * nCand * nu * nRE * B);
-    A((void**)&p->d_total, sizeof(double) * nCand * B);
+    A((void**)&p->d_total, sizeof(double) * nCand * nu * p->nSB * B);  // plain per-subband sums
     A((void**)&p->d_sub, sizeof(double) * nCand * nu * p->nSB * B);
     A((void**)&p->d_sel, sizeof(int) * (4 + p->nSB) * B);
     A((void**)&p->d_sinrSel, sizeof(double) * nu * p->nSB * B);
@@ -476,18 +469,16 @@ int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, c
     }
     ISAC_CUDA_CHECK(ctx, e);
     const int nCand = d.nCand, nu = p->nLayers;
-    dim3 g1((nCand + 127) / 128, batch);
-    pmi_total_kernel<<<g1, 128, 0, st>>>(p->d_S, nCand, nu, nRE, p->d_total);
     dim3 g2((nCand + 127) / 128, nu * p->nSB, batch);
-    pmi_subband_kernel<<<g2, 128, 0, st>>>(p->d_S, nCand, nu, nRE, p->nSB, p->d_sbStart, p->d_reW, p->d_sub);
+    pmi_subband_kernel<<<g2, 128, 0, st>>>(p->d_S, nCand, nu, nRE, p->nSB, p->d_sbStart, p->d_reW, p->d_sub, p->d_total);
     SelDev sd{};
-    sd.total = p->d_total; sd.sub = p->d_sub; sd.S = p->d_S; sd.sbStart = p->d_sbStart; sd.cqiStart = p->d_cqiStart;
+    sd.psum = p->d_total; sd.sub = p->d_sub; sd.S = p->d_S; sd.sbStart = p->d_sbStart; sd.cqiStart = p->d_cqiStart;
     sd.cqiW = p->d_reCqiW; sd.sel = p->d_sel; sd.sinrSel = p->d_sinrSel; sd.sinrWb = p->d_sinrWb;
     sd.nCand = nCand; sd.nu = nu; sd.nRE = nRE; sd.nSB = p->nSB; sd.nCqiSB = p->nCqiSB;
     sd.n2 = t.n2; sd.n11 = t.n11; sd.n12 = t.n12; sd.n13 = t.n13;
     pmi_select_kernel<<<batch, 256, 0, st>>>(sd);
     prof_end(ctx, pr, st);
-    count_launches(ctx, 4);
+    count_launches(ctx, 3);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     return kOk;
 }

@@ -36,7 +36,7 @@ struct PmiPlan {
     int* d_reCqiSb = nullptr;       // CQI subband of each RE
     double* d_reCqiW = nullptr;
     double* d_S = nullptr;          // SINRPerRE compact [nCand][nLayers][nRE][batch]
-    double* d_total = nullptr;      // [nCand][batch]
+    double* d_total = nullptr;      // plain per-subband sums [nCand][nLayers][nSB][batch] (wideband totals derive from them)
     double* d_sub = nullptr;        // SINRPerSubband [nCand][nLayers][nSB][batch]
     int* d_sel = nullptr;           // [4 + nSB][batch]: allNaN flag, i11, i12, i13 (0-based), i2 per subband (0-based, -1 = NaN)
     double* d_sinrSel = nullptr;    // [nLayers][nSB][batch]
