@@ -199,57 +199,106 @@ cdl_cluster_kernel(const double2* __restrict__ g, const double* __restrict__ nu,
 }
 
 // H[k, j] = sum_n E[k,n] C[n, j],  E[k,n] = exp(-2 pi j f_k tau_n);  j = (l,u,s) flattened, output [K x J].
-// 64(k) x 128(j) tile per CTA, 4 x 8 register tile per thread, contraction over <= 24 clusters from shared memory.
+// The complex contraction is run as two real GEMMs that share B on the tensor pipe:
+//   Re H = [Er, -Ei] * [Cr ; Ci],   Im H = [Ei, Er] * [Cr ; Ci]        (M = K rows, N = J cols, inner = 2*nClusters <= 48)
+// with mma.sync.m16n8k8 TF32 in the error-compensated 3xTF32 form (a = a_hi + a_lo, b = b_hi + b_lo;
+// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, ~2^-21 relative) so the result keeps float32-level accuracy.  The kernel is
+// write-bound (8*K*J bytes); the inner dimension is far too short for a tcgen05/TMEM pipeline to pay off.
 constexpr int kCdlTK = 64, kCdlTJ = 128, kCdlMaxCl = 24;
+
+__device__ __forceinline__ unsigned to_tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 __global__ void __launch_bounds__(256)
 cdl_response_kernel(const float2* __restrict__ C, const double* __restrict__ tau, int nCl, int K, long long J, double scs,
                     float2* __restrict__ H) {
-    __shared__ float2 Es[kCdlMaxCl][kCdlTK];
-    __shared__ float2 Cs[kCdlMaxCl][kCdlTJ];
+    __shared__ float2 Es[kCdlMaxCl][kCdlTK + 4];   // +4: fragment loads of 8 consecutive rows hit distinct banks
+    __shared__ float2 Cs[kCdlMaxCl][kCdlTJ + 4];
     const int k0 = blockIdx.x * kCdlTK;
     const long long j0 = (long long)blockIdx.y * kCdlTJ;
-    for (int i = threadIdx.x; i < nCl * kCdlTK; i += blockDim.x) {
+    for (int i = threadIdx.x; i < kCdlMaxCl * kCdlTK; i += blockDim.x) {
         const int n = i / kCdlTK, kk = i % kCdlTK;
-        const double f = ((double)(k0 + kk) - (double)(K / 2)) * scs;
-        double s, c;
-        sincospi(-2.0 * f * tau[n], &s, &c);
-        Es[n][kk] = make_float2((float)c, (float)s);
+        float2 e = make_float2(0.f, 0.f);
+        if (n < nCl) {
+            const double f = ((double)(k0 + kk) - (double)(K / 2)) * scs;
+            double s, c;
+            sincospi(-2.0 * f * tau[n], &s, &c);
+            e = make_float2((float)c, (float)s);
+        }
+        Es[n][kk] = e;
     }
-    for (int i = threadIdx.x; i < nCl * kCdlTJ; i += blockDim.x) {
+    for (int i = threadIdx.x; i < kCdlMaxCl * kCdlTJ; i += blockDim.x) {
         const int n = i / kCdlTJ, jj = i % kCdlTJ;
-        Cs[n][jj] = (j0 + jj < J) ? C[(size_t)n * J + j0 + jj] : make_float2(0.f, 0.f);
+        Cs[n][jj] = (n < nCl && j0 + jj < J) ? C[(size_t)n * J + j0 + jj] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    const int tk = threadIdx.x % 16, tj = threadIdx.x / 16;  // k = tk + 16*a (a<4), j = tj + 16*b (b<8)
-    float2 acc[4][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int wk = (warp & 1) * 32, wj = (warp >> 1) * 32;   // warp tile: 32 (k) x 32 (j)
+    float dre[2][4][4], dim[2][4][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = make_float2(0.f, 0.f);
-    for (int n = 0; n < nCl; ++n) {
-        float2 e[4], c[8];
+        for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-        for (int a = 0; a < 4; ++a) e[a] = Es[n][tk + 16 * a];
+            for (int q = 0; q < 4; ++q) dre[mi][ni][q] = dim[mi][ni][q] = 0.f;
+    const int ksteps = (2 * nCl + 7) / 8;
+    const int part = t & 1;  // inner index q = 8s + t (+4): cluster n = 4s + t/2 (+2), part 0 -> (Er | Cr), 1 -> (-Ei | Ci)
+    for (int s = 0; s < ksteps; ++s) {
+        const int nA = 4 * s + (t >> 1), nB = nA + 2;
+        unsigned bh[4][2], bl[4][2];
 #pragma unroll
-        for (int b = 0; b < 8; ++b) c[b] = Cs[n][tj + 16 * b];
+        for (int ni = 0; ni < 4; ++ni) {
+            const float2 c0 = Cs[nA][wj + ni * 8 + g], c1 = Cs[nB][wj + ni * 8 + g];
+            split_tf32(part ? c0.y : c0.x, bh[ni][0], bl[ni][0]);
+            split_tf32(part ? c1.y : c1.x, bh[ni][1], bl[ni][1]);
+        }
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int mi = 0; mi < 2; ++mi) {
+            const int r0 = wk + mi * 16 + g;
+            const float2 e00 = Es[nA][r0], e10 = Es[nA][r0 + 8], e01 = Es[nB][r0], e11 = Es[nB][r0 + 8];
+            unsigned ah[4], al[4], ch[4], cl[4];   // a*: [Er, -Ei] (real part), c*: [Ei, Er] (imaginary part)
+            split_tf32(part ? -e00.y : e00.x, ah[0], al[0]);
+            split_tf32(part ? -e10.y : e10.x, ah[1], al[1]);
+            split_tf32(part ? -e01.y : e01.x, ah[2], al[2]);
+            split_tf32(part ? -e11.y : e11.x, ah[3], al[3]);
+            split_tf32(part ? e00.x : e00.y, ch[0], cl[0]);
+            split_tf32(part ? e10.x : e10.y, ch[1], cl[1]);
+            split_tf32(part ? e01.x : e01.y, ch[2], cl[2]);
+            split_tf32(part ? e11.x : e11.y, ch[3], cl[3]);
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                acc[a][b].x += e[a].x * c[b].x - e[a].y * c[b].y;
-                acc[a][b].y += e[a].x * c[b].y + e[a].y * c[b].x;
+            for (int ni = 0; ni < 4; ++ni) {
+                mma_tf32(dre[mi][ni], al, bh[ni]);
+                mma_tf32(dre[mi][ni], ah, bl[ni]);
+                mma_tf32(dre[mi][ni], ah, bh[ni]);
+                mma_tf32(dim[mi][ni], cl, bh[ni]);
+                mma_tf32(dim[mi][ni], ch, bl[ni]);
+                mma_tf32(dim[mi][ni], ch, bh[ni]);
             }
-    }
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        const long long j = j0 + tj + 16 * b;
-        if (j >= J) continue;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int k = k0 + tk + 16 * a;
-            if (k < K) H[j * K + k] = acc[a][b];
         }
     }
+    // accumulator (row g / g+8, col 2t / 2t+1) -> H[j*K + k]
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k0 + wk + mi * 16 + g + ((q >> 1) ? 8 : 0);
+                const long long j = j0 + wj + ni * 8 + 2 * t + (q & 1);
+                if (k < K && j < J) H[j * K + k] = make_float2(dre[mi][ni][q], dim[mi][ni][q]);
+            }
 }
 
 // upload the ray tables once (they do not change between calls)
