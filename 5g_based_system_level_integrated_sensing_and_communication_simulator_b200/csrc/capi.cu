@@ -45,6 +45,7 @@ void prof_end(Ctx* ctx, int rec, cudaStream_t st) {
     if (rec >= 0 && rec < (int)ctx->prof.size()) cudaEventRecord(ctx->prof[rec].b, st);
 }
 void count_launches(Ctx* ctx, int n) { ctx->launches += n; }
+int ctx_num_sms(Ctx* ctx) { return ctx->numSMs; }
 
 int ctx_pinned(Ctx* ctx, int slot, size_t bytes, void** out) {
     if (slot < 0 || slot >= Ctx::kPinnedSlots) return kErrInvalidArg;

@@ -133,7 +133,7 @@ struct FftGeom {
 
 // Block FFT.  `v` receives X[tf + NT*d] in v[d].  `load(n)` returns input element n.
 // smem points at this instance's slot 0 (already offset by nl); RT = interleave stride.
-template <int R1, int R2, int SIGN, bool PAD, class Load>
+template <int R1, int R2, int SIGN, bool PAD, class Load, bool PRELOADED = false>
 __device__ __forceinline__ void block_fft(float2 (&v)[16], float2* smem, const int RT, const int tf,
                                           const FftTw tw, Load load) {
     using G = FftGeom<R1, R2, PAD>;
@@ -143,7 +143,10 @@ __device__ __forceinline__ void block_fft(float2 (&v)[16], float2* smem, const i
         for (int i = 0; i < 16 / R1; ++i) {
             const int m = tf + NT * i;  // 0..N2-1
 #pragma unroll
-            for (int j = 0; j < R1; ++j) v[i * R1 + j] = load(N2 * j + m);
+            if constexpr (!PRELOADED) {
+#pragma unroll
+                for (int j = 0; j < R1; ++j) v[i * R1 + j] = load(N2 * j + m);
+            }
             dftR<R1, SIGN>(&v[i * R1]);
 #pragma unroll
             for (int k1 = 1; k1 < R1; ++k1)

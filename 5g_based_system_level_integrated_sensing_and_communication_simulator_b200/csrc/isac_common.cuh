@@ -65,6 +65,7 @@ enum ProfSlot : int {
 int prof_begin(Ctx* ctx, int slot, cudaStream_t st);  // returns a record index (or -1 when disabled)
 void prof_end(Ctx* ctx, int rec, cudaStream_t st);
 void count_launches(Ctx* ctx, int n);
+int ctx_num_sms(Ctx* ctx);
 
 #define ISAC_CUDA_CHECK(ctx, expr)                                                          \
     do {                                                                                    \

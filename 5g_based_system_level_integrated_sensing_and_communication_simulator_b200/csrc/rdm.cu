@@ -83,6 +83,102 @@ rdm_range_ifft_kernel(const RdmDev p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Kernel A' (N = 4096): persistent range IFFT with TMA staging.  One CTA loops over columns; the rx and tx
+// columns of the NEXT column are fetched by two cp.async.bulk (TMA 1-D) copies into shared memory, completion
+// signalled on an mbarrier, while the current column's FFT runs from registers -> the long-scoreboard stalls of
+// kernel A disappear and 2 CTAs/SM keep the copy engine and the FMA pipe busy at the same time.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int R1, int R2>
+__global__ void __launch_bounds__(R1* R2, 2)
+rdm_range_ifft_tma_kernel(const RdmDev p) {
+    using G = FftGeom<R1, R2, true>;
+    static_assert(G::NT == R1 * R2 && R1 == 16, "one column per CTA pass, 16 values per thread");
+    extern __shared__ __align__(128) unsigned char smraw[];
+    float2* fftbuf = reinterpret_cast<float2*>(smraw);
+    float2* stageRx = fftbuf + G::kElems + 8;           // keep 16-byte alignment
+    float2* stageTx = stageRx + p.nSc;
+    __shared__ __align__(8) unsigned long long bar;
+    const int tf = threadIdx.x;
+    const unsigned colBytes = (unsigned)p.nSc * sizeof(float2);
+    auto col_ptrs = [&](long long col, const float2*& rx, const float2*& tx, int& sp, long long& page) {
+        sp = (int)(col % p.M);
+        page = col / p.M;
+        const int s = (sp + p.nSym / 2) % p.nSym;  // ifftshift on the symbol axis (fft2D.m:44)
+        rx = p.rx + (page * p.nSym + s) * (long long)p.nSc;
+        tx = p.tx + (page * p.nSym + s) * (long long)p.nSc;
+    };
+    if (tf == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    long long col = blockIdx.x;
+    if (tf == 0 && col < p.totalCols) {
+        const float2 *rx, *tx; int sp; long long page;
+        col_ptrs(col, rx, tx, sp, page);
+        mbar_expect_tx(&bar, 2 * colBytes);
+        tma_load_1d(stageRx, rx, colBytes, &bar);
+        tma_load_1d(stageTx, tx, colBytes, &bar);
+    }
+    unsigned parity = 0;
+    const float* __restrict__ w1 = p.win1;
+    for (; col < p.totalCols; col += gridDim.x) {
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        float2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = tf + G::NT * j;
+            v[j] = (n < p.nSc) ? cscale(cmulc(stageRx[n], stageTx[n]), __ldg(w1 + n)) : make_float2(0.f, 0.f);
+        }
+        __syncthreads();  // every thread has consumed the stage
+        const long long next = col + gridDim.x;
+        if (tf == 0 && next < p.totalCols) {
+            const float2 *rx, *tx; int sp; long long page;
+            col_ptrs(next, rx, tx, sp, page);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
+            mbar_expect_tx(&bar, 2 * colBytes);
+            tma_load_1d(stageRx, rx, colBytes, &bar);
+            tma_load_1d(stageTx, tx, colBytes, &bar);
+        }
+        auto noload = [](int) -> float2 { return make_float2(0.f, 0.f); };
+        block_fft<R1, R2, +1, true, decltype(noload), true>(v, fftbuf, 1, tf, p.twR, noload);
+        const int sp = (int)(col % p.M);
+        const long long page = col / p.M;
+        float2* __restrict__ out = p.inter + (page * p.M + sp) * (long long)p.nIFFT;
+        const float sgn = (sp & 1) ? -1.f : 1.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+            const int n = tf + G::NT * d;
+            out[n] = cscale(v[d], __ldg(p.win2 + n) * sgn);
+        }
+        __syncthreads();  // fftbuf is reused by the next column's first pass
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Kernel B: Doppler FFT + |.|^2
 // ------------------------------------------------------------------------------------------
 template <int R1, int R2>
@@ -154,43 +250,77 @@ __global__ void __launch_bounds__(256) cfar2d_flags_kernel(const CfarDev p) {
     }
 }
 
+// Reference configuration (cfar2D.m:32-33): guard [2 2], training [1 1] -> 7x7 window minus the 5x5 guard block.
+// Fully unrolled: the 24 training loads are independent and issue back to back (same summation order as above).
+__global__ void __launch_bounds__(256) cfar2d_flags_7x7_kernel(const CfarDev p) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= p.total) return;
+    const int i = (int)(gid % p.nCut);
+    const long long page = gid / p.nCut;
+    const int row = p.row0 + i % p.nCutRows;
+    const int col = p.col0 + i / p.nCutRows;
+    const float* __restrict__ P = p.pow + page * (long long)p.nFFT * p.nIFFT + (long long)col * p.nIFFT + row;
+    float t[24];
+    int q = 0;
+#pragma unroll
+    for (int dc = -3; dc <= 3; ++dc)
+#pragma unroll
+        for (int dr = -3; dr <= 3; ++dr) {
+            if (dc >= -2 && dc <= 2 && dr >= -2 && dr <= 2) continue;
+            t[q++] = __ldcg(P + (long long)dc * p.nIFFT + dr);
+        }
+    const float x = __ldcg(P);
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 24; ++k) acc = acc + (double)t[k];
+    const bool det = (double)x > p.alpha * (acc / p.nTrain);
+    p.flags[gid] = det ? 1 : 0;
+    if (det) atomicOr(p.rowmask + (page / p.nAnts) * p.rowWords + (row >> 5), 1u << (row & 31));
+}
+
 // ------------------------------------------------------------------------------------------
 // Kernel D: ordered compaction -> 'Detection index' [row; col] (1-based) in CUT order
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) cfar2d_compact_kernel(const CfarDev p, int2* det, float* peak, int32_t* detCount) {
-    __shared__ int warpSums[32];
-    __shared__ int base;
+    // each thread owns a contiguous run of CUTs (keeps CUT order), one block-wide exclusive scan of the run counts
+    __shared__ int warpTot[32];
     const long long page = blockIdx.x;
     const uint8_t* __restrict__ f = p.flags + page * (long long)p.nCut;
     const float* __restrict__ P = p.pow + page * (long long)p.nFFT * p.nIFFT;
     int2* __restrict__ o = det + page * (long long)p.nCut;
     float* __restrict__ pk = peak + page * (long long)p.nCut;
-    if (threadIdx.x == 0) base = 0;
-    __syncthreads();
+    const int per = (p.nCut + blockDim.x - 1) / blockDim.x;
+    const int lo = threadIdx.x * per, hi = min(lo + per, p.nCut);
+    int cnt = 0;
+    for (int i = lo; i < hi; ++i) cnt += f[i];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int start = 0; start < p.nCut; start += blockDim.x) {
-        const int i = start + threadIdx.x;
-        const bool d = (i < p.nCut) && f[i];
-        const unsigned m = __ballot_sync(0xffffffffu, d);
-        const int within = __popc(m & ((1u << lane) - 1));
-        if (lane == 0) warpSums[warp] = __popc(m);
-        __syncthreads();
-        int off = base;
-        for (int w = 0; w < warp; ++w) off += warpSums[w];
-        if (d) {
-            const int row = p.row0 + i % p.nCutRows, col = p.col0 + i / p.nCutRows;
-            o[off + within] = make_int2(row + 1, col + 1);
-            pk[off + within] = P[(long long)col * p.nIFFT + row];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warpSums[w];
-            base += t;
-        }
-        __syncthreads();
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
     }
-    if (threadIdx.x == 0) detCount[page] = base;
+    if (lane == 31) warpTot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warpTot[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += v;
+        }
+        warpTot[lane] = w;  // inclusive totals of the warps
+    }
+    __syncthreads();
+    int off = incl - cnt + (warp ? warpTot[warp - 1] : 0);
+    for (int i = lo; i < hi; ++i)
+        if (f[i]) {
+            const int row = p.row0 + i % p.nCutRows, col = p.col0 + i / p.nCutRows;
+            o[off] = make_int2(row + 1, col + 1);
+            pk[off] = P[(long long)col * p.nIFFT + row];
+            ++off;
+        }
+    if (threadIdx.x == blockDim.x - 1) detCount[page] = warpTot[31];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -328,6 +458,17 @@ static cudaError_t launch_range(const RdmDev& d, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static cudaError_t launch_range_tma(const RdmDev& d, int numSMs, cudaStream_t st) {
+    using G = FftGeom<16, 16, true>;
+    const size_t smem = sizeof(float2) * ((size_t)G::kElems + 8 + 2 * (size_t)d.nSc) + 128;
+    auto k = rdm_range_ifft_tma_kernel<16, 16>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long blocks = 2LL * numSMs;
+    if (blocks > d.totalCols) blocks = d.totalCols;
+    k<<<(unsigned)blocks, G::NT, smem, st>>>(d);
+    return cudaGetLastError();
+}
+
 template <int R1, int R2>
 static cudaError_t launch_doppler(const RdmDev& d, long long pages, cudaStream_t st) {
     using G = FftGeom<R1, R2, false>;
@@ -377,7 +518,8 @@ int rdm_cfar_only(RdmPlan* p, const float* pow, int batch, cudaStream_t st) {
     ISAC_CUDA_CHECK(ctx, cudaMemsetAsync(p->d_rowmask, 0, sizeof(uint32_t) * (size_t)p->rowWords * batch, st));
     const long long blocks = (d.total + 255) / 256;
     const int pr = prof_begin(ctx, kProfCfar, st);
-    cfar2d_flags_kernel<<<(unsigned)blocks, 256, 0, st>>>(d);
+    if (d.gr == 2 && d.gc == 2 && d.hr == 3 && d.hc == 3) cfar2d_flags_7x7_kernel<<<(unsigned)blocks, 256, 0, st>>>(d);
+    else cfar2d_flags_kernel<<<(unsigned)blocks, 256, 0, st>>>(d);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     cfar2d_compact_kernel<<<(unsigned)(p->cfg.nAnts * batch), 1024, 0, st>>>(d, p->d_det, p->d_peak, p->d_detCount);
     prof_end(ctx, pr, st);
@@ -429,7 +571,10 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
             case 512: e = launch_range<2, 16>(d, st); break;
             case 1024: e = launch_range<4, 16>(d, st); break;
             case 2048: e = launch_range<8, 16>(d, st); break;
-            case 4096: e = launch_range<16, 16>(d, st); break;
+            case 4096:
+                if ((((uintptr_t)d.rx | (uintptr_t)d.tx) & 15) == 0 && (c.nSc % 2) == 0 && !p->noTma) e = launch_range_tma(d, ctx_num_sms(ctx), st);
+                else e = launch_range<16, 16>(d, st);
+                break;
             default: set_error(ctx, "rdm: unsupported nIFFT"); return kErrUnsupported;
         }
         ISAC_CUDA_CHECK(ctx, e);

@@ -35,6 +35,7 @@ struct RdmPlan {
     float* d_peak = nullptr;        // [nCut x nAnts x maxBatch]
     const float* lastPow = nullptr; // power map used by the last run (plan-owned or caller's)
     int lastBatch = 0;
+    bool noTma = false;          // force the non-TMA range kernel (A/B comparisons)
 };
 
 int rdm_plan_create(Ctx* ctx, const RdmConfig& cfg, RdmPlan** out);
