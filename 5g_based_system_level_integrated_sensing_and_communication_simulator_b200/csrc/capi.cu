@@ -920,6 +920,26 @@ int isac_ul_pmi_select_dev(isac_ctx* h, int32_t nLayers, const void* hest, int32
     return ISAC_OK;
 }
 
+int isac_ul_pmi_select_batch_dev(isac_ctx* h, int32_t nLayers, const void* hest, int32_t K, int32_t nSym, int32_t nRx, int32_t nPorts,
+                                 double noiseEst, int32_t bandSize, int32_t batch, int32_t maxSB, double* pmi, double* sinr,
+                                 int32_t* nSB, int32_t* nTPMI, int32_t* none) {
+    if (!h || !hest || !nSB || !nTPMI || !none) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    std::vector<UlPmiResult> r;
+    int st = ul_pmi_select_batch(c, nLayers, (const float2*)hest, K, nSym, nRx, nPorts, noiseEst, bandSize, batch, r, c->stream);
+    if (st) return st;
+    *nSB = r[0].nSB; *nTPMI = r[0].nTPMI;
+    if (r[0].nSB > maxSB) { set_error(c, "pmiSelect: maxSB too small"); return ISAC_ERR_CAPACITY; }
+    for (int b = 0; b < batch; ++b) {
+        none[b] = r[b].none ? 1 : 0;
+        if (r[b].none) continue;
+        if (pmi) std::memcpy(pmi + (size_t)maxSB * b, r[b].pmi.data(), sizeof(double) * r[b].pmi.size());
+        if (sinr) std::memcpy(sinr + (size_t)maxSB * r[0].nTPMI * b, r[b].sinr.data(), sizeof(double) * r[b].sinr.size());
+    }
+    return ISAC_OK;
+}
+
 int isac_prg_precode_dev(isac_ctx* h, int32_t K, int32_t Lsym, int32_t nStartGrid, const void* portsym, const int32_t* portind,
                          int32_t NRE, int32_t nLayers, const void* F, int32_t P, int32_t NPRG, void* antsym, int32_t* antind) {
     if (!h) return ISAC_ERR_INVALID_ARG;
@@ -971,6 +991,20 @@ int isac_cdl_get_rays(const isac_cdl_channel* ch, int32_t* nCl, int32_t* nRays, 
     if (nu) std::memcpy(nu, r.nu.data(), sizeof(double) * r.nu.size());
     if (cluster) std::memcpy(cluster, r.cluster.data(), sizeof(int) * r.cluster.size());
     if (g) std::memcpy(g, r.g.data(), sizeof(std::complex<double>) * r.g.size());
+    return ISAC_OK;
+}
+
+int isac_cdl_generate_batch_dev(isac_cdl_channel* const* ch, int32_t n, int32_t K, double scsHz, int32_t L, const double* symTime,
+                                const double* t0, void* H) {
+    if (!ch || n < 1 || !H || !symTime || !t0) return ISAC_ERR_INVALID_ARG;
+    for (int i = 0; i < n; ++i) {
+        if (!ch[i]) return ISAC_ERR_INVALID_ARG;
+        Ctx* c = ch[i]->ctx;
+        cudaSetDevice(c->device);
+        const size_t stride = (size_t)K * L * ch[i]->rays.nRx * ch[i]->rays.nTx;
+        int st = cdl_generate(c, ch[i]->rays, K, scsHz, L, symTime, t0[i], (float2*)H + stride * i, c->stream);
+        if (st) return st;
+    }
     return ISAC_OK;
 }
 

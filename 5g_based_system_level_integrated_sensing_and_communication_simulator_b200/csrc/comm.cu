@@ -670,10 +670,12 @@ void cqi_from_pmi(const CsiConfig& cfg, int nu, const PmiResult& r, int nSB, int
 // ------------------------------------------------------------------------------------------
 template <int NU>
 __global__ void __launch_bounds__(128)
-ul_sinr_kernel(const float2* __restrict__ hest, int K, int nSym, int R, int P, const double2* __restrict__ W /*[P][NU][nT]*/,
-               int nT, double nVar, double* __restrict__ sinr /*[K*nSym][nT]*/) {
+ul_sinr_kernel(const float2* __restrict__ hestAll, int K, int nSym, int R, int P, const double2* __restrict__ W /*[P][NU][nT]*/,
+               int nT, double nVar, double* __restrict__ sinrAll /*[K*nSym][nT][batch]*/) {
     const long long re = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (re >= (long long)K * nSym) return;
+    const float2* __restrict__ hest = hestAll + (long long)blockIdx.y * K * nSym * R * P;
+    double* __restrict__ sinr = sinrAll + (long long)blockIdx.y * K * nSym * nT;
     double2 h[16 * 4];  // R <= 16, P <= 4
     double sr = 0.0, si = 0.0;
     for (int r = 0; r < R; ++r)
@@ -746,9 +748,11 @@ ul_sinr_kernel(const float2* __restrict__ hest, int K, int nSym, int R, int P, c
 
 // sinrPerSubband (sinrPerSubband.m:26-34): one CTA per (band, tpmi)
 __global__ void __launch_bounds__(256)
-ul_band_kernel(const double* __restrict__ sinr, int K, int nSym, int nT, const int* __restrict__ bandLo,
-               const int* __restrict__ bandHi, double* __restrict__ out /*[nSB][nT]*/) {
+ul_band_kernel(const double* __restrict__ sinrAll, int K, int nSym, int nT, const int* __restrict__ bandLo,
+               const int* __restrict__ bandHi, double* __restrict__ outAll /*[nSB][nT][batch]*/) {
     const int sb = blockIdx.x, t = blockIdx.y;
+    const double* __restrict__ sinr = sinrAll + (long long)blockIdx.z * K * nSym * nT;
+    double* __restrict__ out = outAll + (long long)blockIdx.z * gridDim.x * nT;
     double acc = 0.0;
     long long cnt = 0;
     const int lo = bandLo[sb] - 1, hi = bandHi[sb];  // 0-based [lo, hi)
@@ -778,6 +782,17 @@ ul_band_kernel(const double* __restrict__ sinr, int K, int nSym, int nT, const i
 
 int ul_pmi_select_run(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int R, int P, double noiseEst, int bandSize,
                       UlPmiResult& out, cudaStream_t st) {
+    std::vector<UlPmiResult> v;
+    int s = ul_pmi_select_batch(ctx, nu, hest, K, nSym, R, P, noiseEst, bandSize, 1, v, st);
+    if (!s) out = v[0];
+    return s;
+}
+
+int ul_pmi_select_batch(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int R, int P, double noiseEst, int bandSize,
+                        int batch, std::vector<UlPmiResult>& outs, cudaStream_t st) {
+    if (batch < 1) { set_error(ctx, "pmiSelect: batch < 1"); return kErrInvalidArg; }
+    outs.assign(batch, UlPmiResult());
+    UlPmiResult& out = outs[0];
     if (!hest || K < 12 || nSym < 1 || R < 1 || R > 16 || bandSize < 1) {
         set_error(ctx, "pmiSelect: invalid argument");
         return kErrInvalidArg;
@@ -798,7 +813,11 @@ int ul_pmi_select_run(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int
     }
     out.subbandIndices.resize((size_t)nSB * 2);
     for (int i = 0; i < nSB; ++i) { out.subbandIndices[i] = lo[i]; out.subbandIndices[nSB + i] = hi[i]; }
-    if (noiseEst == 0.0) { out.none = true; return kOk; }  // pmiSelect.m:39
+    if (noiseEst == 0.0) {  // pmiSelect.m:39
+        out.none = true;
+        for (int b = 1; b < batch; ++b) outs[b] = out;
+        return kOk;
+    }
     // the PUSCH codebook of (nu, P) and the band limits are uploaded once per context and cached
     struct UlCache { Ctx* ctx; int nu, P, K, band; double2* dW; int* dIdx; };
     static std::vector<UlCache> cache;
@@ -821,10 +840,10 @@ int ul_pmi_select_run(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int
         uc = &cache.back();
     }
     void *dW = uc->dW, *dIdx = uc->dIdx, *dS = nullptr, *dB = nullptr;
-    if ((s = ctx_scratch(ctx, 3, sizeof(double) * (size_t)K * nSym * nT, &dS))) return s;
-    if ((s = ctx_scratch(ctx, 4, sizeof(double) * (size_t)nSB * nT, &dB))) return s;
+    if ((s = ctx_scratch(ctx, 3, sizeof(double) * (size_t)K * nSym * nT * batch, &dS))) return s;
+    if ((s = ctx_scratch(ctx, 4, sizeof(double) * (size_t)nSB * nT * batch, &dB))) return s;
     const long long nre = (long long)K * nSym;
-    const unsigned blocks = (unsigned)((nre + 127) / 128);
+    const dim3 blocks((unsigned)((nre + 127) / 128), batch);
     const int pr = prof_begin(ctx, kProfUlPmi, st);
     switch (nu) {
         case 1: ul_sinr_kernel<1><<<blocks, 128, 0, st>>>(hest, K, nSym, R, P, (const double2*)dW, nT, noiseEst, (double*)dS); break;
@@ -833,27 +852,33 @@ int ul_pmi_select_run(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int
         default: ul_sinr_kernel<4><<<blocks, 128, 0, st>>>(hest, K, nSym, R, P, (const double2*)dW, nT, noiseEst, (double*)dS); break;
     }
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
-    dim3 g(nSB, nT);
+    dim3 g(nSB, nT, batch);
     ul_band_kernel<<<g, 256, 0, st>>>((const double*)dS, K, nSym, nT, (const int*)dIdx, (const int*)dIdx + nSB, (double*)dB);
     prof_end(ctx, pr, st);
     count_launches(ctx, 2);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
-    std::vector<double> bands((size_t)nSB * nT);
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(bands.data(), dB, sizeof(double) * bands.size(), cudaMemcpyDeviceToHost, st));
+    std::vector<double> all((size_t)nSB * nT * batch);
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(all.data(), dB, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, st));
     ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    // "no channel estimates" <=> every band is 0/0 (pmiSelect.m:39,60-64)
-    bool any = false;
-    for (double v : bands) any |= !std::isnan(v);
-    if (!any) { out.none = true; return kOk; }
-    out.pmi.resize(nSB);
-    out.sinr.resize((size_t)nSB * nT);
-    for (int sb = 0; sb < nSB; ++sb) {
-        int best = 0;
-        for (int tt = 0; tt < nT; ++tt) {
-            out.sinr[(size_t)tt * nSB + sb] = bands[(size_t)sb * nT + tt];
-            if (bands[(size_t)sb * nT + tt] > bands[(size_t)sb * nT + best]) best = tt;  // first max (pmiSelect.m:56)
+    const UlPmiResult proto = out;
+    for (int b = 0; b < batch; ++b) {
+        UlPmiResult& o = outs[b];
+        o = proto;
+        const double* bands = all.data() + (size_t)b * nSB * nT;
+        // "no channel estimates" <=> every band is 0/0 (pmiSelect.m:39,60-64)
+        bool any = false;
+        for (size_t i = 0; i < (size_t)nSB * nT; ++i) any |= !std::isnan(bands[i]);
+        if (!any) { o.none = true; continue; }
+        o.pmi.resize(nSB);
+        o.sinr.resize((size_t)nSB * nT);
+        for (int sb = 0; sb < nSB; ++sb) {
+            int best = 0;
+            for (int tt = 0; tt < nT; ++tt) {
+                o.sinr[(size_t)tt * nSB + sb] = bands[(size_t)sb * nT + tt];
+                if (bands[(size_t)sb * nT + tt] > bands[(size_t)sb * nT + best]) best = tt;  // first max (pmiSelect.m:56)
+            }
+            o.pmi[sb] = std::isnan(bands[(size_t)sb * nT]) ? NAN : (double)best;           // :57-58 (0-based)
         }
-        out.pmi[sb] = std::isnan(bands[(size_t)sb * nT]) ? NAN : (double)best;           // :57-58 (0-based)
     }
     return kOk;
 }

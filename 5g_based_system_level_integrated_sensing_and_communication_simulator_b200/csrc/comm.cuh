@@ -83,6 +83,10 @@ struct UlPmiResult {
 int ul_pmi_select_run(Ctx* ctx, int nLayers, const float2* hest, int K, int nSym, int nRx, int P, double noiseEst,
                       int bandSize, UlPmiResult& out, cudaStream_t st);
 
+// `batch` independent estimates stacked along a 5th dimension (one synchronisation for all of them)
+int ul_pmi_select_batch(Ctx* ctx, int nLayers, const float2* hest, int K, int nSym, int nRx, int P, double noiseEst,
+                        int bandSize, int batch, std::vector<UlPmiResult>& out, cudaStream_t st);
+
 // prgPrecode (prgPrecode.m:53-144): portsym/portind [NRE x nLayers], F [nLayers x P x NPRG] (device);
 // antsym [NRE x P] complex64, antind [NRE x P] int32 (1-based).  scratch grid owned by ctx.
 int prg_precode_run(Ctx* ctx, int K, int Lsym, int nStartGrid, const float2* portsym, const int* portind, int NRE,

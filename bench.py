@@ -128,7 +128,6 @@ class CommWorkload:
         self.rc = {"NSizeBWP": self.NRB, "NStartBWP": 0, "PanelDimensions": (2, 2), "CodebookMode": 1, "PMIMode": "Subband",
                    "CQIMode": "Subband", "SubbandSize": 16}
         self.cs = ph._csi_struct(self.carrier, self.csirs, self.rc, 8)
-        _, self.csi_plan = ph._csi_plan(self.cs, self.N_UE)
         self.table = np.ascontiguousarray(P.communication.setupSINRtoCQIMappingTable()["downlinkSINR90pc"], dtype=np.float64)
         num = P.workloads.ofdm_numerology(self.NRB, 30)
         starts = P.workloads.symbol_starts(num, 14) / num["SampleRate"]
@@ -139,22 +138,31 @@ class CommWorkload:
         self.ul = [[cm.CDLChannel("CDL-C", TransmitAntennaArraySize=(1, 1, 2), ReceiveAntennaArraySize=(1, 4, 2),
                                   Seed=5000 + 1000 * c + u, device=device) for u in range(self.N_UE)] for c in range(cells)]
         dev = f"cuda:{device}"
-        self.H = torch.empty((self.N_UE, 8, 8, 14, K), dtype=torch.complex64, device=dev)       # [ue][P][R][L][K]
-        self.hest = torch.empty((2, 8, 1, K), dtype=torch.complex64, device=dev)                # [P][R][1][K]
+        self.nb = cells * self.N_UE                                        # UEs of all cells report together (same slot)
+        assert self.nb <= 32, "cells_per_gpu <= 4 (PMI batch limit 32)"
+        _, self.csi_plan = ph._csi_plan(self.cs, self.nb)
+        self.H = torch.empty((self.nb, 8, 8, 14, K), dtype=torch.complex64, device=dev)       # [cell*ue][P][R][L][K]
+        self.nul = cells * 4                                                # 4 UEs share an SRS slot (setupSRS.m:13)
+        self.hest = torch.empty((self.nul, 2, 8, 1, K), dtype=torch.complex64, device=dev)    # [cell*ue][P][R][1][K]
         comb = torch.zeros(K, dtype=torch.complex64, device=dev)
         comb[1::4] = 1.0
         self.comb = comb
-        self.nvar = np.full(self.N_UE, 10 ** (-15 / 10))
+        self.nvar = np.full(self.nb, 10 ** (-15 / 10))
         nSB = (self.NRB + 15) // 16
-        self.RI = np.zeros(self.N_UE)
-        self.i1 = np.zeros((3, self.N_UE), order="F")
-        self.i2 = np.zeros((nSB, self.N_UE), order="F")
-        self.cqi = np.zeros((nSB + 1) * 2 * self.N_UE)
+        self.RI = np.zeros(self.nb)
+        self.i1 = np.zeros((3, self.nb), order="F")
+        self.i2 = np.zeros((nSB, self.nb), order="F")
+        self.cqi = np.zeros((nSB + 1) * 2 * self.nb)
         self.rows = C.c_int32()
-        self.ul_pmi = np.zeros(nSB + 1)
-        self.ul_sinr = np.zeros((nSB + 1) * 3)
-        self.ul_idx = np.zeros((nSB + 1) * 2, dtype=np.int32)
-        self.ul_n = (C.c_int32(), C.c_int32(), C.c_int32())
+        self.ul_pmi = np.zeros((nSB + 1) * self.nul)
+        self.ul_sinr = np.zeros((nSB + 1) * 3 * self.nul)
+        self.ul_none = np.zeros(self.nul, dtype=np.int32)
+        self.ul_n = (C.c_int32(), C.c_int32())
+        self.dl_handles = (C.c_void_p * self.nb)(*[self.dl[c][u].handle for c in range(cells) for u in range(self.N_UE)])
+        self.ul_handles = [(C.c_void_p * self.nul)(*[self.ul[c][4 * grp + q].handle for c in range(cells) for q in range(4)])
+                           for grp in range(2)]
+        self.t0_dl = np.zeros(self.nb)
+        self.t0_ul = np.zeros(self.nul)
         # PDSCH: full band, symbols 2..13 (12 symbols), 2 layers, PRG size 2 -> 137 PRGs; DM-RS: symbol 2, 6 REs/PRB
         L, nu, Pp = 14, 2, 8
         self.nprg = (self.NRB + 1) // 2
@@ -177,29 +185,30 @@ class CommWorkload:
         ptr, check = self._lib.ptr, self._lib.check
         ctx.use_torch_stream()
         frame_t0 = 0.010 * step
+        for occ in range(4):                                                # CSI-RS occasions of the frame, all cells together
+            self.t0_dl[:] = frame_t0 + (5 * occ + 2) * self.slot_t
+            check(lib.isac_cdl_generate_batch_dev(self.dl_handles, self.nb, self.K, self.SCS, 14, ptr(self.sym_t), ptr(self.t0_dl),
+                                                  ptr(self.H)), ctx.handle)
+            check(lib.isac_csi_report_dev(self.csi_plan, ptr(self.H), ptr(self.nvar), self.nb, ptr(self.table),
+                                          self.table.size, 4, ptr(self.RI), ptr(self.i1), ptr(self.i2), ptr(self.cqi),
+                                          C.byref(self.rows)), ctx.handle)
+        # SRS: UEs 0-3 at slots 3, 11, 19 and UEs 4-7 at slots 4, 12 of the frame (period 8, offset 3 + floor(ue/4))
+        for slot, grp in ((3, 0), (4, 1), (11, 0), (12, 1), (19, 0)):
+            self.t0_ul[:] = frame_t0 + slot * self.slot_t
+            check(lib.isac_cdl_generate_batch_dev(self.ul_handles[grp], self.nul, self.K, self.SCS, 1, ptr(self.sym13), ptr(self.t0_ul),
+                                                  ptr(self.hest)), ctx.handle)
+            self.hest.mul_(self.comb)                                       # comb-4 SRS REs only (setupSRS.m:11-18)
+            check(lib.isac_ul_pmi_select_batch_dev(ctx.handle, 2, ptr(self.hest), self.K, 1, 8, 2, 0.05, 16, self.nul,
+                                                   self.ul_pmi.size // self.nul, ptr(self.ul_pmi), ptr(self.ul_sinr),
+                                                   C.byref(self.ul_n[0]), C.byref(self.ul_n[1]), ptr(self.ul_none)), ctx.handle)
         for c in range(self.cells):
-            for occ in range(4):                                            # CSI-RS occasions of the frame
-                t0 = frame_t0 + (5 * occ + 2) * self.slot_t
-                for u in range(self.N_UE):
-                    self.dl[c][u].generate(self.K, self.SCS, self.sym_t, t0, out=self.H[u])
-                check(lib.isac_csi_report_dev(self.csi_plan, ptr(self.H), ptr(self.nvar), self.N_UE, ptr(self.table),
-                                              self.table.size, 4, ptr(self.RI), ptr(self.i1), ptr(self.i2), ptr(self.cqi),
-                                              C.byref(self.rows)), ctx.handle)
-            for i in range(20):                                             # SRS occasions (2.5 per UE per frame)
-                u = i % self.N_UE
-                t0 = frame_t0 + (8 * (i // self.N_UE) + 3 + u // 4) * self.slot_t
-                self.ul[c][u].generate(self.K, self.SCS, self.sym13, t0, out=self.hest)
-                self.hest.mul_(self.comb)                                   # comb-4 SRS REs only (setupSRS.m:11-18)
-                check(lib.isac_ul_pmi_select_dev(ctx.handle, 2, ptr(self.hest), self.K, 1, 8, 2, 0.05, 16, self.ul_pmi.size,
-                                                 ptr(self.ul_pmi), ptr(self.ul_sinr), ptr(self.ul_idx), C.byref(self.ul_n[0]),
-                                                 C.byref(self.ul_n[1]), C.byref(self.ul_n[2])), ctx.handle)
             for slot in range(12):                                          # DL slots: PDSCH + DM-RS precoding (gNBPhy.m:822,826)
                 for sym, ind, nre in (self.pdsch, self.dmrs):
                     check(lib.isac_prg_precode_dev(ctx.handle, self.K, 14, 0, ptr(sym), ptr(ind), nre, 2, ptr(self.F), 8, self.nprg,
                                                    ptr(self.out_sym), ptr(self.out_ind)), ctx.handle)
 
     def d2h_bytes_per_step(self):
-        return self.cells * (4 * (self.RI.nbytes + self.i1.nbytes + self.i2.nbytes + self.cqi.nbytes) + 20 * (self.ul_pmi.nbytes + self.ul_sinr.nbytes))
+        return 4 * (self.RI.nbytes + self.i1.nbytes + self.i2.nbytes + self.cqi.nbytes) + 5 * (self.ul_pmi.nbytes + self.ul_sinr.nbytes)
 
     def algorithmic_bytes(self):
         K = self.K

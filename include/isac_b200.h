@@ -265,6 +265,11 @@ int isac_csi_report_dev(isac_csi_plan* plan, const void* H, const double* nVar, 
 int isac_ul_pmi_select_dev(isac_ctx* ctx, int32_t nLayers, const void* hest, int32_t K, int32_t nSym, int32_t nRx,
                            int32_t nPorts, double noiseEst, int32_t bandSize, int32_t maxSB, double* pmi, double* sinr,
                            int32_t* subbandIndices, int32_t* nSB, int32_t* nTPMI, int32_t* none);
+/* Batched form: hest [K x nSym x nRx x nPorts x batch]; pmi [maxSB x batch], sinr [maxSB*nTPMI x batch] (each column
+ * packed as [nSB x nTPMI]), none [batch].  One stream synchronisation for the whole batch. */
+int isac_ul_pmi_select_batch_dev(isac_ctx* ctx, int32_t nLayers, const void* hest, int32_t K, int32_t nSym, int32_t nRx,
+                                 int32_t nPorts, double noiseEst, int32_t bandSize, int32_t batch, int32_t maxSB, double* pmi,
+                                 double* sinr, int32_t* nSB, int32_t* nTPMI, int32_t* none);
 /* [antsym,antind] = communication.phyLayer.prgPrecode(siz,nstartgrid,portsym,portind,F) (prgPrecode.m:53).
  * portsym complex64 / portind int32 (1-based) [NRE x nLayers], F complex64 [nLayers x P x NPRG] (device);
  * antsym complex64 / antind int32 [NRE x P] (device). */
@@ -297,6 +302,9 @@ int isac_cdl_get_rays(const isac_cdl_channel* ch, int32_t* nClusters, int32_t* n
 /* H: device complex64 [K x L x nRx x nTx] for subcarrier spacing scsHz, symbol times t0 + symTime[l] (seconds) */
 int isac_cdl_generate_dev(isac_cdl_channel* ch, int32_t K, double scsHz, int32_t L, const double* symTime, double t0,
                           void* H);
+/* n channels (all with the same nRx x nTx), outputs stacked: H [K x L x nRx x nTx x n], start times t0[n] */
+int isac_cdl_generate_batch_dev(isac_cdl_channel* const* ch, int32_t n, int32_t K, double scsHz, int32_t L,
+                                const double* symTime, const double* t0, void* H);
 
 #ifdef __cplusplus
 }

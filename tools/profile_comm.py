@@ -11,7 +11,7 @@ P = importlib.import_module(PKG)
 sys.argv = [sys.argv[0]]
 import bench
 
-comm = bench.CommWorkload(P, 1, 0)
+comm = bench.CommWorkload(P, 4, 0)
 for i in range(2):
     comm.step(i)
 torch.cuda.synchronize()
