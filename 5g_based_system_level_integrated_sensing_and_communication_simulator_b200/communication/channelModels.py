@@ -57,6 +57,23 @@ class CDLChannel:
                                                            float(t0), self._lib.ptr(out)), self.ctx.handle)
         return out
 
+    @staticmethod
+    def generateBatch(channels, K, scs_hz, sym_times, t0, out=None):
+        """All ``channels`` (same profile / array sizes) in two launches: H stacked [n][nTx][nRx][L][K]."""
+        import numpy as np
+        import torch
+        c0 = channels[0]
+        C, lib_ = c0._C, c0._lib
+        st = np.ascontiguousarray(sym_times, dtype=np.float64)
+        t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=np.float64), (len(channels),)))
+        if out is None:
+            out = torch.empty((len(channels), c0.nTx, c0.nRx, st.size, K), dtype=torch.complex64, device=f"cuda:{c0.ctx.device}")
+        hs = (C.c_void_p * len(channels))(*[ch.handle for ch in channels])
+        c0.ctx.use_torch_stream()
+        lib_.check(c0.ctx.lib.isac_cdl_generate_batch_dev(hs, len(channels), int(K), float(scs_hz), int(st.size), lib_.ptr(st),
+                                                          lib_.ptr(t0), lib_.ptr(out)), c0.ctx.handle)
+        return out
+
     def close(self):
         if self.handle:
             self.ctx.lib.isac_cdl_destroy(self.handle)

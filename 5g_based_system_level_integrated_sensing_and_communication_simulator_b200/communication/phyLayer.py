@@ -370,6 +370,30 @@ def pmiSelect(nlayers, hest, noiseest, bandSize):
     return pmi[:n].copy(), sinr[: n * nT].reshape((n, nT), order="F"), idx[: 2 * n].reshape((n, 2), order="F")
 
 
+def pmiSelectBatch(nlayers, hest, noiseest, bandSize):
+    """pmiSelect for a batch of estimates resident on the device: hest torch complex64 [batch][nPorts][nRx][nSym][K].
+    Returns (pmi [nSB x batch], sinr [nSB x nTPMI x batch], none [batch]); one synchronisation for the batch."""
+    hd = hest.contiguous()
+    B, P, R, Ls, K = hd.shape
+    ctx = _lib.get_context(None)
+    max_sb = int(math.ceil(K / 12 / bandSize)) + 1
+    nT = maxPUSCHPrecodingMatrixIndicator(nlayers, P) + 1
+    pmi = np.zeros(max_sb * B)
+    sinr = np.zeros(max_sb * nT * B)
+    none = np.zeros(B, dtype=np.int32)
+    nSB, nTo = C.c_int32(), C.c_int32()
+    ctx.use_torch_stream()
+    _lib.check(ctx.lib.isac_ul_pmi_select_batch_dev(ctx.handle, int(nlayers), _lib.ptr(hd), K, Ls, R, P, float(noiseest),
+                                                    int(bandSize), B, max_sb, _lib.ptr(pmi), _lib.ptr(sinr), C.byref(nSB),
+                                                    C.byref(nTo), _lib.ptr(none)), ctx.handle)
+    n = nSB.value
+    pmi = pmi.reshape((max_sb, B), order="F")[:n].copy()
+    sinr = np.stack([sinr.reshape((max_sb * nT, B), order="F")[: n * nT, b].reshape((n, nT), order="F") for b in range(B)], axis=2)
+    pmi[:, none != 0] = np.nan
+    sinr[:, :, none != 0] = np.nan
+    return pmi, sinr, none
+
+
 def precodedSINR(H, sigma, W):
     """``sinr = communication.phyLayer.precodedSINR(H,sigma,W)`` (precodedSINR.m:11-18): LMMSE SINR summed over the
     layers for one RE.  Evaluated by the UL kernel on a one-RE grid."""

@@ -997,15 +997,14 @@ int isac_cdl_get_rays(const isac_cdl_channel* ch, int32_t* nCl, int32_t* nRays, 
 int isac_cdl_generate_batch_dev(isac_cdl_channel* const* ch, int32_t n, int32_t K, double scsHz, int32_t L, const double* symTime,
                                 const double* t0, void* H) {
     if (!ch || n < 1 || !H || !symTime || !t0) return ISAC_ERR_INVALID_ARG;
+    std::vector<CdlRays*> rays(n);
     for (int i = 0; i < n; ++i) {
-        if (!ch[i]) return ISAC_ERR_INVALID_ARG;
-        Ctx* c = ch[i]->ctx;
-        cudaSetDevice(c->device);
-        const size_t stride = (size_t)K * L * ch[i]->rays.nRx * ch[i]->rays.nTx;
-        int st = cdl_generate(c, ch[i]->rays, K, scsHz, L, symTime, t0[i], (float2*)H + stride * i, c->stream);
-        if (st) return st;
+        if (!ch[i] || ch[i]->ctx != ch[0]->ctx) return ISAC_ERR_INVALID_ARG;
+        rays[i] = &ch[i]->rays;
     }
-    return ISAC_OK;
+    Ctx* c = ch[0]->ctx;
+    cudaSetDevice(c->device);
+    return cdl_generate_batch(c, rays.data(), n, K, scsHz, L, symTime, t0, (float2*)H, c->stream);
 }
 
 int isac_cdl_generate_dev(isac_cdl_channel* ch, int32_t K, double scsHz, int32_t L, const double* symTime, double t0, void* H) {

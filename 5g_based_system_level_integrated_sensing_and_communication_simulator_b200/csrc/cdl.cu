@@ -10,6 +10,7 @@
 // and Dopplers.  Device: (1) C_n[l,u,s] = sum_{m in n} g_m[u,s] e^{2 pi j nu_m t_l}; (2) the write-bound
 // contraction H[k,(l,u,s)] = sum_n e^{-2 pi j f_k tau_n} C_n[(l,u,s)] (contraction length = #clusters <= 24).
 #include "cdl.cuh"
+#include <algorithm>
 #include "ctx.cuh"
 #include <cmath>
 #include <cstring>
@@ -170,17 +171,29 @@ struct CdlTimes { double t[kCdlMaxSym]; };
 
 // C_n[l,u,s] = sum_{m in n} g_m[u,s] exp(2 pi j nu_m t_l); rays of cluster n are [n*nRay, (n+1)*nRay) (+ the LOS ray).
 // One CTA per (cluster, symbol): the <= 21 ray phasors are computed once, then threads sweep the antenna pairs.
+// blockIdx.z = channel of the batch (all channels of a launch share nCl / nRay / array sizes; ray tables differ).
+constexpr int kCdlMaxBatch = 32;
+struct CdlBatch {
+    const double2* g[kCdlMaxBatch];
+    const double* nu[kCdlMaxBatch];
+    const double* tau[kCdlMaxBatch];
+    double t0[kCdlMaxBatch];
+};
+
 __global__ void __launch_bounds__(128)
-cdl_cluster_kernel(const double2* __restrict__ g, const double* __restrict__ nu, int nRay, int losRay, int nCl, int nRx,
-                   int nTx, int L, const CdlTimes tl, float2* __restrict__ C /*[nCl][J]*/) {
+cdl_cluster_kernel(const CdlBatch bt, int nRay, int losRay, int nCl, int nRx, int nTx, int L, const CdlTimes tl,
+                   float2* __restrict__ Call /*[batch][nCl][J]*/) {
     __shared__ double2 ph[32];
     __shared__ int rayIdx[32];
     const int n = blockIdx.x, l = blockIdx.y, RT = nRx * nTx;
+    const double2* __restrict__ g = bt.g[blockIdx.z];
+    const double* __restrict__ nu = bt.nu[blockIdx.z];
+    float2* __restrict__ C = Call + (size_t)blockIdx.z * nCl * L * RT;
     const int cnt = nRay + ((n == 0 && losRay >= 0) ? 1 : 0);
     if ((int)threadIdx.x < cnt) {
         const int m = (int)threadIdx.x < nRay ? n * nRay + threadIdx.x : losRay;
         double s, c;
-        sincospi(2.0 * nu[m] * tl.t[l], &s, &c);
+        sincospi(2.0 * nu[m] * (bt.t0[blockIdx.z] + tl.t[l]), &s, &c);
         ph[threadIdx.x] = make_double2(c, s);
         rayIdx[threadIdx.x] = m;
     }
@@ -222,8 +235,11 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], 
 }
 
 __global__ void __launch_bounds__(256)
-cdl_response_kernel(const float2* __restrict__ C, const double* __restrict__ tau, int nCl, int K, long long J, double scs,
-                    float2* __restrict__ H) {
+cdl_response_kernel(const float2* __restrict__ Call, const CdlBatch bt, int nCl, int K, long long J, double scs,
+                    float2* __restrict__ Hall) {
+    const float2* __restrict__ C = Call + (size_t)blockIdx.z * nCl * J;
+    const double* __restrict__ tau = bt.tau[blockIdx.z];
+    float2* __restrict__ H = Hall + (size_t)blockIdx.z * K * J;
     __shared__ float2 Es[kCdlMaxCl][kCdlTK + 4];   // +4: fragment loads of 8 consecutive rows hit distinct banks
     __shared__ float2 Cs[kCdlMaxCl][kCdlTJ + 4];
     const int k0 = blockIdx.x * kCdlTK;
@@ -322,30 +338,59 @@ void cdl_free(CdlRays& rays) {
     rays.d_g = nullptr; rays.d_nu = nullptr; rays.d_tau = nullptr;
 }
 
-int cdl_generate(Ctx* ctx, CdlRays& rays, int K, double scsHz, int L, const double* symTime, double t0, float2* H,
-                 cudaStream_t st) {
-    if (!H || K < 1 || L < 1 || L > kCdlMaxSym || !symTime || rays.nCl < 1 || rays.nCl > kCdlMaxCl) {
+int cdl_generate_batch(Ctx* ctx, CdlRays* const* rays, int n, int K, double scsHz, int L, const double* symTime,
+                       const double* t0, float2* H, cudaStream_t st) {
+    if (!H || !rays || !t0 || n < 1 || K < 1 || L < 1 || L > kCdlMaxSym || !symTime) {
         set_error(ctx, "cdl_generate: invalid argument (L <= 16 symbols per call)");
         return kErrInvalidArg;
     }
-    int s = cdl_upload(ctx, rays);
-    if (s) return s;
-    const int RT = rays.nRx * rays.nTx;
-    void* dC = nullptr;
-    if ((s = ctx_scratch(ctx, 10, sizeof(float2) * (size_t)rays.nCl * L * RT, &dC))) return s;
-    CdlTimes tl{};
-    for (int l = 0; l < L; ++l) tl.t[l] = t0 + symTime[l];
-    const int pr = prof_begin(ctx, kProfCdl, st);
-    const int losRay = rays.los ? rays.nCl * rays.nRay : -1;
-    dim3 g1(rays.nCl, L);
-    cdl_cluster_kernel<<<g1, 128, 0, st>>>(rays.d_g, rays.d_nu, rays.nRay, losRay, rays.nCl, rays.nRx, rays.nTx, L, tl, (float2*)dC);
+    const CdlRays& r0 = *rays[0];
+    if (r0.nCl < 1 || r0.nCl > kCdlMaxCl) {
+        set_error(ctx, "cdl_generate: invalid ray table");
+        return kErrInvalidArg;
+    }
+    for (int i = 0; i < n; ++i) {
+        const CdlRays& r = *rays[i];
+        if (r.nCl != r0.nCl || r.nRay != r0.nRay || r.nRx != r0.nRx || r.nTx != r0.nTx || r.los != r0.los) {
+            set_error(ctx, "cdl_generate_batch: channels of one batch must share profile and array sizes");
+            return kErrInvalidArg;
+        }
+        int s = cdl_upload(ctx, *rays[i]);
+        if (s) return s;
+    }
+    const int RT = r0.nRx * r0.nTx;
     const long long J = (long long)L * RT;
-    dim3 grid((K + kCdlTK - 1) / kCdlTK, (unsigned)((J + kCdlTJ - 1) / kCdlTJ));
-    cdl_response_kernel<<<grid, 256, 0, st>>>((const float2*)dC, rays.d_tau, rays.nCl, K, J, scsHz, H);
-    prof_end(ctx, pr, st);
-    count_launches(ctx, 2);
+    CdlTimes tl{};
+    for (int l = 0; l < L; ++l) tl.t[l] = symTime[l];
+    const int losRay = r0.los ? r0.nCl * r0.nRay : -1;
+    for (int i0 = 0; i0 < n; i0 += kCdlMaxBatch) {
+        const int nb = std::min(kCdlMaxBatch, n - i0);
+        void* dC = nullptr;
+        int s = ctx_scratch(ctx, 10, sizeof(float2) * (size_t)nb * r0.nCl * L * RT, &dC);
+        if (s) return s;
+        CdlBatch bt{};
+        for (int i = 0; i < nb; ++i) {
+            bt.g[i] = rays[i0 + i]->d_g;
+            bt.nu[i] = rays[i0 + i]->d_nu;
+            bt.tau[i] = rays[i0 + i]->d_tau;
+            bt.t0[i] = t0[i0 + i];
+        }
+        const int pr = prof_begin(ctx, kProfCdl, st);
+        dim3 g1(r0.nCl, L, nb);
+        cdl_cluster_kernel<<<g1, 128, 0, st>>>(bt, r0.nRay, losRay, r0.nCl, r0.nRx, r0.nTx, L, tl, (float2*)dC);
+        dim3 grid((K + kCdlTK - 1) / kCdlTK, (unsigned)((J + kCdlTJ - 1) / kCdlTJ), nb);
+        cdl_response_kernel<<<grid, 256, 0, st>>>((const float2*)dC, bt, r0.nCl, K, J, scsHz, H + (size_t)i0 * K * J);
+        prof_end(ctx, pr, st);
+        count_launches(ctx, 2);
+    }
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     return kOk;
+}
+
+int cdl_generate(Ctx* ctx, CdlRays& rays, int K, double scsHz, int L, const double* symTime, double t0, float2* H,
+                 cudaStream_t st) {
+    CdlRays* one = &rays;
+    return cdl_generate_batch(ctx, &one, 1, K, scsHz, L, symTime, &t0, H, st);
 }
 
 }  // namespace isac

@@ -41,4 +41,8 @@ void cdl_free(CdlRays& rays);
 int cdl_generate(Ctx* ctx, CdlRays& rays, int K, double scsHz, int L, const double* symTime, double t0, float2* H,
                  cudaStream_t st);
 
+// n channels of identical geometry in two launches (blockIdx.z = channel); H stacked [n][K x L x nRx x nTx]
+int cdl_generate_batch(Ctx* ctx, CdlRays* const* rays, int n, int K, double scsHz, int L, const double* symTime,
+                       const double* t0, float2* H, cudaStream_t st);
+
 }  // namespace isac

@@ -62,3 +62,21 @@ def test_cdl_statistics_over_seeds(gpu):
     m = float(np.mean(acc))
     print("mean channel power over seeds", m)
     assert 0.8 < m < 1.2
+
+
+@pytest.mark.gpu
+def test_cdl_batch_equals_single(gpu):
+    """isac_cdl_generate_batch_dev (blockIdx.z = channel) against one isac_cdl_generate_dev call per channel."""
+    import torch
+    cm = importlib.import_module(PKG + ".communication.channelModels")
+    chans = [cm.CDLChannel("CDL-C", TransmitAntennaArraySize=(1, 4, 2), ReceiveAntennaArraySize=(1, 2, 2), Seed=40 + i)
+             for i in range(5)]
+    K, scs = 24 * 12, 30e3
+    sym = np.arange(14) * 35.7e-6
+    t0 = 0.01 * np.arange(5)
+    Hb = cm.CDLChannel.generateBatch(chans, K, scs, sym, t0)
+    for i, ch in enumerate(chans):
+        Hi = ch.generate(K, scs, sym, t0=float(t0[i]))
+        assert torch.equal(Hb[i], Hi)
+    for ch in chans:
+        ch.close()

@@ -192,6 +192,28 @@ def test_ul_pmi_select(PH, nu, P, R):
     assert all(np.isnan(x) for x in r)
 
 
+def test_ul_pmi_select_batch(PH):
+    """Batched TPMI selection (one launch pair, one sync) equals per-UE pmiSelect calls, including an all-zero estimate."""
+    import torch
+    rng = np.random.default_rng(77)
+    nrb, band, nu, P, R, B = 24, 4, 2, 4, 8, 5
+    K = 12 * nrb
+    hest = np.zeros((B, K, 1, R, P), dtype=np.complex64)
+    sc = np.arange(1, K, 4)
+    hest[:, sc, 0] = ((rng.standard_normal((B, sc.size, R, P)) + 1j * rng.standard_normal((B, sc.size, R, P))) / np.sqrt(2)).astype(np.complex64)
+    hest[3] = 0                                    # UE without an estimate -> NaN column
+    hd = torch.from_numpy(np.ascontiguousarray(hest.transpose(0, 4, 3, 2, 1))).cuda()
+    pmi_b, sinr_b, none = PH.pmiSelectBatch(nu, hd, 0.05, band)
+    assert list(none) == [0, 0, 0, 1, 0]
+    for b in range(B):
+        r = PH.pmiSelect(nu, hest[b], 0.05, band)
+        if b == 3:
+            assert all(np.isnan(x) for x in r) and np.isnan(pmi_b[:, b]).all()
+            continue
+        assert np.array_equal(pmi_b[:, b], r[0], equal_nan=True)
+        assert np.array_equal(sinr_b[:, :, b], r[1], equal_nan=True)
+
+
 def test_prg_precode(PH):
     rng = np.random.default_rng(8)
     nrb, L, nu, P, nprg = 24, 14, 2, 8, 6
