@@ -128,6 +128,8 @@ def _declare(lib):
         "isac_pusch_codebook": ([i32, i32, P(i32), vp], C.c_int),
         "isac_pmi_plan_create": ([vp, P(CsiConfig), i32, i32, P(vp)], C.c_int),
         "isac_pmi_plan_destroy": ([vp], C.c_int),
+        "isac_pmi_plan_set_kernel": ([vp, i32], C.c_int),
+        "isac_csi_plan_set_kernel": ([vp, i32], C.c_int),
         "isac_pmi_plan_info": ([vp, P(i32), P(i32), P(i32), P(i32), vp, vp], C.c_int),
         "isac_dl_pmi_select_dev": ([vp, vp, vp, i32], C.c_int),
         "isac_dl_pmi_collect": ([vp, i32, vp, vp, vp], C.c_int),

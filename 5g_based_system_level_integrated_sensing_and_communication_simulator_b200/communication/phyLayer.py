@@ -154,6 +154,18 @@ def _h_to_dev(H):
 
 
 _pmi_plans, _csi_plans = {}, {}
+_direct_kernel = False
+
+
+def setSinrKernel(direct):
+    """Choose the SINR kernel of the DL selection functions: False (default) Gram-pair form, True direct H*W form
+    (isac_pmi_plan_set_kernel).  Both give the same results to rounding; exposed for the parity tests."""
+    global _direct_kernel
+    _direct_kernel = bool(direct)
+    for ent in _pmi_plans.values():
+        _lib.get_context(None).lib.isac_pmi_plan_set_kernel(ent[0], int(_direct_kernel))
+    for ent in _csi_plans.values():
+        _lib.get_context(None).lib.isac_csi_plan_set_kernel(ent[0], int(_direct_kernel))
 
 
 def _pmi_plan(cs, nLayers, batch):
@@ -163,6 +175,7 @@ def _pmi_plan(cs, nLayers, batch):
     if ent is None or ent[1] < batch:
         h = C.c_void_p()
         _lib.check(ctx.lib.isac_pmi_plan_create(ctx.handle, C.byref(cs.cfg), int(nLayers), int(batch), C.byref(h)), ctx.handle)
+        ctx.lib.isac_pmi_plan_set_kernel(h, int(_direct_kernel))
         ent = (h, batch, cs)
         _pmi_plans[key] = ent
     return ctx, ent[0]
@@ -175,6 +188,7 @@ def _csi_plan(cs, batch):
     if ent is None or ent[1] < batch:
         h = C.c_void_p()
         _lib.check(ctx.lib.isac_csi_plan_create(ctx.handle, C.byref(cs.cfg), int(batch), C.byref(h)), ctx.handle)
+        ctx.lib.isac_csi_plan_set_kernel(h, int(_direct_kernel))
         ent = (h, batch, cs)
         _csi_plans[key] = ent
     return ctx, ent[0]

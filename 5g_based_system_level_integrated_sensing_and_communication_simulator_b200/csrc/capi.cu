@@ -687,6 +687,12 @@ int isac_pmi_plan_destroy(isac_pmi_plan* pl) {
     return ISAC_OK;
 }
 
+int isac_pmi_plan_set_kernel(isac_pmi_plan* pl, int32_t direct) {
+    if (!pl || !pl->p) return ISAC_ERR_INVALID_ARG;
+    pl->p->direct = direct != 0;
+    return ISAC_OK;
+}
+
 int isac_pmi_plan_info(const isac_pmi_plan* pl, int32_t dims[4], int32_t* nSB, int32_t* nCqiSB, int32_t* nRE, int32_t* reKs,
                        int32_t* reLs) {
     if (!pl || !pl->p) return ISAC_ERR_INVALID_ARG;
@@ -741,8 +747,10 @@ int isac_csi_plan_create(isac_ctx* h, const isac_csi_config* cfg, int32_t maxBat
     pl->maxBatch = maxBatch;
     for (int r = 0; r < kMaxLayers; ++r) pl->byRank[r] = nullptr;
     const int maxRank = pl->cfg.nRx < pl->cfg.nPorts ? pl->cfg.nRx : pl->cfg.nPorts;  // riSelect.m:222
+    PmiShared* share = nullptr;  // ranks built from the same beams share one Gram-pair dictionary -> one fused SINR launch
     for (int r = 1; r <= maxRank && r <= kMaxLayers; ++r) {
-        int st = pmi_plan_create(&h->c, pl->cfg, r, maxBatch, &pl->byRank[r - 1]);
+        int st = pmi_plan_create(&h->c, pl->cfg, r, maxBatch, &pl->byRank[r - 1], share);
+        if (!st && !share) share = pl->byRank[r - 1]->sh;
         if (st) {
             isac_csi_plan_destroy(pl);
             return st;
@@ -762,6 +770,13 @@ int isac_csi_plan_destroy(isac_csi_plan* pl) {
     return ISAC_OK;
 }
 
+int isac_csi_plan_set_kernel(isac_csi_plan* pl, int32_t direct) {
+    if (!pl) return ISAC_ERR_INVALID_ARG;
+    for (int r = 0; r < kMaxLayers; ++r)
+        if (pl->byRank[r]) pl->byRank[r]->direct = direct != 0;
+    return ISAC_OK;
+}
+
 // riSelect.m:254-294 for a batch; keeps every evaluated rank's results for the fused report
 static int ri_select_batch(isac_csi_plan* pl, const float2* H, const double* nVar, int batch, std::vector<double>& RI,
                            std::vector<PmiResult>& chosen, std::vector<std::vector<PmiResult>>& all) {
@@ -778,8 +793,10 @@ static int ri_select_batch(isac_csi_plan* pl, const float2* H, const double* nVa
         for (auto& r : chosen) { r.allNaN = true; r.i2.assign(nSB, NAN); }
         return kOk;
     }
-    for (int r : valid) {
-        int st = pmi_select_run(pl->byRank[r - 1], H, nVar, batch, c->stream);
+    {
+        std::vector<PmiPlan*> plans;
+        for (int r : valid) plans.push_back(pl->byRank[r - 1]);
+        int st = pmi_select_run_multi(plans.data(), (int)plans.size(), H, nVar, batch, c->stream);
         if (st) return st;
     }
     for (int r : valid) {

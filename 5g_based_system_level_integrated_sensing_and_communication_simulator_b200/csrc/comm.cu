@@ -36,6 +36,58 @@ struct PmiDev {
 
 __device__ __forceinline__ double round4(double x) { return copysign(floor(fabs(x) * 1e4 + 0.5) / 1e4, x); }
 
+#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))   /* packed lower triangle, i >= j: stays in registers */
+
+// A (packed lower triangle of (HW)'(HW)) -> sinr_l = 1/(nVar [ (A + nVar I)^-1 ]_ll) - 1, l = 0..NU-1, written with stride
+// (dlPMISelect.m:1831-1833).  Cholesky A = L L^H in place, then [A^-1]_cc = || L^-1 e_c ||^2.
+template <int NU>
+__device__ __forceinline__ void chol_sinr(double2 (&A)[NU * (NU + 1) / 2], double nVar, double* __restrict__ out, long long stride) {
+    // every loop runs 0..NU with a compile-time guard, so each one unrolls on its own (trip counts that depend on an
+    // outer induction variable made the unroller fall back to local memory for some NU)
+#pragma unroll
+    for (int i = 0; i < NU; ++i) A[TRI(i, i)].x += nVar;
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+        double d = A[TRI(j, j)].x;
+#pragma unroll
+        for (int k = 0; k < NU; ++k)
+            if (k < j) d -= A[TRI(j, k)].x * A[TRI(j, k)].x + A[TRI(j, k)].y * A[TRI(j, k)].y;
+        // store 1/L_jj on the diagonal (one rsqrt + one Newton step instead of sqrt and two divisions)
+        double inv = rsqrt(d);
+        inv = inv * (1.5 - 0.5 * d * inv * inv);
+        A[TRI(j, j)] = make_double2(inv, 0.0);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            if (i > j) {
+                double2 s = A[TRI(i, j)];
+#pragma unroll
+                for (int k = 0; k < NU; ++k)
+                    if (k < j) s = zsub(s, zmulc(A[TRI(i, k)], A[TRI(j, k)]));
+                A[TRI(i, j)] = make_double2(s.x * inv, s.y * inv);
+            }
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < NU; ++cc) {
+        double2 x[NU];
+        x[cc] = make_double2(A[TRI(cc, cc)].x, 0.0);  // diagonal holds 1/L_cc
+        double nrm = x[cc].x * x[cc].x;
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+            if (i > cc) {
+                double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < NU; ++k)
+                    if (k >= cc && k < i) s = zadd(s, zmul(A[TRI(i, k)], x[k]));
+                const double inv = -A[TRI(i, i)].x;
+                x[i] = make_double2(s.x * inv, s.y * inv);
+                nrm += x[i].x * x[i].x + x[i].y * x[i].y;
+            }
+        }
+        out[(long long)cc * stride] = 1.0 / (nVar * nrm) - 1.0;
+    }
+}
+
 template <int NU>
 __global__ void __launch_bounds__(128)
 pmi_sinr_kernel(const PmiDev p) {
@@ -72,7 +124,6 @@ pmi_sinr_kernel(const PmiDev p) {
         }
         const double sc = p.candScale ? p.candScale[c] : p.scale;
         constexpr int NT = NU * (NU + 1) / 2;
-#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))   /* packed lower triangle, i >= j: stays in registers */
         double2 A[NT];
 #pragma unroll
         for (int i = 0; i < NT; ++i) A[i] = make_double2(0.0, 0.0);
@@ -100,44 +151,114 @@ pmi_sinr_kernel(const PmiDev p) {
 #pragma unroll
                 for (int j = 0; j <= i; ++j) A[TRI(i, j)] = zadd(A[TRI(i, j)], zmulc(g[j], g[i]));  // conj(g_i) g_j
         }
+        chol_sinr<NU>(A, nVar, Sout + c, p.nCand);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K9': Gram-pair form.  Every precoder column is sum_blk c_blk (e_blk (x) v_beam), so every entry of (HW)'(HW) is a
+// short sum of inner products Gamma[a,a'] = <Bf[a], Bf[a']> of beam responses ("atoms" a = (blk, beam)) times a
+// coefficient product conj(c_i,blk) c_j,blk' (a 4th/8th root of unity times the codebook scale^2).  The host lists the
+// distinct (a,a') pairs all candidates of ALL ranks need (576 for the 8-port (2,2) panel against 1920 candidates) and the
+// distinct coefficient products (the palette); one CTA per (RE, UE) then computes Bf, the pair table Gamma and walks the
+// candidates of every rank: A_ij = sum_t pal[q_t] Gamma[p_t] (2..4 complex MACs instead of R + 2 NB), Cholesky, SINR.
+// ------------------------------------------------------------------------------------------
+struct PairRank {
+    const uint32_t* terms;   // [NT][T][nCand]
+    const uint8_t* valid;
+    double* S;
+    int nCand, nu, T;
+};
+struct PairDev {
+    const float2* H;
+    const double2* beams;
+    const uint32_t* pairs;
+    const double2* pal;
+    const int* reK;
+    const int* reL;
+    int K, L, R, P, NB, Pb, nBeams, nRE, nPairs, nPal, nRanks;
+    PairRank rk[kMaxLayers];
+    double nVar[kMaxPmiBatch];
+};
+
+template <int NU>
+__device__ __noinline__ void pair_rank_eval(const PairRank rk, const double2* __restrict__ Gm, const double2* __restrict__ pal,
+                                               double nVar, double* __restrict__ Sout) {
+    constexpr int NT = NU * (NU + 1) / 2;
+    const int T = rk.T;
+    for (int c = threadIdx.x; c < rk.nCand; c += blockDim.x) {
+        if (!rk.valid[c]) {
 #pragma unroll
-        for (int i = 0; i < NU; ++i) A[TRI(i, i)].x += nVar;  // (W'H')HW + noise  (dlPMISelect.m:1831-1832)
-        // Cholesky A = L L^H (lower triangle in place)
-#pragma unroll
-        for (int j = 0; j < NU; ++j) {
-            double d = A[TRI(j, j)].x;
-#pragma unroll
-            for (int k = 0; k < j; ++k) d -= A[TRI(j, k)].x * A[TRI(j, k)].x + A[TRI(j, k)].y * A[TRI(j, k)].y;
-            // store 1/L_jj on the diagonal (one rsqrt + one Newton step instead of sqrt and two divisions)
-            double inv = rsqrt(d);
-            inv = inv * (1.5 - 0.5 * d * inv * inv);
-            A[TRI(j, j)] = make_double2(inv, 0.0);
-#pragma unroll
-            for (int i = j + 1; i < NU; ++i) {
-                double2 s = A[TRI(i, j)];
-#pragma unroll
-                for (int k = 0; k < j; ++k) s = zsub(s, zmulc(A[TRI(i, k)], A[TRI(j, k)]));
-                A[TRI(i, j)] = make_double2(s.x * inv, s.y * inv);
-            }
+            for (int j = 0; j < NU; ++j) Sout[(long long)j * rk.nCand + c] = NAN;  // restricted precoder (dlPMISelect.m:418)
+            continue;
         }
-        // [A^-1]_cc = || L^-1 e_c ||^2 ; sinr = 1/(nVar*[A^-1]_cc) - 1   (dlPMISelect.m:1832-1833)
+        double2 A[NT];
+        const uint32_t* __restrict__ tp = rk.terms + c;
 #pragma unroll
-        for (int cc = 0; cc < NU; ++cc) {
-            double2 x[NU];
-            x[cc] = make_double2(A[TRI(cc, cc)].x, 0.0);  // diagonal holds 1/L_cc
-            double nrm = x[cc].x * x[cc].x;
+        for (int e = 0; e < NT; ++e) {
+            double2 acc = make_double2(0.0, 0.0);
+            for (int t = 0; t < T; t += 4) {   // T is a multiple of 4 (absent terms: pair 0 x palette 0 = 0)
 #pragma unroll
-            for (int i = cc + 1; i < NU; ++i) {
-                double2 s = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int k = cc; k < i; ++k) s = zadd(s, zmul(A[TRI(i, k)], x[k]));
-                const double inv = -A[TRI(i, i)].x;
-                x[i] = make_double2(s.x * inv, s.y * inv);
-                nrm += x[i].x * x[i].x + x[i].y * x[i].y;
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t w = __ldg(tp + (size_t)(e * T + t + u) * rk.nCand);
+                    acc = zadd(acc, zmul(Gm[w & 0xffffu], pal[w >> 16]));
+                }
             }
-            Sout[(long long)cc * p.nCand + c] = 1.0 / (nVar * nrm) - 1.0;
+            A[e] = acc;
         }
-#undef TRI
+        chol_sinr<NU>(A, nVar, Sout + c, rk.nCand);
+    }
+}
+
+__global__ void __launch_bounds__(128, 3)
+pmi_pair_kernel(const __grid_constant__ PairDev p) {
+    extern __shared__ double2 sm[];
+    const int R = p.R, P = p.P, nAtoms = p.NB * p.nBeams;
+    double2* Hs = sm;                       // [R][P]
+    double2* Bf = Hs + R * P;               // [R][NB][nBeams]
+    double2* Gm = Bf + (size_t)R * nAtoms;  // [nPairs]
+    double2* pal = Gm + p.nPairs;           // [nPal]
+    const int e = blockIdx.x, b = blockIdx.y;
+    const long long kk = p.reK[e] - 1, ll = p.reL[e] - 1;
+    const float2* __restrict__ Hb = p.H + (long long)b * p.K * p.L * R * P;
+    for (int i = threadIdx.x; i < R * P; i += blockDim.x) {
+        const int r = i % R, pp = i / R;
+        const float2 h = __ldg(Hb + kk + p.K * (ll + (long long)p.L * (r + (long long)R * pp)));
+        Hs[r * P + pp] = make_double2((double)h.x, (double)h.y);
+    }
+    for (int i = threadIdx.x; i < p.nPal; i += blockDim.x) pal[i] = p.pal[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * nAtoms; i += blockDim.x) {
+        const int bm = i % p.nBeams, blk = (i / p.nBeams) % p.NB, r = i / nAtoms;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int q = 0; q < p.Pb; ++q) acc = zadd(acc, zmul(Hs[r * P + blk * p.Pb + q], p.beams[bm * p.Pb + q]));
+        Bf[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.nPairs; i += blockDim.x) {
+        const uint32_t w = __ldg(p.pairs + i);
+        const int a = w & 0xffffu, a2 = w >> 16;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int r = 0; r < R; ++r) acc = zadd(acc, zmulc(Bf[r * nAtoms + a2], Bf[r * nAtoms + a]));  // conj(Bf[a]) Bf[a']
+        Gm[i] = acc;
+    }
+    __syncthreads();
+    const double nVar = p.nVar[b];
+#pragma unroll
+    for (int q = 0; q < kMaxLayers; ++q) {   // static index: the descriptors stay in the parameter bank
+        if (q >= p.nRanks) break;
+        const PairRank rk = p.rk[q];
+        double* __restrict__ Sout = rk.S + ((long long)b * p.nRE + e) * rk.nu * (long long)rk.nCand;
+        switch (rk.nu) {
+            case 1: pair_rank_eval<1>(rk, Gm, pal, nVar, Sout); break;
+            case 2: pair_rank_eval<2>(rk, Gm, pal, nVar, Sout); break;
+            case 3: pair_rank_eval<3>(rk, Gm, pal, nVar, Sout); break;
+            case 4: pair_rank_eval<4>(rk, Gm, pal, nVar, Sout); break;
+            case 5: pair_rank_eval<5>(rk, Gm, pal, nVar, Sout); break;
+            case 6: pair_rank_eval<6>(rk, Gm, pal, nVar, Sout); break;
+            case 7: pair_rank_eval<7>(rk, Gm, pal, nVar, Sout); break;
+            default: pair_rank_eval<8>(rk, Gm, pal, nVar, Sout); break;
+        }
     }
 }
 
@@ -304,7 +425,7 @@ static void partition_res(const std::vector<int>& k, const std::vector<int>& l, 
     start[nSB] = e;
 }
 
-int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, PmiPlan** out) {
+int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, PmiPlan** out, PmiShared* share) {
     if (maxBatch < 1 || cin.nRx < 1 || cin.nPorts < 1 || cin.K < 12 || cin.L < 1 || cin.nRE < 0) {
         set_error(ctx, "pmi_plan_create: invalid configuration");
         return kErrInvalidArg;
@@ -374,6 +495,77 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
             lb[(size_t)c * nu + j] = store_idx(d.beam);
             for (int b = 0; b < t.NB; ++b) coef[((size_t)c * nu + j) * t.NB + b] = make_double2(d.coef[b].real(), d.coef[b].imag());
         }
+    // Gram-pair terms (K9'): register this rank's pairs / coefficient products in the (shared) dictionary
+    {
+        PmiShared* sh = share;
+        auto compatible = [&](const PmiShared* q) {
+            if (q->pairs.empty() && q->beams.empty()) return true;
+            if (q->NB != t.NB || q->Pb != t.Pb || q->nBeams != t.nBeams || q->P != t.P || q->beams.size() != beams.size()) return false;
+            for (size_t i = 0; i < beams.size(); ++i)
+                if (q->beams[i].x != beams[i].x || q->beams[i].y != beams[i].y) return false;
+            return true;
+        };
+        if (!sh || !compatible(sh)) sh = new PmiShared();
+        if (sh->beams.empty()) {
+            sh->NB = t.NB; sh->Pb = t.Pb; sh->nBeams = t.nBeams; sh->P = t.P;
+            sh->beams = beams;
+            sh->pal.push_back(make_double2(0.0, 0.0));
+            sh->pairs.push_back(0u);
+            sh->pairIdx[0u] = 0;
+        }
+        ++sh->refs;
+        p->sh = sh;
+        const int NT = nu * (nu + 1) / 2;
+        std::vector<std::vector<uint32_t>> cand((size_t)nCand * NT);
+        int T = 1;
+        for (int c = 0; c < nCand; ++c) {
+            if (!t.valid[c]) continue;
+            const double sc = t.candScale.empty() ? t.scale : t.candScale[c];
+            for (int i = 0; i < nu; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    const LayerDesc& di = t.layers[(size_t)c * nu + i];
+                    const LayerDesc& dj = t.layers[(size_t)c * nu + j];
+                    std::vector<uint32_t>& v = cand[(size_t)c * NT + i * (i + 1) / 2 + j];
+                    for (int bi = 0; bi < t.NB; ++bi)
+                        for (int bj = 0; bj < t.NB; ++bj) {
+                            const std::complex<double> q = std::conj(di.coef[bi]) * dj.coef[bj] * (sc * sc);
+                            if (std::abs(q) < 1e-300) continue;
+                            const uint32_t a = (uint32_t)(bi * t.nBeams + store_idx(di.beam)), a2 = (uint32_t)(bj * t.nBeams + store_idx(dj.beam));
+                            const uint32_t key = a | (a2 << 16);
+                            auto pit = sh->pairIdx.find(key);
+                            int pi;
+                            if (pit == sh->pairIdx.end()) {
+                                pi = (int)sh->pairs.size();
+                                sh->pairs.push_back(key);
+                                sh->pairIdx[key] = pi;
+                            } else pi = pit->second;
+                            const std::pair<long long, long long> pk(std::llround(q.real() * 1099511627776.0), std::llround(q.imag() * 1099511627776.0));
+                            auto qit = sh->palIdx.find(pk);
+                            int qi;
+                            if (qit == sh->palIdx.end()) {
+                                qi = (int)sh->pal.size();
+                                sh->pal.push_back(make_double2(q.real(), q.imag()));
+                                sh->palIdx[pk] = qi;
+                            } else qi = qit->second;
+                            if (pi > 0xffff || qi > 0xffff || t.NB * t.nBeams > 0xffff) { sh->ok = false; pi = qi = 0; }
+                            v.push_back((uint32_t)pi | ((uint32_t)qi << 16));
+                        }
+                    T = std::max(T, (int)v.size());
+                }
+        }
+        T = (T + 3) / 4 * 4;
+        p->termT = T;
+        std::vector<uint32_t> terms((size_t)NT * T * nCand, 0u);  // absent term: pair 0 x palette 0 (= 0)
+        for (int c = 0; c < nCand; ++c)
+            for (int e = 0; e < NT; ++e) {
+                const std::vector<uint32_t>& v = cand[(size_t)c * NT + e];
+                for (size_t q = 0; q < v.size(); ++q) terms[((size_t)e * T + q) * nCand + c] = v[q];
+            }
+        if ((s = upload(ctx, &p->d_terms, terms))) {
+            pmi_plan_destroy(p);
+            return s;
+        }
+    }
     PmiPlan* ex = p;
 #define UP(dst, vec)                                   \
     if ((s = upload(ctx, &(dst), vec))) {              \
@@ -417,7 +609,12 @@ void pmi_plan_destroy(PmiPlan* p) {
     cudaFree(p->d_beams); cudaFree(p->d_layerBeam); cudaFree(p->d_layerCoef); cudaFree(p->d_candScale);
     cudaFree(p->d_valid); cudaFree(p->d_reK); cudaFree(p->d_reL); cudaFree(p->d_reSb); cudaFree(p->d_reW);
     cudaFree(p->d_reCqiSb); cudaFree(p->d_reCqiW); cudaFree(p->d_S); cudaFree(p->d_total); cudaFree(p->d_sub);
-    cudaFree(p->d_sel); cudaFree(p->d_sinrSel); cudaFree(p->d_sinrWb);
+    cudaFree(p->d_sel); cudaFree(p->d_sinrSel); cudaFree(p->d_sinrWb); cudaFree(p->d_terms);
+    if (p->sh && --p->sh->refs == 0) {
+        cudaFree(p->sh->d_pairs);
+        cudaFree(p->sh->d_pal);
+        delete p->sh;
+    }
     delete p;
 }
 
@@ -431,31 +628,14 @@ static cudaError_t launch_sinr(const PmiDev& d, int batch, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, cudaStream_t st) {
-    Ctx* ctx = p->ctx;
-    if (batch < 1 || batch > p->maxBatch || !H || !nVar) {
-        set_error(ctx, "pmi_select_run: invalid argument");
-        return kErrInvalidArg;
-    }
-    const int nRE = (int)p->reK.size();
-    if (nRE == 0) return kOk;  // everything NaN (dlPMISelect.m:362-379), decided at collect time
-    if (batch > kMaxPmiBatch) {
-        set_error(ctx, "pmi_select_run: batch exceeds kMaxPmiBatch");
-        return kErrCapacity;
-    }
-    for (int b = 0; b < batch; ++b)
-        if (!(nVar[b] >= 0.0) || !std::isfinite(nVar[b])) {
-            set_error(ctx, "dlPMISelect: NVAR must be real, nonnegative and finite");
-            return kErrInvalidArg;
-        }
+static int pmi_direct_launch(PmiPlan* p, const float2* H, const double* nv, int batch, cudaStream_t st) {
     const CodebookTable& t = p->tab;
     PmiDev d{};
     d.H = H; d.beams = p->d_beams; d.layerBeam = p->d_layerBeam; d.layerCoef = p->d_layerCoef;
     d.candScale = nullptr; d.valid = p->d_valid; d.reK = p->d_reK; d.reL = p->d_reL; d.S = p->d_S;
-    for (int b = 0; b < batch; ++b) d.nVar[b] = nVar[b] < 1e-10 ? 1e-10 : nVar[b];  // dlPMISelect.m:846-848
+    for (int b = 0; b < batch; ++b) d.nVar[b] = nv[b];
     d.K = p->cfg.K; d.L = p->cfg.L; d.R = p->cfg.nRx; d.P = t.P; d.NB = t.NB; d.Pb = t.Pb; d.nBeams = t.nBeams;
-    d.nCand = t.nCand(); d.nRE = nRE; d.scale = t.scale;
-    const int pr = prof_begin(ctx, kProfPmi, st);
+    d.nCand = t.nCand(); d.nRE = (int)p->reK.size(); d.scale = t.scale;
     cudaError_t e;
     switch (p->nLayers) {
         case 1: e = launch_sinr<1>(d, batch, st); break;
@@ -467,20 +647,114 @@ int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, c
         case 7: e = launch_sinr<7>(d, batch, st); break;
         default: e = launch_sinr<8>(d, batch, st); break;
     }
-    ISAC_CUDA_CHECK(ctx, e);
-    const int nCand = d.nCand, nu = p->nLayers;
-    dim3 g2((nCand + 127) / 128, nu * p->nSB, batch);
-    pmi_subband_kernel<<<g2, 128, 0, st>>>(p->d_S, nCand, nu, nRE, p->nSB, p->d_sbStart, p->d_reW, p->d_sub, p->d_total);
-    SelDev sd{};
-    sd.psum = p->d_total; sd.sub = p->d_sub; sd.S = p->d_S; sd.sbStart = p->d_sbStart; sd.cqiStart = p->d_cqiStart;
-    sd.cqiW = p->d_reCqiW; sd.sel = p->d_sel; sd.sinrSel = p->d_sinrSel; sd.sinrWb = p->d_sinrWb;
-    sd.nCand = nCand; sd.nu = nu; sd.nRE = nRE; sd.nSB = p->nSB; sd.nCqiSB = p->nCqiSB;
-    sd.n2 = t.n2; sd.n11 = t.n11; sd.n12 = t.n12; sd.n13 = t.n13;
-    pmi_select_kernel<<<batch, 256, 0, st>>>(sd);
+    ISAC_CUDA_CHECK(p->ctx, e);
+    count_launches(p->ctx, 1);
+    return kOk;
+}
+
+static size_t pair_smem_bytes(const PmiShared* sh, int R) {
+    return sizeof(double2) * ((size_t)R * sh->P + (size_t)R * sh->NB * sh->nBeams + sh->pairs.size() + sh->pal.size());
+}
+
+// (re-)upload the dictionary when ranks were added since the last launch
+static int pair_sync_dict(Ctx* ctx, PmiShared* sh, cudaStream_t st) {
+    if (sh->upPairs == sh->pairs.size() && sh->upPal == sh->pal.size()) return kOk;
+    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    cudaFree(sh->d_pairs);
+    cudaFree(sh->d_pal);
+    sh->d_pairs = nullptr; sh->d_pal = nullptr;
+    int s;
+    if ((s = upload(ctx, &sh->d_pairs, sh->pairs))) return s;
+    if ((s = upload(ctx, &sh->d_pal, sh->pal))) return s;
+    sh->upPairs = sh->pairs.size();
+    sh->upPal = sh->pal.size();
+    return kOk;
+}
+
+int pmi_select_run_multi(PmiPlan* const* plans, int n, const float2* H, const double* nVar, int batch, cudaStream_t st) {
+    if (n < 1 || !plans || !plans[0]) return kErrInvalidArg;
+    Ctx* ctx = plans[0]->ctx;
+    if (batch < 1 || !H || !nVar) {
+        set_error(ctx, "pmi_select_run: invalid argument");
+        return kErrInvalidArg;
+    }
+    if (batch > kMaxPmiBatch) {
+        set_error(ctx, "pmi_select_run: batch exceeds kMaxPmiBatch");
+        return kErrCapacity;
+    }
+    double nv[kMaxPmiBatch];
+    for (int b = 0; b < batch; ++b) {
+        if (!(nVar[b] >= 0.0) || !std::isfinite(nVar[b])) {
+            set_error(ctx, "dlPMISelect: NVAR must be real, nonnegative and finite");
+            return kErrInvalidArg;
+        }
+        nv[b] = nVar[b] < 1e-10 ? 1e-10 : nVar[b];  // dlPMISelect.m:846-848
+    }
+    std::vector<PmiPlan*> live;
+    for (int i = 0; i < n; ++i) {
+        PmiPlan* p = plans[i];
+        if (batch > p->maxBatch) {
+            set_error(ctx, "pmi_select_run: invalid argument");
+            return kErrInvalidArg;
+        }
+        if (!p->reK.empty()) live.push_back(p);  // else everything NaN (dlPMISelect.m:362-379), decided at collect time
+    }
+    if (live.empty()) return kOk;
+    const int pr = prof_begin(ctx, kProfPmi, st);
+    // SINR of every candidate: one fused launch per dictionary, the direct kernel for the rest
+    std::vector<char> done(live.size(), 0);
+    for (size_t i = 0; i < live.size(); ++i) {
+        if (done[i]) continue;
+        PmiPlan* p = live[i];
+        PmiShared* sh = p->sh;
+        const bool pairOk = sh && sh->ok && !p->direct && pair_smem_bytes(sh, p->cfg.nRx) <= 200 * 1024;
+        if (!pairOk) {
+            int s = pmi_direct_launch(p, H, nv, batch, st);
+            if (s) return s;
+            done[i] = 1;
+            continue;
+        }
+        int s = pair_sync_dict(ctx, sh, st);
+        if (s) return s;
+        PairDev d{};
+        d.H = H; d.beams = p->d_beams; d.pairs = sh->d_pairs; d.pal = sh->d_pal; d.reK = p->d_reK; d.reL = p->d_reL;
+        d.K = p->cfg.K; d.L = p->cfg.L; d.R = p->cfg.nRx; d.P = sh->P; d.NB = sh->NB; d.Pb = sh->Pb; d.nBeams = sh->nBeams;
+        d.nRE = (int)p->reK.size(); d.nPairs = (int)sh->pairs.size(); d.nPal = (int)sh->pal.size();
+        for (int b = 0; b < batch; ++b) d.nVar[b] = nv[b];
+        for (size_t j = i; j < live.size(); ++j) {
+            PmiPlan* q = live[j];
+            if (done[j] || q->sh != sh || q->direct || q->reK != p->reK) continue;
+            PairRank& rk = d.rk[d.nRanks++];
+            rk.terms = q->d_terms; rk.valid = q->d_valid; rk.S = q->d_S; rk.nCand = q->tab.nCand(); rk.nu = q->nLayers; rk.T = q->termT;
+            done[j] = 1;
+        }
+        const size_t smem = pair_smem_bytes(sh, d.R);
+        cudaFuncSetAttribute(pmi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dim3 grid(d.nRE, batch);
+        pmi_pair_kernel<<<grid, 128, smem, st>>>(d);
+        ISAC_CUDA_CHECK(ctx, cudaGetLastError());
+        count_launches(ctx, 1);
+    }
+    for (PmiPlan* p : live) {
+        const CodebookTable& t = p->tab;
+        const int nCand = t.nCand(), nu = p->nLayers, nRE = (int)p->reK.size();
+        dim3 g2((nCand + 127) / 128, nu * p->nSB, batch);
+        pmi_subband_kernel<<<g2, 128, 0, st>>>(p->d_S, nCand, nu, nRE, p->nSB, p->d_sbStart, p->d_reW, p->d_sub, p->d_total);
+        SelDev sd{};
+        sd.psum = p->d_total; sd.sub = p->d_sub; sd.S = p->d_S; sd.sbStart = p->d_sbStart; sd.cqiStart = p->d_cqiStart;
+        sd.cqiW = p->d_reCqiW; sd.sel = p->d_sel; sd.sinrSel = p->d_sinrSel; sd.sinrWb = p->d_sinrWb;
+        sd.nCand = nCand; sd.nu = nu; sd.nRE = nRE; sd.nSB = p->nSB; sd.nCqiSB = p->nCqiSB;
+        sd.n2 = t.n2; sd.n11 = t.n11; sd.n12 = t.n12; sd.n13 = t.n13;
+        pmi_select_kernel<<<batch, 256, 0, st>>>(sd);
+        count_launches(ctx, 2);
+    }
     prof_end(ctx, pr, st);
-    count_launches(ctx, 3);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     return kOk;
+}
+
+int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, cudaStream_t st) {
+    return pmi_select_run_multi(&p, 1, H, nVar, batch, st);
 }
 
 static bool plan_all_nan(const PmiPlan* p) {

@@ -1,9 +1,28 @@
 // K8-K10, K12: Type-I PMI / RI / CQI selection, UL TPMI selection, PRG precoding.
 #pragma once
 #include "codebook.cuh"
+#include <map>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 namespace isac {
+
+// Dictionary of the beam-response inner products ("Gram pairs") the candidates of one report configuration need, shared
+// by all ranks whose codebooks are built from the same beams (K9', comm.cu).  Host side; uploaded lazily.
+struct PmiShared {
+    int NB = 0, Pb = 0, nBeams = 0, P = 0;
+    std::vector<double2> beams;                         // storage order [nBeams][Pb]
+    std::vector<uint32_t> pairs;                        // atom a | atom a' << 16 ; Gamma = <Bf[a], Bf[a']>
+    std::unordered_map<uint32_t, int> pairIdx;
+    std::vector<double2> pal;                           // palette of coefficient products conj(c_i) c_j * scale^2; pal[0] = 0
+    std::map<std::pair<long long, long long>, int> palIdx;
+    uint32_t* d_pairs = nullptr;
+    double2* d_pal = nullptr;
+    size_t upPairs = 0, upPal = 0;                      // sizes of the device copies
+    int refs = 0;
+    bool ok = true;                                     // false: dictionary outgrew 16-bit indices / shared memory
+};
 
 // results of one dlPMISelect evaluation for one UE (host side)
 struct PmiResult {
@@ -44,15 +63,21 @@ struct PmiPlan {
     int* d_sbStart = nullptr;       // [nSB+1] RE ranges of the PMI subbands (REs sorted by subcarrier)
     int* d_cqiStart = nullptr;      // [nCqiSB+1]
     double* d_nVar = nullptr;       // [batch] (unused: nVar travels as a kernel parameter)
+    PmiShared* sh = nullptr;        // Gram-pair dictionary (shared between the ranks of a CSI plan)
+    uint32_t* d_terms = nullptr;    // [NT][termT][nCand]: pair index | palette index << 16
+    int termT = 0;
+    bool direct = false;            // force the direct (H*W) kernel
     void* pin = nullptr;            // pinned staging of the selection results
     size_t pinBytes = 0;
     std::vector<uint8_t> sbHasRE, cqiSbHasRE;
 };
 
-int pmi_plan_create(Ctx* ctx, const CsiConfig& cfg, int nLayers, int maxBatch, PmiPlan** out);
+int pmi_plan_create(Ctx* ctx, const CsiConfig& cfg, int nLayers, int maxBatch, PmiPlan** out, PmiShared* share = nullptr);
 void pmi_plan_destroy(PmiPlan* p);
 // H: device complex64 [K x L x nRx x P x batch]; nVar: host [batch]
 int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, cudaStream_t st);
+// several ranks of one report configuration: one fused SINR launch for the plans that share a dictionary
+int pmi_select_run_multi(PmiPlan* const* plans, int n, const float2* H, const double* nVar, int batch, cudaStream_t st);
 int pmi_select_collect(PmiPlan* p, int batch, std::vector<PmiResult>& out);   // synchronises
 // split form: enqueue the D2H copies for several plans, synchronise once, then parse
 int pmi_select_collect_enqueue(PmiPlan* p, int batch, cudaStream_t st);

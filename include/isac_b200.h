@@ -227,6 +227,10 @@ typedef struct isac_pmi_plan isac_pmi_plan;
 /* [PMISet,info] = communication.phyLayer.dlPMISelect(carrier,csirs,reportConfig,nLayers,H,nVar) (dlPMISelect.m:1) */
 int isac_pmi_plan_create(isac_ctx* ctx, const isac_csi_config* cfg, int32_t nLayers, int32_t maxBatch, isac_pmi_plan** plan);
 int isac_pmi_plan_destroy(isac_pmi_plan* plan);
+/* SINR kernel of the plan: 0 (default) = Gram-pair form (beam-response inner products shared by all candidates),
+ * 1 = direct form (H*W per candidate).  Same results to rounding; the direct form is the fallback for codebooks whose
+ * pair dictionary does not fit in shared memory. */
+int isac_pmi_plan_set_kernel(isac_pmi_plan* plan, int32_t direct);
 /* dims = [i2 i11 i12 i13]; REs sorted by subcarrier as the plan stores them (reKs/reLs may be NULL) */
 int isac_pmi_plan_info(const isac_pmi_plan* plan, int32_t dims[4], int32_t* nSB, int32_t* nCqiSB, int32_t* nRE,
                        int32_t* reKs, int32_t* reLs);
@@ -243,6 +247,7 @@ typedef struct isac_csi_plan isac_csi_plan;
 /* One plan per report configuration: holds the per-rank PMI plans (riSelect.m:254 loops over the valid ranks). */
 int isac_csi_plan_create(isac_ctx* ctx, const isac_csi_config* cfg, int32_t maxBatch, isac_csi_plan** plan);
 int isac_csi_plan_destroy(isac_csi_plan* plan);
+int isac_csi_plan_set_kernel(isac_csi_plan* plan, int32_t direct);   /* as isac_pmi_plan_set_kernel, all ranks */
 /* [RI,PMISet] = communication.phyLayer.riSelect(carrier,csirs,reportConfig,H,nVar) (riSelect.m:1).
  * RI [batch] (NaN when nothing is reportable), i1 [3 x batch], i2 [nSB x batch]. */
 int isac_ri_select_dev(isac_csi_plan* plan, const void* H, const double* nVar, int32_t batch, double* RI, double* i1,

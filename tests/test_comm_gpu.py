@@ -16,9 +16,13 @@ PKG = "5g_based_system_level_integrated_sensing_and_communication_simulator_b200
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def PH(gpu):
-    return importlib.import_module(PKG + ".communication.phyLayer")
+@pytest.fixture(scope="module", params=["pair", "direct"])
+def PH(gpu, request):
+    """Every test runs with both SINR kernels: the Gram-pair form (default) and the direct H*W form (fallback)."""
+    ph = importlib.import_module(PKG + ".communication.phyLayer")
+    ph.setSinrKernel(request.param == "direct")
+    yield ph
+    ph.setSinrKernel(False)
 
 
 def _setup(n_ports, panel, nrb, n_rx, seed, mode=1, pmi_mode="Subband", cqi_mode="Subband", sb=4, nstart=0, snr_db=10.0):
