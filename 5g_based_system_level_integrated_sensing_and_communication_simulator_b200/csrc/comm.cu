@@ -51,7 +51,7 @@ __device__ __forceinline__ void chol_sinr(double2 (&A)[NU * (NU + 1) / 2], doubl
         double d = A[TRI(j, j)].x;
 #pragma unroll
         for (int k = 0; k < NU; ++k)
-            if (k < j) d -= A[TRI(j, k)].x * A[TRI(j, k)].x + A[TRI(j, k)].y * A[TRI(j, k)].y;
+            if (k < j) d = fma(-A[TRI(j, k)].x, A[TRI(j, k)].x, fma(-A[TRI(j, k)].y, A[TRI(j, k)].y, d));
         // store 1/L_jj on the diagonal (one rsqrt + one Newton step instead of sqrt and two divisions)
         double inv = rsqrt(d);
         inv = inv * (1.5 - 0.5 * d * inv * inv);
@@ -62,7 +62,7 @@ __device__ __forceinline__ void chol_sinr(double2 (&A)[NU * (NU + 1) / 2], doubl
                 double2 s = A[TRI(i, j)];
 #pragma unroll
                 for (int k = 0; k < NU; ++k)
-                    if (k < j) s = zsub(s, zmulc(A[TRI(i, k)], A[TRI(j, k)]));
+                    if (k < j) s = zfmsc(s, A[TRI(i, k)], A[TRI(j, k)]);
                 A[TRI(i, j)] = make_double2(s.x * inv, s.y * inv);
             }
         }
@@ -78,10 +78,10 @@ __device__ __forceinline__ void chol_sinr(double2 (&A)[NU * (NU + 1) / 2], doubl
                 double2 s = make_double2(0.0, 0.0);
 #pragma unroll
                 for (int k = 0; k < NU; ++k)
-                    if (k >= cc && k < i) s = zadd(s, zmul(A[TRI(i, k)], x[k]));
+                    if (k >= cc && k < i) s = zfma(s, A[TRI(i, k)], x[k]);
                 const double inv = -A[TRI(i, i)].x;
                 x[i] = make_double2(s.x * inv, s.y * inv);
-                nrm += x[i].x * x[i].x + x[i].y * x[i].y;
+                nrm = fma(x[i].x, x[i].x, fma(x[i].y, x[i].y, nrm));
             }
         }
         out[(long long)cc * stride] = 1.0 / (nVar * nrm) - 1.0;
@@ -110,7 +110,7 @@ pmi_sinr_kernel(const PmiDev p) {
     for (int i = threadIdx.x; i < nB; i += blockDim.x) {
         const int bm = i % p.nBeams, blk = (i / p.nBeams) % p.NB, r = i / (p.nBeams * p.NB);
         double2 acc = make_double2(0.0, 0.0);
-        for (int q = 0; q < p.Pb; ++q) acc = zadd(acc, zmul(Hs[r * P + blk * p.Pb + q], p.beams[bm * p.Pb + q]));
+        for (int q = 0; q < p.Pb; ++q) acc = zfma(acc, Hs[r * P + blk * p.Pb + q], p.beams[bm * p.Pb + q]);
         Bf[i] = acc;
     }
     __syncthreads();
@@ -141,51 +141,58 @@ pmi_sinr_kernel(const PmiDev p) {
             for (int j = 0; j < NU; ++j) {
                 const double2* __restrict__ Br = Bf + (size_t)r * p.NB * p.nBeams + beamOf[j];
                 double2 acc = zmul(cf[j][0], Br[0]);
-                if (p.NB > 1) acc = zadd(acc, zmul(cf[j][1], Br[p.nBeams]));
+                if (p.NB > 1) acc = zfma(acc, cf[j][1], Br[p.nBeams]);
                 for (int blk = 2; blk < p.NB; ++blk)
-                    acc = zadd(acc, zmul(p.layerCoef[(c * NU + j) * p.NB + blk], Br[blk * p.nBeams]));
+                    acc = zfma(acc, p.layerCoef[(c * NU + j) * p.NB + blk], Br[blk * p.nBeams]);
                 g[j] = make_double2(acc.x * sc, acc.y * sc);
             }
 #pragma unroll
             for (int i = 0; i < NU; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j) A[TRI(i, j)] = zadd(A[TRI(i, j)], zmulc(g[j], g[i]));  // conj(g_i) g_j
+                for (int j = 0; j <= i; ++j) A[TRI(i, j)] = zfmac(A[TRI(i, j)], g[j], g[i]);  // conj(g_i) g_j
         }
         chol_sinr<NU>(A, nVar, Sout + c, p.nCand);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// K9': Gram-pair form.  Every precoder column is sum_blk c_blk (e_blk (x) v_beam), so every entry of (HW)'(HW) is a
-// short sum of inner products Gamma[a,a'] = <Bf[a], Bf[a']> of beam responses ("atoms" a = (blk, beam)) times a
-// coefficient product conj(c_i,blk) c_j,blk' (a 4th/8th root of unity times the codebook scale^2).  The host lists the
-// distinct (a,a') pairs all candidates of ALL ranks need (576 for the 8-port (2,2) panel against 1920 candidates) and the
-// distinct coefficient products (the palette); one CTA per (RE, UE) then computes Bf, the pair table Gamma and walks the
-// candidates of every rank: A_ij = sum_t pal[q_t] Gamma[p_t] (2..4 complex MACs instead of R + 2 NB), Cholesky, SINR.
+// K9': Gram-pair form.  Every precoder column is g = sum_blk c_blk (e_blk (x) v_beam): a (beam, co-phasing) pair, of
+// which a Type-I codebook has only a few hundred distinct ones ("columns") however many candidates and ranks it spans.
+// The entries of (HW)'(HW) are inner products <H g_i, H g_j> of those columns, shared massively between candidates
+// (2.2 k distinct column pairs against 1920 candidates x up to 36 entries for the 8-port (2,2) panel, ranks 1-8).
+// One CTA per (RE, UE):
+//   1. beam responses      Bf[a]   = H[:, blk] v_beam            (atoms a = (blk, beam))
+//   2. atom Gram pairs     Gam[p]  = <Bf[a], Bf[a']>             (the distinct pairs the column pairs need)
+//   3. column-pair table   G[q]    = sum_t pal[.] Gam[.]         (NB^2 terms: conj(c_i,blk) c_j,blk' products)
+//   4. per rank, per candidate: A_ij = G[ent_ij] (a table look-up), Cholesky of A + (nVar/scale^2) I, SINR.
+// The codebook scale is folded into the noise term: sinr = 1/(nVar' [(A' + nVar' I)^-1]_ll) - 1 with A' = A/scale^2,
+// nVar' = nVar/scale^2, so the table is shared by all ranks.
 // ------------------------------------------------------------------------------------------
 struct PairRank {
-    const uint32_t* terms;   // [NT][T][nCand]
+    const uint16_t* ent;     // [nCand][ntPad]: column-pair index of each packed lower-triangle entry
     const uint8_t* valid;
+    const double* invScale2; // per candidate 1/scale^2 (explicit codebooks) or nullptr
     double* S;
-    int nCand, nu, T;
+    double invS2;            // 1/scale^2 of the rank
+    int nCand, nu, ntPad;
 };
 struct PairDev {
     const float2* H;
     const double2* beams;
-    const uint32_t* pairs;
-    const double2* pal;
+    const uint32_t* pairs;     // [nPairs] atom a | atom a' << 16
+    const double2* pal;        // [nPal]
+    const uint32_t* cpTerms;   // [cpT][nCP]: pair index | palette index << 16
     const int* reK;
     const int* reL;
-    int K, L, R, P, NB, Pb, nBeams, nRE, nPairs, nPal, nRanks;
+    int K, L, R, P, NB, Pb, nBeams, nRE, nPairs, nPal, nCP, cpT, nRanks;
     PairRank rk[kMaxLayers];
     double nVar[kMaxPmiBatch];
 };
 
 template <int NU>
-__device__ __noinline__ void pair_rank_eval(const PairRank rk, const double2* __restrict__ Gm, const double2* __restrict__ pal,
-                                               double nVar, double* __restrict__ Sout) {
+__device__ __noinline__ void pair_rank_eval(const PairRank rk, const double2* __restrict__ G, double nVar, double* __restrict__ Sout) {
     constexpr int NT = NU * (NU + 1) / 2;
-    const int T = rk.T;
+    constexpr int NW = (NT + 7) / 8;   // 16-byte words of indices per candidate
     for (int c = threadIdx.x; c < rk.nCand; c += blockDim.x) {
         if (!rk.valid[c]) {
 #pragma unroll
@@ -193,20 +200,19 @@ __device__ __noinline__ void pair_rank_eval(const PairRank rk, const double2* __
             continue;
         }
         double2 A[NT];
-        const uint32_t* __restrict__ tp = rk.terms + c;
+        const uint4* __restrict__ ep = reinterpret_cast<const uint4*>(rk.ent + (size_t)c * rk.ntPad);
 #pragma unroll
-        for (int e = 0; e < NT; ++e) {
-            double2 acc = make_double2(0.0, 0.0);
-            for (int t = 0; t < T; t += 4) {   // T is a multiple of 4 (absent terms: pair 0 x palette 0 = 0)
+        for (int w = 0; w < NW; ++w) {
+            const uint4 v = __ldg(ep + w);
+            const uint32_t q[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t w = __ldg(tp + (size_t)(e * T + t + u) * rk.nCand);
-                    acc = zadd(acc, zmul(Gm[w & 0xffffu], pal[w >> 16]));
-                }
+            for (int u = 0; u < 8; ++u) {
+                const int e = w * 8 + u;
+                if (e < NT) A[e] = G[(q[u >> 1] >> ((u & 1) * 16)) & 0xffffu];
             }
-            A[e] = acc;
         }
-        chol_sinr<NU>(A, nVar, Sout + c, rk.nCand);
+        const double nv = nVar * (rk.invScale2 ? rk.invScale2[c] : rk.invS2);
+        chol_sinr<NU>(A, nv, Sout + c, rk.nCand);
     }
 }
 
@@ -215,9 +221,10 @@ pmi_pair_kernel(const __grid_constant__ PairDev p) {
     extern __shared__ double2 sm[];
     const int R = p.R, P = p.P, nAtoms = p.NB * p.nBeams;
     double2* Hs = sm;                       // [R][P]
-    double2* Bf = Hs + R * P;               // [R][NB][nBeams]
-    double2* Gm = Bf + (size_t)R * nAtoms;  // [nPairs]
-    double2* pal = Gm + p.nPairs;           // [nPal]
+    double2* pal = Hs + R * P;              // [nPal]
+    double2* Gm = pal + p.nPal;             // [nPairs]
+    double2* Bf = Gm + p.nPairs;            // [R][NB][nBeams]; dead after step 2, the column-pair table G reuses it
+    double2* G = Bf;                        // [nCP]
     const int e = blockIdx.x, b = blockIdx.y;
     const long long kk = p.reK[e] - 1, ll = p.reL[e] - 1;
     const float2* __restrict__ Hb = p.H + (long long)b * p.K * p.L * R * P;
@@ -231,7 +238,7 @@ pmi_pair_kernel(const __grid_constant__ PairDev p) {
     for (int i = threadIdx.x; i < R * nAtoms; i += blockDim.x) {
         const int bm = i % p.nBeams, blk = (i / p.nBeams) % p.NB, r = i / nAtoms;
         double2 acc = make_double2(0.0, 0.0);
-        for (int q = 0; q < p.Pb; ++q) acc = zadd(acc, zmul(Hs[r * P + blk * p.Pb + q], p.beams[bm * p.Pb + q]));
+        for (int q = 0; q < p.Pb; ++q) acc = zfma(acc, Hs[r * P + blk * p.Pb + q], p.beams[bm * p.Pb + q]);
         Bf[i] = acc;
     }
     __syncthreads();
@@ -239,8 +246,17 @@ pmi_pair_kernel(const __grid_constant__ PairDev p) {
         const uint32_t w = __ldg(p.pairs + i);
         const int a = w & 0xffffu, a2 = w >> 16;
         double2 acc = make_double2(0.0, 0.0);
-        for (int r = 0; r < R; ++r) acc = zadd(acc, zmulc(Bf[r * nAtoms + a2], Bf[r * nAtoms + a]));  // conj(Bf[a]) Bf[a']
+        for (int r = 0; r < R; ++r) acc = zfmac(acc, Bf[r * nAtoms + a2], Bf[r * nAtoms + a]);  // conj(Bf[a]) Bf[a']
         Gm[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.nCP; i += blockDim.x) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int t = 0; t < p.cpT; ++t) {
+            const uint32_t w = __ldg(p.cpTerms + (size_t)t * p.nCP + i);
+            acc = zfma(acc, Gm[w & 0xffffu], pal[w >> 16]);
+        }
+        G[i] = acc;
     }
     __syncthreads();
     const double nVar = p.nVar[b];
@@ -250,14 +266,14 @@ pmi_pair_kernel(const __grid_constant__ PairDev p) {
         const PairRank rk = p.rk[q];
         double* __restrict__ Sout = rk.S + ((long long)b * p.nRE + e) * rk.nu * (long long)rk.nCand;
         switch (rk.nu) {
-            case 1: pair_rank_eval<1>(rk, Gm, pal, nVar, Sout); break;
-            case 2: pair_rank_eval<2>(rk, Gm, pal, nVar, Sout); break;
-            case 3: pair_rank_eval<3>(rk, Gm, pal, nVar, Sout); break;
-            case 4: pair_rank_eval<4>(rk, Gm, pal, nVar, Sout); break;
-            case 5: pair_rank_eval<5>(rk, Gm, pal, nVar, Sout); break;
-            case 6: pair_rank_eval<6>(rk, Gm, pal, nVar, Sout); break;
-            case 7: pair_rank_eval<7>(rk, Gm, pal, nVar, Sout); break;
-            default: pair_rank_eval<8>(rk, Gm, pal, nVar, Sout); break;
+            case 1: pair_rank_eval<1>(rk, G, nVar, Sout); break;
+            case 2: pair_rank_eval<2>(rk, G, nVar, Sout); break;
+            case 3: pair_rank_eval<3>(rk, G, nVar, Sout); break;
+            case 4: pair_rank_eval<4>(rk, G, nVar, Sout); break;
+            case 5: pair_rank_eval<5>(rk, G, nVar, Sout); break;
+            case 6: pair_rank_eval<6>(rk, G, nVar, Sout); break;
+            case 7: pair_rank_eval<7>(rk, G, nVar, Sout); break;
+            default: pair_rank_eval<8>(rk, G, nVar, Sout); break;
         }
     }
 }
@@ -495,11 +511,11 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
             lb[(size_t)c * nu + j] = store_idx(d.beam);
             for (int b = 0; b < t.NB; ++b) coef[((size_t)c * nu + j) * t.NB + b] = make_double2(d.coef[b].real(), d.coef[b].imag());
         }
-    // Gram-pair terms (K9'): register this rank's pairs / coefficient products in the (shared) dictionary
+    // Gram-pair form (K9'): register this rank's columns / column pairs in the (shared) dictionary
     {
         PmiShared* sh = share;
         auto compatible = [&](const PmiShared* q) {
-            if (q->pairs.empty() && q->beams.empty()) return true;
+            if (q->beams.empty()) return true;
             if (q->NB != t.NB || q->Pb != t.Pb || q->nBeams != t.nBeams || q->P != t.P || q->beams.size() != beams.size()) return false;
             for (size_t i = 0; i < beams.size(); ++i)
                 if (q->beams[i].x != beams[i].x || q->beams[i].y != beams[i].y) return false;
@@ -509,59 +525,81 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
         if (sh->beams.empty()) {
             sh->NB = t.NB; sh->Pb = t.Pb; sh->nBeams = t.nBeams; sh->P = t.P;
             sh->beams = beams;
-            sh->pal.push_back(make_double2(0.0, 0.0));
+            sh->pal.push_back(make_double2(0.0, 0.0));   // palette 0 = 0, pair 0 = (0,0): the "absent term"
             sh->pairs.push_back(0u);
             sh->pairIdx[0u] = 0;
+            sh->cpT = (t.NB * t.NB + 3) / 4 * 4;
         }
         ++sh->refs;
         p->sh = sh;
-        const int NT = nu * (nu + 1) / 2;
-        std::vector<std::vector<uint32_t>> cand((size_t)nCand * NT);
-        int T = 1;
+        auto qkey = [](std::complex<double> q) {
+            return std::pair<long long, long long>(std::llround(q.real() * 1099511627776.0), std::llround(q.imag() * 1099511627776.0));
+        };
+        auto column_of = [&](const LayerDesc& d) {   // distinct (beam, co-phasing coefficients)
+            std::vector<long long> key{(long long)store_idx(d.beam)};
+            for (int b = 0; b < t.NB; ++b) { auto k = qkey(d.coef[b]); key.push_back(k.first); key.push_back(k.second); }
+            auto it = sh->colIdx.find(key);
+            if (it != sh->colIdx.end()) return it->second;
+            const int id = (int)sh->cols.size();
+            PmiShared::Column col;
+            col.beam = store_idx(d.beam);
+            for (int b = 0; b < t.NB; ++b) col.coef[b] = d.coef[b];
+            sh->cols.push_back(col);
+            sh->colIdx[key] = id;
+            return id;
+        };
+        auto colpair_of = [&](int ci, int cj) {      // G = <g_ci, g_cj> = sum conj(c_i,blk) c_j,blk' Gamma[(blk,b_i),(blk',b_j)]
+            const unsigned long long key = ((unsigned long long)ci << 32) | (unsigned)cj;
+            auto it = sh->cpIdx.find(key);
+            if (it != sh->cpIdx.end()) return it->second;
+            const int id = (int)sh->cpTerms.size() / sh->cpT;
+            const PmiShared::Column &a = sh->cols[ci], &bcol = sh->cols[cj];
+            std::vector<uint32_t> v;
+            for (int bi = 0; bi < t.NB; ++bi)
+                for (int bj = 0; bj < t.NB; ++bj) {
+                    const std::complex<double> q = std::conj(a.coef[bi]) * bcol.coef[bj];
+                    if (std::abs(q) < 1e-300) continue;
+                    const uint32_t a1 = (uint32_t)(bi * t.nBeams + a.beam), a2 = (uint32_t)(bj * t.nBeams + bcol.beam);
+                    const uint32_t pk = a1 | (a2 << 16);
+                    auto pit = sh->pairIdx.find(pk);
+                    int pi;
+                    if (pit == sh->pairIdx.end()) {
+                        pi = (int)sh->pairs.size();
+                        sh->pairs.push_back(pk);
+                        sh->pairIdx[pk] = pi;
+                    } else pi = pit->second;
+                    auto qit = sh->palIdx.find(qkey(q));
+                    int qi;
+                    if (qit == sh->palIdx.end()) {
+                        qi = (int)sh->pal.size();
+                        sh->pal.push_back(make_double2(q.real(), q.imag()));
+                        sh->palIdx[qkey(q)] = qi;
+                    } else qi = qit->second;
+                    if (pi > 0xffff || qi > 0xffff) { sh->ok = false; pi = qi = 0; }
+                    v.push_back((uint32_t)pi | ((uint32_t)qi << 16));
+                }
+            v.resize(sh->cpT, 0u);
+            sh->cpTerms.insert(sh->cpTerms.end(), v.begin(), v.end());
+            sh->cpIdx[key] = id;
+            if (id > 0xffff || t.NB * t.nBeams > 0xffff) sh->ok = false;
+            return id;
+        };
+        const int NT = nu * (nu + 1) / 2, ntPad = (NT + 7) / 8 * 8;
+        p->ntPad = ntPad;
+        std::vector<uint16_t> ent((size_t)nCand * ntPad, 0);
+        std::vector<double> is2;
+        if (!t.candScale.empty()) is2.assign(nCand, 1.0);
+        p->invS2 = 1.0 / (t.scale * t.scale);
         for (int c = 0; c < nCand; ++c) {
             if (!t.valid[c]) continue;
-            const double sc = t.candScale.empty() ? t.scale : t.candScale[c];
+            if (!t.candScale.empty()) is2[c] = 1.0 / (t.candScale[c] * t.candScale[c]);
+            int colId[kMaxLayers];
+            for (int i = 0; i < nu; ++i) colId[i] = column_of(t.layers[(size_t)c * nu + i]);
             for (int i = 0; i < nu; ++i)
-                for (int j = 0; j <= i; ++j) {
-                    const LayerDesc& di = t.layers[(size_t)c * nu + i];
-                    const LayerDesc& dj = t.layers[(size_t)c * nu + j];
-                    std::vector<uint32_t>& v = cand[(size_t)c * NT + i * (i + 1) / 2 + j];
-                    for (int bi = 0; bi < t.NB; ++bi)
-                        for (int bj = 0; bj < t.NB; ++bj) {
-                            const std::complex<double> q = std::conj(di.coef[bi]) * dj.coef[bj] * (sc * sc);
-                            if (std::abs(q) < 1e-300) continue;
-                            const uint32_t a = (uint32_t)(bi * t.nBeams + store_idx(di.beam)), a2 = (uint32_t)(bj * t.nBeams + store_idx(dj.beam));
-                            const uint32_t key = a | (a2 << 16);
-                            auto pit = sh->pairIdx.find(key);
-                            int pi;
-                            if (pit == sh->pairIdx.end()) {
-                                pi = (int)sh->pairs.size();
-                                sh->pairs.push_back(key);
-                                sh->pairIdx[key] = pi;
-                            } else pi = pit->second;
-                            const std::pair<long long, long long> pk(std::llround(q.real() * 1099511627776.0), std::llround(q.imag() * 1099511627776.0));
-                            auto qit = sh->palIdx.find(pk);
-                            int qi;
-                            if (qit == sh->palIdx.end()) {
-                                qi = (int)sh->pal.size();
-                                sh->pal.push_back(make_double2(q.real(), q.imag()));
-                                sh->palIdx[pk] = qi;
-                            } else qi = qit->second;
-                            if (pi > 0xffff || qi > 0xffff || t.NB * t.nBeams > 0xffff) { sh->ok = false; pi = qi = 0; }
-                            v.push_back((uint32_t)pi | ((uint32_t)qi << 16));
-                        }
-                    T = std::max(T, (int)v.size());
-                }
+                for (int j = 0; j <= i; ++j)
+                    ent[(size_t)c * ntPad + i * (i + 1) / 2 + j] = (uint16_t)(colpair_of(colId[i], colId[j]) & 0xffff);
         }
-        T = (T + 3) / 4 * 4;
-        p->termT = T;
-        std::vector<uint32_t> terms((size_t)NT * T * nCand, 0u);  // absent term: pair 0 x palette 0 (= 0)
-        for (int c = 0; c < nCand; ++c)
-            for (int e = 0; e < NT; ++e) {
-                const std::vector<uint32_t>& v = cand[(size_t)c * NT + e];
-                for (size_t q = 0; q < v.size(); ++q) terms[((size_t)e * T + q) * nCand + c] = v[q];
-            }
-        if ((s = upload(ctx, &p->d_terms, terms))) {
+        if ((s = upload(ctx, &p->d_ent, ent)) || (!is2.empty() && (s = upload(ctx, &p->d_invScale2, is2)))) {
             pmi_plan_destroy(p);
             return s;
         }
@@ -609,10 +647,11 @@ void pmi_plan_destroy(PmiPlan* p) {
     cudaFree(p->d_beams); cudaFree(p->d_layerBeam); cudaFree(p->d_layerCoef); cudaFree(p->d_candScale);
     cudaFree(p->d_valid); cudaFree(p->d_reK); cudaFree(p->d_reL); cudaFree(p->d_reSb); cudaFree(p->d_reW);
     cudaFree(p->d_reCqiSb); cudaFree(p->d_reCqiW); cudaFree(p->d_S); cudaFree(p->d_total); cudaFree(p->d_sub);
-    cudaFree(p->d_sel); cudaFree(p->d_sinrSel); cudaFree(p->d_sinrWb); cudaFree(p->d_terms);
+    cudaFree(p->d_sel); cudaFree(p->d_sinrSel); cudaFree(p->d_sinrWb); cudaFree(p->d_ent); cudaFree(p->d_invScale2);
     if (p->sh && --p->sh->refs == 0) {
         cudaFree(p->sh->d_pairs);
         cudaFree(p->sh->d_pal);
+        cudaFree(p->sh->d_cpTerms);
         delete p->sh;
     }
     delete p;
@@ -653,21 +692,29 @@ static int pmi_direct_launch(PmiPlan* p, const float2* H, const double* nv, int 
 }
 
 static size_t pair_smem_bytes(const PmiShared* sh, int R) {
-    return sizeof(double2) * ((size_t)R * sh->P + (size_t)R * sh->NB * sh->nBeams + sh->pairs.size() + sh->pal.size());
+    const size_t nCP = sh->cpTerms.size() / (sh->cpT ? sh->cpT : 1), nBf = (size_t)R * sh->NB * sh->nBeams;
+    return sizeof(double2) * ((size_t)R * sh->P + sh->pal.size() + sh->pairs.size() + (nCP > nBf ? nCP : nBf));
 }
 
 // (re-)upload the dictionary when ranks were added since the last launch
 static int pair_sync_dict(Ctx* ctx, PmiShared* sh, cudaStream_t st) {
-    if (sh->upPairs == sh->pairs.size() && sh->upPal == sh->pal.size()) return kOk;
+    if (sh->upPairs == sh->pairs.size() && sh->upPal == sh->pal.size() && sh->upCp == sh->cpTerms.size()) return kOk;
     ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
     cudaFree(sh->d_pairs);
     cudaFree(sh->d_pal);
-    sh->d_pairs = nullptr; sh->d_pal = nullptr;
+    cudaFree(sh->d_cpTerms);
+    sh->d_pairs = nullptr; sh->d_pal = nullptr; sh->d_cpTerms = nullptr;
+    const size_t nCP = sh->cpTerms.size() / sh->cpT;
+    std::vector<uint32_t> tt(sh->cpTerms.size());   // [cpT][nCP]: coalesced over the column pairs
+    for (size_t q = 0; q < nCP; ++q)
+        for (int t = 0; t < sh->cpT; ++t) tt[(size_t)t * nCP + q] = sh->cpTerms[q * sh->cpT + t];
     int s;
     if ((s = upload(ctx, &sh->d_pairs, sh->pairs))) return s;
     if ((s = upload(ctx, &sh->d_pal, sh->pal))) return s;
+    if ((s = upload(ctx, &sh->d_cpTerms, tt))) return s;
     sh->upPairs = sh->pairs.size();
     sh->upPal = sh->pal.size();
+    sh->upCp = sh->cpTerms.size();
     return kOk;
 }
 
@@ -720,12 +767,14 @@ int pmi_select_run_multi(PmiPlan* const* plans, int n, const float2* H, const do
         d.H = H; d.beams = p->d_beams; d.pairs = sh->d_pairs; d.pal = sh->d_pal; d.reK = p->d_reK; d.reL = p->d_reL;
         d.K = p->cfg.K; d.L = p->cfg.L; d.R = p->cfg.nRx; d.P = sh->P; d.NB = sh->NB; d.Pb = sh->Pb; d.nBeams = sh->nBeams;
         d.nRE = (int)p->reK.size(); d.nPairs = (int)sh->pairs.size(); d.nPal = (int)sh->pal.size();
+        d.cpTerms = sh->d_cpTerms; d.cpT = sh->cpT; d.nCP = (int)(sh->cpTerms.size() / sh->cpT);
         for (int b = 0; b < batch; ++b) d.nVar[b] = nv[b];
         for (size_t j = i; j < live.size(); ++j) {
             PmiPlan* q = live[j];
             if (done[j] || q->sh != sh || q->direct || q->reK != p->reK) continue;
             PairRank& rk = d.rk[d.nRanks++];
-            rk.terms = q->d_terms; rk.valid = q->d_valid; rk.S = q->d_S; rk.nCand = q->tab.nCand(); rk.nu = q->nLayers; rk.T = q->termT;
+            rk.ent = q->d_ent; rk.valid = q->d_valid; rk.invScale2 = q->d_invScale2; rk.S = q->d_S; rk.invS2 = q->invS2;
+            rk.nCand = q->tab.nCand(); rk.nu = q->nLayers; rk.ntPad = q->ntPad;
             done[j] = 1;
         }
         const size_t smem = pair_smem_bytes(sh, d.R);
@@ -1011,7 +1060,7 @@ ul_sinr_kernel(const float2* __restrict__ hestAll, int K, int nSym, int R, int P
                     for (int k = cc; k < i; ++k) s = zadd(s, zmul(A[i][k], x[k]));
                     const double inv = -1.0 / A[i][i].x;
                     x[i] = make_double2(s.x * inv, s.y * inv);
-                    nrm += x[i].x * x[i].x + x[i].y * x[i].y;
+                    nrm = fma(x[i].x, x[i].x, fma(x[i].y, x[i].y, nrm));
                 }
                 out += 1.0 / (nVar * nrm) - 1.0;  // sum over layers (precodedSINR.m:16)
             }

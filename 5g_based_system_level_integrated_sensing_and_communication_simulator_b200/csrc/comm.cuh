@@ -1,6 +1,7 @@
 // K8-K10, K12: Type-I PMI / RI / CQI selection, UL TPMI selection, PRG precoding.
 #pragma once
 #include "codebook.cuh"
+#include <complex>
 #include <map>
 #include <unordered_map>
 #include <utility>
@@ -11,17 +12,24 @@ namespace isac {
 // Dictionary of the beam-response inner products ("Gram pairs") the candidates of one report configuration need, shared
 // by all ranks whose codebooks are built from the same beams (K9', comm.cu).  Host side; uploaded lazily.
 struct PmiShared {
+    struct Column { int beam; std::complex<double> coef[kMaxBlocks]; };
     int NB = 0, Pb = 0, nBeams = 0, P = 0;
     std::vector<double2> beams;                         // storage order [nBeams][Pb]
+    std::vector<Column> cols;                           // distinct precoder columns (beam, co-phasing)
+    std::map<std::vector<long long>, int> colIdx;
     std::vector<uint32_t> pairs;                        // atom a | atom a' << 16 ; Gamma = <Bf[a], Bf[a']>
     std::unordered_map<uint32_t, int> pairIdx;
-    std::vector<double2> pal;                           // palette of coefficient products conj(c_i) c_j * scale^2; pal[0] = 0
+    std::vector<double2> pal;                           // palette of coefficient products conj(c_i) c_j; pal[0] = 0
     std::map<std::pair<long long, long long>, int> palIdx;
+    int cpT = 4;                                        // terms per column pair (NB^2 rounded up to 4)
+    std::vector<uint32_t> cpTerms;                      // [nCP][cpT]: pair index | palette index << 16
+    std::unordered_map<unsigned long long, int> cpIdx;
     uint32_t* d_pairs = nullptr;
     double2* d_pal = nullptr;
-    size_t upPairs = 0, upPal = 0;                      // sizes of the device copies
+    uint32_t* d_cpTerms = nullptr;
+    size_t upPairs = 0, upPal = 0, upCp = 0;            // sizes of the device copies
     int refs = 0;
-    bool ok = true;                                     // false: dictionary outgrew 16-bit indices / shared memory
+    bool ok = true;                                     // false: dictionary outgrew 16-bit indices
 };
 
 // results of one dlPMISelect evaluation for one UE (host side)
@@ -64,8 +72,10 @@ struct PmiPlan {
     int* d_cqiStart = nullptr;      // [nCqiSB+1]
     double* d_nVar = nullptr;       // [batch] (unused: nVar travels as a kernel parameter)
     PmiShared* sh = nullptr;        // Gram-pair dictionary (shared between the ranks of a CSI plan)
-    uint32_t* d_terms = nullptr;    // [NT][termT][nCand]: pair index | palette index << 16
-    int termT = 0;
+    uint16_t* d_ent = nullptr;      // [nCand][ntPad]: column-pair index of every packed lower-triangle entry
+    double* d_invScale2 = nullptr;  // [nCand] 1/scale^2 (explicit codebooks only)
+    double invS2 = 1.0;             // 1/scale^2 of the rank
+    int ntPad = 0;
     bool direct = false;            // force the direct (H*W) kernel
     void* pin = nullptr;            // pinned staging of the selection results
     size_t pinBytes = 0;

@@ -27,6 +27,19 @@ __host__ __device__ __forceinline__ double2 zmul(double2 a, double2 b) {
 __host__ __device__ __forceinline__ double2 zmulc(double2 a, double2 b) {  // a*conj(b)
     return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
+// fused complex multiply-accumulate forms (4 DFMA each; acc + a*b written with zadd/zmul costs DMUL+DFMA+DADD per part)
+__device__ __forceinline__ double2 zfma(double2 acc, double2 a, double2 b) {    // acc + a*b
+    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, acc.x)), fma(a.x, b.y, fma(a.y, b.x, acc.y)));
+}
+__device__ __forceinline__ double2 zfmac(double2 acc, double2 a, double2 b) {   // acc + a*conj(b)
+    return make_double2(fma(a.x, b.x, fma(a.y, b.y, acc.x)), fma(a.y, b.x, fma(-a.x, b.y, acc.y)));
+}
+__device__ __forceinline__ double2 zfms(double2 acc, double2 a, double2 b) {    // acc - a*b
+    return make_double2(fma(-a.x, b.x, fma(a.y, b.y, acc.x)), fma(-a.x, b.y, fma(-a.y, b.x, acc.y)));
+}
+__device__ __forceinline__ double2 zfmsc(double2 acc, double2 a, double2 b) {   // acc - a*conj(b)
+    return make_double2(fma(-a.x, b.x, fma(-a.y, b.y, acc.x)), fma(-a.y, b.x, fma(a.x, b.y, acc.y)));
+}
 __host__ __device__ __forceinline__ double2 zadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ double2 zsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
