@@ -52,9 +52,8 @@ __device__ __forceinline__ void chol_sinr(double2 (&A)[NU * (NU + 1) / 2], doubl
 #pragma unroll
         for (int k = 0; k < NU; ++k)
             if (k < j) d = fma(-A[TRI(j, k)].x, A[TRI(j, k)].x, fma(-A[TRI(j, k)].y, A[TRI(j, k)].y, d));
-        // store 1/L_jj on the diagonal (one rsqrt + one Newton step instead of sqrt and two divisions)
-        double inv = rsqrt(d);
-        inv = inv * (1.5 - 0.5 * d * inv * inv);
+        // store 1/L_jj on the diagonal (MUFU seed + Newton instead of sqrt and two divisions)
+        const double inv = fast_rsqrt(d);
         A[TRI(j, j)] = make_double2(inv, 0.0);
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
@@ -84,7 +83,7 @@ __device__ __forceinline__ void chol_sinr(double2 (&A)[NU * (NU + 1) / 2], doubl
                 nrm = fma(x[i].x, x[i].x, fma(x[i].y, x[i].y, nrm));
             }
         }
-        out[(long long)cc * stride] = 1.0 / (nVar * nrm) - 1.0;
+        out[(long long)cc * stride] = fast_rcp(nVar * nrm) - 1.0;
     }
 }
 
@@ -194,21 +193,28 @@ __device__ __noinline__ void pair_rank_eval(const PairRank rk, const double2* __
     constexpr int NT = NU * (NU + 1) / 2;
     constexpr int NW = (NT + 7) / 8;   // 16-byte words of indices per candidate
     for (int c = threadIdx.x; c < rk.nCand; c += blockDim.x) {
+        const uint4* __restrict__ ep = reinterpret_cast<const uint4*>(rk.ent + (size_t)c * rk.ntPad);
+        uint4 ev[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) ev[w] = __ldg(ep + w);   // issued together with the validity flag
         if (!rk.valid[c]) {
 #pragma unroll
             for (int j = 0; j < NU; ++j) Sout[(long long)j * rk.nCand + c] = NAN;  // restricted precoder (dlPMISelect.m:418)
             continue;
         }
         double2 A[NT];
-        const uint4* __restrict__ ep = reinterpret_cast<const uint4*>(rk.ent + (size_t)c * rk.ntPad);
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
-            const uint4 v = __ldg(ep + w);
+            const uint4 v = ev[w];
             const uint32_t q[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int e = w * 8 + u;
-                if (e < NT) A[e] = G[(q[u >> 1] >> ((u & 1) * 16)) & 0xffffu];
+                if (e < NT) {   // bit 15: the pair is stored as (j,i) -> conjugate
+                    const uint32_t id = (q[u >> 1] >> ((u & 1) * 16)) & 0xffffu;
+                    const double2 g = G[id & 0x7fffu];
+                    A[e] = make_double2(g.x, (id & 0x8000u) ? -g.y : g.y);
+                }
             }
         }
         const double nv = nVar * (rk.invScale2 ? rk.invScale2[c] : rk.invS2);
@@ -235,26 +241,37 @@ pmi_pair_kernel(const __grid_constant__ PairDev p) {
     }
     for (int i = threadIdx.x; i < p.nPal; i += blockDim.x) pal[i] = p.pal[i];
     __syncthreads();
-    for (int i = threadIdx.x; i < R * nAtoms; i += blockDim.x) {
-        const int bm = i % p.nBeams, blk = (i / p.nBeams) % p.NB, r = i / nAtoms;
-        double2 acc = make_double2(0.0, 0.0);
-        for (int q = 0; q < p.Pb; ++q) acc = zfma(acc, Hs[r * P + blk * p.Pb + q], p.beams[bm * p.Pb + q]);
-        Bf[i] = acc;
-    }
+    for (int blk = 0; blk < p.NB; ++blk)
+        for (int bm = threadIdx.x; bm < p.nBeams; bm += blockDim.x) {
+            const double2* __restrict__ bv = p.beams + (size_t)bm * p.Pb;
+            for (int r = 0; r < R; ++r) {
+                const double2* __restrict__ hr = Hs + r * P + blk * p.Pb;
+                double2 acc = make_double2(0.0, 0.0);
+                for (int q = 0; q < p.Pb; ++q) acc = zfma(acc, hr[q], __ldg(bv + q));
+                Bf[r * nAtoms + blk * p.nBeams + bm] = acc;
+            }
+        }
     __syncthreads();
     for (int i = threadIdx.x; i < p.nPairs; i += blockDim.x) {
         const uint32_t w = __ldg(p.pairs + i);
-        const int a = w & 0xffffu, a2 = w >> 16;
+        const double2* __restrict__ pa = Bf + (w & 0xffffu);
+        const double2* __restrict__ pb = Bf + (w >> 16);
         double2 acc = make_double2(0.0, 0.0);
-        for (int r = 0; r < R; ++r) acc = zfmac(acc, Bf[r * nAtoms + a2], Bf[r * nAtoms + a]);  // conj(Bf[a]) Bf[a']
+        for (int r = 0; r < R; ++r, pa += nAtoms, pb += nAtoms) acc = zfmac(acc, *pb, *pa);  // conj(Bf[a]) Bf[a']
         Gm[i] = acc;
     }
     __syncthreads();
+    const uint4* __restrict__ cpt = reinterpret_cast<const uint4*>(p.cpTerms);
     for (int i = threadIdx.x; i < p.nCP; i += blockDim.x) {
         double2 acc = make_double2(0.0, 0.0);
-        for (int t = 0; t < p.cpT; ++t) {
-            const uint32_t w = __ldg(p.cpTerms + (size_t)t * p.nCP + i);
-            acc = zfma(acc, Gm[w & 0xffffu], pal[w >> 16]);
+        for (int t = 0; t < p.cpT / 4; ++t) {   // [cpT/4][nCP] words of 4 terms: pair index (bit 15: conjugate) | palette << 16
+            const uint4 v = __ldg(cpt + (size_t)t * p.nCP + i);
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double2 g = Gm[w4[u] & 0x7fffu];
+                acc = zfma(acc, make_double2(g.x, (w4[u] & 0x8000u) ? -g.y : g.y), pal[w4[u] >> 16]);
+            }
         }
         G[i] = acc;
     }
@@ -278,54 +295,75 @@ pmi_pair_kernel(const __grid_constant__ PairDev p) {
     }
 }
 
-// subband means (dlPMISelect.m:481): REs are sorted by subband; weight = mean-of-means weight
-__global__ void pmi_subband_kernel(const double* __restrict__ S, int nCand, int nu, int nRE, int nSB,
-                                   const int* __restrict__ sbStart, const double* __restrict__ reW,
-                                   double* __restrict__ sub, double* __restrict__ psum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nCand) return;
-    const int l = blockIdx.y % nu, sb = blockIdx.y / nu, b = blockIdx.z;
-    const double* __restrict__ s = S + (long long)b * nRE * nu * nCand + c;
-    double acc = 0.0, plain = 0.0;
-    bool any = false;
-#pragma unroll 4
-    for (int e = sbStart[sb]; e < sbStart[sb + 1]; ++e) {
-        const double v = s[((long long)e * nu + l) * nCand];
-        if (!isnan(v)) {
-            acc += reW[e] * v;
-            plain += v;   // un-weighted partial of sum(SINRPerRE,[1 2 3],'omitnan') (dlPMISelect.m:444)
-            any = true;
-        }
-    }
-    const long long o = (((long long)b * nSB + sb) * nu + l) * nCand + c;
-    sub[o] = any ? acc : NAN;
-    psum[o] = plain;
-}
-
-struct SelDev {
-    const double* psum;
-    const double* sub;
+// ---- selection kernels, all ranks of a report in one launch each ----
+struct PostRank {
     const double* S;
-    const int* sbStart;
-    const int* cqiStart;
-    const double* cqiW;
+    double* sub;
+    double* psum;
     int* sel;
     double* sinrSel;
     double* sinrWb;
-    int nCand, nu, nRE, nSB, nCqiSB, n2, n11, n12, n13;
+    int nCand, nu, n2, n11, n12, n13, chunk0;
+};
+struct PostDev {
+    PostRank rk[kMaxLayers];
+    const int* sbStart;
+    const int* cqiStart;
+    const double* reW;
+    const double* cqiW;
+    int nRanks, nRE, nSB, nCqiSB;
 };
 
-__global__ void __launch_bounds__(256) pmi_select_kernel(const SelDev p) {
+__device__ __forceinline__ PostRank pick_rank(const PostDev& p, int key, bool byChunk) {
+    PostRank rk = p.rk[0];
+#pragma unroll
+    for (int q = 1; q < kMaxLayers; ++q)   // static indices: the descriptors stay in the parameter bank
+        if (q < p.nRanks && (byChunk ? key >= p.rk[q].chunk0 : key == q)) rk = p.rk[q];
+    return rk;
+}
+
+// subband means (dlPMISelect.m:481): REs are sorted by subband; weight = mean-of-means weight.
+// grid: x = 128-candidate chunks of all ranks, y = subband, z = UE
+__global__ void __launch_bounds__(128) pmi_subband_kernel(const __grid_constant__ PostDev p) {
+    const PostRank rk = pick_rank(p, blockIdx.x, true);
+    const int c = (blockIdx.x - rk.chunk0) * blockDim.x + threadIdx.x;
+    const int sb = blockIdx.y, b = blockIdx.z;
+    if (c >= rk.nCand) return;
+    const int nCand = rk.nCand, nu = rk.nu;
+    const int e0 = p.sbStart[sb], e1 = p.sbStart[sb + 1];
+    for (int l = 0; l < nu; ++l) {
+        const double* __restrict__ s = rk.S + ((long long)b * p.nRE * nu + l) * nCand + c;
+        double acc = 0.0, plain = 0.0;
+        bool any = false;
+#pragma unroll 4
+        for (int e = e0; e < e1; ++e) {
+            const double v = s[(long long)e * nu * nCand];
+            if (!isnan(v)) {
+                acc += p.reW[e] * v;
+                plain += v;   // un-weighted partial of sum(SINRPerRE,[1 2 3],'omitnan') (dlPMISelect.m:444)
+                any = true;
+            }
+        }
+        const long long o = (((long long)b * p.nSB + sb) * nu + l) * nCand + c;
+        rk.sub[o] = any ? acc : NAN;
+        rk.psum[o] = plain;
+    }
+}
+
+// grid: x = UE, y = rank slot
+__global__ void __launch_bounds__(256) pmi_select_kernel(const __grid_constant__ PostDev pd) {
     __shared__ double bv[8];
     __shared__ int bi[8];
     __shared__ int best;
+    const PostRank p = pick_rank(pd, blockIdx.y, false);
+    const int nSB = pd.nSB;
     const int b = blockIdx.x;
-    const double* __restrict__ ps = p.psum + (long long)b * p.nSB * p.nu * p.nCand;
+    const double* __restrict__ ps = p.psum + (long long)b * nSB * p.nu * p.nCand;
     double v = -INFINITY;
     int ix = -1;
     for (int c = threadIdx.x; c < p.nCand; c += blockDim.x) {
         double tot = 0.0;  // totalSINR: fixed summation order (subband-major, then layer)
-        for (int q = 0; q < p.nSB * p.nu; ++q) tot += ps[(long long)q * p.nCand + c];
+        for (int q = 0; q < nSB * p.nu; ++q) tot += ps[(long long)q * p.nCand + c];
         const double t = round4(tot);  // dlPMISelect.m:449
         if (ix < 0 || t > v) {
             v = t;
@@ -360,7 +398,7 @@ __global__ void __launch_bounds__(256) pmi_select_kernel(const SelDev p) {
     const int lin = best;
     const int i2wb = lin % p.n2, i11 = (lin / p.n2) % p.n11, i12 = (lin / (p.n2 * p.n11)) % p.n12,
               i13 = lin / (p.n2 * p.n11 * p.n12);
-    int* __restrict__ sel = p.sel + (long long)b * (4 + p.nSB);
+    int* __restrict__ sel = p.sel + (long long)b * (4 + nSB);
     if (threadIdx.x == 0) {
         sel[0] = i2wb;
         sel[1] = i11;
@@ -368,14 +406,14 @@ __global__ void __launch_bounds__(256) pmi_select_kernel(const SelDev p) {
         sel[3] = i13;
     }
     const long long base1 = (long long)p.n2 * (i11 + (long long)p.n11 * (i12 + (long long)p.n12 * i13));
-    for (int sb = threadIdx.x; sb < p.nSB; sb += blockDim.x) {
+    for (int sb = threadIdx.x; sb < nSB; sb += blockDim.x) {
         int pick = -1;
-        if (p.sbStart[sb + 1] > p.sbStart[sb]) {  // CSI-RS present in the subband
+        if (pd.sbStart[sb + 1] > pd.sbStart[sb]) {  // CSI-RS present in the subband
             double bestT = -INFINITY;
             for (int i2 = 0; i2 < p.n2; ++i2) {
                 double acc = 0.0;
                 for (int l = 0; l < p.nu; ++l) {
-                    const double x = p.sub[(((long long)b * p.nSB + sb) * p.nu + l) * p.nCand + base1 + i2];
+                    const double x = p.sub[(((long long)b * nSB + sb) * p.nu + l) * p.nCand + base1 + i2];
                     if (!isnan(x)) acc += x;  // sum(...,2,'omitnan')  (dlPMISelect.m:492)
                 }
                 const double t = round4(acc);
@@ -387,21 +425,21 @@ __global__ void __launch_bounds__(256) pmi_select_kernel(const SelDev p) {
         }
         sel[4 + sb] = pick;
         for (int l = 0; l < p.nu; ++l)
-            p.sinrSel[((long long)b * p.nSB + sb) * p.nu + l] =
-                pick >= 0 ? p.sub[(((long long)b * p.nSB + sb) * p.nu + l) * p.nCand + base1 + pick] : NAN;
+            p.sinrSel[((long long)b * nSB + sb) * p.nu + l] =
+                pick >= 0 ? p.sub[(((long long)b * nSB + sb) * p.nu + l) * p.nCand + base1 + pick] : NAN;
     }
     __syncthreads();
     // CQI-subband SINR with one wideband i2 (cqiSelect.m:586-596 -> getSubbandSINR :768-800)
     const int i2first = sel[4];
-    for (int idx = threadIdx.x; idx < p.nCqiSB * p.nu; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < pd.nCqiSB * p.nu; idx += blockDim.x) {
         const int l = idx % p.nu, cs = idx / p.nu;
         double acc = NAN;
-        if (i2first >= 0 && p.cqiStart[cs + 1] > p.cqiStart[cs]) {
+        if (i2first >= 0 && pd.cqiStart[cs + 1] > pd.cqiStart[cs]) {
             acc = 0.0;
-            for (int e = p.cqiStart[cs]; e < p.cqiStart[cs + 1]; ++e)
-                acc += p.cqiW[e] * p.S[(((long long)b * p.nRE + e) * p.nu + l) * p.nCand + base1 + i2first];
+            for (int e = pd.cqiStart[cs]; e < pd.cqiStart[cs + 1]; ++e)
+                acc += pd.cqiW[e] * p.S[(((long long)b * pd.nRE + e) * p.nu + l) * p.nCand + base1 + i2first];
         }
-        p.sinrWb[((long long)b * p.nCqiSB + cs) * p.nu + l] = acc;
+        p.sinrWb[((long long)b * pd.nCqiSB + cs) * p.nu + l] = acc;
     }
 }
 
@@ -548,7 +586,8 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
             sh->colIdx[key] = id;
             return id;
         };
-        auto colpair_of = [&](int ci, int cj) {      // G = <g_ci, g_cj> = sum conj(c_i,blk) c_j,blk' Gamma[(blk,b_i),(blk',b_j)]
+        // G = <g_ci, g_cj> = sum conj(c_i,blk) c_j,blk' Gamma[(blk,b_i),(blk',b_j)], stored once per unordered pair
+        auto colpair_impl = [&](int ci, int cj) -> int {
             const unsigned long long key = ((unsigned long long)ci << 32) | (unsigned)cj;
             auto it = sh->cpIdx.find(key);
             if (it != sh->cpIdx.end()) return it->second;
@@ -559,7 +598,9 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
                 for (int bj = 0; bj < t.NB; ++bj) {
                     const std::complex<double> q = std::conj(a.coef[bi]) * bcol.coef[bj];
                     if (std::abs(q) < 1e-300) continue;
-                    const uint32_t a1 = (uint32_t)(bi * t.nBeams + a.beam), a2 = (uint32_t)(bj * t.nBeams + bcol.beam);
+                    uint32_t a1 = (uint32_t)(bi * t.nBeams + a.beam), a2 = (uint32_t)(bj * t.nBeams + bcol.beam);
+                    uint32_t cj = 0;                       // Gamma[a2,a1] = conj(Gamma[a1,a2]): keep one orientation
+                    if (a1 > a2) { std::swap(a1, a2); cj = 0x8000u; }
                     const uint32_t pk = a1 | (a2 << 16);
                     auto pit = sh->pairIdx.find(pk);
                     int pi;
@@ -575,14 +616,17 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
                         sh->pal.push_back(make_double2(q.real(), q.imag()));
                         sh->palIdx[qkey(q)] = qi;
                     } else qi = qit->second;
-                    if (pi > 0xffff || qi > 0xffff) { sh->ok = false; pi = qi = 0; }
-                    v.push_back((uint32_t)pi | ((uint32_t)qi << 16));
+                    if (pi > 0x7fff || qi > 0xffff) { sh->ok = false; pi = qi = 0; }
+                    v.push_back((uint32_t)pi | cj | ((uint32_t)qi << 16));
                 }
             v.resize(sh->cpT, 0u);
             sh->cpTerms.insert(sh->cpTerms.end(), v.begin(), v.end());
             sh->cpIdx[key] = id;
-            if (id > 0xffff || t.NB * t.nBeams > 0xffff) sh->ok = false;
+            if (id > 0x7fff || t.NB * t.nBeams > 0xffff) sh->ok = false;
             return id;
+        };
+        auto colpair_of = [&](int ci, int cj) -> int {    // <g_cj, g_ci> = conj(<g_ci, g_cj>): bit 15 of the entry
+            return ci > cj ? (colpair_impl(cj, ci) | 0x8000) : colpair_impl(ci, cj);
         };
         const int NT = nu * (nu + 1) / 2, ntPad = (NT + 7) / 8 * 8;
         p->ntPad = ntPad;
@@ -705,9 +749,9 @@ static int pair_sync_dict(Ctx* ctx, PmiShared* sh, cudaStream_t st) {
     cudaFree(sh->d_cpTerms);
     sh->d_pairs = nullptr; sh->d_pal = nullptr; sh->d_cpTerms = nullptr;
     const size_t nCP = sh->cpTerms.size() / sh->cpT;
-    std::vector<uint32_t> tt(sh->cpTerms.size());   // [cpT][nCP]: coalesced over the column pairs
+    std::vector<uint32_t> tt(sh->cpTerms.size());   // [cpT/4][nCP][4]: one 16-byte word of 4 terms per column pair, coalesced
     for (size_t q = 0; q < nCP; ++q)
-        for (int t = 0; t < sh->cpT; ++t) tt[(size_t)t * nCP + q] = sh->cpTerms[q * sh->cpT + t];
+        for (int t = 0; t < sh->cpT; ++t) tt[((size_t)(t / 4) * nCP + q) * 4 + (t % 4)] = sh->cpTerms[q * sh->cpT + t];
     int s;
     if ((s = upload(ctx, &sh->d_pairs, sh->pairs))) return s;
     if ((s = upload(ctx, &sh->d_pal, sh->pal))) return s;
@@ -784,17 +828,32 @@ int pmi_select_run_multi(PmiPlan* const* plans, int n, const float2* H, const do
         ISAC_CUDA_CHECK(ctx, cudaGetLastError());
         count_launches(ctx, 1);
     }
-    for (PmiPlan* p : live) {
-        const CodebookTable& t = p->tab;
-        const int nCand = t.nCand(), nu = p->nLayers, nRE = (int)p->reK.size();
-        dim3 g2((nCand + 127) / 128, nu * p->nSB, batch);
-        pmi_subband_kernel<<<g2, 128, 0, st>>>(p->d_S, nCand, nu, nRE, p->nSB, p->d_sbStart, p->d_reW, p->d_sub, p->d_total);
-        SelDev sd{};
-        sd.psum = p->d_total; sd.sub = p->d_sub; sd.S = p->d_S; sd.sbStart = p->d_sbStart; sd.cqiStart = p->d_cqiStart;
-        sd.cqiW = p->d_reCqiW; sd.sel = p->d_sel; sd.sinrSel = p->d_sinrSel; sd.sinrWb = p->d_sinrWb;
-        sd.nCand = nCand; sd.nu = nu; sd.nRE = nRE; sd.nSB = p->nSB; sd.nCqiSB = p->nCqiSB;
-        sd.n2 = t.n2; sd.n11 = t.n11; sd.n12 = t.n12; sd.n13 = t.n13;
-        pmi_select_kernel<<<batch, 256, 0, st>>>(sd);
+    // subband means + selection: one launch each for the plans that share the RE partition (all ranks of a CSI plan)
+    std::fill(done.begin(), done.end(), 0);
+    for (size_t i = 0; i < live.size(); ++i) {
+        if (done[i]) continue;
+        PmiPlan* p = live[i];
+        PostDev pd{};
+        pd.sbStart = p->d_sbStart; pd.cqiStart = p->d_cqiStart; pd.reW = p->d_reW; pd.cqiW = p->d_reCqiW;
+        pd.nRE = (int)p->reK.size(); pd.nSB = p->nSB; pd.nCqiSB = p->nCqiSB;
+        int chunks = 0;
+        for (size_t j = i; j < live.size(); ++j) {
+            PmiPlan* q = live[j];
+            if (done[j] || q->reK != p->reK || q->reL != p->reL || q->nSB != p->nSB || q->nCqiSB != p->nCqiSB || q->sbSizes != p->sbSizes ||
+                q->cqiSbSizes != p->cqiSbSizes)
+                continue;
+            const CodebookTable& t = q->tab;
+            PostRank& rk = pd.rk[pd.nRanks++];
+            rk.S = q->d_S; rk.sub = q->d_sub; rk.psum = q->d_total; rk.sel = q->d_sel; rk.sinrSel = q->d_sinrSel; rk.sinrWb = q->d_sinrWb;
+            rk.nCand = t.nCand(); rk.nu = q->nLayers; rk.n2 = t.n2; rk.n11 = t.n11; rk.n12 = t.n12; rk.n13 = t.n13;
+            rk.chunk0 = chunks;
+            chunks += (rk.nCand + 127) / 128;
+            done[j] = 1;
+        }
+        dim3 g2(chunks, p->nSB, batch);
+        pmi_subband_kernel<<<g2, 128, 0, st>>>(pd);
+        dim3 g3(batch, pd.nRanks);
+        pmi_select_kernel<<<g3, 256, 0, st>>>(pd);
         count_launches(ctx, 2);
     }
     prof_end(ctx, pr, st);

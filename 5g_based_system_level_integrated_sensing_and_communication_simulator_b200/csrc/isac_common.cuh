@@ -40,6 +40,23 @@ __device__ __forceinline__ double2 zfms(double2 acc, double2 a, double2 b) {    
 __device__ __forceinline__ double2 zfmsc(double2 acc, double2 a, double2 b) {   // acc - a*conj(b)
     return make_double2(fma(-a.x, b.x, fma(-a.y, b.y, acc.x)), fma(-a.y, b.x, fma(a.x, b.y, acc.y)));
 }
+// fast float64 reciprocal / reciprocal square root: MUFU seed (rcp/rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps
+// (relative error ~1e-16; not correctly rounded, which the 1e-5 parity budget of the SINR path does not need)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    return y * fma(-hx * y, y, 1.5);
+}
 __host__ __device__ __forceinline__ double2 zadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ double2 zsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
