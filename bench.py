@@ -212,7 +212,10 @@ class CommWorkload:
 
     def algorithmic_bytes(self):
         K = self.K
-        return {"cdl": 8 * K * 14 * 8 * 8}   # bytes written per DL H; UL launches are smaller (reported with the same slot)
+        # bytes of H written per launch pair, averaged over the 4 DL (nb channels x 14 symbols x 8x8) and 5 UL
+        # (nul channels x 1 symbol x 8x2) batched generations of a step (8 bytes per channel coefficient)
+        total = 4 * self.nb * 8 * K * 14 * 8 * 8 + 5 * self.nul * 8 * K * 1 * 8 * 2
+        return {"cdl": total / 9.0}
 
 
 def run_b200(args):
@@ -308,30 +311,51 @@ def run_b200(args):
     # ---- end-to-end through the host API (pinned host in, host results out) -------------------------
     pin_wave = [torch.from_numpy(np.ascontiguousarray(host_wave[c % uniq].T)).pin_memory() for c in range(uniq)]
     pin_grid = [torch.from_numpy(np.ascontiguousarray(host_grid[c % uniq].transpose(2, 1, 0))).pin_memory() for c in range(uniq)]
-    stage_wave = [torch.empty((nTx, T), dtype=torch.complex64, device="cuda") for _ in range(2)]
+    # Two sets of device staging buffers: the copy stream fills set (s+1)%2 with the next step's inputs while the compute
+    # stream works on set s%2, so PCIe traffic overlaps the COMM/sensing kernels of the step before.
+    stage_wave = [[torch.empty((nTx, T), dtype=torch.complex64, device="cuda") for _ in range(cells)] for _ in range(2)]
+    stage_grid = [tx_grid_d, torch.empty_like(tx_grid_d)]
+    copy_stream = torch.cuda.Stream()
+    copied = [torch.cuda.Event(), torch.cuda.Event()]     # set s holds the inputs of its step
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]   # the sensing pass that read set s has been enqueued and finished
 
-    def step_e2e(step):
+    def upload(step):
+        s = step % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            for c in range(cells):
+                stage_wave[s][c].copy_(pin_wave[c % uniq], non_blocking=True)
+                stage_grid[s][c].copy_(pin_grid[c % uniq], non_blocking=True)
+            copied[s].record(copy_stream)
+
+    def step_e2e(step, last):
+        s = step % 2
+        if not last:
+            upload(step + 1)
         comm.step(step)   # COMM results already land on the host (PMI/RI/CQI/TPMI); H is generated on the device
         # simulation.cellSimulation's sensing pass (cellSimulation.m:191-197) per cell: txWave+txGrid in, estResults out
         ctx.use_torch_stream()
+        torch.cuda.current_stream().wait_event(copied[s])
         for c in range(cells):
-            sw = stage_wave[c % 2]
-            sw.copy_(pin_wave[c % uniq], non_blocking=True)
-            tx_grid_d[c].copy_(pin_grid[c % uniq], non_blocking=True)
-            _lib.check(ctx.lib.isac_mono_static_sensing_dev(ctx.handle, C.byref(eargs.cfg), _lib.ptr(sw), None,
+            _lib.check(ctx.lib.isac_mono_static_sensing_dev(ctx.handle, C.byref(eargs.cfg), _lib.ptr(stage_wave[s][c]), None,
                                                             _lib.NOISE_PHILOX, 7919 * step + c, _lib.ptr(rx_grid_d[c]),
                                                             C.byref(nsym_out)), ctx.handle)
-        plan.run_dev(rx_grid_d, tx_grid_d, cells)
+        plan.run_dev(rx_grid_d, stage_grid[s], cells)
+        consumed[s].record(torch.cuda.current_stream())
         return plan.collect(cells)   # D2H of detections / estimates (synchronises)
 
     e2e_steps = max(1, min(args.steps, 5))
-    step_e2e(0)
+    for ev in consumed:
+        ev.record(torch.cuda.current_stream())
+    upload(0)
+    step_e2e(0, True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.time()
+    upload(1)                      # every timed step's inputs cross PCIe inside the timed region
     for i in range(e2e_steps):
-        out = step_e2e(i + 1)
+        out = step_e2e(i + 1, i == e2e_steps - 1)
     torch.cuda.synchronize()
     t_e2e = time.time() - t0
     if world > 1:
