@@ -128,6 +128,7 @@ def _declare(lib):
         "isac_pusch_codebook": ([i32, i32, P(i32), vp], C.c_int),
         "isac_pmi_plan_create": ([vp, P(CsiConfig), i32, i32, P(vp)], C.c_int),
         "isac_pmi_plan_destroy": ([vp], C.c_int),
+        "isac_precoded_sinr_host": ([vp, vp, i32, i32, f64, vp, i32, i32, vp], C.c_int),
         "isac_pmi_plan_set_kernel": ([vp, i32], C.c_int),
         "isac_csi_plan_set_kernel": ([vp, i32], C.c_int),
         "isac_pmi_plan_info": ([vp, P(i32), P(i32), P(i32), P(i32), vp, vp], C.c_int),

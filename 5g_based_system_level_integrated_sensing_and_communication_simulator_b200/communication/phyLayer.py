@@ -409,14 +409,24 @@ def pmiSelectBatch(nlayers, hest, noiseest, bandSize):
 
 
 def precodedSINR(H, sigma, W):
-    """``sinr = communication.phyLayer.precodedSINR(H,sigma,W)`` (precodedSINR.m:11-18): LMMSE SINR summed over the
-    layers for one RE.  Evaluated by the UL kernel on a one-RE grid."""
-    H = np.asarray(H)
-    W = np.asarray(W)
-    R, P = H.shape
-    nu = W.shape[1]
-    # one-RE problem through the generic Type-I machinery is overkill; use the UL kernel with an explicit W
-    raise NotImplementedError("single-RE precodedSINR is exposed through pmiSelect / dlPMISelect batches")
+    """``sinr = communication.phyLayer.precodedSINR(H,sigma,W)`` (precodedSINR.m:11-18): LMMSE SINR of the precoded
+    channel summed over the layers.  H [nRx x nPorts] (or [nRx x nPorts x nRE] for a batch of REs sharing W),
+    W [nPorts x nLayers]; float64 throughout as in the reference."""
+    H = np.asarray(H, dtype=np.complex128)
+    W = np.ascontiguousarray(np.asarray(W, dtype=np.complex128).T)      # column-major [P x nu]
+    single = H.ndim == 2
+    if single:
+        H = H[:, :, None]
+    R, P, B = H.shape
+    nu = W.shape[0]
+    if W.shape[1] != P:
+        raise ValueError("W must be nPorts-by-nLayers")
+    Hc = np.ascontiguousarray(H.transpose(2, 1, 0))                     # [B][P][R] == column-major [R x P x B]
+    out = np.zeros(B)
+    ctx = _lib.get_context(None)
+    _lib.check(ctx.lib.isac_precoded_sinr_host(ctx.handle, _lib.ptr(Hc), R, P, float(sigma), _lib.ptr(W), nu, B, _lib.ptr(out)),
+               ctx.handle)
+    return float(out[0]) if single else out
 
 
 def sinrPerSubband(sinr, bandSize):

@@ -918,6 +918,27 @@ int isac_csi_report_dev(isac_csi_plan* pl, const void* H, const double* nVar, in
     return ISAC_OK;
 }
 
+int isac_precoded_sinr_host(isac_ctx* h, const void* H, int32_t nRx, int32_t nPorts, double sigma, const void* W, int32_t nLayers,
+                            int32_t batch, double* sinr) {
+    if (!h || !H || !W || !sinr || batch < 1 || nRx < 1 || nPorts < 1 || nLayers < 1) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    const size_t bH = sizeof(double2) * (size_t)nRx * nPorts * batch, bW = sizeof(double2) * (size_t)nPorts * nLayers;
+    void* d = nullptr;
+    int st = ctx_scratch(c, 11, bH + bW + sizeof(double) * batch, &d);
+    if (st) return st;
+    double2* dH = (double2*)d;
+    double2* dW = (double2*)((char*)d + bH);
+    double* dOut = (double*)((char*)d + bH + bW);
+    ISAC_CUDA_CHECK(c, cudaMemcpyAsync(dH, H, bH, cudaMemcpyHostToDevice, c->stream));
+    ISAC_CUDA_CHECK(c, cudaMemcpyAsync(dW, W, bW, cudaMemcpyHostToDevice, c->stream));
+    st = precoded_sinr_run(c, dH, nRx, nPorts, sigma, dW, nLayers, batch, dOut, c->stream);
+    if (st) return st;
+    ISAC_CUDA_CHECK(c, cudaMemcpyAsync(sinr, dOut, sizeof(double) * batch, cudaMemcpyDeviceToHost, c->stream));
+    ISAC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return ISAC_OK;
+}
+
 int isac_ul_pmi_select_dev(isac_ctx* h, int32_t nLayers, const void* hest, int32_t K, int32_t nSym, int32_t nRx, int32_t nPorts,
                            double noiseEst, int32_t bandSize, int32_t maxSB, double* pmi, double* sinr, int32_t* sbIdx,
                            int32_t* nSB, int32_t* nTPMI, int32_t* none) {

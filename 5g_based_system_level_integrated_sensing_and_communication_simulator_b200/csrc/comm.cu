@@ -1322,4 +1322,64 @@ int prg_precode_run(Ctx* ctx, int K, int Lsym, int nStartGrid, const float2* por
     return kOk;
 }
 
+// ------------------------------------------------------------------------------------------
+// precodedSINR (precodedSINR.m:11-18): sum over the layers of the LMMSE SINR of one RE, for a batch of REs that
+// share the precoder W.  float64 in and out (the reference passes doubles); one thread per RE.
+// ------------------------------------------------------------------------------------------
+template <int NU>
+__global__ void __launch_bounds__(128)
+precoded_sinr_kernel(const double2* __restrict__ H, int R, int P, const double2* __restrict__ W, double nVar, int batch,
+                     double* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    constexpr int NT = NU * (NU + 1) / 2;
+    double2 A[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) A[i] = make_double2(0.0, 0.0);
+    const double2* __restrict__ Hb = H + (size_t)b * R * P;
+    for (int r = 0; r < R; ++r) {
+        double2 g[NU];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) g[j] = make_double2(0.0, 0.0);
+        for (int q = 0; q < P; ++q) {
+            const double2 h = Hb[r + (size_t)R * q];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) g[j] = zfma(g[j], h, __ldg(W + q + (size_t)P * j));
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) A[TRI(i, j)] = zfmac(A[TRI(i, j)], g[j], g[i]);
+    }
+    double s[NU];
+    chol_sinr<NU>(A, nVar, s, 1);
+    double tot = 0.0;
+#pragma unroll
+    for (int j = 0; j < NU; ++j) tot += s[j];
+    out[b] = tot;
+}
+
+int precoded_sinr_run(Ctx* ctx, const double2* H, int R, int P, double sigma, const double2* W, int nLayers, int batch,
+                      double* out, cudaStream_t st) {
+    if (!H || !W || !out || R < 1 || P < 1 || nLayers < 1 || nLayers > kMaxLayers || batch < 1 || !(sigma > 0.0)) {
+        set_error(ctx, "precodedSINR: invalid argument (1 <= nLayers <= 8, sigma > 0)");
+        return kErrInvalidArg;
+    }
+    const double nVar = sigma * sigma;
+    const int grid = (batch + 127) / 128;
+    switch (nLayers) {
+        case 1: precoded_sinr_kernel<1><<<grid, 128, 0, st>>>(H, R, P, W, nVar, batch, out); break;
+        case 2: precoded_sinr_kernel<2><<<grid, 128, 0, st>>>(H, R, P, W, nVar, batch, out); break;
+        case 3: precoded_sinr_kernel<3><<<grid, 128, 0, st>>>(H, R, P, W, nVar, batch, out); break;
+        case 4: precoded_sinr_kernel<4><<<grid, 128, 0, st>>>(H, R, P, W, nVar, batch, out); break;
+        case 5: precoded_sinr_kernel<5><<<grid, 128, 0, st>>>(H, R, P, W, nVar, batch, out); break;
+        case 6: precoded_sinr_kernel<6><<<grid, 128, 0, st>>>(H, R, P, W, nVar, batch, out); break;
+        case 7: precoded_sinr_kernel<7><<<grid, 128, 0, st>>>(H, R, P, W, nVar, batch, out); break;
+        default: precoded_sinr_kernel<8><<<grid, 128, 0, st>>>(H, R, P, W, nVar, batch, out); break;
+    }
+    count_launches(ctx, 1);
+    ISAC_CUDA_CHECK(ctx, cudaGetLastError());
+    return kOk;
+}
+
 }  // namespace isac

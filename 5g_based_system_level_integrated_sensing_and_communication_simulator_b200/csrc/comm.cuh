@@ -122,6 +122,10 @@ int ul_pmi_select_run(Ctx* ctx, int nLayers, const float2* hest, int K, int nSym
 int ul_pmi_select_batch(Ctx* ctx, int nLayers, const float2* hest, int K, int nSym, int nRx, int P, double noiseEst,
                         int bandSize, int batch, std::vector<UlPmiResult>& out, cudaStream_t st);
 
+// precodedSINR (precodedSINR.m:11-18) for `batch` REs sharing W: H [nRx x P x batch], W [P x nLayers] complex128 (device)
+int precoded_sinr_run(Ctx* ctx, const double2* H, int R, int P, double sigma, const double2* W, int nLayers, int batch,
+                      double* out, cudaStream_t st);
+
 // prgPrecode (prgPrecode.m:53-144): portsym/portind [NRE x nLayers], F [nLayers x P x NPRG] (device);
 // antsym [NRE x P] complex64, antind [NRE x P] int32 (1-based).  scratch grid owned by ctx.
 int prg_precode_run(Ctx* ctx, int K, int Lsym, int nStartGrid, const float2* portsym, const int* portind, int NRE,

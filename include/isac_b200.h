@@ -264,6 +264,11 @@ int isac_csi_report_dev(isac_csi_plan* plan, const void* H, const double* nVar, 
                         int32_t tableLen, int32_t rankCap, double* RI, double* i1, double* i2, double* cqi,
                         int32_t* cqiRows);
 
+/* sinr = communication.phyLayer.precodedSINR(H,sigma,W) (precodedSINR.m:11-18) for `batch` REs that share W:
+ * H host complex128 [nRx x nPorts x batch], W host complex128 [nPorts x nLayers], sinr host double [batch]
+ * (LMMSE SINR summed over the layers).  nLayers <= 8, sigma > 0. */
+int isac_precoded_sinr_host(isac_ctx* ctx, const void* H, int32_t nRx, int32_t nPorts, double sigma, const void* W,
+                            int32_t nLayers, int32_t batch, double* sinr);
 /* [pmi,sinr,subbandIndices] = communication.phyLayer.pmiSelect(nlayers,hest,noiseest,bandSize) (pmiSelect.m:28).
  * hest: device complex64 [K x nSym x nRx x nPorts].  pmi [nSB] 0-based TPMI (NaN), sinr [nSB x nTPMI],
  * subbandIndices [nSB x 2].  *none = 1 reproduces the reference's scalar-NaN outputs (pmiSelect.m:60-64). */

@@ -1,0 +1,118 @@
+"""Regenerate the fixtures under tests/golden/ (run from the repo root: ``python tests/golden/make_golden.py``).
+
+The reference is MATLAB + 5G/Phased-Array toolboxes and cannot be executed in this image, so these vectors are NOT
+reference outputs: they freeze the float64 oracle (oracle/, itself PARITY-UNPINNED) on small seeded cases.  They
+serve two purposes: (1) `tests/test_golden_cpu.py` detects drift of the oracle itself (NumPy/SciPy upgrades, edits);
+(2) `tests/test_golden_gpu.py` checks the CUDA path against committed numbers, independent of a live oracle run.
+Inputs are regenerated from seeds by `workloads.py` (QPSK grids, OFDM waveforms) and NumPy `default_rng`.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import cdl as OCDL  # noqa: E402
+from oracle import comm as OC  # noqa: E402
+from oracle import sensing as OS  # noqa: E402
+
+PKG = "5g_based_system_level_integrated_sensing_and_communication_simulator_b200"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def sensing_case(name="tiny", seed=1):
+    W = importlib.import_module(PKG + ".workloads")
+    cell, car, wave = W.cell_config(name)
+    rp = OS.radar_params(cell, car, wave)
+    grid, txw = W.sensing_tx(name, seed)
+    noise = W.std_normal_complex(txw.shape, seed + 1)
+    rx = OS.mono_static_sensing(txw, grid.shape, car, rp, cell["targetLoSConditions"], noise)
+    cf = OS.cfar2d_config(rp)
+    return cell, car, wave, rp, cf, grid, txw, noise, rx
+
+
+def make_sensing():
+    cell, car, wave, rp, cf, grid, txw, noise, rx = sensing_case()
+    rx32, tx32 = rx.astype(np.complex64), grid.astype(np.complex64)
+    ref = OS.fft2d(rp, cf, rx32, tx32)
+    P = np.abs(ref["rdm"]) ** 2
+    det = ref["detections"]
+    out = {
+        "echo_grid_sample": rx[::7, ::5, :],                      # float64 echo grid, decimated (monoStaticSensing)
+        "echo_grid_rms": np.sqrt(np.mean(np.abs(rx) ** 2)),
+        "power_peak": P.max(), "power_sum": P.sum(axis=(0, 1)),   # per-antenna checksums of |RDM|^2
+        "power_sample": P[::9, ::3, :],
+        "n_det": np.array([d.shape[1] for d in det]),
+        "det_rows": np.concatenate([d[0] for d in det]), "det_cols": np.concatenate([d[1] for d in det]),
+        "rngEst": ref["rngEst"], "velEst": ref["velEst"], "aziEst": ref["aziEst"],
+        "PmusicdB": ref["PmusicdB"],
+        "cfar_alpha": OS.cfar_threshold_factor(24, rp["Pfa"]),
+        "nIFFT": rp["nIFFT"], "nFFT": rp["nFFT"],
+    }
+    np.savez_compressed(os.path.join(HERE, "sensing_tiny.npz"), **out)
+
+
+def comm_case(n_ports, panel, nrb, n_rx, seed, sb=4):
+    rng = np.random.default_rng(seed)
+    K = 12 * nrb
+    H = ((rng.standard_normal((K, 14, n_rx, n_ports)) + 1j * rng.standard_normal((K, 14, n_rx, n_ports))) / np.sqrt(2)).astype(np.complex64)
+    H = (H + np.roll(H, 1, axis=0) + np.roll(H, 2, axis=0)).astype(np.complex64)
+    ocfg = OC.report_config(n_ports, panel, nrb, 0, 1, "Subband", "Subband", sb)
+    re_k, re_l = OC.csirs_first_port_res(nrb, 1, 0)
+    return ocfg, re_k, re_l, H, 0.1
+
+
+COMM_CASES = {"p4": (4, (2, 1), 24, 4, 11), "p8": (8, (2, 2), 24, 8, 12)}
+
+
+def make_comm():
+    out = {}
+    table = np.array([-5.8, -4.0, -2.0, 0.1, 2.1, 4.0, 6.0, 7.9, 9.8, 11.7, 13.7, 15.6, 17.5, 19.5, 21.4])  # any monotone table
+    out["cqi_table"] = table
+    for tag, (P, panel, nrb, R, seed) in COMM_CASES.items():
+        ocfg, re_k, re_l, H, nv = comm_case(P, panel, nrb, R, seed)
+        for nu in (1, 2, min(R, P)):
+            pm, info = OC.dl_pmi_select(ocfg, re_k, re_l, nu, H, nv)
+            out[f"{tag}_nu{nu}_i1"] = pm["i1"]
+            out[f"{tag}_nu{nu}_i2"] = pm["i2"]
+            out[f"{tag}_nu{nu}_sinr_sb_sum"] = np.nansum(info["SINRPerSubband"], axis=(0, 1))
+            out[f"{tag}_nu{nu}_sinr_re_sample"] = info["SINRPerRE"][::5, :, ...].reshape(-1)[::97]
+        ri, pm = OC.ri_select(ocfg, re_k, re_l, H, nv)
+        out[f"{tag}_ri"] = ri
+        cqi, pmc, _, _ = OC.cqi_select(ocfg, re_k, re_l, int(ri), H, nv, table)
+        out[f"{tag}_cqi"] = cqi
+    # UL TPMI selection
+    rng = np.random.default_rng(21)
+    K = 12 * 24
+    hest = np.zeros((K, 14, 8, 4), dtype=np.complex64)
+    sc = np.arange(1, K, 4)
+    hest[sc, 13] = ((rng.standard_normal((sc.size, 8, 4)) + 1j * rng.standard_normal((sc.size, 8, 4))) / np.sqrt(2)).astype(np.complex64)
+    pmi, sinr, idx = OC.pmi_select(2, hest, 0.05, 4)
+    out["ul_pmi"], out["ul_sinr"], out["ul_idx"] = pmi, sinr, idx
+    # codebook checksums (Type-I single panel, PUSCH)
+    for tag, (P, panel, nrb, R, seed) in COMM_CASES.items():
+        ocfg = OC.report_config(P, panel, nrb, 0, 1, "Subband", "Subband", 4)
+        for nu in range(1, min(R, P) + 1):
+            Wc = OC.type1_single_panel_codebook(ocfg, nu, "ue")
+            w = np.arange(1, Wc.size + 1).reshape(Wc.shape, order="F")
+            out[f"{tag}_cb{nu}_shape"] = np.array(Wc.shape)
+            out[f"{tag}_cb{nu}_checksum"] = np.array([np.sum(Wc * w), np.sum(np.abs(Wc) ** 2)])
+    np.savez_compressed(os.path.join(HERE, "comm_small.npz"), **out)
+
+
+def make_cdl():
+    rays = OCDL.build_rays(2, 300e-9, 5.0, (1, 4, 2), (1, 2, 2), True, False, 73)   # 2 = CDL-C
+    H = OCDL.frequency_response(rays, 24 * 12, 30e3, np.arange(14) * 35.7e-6)
+    out = {"tau": rays["tau"], "power": rays["power"], "nu": rays["nu"], "g_abs2_sum": np.sum(np.abs(rays["g"]) ** 2, axis=(1, 2)),
+           "H_sample": H[::17, ::3], "H_power": np.mean(np.abs(H) ** 2)}
+    np.savez_compressed(os.path.join(HERE, "cdl_c.npz"), **out)
+
+
+if __name__ == "__main__":
+    make_sensing()
+    make_comm()
+    make_cdl()
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))

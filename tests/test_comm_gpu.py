@@ -218,6 +218,18 @@ def test_ul_pmi_select_batch(PH):
         assert np.array_equal(sinr_b[:, :, b], r[1], equal_nan=True)
 
 
+def test_precoded_sinr(PH):
+    """precodedSINR (precodedSINR.m:11-18): single RE and a batch of REs against the float64 oracle."""
+    rng = np.random.default_rng(5)
+    for nu, P, R in [(1, 2, 4), (2, 4, 8), (4, 4, 16), (3, 8, 8)]:
+        H = rng.standard_normal((R, P, 37)) + 1j * rng.standard_normal((R, P, 37))
+        W = (rng.standard_normal((P, nu)) + 1j * rng.standard_normal((P, nu))) / np.sqrt(2 * P)
+        ref = np.array([C.precoded_sinr_ul(H[:, :, b], 0.3, W) for b in range(37)])
+        got = PH.precodedSINR(H, 0.3, W)
+        assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max()
+        assert abs(PH.precodedSINR(H[:, :, 0], 0.3, W) - ref[0]) <= 1e-9 * abs(ref[0])
+
+
 def test_prg_precode(PH):
     rng = np.random.default_rng(8)
     nrb, L, nu, P, nprg = 24, 14, 2, 8, 6
