@@ -145,6 +145,7 @@ def _declare(lib):
         "isac_ul_pmi_select_batch_dev": ([vp, i32, vp, i32, i32, i32, i32, f64, i32, i32, i32, vp, vp, P(i32), P(i32), vp], C.c_int),
         "isac_cdl_generate_batch_dev": ([vp, i32, i32, f64, i32, vp, vp, vp], C.c_int),
         "isac_prg_precode_dev": ([vp, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, vp, vp], C.c_int),
+        "isac_prg_precode_batch_dev": ([vp, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp, vp], C.c_int),
         "isac_cdl_create": ([vp, P(CdlConfig), P(vp)], C.c_int),
         "isac_cdl_destroy": ([vp], C.c_int),
         "isac_cdl_get_rays": ([vp, P(i32), P(i32), P(i32), P(i32), vp, vp, vp, vp], C.c_int),

@@ -984,7 +984,17 @@ int isac_prg_precode_dev(isac_ctx* h, int32_t K, int32_t Lsym, int32_t nStartGri
     Ctx* c = &h->c;
     cudaSetDevice(c->device);
     return prg_precode_run(c, K, Lsym, nStartGrid, (const float2*)portsym, portind, NRE, nLayers, (const float2*)F, P, NPRG,
-                           (float2*)antsym, antind, c->stream);
+                           (float2*)antsym, antind, 1, c->stream);
+}
+
+int isac_prg_precode_batch_dev(isac_ctx* h, int32_t K, int32_t Lsym, int32_t nStartGrid, const void* portsym, const int32_t* portind,
+                               int32_t NRE, int32_t nLayers, const void* F, int32_t P, int32_t NPRG, int32_t batch, void* antsym,
+                               int32_t* antind) {
+    if (!h) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    return prg_precode_run(c, K, Lsym, nStartGrid, (const float2*)portsym, portind, NRE, nLayers, (const float2*)F, P, NPRG,
+                           (float2*)antsym, antind, batch, c->stream);
 }
 
 // ---- CDL channel ---------------------------------------------------------------------------------

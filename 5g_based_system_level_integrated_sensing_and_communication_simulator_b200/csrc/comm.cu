@@ -1268,27 +1268,39 @@ int ul_pmi_select_batch(Ctx* ctx, int nu, const float2* hest, int K, int nSym, i
 // ------------------------------------------------------------------------------------------
 // PRG precoding (prgPrecode.m:53-144)
 // ------------------------------------------------------------------------------------------
-__global__ void prg_scatter_kernel(const float2* __restrict__ sym, const int* __restrict__ ind, long long n, long long plane,
-                                   int nu, float2* __restrict__ portgrid /*[plane][nu]*/) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const long long lin = (long long)ind[i] - 1;
-    const long long pos = lin % plane, layer = lin / plane;
-    if (layer < nu) portgrid[pos * nu + layer] = sym[i];  // portgrid(indin) = symin (prgPrecode.m:131)
-}
-
-__global__ void prg_apply_kernel(const float2* __restrict__ portgrid, const int* __restrict__ ind, int NRE, long long plane,
-                                 int K, int nu, const float2* __restrict__ F, int P, int NPRG, int nStartGrid, int Pd,
-                                 float2* __restrict__ antsym, int* __restrict__ antind) {
+// One thread per (RE, antenna port).  The reference writes the layer symbols into a K x L x nLayers grid by linear
+// index (portgrid(indin) = symin, prgPrecode.m:131), multiplies every RE by F(:,:,prg) (:134) and reads the result back at
+// the RE positions of the first layer (:139-144).  nrPDSCHIndices-style input has the same RE positions in every layer
+// column, so the symbol that lands at (position of row i, layer l) is symin(i,l): the kernel checks exactly that and
+// otherwise falls back to scanning the index list for the target linear index (last write wins; absent -> 0), which
+// reproduces the grid semantics for arbitrary indices without a scratch grid or a second pass.
+__global__ void __launch_bounds__(256)
+prg_precode_kernel(const float2* __restrict__ sym, const int* __restrict__ ind, int NRE, long long plane, int K, int nu,
+                   const float2* __restrict__ F, int P, int NPRG, int nStartGrid, int Pd, float2* __restrict__ antsym,
+                   int* __restrict__ antind) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)NRE * P) return;
+    // blockIdx.y: independent allocations of a batch (e.g. the cells of one slot), every array stacked along its last dim
+    sym += (long long)blockIdx.y * NRE * nu;
+    ind += (long long)blockIdx.y * NRE * nu;
+    F += (long long)blockIdx.y * nu * P * NPRG;
+    antsym += (long long)blockIdx.y * NRE * P;
+    antind += (long long)blockIdx.y * NRE * P;
     const int i = (int)(gid % NRE), p = (int)(gid / NRE);
     const long long pos = ((long long)ind[i] - 1) % plane;  // RE position of the first layer's index
     const int k = (int)(pos % K);
     const int prg = (nStartGrid + k / 12) / Pd;             // getPRGSet (prgPrecode.m:94-100), 0-based
     float2 acc = make_float2(0.f, 0.f);
     for (int l = 0; l < nu; ++l) {
-        const float2 x = portgrid[pos * nu + l], f = __ldg(F + l + nu * (p + (long long)P * prg));
+        const long long target = pos + plane * l + 1;
+        float2 x;
+        if ((long long)ind[i + (long long)NRE * l] == target) x = sym[i + (long long)NRE * l];
+        else {
+            x = make_float2(0.f, 0.f);
+            for (long long q = 0; q < (long long)NRE * nu; ++q)
+                if ((long long)ind[q] == target) x = sym[q];
+        }
+        const float2 f = __ldg(F + l + nu * (p + (long long)P * prg));
         acc.x += x.x * f.x - x.y * f.y;                     // portgrid * F(:,:,prg) (prgPrecode.m:134)
         acc.y += x.x * f.y + x.y * f.x;
     }
@@ -1297,27 +1309,22 @@ __global__ void prg_apply_kernel(const float2* __restrict__ portgrid, const int*
 }
 
 int prg_precode_run(Ctx* ctx, int K, int Lsym, int nStartGrid, const float2* portsym, const int* portind, int NRE, int nu,
-                    const float2* F, int P, int NPRG, float2* antsym, int* antind, cudaStream_t st) {
-    if (!portsym || !portind || !F || !antsym || !antind || K < 12 || K % 12 || Lsym < 1 || nu < 1 || P < 1 || NPRG < 1 || NRE < 0) {
+                    const float2* F, int P, int NPRG, float2* antsym, int* antind, int batch, cudaStream_t st) {
+    if (!portsym || !portind || !F || !antsym || !antind || K < 12 || K % 12 || Lsym < 1 || nu < 1 || P < 1 || NPRG < 1 || NRE < 0 ||
+        batch < 1 || batch > 65535) {
         set_error(ctx, "prgPrecode: invalid argument");
         return kErrInvalidArg;
     }
     if (NRE == 0) return kOk;
     const long long plane = (long long)K * Lsym;
-    void* grid = nullptr;
-    int s = ctx_scratch(ctx, 6, sizeof(float2) * plane * nu, &grid);
-    if (s) return s;
     const int nrb = K / 12;
     const int Pd = (nrb + nStartGrid + NPRG - 1) / NPRG;  // Pd_BWP = ceil((NRB+nstartgrid)/NPRG)
     const int pr = prof_begin(ctx, kProfPrecode, st);
-    ISAC_CUDA_CHECK(ctx, cudaMemsetAsync(grid, 0, sizeof(float2) * plane * nu, st));
-    const long long n = (long long)NRE * nu;
-    prg_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(portsym, portind, n, plane, nu, (float2*)grid);
     const long long m = (long long)NRE * P;
-    prg_apply_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>((const float2*)grid, portind, NRE, plane, K, nu, F, P, NPRG,
-                                                                nStartGrid, Pd, antsym, antind);
+    dim3 grid((unsigned)((m + 255) / 256), batch);
+    prg_precode_kernel<<<grid, 256, 0, st>>>(portsym, portind, NRE, plane, K, nu, F, P, NPRG, nStartGrid, Pd, antsym, antind);
     prof_end(ctx, pr, st);
-    count_launches(ctx, 2);
+    count_launches(ctx, 1);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     return kOk;
 }

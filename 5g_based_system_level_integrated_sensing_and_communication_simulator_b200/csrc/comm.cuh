@@ -129,6 +129,6 @@ int precoded_sinr_run(Ctx* ctx, const double2* H, int R, int P, double sigma, co
 // prgPrecode (prgPrecode.m:53-144): portsym/portind [NRE x nLayers], F [nLayers x P x NPRG] (device);
 // antsym [NRE x P] complex64, antind [NRE x P] int32 (1-based).  scratch grid owned by ctx.
 int prg_precode_run(Ctx* ctx, int K, int Lsym, int nStartGrid, const float2* portsym, const int* portind, int NRE,
-                    int nLayers, const float2* F, int P, int NPRG, float2* antsym, int* antind, cudaStream_t st);
+                    int nLayers, const float2* F, int P, int NPRG, float2* antsym, int* antind, int batch, cudaStream_t st);
 
 }  // namespace isac

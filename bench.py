@@ -171,13 +171,14 @@ class CommWorkload:
         def alloc(syms, ksel):
             pos = (ksel[:, None] + K * torch.tensor(syms, device=dev)[None, :]).T.reshape(-1)
             ind = torch.stack([pos + 1 + K * L * j for j in range(nu)], dim=0).to(torch.int32).contiguous()   # [nu][NRE] == MATLAB [NRE x nu]
-            sym = torch.view_as_complex(torch.randn(nu, pos.numel(), 2, device=dev, generator=g)).contiguous()
+            ind = ind[None].repeat(cells, 1, 1).contiguous()                                                 # every cell: same allocation
+            sym = torch.view_as_complex(torch.randn(cells, nu, pos.numel(), 2, device=dev, generator=g)).contiguous()
             return sym, ind, pos.numel()
         self.pdsch = alloc(list(range(2, 14)), k)
         self.dmrs = alloc([2], k[::2])
-        self.F = torch.view_as_complex(torch.randn(self.nprg, Pp, nu, 2, device=dev, generator=g)).contiguous()  # == MATLAB [nu x P x NPRG]
-        self.out_sym = torch.empty(self.pdsch[2] * Pp, dtype=torch.complex64, device=dev)
-        self.out_ind = torch.empty(self.pdsch[2] * Pp, dtype=torch.int32, device=dev)
+        self.F = torch.view_as_complex(torch.randn(cells, self.nprg, Pp, nu, 2, device=dev, generator=g)).contiguous()  # == MATLAB [nu x P x NPRG x cells]
+        self.out_sym = torch.empty(cells * self.pdsch[2] * Pp, dtype=torch.complex64, device=dev)
+        self.out_ind = torch.empty(cells * self.pdsch[2] * Pp, dtype=torch.int32, device=dev)
         self.slot_t = 0.5e-3
 
     def step(self, step):
@@ -185,27 +186,28 @@ class CommWorkload:
         ptr, check = self._lib.ptr, self._lib.check
         ctx.use_torch_stream()
         frame_t0 = 0.010 * step
-        for occ in range(4):                                                # CSI-RS occasions of the frame, all cells together
-            self.t0_dl[:] = frame_t0 + (5 * occ + 2) * self.slot_t
-            check(lib.isac_cdl_generate_batch_dev(self.dl_handles, self.nb, self.K, self.SCS, 14, ptr(self.sym_t), ptr(self.t0_dl),
-                                                  ptr(self.H)), ctx.handle)
-            check(lib.isac_csi_report_dev(self.csi_plan, ptr(self.H), ptr(self.nvar), self.nb, ptr(self.table),
-                                          self.table.size, 4, ptr(self.RI), ptr(self.i1), ptr(self.i2), ptr(self.cqi),
-                                          C.byref(self.rows)), ctx.handle)
-        # SRS: UEs 0-3 at slots 3, 11, 19 and UEs 4-7 at slots 4, 12 of the frame (period 8, offset 3 + floor(ue/4))
-        for slot, grp in ((3, 0), (4, 1), (11, 0), (12, 1), (19, 0)):
-            self.t0_ul[:] = frame_t0 + slot * self.slot_t
-            check(lib.isac_cdl_generate_batch_dev(self.ul_handles[grp], self.nul, self.K, self.SCS, 1, ptr(self.sym13), ptr(self.t0_ul),
-                                                  ptr(self.hest)), ctx.handle)
-            self.hest.mul_(self.comb)                                       # comb-4 SRS REs only (setupSRS.m:11-18)
-            check(lib.isac_ul_pmi_select_batch_dev(ctx.handle, 2, ptr(self.hest), self.K, 1, 8, 2, 0.05, 16, self.nul,
-                                                   self.ul_pmi.size // self.nul, ptr(self.ul_pmi), ptr(self.ul_sinr),
-                                                   C.byref(self.ul_n[0]), C.byref(self.ul_n[1]), ptr(self.ul_none)), ctx.handle)
-        for c in range(self.cells):
-            for slot in range(12):                                          # DL slots: PDSCH + DM-RS precoding (gNBPhy.m:822,826)
+        srs = {3: 0, 4: 1, 11: 0, 12: 1, 19: 0}   # UEs 0-3 at slots 3, 11, 19, UEs 4-7 at slots 4, 12 (period 8, offset 3 + floor(ue/4))
+        for slot in range(20):                    # slot order of the frame (TDD DDDSU @30 kHz); the GPU's cells advance together
+            if slot % 5 < 3:                      # DL slot: PDSCH + DM-RS precoding of every cell (gNBPhy.m:822,826)
                 for sym, ind, nre in (self.pdsch, self.dmrs):
-                    check(lib.isac_prg_precode_dev(ctx.handle, self.K, 14, 0, ptr(sym), ptr(ind), nre, 2, ptr(self.F), 8, self.nprg,
-                                                   ptr(self.out_sym), ptr(self.out_ind)), ctx.handle)
+                    check(lib.isac_prg_precode_batch_dev(ctx.handle, self.K, 14, 0, ptr(sym), ptr(ind), nre, 2, ptr(self.F), 8, self.nprg,
+                                                         self.cells, ptr(self.out_sym), ptr(self.out_ind)), ctx.handle)
+            if slot % 5 == 2:                     # CSI-RS occasion (period 5 slots): channel of all UEs + fused RI/PMI/CQI report
+                self.t0_dl[:] = frame_t0 + slot * self.slot_t
+                check(lib.isac_cdl_generate_batch_dev(self.dl_handles, self.nb, self.K, self.SCS, 14, ptr(self.sym_t), ptr(self.t0_dl),
+                                                      ptr(self.H)), ctx.handle)
+                check(lib.isac_csi_report_dev(self.csi_plan, ptr(self.H), ptr(self.nvar), self.nb, ptr(self.table),
+                                              self.table.size, 4, ptr(self.RI), ptr(self.i1), ptr(self.i2), ptr(self.cqi),
+                                              C.byref(self.rows)), ctx.handle)
+            if slot in srs:                       # SRS occasion: UL channel of the 4 UEs of the group + TPMI selection
+                grp = srs[slot]
+                self.t0_ul[:] = frame_t0 + slot * self.slot_t
+                check(lib.isac_cdl_generate_batch_dev(self.ul_handles[grp], self.nul, self.K, self.SCS, 1, ptr(self.sym13), ptr(self.t0_ul),
+                                                      ptr(self.hest)), ctx.handle)
+                self.hest.mul_(self.comb)                                   # comb-4 SRS REs only (setupSRS.m:11-18)
+                check(lib.isac_ul_pmi_select_batch_dev(ctx.handle, 2, ptr(self.hest), self.K, 1, 8, 2, 0.05, 16, self.nul,
+                                                       self.ul_pmi.size // self.nul, ptr(self.ul_pmi), ptr(self.ul_sinr),
+                                                       C.byref(self.ul_n[0]), C.byref(self.ul_n[1]), ptr(self.ul_none)), ctx.handle)
 
     def d2h_bytes_per_step(self):
         return 4 * (self.RI.nbytes + self.i1.nbytes + self.i2.nbytes + self.cqi.nbytes) + 5 * (self.ul_pmi.nbytes + self.ul_sinr.nbytes)

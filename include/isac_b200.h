@@ -286,6 +286,11 @@ int isac_ul_pmi_select_batch_dev(isac_ctx* ctx, int32_t nLayers, const void* hes
 int isac_prg_precode_dev(isac_ctx* ctx, int32_t K, int32_t Lsym, int32_t nStartGrid, const void* portsym,
                          const int32_t* portind, int32_t NRE, int32_t nLayers, const void* F, int32_t P, int32_t NPRG,
                          void* antsym, int32_t* antind);
+/* `batch` independent allocations of the same size in one launch (e.g. the cells of one slot): every array gains a
+ * trailing batch dimension (portsym/portind [NRE x nLayers x batch], F [nLayers x P x NPRG x batch], outputs [NRE x P x batch]). */
+int isac_prg_precode_batch_dev(isac_ctx* ctx, int32_t K, int32_t Lsym, int32_t nStartGrid, const void* portsym,
+                               const int32_t* portind, int32_t NRE, int32_t nLayers, const void* F, int32_t P, int32_t NPRG,
+                               int32_t batch, void* antsym, int32_t* antind);
 
 /* ---- K11: CDL channel (TR 38.901 7.7.1) as a frequency-domain channel matrix ---------------------
  * Replaces nrCDLChannel filtering + nrChannelEstimate (uePhy.m:731,897; gNBPhy.m:840,1030; objects

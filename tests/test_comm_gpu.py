@@ -248,3 +248,13 @@ def test_prg_precode(PH):
         err = np.abs(s_g - s_o).max() / np.abs(s_o).max()
         print("prgPrecode err", err)
         assert err <= 1e-5
+    # layer columns that do not share their RE order (second layer reversed, a few of its REs missing): the grid
+    # semantics of prgPrecode.m:131-144 still hold (slow path of the kernel)
+    small = pos[:40]
+    pi2 = np.stack([small + 1, small[::-1] + 1 + K * L], axis=1)
+    pi2[3, 1] = pi2[4, 1]                           # duplicate index: the later symbol wins, RE of row 36 gets no layer-2 symbol
+    ps2 = (rng.standard_normal(pi2.shape) + 1j * rng.standard_normal(pi2.shape)).astype(np.complex64)
+    s_o, i_o = C.prg_precode((K, L, P), 0, ps2, pi2, F)
+    s_g, i_g = PH.prgPrecode((K, L, P), 0, ps2, pi2, F)
+    assert np.array_equal(i_g, i_o)
+    assert np.abs(s_g - s_o).max() <= 1e-5 * np.abs(s_o).max()
