@@ -625,6 +625,9 @@ struct isac_csi_plan {
     std::vector<int> reK, reL;
     int maxBatch;
     PmiPlan* byRank[kMaxLayers];
+    char* d_arena = nullptr;    // selection results of all ranks, contiguous -> one D2H copy per report
+    char* h_arena = nullptr;    // pinned
+    size_t arenaBytes = 0;
 };
 
 static CsiConfig to_csi_config(const isac_csi_config* c) {
@@ -756,6 +759,20 @@ int isac_csi_plan_create(isac_ctx* h, const isac_csi_config* cfg, int32_t maxBat
             return st;
         }
     }
+    for (int r = 0; r < kMaxLayers; ++r)
+        if (pl->byRank[r]) pl->arenaBytes += pl->byRank[r]->resBytes;
+    if (cudaMalloc((void**)&pl->d_arena, pl->arenaBytes ? pl->arenaBytes : 16) != cudaSuccess ||
+        cudaMallocHost((void**)&pl->h_arena, pl->arenaBytes ? pl->arenaBytes : 16) != cudaSuccess) {
+        set_error(pl->ctx, "csi_plan_create: result arena allocation failed");
+        isac_csi_plan_destroy(pl);
+        return ISAC_ERR_CUDA;
+    }
+    size_t off = 0;
+    for (int r = 0; r < kMaxLayers; ++r)
+        if (pl->byRank[r]) {
+            pmi_plan_use_arena(pl->byRank[r], pl->d_arena + off, pl->h_arena + off);
+            off += pl->byRank[r]->resBytes;
+        }
     *out = pl;
     return ISAC_OK;
 }
@@ -764,6 +781,8 @@ int isac_csi_plan_destroy(isac_csi_plan* pl) {
     if (!pl) return ISAC_OK;
     cudaSetDevice(pl->ctx->device);
     cudaStreamSynchronize(pl->ctx->stream);
+    cudaFree(pl->d_arena);
+    if (pl->h_arena) cudaFreeHost(pl->h_arena);
     for (int r = 0; r < kMaxLayers; ++r)
         if (pl->byRank[r]) pmi_plan_destroy(pl->byRank[r]);
     delete pl;
@@ -799,11 +818,8 @@ static int ri_select_batch(isac_csi_plan* pl, const float2* H, const double* nVa
         int st = pmi_select_run_multi(plans.data(), (int)plans.size(), H, nVar, batch, c->stream);
         if (st) return st;
     }
-    for (int r : valid) {
-        int st = pmi_select_collect_enqueue(pl->byRank[r - 1], batch, c->stream);
-        if (st) return st;
-    }
-    ISAC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));  // one synchronisation for all ranks
+    ISAC_CUDA_CHECK(c, cudaMemcpyAsync(pl->h_arena, pl->d_arena, pl->arenaBytes, cudaMemcpyDeviceToHost, c->stream));
+    ISAC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));  // one copy + one synchronisation for all ranks
     for (int r : valid) {
         int st = pmi_select_collect_finish(pl->byRank[r - 1], batch, all[r - 1]);
         if (st) return st;

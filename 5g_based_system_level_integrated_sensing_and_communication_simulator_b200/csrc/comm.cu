@@ -15,6 +15,7 @@
 #include "ctx.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace isac {
@@ -222,7 +223,8 @@ __device__ __noinline__ void pair_rank_eval(const PairRank rk, const double2* __
     }
 }
 
-__global__ void __launch_bounds__(128, 3)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 pmi_pair_kernel(const __grid_constant__ PairDev p) {
     extern __shared__ double2 sm[];
     const int R = p.R, P = p.P, nAtoms = p.NB * p.nBeams;
@@ -671,9 +673,14 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
     A((void**)&p->d_S, sizeof(double) * nCand * nu * nRE * B);
     A((void**)&p->d_total, sizeof(double) * nCand * nu * p->nSB * B);  // plain per-subband sums
     A((void**)&p->d_sub, sizeof(double) * nCand * nu * p->nSB * B);
-    A((void**)&p->d_sel, sizeof(int) * (4 + p->nSB) * B);
-    A((void**)&p->d_sinrSel, sizeof(double) * nu * p->nSB * B);
-    A((void**)&p->d_sinrWb, sizeof(double) * nu * p->nCqiSB * B);
+    // selection results of the plan: one arena (sel | sinrSel | sinrWb, laid out for maxBatch) -> one D2H copy
+    p->resOff[0] = 0;
+    p->resOff[1] = (sizeof(int) * (4 + p->nSB) * B + 15) / 16 * 16;
+    p->resOff[2] = p->resOff[1] + (sizeof(double) * nu * p->nSB * B + 15) / 16 * 16;
+    p->resBytes = p->resOff[2] + (sizeof(double) * nu * p->nCqiSB * B + 15) / 16 * 16;
+    A((void**)&p->d_res, p->resBytes);
+    p->ownsRes = true;
+    if (e == cudaSuccess) pmi_plan_use_arena(p, p->d_res, nullptr);
     A((void**)&ex->d_nVar, sizeof(double) * B);
     if (e != cudaSuccess) {
         set_error(ctx, std::string("pmi_plan_create: cudaMalloc: ") + cudaGetErrorString(e));
@@ -684,6 +691,19 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
     return kOk;
 }
 
+// point the plan's result arrays into `dev` (resBytes bytes) and its host staging area to `host` (may be null)
+void pmi_plan_use_arena(PmiPlan* p, char* dev, char* host) {
+    if (p->ownsRes && dev != p->d_res) {
+        cudaFree(p->d_res);
+        p->ownsRes = false;
+    }
+    p->d_res = dev;
+    p->d_sel = (int*)(dev + p->resOff[0]);
+    p->d_sinrSel = (double*)(dev + p->resOff[1]);
+    p->d_sinrWb = (double*)(dev + p->resOff[2]);
+    p->hostRes = host;
+}
+
 void pmi_plan_destroy(PmiPlan* p) {
     if (!p) return;
     cudaFree(p->d_sbStart); cudaFree(p->d_cqiStart); cudaFree(p->d_nVar);
@@ -691,7 +711,8 @@ void pmi_plan_destroy(PmiPlan* p) {
     cudaFree(p->d_beams); cudaFree(p->d_layerBeam); cudaFree(p->d_layerCoef); cudaFree(p->d_candScale);
     cudaFree(p->d_valid); cudaFree(p->d_reK); cudaFree(p->d_reL); cudaFree(p->d_reSb); cudaFree(p->d_reW);
     cudaFree(p->d_reCqiSb); cudaFree(p->d_reCqiW); cudaFree(p->d_S); cudaFree(p->d_total); cudaFree(p->d_sub);
-    cudaFree(p->d_sel); cudaFree(p->d_sinrSel); cudaFree(p->d_sinrWb); cudaFree(p->d_ent); cudaFree(p->d_invScale2);
+    if (p->ownsRes) cudaFree(p->d_res);
+    cudaFree(p->d_ent); cudaFree(p->d_invScale2);
     if (p->sh && --p->sh->refs == 0) {
         cudaFree(p->sh->d_pairs);
         cudaFree(p->sh->d_pal);
@@ -822,9 +843,15 @@ int pmi_select_run_multi(PmiPlan* const* plans, int n, const float2* H, const do
             done[j] = 1;
         }
         const size_t smem = pair_smem_bytes(sh, d.R);
-        cudaFuncSetAttribute(pmi_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static const int minb = getenv("ISAC_PAIR_MINB") ? atoi(getenv("ISAC_PAIR_MINB")) : 3;
         dim3 grid(d.nRE, batch);
-        pmi_pair_kernel<<<grid, 128, smem, st>>>(d);
+        if (minb == 4) {
+            cudaFuncSetAttribute(pmi_pair_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            pmi_pair_kernel<4><<<grid, 128, smem, st>>>(d);
+        } else {
+            cudaFuncSetAttribute(pmi_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            pmi_pair_kernel<3><<<grid, 128, smem, st>>>(d);
+        }
         ISAC_CUDA_CHECK(ctx, cudaGetLastError());
         count_launches(ctx, 1);
     }
@@ -871,23 +898,23 @@ static bool plan_all_nan(const PmiPlan* p) {
     return p->reK.empty() || !anyValid;  // dlPMISelect.m:362-379
 }
 
-// enqueue the D2H copies of the selection results into the plan's pinned staging buffer (no synchronisation)
+// enqueue the D2H copy of the selection results into pinned host memory (no synchronisation)
 int pmi_select_collect_enqueue(PmiPlan* p, int batch, cudaStream_t st) {
     Ctx* ctx = p->ctx;
+    (void)batch;
     if (plan_all_nan(p)) return kOk;
-    const size_t nu = p->nLayers, nSB = p->nSB, nC = p->nCqiSB;
-    const size_t bSel = sizeof(int) * (4 + nSB) * batch, bSs = sizeof(double) * nu * nSB * batch, bSw = sizeof(double) * nu * nC * batch;
-    const size_t need = bSel + bSs + bSw + 64;
-    if (p->pinBytes < need) {
+    if (!p->ownsRes) {   // slice of a shared arena: copy just this plan's slice to its place in the owner's pinned buffer
+        ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(p->hostRes, p->d_res, p->resBytes, cudaMemcpyDeviceToHost, st));
+        return kOk;
+    }
+    if (p->pinBytes < p->resBytes) {
         if (p->pin) cudaFreeHost(p->pin);
         p->pin = nullptr;
-        ISAC_CUDA_CHECK(ctx, cudaMallocHost(&p->pin, need));
-        p->pinBytes = need;
+        ISAC_CUDA_CHECK(ctx, cudaMallocHost(&p->pin, p->resBytes));
+        p->pinBytes = p->resBytes;
     }
-    char* h = (char*)p->pin;
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(h, p->d_sel, bSel, cudaMemcpyDeviceToHost, st));
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(h + ((bSel + 15) / 16) * 16, p->d_sinrSel, bSs, cudaMemcpyDeviceToHost, st));
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(h + ((bSel + 15) / 16) * 16 + ((bSs + 15) / 16) * 16, p->d_sinrWb, bSw, cudaMemcpyDeviceToHost, st));
+    p->hostRes = (char*)p->pin;
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(p->pin, p->d_res, p->resBytes, cudaMemcpyDeviceToHost, st));
     return kOk;
 }
 
@@ -904,11 +931,10 @@ int pmi_select_collect_finish(PmiPlan* p, int batch, std::vector<PmiResult>& out
         }
         return kOk;
     }
-    const size_t bSel = sizeof(int) * (4 + nSB) * batch, bSs = sizeof(double) * nu * nSB * batch;
-    const char* h = (const char*)p->pin;
-    const int* sel = (const int*)h;
-    const double* ss = (const double*)(h + ((bSel + 15) / 16) * 16);
-    const double* sw = (const double*)(h + ((bSel + 15) / 16) * 16 + ((bSs + 15) / 16) * 16);
+    const char* h = p->hostRes;
+    const int* sel = (const int*)(h + p->resOff[0]);
+    const double* ss = (const double*)(h + p->resOff[1]);
+    const double* sw = (const double*)(h + p->resOff[2]);
     for (int b = 0; b < batch; ++b) {
         PmiResult& r = out[b];
         const int* s = sel + (size_t)b * (4 + nSB);

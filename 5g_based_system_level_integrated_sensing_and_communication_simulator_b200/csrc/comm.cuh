@@ -77,6 +77,10 @@ struct PmiPlan {
     double invS2 = 1.0;             // 1/scale^2 of the rank
     int ntPad = 0;
     bool direct = false;            // force the direct (H*W) kernel
+    char* d_res = nullptr;          // arena holding d_sel | d_sinrSel | d_sinrWb (own allocation or a slice of a CSI plan's)
+    size_t resOff[3] = {0, 0, 0}, resBytes = 0;
+    bool ownsRes = false;
+    char* hostRes = nullptr;        // where the arena lands on the host (pinned)
     void* pin = nullptr;            // pinned staging of the selection results
     size_t pinBytes = 0;
     std::vector<uint8_t> sbHasRE, cqiSbHasRE;
@@ -84,6 +88,7 @@ struct PmiPlan {
 
 int pmi_plan_create(Ctx* ctx, const CsiConfig& cfg, int nLayers, int maxBatch, PmiPlan** out, PmiShared* share = nullptr);
 void pmi_plan_destroy(PmiPlan* p);
+void pmi_plan_use_arena(PmiPlan* p, char* dev, char* host);
 // H: device complex64 [K x L x nRx x P x batch]; nVar: host [batch]
 int pmi_select_run(PmiPlan* p, const float2* H, const double* nVar, int batch, cudaStream_t st);
 // several ranks of one report configuration: one fused SINR launch for the plans that share a dictionary
