@@ -234,30 +234,75 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-__global__ void __launch_bounds__(256)
+// Shared memory holds the operands already split into TF32 hi/lo parts and stored in mma FRAGMENT order (one 16-byte
+// word per lane and fragment), so the inner loop is 12 conflict-free LDS.128 + 48 MMAs per k-step and warp; splitting
+// every operand again at each use cost 3x the instructions of the MMAs themselves.
+//   Af[s][mt][v][lane] = {a0,a1,a2,a3} of the 16x8 A fragment of m-tile mt; v: 0 re-hi, 1 re-lo, 2 im-hi, 3 im-lo
+//   Bf[s][nt][lane]    = {b0_hi, b1_hi, b0_lo, b1_lo} of the 8x8 B fragment of n-tile nt
+constexpr int kCdlKSteps = (2 * kCdlMaxCl + 7) / 8;                                   // 6
+constexpr size_t kCdlAfBytes = sizeof(uint4) * kCdlKSteps * (kCdlTK / 16) * 4 * 32;   // 49152
+constexpr size_t kCdlBfBytes = sizeof(uint4) * kCdlKSteps * (kCdlTJ / 8) * 32;        // 49152
+constexpr size_t kCdlSmemBytes = kCdlAfBytes + kCdlBfBytes;
+
+__global__ void __launch_bounds__(256, 2)
 cdl_response_kernel(const float2* __restrict__ Call, const CdlBatch bt, int nCl, int K, long long J, double scs,
                     float2* __restrict__ Hall) {
+    extern __shared__ uint4 cdl_sm[];
+    uint4* Af = cdl_sm;
+    uint4* Bf = cdl_sm + kCdlAfBytes / sizeof(uint4);
+    float2* Es = reinterpret_cast<float2*>(Bf);   // [kCdlMaxCl][kCdlTK] staging of E, dead before Bf is filled
     const float2* __restrict__ C = Call + (size_t)blockIdx.z * nCl * J;
     const double* __restrict__ tau = bt.tau[blockIdx.z];
     float2* __restrict__ H = Hall + (size_t)blockIdx.z * K * J;
-    __shared__ float2 Es[kCdlMaxCl][kCdlTK + 4];   // +4: fragment loads of 8 consecutive rows hit distinct banks
-    __shared__ float2 Cs[kCdlMaxCl][kCdlTJ + 4];
     const int k0 = blockIdx.x * kCdlTK;
     const long long j0 = (long long)blockIdx.y * kCdlTJ;
+    const int ksteps = (2 * nCl + 7) / 8;
     for (int i = threadIdx.x; i < kCdlMaxCl * kCdlTK; i += blockDim.x) {
         const int n = i / kCdlTK, kk = i % kCdlTK;
         float2 e = make_float2(0.f, 0.f);
         if (n < nCl) {
             const double f = ((double)(k0 + kk) - (double)(K / 2)) * scs;
-            double s, c;
-            sincospi(-2.0 * f * tau[n], &s, &c);
-            e = make_float2((float)c, (float)s);
+            double sn, cs;
+            sincospi(-2.0 * f * tau[n], &sn, &cs);
+            e = make_float2((float)cs, (float)sn);
         }
-        Es[n][kk] = e;
+        Es[i] = e;
     }
-    for (int i = threadIdx.x; i < kCdlMaxCl * kCdlTJ; i += blockDim.x) {
-        const int n = i / kCdlTJ, jj = i % kCdlTJ;
-        Cs[n][jj] = (n < nCl && j0 + jj < J) ? C[(size_t)n * J + j0 + jj] : make_float2(0.f, 0.f);
+    __syncthreads();
+    // inner index q = 8s + t (+4): cluster n = 4s + t/2 (+2); part = t & 1: 0 -> (Er | Cr), 1 -> (-Ei | Ci) for Re H,
+    // (Ei | Cr), (Er | Ci) for Im H
+    for (int i = threadIdx.x; i < ksteps * (kCdlTK / 16) * 32; i += blockDim.x) {
+        const int lane = i & 31, mt = (i >> 5) % (kCdlTK / 16), sidx = i / (32 * (kCdlTK / 16));
+        const int g = lane >> 2, t = lane & 3, part = t & 1;
+        const int nA = 4 * sidx + (t >> 1), nB = nA + 2, r0 = mt * 16 + g;
+        const float2 z = make_float2(0.f, 0.f);
+        const float2 e[4] = {nA < kCdlMaxCl ? Es[nA * kCdlTK + r0] : z, nA < kCdlMaxCl ? Es[nA * kCdlTK + r0 + 8] : z,
+                             nB < kCdlMaxCl ? Es[nB * kCdlTK + r0] : z, nB < kCdlMaxCl ? Es[nB * kCdlTK + r0 + 8] : z};
+        unsigned rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            split_tf32(part ? -e[q].y : e[q].x, rh[q], rl[q]);
+            split_tf32(part ? e[q].x : e[q].y, ih[q], il[q]);
+        }
+        uint4* dst = Af + ((size_t)(sidx * (kCdlTK / 16) + mt) * 4) * 32 + lane;
+        dst[0] = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+        dst[32] = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+        dst[64] = make_uint4(ih[0], ih[1], ih[2], ih[3]);
+        dst[96] = make_uint4(il[0], il[1], il[2], il[3]);
+    }
+    __syncthreads();   // Es is dead: Bf may overwrite it
+    for (int i = threadIdx.x; i < ksteps * (kCdlTJ / 8) * 32; i += blockDim.x) {
+        const int lane = i & 31, nt = (i >> 5) % (kCdlTJ / 8), sidx = i / (32 * (kCdlTJ / 8));
+        const int g = lane >> 2, t = lane & 3, part = t & 1;
+        const int nA = 4 * sidx + (t >> 1), nB = nA + 2;
+        const long long j = j0 + nt * 8 + g;
+        const float2 z = make_float2(0.f, 0.f);
+        const float2 c0 = (nA < nCl && j < J) ? __ldg(C + (size_t)nA * J + j) : z;
+        const float2 c1 = (nB < nCl && j < J) ? __ldg(C + (size_t)nB * J + j) : z;
+        unsigned h0, l0, h1, l1;
+        split_tf32(part ? c0.y : c0.x, h0, l0);
+        split_tf32(part ? c1.y : c1.x, h1, l1);
+        Bf[i] = make_uint4(h0, h1, l0, l1);
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -269,30 +314,19 @@ cdl_response_kernel(const float2* __restrict__ Call, const CdlBatch bt, int nCl,
         for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
             for (int q = 0; q < 4; ++q) dre[mi][ni][q] = dim[mi][ni][q] = 0.f;
-    const int ksteps = (2 * nCl + 7) / 8;
-    const int part = t & 1;  // inner index q = 8s + t (+4): cluster n = 4s + t/2 (+2), part 0 -> (Er | Cr), 1 -> (-Ei | Ci)
-    for (int s = 0; s < ksteps; ++s) {
-        const int nA = 4 * s + (t >> 1), nB = nA + 2;
+    for (int sidx = 0; sidx < ksteps; ++sidx) {
         unsigned bh[4][2], bl[4][2];
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
-            const float2 c0 = Cs[nA][wj + ni * 8 + g], c1 = Cs[nB][wj + ni * 8 + g];
-            split_tf32(part ? c0.y : c0.x, bh[ni][0], bl[ni][0]);
-            split_tf32(part ? c1.y : c1.x, bh[ni][1], bl[ni][1]);
+            const uint4 b = Bf[(size_t)(sidx * (kCdlTJ / 8) + (wj >> 3) + ni) * 32 + lane];
+            bh[ni][0] = b.x; bh[ni][1] = b.y; bl[ni][0] = b.z; bl[ni][1] = b.w;
         }
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {
-            const int r0 = wk + mi * 16 + g;
-            const float2 e00 = Es[nA][r0], e10 = Es[nA][r0 + 8], e01 = Es[nB][r0], e11 = Es[nB][r0 + 8];
-            unsigned ah[4], al[4], ch[4], cl[4];   // a*: [Er, -Ei] (real part), c*: [Ei, Er] (imaginary part)
-            split_tf32(part ? -e00.y : e00.x, ah[0], al[0]);
-            split_tf32(part ? -e10.y : e10.x, ah[1], al[1]);
-            split_tf32(part ? -e01.y : e01.x, ah[2], al[2]);
-            split_tf32(part ? -e11.y : e11.x, ah[3], al[3]);
-            split_tf32(part ? e00.x : e00.y, ch[0], cl[0]);
-            split_tf32(part ? e10.x : e10.y, ch[1], cl[1]);
-            split_tf32(part ? e01.x : e01.y, ch[2], cl[2]);
-            split_tf32(part ? e11.x : e11.y, ch[3], cl[3]);
+            const uint4* src = Af + ((size_t)(sidx * (kCdlTK / 16) + (wk >> 4) + mi) * 4) * 32 + lane;
+            const uint4 v0 = src[0], v1 = src[32], v2 = src[64], v3 = src[96];
+            const unsigned ah[4] = {v0.x, v0.y, v0.z, v0.w}, al[4] = {v1.x, v1.y, v1.z, v1.w};
+            const unsigned ch[4] = {v2.x, v2.y, v2.z, v2.w}, cl[4] = {v3.x, v3.y, v3.z, v3.w};
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) {
                 mma_tf32(dre[mi][ni], al, bh[ni]);
@@ -379,7 +413,8 @@ int cdl_generate_batch(Ctx* ctx, CdlRays* const* rays, int n, int K, double scsH
         dim3 g1(r0.nCl, L, nb);
         cdl_cluster_kernel<<<g1, 128, 0, st>>>(bt, r0.nRay, losRay, r0.nCl, r0.nRx, r0.nTx, L, tl, (float2*)dC);
         dim3 grid((K + kCdlTK - 1) / kCdlTK, (unsigned)((J + kCdlTJ - 1) / kCdlTJ), nb);
-        cdl_response_kernel<<<grid, 256, 0, st>>>((const float2*)dC, bt, r0.nCl, K, J, scsHz, H + (size_t)i0 * K * J);
+        cudaFuncSetAttribute(cdl_response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCdlSmemBytes);
+        cdl_response_kernel<<<grid, 256, kCdlSmemBytes, st>>>((const float2*)dC, bt, r0.nCl, K, J, scsHz, H + (size_t)i0 * K * J);
         prof_end(ctx, pr, st);
         count_launches(ctx, 2);
     }
