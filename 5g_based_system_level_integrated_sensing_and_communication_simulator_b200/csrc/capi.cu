@@ -941,7 +941,7 @@ int isac_precoded_sinr_host(isac_ctx* h, const void* H, int32_t nRx, int32_t nPo
     cudaSetDevice(c->device);
     const size_t bH = sizeof(double2) * (size_t)nRx * nPorts * batch, bW = sizeof(double2) * (size_t)nPorts * nLayers;
     void* d = nullptr;
-    int st = ctx_scratch(c, 11, bH + bW + sizeof(double) * batch, &d);
+    int st = ctx_scratch(c, 16, bH + bW + sizeof(double) * batch, &d);
     if (st) return st;
     double2* dH = (double2*)d;
     double2* dW = (double2*)((char*)d + bH);

@@ -94,108 +94,92 @@ __device__ __forceinline__ float2 target_sample(const EchoDev& p, int i, long lo
     return cmul(cmul(u, make_float2(c, s)), p.beta[i]);
 }
 
+// Pass 1: one CTA per (OFDM symbol, stream).  Streams 0..nTgt-1 are the target waveforms w_i; with an explicit noise
+// tensor (parity mode) streams nTgt..nTgt+nAnts-1 are the mixed noise of each antenna.  The spectrum of the stream at the
+// nSc occupied subcarriers goes to W[(stream*nSymRx + s)*nSc + k] (17.6 MB at cfg2: stays in L2 for pass 2).
 template <int R1, int R2>
-__global__ void __launch_bounds__((R1 * R2 >= 256 ? R1 * R2 : 256))
-echo_demod_kernel(const EchoDev p) {
+__global__ void __launch_bounds__(R1 * R2)
+echo_stream_fft_kernel(const EchoDev p, float2* __restrict__ W) {
     using G = FftGeom<R1, R2, true>;
     constexpr int NT = G::NT, NF = G::N;
     extern __shared__ float2 smem[];
-    const int groups = blockDim.x / NT;
-    const int grp = threadIdx.x / NT, tf = threadIdx.x % NT;
-    float2* fftbuf = smem + grp * G::kElems;
-    float2* Wf = smem + groups * G::kElems;                       // [nTgt][nSc]
-    float2* steerS = Wf + (size_t)p.nTgt * p.nSc;                  // [nAnts x nTgt]
-    __shared__ double baseCycles[kEchoMaxTargets];
-    const int s = blockIdx.x;
-    for (int i = threadIdx.x; i < p.nAnts * p.nTgt; i += blockDim.x) steerS[i] = p.steerInline ? p.steerTab[i] : p.steer[i];
-    if (s >= p.nSymRx) {  // zero padding up to txDimension(2) (monoStaticSensing.m:19-21)
-        for (int r = 0; r < p.nAnts; ++r)
-            for (int k = threadIdx.x; k < p.nSc; k += blockDim.x)
-                p.out[((long long)r * p.nSymOut + s) * p.nSc + k] = make_float2(0.f, 0.f);
-        return;
-    }
+    float2* fftbuf = smem;
+    float2* steerS = smem + G::kElems;   // [nAnts] steering vector of this target
+    const int s = blockIdx.x, q = blockIdx.y, tf = threadIdx.x;
     const int cp = p.cpTab[s % p.symPer];
     const int off = cp / 2;                       // fix(cp * CyclicPrefixFraction), fraction 0.5
     const long long n0 = (long long)(s / p.symPer) * p.subframeLen + p.startTab[s % p.symPer] + off;
-    if (threadIdx.x < p.nTgt) {
-        const double c = p.fdTs[threadIdx.x] * (double)n0;
-        baseCycles[threadIdx.x] = c - floor(c);
-    }
-    __syncthreads();
     const int half = p.nSc / 2;
-    // ---- targets: FFT{w_i} -> Wf[i][k] ----
-    for (int j0 = 0; j0 < p.nTgt; j0 += groups) {
-        const int i = j0 + grp;
-        const bool act = i < p.nTgt;
-        const float2* a = steerS + (act ? i : 0) * p.nAnts;  // a_t == a_r (basicRadarChannel.m:36)
-        const double base = act ? baseCycles[i] : 0.0;
-        auto load = [&](int n) -> float2 {
-            if (!act) return make_float2(0.f, 0.f);
-            return target_sample(p, i, n0 + n, n0, base, a);
-        };
-        float2 v[16];
-        block_fft<R1, R2, -1, true>(v, fftbuf, 1, tf, p.tw, load);
-        if (act) {
-#pragma unroll
-            for (int d = 0; d < 16; ++d) {
-                const int bin = tf + NT * d;
-                int k = -1;
-                if (bin < p.nSc - half) k = bin + half;
-                else if (bin >= NF - half) k = bin - (NF - half);
-                if (k >= 0) Wf[(size_t)i * p.nSc + k] = v[d];
-            }
-        }
+    float2 v[16];
+    if (q < p.nTgt) {
+        for (int i = threadIdx.x; i < p.nAnts; i += blockDim.x)
+            steerS[i] = p.steerInline ? p.steerTab[q * p.nAnts + i] : p.steer[q * p.nAnts + i];   // a_t == a_r (:36)
         __syncthreads();
+        const double c = p.fdTs[q] * (double)n0;
+        const double base = c - floor(c);
+        auto load = [&](int n) -> float2 { return target_sample(p, q, n0 + n, n0, base, steerS); };
+        block_fft<R1, R2, -1, true>(v, fftbuf, 1, tf, p.tw, load);
+    } else {
+        const float2* __restrict__ z = p.noise + (long long)(q - p.nTgt) * p.T;
+        auto load = [&](int n) -> float2 {
+            const long long nn = n0 + n;
+            if (nn >= p.T) return make_float2(0.f, 0.f);
+            return mixed_noise(p, z, nn);
+        };
+        block_fft<R1, R2, -1, true>(v, fftbuf, 1, tf, p.tw, load);
     }
-    // ---- antennas: combine, add noise, phase ramp, store ----
-    const float rampStep = (float)(cp - off) / (float)NF;  // cycles per subcarrier index
-    for (int r0 = 0; r0 < p.nAnts; r0 += groups) {
-        const int r = r0 + grp;
-        const bool act = r < p.nAnts;
-        float2 v[16];
-        if (p.noiseMode == 1) {
-            const float2* __restrict__ z = p.noise + (long long)(act ? r : 0) * p.T;
-            auto load = [&](int n) -> float2 {
-                const long long nn = n0 + n;
-                if (!act || nn >= p.T) return make_float2(0.f, 0.f);
-                return mixed_noise(p, z, nn);
-            };
-            block_fft<R1, R2, -1, true>(v, fftbuf, 1, tf, p.tw, load);
-        }
-        if (act) {
+    float2* __restrict__ Wq = W + ((size_t)q * p.nSymRx + s) * p.nSc;
 #pragma unroll
-            for (int d = 0; d < 16; ++d) {
-                const int bin = tf + NT * d;
-                int k = -1;
-                if (bin < p.nSc - half) k = bin + half;
-                else if (bin >= NF - half) k = bin - (NF - half);
-                if (k < 0) continue;
-                float2 acc = make_float2(0.f, 0.f);
-                for (int i = 0; i < p.nTgt; ++i) {
-                    const float2 w = Wf[(size_t)i * p.nSc + k];
-                    const float2 ar = steerS[i * p.nAnts + r];
-                    acc.x += w.x * ar.x - w.y * ar.y;
-                    acc.y += w.x * ar.y + w.y * ar.x;
-                }
-                if (p.noiseMode == 1) {
-                    acc.x += p.noiseSigma * v[d].x;
-                    acc.y += p.noiseSigma * v[d].y;
-                } else if (p.noiseMode == 2) {
-                    const uint4 ctr = make_uint4((unsigned)k, (unsigned)s, (unsigned)r, 0x15ACu);
-                    const uint4 rn = philox4x32(ctr, make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
-                    const float2 g = gauss_pair(rn.x, rn.y);
-                    const float sc = p.noiseSigma * sqrtf((float)NF);
-                    acc.x += sc * g.x;
-                    acc.y += sc * g.y;
-                }
-                // undo the early FFT window start: exp(+2 pi j kk (cp - off)/Nfft), kk = k - nSc/2
-                float sn, cs;
-                sincospif(2.0f * rampStep * (float)(k - half), &sn, &cs);
-                p.out[((long long)r * p.nSymOut + s) * p.nSc + k] = cmul(acc, make_float2(cs, sn));
-            }
-        }
-        if (p.noiseMode == 1) __syncthreads();
+    for (int d = 0; d < 16; ++d) {
+        const int bin = tf + NT * d;
+        int k = -1;
+        if (bin < p.nSc - half) k = bin + half;
+        else if (bin >= NF - half) k = bin - (NF - half);
+        if (k >= 0) Wq[k] = v[d];
     }
+}
+
+// Pass 2: echoGrid[k,s,r] = ramp_s[k] * ( sum_i a_i[r] W_i[k,s] + noise ), zero beyond the demodulated symbols
+__global__ void __launch_bounds__(256)
+echo_combine_kernel(const EchoDev p, const float2* __restrict__ W, int NF) {
+    __shared__ float2 steerS[kEchoInlineSteer];
+    for (int i = threadIdx.x; i < p.nAnts * p.nTgt && i < kEchoInlineSteer; i += blockDim.x)
+        steerS[i] = p.steerInline ? p.steerTab[i] : p.steer[i];
+    __syncthreads();
+    const int s = blockIdx.y, r = blockIdx.z;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.nSc) return;
+    float2* __restrict__ o = p.out + ((long long)r * p.nSymOut + s) * p.nSc + k;
+    if (s >= p.nSymRx) {  // zero padding up to txDimension(2) (monoStaticSensing.m:19-21)
+        *o = make_float2(0.f, 0.f);
+        return;
+    }
+    const int cp = p.cpTab[s % p.symPer];
+    const int off = cp / 2, half = p.nSc / 2;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int i = 0; i < p.nTgt; ++i) {
+        const float2 w = W[((size_t)i * p.nSymRx + s) * p.nSc + k];
+        const float2 ar = p.steerInline || p.nAnts * p.nTgt <= kEchoInlineSteer ? steerS[i * p.nAnts + r] : p.steer[i * p.nAnts + r];
+        acc.x += w.x * ar.x - w.y * ar.y;
+        acc.y += w.x * ar.y + w.y * ar.x;
+    }
+    if (p.noiseMode == 1) {
+        const float2 z = W[((size_t)(p.nTgt + r) * p.nSymRx + s) * p.nSc + k];
+        acc.x += p.noiseSigma * z.x;
+        acc.y += p.noiseSigma * z.y;
+    } else if (p.noiseMode == 2) {
+        const uint4 ctr = make_uint4((unsigned)k, (unsigned)s, (unsigned)r, 0x15ACu);
+        const uint4 rn = philox4x32(ctr, make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
+        const float2 g = gauss_pair(rn.x, rn.y);
+        const float sc = p.noiseSigma * sqrtf((float)NF);
+        acc.x += sc * g.x;
+        acc.y += sc * g.y;
+    }
+    // undo the early FFT window start: exp(+2 pi j kk (cp - off)/Nfft), kk = k - nSc/2
+    const float rampStep = (float)(cp - off) / (float)NF;  // cycles per subcarrier index
+    float sn, cs;
+    sincospif(2.0f * rampStep * (float)(k - half), &sn, &cs);
+    *o = cmul(acc, make_float2(cs, sn));
 }
 
 // basicRadarChannel alone: rxWaveform [T x nAnts]
@@ -324,15 +308,14 @@ int radar_channel_run(Ctx* ctx, const EchoConfig& c, const float2* tx, const flo
 }
 
 template <int R1, int R2>
-static cudaError_t launch_echo(const EchoDev& d, cudaStream_t st) {
+static cudaError_t launch_echo(const EchoDev& d, float2* W, cudaStream_t st) {
     using G = FftGeom<R1, R2, true>;
-    const int groups = G::NT >= 256 ? 1 : 256 / G::NT;
-    const int threads = G::NT * groups;
-    const size_t smem = sizeof(float2) * ((size_t)groups * G::kElems + (size_t)d.nTgt * d.nSc + (size_t)d.nAnts * d.nTgt);
-    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;  // too many LoS targets for one pass
-    auto k = echo_demod_kernel<R1, R2>;
+    const size_t smem = sizeof(float2) * ((size_t)G::kElems + d.nAnts);
+    auto k = echo_stream_fft_kernel<R1, R2>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<d.nSymOut, threads, smem, st>>>(d);
+    const int streams = d.nTgt + (d.noiseMode == 1 ? d.nAnts : 0);
+    if (d.nSymRx > 0 && streams > 0) k<<<dim3(d.nSymRx, streams), G::NT, smem, st>>>(d, W);
+    echo_combine_kernel<<<dim3((d.nSc + 255) / 256, d.nSymOut, d.nAnts), 256, 0, st>>>(d, W, G::N);
     return cudaGetLastError();
 }
 
@@ -375,18 +358,21 @@ int mono_static_sensing_run(Ctx* ctx, const EchoConfig& c, const float2* tx, con
     d.nSc = c.nSc;
     d.out = echoGrid;
     ctx_fft_tw(ctx, c.nfft, &d.tw.tw1, &d.tw.tw2);
+    void* dW = nullptr;   // stream spectra between the two passes
+    const size_t streams = (size_t)d.nTgt + (noiseMode == 1 ? d.nAnts : 0);
+    if ((s = ctx_scratch(ctx, 17, sizeof(float2) * (streams ? streams : 1) * (nSymRx ? nSymRx : 1) * c.nSc, &dW))) return s;
     cudaError_t e;
     const int pr = prof_begin(ctx, kProfEcho, st);
     switch (c.nfft) {
-        case 128: e = launch_echo<1, 8>(d, st); break;
-        case 256: e = launch_echo<1, 16>(d, st); break;
-        case 512: e = launch_echo<2, 16>(d, st); break;
-        case 1024: e = launch_echo<4, 16>(d, st); break;
-        case 2048: e = launch_echo<8, 16>(d, st); break;
-        default: e = launch_echo<16, 16>(d, st); break;
+        case 128: e = launch_echo<1, 8>(d, (float2*)dW, st); break;
+        case 256: e = launch_echo<1, 16>(d, (float2*)dW, st); break;
+        case 512: e = launch_echo<2, 16>(d, (float2*)dW, st); break;
+        case 1024: e = launch_echo<4, 16>(d, (float2*)dW, st); break;
+        case 2048: e = launch_echo<8, 16>(d, (float2*)dW, st); break;
+        default: e = launch_echo<16, 16>(d, (float2*)dW, st); break;
     }
     prof_end(ctx, pr, st);
-    count_launches(ctx, 1);
+    count_launches(ctx, 2);
     ISAC_CUDA_CHECK(ctx, e);
     return kOk;
 }
