@@ -148,6 +148,7 @@ def _declare(lib):
         "isac_prg_precode_batch_dev": ([vp, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp, vp], C.c_int),
         "isac_cdl_create": ([vp, P(CdlConfig), P(vp)], C.c_int),
         "isac_cdl_destroy": ([vp], C.c_int),
+        "isac_cdl_set_kernel": ([vp, i32], C.c_int),
         "isac_cdl_get_rays": ([vp, P(i32), P(i32), P(i32), P(i32), vp, vp, vp, vp], C.c_int),
         "isac_cdl_generate_dev": ([vp, i32, f64, i32, vp, f64, vp], C.c_int),
         "isac_radar_channel_dev": ([vp, P(EchoConfig), vp, vp, i32, C.c_uint64, vp], C.c_int),

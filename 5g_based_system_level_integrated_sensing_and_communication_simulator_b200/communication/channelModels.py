@@ -33,6 +33,10 @@ class CDLChannel:
         self.nTx = int(TransmitAntennaArraySize[0] * TransmitAntennaArraySize[1] * TransmitAntennaArraySize[2])
         self.nRx = int(ReceiveAntennaArraySize[0] * ReceiveAntennaArraySize[1] * ReceiveAntennaArraySize[2])
 
+    def setKernel(self, legacy_mma):
+        """False (default): tcgen05/TMEM response kernel; True: legacy mma.sync kernel (isac_cdl_set_kernel)."""
+        self._lib.check(self.ctx.lib.isac_cdl_set_kernel(self.handle, int(bool(legacy_mma))), self.ctx.handle)
+
     def rays(self):
         import numpy as np
         C, lib = self._C, self.ctx.lib

@@ -1058,6 +1058,12 @@ int isac_cdl_get_rays(const isac_cdl_channel* ch, int32_t* nCl, int32_t* nRays, 
     return ISAC_OK;
 }
 
+int isac_cdl_set_kernel(isac_cdl_channel* ch, int32_t legacyMma) {
+    if (!ch) return ISAC_ERR_INVALID_ARG;
+    ch->rays.legacyMma = legacyMma != 0;
+    return ISAC_OK;
+}
+
 int isac_cdl_generate_batch_dev(isac_cdl_channel* const* ch, int32_t n, int32_t K, double scsHz, int32_t L, const double* symTime,
                                 const double* t0, void* H) {
     if (!ch || n < 1 || !H || !symTime || !t0) return ISAC_ERR_INVALID_ARG;

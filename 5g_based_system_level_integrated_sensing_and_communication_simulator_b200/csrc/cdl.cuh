@@ -23,6 +23,7 @@ struct CdlConfig {
 struct CdlRays {
     int nCl = 0, nRay = 0, nRx = 0, nTx = 0;
     bool los = false;
+    bool legacyMma = false;                    // true: mma.sync kernel instead of the tcgen05 one (isac_cdl_set_kernel)
     std::vector<double> tau;                   // [nCl] seconds
     std::vector<double> power;                 // [nCl] linear (after normalisation, NLOS part of cluster 1 for CDL-D)
     std::vector<double> nu;                    // [nCl*nRay (+1 LOS)] Doppler of each ray (Hz)

@@ -318,6 +318,9 @@ int isac_cdl_get_rays(const isac_cdl_channel* ch, int32_t* nClusters, int32_t* n
 int isac_cdl_generate_dev(isac_cdl_channel* ch, int32_t K, double scsHz, int32_t L, const double* symTime, double t0,
                           void* H);
 /* n channels (all with the same nRx x nTx), outputs stacked: H [K x L x nRx x nTx x n], start times t0[n] */
+/* Response kernel of the channel: 0 (default) tcgen05.mma kind::tf32 with TMEM accumulators, 1 legacy mma.sync.
+ * Same 3xTF32 arithmetic; a batch uses the setting of its first channel. */
+int isac_cdl_set_kernel(isac_cdl_channel* ch, int32_t legacyMma);
 int isac_cdl_generate_batch_dev(isac_cdl_channel* const* ch, int32_t n, int32_t K, double scsHz, int32_t L,
                                 const double* symTime, const double* t0, void* H);
 

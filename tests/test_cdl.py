@@ -44,6 +44,11 @@ def test_cdl_rays_and_frequency_response(gpu, prof, name, tx, rx):
     err = np.abs(H - Href).max() / np.sqrt(np.mean(np.abs(Href) ** 2))
     print(name, "H err / rms", err, "mean |H|^2", np.mean(np.abs(Href) ** 2))
     assert err <= 1e-5
+    ch.setKernel(True)   # legacy mma.sync kernel: same 3xTF32 arithmetic as the default tcgen05 kernel
+    H2 = ch.generate(K, scs, t - 0.0135, t0=0.0135).cpu().numpy().transpose(3, 2, 1, 0)
+    err2 = np.abs(H2 - Href).max() / np.sqrt(np.mean(np.abs(Href) ** 2))
+    print(name, "legacy kernel H err / rms", err2, " tcgen05 vs legacy", np.abs(H2 - H).max())
+    assert err2 <= 1e-5
     ch.close()
 
 
