@@ -354,7 +354,7 @@ cdl_response_kernel(const float2* __restrict__ Call, const CdlBatch bt, int nCl,
 // ------------------------------------------------------------------------------------------
 // K11 on the 5th-generation tensor cores: tcgen05.mma kind::tf32, operands in shared memory, accumulators in TMEM.
 //
-// One CTA per 128 (subcarriers) x 128 (columns j) tile of one channel.  With E = Er + j Ei [128 x nCl] and
+// One CTA per 128-subcarrier tile of one channel; it walks the 128-column tiles j of H (E is built once).  With E = Er + j Ei [128 x nCl] and
 // C = Cr + j Ci [nCl x 128]:   Re H = Er Cr - Ei Ci,   Im H = Ei Cr + Er Ci   -> four real products per k-step of 8
 // clusters, each in the 3xTF32 form (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM, ~2^-21 relative), the minus
 // sign through the instruction descriptor's a_negate bit.  36 MMAs of 128x128x8 per tile (~1.2 us of tensor time),
@@ -401,11 +401,10 @@ cdl_response_umma_kernel(const float2* __restrict__ Call, const CdlBatch bt, int
     __shared__ unsigned tmemBase;
     unsigned char* sm = (unsigned char*)(((size_t)umma_raw + 1023) & ~(size_t)1023);
     // tiles: 0 Er_hi, 1 Er_lo, 2 Ei_hi, 3 Ei_lo, 4 Cr_hi, 5 Cr_lo, 6 Ci_hi, 7 Ci_lo
-    const float2* __restrict__ C = Call + (size_t)blockIdx.z * nCl * J;
-    const double* __restrict__ tau = bt.tau[blockIdx.z];
-    float2* __restrict__ H = Hall + (size_t)blockIdx.z * K * J;
+    const float2* __restrict__ C = Call + (size_t)blockIdx.y * nCl * J;
+    const double* __restrict__ tau = bt.tau[blockIdx.y];
+    float2* __restrict__ H = Hall + (size_t)blockIdx.y * K * J;
     const int k0 = blockIdx.x * kUmmaM;
-    const long long j0 = (long long)blockIdx.y * kUmmaN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0) {   // TMEM: 256 columns (Re | Im accumulators, 128 fp32 columns each)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr_u32(&tmemBase)), "r"(256u)
@@ -416,16 +415,14 @@ cdl_response_umma_kernel(const float2* __restrict__ Call, const CdlBatch bt, int
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(&mmaBar)), "r"(1u));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // operands: E[k0+row, n] = exp(-2 pi j f tau_n) and C[n, j0+col], split into TF32 hi/lo, zero beyond nCl / K / J
+    // E[k0+row, n] = exp(-2 pi j f tau_n), once per CTA (shared by all column tiles): the phase f*tau is reduced to
+    // [0,1) in float64, the sine/cosine of the reduced phase are float32 (as accurate as the fp32 operand they feed)
     for (int i = threadIdx.x; i < kCdlMaxCl * kUmmaM; i += blockDim.x) {
         const int n = i / kUmmaM, row = i % kUmmaM;
         float er = 0.f, ei = 0.f;
         if (n < nCl) {
-            const double f = ((double)(k0 + row) - (double)(K / 2)) * scs;
-            double sn, cs;
-            sincospi(-2.0 * f * tau[n], &sn, &cs);
-            er = (float)cs;
-            ei = (float)sn;
+            const double c = ((double)(k0 + row) - (double)(K / 2)) * scs * tau[n];
+            sincospif(-2.0f * (float)(c - floor(c)), &ei, &er);
         }
         unsigned h, l;
         const int o = (n >> 3) * 4096 + umma_off(row, n & 7);
@@ -436,103 +433,116 @@ cdl_response_umma_kernel(const float2* __restrict__ Call, const CdlBatch bt, int
         *(unsigned*)(sm + 2 * kUmmaTileBytes + o) = h;
         *(unsigned*)(sm + 3 * kUmmaTileBytes + o) = l;
     }
-    for (int i = threadIdx.x; i < kCdlMaxCl * kUmmaN; i += blockDim.x) {
-        const int n = i / kUmmaN, col = i % kUmmaN;
-        const long long j = j0 + col;
-        const float2 c = (n < nCl && j < J) ? __ldg(C + (size_t)n * J + j) : make_float2(0.f, 0.f);
-        unsigned h, l;
-        const int o = (n >> 3) * 4096 + umma_off(col, n & 7);
-        split_tf32(c.x, h, l);
-        *(unsigned*)(sm + 4 * kUmmaTileBytes + o) = h;
-        *(unsigned*)(sm + 5 * kUmmaTileBytes + o) = l;
-        split_tf32(c.y, h, l);
-        *(unsigned*)(sm + 6 * kUmmaTileBytes + o) = h;
-        *(unsigned*)(sm + 7 * kUmmaTileBytes + o) = l;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned tmem = tmemBase;
-    if (threadIdx.x == 0) {
-        // instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, K-major both, N>>3 at [17,23), M>>4 at [24,29)
-        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kUmmaN >> 3) << 17) | ((unsigned)(kUmmaM >> 4) << 24);
-        const unsigned idescNegA = idesc | (1u << 13);
-        const unsigned base = smem_addr_u32(sm);
-        const int ksteps = (nCl + 7) / 8;
-        for (int s = 0; s < ksteps; ++s) {
-            unsigned long long d[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) d[q] = umma_smem_desc(base + q * kUmmaTileBytes + s * 4096);
-            const unsigned acc = s > 0;
-            // Re (columns 0..127): Er*Cr - Ei*Ci
-            umma_tf32(tmem, d[1], d[4], idesc, acc);          // Er_lo * Cr_hi
-            umma_tf32(tmem, d[0], d[5], idesc, 1u);           // Er_hi * Cr_lo
-            umma_tf32(tmem, d[0], d[4], idesc, 1u);           // Er_hi * Cr_hi
-            umma_tf32(tmem, d[3], d[6], idescNegA, 1u);       // -Ei_lo * Ci_hi
-            umma_tf32(tmem, d[2], d[7], idescNegA, 1u);
-            umma_tf32(tmem, d[2], d[6], idescNegA, 1u);
-            // Im (columns 128..255): Ei*Cr + Er*Ci
-            umma_tf32(tmem + 128, d[3], d[4], idesc, acc);
-            umma_tf32(tmem + 128, d[2], d[5], idesc, 1u);
-            umma_tf32(tmem + 128, d[2], d[4], idesc, 1u);
-            umma_tf32(tmem + 128, d[1], d[6], idesc, 1u);
-            umma_tf32(tmem + 128, d[0], d[7], idesc, 1u);
-            umma_tf32(tmem + 128, d[0], d[6], idesc, 1u);
-        }
-        // arrives on the barrier when every MMA above has completed (implies tcgen05.fence::before_thread_sync)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr_u32(&mmaBar))
-                     : "memory");
-    }
-    {   // everyone waits for the accumulators
-        const unsigned bar = smem_addr_u32(&mmaBar);
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "WAIT_MMA:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-            "@p bra DONE_MMA;\n\t"
-            "bra WAIT_MMA;\n\t"
-            "DONE_MMA:\n\t"
-            "}\n" ::"r"(bar), "r"(0u)
-            : "memory");
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // epilogue: warp w drains TMEM lanes 32*(w%4).. (rows = subcarriers) and the column half w/4; thread = one row
-    const int row = (warp & 3) * 32 + lane, k = k0 + row;
+    // instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, K-major both, N>>3 at [17,23), M>>4 at [24,29)
+    const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kUmmaN >> 3) << 17) | ((unsigned)(kUmmaM >> 4) << 24);
+    const unsigned idescNegA = idesc | (1u << 13);
+    const unsigned base = smem_addr_u32(sm), bar = smem_addr_u32(&mmaBar);
+    const int ksteps = (nCl + 7) / 8;
+    const int row = (warp & 3) * 32 + lane, k = k0 + row;   // epilogue: warp w drains TMEM lanes 32*(w%4).., column half w/4
     const int colHalf = (warp >> 2) * 64;
+    const int nTiles = (int)((J + kUmmaN - 1) / kUmmaN);
+    constexpr int kCPer = kCdlMaxCl * kUmmaN / 256;   // C elements per thread and tile (12)
+    float2 cnext[kCPer];
+    auto fetch_c = [&](long long j0) {   // global loads of one column tile of C (zero beyond nCl / J)
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-        unsigned re[32], im[32];
-        const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(colHalf + c0);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-            "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(re[0]), "=r"(re[1]), "=r"(re[2]), "=r"(re[3]), "=r"(re[4]), "=r"(re[5]), "=r"(re[6]), "=r"(re[7]), "=r"(re[8]),
-              "=r"(re[9]), "=r"(re[10]), "=r"(re[11]), "=r"(re[12]), "=r"(re[13]), "=r"(re[14]), "=r"(re[15]), "=r"(re[16]),
-              "=r"(re[17]), "=r"(re[18]), "=r"(re[19]), "=r"(re[20]), "=r"(re[21]), "=r"(re[22]), "=r"(re[23]), "=r"(re[24]),
-              "=r"(re[25]), "=r"(re[26]), "=r"(re[27]), "=r"(re[28]), "=r"(re[29]), "=r"(re[30]), "=r"(re[31])
-            : "r"(taddr));
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-            "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(im[0]), "=r"(im[1]), "=r"(im[2]), "=r"(im[3]), "=r"(im[4]), "=r"(im[5]), "=r"(im[6]), "=r"(im[7]), "=r"(im[8]),
-              "=r"(im[9]), "=r"(im[10]), "=r"(im[11]), "=r"(im[12]), "=r"(im[13]), "=r"(im[14]), "=r"(im[15]), "=r"(im[16]),
-              "=r"(im[17]), "=r"(im[18]), "=r"(im[19]), "=r"(im[20]), "=r"(im[21]), "=r"(im[22]), "=r"(im[23]), "=r"(im[24]),
-              "=r"(im[25]), "=r"(im[26]), "=r"(im[27]), "=r"(im[28]), "=r"(im[29]), "=r"(im[30]), "=r"(im[31])
-            : "r"(taddr + 128u));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (k < K) {
+        for (int q = 0; q < kCPer; ++q) {
+            const int i = threadIdx.x + q * 256, n = i / kUmmaN, col = i % kUmmaN;
+            const long long j = j0 + col;
+            cnext[q] = (n < nCl && j < J) ? __ldg(C + (size_t)n * J + j) : make_float2(0.f, 0.f);
+        }
+    };
+    fetch_c(0);
+    for (int tile = 0; tile < nTiles; ++tile) {
+        const long long j0 = (long long)tile * kUmmaN;
+        // C tile split into TF32 hi/lo; the previous tile's MMAs have completed (barrier wait below), its loads were
+        // issued before that wait so their latency hides behind the tensor work
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const long long j = j0 + colHalf + c0 + q;
-                if (j < J) H[j * K + k] = make_float2(__uint_as_float(re[q]), __uint_as_float(im[q]));   // lanes: consecutive k
+        for (int q = 0; q < kCPer; ++q) {
+            const int i = threadIdx.x + q * 256, n = i / kUmmaN, col = i % kUmmaN;
+            unsigned h, l;
+            const int o = (n >> 3) * 4096 + umma_off(col, n & 7);
+            split_tf32(cnext[q].x, h, l);
+            *(unsigned*)(sm + 4 * kUmmaTileBytes + o) = h;
+            *(unsigned*)(sm + 5 * kUmmaTileBytes + o) = l;
+            split_tf32(cnext[q].y, h, l);
+            *(unsigned*)(sm + 6 * kUmmaTileBytes + o) = h;
+            *(unsigned*)(sm + 7 * kUmmaTileBytes + o) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();   // also: every warp has drained the previous tile's accumulators
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned tmem = tmemBase;
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < ksteps; ++s) {
+                unsigned long long d[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d[q] = umma_smem_desc(base + q * kUmmaTileBytes + s * 4096);
+                const unsigned acc = s > 0;
+                // Re (columns 0..127): Er*Cr - Ei*Ci
+                umma_tf32(tmem, d[1], d[4], idesc, acc);          // Er_lo * Cr_hi
+                umma_tf32(tmem, d[0], d[5], idesc, 1u);           // Er_hi * Cr_lo
+                umma_tf32(tmem, d[0], d[4], idesc, 1u);           // Er_hi * Cr_hi
+                umma_tf32(tmem, d[3], d[6], idescNegA, 1u);       // -Ei_lo * Ci_hi
+                umma_tf32(tmem, d[2], d[7], idescNegA, 1u);
+                umma_tf32(tmem, d[2], d[6], idescNegA, 1u);
+                // Im (columns 128..255): Ei*Cr + Er*Ci
+                umma_tf32(tmem + 128, d[3], d[4], idesc, acc);
+                umma_tf32(tmem + 128, d[2], d[5], idesc, 1u);
+                umma_tf32(tmem + 128, d[2], d[4], idesc, 1u);
+                umma_tf32(tmem + 128, d[1], d[6], idesc, 1u);
+                umma_tf32(tmem + 128, d[0], d[7], idesc, 1u);
+                umma_tf32(tmem + 128, d[0], d[6], idesc, 1u);
+            }
+            // arrives on the barrier when every MMA above has completed (implies tcgen05.fence::before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+        }
+        if (tile + 1 < nTiles) fetch_c(j0 + kUmmaN);
+        {   // everyone waits for the accumulators (phase parity alternates per tile)
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "WAIT_MMA:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra DONE_MMA;\n\t"
+                "bra WAIT_MMA;\n\t"
+                "DONE_MMA:\n\t"
+                "}\n" ::"r"(bar), "r"((unsigned)(tile & 1))
+                : "memory");
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            unsigned re[32], im[32];
+            const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(colHalf + c0);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+                "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(re[0]), "=r"(re[1]), "=r"(re[2]), "=r"(re[3]), "=r"(re[4]), "=r"(re[5]), "=r"(re[6]), "=r"(re[7]), "=r"(re[8]),
+                  "=r"(re[9]), "=r"(re[10]), "=r"(re[11]), "=r"(re[12]), "=r"(re[13]), "=r"(re[14]), "=r"(re[15]), "=r"(re[16]),
+                  "=r"(re[17]), "=r"(re[18]), "=r"(re[19]), "=r"(re[20]), "=r"(re[21]), "=r"(re[22]), "=r"(re[23]), "=r"(re[24]),
+                  "=r"(re[25]), "=r"(re[26]), "=r"(re[27]), "=r"(re[28]), "=r"(re[29]), "=r"(re[30]), "=r"(re[31])
+                : "r"(taddr));
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+                "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(im[0]), "=r"(im[1]), "=r"(im[2]), "=r"(im[3]), "=r"(im[4]), "=r"(im[5]), "=r"(im[6]), "=r"(im[7]), "=r"(im[8]),
+                  "=r"(im[9]), "=r"(im[10]), "=r"(im[11]), "=r"(im[12]), "=r"(im[13]), "=r"(im[14]), "=r"(im[15]), "=r"(im[16]),
+                  "=r"(im[17]), "=r"(im[18]), "=r"(im[19]), "=r"(im[20]), "=r"(im[21]), "=r"(im[22]), "=r"(im[23]), "=r"(im[24]),
+                  "=r"(im[25]), "=r"(im[26]), "=r"(im[27]), "=r"(im[28]), "=r"(im[29]), "=r"(im[30]), "=r"(im[31])
+                : "r"(taddr + 128u));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (k < K) {
+                float2* __restrict__ hp = H + (j0 + colHalf + c0) * K + k;   // lanes: consecutive subcarriers
+#pragma unroll
+                for (int q = 0; q < 32; ++q, hp += K)
+                    if (j0 + colHalf + c0 + q < J) *hp = make_float2(__uint_as_float(re[q]), __uint_as_float(im[q]));
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(256u) : "memory");
 }
 
 // upload the ray tables once (they do not change between calls)
@@ -599,7 +609,7 @@ int cdl_generate_batch(Ctx* ctx, CdlRays* const* rays, int n, int K, double scsH
         cdl_cluster_kernel<<<g1, 128, 0, st>>>(bt, r0.nRay, losRay, r0.nCl, r0.nRx, r0.nTx, L, tl, (float2*)dC);
         dim3 grid((K + kCdlTK - 1) / kCdlTK, (unsigned)((J + kCdlTJ - 1) / kCdlTJ), nb);
         if (!legacyMma) {   // tcgen05 / TMEM path
-            dim3 gu((K + kUmmaM - 1) / kUmmaM, (unsigned)((J + kUmmaN - 1) / kUmmaN), nb);
+            dim3 gu((K + kUmmaM - 1) / kUmmaM, nb);   // one CTA per (128-subcarrier tile, channel), looping over the column tiles
             cudaFuncSetAttribute(cdl_response_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmemBytes);
             cdl_response_umma_kernel<<<gu, 256, kUmmaSmemBytes, st>>>((const float2*)dC, bt, r0.nCl, K, J, scsHz, H + (size_t)i0 * K * J);
         } else {
