@@ -183,31 +183,53 @@ struct CdlBatch {
 __global__ void __launch_bounds__(128)
 cdl_cluster_kernel(const CdlBatch bt, int nRay, int losRay, int nCl, int nRx, int nTx, int L, const CdlTimes tl,
                    float2* __restrict__ Call /*[batch][nCl][J]*/) {
-    __shared__ double2 ph[32];
-    __shared__ int rayIdx[32];
-    const int n = blockIdx.x, l = blockIdx.y, RT = nRx * nTx;
-    const double2* __restrict__ g = bt.g[blockIdx.z];
-    const double* __restrict__ nu = bt.nu[blockIdx.z];
-    float2* __restrict__ C = Call + (size_t)blockIdx.z * nCl * L * RT;
+    // one CTA per (cluster, channel): the (<= 21 rays) x (L symbols) phasors once, then each thread keeps one antenna
+    // pair's ray coefficients in flight while it sweeps its share of the symbols
+    __shared__ double2 ph[kCdlMaxSym][24];
+    __shared__ int rayIdx[24];
+    const int n = blockIdx.x, RT = nRx * nTx;
+    const double2* __restrict__ g = bt.g[blockIdx.y];
+    const double* __restrict__ nu = bt.nu[blockIdx.y];
+    float2* __restrict__ C = Call + (size_t)blockIdx.y * nCl * L * RT;
     const int cnt = nRay + ((n == 0 && losRay >= 0) ? 1 : 0);
-    if ((int)threadIdx.x < cnt) {
-        const int m = (int)threadIdx.x < nRay ? n * nRay + threadIdx.x : losRay;
+    for (int i = threadIdx.x; i < cnt * L; i += blockDim.x) {
+        const int q = i % cnt, l = i / cnt;
+        const int m = q < nRay ? n * nRay + q : losRay;
         double s, c;
-        sincospi(2.0 * nu[m] * (bt.t0[blockIdx.z] + tl.t[l]), &s, &c);
-        ph[threadIdx.x] = make_double2(c, s);
-        rayIdx[threadIdx.x] = m;
+        sincospi(2.0 * nu[m] * (bt.t0[blockIdx.y] + tl.t[l]), &s, &c);
+        ph[l][q] = make_double2(c, s);
+        if (l == 0) rayIdx[q] = m;
     }
     __syncthreads();
-    for (int us = threadIdx.x; us < RT; us += blockDim.x) {
+    // work item = (antenna pair us, symbol group): groups of symbols so that all 128 threads are busy when RT < 128
+    const int groups = RT >= (int)blockDim.x ? 1 : (int)blockDim.x / RT;
+    const int lper = (L + groups - 1) / groups;
+    for (int w = threadIdx.x; w < RT * groups; w += blockDim.x) {
+        const int us = w % RT, grp = w / RT;
         const int u = us / nTx, sx = us % nTx;
-        double re = 0.0, im = 0.0;
+        const int l0 = grp * lper, l1 = min(L, l0 + lper);
+        double re[kCdlMaxSym], im[kCdlMaxSym];
+#pragma unroll
+        for (int l = 0; l < kCdlMaxSym; ++l) re[l] = im[l] = 0.0;
         for (int q = 0; q < cnt; ++q) {
-            const double2 gv = g[(size_t)rayIdx[q] * RT + us], p = ph[q];
-            re += gv.x * p.x - gv.y * p.y;
-            im += gv.x * p.y + gv.y * p.x;
+            const double2 gv = g[(size_t)rayIdx[q] * RT + us];
+#pragma unroll
+            for (int d = 0; d < kCdlMaxSym; ++d) {
+                const int l = l0 + d;
+                if (d < lper && l < l1) {
+                    const double2 p = ph[l][q];
+                    re[d] = fma(gv.x, p.x, fma(-gv.y, p.y, re[d]));
+                    im[d] = fma(gv.x, p.y, fma(gv.y, p.x, im[d]));
+                }
+            }
         }
         // MATLAB order of H(k,l,u,s): j = l + L*(u + nRx*s)
-        C[(size_t)n * L * RT + l + (size_t)L * (u + (size_t)nRx * sx)] = make_float2((float)re, (float)im);
+#pragma unroll
+        for (int d = 0; d < kCdlMaxSym; ++d) {
+            const int l = l0 + d;
+            if (d < lper && l < l1)
+                C[(size_t)n * L * RT + l + (size_t)L * (u + (size_t)nRx * sx)] = make_float2((float)re[d], (float)im[d]);
+        }
     }
 }
 
@@ -605,7 +627,7 @@ int cdl_generate_batch(Ctx* ctx, CdlRays* const* rays, int n, int K, double scsH
             bt.t0[i] = t0[i0 + i];
         }
         const int pr = prof_begin(ctx, kProfCdl, st);
-        dim3 g1(r0.nCl, L, nb);
+        dim3 g1(r0.nCl, nb);
         cdl_cluster_kernel<<<g1, 128, 0, st>>>(bt, r0.nRay, losRay, r0.nCl, r0.nRx, r0.nTx, L, tl, (float2*)dC);
         dim3 grid((K + kCdlTK - 1) / kCdlTK, (unsigned)((J + kCdlTJ - 1) / kCdlTJ), nb);
         if (!legacyMma) {   // tcgen05 / TMEM path
