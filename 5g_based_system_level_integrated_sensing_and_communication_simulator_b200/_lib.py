@@ -108,6 +108,7 @@ def _declare(lib):
         "isac_rdm_plan_create": ([vp, P(RdmConfig), P(vp)], C.c_int),
         "isac_rdm_plan_destroy": ([vp], C.c_int),
         "isac_rdm_plan_info": ([vp, P(f64), P(i32), P(i32)], C.c_int),
+        "isac_rdm_plan_set_variant": ([vp, i32], C.c_int),
         "isac_rdm_cfar_dev": ([vp, vp, vp, i32, vp], C.c_int),
         "isac_cfar2d_dev": ([vp, vp, i32], C.c_int),
         "isac_rdm_get_detections": ([vp, i32, i32, vp, vp, vp], C.c_int),

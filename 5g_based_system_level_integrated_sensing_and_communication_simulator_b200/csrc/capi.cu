@@ -275,6 +275,12 @@ int isac_rdm_plan_info(const isac_rdm_plan* pl, double* alpha, int32_t* nTrain, 
     return ISAC_OK;
 }
 
+int isac_rdm_plan_set_variant(isac_rdm_plan* pl, int32_t variant) {
+    if (!pl || !pl->p || variant < 0 || variant > 3) return ISAC_ERR_INVALID_ARG;
+    pl->p->variant = variant;
+    return ISAC_OK;
+}
+
 int isac_rdm_cfar_dev(isac_rdm_plan* pl, const void* rx, const void* tx, int32_t batch, float* rdPower) {
     if (!pl || !pl->p) return ISAC_ERR_INVALID_ARG;
     Ctx* c = pl->p->ctx;

@@ -179,31 +179,221 @@ rdm_range_ifft_tma_kernel(const RdmDev p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel B: Doppler FFT + |.|^2
+// Kernel A'' (N = 4096): lean persistent range IFFT.  Same TMA staging as kernel A', but everything that is constant
+// across the columns a CTA walks lives in registers, shared memory or folds into immediates: the range window w1
+// (NJ registers per thread), the second-pass twiddles (shared memory), every shared-memory / twiddle / output offset
+// (one base register each), no per-column predicate (the stage tail [nSc, NJ*256) is zeroed once, w1 = 0 there; the
+// register rows j >= NJ are compile-time zeros), no per-column 64-bit division (out = inter + col * N), and one barrier
+// less per column (the "stage consumed" barrier of the next column also orders its first-pass stores after this
+// column's third-pass loads).  The output is the RAW unnormalised IFFT: the shifted Doppler-axis window w2, the
+// 1/sqrt(N) scale and the (-1)^s' Doppler centring all move into the Doppler kernel, where they cost one multiply per
+// output (a per-row power scale) and an output-index rotation by F/2.
+// NJ = ceil(nSc / 256): 13 for 273 PRB (nSc = 3276), 16 in general.
 // ------------------------------------------------------------------------------------------
-template <int R1, int R2>
-__global__ void __launch_bounds__(512)
-rdm_doppler_fft_kernel(const RdmDev p, const int RT, const float invF) {
+template <int NJ>
+__global__ void __launch_bounds__(256, 2)
+rdm_range4096_lean_kernel(const RdmDev p) {
+    constexpr int N = 4096, NT = 256, S1 = 257;  // FftGeom<16,16,true>: addr(k1, mid, lo) = k1*257 + mid*16 + lo
+    constexpr int NS = NJ * NT;                  // staged entries per column
+    extern __shared__ __align__(128) unsigned char smraw[];
+    float2* stageRx = reinterpret_cast<float2*>(smraw);
+    float2* stageTx = stageRx + NS;
+    float2* fftbuf = stageTx + NS;
+    float2* tw2s = fftbuf + 16 * S1;                        // [15][16]
+    float* w1s = reinterpret_cast<float*>(tw2s + 240);     // [NS], zero beyond nSc
+    __shared__ __align__(8) unsigned long long bar;
+    const int tf = threadIdx.x;
+    const int nSc = p.nSc;
+    const unsigned colBytes = (unsigned)nSc * sizeof(float2);
+    for (int n = nSc + tf; n < NS; n += NT) {
+        stageRx[n] = make_float2(0.f, 0.f);
+        stageTx[n] = make_float2(0.f, 0.f);
+    }
+    if (tf < 240) tw2s[tf] = __ldg(p.twR.tw2 + tf);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int n = tf + NT * j;
+        w1s[n] = (n < nSc) ? __ldg(p.win1 + n) : 0.f;
+    }
+    float2 tw1r[15];  // first-pass twiddles exp(+2 pi i tf k1 / N): constant across the columns this thread works on
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) tw1r[k1 - 1] = __ldg(p.twR.tw1 + (k1 - 1) * NT + tf);
+    const float* const w1 = w1s + tf;                            // + 256*j
+    const float2* const tw2 = tw2s + (tf & 15);                  // + (c-1)*16
+    float2* const f1 = fftbuf + tf;                                     // pass-1 stores: + k1*257
+    float2* const f2 = fftbuf + (tf >> 4) * S1 + (tf & 15);             // pass-2 loads/stores: + a*16
+    const float2* const f3 = fftbuf + (tf & 15) * S1 + (tf >> 4) * 16;  // pass-3 loads: + b
+    const float2* const sRx = stageRx + tf;
+    const float2* const sTx = stageTx + tf;
+    const int M = p.M, nSym = p.nSym, half = p.nSym / 2;
+    const int total = (int)p.totalCols, stride = (int)gridDim.x;
+    auto issue = [&](int col) {  // thread 0: fetch the rx and tx columns of `col`
+        const int sp = col % M, page = col / M;
+        int s = sp + half;
+        if (s >= nSym) s -= nSym;  // ifftshift on the symbol axis (fft2D.m:44)
+        const size_t off = ((size_t)page * nSym + s) * (size_t)nSc;
+        mbar_expect_tx(&bar, 2 * colBytes);
+        tma_load_1d(stageRx, p.rx + off, colBytes, &bar);
+        tma_load_1d(stageTx, p.tx + off, colBytes, &bar);
+    };
+    if (tf == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int col = blockIdx.x;
+    if (tf == 0 && col < total) issue(col);
+    unsigned parity = 0;
+    float2* __restrict__ out = p.inter + (size_t)col * N + tf;
+    const size_t outStride = (size_t)stride * N;
+    for (; col < total; col += stride, out += outStride) {
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        float2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            v[j] = (j < NJ) ? cscale(cmulc(sRx[NT * j], sTx[NT * j]), w1[NT * j])  // rx.*conj(tx).*rngWin (fft2D.m:37,43)
+                            : make_float2(0.f, 0.f);
+        __syncthreads();  // stage consumed by every thread (and the previous column's pass-3 loads are done)
+        if (tf == 0 && col + stride < total) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
+            issue(col + stride);
+        }
+        dft16<+1>(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], tw1r[k1 - 1]);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) f1[k1 * S1] = v[k1];
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 16; ++a) v[a] = f2[a * 16];
+        dft16<+1>(v);
+#pragma unroll
+        for (int c = 1; c < 16; ++c) v[c] = cmul(v[c], tw2[(c - 1) * 16]);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) f2[c * 16] = v[c];
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < 16; ++b) v[b] = f3[b];
+        dft16<+1>(v);
+#pragma unroll
+        for (int d = 0; d < 16; ++d) out[NT * d] = v[d];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel B' (F = 256): persistent Doppler FFT with bulk-copy staging.  One 256-thread CTA walks tiles of 16
+// consecutive range rows of one antenna page; the [M symbols x 16 rows] input tile of the NEXT tile is fetched from
+// the (L2-resident) range profiles by ONE 2-D tensor copy (cp.async.bulk.tensor, one mbarrier per buffer) while
+// the current tile's two radix-16 passes run -> no thread ever waits on a global load.  The exchange between the two
+// passes happens in place in the staged tile (each thread overwrites exactly the 16 entries it read), so two 32 KB
+// buffers per CTA suffice and 3 CTAs fit per SM.  Twiddles sit in shared memory.  Epilogue: |X|^2 times the per-row
+// scale w2[(n - N/2) mod N]^2 / (N F) (fft2D.m:44-46, :61), written at the Doppler index rotated by F/2 (fftshift).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <int NI>  // range size when known at compile time (every output offset becomes an immediate), else 0
+__global__ void __launch_bounds__(256, 3)
+rdm_doppler256_tma_kernel(const RdmDev p, const int nPages, const __grid_constant__ CUtensorMap interMap) {
+    constexpr int F = 256, RT = 16, TILE = F * RT;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    float2* buf0 = reinterpret_cast<float2*>(smraw);  // 2 x [256 symbols][16 rows]
+    float2* tws = buf0 + 2 * TILE;                    // [15][16]
+    __shared__ __align__(8) unsigned long long bar[2];
+    const int tid = threadIdx.x, nl = tid & 15, tf = tid >> 4;
+    const int M = p.M, nIFFT = NI > 0 ? NI : p.nIFFT;
+    const int tilesPerPage = nIFFT / RT;
+    const int total = nPages * tilesPerPage, stride = (int)gridDim.x;
+    if (tid < 240) {
+        float2 w = __ldg(p.twD.tw2 + tid);
+        tws[tid] = make_float2(w.x, -w.y);  // forward transform: conjugate table
+    }
+    const float2* const tw = tws + tf;  // + (c-1)*16
+    const int nA = (M - tf + 15) >> 4;  // valid first-pass inputs: a*16 + tf < M
+    auto issue = [&](int tile, int s) {  // thread 0: one 2-D tensor copy [M symbols x 16 rows] -> buffer s
+        const int page = tile / tilesPerPage, row0 = (tile - page * tilesPerPage) * RT;
+        mbar_expect_tx(&bar[s], (unsigned)M * RT * (unsigned)sizeof(float2));
+        tma_load_2d(buf0 + s * TILE, &interMap, row0, page * M, &bar[s]);
+    };
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < total) issue(tile, 0);
+    unsigned phase = 0;  // bit s = parity to wait for on bar[s]
+    for (int i = 0; tile < total; tile += stride, ++i) {
+        const int s = i & 1;
+        float2* const buf = buf0 + s * TILE + tf * RT + nl;        // pass A: + a*256 (symbol a*16 + tf)
+        const float2* const bufB = buf0 + s * TILE + tf * TILE / 16 + nl;  // pass B: + b*16   (entry tf*16 + b)
+        const int page = tile / tilesPerPage, n = (tile - page * tilesPerPage) * RT + nl;
+        const float sc = __ldg(p.win2 + n);  // per-row power scale (see rdm_plan_create)
+        mbar_wait(&bar[s], (phase >> s) & 1u);
+        phase ^= 1u << s;
+        float2 v[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a) v[a] = (a < nA) ? buf[a * TILE / 16] : make_float2(0.f, 0.f);
+        dft16<-1>(v);
+#pragma unroll
+        for (int c = 1; c < 16; ++c) v[c] = cmul(v[c], tw[(c - 1) * 16]);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) buf[c * TILE / 16] = v[c];
+        __syncthreads();  // exchange complete; every thread is also past its pass-B loads of the previous tile
+        if (tid == 0 && tile + stride < total) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses before async writes
+            issue(tile + stride, s ^ 1);
+        }
+#pragma unroll
+        for (int b = 0; b < 16; ++b) v[b] = bufB[b * RT];
+        dft16<-1>(v);
+        float* __restrict__ out = p.pow + (size_t)page * F * nIFFT + n;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+            const int q = tf + 16 * ((d + 8) & 15);  // Doppler-axis fftshift (fft2D.m:46) as an output rotation
+            out[(size_t)q * nIFFT] = (v[d].x * v[d].x + v[d].y * v[d].y) * sc;  // abs(rdm).^2 (fft2D.m:61)
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel B: Doppler FFT + |.|^2
+// RT (rows interleaved per CTA) and, for the hot shapes, the range size NI are compile-time so that every
+// shared-memory and global offset is an immediate.  RAW: the input is the raw IFFT of the lean range kernel -> the
+// Doppler-axis fftshift (fft2D.m:46) is an output-index rotation by F/2 and the power is scaled per range row by
+// p.win2[n] = w2[(n - N/2) mod N]^2 / (N F); !RAW: kernel A / A' already windowed, scaled and modulated by (-1)^s'.
+// ------------------------------------------------------------------------------------------
+template <int R1, int R2, int RT, int NI, bool RAW>
+__global__ void __launch_bounds__(RT * R1 * R2)
+rdm_doppler_fft_kernel(const RdmDev p, const float invF) {
     using G = FftGeom<R1, R2, false>;
     extern __shared__ float2 smem[];
     const int nl = threadIdx.x % RT, tf = threadIdx.x / RT;
-    const int tilesPerPage = p.nIFFT / RT;
-    const long long page = blockIdx.x / tilesPerPage;
+    const int nIFFT = NI > 0 ? NI : p.nIFFT;
+    const int tilesPerPage = nIFFT / RT;
+    const int page = blockIdx.x / tilesPerPage;
     const int n = (blockIdx.x % tilesPerPage) * RT + nl;
-    const float2* __restrict__ in = p.inter + page * (long long)p.M * p.nIFFT + n;
-    const int M = p.M, nIFFT = p.nIFFT;
+    const int M = p.M;
+    const float2* __restrict__ in = p.inter + (size_t)page * M * nIFFT + n;
     auto load = [&](int sp) -> float2 {
-        if (sp < M) return __ldcg(in + (long long)sp * nIFFT);
+        if (sp < M) return __ldcg(in + (size_t)sp * nIFFT);
         return make_float2(0.f, 0.f);
     };
     float2 v[16];
     block_fft<R1, R2, -1, false>(v, smem + nl, RT, tf, p.twD, load);
-    float* __restrict__ out = p.pow + page * (long long)p.nFFT * nIFFT + n;
+    float* __restrict__ out = p.pow + (size_t)page * G::N * nIFFT + n;
+    const float sc = RAW ? __ldg(p.win2 + n) : invF;
 #pragma unroll
     for (int d = 0; d < 16; ++d) {
-        // Doppler-axis fftshift (fft2D.m:46) already applied: kernel A modulated symbol s' by (-1)^s'
-        const int q = tf + G::NT * d;
-        out[(long long)q * nIFFT] = (v[d].x * v[d].x + v[d].y * v[d].y) * invF;  // abs(rdm).^2 (fft2D.m:61)
+        const int q = tf + G::NT * (RAW ? ((d + 8) & 15) : d);
+        out[(size_t)q * nIFFT] = (v[d].x * v[d].x + v[d].y * v[d].y) * sc;  // abs(rdm).^2 (fft2D.m:61)
     }
 }
 
@@ -352,6 +542,8 @@ static std::vector<double> kaiser_window(int n, double beta) {
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
+static bool make_inter_tensor_map(CUtensorMap* map, void* inter, int nIFFT, int M, int nAnts);
+
 int rdm_plan_create(Ctx* ctx, const RdmConfig& c, RdmPlan** out) {
     if (c.nSc < 1 || c.nSym < 1 || c.nAnts < 1 || c.maxBatch < 1) {
         set_error(ctx, "rdm_plan_create: non-positive dimension");
@@ -417,6 +609,7 @@ int rdm_plan_create(Ctx* ctx, const RdmConfig& c, RdmPlan** out) {
     } while (0)
     ALLOC(p->d_win1, sizeof(float) * c.nSc);
     ALLOC(p->d_win2, sizeof(float) * c.nIFFT);
+    ALLOC(p->d_rowScale, sizeof(float) * c.nIFFT);
     ALLOC(p->d_inter, sizeof(float2) * (size_t)c.nIFFT * p->M * A);  // one map-set, reused (L2 resident)
     ALLOC(p->d_pow, sizeof(float) * (size_t)c.nIFFT * c.nFFT * A * B);
     ALLOC(p->d_flags, (size_t)p->nCut * A * B);
@@ -427,6 +620,13 @@ int rdm_plan_create(Ctx* ctx, const RdmConfig& c, RdmPlan** out) {
 #undef ALLOC
     cudaMemcpy(p->d_win1, f1.data(), sizeof(float) * c.nSc, cudaMemcpyHostToDevice);
     cudaMemcpy(p->d_win2, f2.data(), sizeof(float) * c.nIFFT, cudaMemcpyHostToDevice);
+    for (int n = 0; n < c.nIFFT; ++n) {  // power scale of range row n when the range kernel emits the raw IFFT
+        int idx = ((n - c.nIFFT / 2) % c.nIFFT + c.nIFFT) % c.nIFFT;
+        f2[n] = (float)(w2[idx] * w2[idx] / ((double)c.nIFFT * (double)c.nFFT));
+    }
+    cudaMemcpy(p->d_rowScale, f2.data(), sizeof(float) * c.nIFFT, cudaMemcpyHostToDevice);
+    p->hasInterMap = c.nFFT == 256 && c.nIFFT % 16 == 0 && p->M <= 256 &&
+                     make_inter_tensor_map(&p->interMap, p->d_inter, c.nIFFT, p->M, c.nAnts);
     *out = p;
     return kOk;
 }
@@ -435,6 +635,7 @@ void rdm_plan_destroy(RdmPlan* p) {
     if (!p) return;
     cudaFree(p->d_win1);
     cudaFree(p->d_win2);
+    cudaFree(p->d_rowScale);
     cudaFree(p->d_inter);
     cudaFree(p->d_pow);
     cudaFree(p->d_flags);
@@ -469,19 +670,81 @@ static cudaError_t launch_range_tma(const RdmDev& d, int numSMs, cudaStream_t st
     return cudaGetLastError();
 }
 
-template <int R1, int R2>
-static cudaError_t launch_doppler(const RdmDev& d, long long pages, cudaStream_t st) {
+template <int NJ>
+static cudaError_t launch_range_lean_nj(const RdmDev& d, int numSMs, cudaStream_t st) {
+    const size_t smem = sizeof(float2) * (2 * NJ * 256 + 16 * 257 + 240) + sizeof(float) * NJ * 256;
+    auto k = rdm_range4096_lean_kernel<NJ>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    long long blocks = 2LL * numSMs;
+    if (blocks > d.totalCols) blocks = d.totalCols;
+    k<<<(unsigned)blocks, 256, smem, st>>>(d);
+    return cudaGetLastError();
+}
+static cudaError_t launch_range_lean(const RdmDev& d, int numSMs, cudaStream_t st) {
+    return d.nSc <= 13 * 256 ? launch_range_lean_nj<13>(d, numSMs, st) : launch_range_lean_nj<16>(d, numSMs, st);
+}
+
+// F = 256, raw range profiles, nIFFT a multiple of 16
+static cudaError_t launch_doppler256_tma(const RdmDev& d, int pages, int numSMs, const CUtensorMap& map, cudaStream_t st) {
+    const size_t smem = sizeof(float2) * (2 * 4096 + 240);
+    long long blocks = 3LL * numSMs;
+    const long long tiles = (long long)pages * (d.nIFFT / 16);
+    if (blocks > tiles) blocks = tiles;
+    auto k = d.nIFFT == 4096 ? rdm_doppler256_tma_kernel<4096> : rdm_doppler256_tma_kernel<0>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    k<<<(unsigned)blocks, 256, smem, st>>>(d, pages, map);
+    return cudaGetLastError();
+}
+
+// 2-D view of the range-profile buffer for the bulk-staged Doppler kernel: dim0 = range row (nIFFT, contiguous),
+// dim1 = symbol of every page (M * nAnts), 8-byte elements (one complex64), box = [16 rows x M symbols], no swizzle.
+static bool make_inter_tensor_map(CUtensorMap* map, void* inter, int nIFFT, int M, int nAnts) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess)
+        return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)nIFFT, (cuuint64_t)M * nAnts};
+    const cuuint64_t strides[1] = {(cuuint64_t)nIFFT * sizeof(float2)};
+    const cuuint32_t box[2] = {16u, (cuuint32_t)M};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return ((EncodeTiled)fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, inter, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int R1, int R2, int RT, int NI>
+static cudaError_t launch_doppler_rt(const RdmDev& d, long long pages, bool raw, cudaStream_t st) {
     using G = FftGeom<R1, R2, false>;
-    int RT = 8192 / G::N;
-    if (RT > 32) RT = 32;
-    if (RT < 1) RT = 1;
     const int threads = RT * G::NT;
     const size_t smem = (size_t)RT * G::kElems * sizeof(float2);
-    auto k = rdm_doppler_fft_kernel<R1, R2>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long long blocks = pages * (d.nIFFT / RT);
-    k<<<(unsigned)blocks, threads, smem, st>>>(d, RT, 1.0f / (float)G::N);
+    const float invF = 1.0f / (float)G::N;
+    if (raw) {
+        auto k = rdm_doppler_fft_kernel<R1, R2, RT, NI, true>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<(unsigned)blocks, threads, smem, st>>>(d, invF);
+    } else {
+        auto k = rdm_doppler_fft_kernel<R1, R2, RT, NI, false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<(unsigned)blocks, threads, smem, st>>>(d, invF);
+    }
     return cudaGetLastError();
+}
+
+// RT = rows interleaved per CTA: 8192 / N capped to [1, 32] (64 KB of shared memory, <= 512 threads)
+template <int R1, int R2>
+static cudaError_t launch_doppler(const RdmDev& d, long long pages, bool raw, cudaStream_t st) {
+    constexpr int N = R1 * R2 * 16;
+    constexpr int RT = (8192 / N > 32) ? 32 : (8192 / N < 1 ? 1 : 8192 / N);
+    if (N == 256 && d.nIFFT == 4096) return launch_doppler_rt<R1, R2, RT, (N == 256 ? 4096 : 0)>(d, pages, raw, st);
+    if (N == 1024 && d.nIFFT == 1024) return launch_doppler_rt<R1, R2, RT, (N == 1024 ? 1024 : 0)>(d, pages, raw, st);
+    return launch_doppler_rt<R1, R2, RT, 0>(d, pages, raw, st);
 }
 
 static CfarDev make_cfar_dev(RdmPlan* p, const float* pow, int batch) {
@@ -566,29 +829,43 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
         d.M = p->M;
         d.totalCols = (long long)p->M * c.nAnts;
         cudaError_t e = cudaSuccess;
+        bool raw = false;
         switch (c.nIFFT) {
             case 256: e = launch_range<1, 16>(d, st); break;
             case 512: e = launch_range<2, 16>(d, st); break;
             case 1024: e = launch_range<4, 16>(d, st); break;
             case 2048: e = launch_range<8, 16>(d, st); break;
             case 4096:
-                if ((((uintptr_t)d.rx | (uintptr_t)d.tx) & 15) == 0 && (c.nSc % 2) == 0 && !p->noTma) e = launch_range_tma(d, ctx_num_sms(ctx), st);
-                else e = launch_range<16, 16>(d, st);
+                if ((((uintptr_t)d.rx | (uintptr_t)d.tx) & 15) == 0 && (c.nSc % 2) == 0 && p->variant != 2) {
+                    if (p->variant == 0 || p->variant == 3) {
+                        d.win2 = p->d_rowScale;  // raw range profiles: window / scale / centring move to the Doppler kernel
+                        e = launch_range_lean(d, ctx_num_sms(ctx), st);
+                        raw = true;
+                    } else {
+                        e = launch_range_tma(d, ctx_num_sms(ctx), st);
+                    }
+                } else {
+                    e = launch_range<16, 16>(d, st);
+                }
                 break;
             default: set_error(ctx, "rdm: unsupported nIFFT"); return kErrUnsupported;
         }
         ISAC_CUDA_CHECK(ctx, e);
         const long long pages = (long long)c.nAnts;
+        if (raw && c.nFFT == 256 && p->variant == 0 && p->hasInterMap) {
+            ISAC_CUDA_CHECK(ctx, launch_doppler256_tma(d, (int)pages, ctx_num_sms(ctx), p->interMap, st));
+            continue;
+        }
         switch (c.nFFT) {
-            case 16: e = launch_doppler<1, 1>(d, pages, st); break;
-            case 32: e = launch_doppler<1, 2>(d, pages, st); break;
-            case 64: e = launch_doppler<1, 4>(d, pages, st); break;
-            case 128: e = launch_doppler<1, 8>(d, pages, st); break;
-            case 256: e = launch_doppler<1, 16>(d, pages, st); break;
-            case 512: e = launch_doppler<2, 16>(d, pages, st); break;
-            case 1024: e = launch_doppler<4, 16>(d, pages, st); break;
-            case 2048: e = launch_doppler<8, 16>(d, pages, st); break;
-            case 4096: e = launch_doppler<16, 16>(d, pages, st); break;
+            case 16: e = launch_doppler<1, 1>(d, pages, raw, st); break;
+            case 32: e = launch_doppler<1, 2>(d, pages, raw, st); break;
+            case 64: e = launch_doppler<1, 4>(d, pages, raw, st); break;
+            case 128: e = launch_doppler<1, 8>(d, pages, raw, st); break;
+            case 256: e = launch_doppler<1, 16>(d, pages, raw, st); break;
+            case 512: e = launch_doppler<2, 16>(d, pages, raw, st); break;
+            case 1024: e = launch_doppler<4, 16>(d, pages, raw, st); break;
+            case 2048: e = launch_doppler<8, 16>(d, pages, raw, st); break;
+            case 4096: e = launch_doppler<16, 16>(d, pages, raw, st); break;
             default: set_error(ctx, "rdm: unsupported nFFT"); return kErrUnsupported;
         }
         ISAC_CUDA_CHECK(ctx, e);

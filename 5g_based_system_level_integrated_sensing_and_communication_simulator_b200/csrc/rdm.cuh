@@ -1,6 +1,7 @@
 // Range-Doppler map pipeline (K3 + K4): declarations shared between rdm.cu, music.cu and capi.cu.
 #pragma once
 #include "isac_common.cuh"
+#include <cuda.h>
 #include <vector>
 
 namespace isac {
@@ -26,6 +27,7 @@ struct RdmPlan {
     // device buffers (plan-owned)
     float* d_win1 = nullptr;     // kaiser(nSc)                         (fft2D.m:43)
     float* d_win2 = nullptr;     // kaiser(nIFFT)[(n-N/2) mod N]/sqrt(N) (fft2D.m:44-45 folded)
+    float* d_rowScale = nullptr; // w2[(n-N/2) mod N]^2 / (nIFFT nFFT): power scale per range row (raw-IFFT pipeline)
     float2* d_inter = nullptr;   // range profiles [nIFFT x M x nAnts]: ONE map-set, reused so it stays in L2
     float* d_pow = nullptr;      // |RDM|^2 [nIFFT x nFFT x nAnts x maxBatch]
     uint8_t* d_flags = nullptr;  // CFAR decisions [nCut x nAnts x maxBatch]
@@ -33,9 +35,13 @@ struct RdmPlan {
     int32_t* d_detCount = nullptr;  // [nAnts x maxBatch]
     int2* d_det = nullptr;          // [nCut x nAnts x maxBatch] (row, col) 1-based, CUT order
     float* d_peak = nullptr;        // [nCut x nAnts x maxBatch]
+    CUtensorMap interMap{};      // 2-D TMA view of d_inter for the bulk-staged Doppler kernel (nFFT = 256)
+    bool hasInterMap = false;
     const float* lastPow = nullptr; // power map used by the last run (plan-owned or caller's)
     int lastBatch = 0;
-    bool noTma = false;          // force the non-TMA range kernel (A/B comparisons)
+    int variant = 0;             // N = 4096 pipelines: 0 lean persistent TMA range kernel (raw IFFT) + bulk-staged
+                                 // persistent Doppler kernel (F = 256; other F as 3), 1 first TMA range kernel,
+                                 // 2 one-CTA-per-column range kernel, 3 lean range kernel + one-tile-per-CTA Doppler kernel
 };
 
 int rdm_plan_create(Ctx* ctx, const RdmConfig& cfg, RdmPlan** out);

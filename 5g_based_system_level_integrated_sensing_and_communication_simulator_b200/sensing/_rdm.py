@@ -36,6 +36,11 @@ class RangeDopplerPlan:
         self.shape_rdm = (nIFFT, nFFT, nAnts)
         self.max_batch = max_batch
 
+    def set_variant(self, variant):
+        """Range-kernel selection for nIFFT = 4096 (isac_rdm_plan_set_variant): 0 lean persistent TMA kernel (default),
+        1 first TMA kernel, 2 one CTA per column.  Same results to rounding; used by the parity tests and A/B timing."""
+        _lib.check(self.lib.isac_rdm_plan_set_variant(self.handle, int(variant)), self.ctx.handle)
+
     # -- device path -------------------------------------------------------------------------
     def run_dev(self, rx_dev, tx_dev, batch=1, power_out=None):
         """rx_dev/tx_dev: torch CUDA complex64 tensors laid out [batch][nAnts][nSym][nSc]

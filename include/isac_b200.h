@@ -78,6 +78,10 @@ int isac_rdm_plan_create(isac_ctx* ctx, const isac_rdm_config* cfg, isac_rdm_pla
 int isac_rdm_plan_destroy(isac_rdm_plan* plan);
 /* CA-CFAR threshold factor alpha = N (Pfa^(-1/N) - 1) the plan uses, and its training-cell count N */
 int isac_rdm_plan_info(const isac_rdm_plan* plan, double* alpha, int32_t* nTrain, int32_t* nCut);
+/* Range-kernel selection for nIFFT = 4096 (same results to rounding; exposed for A/B timing and the parity tests):
+ * 0 = lean persistent TMA range kernel (raw IFFT) + bulk-staged persistent Doppler kernel (default), 1 = first TMA
+ * range kernel, 2 = one CTA per column, 3 = lean range kernel + one-tile-per-CTA Doppler kernel. */
+int isac_rdm_plan_set_variant(isac_rdm_plan* plan, int32_t variant);
 
 /* rxGrid / txGrid: device, complex64 [nSc x nSym x nAnts x batch].
  * rdPower: device float32 [nIFFT x nFFT x nAnts x batch] or NULL (plan-owned buffer is used).

@@ -115,6 +115,35 @@ def test_rdm_fft_sizes(gpu, nfft_sym):
     plan.close()
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("sym_fft", [(168, 256), (77, 64), (300, 256), (9, 16)])
+def test_rdm_4096_range_kernel_variants(gpu, variant, sym_fft):
+    """nIFFT = 4096: lean persistent TMA kernel + Doppler output rotation (0), first TMA kernel (1) and the
+    one-CTA-per-column kernel (2) against numpy, with odd / truncated / padded symbol counts and odd antenna counts."""
+    nSym, nFFT = sym_fft
+    nIFFT, nSc, nAnts = 4096, 3276, 3
+    rng = np.random.default_rng(100 * nSym + nFFT)
+    rp = {"nIFFT": nIFFT, "nFFT": nFFT, "rRes": 1.0, "vRes": 1.0, "Pfa": 1e-4,
+          "cfarEstZone": np.array([[10.0, 100.0], [-4.0, 3.0]])}
+    cf = S.cfar2d_config(rp)
+    rx = (rng.standard_normal((nSc, nSym, nAnts)) + 1j * rng.standard_normal((nSc, nSym, nAnts))).astype(np.complex64)
+    tx = np.exp(2j * np.pi * rng.random((nSc, nSym, nAnts))).astype(np.complex64)
+    # a coherent target so that the map has structure (range bin 300, Doppler slope) on top of the noise
+    k = np.arange(nSc)[:, None, None]
+    s = np.arange(nSym)[None, :, None]
+    rx = (rx * 0.05 + tx * np.exp(-2j * np.pi * k * 300 / nIFFT + 2j * np.pi * s * 0.11)).astype(np.complex64)
+    plan = _plan(rp, cf, rx.shape)
+    plan.set_variant(variant)
+    plan.run_dev(_to_dev(rx), _to_dev(tx), 1)
+    P_gpu = plan.power(1)[..., 0].astype(np.float64)
+    P_ref = np.abs(S.rdm_2dfft(rp, rx, tx)) ** 2
+    _check_power(P_gpu, P_ref)
+    _, dets = plan.detections(1)
+    for r in range(nAnts):
+        assert np.array_equal(dets[0][r][0], S.cfar2d_detect_exact(P_gpu[:, :, r], cf))
+    plan.close()
+
+
 def test_rdm_batch_and_host_path(gpu, workloads):
     """A batch of map-sets equals the per-map results; host-pointer entry equals device entry."""
     import torch

@@ -11,8 +11,9 @@ sys.path.insert(0, ".")
 rdm = importlib.import_module(PKG + ".sensing._rdm")
 
 
-def run(nSc, nSym, nAnts, nIFFT, nFFT, rows, cols, B, iters=20):
+def run(nSc, nSym, nAnts, nIFFT, nFFT, rows, cols, B, iters=20, variant=0):
     plan = rdm.RangeDopplerPlan(nSc, nSym, nAnts, nIFFT, nFFT, rows, cols, 1e-9, max_batch=B)
+    plan.set_variant(variant)
     g = torch.Generator(device="cuda").manual_seed(0)
     rx = torch.view_as_complex(torch.randn(B, nAnts, nSym, nSc, 2, device="cuda", generator=g))
     tx = torch.view_as_complex(torch.randn(B, nAnts, nSym, nSc, 2, device="cuda", generator=g))
@@ -33,14 +34,15 @@ def run(nSc, nSym, nAnts, nIFFT, nFFT, rows, cols, B, iters=20):
     ts = np.array(ts)
     alg = (16 * nSc * nSym * nAnts + 4 * nIFFT * nFFT * nAnts) * B
     ms = np.median(ts)
-    print(f"B={B} {nSc}x{nSym}x{nAnts}->{nIFFT}x{nFFT}: median {ms*1e3:.1f} us  min {ts.min()*1e3:.1f} us  "
+    print(f"variant={variant} B={B} {nSc}x{nSym}x{nAnts}->{nIFFT}x{nFFT}: median {ms*1e3:.1f} us  min {ts.min()*1e3:.1f} us  "
           f"alg {alg/1e6:.1f} MB  {alg/ms/1e6:.0f} GB/s  ({alg/ms/1e6/6570:.2%} of 6570)  maps/s {B/ms*1e3:.0f}")
     plan.close()
 
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    for B in (1, 4, 16):
-        run(3276, 168, 8, 4096, 256, (42, 411), (118, 140), B)
+    for variant in (0, 3, 1):
+        for B in (1, 4, 16):
+            run(3276, 168, 8, 4096, 256, (42, 411), (118, 140), B, variant=variant)
     run(624, 840, 4, 1024, 1024, (6, 52), (427, 599), 1)
     run(624, 840, 4, 1024, 1024, (6, 52), (427, 599), 8)
