@@ -25,6 +25,7 @@
 #include "rdm.cuh"
 #include "fft_core.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace isac {
@@ -241,9 +242,13 @@ rdm_range4096_lean_kernel(const RdmDev p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // Programmatic dependent launch: the Doppler kernel of this map-set may be scheduled as soon as every CTA is here
+    // (it waits for this grid's completion before it reads the range profiles).
+    asm volatile("griddepcontrol.launch_dependents;");
     int col = blockIdx.x;
     if (tf == 0 && col < total) issue(col);
     unsigned parity = 0;
+    bool mustWait = true;  // the previous map-set's Doppler kernel may still be reading the range-profile buffer
     float2* __restrict__ out = p.inter + (size_t)col * N + tf;
     const size_t outStride = (size_t)stride * N;
     for (; col < total; col += stride, out += outStride) {
@@ -276,6 +281,10 @@ rdm_range4096_lean_kernel(const RdmDev p) {
 #pragma unroll
         for (int b = 0; b < 16; ++b) v[b] = f3[b];
         dft16<+1>(v);
+        if (mustWait) {  // first column only: everything above overlapped the tail of the preceding grid
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            mustWait = false;
+        }
 #pragma unroll
         for (int d = 0; d < 16; ++d) out[NT * d] = v[d];
     }
@@ -327,6 +336,10 @@ rdm_doppler256_tma_kernel(const RdmDev p, const int nPages, const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // Programmatic dependent launch: the next map-set's range kernel may start its prologue / first column now (it waits
+    // for this grid before its first store); this grid waits for the range kernel that produced the profiles.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int tile = blockIdx.x;
     if (tid == 0 && tile < total) issue(tile, 0);
     unsigned phase = 0;  // bit s = parity to wait for on bar[s]
@@ -414,6 +427,8 @@ struct CfarDev {
 };
 
 __global__ void __launch_bounds__(256) cfar2d_flags_kernel(const CfarDev p) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched as a programmatic dependent
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= p.total) return;
     const int i = (int)(gid % p.nCut);
@@ -443,6 +458,8 @@ __global__ void __launch_bounds__(256) cfar2d_flags_kernel(const CfarDev p) {
 // Reference configuration (cfar2D.m:32-33): guard [2 2], training [1 1] -> 7x7 window minus the 5x5 guard block.
 // Fully unrolled: the 24 training loads are independent and issue back to back (same summation order as above).
 __global__ void __launch_bounds__(256) cfar2d_flags_7x7_kernel(const CfarDev p) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched as a programmatic dependent
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= p.total) return;
     const int i = (int)(gid % p.nCut);
@@ -474,6 +491,7 @@ __global__ void __launch_bounds__(256) cfar2d_flags_7x7_kernel(const CfarDev p) 
 __global__ void __launch_bounds__(1024) cfar2d_compact_kernel(const CfarDev p, int2* det, float* peak, int32_t* detCount) {
     // each thread owns a contiguous run of CUTs (keeps CUT order), one block-wide exclusive scan of the run counts
     __shared__ int warpTot[32];
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // flags of the preceding grid (programmatic dependent launch)
     const long long page = blockIdx.x;
     const uint8_t* __restrict__ f = p.flags + page * (long long)p.nCut;
     const float* __restrict__ P = p.pow + page * (long long)p.nFFT * p.nIFFT;
@@ -625,6 +643,7 @@ int rdm_plan_create(Ctx* ctx, const RdmConfig& c, RdmPlan** out) {
         f2[n] = (float)(w2[idx] * w2[idx] / ((double)c.nIFFT * (double)c.nFFT));
     }
     cudaMemcpy(p->d_rowScale, f2.data(), sizeof(float) * c.nIFFT, cudaMemcpyHostToDevice);
+    if (const char* e = getenv("ISAC_RDM_PDL")) p->pdl = atoi(e) != 0;
     p->hasInterMap = c.nFFT == 256 && c.nIFFT % 16 == 0 && p->M <= 256 &&
                      make_inter_tensor_map(&p->interMap, p->d_inter, c.nIFFT, p->M, c.nAnts);
     *out = p;
@@ -670,23 +689,41 @@ static cudaError_t launch_range_tma(const RdmDev& d, int numSMs, cudaStream_t st
     return cudaGetLastError();
 }
 
+// Launch with (pdl) or without the programmatic-stream-serialization attribute: with it the grid may start while its
+// predecessor in the stream is still running and orders itself with griddepcontrol.wait.
+template <class... KArgs, class... Args>
+static cudaError_t launch_ex(void (*k)(KArgs...), unsigned blocks, unsigned threads, size_t smem, cudaStream_t st, bool pdl,
+                             Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, args...);
+}
+
 template <int NJ>
-static cudaError_t launch_range_lean_nj(const RdmDev& d, int numSMs, cudaStream_t st) {
+static cudaError_t launch_range_lean_nj(const RdmDev& d, int numSMs, bool pdl, cudaStream_t st) {
     const size_t smem = sizeof(float2) * (2 * NJ * 256 + 16 * 257 + 240) + sizeof(float) * NJ * 256;
     auto k = rdm_range4096_lean_kernel<NJ>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     long long blocks = 2LL * numSMs;
     if (blocks > d.totalCols) blocks = d.totalCols;
-    k<<<(unsigned)blocks, 256, smem, st>>>(d);
-    return cudaGetLastError();
+    return launch_ex(k, (unsigned)blocks, 256, smem, st, pdl, d);
 }
-static cudaError_t launch_range_lean(const RdmDev& d, int numSMs, cudaStream_t st) {
-    return d.nSc <= 13 * 256 ? launch_range_lean_nj<13>(d, numSMs, st) : launch_range_lean_nj<16>(d, numSMs, st);
+static cudaError_t launch_range_lean(const RdmDev& d, int numSMs, bool pdl, cudaStream_t st) {
+    return d.nSc <= 13 * 256 ? launch_range_lean_nj<13>(d, numSMs, pdl, st) : launch_range_lean_nj<16>(d, numSMs, pdl, st);
 }
 
 // F = 256, raw range profiles, nIFFT a multiple of 16
-static cudaError_t launch_doppler256_tma(const RdmDev& d, int pages, int numSMs, const CUtensorMap& map, cudaStream_t st) {
+static cudaError_t launch_doppler256_tma(const RdmDev& d, int pages, int numSMs, const CUtensorMap& map, bool pdl,
+                                         cudaStream_t st) {
     const size_t smem = sizeof(float2) * (2 * 4096 + 240);
     long long blocks = 3LL * numSMs;
     const long long tiles = (long long)pages * (d.nIFFT / 16);
@@ -694,8 +731,7 @@ static cudaError_t launch_doppler256_tma(const RdmDev& d, int pages, int numSMs,
     auto k = d.nIFFT == 4096 ? rdm_doppler256_tma_kernel<4096> : rdm_doppler256_tma_kernel<0>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    k<<<(unsigned)blocks, 256, smem, st>>>(d, pages, map);
-    return cudaGetLastError();
+    return launch_ex(k, (unsigned)blocks, 256, smem, st, pdl, d, pages, map);
 }
 
 // 2-D view of the range-profile buffer for the bulk-staged Doppler kernel: dim0 = range row (nIFFT, contiguous),
@@ -771,26 +807,35 @@ static CfarDev make_cfar_dev(RdmPlan* p, const float* pow, int batch) {
     return d;
 }
 
-int rdm_cfar_only(RdmPlan* p, const float* pow, int batch, cudaStream_t st) {
+// chained: called at the tail of rdm_run -- the row bitmap was cleared before the range kernels, no profiling events are
+// recorded in between, and the flags kernel is launched as a programmatic dependent of the last Doppler kernel.
+static int rdm_cfar_launch(RdmPlan* p, const float* pow, int batch, bool chained, cudaStream_t st) {
     Ctx* ctx = p->ctx;
-    if (batch < 1 || batch > p->cfg.maxBatch) {
-        set_error(ctx, "rdm: batch out of range");
-        return kErrInvalidArg;
-    }
     CfarDev d = make_cfar_dev(p, pow, batch);
-    ISAC_CUDA_CHECK(ctx, cudaMemsetAsync(p->d_rowmask, 0, sizeof(uint32_t) * (size_t)p->rowWords * batch, st));
+    int pr = -1;
+    if (!chained) {
+        ISAC_CUDA_CHECK(ctx, cudaMemsetAsync(p->d_rowmask, 0, sizeof(uint32_t) * (size_t)p->rowWords * batch, st));
+        pr = prof_begin(ctx, kProfCfar, st);
+    }
     const long long blocks = (d.total + 255) / 256;
-    const int pr = prof_begin(ctx, kProfCfar, st);
-    if (d.gr == 2 && d.gc == 2 && d.hr == 3 && d.hc == 3) cfar2d_flags_7x7_kernel<<<(unsigned)blocks, 256, 0, st>>>(d);
-    else cfar2d_flags_kernel<<<(unsigned)blocks, 256, 0, st>>>(d);
-    ISAC_CUDA_CHECK(ctx, cudaGetLastError());
-    cfar2d_compact_kernel<<<(unsigned)(p->cfg.nAnts * batch), 1024, 0, st>>>(d, p->d_det, p->d_peak, p->d_detCount);
-    prof_end(ctx, pr, st);
+    const bool ref7 = d.gr == 2 && d.gc == 2 && d.hr == 3 && d.hc == 3;
+    ISAC_CUDA_CHECK(ctx, launch_ex(ref7 ? cfar2d_flags_7x7_kernel : cfar2d_flags_kernel, (unsigned)blocks, 256, 0, st,
+                                   chained && p->pdl, d));
+    ISAC_CUDA_CHECK(ctx, launch_ex(cfar2d_compact_kernel, (unsigned)(p->cfg.nAnts * batch), 1024, 0, st, p->pdl, d, p->d_det,
+                                   p->d_peak, p->d_detCount));
+    if (!chained) prof_end(ctx, pr, st);
     count_launches(ctx, 2);
-    ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     p->lastPow = pow;
     p->lastBatch = batch;
     return kOk;
+}
+
+int rdm_cfar_only(RdmPlan* p, const float* pow, int batch, cudaStream_t st) {
+    if (batch < 1 || batch > p->cfg.maxBatch) {
+        set_error(p->ctx, "rdm: batch out of range");
+        return kErrInvalidArg;
+    }
+    return rdm_cfar_launch(p, pow, batch, false, st);
 }
 
 int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* powOut, cudaStream_t st) {
@@ -810,7 +855,9 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
     // Doppler kernels instead of making a round trip through HBM.
     const size_t gridElems = (size_t)c.nSc * c.nSym * c.nAnts;
     const size_t powElems = (size_t)c.nIFFT * c.nFFT * c.nAnts;
-    const int prR = prof_begin(ctx, kProfRdmRange, st);  // range+Doppler pairs are timed together
+    ISAC_CUDA_CHECK(ctx, cudaMemsetAsync(p->d_rowmask, 0, sizeof(uint32_t) * (size_t)p->rowWords * batch, st));
+    const int prR = prof_begin(ctx, kProfRdmRange, st);  // the whole range / Doppler / CFAR chain is timed as one group
+    bool prevTmaDoppler = false;
     for (int b = 0; b < batch; ++b) {
         RdmDev d{};
         d.rx = rx + b * gridElems;
@@ -839,7 +886,8 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
                 if ((((uintptr_t)d.rx | (uintptr_t)d.tx) & 15) == 0 && (c.nSc % 2) == 0 && p->variant != 2) {
                     if (p->variant == 0 || p->variant == 3) {
                         d.win2 = p->d_rowScale;  // raw range profiles: window / scale / centring move to the Doppler kernel
-                        e = launch_range_lean(d, ctx_num_sms(ctx), st);
+                        // PDL edge Doppler(b-1) -> range(b): only behind this plan's own bulk-staged Doppler kernel
+                        e = launch_range_lean(d, ctx_num_sms(ctx), p->pdl && b > 0 && prevTmaDoppler, st);
                         raw = true;
                     } else {
                         e = launch_range_tma(d, ctx_num_sms(ctx), st);
@@ -853,7 +901,8 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
         ISAC_CUDA_CHECK(ctx, e);
         const long long pages = (long long)c.nAnts;
         if (raw && c.nFFT == 256 && p->variant == 0 && p->hasInterMap) {
-            ISAC_CUDA_CHECK(ctx, launch_doppler256_tma(d, (int)pages, ctx_num_sms(ctx), p->interMap, st));
+            ISAC_CUDA_CHECK(ctx, launch_doppler256_tma(d, (int)pages, ctx_num_sms(ctx), p->interMap, p->pdl, st));
+            prevTmaDoppler = true;
             continue;
         }
         switch (c.nFFT) {
@@ -870,9 +919,10 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
         }
         ISAC_CUDA_CHECK(ctx, e);
     }
-    prof_end(ctx, prR, st);
     count_launches(ctx, 2 * batch);
-    return rdm_cfar_only(p, pow, batch, st);
+    const int rc = rdm_cfar_launch(p, pow, batch, true, st);
+    prof_end(ctx, prR, st);
+    return rc;
 }
 
 }  // namespace isac

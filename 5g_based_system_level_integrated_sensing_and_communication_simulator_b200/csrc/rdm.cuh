@@ -37,6 +37,7 @@ struct RdmPlan {
     float* d_peak = nullptr;        // [nCut x nAnts x maxBatch]
     CUtensorMap interMap{};      // 2-D TMA view of d_inter for the bulk-staged Doppler kernel (nFFT = 256)
     bool hasInterMap = false;
+    bool pdl = true;             // programmatic dependent launch between the range and Doppler kernels of a batch (ISAC_RDM_PDL=0 disables)
     const float* lastPow = nullptr; // power map used by the last run (plan-owned or caller's)
     int lastBatch = 0;
     int variant = 0;             // N = 4096 pipelines: 0 lean persistent TMA range kernel (raw IFFT) + bulk-staged

@@ -41,7 +41,8 @@ def run(nSc, nSym, nAnts, nIFFT, nFFT, rows, cols, B, iters=20, variant=0):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    for variant in (0, 3, 1):
+    variants = [int(a) for a in sys.argv[1:]] or [0, 3, 1]
+    for variant in variants:
         for B in (1, 4, 16):
             run(3276, 168, 8, 4096, 256, (42, 411), (118, 140), B, variant=variant)
     run(624, 840, 4, 1024, 1024, (6, 52), (427, 599), 1)
