@@ -14,28 +14,83 @@
 
 namespace isac {
 
+// ---- packed FP32x2 complex arithmetic (Blackwell FADD2 / FMUL2 / FFMA2) ----------------------------------------
+// A complex value is one 64-bit register pair (re = low half, im = high half).  sm_100a executes add/mul/fma.f32x2 on
+// both halves in ONE instruction, and ptxas folds the half swap (".LO_HI"), a one-sided negation (".NP") and scalar
+// broadcasts (".F32") of these patterns into operand modifiers -> complex add/sub = 1 instruction (2 scalar),
+// complex multiply = 2 (4 scalar), "+- j*u" = 1 FFMA2 (the j rotation is free).  Per-lane rounding is identical to
+// the scalar FADD / FMUL / FFMA forms.
+__device__ __forceinline__ unsigned long long pk(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 unpk(unsigned long long r) {
+    float2 a;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+    return a;
+}
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
+    return unpk(r);
+}
+__device__ __forceinline__ float2 pk_sub(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
+    return unpk(r);
+}
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) {  // element-wise
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
+    return unpk(r);
+}
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) {  // element-wise a*b + c
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c)));
+    return unpk(r);
+}
+__device__ __forceinline__ float2 pk_swap(float2 a) { return make_float2(a.y, a.x); }
+// a * w  (complex)
+__device__ __forceinline__ float2 pk_cmul(float2 a, float2 w) {
+    return pk_fma(pk_swap(a), make_float2(-w.y, w.y), pk_mul(a, make_float2(w.x, w.x)));
+}
+// a * conj(b)
+__device__ __forceinline__ float2 pk_cmulc(float2 a, float2 b) {
+    return pk_fma(pk_swap(a), make_float2(b.y, -b.y), pk_mul(a, make_float2(b.x, b.x)));
+}
+__device__ __forceinline__ float2 pk_scale(float2 a, float s) { return pk_mul(a, make_float2(s, s)); }
+// t + SIGN*j*u  and  t - SIGN*j*u
+template <int SIGN>
+__device__ __forceinline__ float2 pk_addj(float2 t, float2 u) {
+    return pk_fma(pk_swap(u), make_float2(-(float)SIGN, (float)SIGN), t);
+}
+template <int SIGN>
+__device__ __forceinline__ float2 pk_subj(float2 t, float2 u) {
+    return pk_fma(pk_swap(u), make_float2((float)SIGN, -(float)SIGN), t);
+}
 // multiply by SIGN*j
 template <int SIGN>
 __device__ __forceinline__ float2 mulj(float2 a) {
-    return SIGN > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+    return pk_mul(pk_swap(a), make_float2(-(float)SIGN, (float)SIGN));
 }
 
 template <int SIGN>
 __device__ __forceinline__ void dft2(float2& a, float2& b) {
-    float2 t = csub(a, b);
-    a = cadd(a, b);
+    float2 t = pk_sub(a, b);
+    a = pk_add(a, b);
     b = t;
 }
 
 // y_k = sum_n x_n exp(SIGN*2*pi*i*n*k/4)
 template <int SIGN>
 __device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
-    float2 t0 = cadd(x0, x2), t1 = csub(x0, x2);
-    float2 t2 = cadd(x1, x3), t3 = mulj<SIGN>(csub(x1, x3));
-    x0 = cadd(t0, t2);
-    x2 = csub(t0, t2);
-    x1 = cadd(t1, t3);
-    x3 = csub(t1, t3);
+    const float2 t0 = pk_add(x0, x2), t1 = pk_sub(x0, x2);
+    const float2 t2 = pk_add(x1, x3), u = pk_sub(x1, x3);
+    x0 = pk_add(t0, t2);
+    x2 = pk_sub(t0, t2);
+    x1 = pk_addj<SIGN>(t1, u);  // t1 + SIGN*j*(x1 - x3)
+    x3 = pk_subj<SIGN>(t1, u);
 }
 
 template <int SIGN>
@@ -45,13 +100,13 @@ __device__ __forceinline__ void dft8(float2* v) {
     float2 A0[4], A1[4];
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2) {
-        A0[n2] = cadd(v[n2], v[4 + n2]);
-        A1[n2] = csub(v[n2], v[4 + n2]);
+        A0[n2] = pk_add(v[n2], v[4 + n2]);
+        A1[n2] = pk_sub(v[n2], v[4 + n2]);
     }
     // twiddles w8^{n2}, w8 = exp(SIGN*2*pi*i/8)
-    A1[1] = cmul(A1[1], make_float2(c, SIGN * c));
+    A1[1] = pk_cmul(A1[1], make_float2(c, SIGN * c));
     A1[2] = mulj<SIGN>(A1[2]);
-    A1[3] = cmul(A1[3], make_float2(-c, SIGN * c));
+    A1[3] = pk_cmul(A1[3], make_float2(-c, SIGN * c));
     dft4<SIGN>(A0[0], A0[1], A0[2], A0[3]);
     dft4<SIGN>(A1[0], A1[1], A1[2], A1[3]);
 #pragma unroll
@@ -78,15 +133,15 @@ __device__ __forceinline__ void dft16(float2* v) {
         A[3][n2] = d;
     }
     // twiddle w16^{n2*k1}, w16 = exp(SIGN*2*pi*i/16): exponent m -> (cos(pi m/8), SIGN sin(pi m/8))
-    A[1][1] = cmul(A[1][1], make_float2(c1, SIGN * s1));    // m=1
-    A[1][2] = cmul(A[1][2], make_float2(c2, SIGN * c2));    // m=2
-    A[1][3] = cmul(A[1][3], make_float2(s1, SIGN * c1));    // m=3
-    A[2][1] = cmul(A[2][1], make_float2(c2, SIGN * c2));    // m=2
-    A[2][2] = mulj<SIGN>(A[2][2]);                          // m=4
-    A[2][3] = cmul(A[2][3], make_float2(-c2, SIGN * c2));   // m=6
-    A[3][1] = cmul(A[3][1], make_float2(s1, SIGN * c1));    // m=3
-    A[3][2] = cmul(A[3][2], make_float2(-c2, SIGN * c2));   // m=6
-    A[3][3] = cmul(A[3][3], make_float2(-c1, -SIGN * s1));  // m=9
+    A[1][1] = pk_cmul(A[1][1], make_float2(c1, SIGN * s1));    // m=1
+    A[1][2] = pk_cmul(A[1][2], make_float2(c2, SIGN * c2));    // m=2
+    A[1][3] = pk_cmul(A[1][3], make_float2(s1, SIGN * c1));    // m=3
+    A[2][1] = pk_cmul(A[2][1], make_float2(c2, SIGN * c2));    // m=2
+    A[2][2] = mulj<SIGN>(A[2][2]);                             // m=4
+    A[2][3] = pk_cmul(A[2][3], make_float2(-c2, SIGN * c2));   // m=6
+    A[3][1] = pk_cmul(A[3][1], make_float2(s1, SIGN * c1));    // m=3
+    A[3][2] = pk_cmul(A[3][2], make_float2(-c2, SIGN * c2));   // m=6
+    A[3][3] = pk_cmul(A[3][3], make_float2(-c1, -SIGN * s1));  // m=9
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) {
         dft4<SIGN>(A[k1][0], A[k1][1], A[k1][2], A[k1][3]);
@@ -150,7 +205,7 @@ __device__ __forceinline__ void block_fft(float2 (&v)[16], float2* smem, const i
             dftR<R1, SIGN>(&v[i * R1]);
 #pragma unroll
             for (int k1 = 1; k1 < R1; ++k1)
-                v[i * R1 + k1] = cmul(v[i * R1 + k1], tw_load<SIGN>(tw.tw1 + (k1 - 1) * N2 + m));
+                v[i * R1 + k1] = pk_cmul(v[i * R1 + k1], tw_load<SIGN>(tw.tw1 + (k1 - 1) * N2 + m));
 #pragma unroll
             for (int k1 = 0; k1 < R1; ++k1) smem[G::addr(k1, m >> 4, m & 15) * RT] = v[i * R1 + k1];
         }
@@ -169,7 +224,7 @@ __device__ __forceinline__ void block_fft(float2 (&v)[16], float2* smem, const i
             dftR<R2, SIGN>(&v[i * R2]);
 #pragma unroll
             for (int c = 1; c < R2; ++c)
-                v[i * R2 + c] = cmul(v[i * R2 + c], tw_load<SIGN>(tw.tw2 + (c - 1) * 16 + b));
+                v[i * R2 + c] = pk_cmul(v[i * R2 + c], tw_load<SIGN>(tw.tw2 + (c - 1) * 16 + b));
 #pragma unroll
             for (int c = 0; c < R2; ++c) smem[G::addr(k1, c, b) * RT] = v[i * R2 + c];
         }

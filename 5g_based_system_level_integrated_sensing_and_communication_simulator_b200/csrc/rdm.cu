@@ -257,7 +257,7 @@ rdm_range4096_lean_kernel(const RdmDev p) {
         float2 v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            v[j] = (j < NJ) ? cscale(cmulc(sRx[NT * j], sTx[NT * j]), w1[NT * j])  // rx.*conj(tx).*rngWin (fft2D.m:37,43)
+            v[j] = (j < NJ) ? pk_scale(pk_cmulc(sRx[NT * j], sTx[NT * j]), w1[NT * j])  // rx.*conj(tx).*rngWin (fft2D.m:37,43)
                             : make_float2(0.f, 0.f);
         __syncthreads();  // stage consumed by every thread (and the previous column's pass-3 loads are done)
         if (tf == 0 && col + stride < total) {
@@ -266,7 +266,7 @@ rdm_range4096_lean_kernel(const RdmDev p) {
         }
         dft16<+1>(v);
 #pragma unroll
-        for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], tw1r[k1 - 1]);
+        for (int k1 = 1; k1 < 16; ++k1) v[k1] = pk_cmul(v[k1], tw1r[k1 - 1]);
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) f1[k1 * S1] = v[k1];
         __syncthreads();
@@ -274,7 +274,7 @@ rdm_range4096_lean_kernel(const RdmDev p) {
         for (int a = 0; a < 16; ++a) v[a] = f2[a * 16];
         dft16<+1>(v);
 #pragma unroll
-        for (int c = 1; c < 16; ++c) v[c] = cmul(v[c], tw2[(c - 1) * 16]);
+        for (int c = 1; c < 16; ++c) v[c] = pk_cmul(v[c], tw2[(c - 1) * 16]);
 #pragma unroll
         for (int c = 0; c < 16; ++c) f2[c * 16] = v[c];
         __syncthreads();
@@ -356,7 +356,7 @@ rdm_doppler256_tma_kernel(const RdmDev p, const int nPages, const __grid_constan
         for (int a = 0; a < 16; ++a) v[a] = (a < nA) ? buf[a * TILE / 16] : make_float2(0.f, 0.f);
         dft16<-1>(v);
 #pragma unroll
-        for (int c = 1; c < 16; ++c) v[c] = cmul(v[c], tw[(c - 1) * 16]);
+        for (int c = 1; c < 16; ++c) v[c] = pk_cmul(v[c], tw[(c - 1) * 16]);
 #pragma unroll
         for (int c = 0; c < 16; ++c) buf[c * TILE / 16] = v[c];
         __syncthreads();  // exchange complete; every thread is also past its pass-B loads of the previous tile
