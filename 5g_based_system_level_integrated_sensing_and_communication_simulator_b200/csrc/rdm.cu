@@ -41,6 +41,8 @@ struct RdmDev {
     float* pow;
     int nSc, nSym, nAnts, nIFFT, nFFT, M;
     long long totalCols;  // M * nAnts * batch
+    int* ticketR;         // work counters of the persistent kernels (zeroed per run): columns / Doppler tiles are handed
+    int* ticketD;         // out in order, so every SM stays busy until the last item
 };
 
 // ------------------------------------------------------------------------------------------
@@ -227,7 +229,6 @@ rdm_range4096_lean_kernel(const RdmDev p) {
     const float2* const sRx = stageRx + tf;
     const float2* const sTx = stageTx + tf;
     const int M = p.M, nSym = p.nSym, half = p.nSym / 2;
-    const int total = (int)p.totalCols, stride = (int)gridDim.x;
     auto issue = [&](int col) {  // thread 0: fetch the rx and tx columns of `col`
         const int sp = col % M, page = col / M;
         int s = sp + half;
@@ -241,17 +242,23 @@ rdm_range4096_lean_kernel(const RdmDev p) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __shared__ int sNext;
+    const int total = (int)p.totalCols;
+    if (tf == 0) {
+        const int c0 = atomicAdd(p.ticketR, 1);
+        sNext = c0;
+        if (c0 < total) issue(c0);
+    }
     __syncthreads();
     // Programmatic dependent launch: the Doppler kernel of this map-set may be scheduled as soon as every CTA is here
     // (it waits for this grid's completion before it reads the range profiles).
     asm volatile("griddepcontrol.launch_dependents;");
-    int col = blockIdx.x;
-    if (tf == 0 && col < total) issue(col);
+    int col = sNext;
     unsigned parity = 0;
     bool mustWait = true;  // the previous map-set's Doppler kernel may still be reading the range-profile buffer
-    float2* __restrict__ out = p.inter + (size_t)col * N + tf;
-    const size_t outStride = (size_t)stride * N;
-    for (; col < total; col += stride, out += outStride) {
+    while (col < total) {
+        int ticket = 0;
+        if (tf == 0) ticket = atomicAdd(p.ticketR, 1);  // next column of this CTA; the round trip hides behind the prologue
         mbar_wait(&bar, parity);
         parity ^= 1;
         float2 v[16];
@@ -259,10 +266,12 @@ rdm_range4096_lean_kernel(const RdmDev p) {
         for (int j = 0; j < 16; ++j)
             v[j] = (j < NJ) ? pk_scale(pk_cmulc(sRx[NT * j], sTx[NT * j]), w1[NT * j])  // rx.*conj(tx).*rngWin (fft2D.m:37,43)
                             : make_float2(0.f, 0.f);
+        if (tf == 0) sNext = ticket;
         __syncthreads();  // stage consumed by every thread (and the previous column's pass-3 loads are done)
-        if (tf == 0 && col + stride < total) {
+        const int nxt = sNext;
+        if (tf == 0 && nxt < total) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
-            issue(col + stride);
+            issue(nxt);
         }
         dft16<+1>(v);
 #pragma unroll
@@ -285,8 +294,10 @@ rdm_range4096_lean_kernel(const RdmDev p) {
             asm volatile("griddepcontrol.wait;" ::: "memory");
             mustWait = false;
         }
+        float2* __restrict__ out = p.inter + (size_t)col * N + tf;
 #pragma unroll
         for (int d = 0; d < 16; ++d) out[NT * d] = v[d];
+        col = nxt;
     }
 }
 
@@ -318,7 +329,7 @@ rdm_doppler256_tma_kernel(const RdmDev p, const int nPages, const __grid_constan
     const int tid = threadIdx.x, nl = tid & 15, tf = tid >> 4;
     const int M = p.M, nIFFT = NI > 0 ? NI : p.nIFFT;
     const int tilesPerPage = nIFFT / RT;
-    const int total = nPages * tilesPerPage, stride = (int)gridDim.x;
+    const int total = nPages * tilesPerPage;
     if (tid < 240) {
         float2 w = __ldg(p.twD.tw2 + tid);
         tws[tid] = make_float2(w.x, -w.y);  // forward transform: conjugate table
@@ -340,11 +351,19 @@ rdm_doppler256_tma_kernel(const RdmDev p, const int nPages, const __grid_constan
     // for this grid before its first store); this grid waits for the range kernel that produced the profiles.
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    int tile = blockIdx.x;
-    if (tid == 0 && tile < total) issue(tile, 0);
+    __shared__ int sNext;
+    if (tid == 0) {
+        const int t0 = atomicAdd(p.ticketD, 1);
+        sNext = t0;
+        if (t0 < total) issue(t0, 0);
+    }
+    __syncthreads();
+    int tile = sNext;
     unsigned phase = 0;  // bit s = parity to wait for on bar[s]
-    for (int i = 0; tile < total; tile += stride, ++i) {
+    for (int i = 0; tile < total; ++i) {
         const int s = i & 1;
+        int ticket = 0;
+        if (tid == 0) ticket = atomicAdd(p.ticketD, 1);
         float2* const buf = buf0 + s * TILE + tf * RT + nl;        // pass A: + a*256 (symbol a*16 + tf)
         const float2* const bufB = buf0 + s * TILE + tf * TILE / 16 + nl;  // pass B: + b*16   (entry tf*16 + b)
         const int page = tile / tilesPerPage, n = (tile - page * tilesPerPage) * RT + nl;
@@ -359,10 +378,12 @@ rdm_doppler256_tma_kernel(const RdmDev p, const int nPages, const __grid_constan
         for (int c = 1; c < 16; ++c) v[c] = pk_cmul(v[c], tw[(c - 1) * 16]);
 #pragma unroll
         for (int c = 0; c < 16; ++c) buf[c * TILE / 16] = v[c];
+        if (tid == 0) sNext = ticket;
         __syncthreads();  // exchange complete; every thread is also past its pass-B loads of the previous tile
-        if (tid == 0 && tile + stride < total) {
+        const int nxt = sNext;
+        if (tid == 0 && nxt < total) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses before async writes
-            issue(tile + stride, s ^ 1);
+            issue(nxt, s ^ 1);
         }
 #pragma unroll
         for (int b = 0; b < 16; ++b) v[b] = bufB[b * RT];
@@ -373,6 +394,7 @@ rdm_doppler256_tma_kernel(const RdmDev p, const int nPages, const __grid_constan
             const int q = tf + 16 * ((d + 8) & 15);  // Doppler-axis fftshift (fft2D.m:46) as an output rotation
             out[(size_t)q * nIFFT] = (v[d].x * v[d].x + v[d].y * v[d].y) * sc;  // abs(rdm).^2 (fft2D.m:61)
         }
+        tile = nxt;
     }
 }
 
@@ -628,6 +650,7 @@ int rdm_plan_create(Ctx* ctx, const RdmConfig& c, RdmPlan** out) {
     ALLOC(p->d_win1, sizeof(float) * c.nSc);
     ALLOC(p->d_win2, sizeof(float) * c.nIFFT);
     ALLOC(p->d_rowScale, sizeof(float) * c.nIFFT);
+    ALLOC(p->d_tickets, sizeof(int) * 2 * B);
     ALLOC(p->d_inter, sizeof(float2) * (size_t)c.nIFFT * p->M * A);  // one map-set, reused (L2 resident)
     ALLOC(p->d_pow, sizeof(float) * (size_t)c.nIFFT * c.nFFT * A * B);
     ALLOC(p->d_flags, (size_t)p->nCut * A * B);
@@ -655,6 +678,7 @@ void rdm_plan_destroy(RdmPlan* p) {
     cudaFree(p->d_win1);
     cudaFree(p->d_win2);
     cudaFree(p->d_rowScale);
+    cudaFree(p->d_tickets);
     cudaFree(p->d_inter);
     cudaFree(p->d_pow);
     cudaFree(p->d_flags);
@@ -856,6 +880,7 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
     const size_t gridElems = (size_t)c.nSc * c.nSym * c.nAnts;
     const size_t powElems = (size_t)c.nIFFT * c.nFFT * c.nAnts;
     ISAC_CUDA_CHECK(ctx, cudaMemsetAsync(p->d_rowmask, 0, sizeof(uint32_t) * (size_t)p->rowWords * batch, st));
+    ISAC_CUDA_CHECK(ctx, cudaMemsetAsync(p->d_tickets, 0, sizeof(int) * 2 * (size_t)batch, st));
     const int prR = prof_begin(ctx, kProfRdmRange, st);  // the whole range / Doppler / CFAR chain is timed as one group
     bool prevTmaDoppler = false;
     for (int b = 0; b < batch; ++b) {
@@ -875,6 +900,8 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
         d.nFFT = c.nFFT;
         d.M = p->M;
         d.totalCols = (long long)p->M * c.nAnts;
+        d.ticketR = p->d_tickets + 2 * b;
+        d.ticketD = p->d_tickets + 2 * b + 1;
         cudaError_t e = cudaSuccess;
         bool raw = false;
         switch (c.nIFFT) {

@@ -28,6 +28,7 @@ struct RdmPlan {
     float* d_win1 = nullptr;     // kaiser(nSc)                         (fft2D.m:43)
     float* d_win2 = nullptr;     // kaiser(nIFFT)[(n-N/2) mod N]/sqrt(N) (fft2D.m:44-45 folded)
     float* d_rowScale = nullptr; // w2[(n-N/2) mod N]^2 / (nIFFT nFFT): power scale per range row (raw-IFFT pipeline)
+    int* d_tickets = nullptr;    // [2 x maxBatch] work counters of the persistent range / Doppler kernels
     float2* d_inter = nullptr;   // range profiles [nIFFT x M x nAnts]: ONE map-set, reused so it stays in L2
     float* d_pow = nullptr;      // |RDM|^2 [nIFFT x nFFT x nAnts x maxBatch]
     uint8_t* d_flags = nullptr;  // CFAR decisions [nCut x nAnts x maxBatch]

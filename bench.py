@@ -36,6 +36,12 @@ SUBFRAMES_PER_STEP = 10
 WORKLOAD = "cfg2: 1 gNB, 8 UE, 4 targets, 8x8, 273 PRB @30 kHz, 1 frame (168 DL symbols) per cell per step"
 
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch group from the committed ncu capture
+# profiles/r1_rdm_warm_traffic_v4.txt (--cache-control none: 499.2 MB per chain of 4 cfg2 map-sets = 124.8 MB per map-set
+# against 104.0 MB algorithmic; the 44 MB range-profile intermediate is written back once, 73 % of its re-read hits L2).
+TRAFFIC = {"rdm_2dfft+cfar": lambda cells: int(124.8e6 * cells)}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -396,7 +402,8 @@ def run_b200(args):
         if n and ms > 0:
             ach = alg[name] / (ms / n * 1e-3) / 1e9
             roof[name] = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                          "frac": round(ach / peak, 4), "traffic": None, "avg_launch_us": round(ms / n * 1e3, 2),
+                          "frac": round(ach / peak, 4), "traffic": TRAFFIC.get(name, lambda c: None)(cells),
+                          "avg_launch_us": round(ms / n * 1e3, 2),
                           "share_of_step": round(ms / ms_total, 4), "peak_source": peak_src}
     if rank == 0:
         line = {
@@ -412,7 +419,9 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(d2h), "api": "simulation-level sensing pass: pinned txWave/txGrid -> estResults"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": dict(roof.get("rdm_2dfft+cfar", {}), kernel="rdm_2dfft+cfar (range IFFT + Doppler FFT + CFAR)"),
+            "roofline": dict(roof.get("rdm_2dfft+cfar", {}),
+                             kernel="rdm_2dfft+cfar: one chain of range IFFT + Doppler FFT launches (one pair per cell) + 2 CFAR "
+                                    "launches, linked by programmatic dependent launch; bytes and time are per chain"),
             "roofline_all": roof, "dominant_group": dom,
         }
         if args.cpu_baseline:
