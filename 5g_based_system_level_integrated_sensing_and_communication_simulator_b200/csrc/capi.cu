@@ -382,7 +382,12 @@ static bool doa_valid(Ctx* c, const isac_doa_config* d) {
 
 int isac_music_doa_host(isac_ctx* h, const isac_doa_config* doa, const double* Ra, int32_t numDets, int32_t* L,
                         double* aziEst, int32_t* nAzi, double* PmusicdB, double* Pmusic) {
-    if (!h || !Ra || !L || !nAzi) return ISAC_ERR_INVALID_ARG;
+    return isac_doa_scan_host(h, doa, ISAC_DOA_MUSIC, Ra, numDets, L, aziEst, nAzi, PmusicdB, Pmusic);
+}
+
+int isac_doa_scan_host(isac_ctx* h, const isac_doa_config* doa, int32_t method, const double* Ra, int32_t numDets, int32_t* L,
+                       double* aziEst, int32_t* nAzi, double* PmusicdB, double* Pmusic) {
+    if (!h || !Ra || !L || !nAzi || method < ISAC_DOA_MUSIC || method > ISAC_DOA_DBF) return ISAC_ERR_INVALID_ARG;
     Ctx* c = &h->c;
     cudaSetDevice(c->device);
     if (!doa_valid(c, doa)) return ISAC_ERR_INVALID_ARG;
@@ -394,7 +399,7 @@ int isac_music_doa_host(isac_ctx* h, const isac_doa_config* doa, const double* R
     ISAC_CUDA_CHECK(c, cudaMemcpyAsync(dRa, Ra, sizeof(double2) * (size_t)n * n, cudaMemcpyHostToDevice, c->stream));
     std::vector<double> azi, PdB, P;
     int Lh = 0;
-    st = music_doa_run(c, d, (const double2*)dRa, numDets, &Lh, azi, PdB, P, c->stream);
+    st = music_doa_run(c, d, (const double2*)dRa, numDets, &Lh, azi, PdB, P, c->stream, method);
     *L = Lh;
     if (st) return st;
     *nAzi = (int32_t)azi.size();

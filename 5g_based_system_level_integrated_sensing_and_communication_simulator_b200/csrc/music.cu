@@ -552,7 +552,7 @@ __device__ void findpeaks_block(const double* __restrict__ y, int S, int L, unsi
 // ULA MUSIC (music.m:73-104), direct noise-subspace form, one CTA per batch item
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
-music_ula_kernel(const double* __restrict__ w, const double2* __restrict__ V, int n, DoaConfig cfg, LSource ls,
+music_ula_kernel(const double* __restrict__ w, const double2* __restrict__ V, int n, DoaConfig cfg, LSource ls, int method,
                  int aSteps, int* __restrict__ Lout, double* __restrict__ P, double* __restrict__ PdB,
                  int* __restrict__ peakLoc, int* __restrict__ nPeaks, int* __restrict__ status) {
     extern __shared__ unsigned char smraw[];
@@ -584,11 +584,16 @@ music_ula_kernel(const double* __restrict__ w, const double2* __restrict__ V, in
         return;
     }
     const double eps1 = 2.220446049250313e-16;
+    // All three scanners are sum_k g_k |u_k' a|^2 over the eigenpairs (w_k, u_k) of Ra:
+    //   MUSIC  g_k = [k >= L]   (a' Un Un' a,  music.m:28-29,90)
+    //   MVDR   g_k = 1 / w_k    (a' Ra^-1 a,   mvdrBF.m:73)
+    //   DBF    g_k = w_k        (a' Ra a,      digitalBF.m:73)
+    const double* __restrict__ wb = w + (long long)b * n;
     for (int a = threadIdx.x; a < aSteps; a += blockDim.x) {
         const double ang = a * cfg.aGran - cfg.aMax / 2.0;            // music.m:88
         const double sd = sind_dev(ang);
         double q = 0.0;
-        for (int k = L; k < n; ++k) {                                  // noise eigenvectors (music.m:28-29)
+        for (int k = (method == kDoaMusic ? L : 0); k < n; ++k) {      // noise eigenvectors (music.m:28-29)
             double re = 0.0, im = 0.0;
             for (int m = 0; m < n; ++m) {
                 const double2 av = cis2pi(-(double)m * cfg.d * sd);    // aULA (music.m:82)
@@ -596,9 +601,10 @@ music_ula_kernel(const double* __restrict__ w, const double2* __restrict__ V, in
                 re += u.x * av.x + u.y * av.y;                         // conj(u)*a
                 im += u.x * av.y - u.y * av.x;
             }
-            q += re * re + im * im;
+            const double g = method == kDoaMusic ? 1.0 : (method == kDoaMvdr ? 1.0 / wb[k] : wb[k]);
+            q += g * (re * re + im * im);
         }
-        Pb[a] = fabs(1.0 / (q + eps1));                                // music.m:90,94
+        Pb[a] = method == kDoaDbf ? fabs(q) : fabs(1.0 / (q + eps1));  // music.m:90,94 / mvdrBF.m:73,77 / digitalBF.m:73,77
     }
     __syncthreads();
     double mx = 0.0;
@@ -623,7 +629,7 @@ music_ula_kernel(const double* __restrict__ w, const double2* __restrict__ V, in
 
 int music_doa_ula(Ctx* ctx, const double* w, const double2* V, int n, int batch, const DoaConfig& cfg,
                   const LSource& ls, int* Lout, double* P, double* PdB, int* peakLoc, int* nPeaks, int* status,
-                  cudaStream_t st) {
+                  cudaStream_t st, int method) {
     if (n < 2 || n > kSmallEigMax) {
         set_error(ctx, "music_doa_ula: array size must be in [2,64]");
         return kErrUnsupported;
@@ -632,7 +638,7 @@ int music_doa_ula(Ctx* ctx, const double* w, const double2* V, int n, int batch,
     const size_t smem = sizeof(double2) * (size_t)n * n + sizeof(double) * aSteps + aSteps + 16;
     cudaFuncSetAttribute(music_ula_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int pr = prof_begin(ctx, kProfMusic, st);
-    music_ula_kernel<<<batch, 512, smem, st>>>(w, V, n, cfg, ls, aSteps, Lout, P, PdB, peakLoc, nPeaks, status);
+    music_ula_kernel<<<batch, 512, smem, st>>>(w, V, n, cfg, ls, method, aSteps, Lout, P, PdB, peakLoc, nPeaks, status);
     prof_end(ctx, pr, st);
     count_launches(ctx, 1);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
@@ -733,7 +739,8 @@ int music_finish_1d(Ctx* ctx, const double* q, int steps, const int* dL, double*
 // UPA (music.m:31-63): one warp per (elevation, azimuth) point
 __global__ void __launch_bounds__(256)
 upa_scan_kernel(const double2* __restrict__ vecs, long long ld, const int* __restrict__ order, int n, DoaConfig cfg,
-                const int* __restrict__ dL, int aSteps, int eSteps, double* __restrict__ P) {
+                const int* __restrict__ dL, int aSteps, int eSteps, double* __restrict__ P, int method,
+                const double* __restrict__ wDesc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (pt >= (long long)aSteps * eSteps) return;
@@ -741,7 +748,7 @@ upa_scan_kernel(const double2* __restrict__ vecs, long long ld, const int* __res
     const double el = e * cfg.eGran - cfg.eMax / 2.0;          // music.m:52
     const double az = a * cfg.aGran - cfg.aMax / 2.0;          // music.m:53
     const double st = sind_dev(el), ca = cosd_dev(az), sa = sind_dev(az);
-    int L = *dL;
+    int L = method == kDoaMusic ? *dL : n;   // MVDR / DBF: weighted sum over ALL eigenpairs (see music_ula_kernel)
     if (L > n) L = n;
     double acc = 0.0;
     for (int k = 0; k < L; ++k) {
@@ -756,40 +763,42 @@ upa_scan_kernel(const double2* __restrict__ vecs, long long ld, const int* __res
         }
         re = warp_sum(re);
         im = warp_sum(im);
-        acc += re * re + im * im;
+        const double g = method == kDoaMusic ? 1.0 : (method == kDoaMvdr ? 1.0 / wDesc[k] : wDesc[k]);
+        acc += g * (re * re + im * im);
     }
     if (lane == 0) {
-        double q = (double)n - acc;
-        if (L >= n) q = 0.0;
-        P[pt] = fabs(1.0 / (q + 2.220446049250313e-16));       // music.m:56 then abs (:61)
+        if (method == kDoaMusic) {
+            double q = (double)n - acc;
+            if (L >= n) q = 0.0;
+            P[pt] = fabs(1.0 / (q + 2.220446049250313e-16));   // music.m:56 then abs (:61)
+        } else if (method == kDoaMvdr) {
+            P[pt] = fabs(1.0 / (acc + 2.220446049250313e-16)); // mvdrBF.m:40,43
+        } else {
+            P[pt] = fabs(acc);                                  // digitalBF.m:40,43
+        }
     }
 }
 
-__global__ void __launch_bounds__(1024) upa_min_kernel(const double* __restrict__ P, long long tot, double* __restrict__ mn) {
-    __shared__ double red[32];
-    double v = INFINITY;
-    for (long long i = threadIdx.x; i < tot; i += blockDim.x) v = fmin(v, P[i]);
+// Pmusic = -abs(P); PmusicNorm = Pmusic./max(Pmusic); mag2db (music.m:61-63, mvdrBF.m:43-45, digitalBF.m:43-45).
+// max() of the [eSteps x aSteps] matrix is MATLAB's column-wise maximum (along the single row when eSteps == 1) and
+// implicit expansion divides every column by its own maximum = minus the column's smallest magnitude.
+// One warp per azimuth column (eSteps > 1) / one warp for the whole row (eSteps == 1).
+__global__ void __launch_bounds__(256)
+upa_norm_db_kernel(const double* __restrict__ P, int eSteps, int aSteps, double* __restrict__ PdB) {
+    const int lane = threadIdx.x & 31;
+    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nCols = eSteps > 1 ? aSteps : 1, len = eSteps > 1 ? eSteps : aSteps;
+    if (col >= nCols) return;
+    const double* __restrict__ c = P + (long long)col * len;
+    double mn = INFINITY;
+    for (int i = lane; i < len; i += 32) mn = fmin(mn, c[i]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double m = INFINITY;
-        for (int wv = 0; wv < 32; ++wv) m = fmin(m, red[wv]);
-        *mn = m;
-    }
-}
-
-__global__ void upa_db_kernel(const double* __restrict__ P, long long tot, const double* __restrict__ mn,
-                              double* __restrict__ PdB) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= tot) return;
-    // Pmusic = -abs(P); PmusicNorm = Pmusic./max(Pmusic) = abs(P)/min(abs(P)); mag2db   (music.m:61-63)
-    PdB[i] = 20.0 * log10(P[i] / *mn);
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    for (int i = lane; i < len; i += 32) PdB[(long long)col * len + i] = 20.0 * log10(c[i] / mn);
 }
 
 int music_doa_upa(Ctx* ctx, const double2* vecs, long long ld, const int* order, int n, const DoaConfig& cfg,
-                  const int* dL, double* P, double* PdB, cudaStream_t st) {
+                  const int* dL, double* P, double* PdB, cudaStream_t st, int method, const double* wDesc) {
     const int aSteps = (int)std::floor((cfg.aMax + 1.0) / cfg.aGran);  // music.m:40
     const int eSteps = (int)std::floor((cfg.eMax + 1.0) / cfg.eGran);  // music.m:41
     if (cfg.nX * cfg.nY != n) {
@@ -797,14 +806,14 @@ int music_doa_upa(Ctx* ctx, const double2* vecs, long long ld, const int* order,
         return kErrInvalidArg;
     }
     const long long tot = (long long)aSteps * eSteps;
-    void* mn = nullptr;
-    int s = ctx_scratch(ctx, 10, sizeof(double), &mn);
-    if (s) return s;
-    upa_scan_kernel<<<(unsigned)((tot + 7) / 8), 256, 0, st>>>(vecs, ld, order, n, cfg, dL, aSteps, eSteps, P);
+    if (method != kDoaMusic && !wDesc) {
+        set_error(ctx, "music_doa_upa: MVDR / beamscan need the eigenvalues");
+        return kErrInvalidArg;
+    }
+    upa_scan_kernel<<<(unsigned)((tot + 7) / 8), 256, 0, st>>>(vecs, ld, order, n, cfg, dL, aSteps, eSteps, P, method, wDesc);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
-    upa_min_kernel<<<1, 1024, 0, st>>>(P, tot, (double*)mn);
-    ISAC_CUDA_CHECK(ctx, cudaGetLastError());
-    upa_db_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, tot, (const double*)mn, PdB);
+    const int nCols = eSteps > 1 ? aSteps : 1;
+    upa_norm_db_kernel<<<(unsigned)((nCols + 7) / 8), 256, 0, st>>>(P, eSteps, aSteps, PdB);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
     return kOk;
 }

@@ -22,6 +22,9 @@ int eig_psd_small(Ctx* ctx, const double2* A, int n, int batch, double* w, doubl
 int svd_onesided_jacobi(Ctx* ctx, double2* G, int m, int n, double2* V, double* sigma, int* order,
                         int* sweepsOut, cudaStream_t st);
 
+// DoA scanners sharing the eigen-decomposition of Ra: doaEstimation.music (music.m:1), mvdrBF (mvdrBF.m:1), digitalBF (digitalBF.m:1)
+enum DoaMethod : int { kDoaMusic = 0, kDoaMvdr = 1, kDoaDbf = 2 };
+
 struct DoaConfig {
     int isUpa;        // 0 = ULA (music.m:73-104), 1 = UPA (music.m:31-71)
     int nAnts;        // ULA: array.numElements
@@ -42,13 +45,14 @@ struct LSource {
 //   Lout[1], P[aSteps] (abs(1/(a'Unn a + eps))), PdB[aSteps], peakLoc[kMaxPeaks] (1-based), nPeaks[1], status[1]
 int music_doa_ula(Ctx* ctx, const double* w, const double2* V, int n, int batch, const DoaConfig& cfg,
                   const LSource& ls, int* Lout, double* P, double* PdB, int* peakLoc, int* nPeaks,
-                  int* status, cudaStream_t st);
+                  int* status, cudaStream_t st, int method = kDoaMusic);
 
 // UPA MUSIC (any n = nX*nY): complement form with the L leading eigenvectors.
 //   vecs: [n x nVecs] column-major; order: indices of the leading columns (descending eigenvalue);
 //   PdB [eSteps x aSteps] column-major = mag2db(Pmusic/max(Pmusic)) with Pmusic = -abs(...) (music.m:61-63)
 int music_doa_upa(Ctx* ctx, const double2* vecs, long long ld, const int* order, int n, const DoaConfig& cfg,
-                  const int* dL, double* P, double* PdB, cudaStream_t st);
+                  const int* dL, double* P, double* PdB, cudaStream_t st, int method = kDoaMusic,
+                  const double* wDesc = nullptr);
 
 // 1-D complement-form scan  q[i] = len - sum_{k<L} |<u_k, a(x_i)>|^2, a[n] = exp(2*pi*j*coef*x_i*n)
 //   vecs columns are scaled by colScale[order[k]] (nullptr -> 1) and conjugated when conjVec != 0.

@@ -213,7 +213,11 @@ int sense_fft2d_collect(SensePlan* p, int batch, std::vector<Fft2dResult>& out) 
 // doaEstimation.music on a given covariance
 // ------------------------------------------------------------------------------------------
 int music_doa_run(Ctx* ctx, const DoaConfig& doa, const double2* dRa, int numDets, int* Lout, std::vector<double>& aziEst,
-                  std::vector<double>& PdB, std::vector<double>& P, cudaStream_t st) {
+                  std::vector<double>& PdB, std::vector<double>& P, cudaStream_t st, int method) {
+    if (method != kDoaMusic && numDets < 1) {  // mvdrBF / digitalBF have no source-count rule: findpeaks needs NPeaks >= 1
+        set_error(ctx, "mvdrBF/digitalBF: numDets must be a positive integer (findpeaks 'NPeaks')");
+        return kErrNumDetsZero;
+    }
     const int n = doa.isUpa ? doa.nX * doa.nY : doa.nAnts;
     int aSteps, eSteps;
     const int spec = doa_spec_len(doa, &aSteps, &eSteps);
@@ -239,7 +243,7 @@ int music_doa_run(Ctx* ctx, const DoaConfig& doa, const double2* dRa, int numDet
             return kErrNumDetsZero;
         }
         if ((s = music_doa_ula(ctx, (double*)w, (double2*)V, n, 1, doa, ls, dL, (double*)dP, (double*)dPdB, dPk, dNp,
-                               dSt, st)))
+                               dSt, st, method)))
             return s;
         int h[8 + kMaxPeaks];
         ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(h, dL, sizeof(int) * (8 + kMaxPeaks), cudaMemcpyDeviceToHost, st));
@@ -284,7 +288,8 @@ int music_doa_run(Ctx* ctx, const DoaConfig& doa, const double2* dRa, int numDet
         set_error(ctx, "music: ULA arrays larger than 64 elements are not supported");
         return kErrUnsupported;
     }
-    if ((s = music_doa_upa(ctx, (double2*)V, n, order, n, doa, dL, (double*)dP, (double*)dPdB, st))) return s;
+    if ((s = music_doa_upa(ctx, (double2*)V, n, order, n, doa, dL, (double*)dP, (double*)dPdB, st, method, (const double*)w)))
+        return s;
     PdB.resize(spec);
     P.resize(spec);
     ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(PdB.data(), dPdB, sizeof(double) * spec, cudaMemcpyDeviceToHost, st));

@@ -38,9 +38,10 @@ struct Fft2dResult {          // estResults of fft2D.m for one map-set
 // D2H + host tail (per-antenna stable sort by peak, unique-stable: fft2D.m:64-102)
 int sense_fft2d_collect(SensePlan* p, int batch, std::vector<Fft2dResult>& out);
 
-// doaEstimation.music on a caller-supplied covariance (device double2 [n x n]); numDets <= 0 -> eigen-gap rule
+// doaEstimation.music / mvdrBF / digitalBF (method = DoaMethod) on a caller-supplied covariance (device double2 [n x n]);
+// MUSIC: numDets <= 0 -> eigen-gap rule
 int music_doa_run(Ctx* ctx, const DoaConfig& doa, const double2* dRa, int numDets, int* L, std::vector<double>& aziEst,
-                  std::vector<double>& PdB, std::vector<double>& P, cudaStream_t st);
+                  std::vector<double>& PdB, std::vector<double>& P, cudaStream_t st, int method = kDoaMusic);
 
 struct Music2dConfig {
     int nSc, nSym, nAnts;

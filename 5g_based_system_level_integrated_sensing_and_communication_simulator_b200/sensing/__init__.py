@@ -5,7 +5,7 @@ import math
 
 import numpy as np
 
-from . import channelModels, detection, estimation  # noqa: F401
+from . import channelModels, detection, estimation, postProcessing  # noqa: F401
 from ._echo import monoStaticSensing  # noqa: F401
 
 LIGHTSPEED = 299792458.0   # physconst('Lightspeed')

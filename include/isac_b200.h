@@ -124,6 +124,19 @@ typedef struct {
 int isac_music_doa_host(isac_ctx* ctx, const isac_doa_config* doa, const double* Ra, int32_t numDets,
                         int32_t* L, double* aziEst, int32_t* nAzi, double* PmusicdB, double* Pmusic);
 
+/* The three DoA scanners of +sensing/+estimation/+doaEstimation share one entry point (same steering vectors, scan
+ * grids, normalisation and findpeaks tail; they differ in the scanned quadratic form):
+ *   ISAC_DOA_MUSIC  1/(a' Un Un' a + eps)   music.m:1      (numDets < 0 -> eigen-gap rule)
+ *   ISAC_DOA_MVDR   1/(a' Ra^-1 a + eps)    [aziEst, eleEst] = doaEstimation.mvdrBF(numDets, radarEstParams, Ra)    mvdrBF.m:1
+ *   ISAC_DOA_DBF    a' Ra a                 [aziEst, eleEst] = doaEstimation.digitalBF(numDets, radarEstParams, Ra) digitalBF.m:1
+ * MVDR / DBF need numDets >= 1 (it is findpeaks' NPeaks); *L returns the source count used.  Outputs as
+ * isac_music_doa_host: the dB spectrum in PdB, the absolute spectrum in P (may be NULL). */
+#define ISAC_DOA_MUSIC 0
+#define ISAC_DOA_MVDR 1
+#define ISAC_DOA_DBF 2
+int isac_doa_scan_host(isac_ctx* ctx, const isac_doa_config* doa, int32_t method, const double* Ra, int32_t numDets,
+                       int32_t* L, double* aziEst, int32_t* nAzi, double* PdB, double* P);
+
 typedef struct isac_sense_plan isac_sense_plan;
 /* estResults = sensing.estimation.fft2D(radarEstParams, cfar, rxGrid, txGrid)
  * (+sensing/+estimation/fft2D.m:1): RDM + CFAR (above) + Ra (fft2D.m:106-107) + MUSIC (fft2D.m:111). */

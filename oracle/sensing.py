@@ -524,7 +524,9 @@ def music_doa(num_dets, rp, Ra):
     ULA: returns (L, aziEst[deg], eleEst=NaN, PmusicdB[1 x 361]).
     UPA: the reference calls the non-existent tools.find2DPeaks (:69) so peak
     lists are undefined; returns (L, None, None, PmusicdB[eSteps x aSteps]) where
-    PmusicdB follows :61-63 literally (Pmusic = -abs(.), normalised by its max).
+    PmusicdB follows :61-63 literally (Pmusic = -abs(.), ``./max(Pmusic)`` = MATLAB's
+    column-wise maximum of a matrix, i.e. every azimuth column is normalised by its own
+    smallest magnitude over the elevation scan).
     """
     ant = rp["antennaType"]
     d = 0.5
@@ -552,10 +554,8 @@ def music_doa(num_dets, rp, Ra):
                 aa = aa.reshape(-1, order="F")
                 q = np.vdot(aa, Uann @ aa)
                 P[e, a] = np.abs(1.0 / (q + EPS1))        # :56 then abs of :61
-        P = -P                                            # :61
-        Pn = P / P.max()                                  # :62
-        PdB = 20.0 * np.log10(Pn)                         # :63
-        return L, None, None, PdB
+        return L, None, None, _upa_normalise_db(P)
+
     n_ants = int(ant["nV"]) * int(ant["p"])                                # numElements (ula.m)
     gran = rp["azimuthScanGranularity"]
     a_max = rp["azimuthScanScale"]
@@ -572,6 +572,75 @@ def music_doa(num_dets, rp, Ra):
     azi = (locs - 1) * gran - a_max / 2.0                                  # :103
     ele = np.full(azi.size, np.nan)
     return L, azi, ele, PdB
+
+
+def _upa_normalise_db(P_abs):
+    """music.m:61-63 / mvdrBF.m:43-45 / digitalBF.m:43-45 on a [eSteps x aSteps] matrix:
+    ``P = -abs(P); Pn = P./max(P); PdB = mag2db(Pn)``.  ``max`` of a matrix runs along the
+    first dimension (column-wise; along the only row when eSteps == 1), implicit expansion
+    divides every column by its own maximum; the maximum of the negated magnitudes is minus
+    the column's smallest magnitude."""
+    P = -np.abs(np.asarray(P_abs, dtype=np.float64))
+    mx = P.max(axis=0, keepdims=True) if P.shape[0] > 1 else P.max(axis=1, keepdims=True)
+    return 20.0 * np.log10(P / mx)
+
+
+def _beamformer_doa(num_dets, rp, Ra, kind):
+    """Shared body of ``mvdrBF`` (+sensing/+estimation/+doaEstimation/mvdrBF.m:11-92) and ``digitalBF``
+    (+sensing/+estimation/+doaEstimation/digitalBF.m:11-93): they differ only in the scanned quantity,
+    ``1./(aa'*Ra^-1*aa + eps(1))`` (mvdrBF.m:40,73) vs ``aa'*Ra*aa`` (digitalBF.m:40,73)."""
+    ant = rp["antennaType"]
+    d = 0.5                                                                 # :12
+    Ra = np.asarray(Ra, dtype=np.complex128)
+    Q = np.linalg.inv(Ra) if kind == "mvdr" else Ra                         # Ra^-1
+
+    def power(aa):
+        q = np.vdot(aa, Q @ aa)
+        return 1.0 / (q + EPS1) if kind == "mvdr" else q
+
+    if ant["type"] == "upa":                                                # :14-55
+        nx, ny = int(ant["nV"]), int(ant["nH"])
+        a_gran, e_gran = rp["azimuthScanGranularity"], rp["elevationScanGranularity"]
+        a_max, e_max = rp["azimuthScanScale"], rp["elevationScanScale"]
+        a_steps = int(math.floor((a_max + 1) / a_gran))
+        e_steps = int(math.floor((e_max + 1) / e_gran))
+        mm = np.arange(nx, dtype=np.float64)[None, :]
+        nn = np.arange(ny, dtype=np.float64)[:, None]
+        P = np.zeros((e_steps, a_steps))
+        for e in range(e_steps):
+            el = e * e_gran - e_max / 2.0
+            for a in range(a_steps):
+                az = a * a_gran - a_max / 2.0
+                aa = np.exp(-2j * np.pi * sind(el) * (mm * d * cosd(az) + nn * d * sind(az)))
+                P[e, a] = np.abs(power(aa.reshape(-1, order="F")))
+        # tools.find2DPeaks (:51) does not exist in the reference: peak lists undefined
+        return None, None, _upa_normalise_db(P)
+    n_ants = int(ant["nV"]) * int(ant["p"])                                 # numElements (ula.m)
+    gran = rp["azimuthScanGranularity"]
+    a_max = rp["azimuthScanScale"]
+    a_steps = int(math.floor((a_max + 1) / gran))
+    nn = np.arange(n_ants, dtype=np.float64)
+    P = np.zeros(a_steps)
+    for a in range(a_steps):                                                # :70-74
+        ang = a * gran - a_max / 2.0
+        aa = np.exp(-2j * np.pi * nn * d * sind(ang))
+        P[a] = np.abs(power(aa))                                            # :77
+    PdB = 20.0 * np.log10(P / P.max())                                      # :78-79
+    _, locs = findpeaks(PdB, int(num_dets))                                 # :85
+    azi = (locs - 1) * gran - a_max / 2.0                                   # :86
+    return azi, np.full(azi.size, np.nan), PdB                              # :87
+
+
+def mvdr_bf(num_dets, rp, Ra):
+    """``[aziEst, eleEst] = doaEstimation.mvdrBF(numDets, radarEstParams, Ra)`` (mvdrBF.m:1).
+    Returns (aziEst, eleEst, PmvdrdB); UPA: (None, None, PmvdrdB[eSteps x aSteps])."""
+    return _beamformer_doa(num_dets, rp, Ra, "mvdr")
+
+
+def digital_bf(num_dets, rp, Ra):
+    """``[aziEst, eleEst] = doaEstimation.digitalBF(numDets, radarEstParams, Ra)`` (digitalBF.m:1).
+    Returns (aziEst, eleEst, PdbfdB); UPA: (None, None, PdbfdB[eSteps x aSteps])."""
+    return _beamformer_doa(num_dets, rp, Ra, "dbf")
 
 
 # ----------------------------------------------------------------------------

@@ -119,3 +119,36 @@ def test_music_on_exact_covariance():
     Uann, _ = S.noise_projector(Ra, 2)
     a = np.exp(-2j * np.pi * np.arange(n) * 0.5 * S.sind(20.0))
     assert abs(np.vdot(a, Uann @ a)) < 1e-10
+
+
+def test_mvdr_and_beamscan_known_answers():
+    """mvdrBF / digitalBF on Ra = p a0 a0' + s I (one on-grid source): closed forms by Sherman-Morrison.
+    a' Ra^-1 a = (n - p |a'a0|^2 / (s + p n)) / s  and  a' Ra a = p |a'a0|^2 + s n."""
+    n, p, s = 16, 3.0, 0.2
+    rp = {"antennaType": {"type": "ula", "nV": 8, "p": 2, "d": 0.5}, "azimuthScanScale": 360, "azimuthScanGranularity": 1}
+    m = np.arange(n)
+    a0 = np.exp(-2j * np.pi * m * 0.5 * S.sind(20.0))
+    Ra = p * np.outer(a0, a0.conj()) + s * np.eye(n)
+    azi_m, ele_m, PdB_m = S.mvdr_bf(2, rp, Ra)
+    azi_d, ele_d, PdB_d = S.digital_bf(2, rp, Ra)
+    assert set(azi_m.tolist()) == {20.0, 160.0} and set(azi_d.tolist()) == {20.0, 160.0}   # mirror-ambiguous ULA scan
+    assert np.all(np.isnan(ele_m)) and np.all(np.isnan(ele_d))
+    ang = np.arange(361) - 180.0
+    g = np.array([abs(np.vdot(np.exp(-2j * np.pi * m * 0.5 * S.sind(x)), a0)) ** 2 for x in ang])
+    P_m = 1.0 / ((n - p * g / (s + p * n)) / s + S.EPS1)
+    P_d = p * g + s * n
+    assert np.abs(PdB_m - 20 * np.log10(P_m / P_m.max())).max() < 1e-9
+    assert np.abs(PdB_d - 20 * np.log10(P_d / P_d.max())).max() < 1e-9
+
+
+def test_upa_spectrum_is_normalised_per_azimuth_column():
+    """music.m:61-63 on a matrix: Pmusic./max(Pmusic) divides every column by ITS maximum (MATLAB max of a matrix is
+    column-wise) -> with Pmusic = -abs(.) every column of the dB map has minimum 0 dB."""
+    rp = {"antennaType": {"type": "upa", "nV": 3, "nH": 3, "p": 1}, "azimuthScanScale": 360, "azimuthScanGranularity": 30,
+          "elevationScanScale": 180, "elevationScanGranularity": 20}
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((9, 40)) + 1j * rng.standard_normal((9, 40))
+    Ra = X @ X.conj().T / 40
+    for spec in (S.music_doa(1, rp, Ra)[3], S.mvdr_bf(1, rp, Ra)[2], S.digital_bf(1, rp, Ra)[2]):
+        assert spec.shape == (9, 12)
+        assert np.allclose(spec.min(axis=0), 0.0) and (spec >= 0).all()

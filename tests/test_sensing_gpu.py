@@ -198,6 +198,68 @@ def test_music_upa_spectrum(P, nxy):
     assert err <= 1e-4
 
 
+@pytest.mark.parametrize("method", ["mvdrBF", "digitalBF"])
+def test_mvdr_and_beamscan_ula(P, method):
+    """doaEstimation.mvdrBF / digitalBF, ULA branch (mvdrBF.m:57-89, digitalBF.m:57-90) vs the float64 oracle:
+    spectra within 1e-5 relative (8.7e-5 dB), peak lists identical."""
+    _lib = importlib.import_module(PKG + "._lib")
+    rng = np.random.default_rng(31)
+    n, N = 16, 4000
+    rp = {"antennaType": {"type": "ula", "nV": 8, "p": 2, "d": 0.5}, "azimuthScanScale": 360,
+          "azimuthScanGranularity": 1, "elevationScanScale": 180, "elevationScanGranularity": 1}
+    angs = np.array([-41.0, 7.0, 33.0])
+    A = np.exp(-2j * np.pi * np.arange(n)[:, None] * 0.5 * S.sind(angs)[None, :])
+    sig = (rng.standard_normal((3, N)) + 1j * rng.standard_normal((3, N))) * np.array([[3.0], [2.0], [1.5]])
+    X = A @ sig + 0.5 * (rng.standard_normal((n, N)) + 1j * rng.standard_normal((n, N)))
+    Ra = X @ X.conj().T / N
+    fn = getattr(P.sensing.estimation.doaEstimation, method)
+    ref = S.mvdr_bf if method == "mvdrBF" else S.digital_bf
+    for nd in (3, 6, 1):
+        azi, ele, spec = fn(nd, rp, Ra, return_spectrum=True)
+        azir, eler, specr = ref(nd, rp, Ra)
+        assert np.array_equal(azi, azir), (nd, azi, azir)
+        assert np.all(np.isnan(ele)) and ele.size == azi.size
+        err = np.abs(spec - specr).max()
+        print(method, "numDets", nd, "azi", azi, "dB spectrum max abs err", err)
+        assert err <= 1e-4
+    for a in angs:   # mirror-ambiguous +-180 deg scan: the true angle or its mirror is among the 6 strongest peaks
+        azi6 = fn(6, rp, Ra)[0]
+        assert any(abs(azi6 - x).min() < 1.5 for x in (a, 180 - a if a > 0 else -180 - a))
+    with pytest.raises(_lib.IsacError) as e:   # no source-count rule in the beamformers: NPeaks must be >= 1
+        fn(None, rp, Ra)
+    assert e.value.status == 7
+
+
+@pytest.mark.parametrize("method", ["mvdrBF", "digitalBF"])
+@pytest.mark.parametrize("nxy", [(4, 4), (9, 8)])
+def test_mvdr_and_beamscan_upa(P, method, nxy):
+    """UPA branch (mvdrBF.m:14-55, digitalBF.m:14-55): spectrum parity incl. MATLAB's column-wise ./max normalisation.
+    (9,8) = 72 elements exercises the multi-CTA Jacobi path."""
+    nX, nY = nxy
+    n = nX * nY
+    rng = np.random.default_rng(17)
+    rp = {"antennaType": {"type": "upa", "nV": nX, "nH": nY, "p": 1, "dV": 0.5, "dH": 0.5}, "azimuthScanScale": 360,
+          "azimuthScanGranularity": 5, "elevationScanScale": 180, "elevationScanGranularity": 4}
+    N = 600
+    mm, nn = np.arange(nX)[None, :], np.arange(nY)[:, None]
+    cols = []
+    for az, el in ((25.0, 32.0), (-70.0, 48.0)):
+        a = np.exp(-2j * np.pi * S.sind(el) * (mm * 0.5 * S.cosd(az) + nn * 0.5 * S.sind(az)))
+        cols.append(a.reshape(-1, order="F"))
+    A = np.stack(cols, axis=1)
+    X = A @ (rng.standard_normal((2, N)) + 1j * rng.standard_normal((2, N))) + 0.4 * (
+        rng.standard_normal((n, N)) + 1j * rng.standard_normal((n, N)))
+    Ra = X @ X.conj().T / N
+    fn = getattr(P.sensing.estimation.doaEstimation, method)
+    ref = S.mvdr_bf if method == "mvdrBF" else S.digital_bf
+    azi, ele, spec = fn(2, rp, Ra, return_spectrum=True)
+    _, _, specr = ref(2, rp, Ra)
+    assert azi is None and ele is None and spec.shape == specr.shape
+    err = np.abs(spec - specr).max()
+    print(method, nxy, "UPA dB spectrum max abs err", err)
+    assert err <= 1e-4
+
+
 @pytest.mark.parametrize("shape", [(96, 40, 4), (60, 90, 4)])
 def test_music2d_matches_oracle(P, shape):
     """music2D (music2D.m:33-123) on tall (nSc>nSym) and wide (nSc<nSym) channel matrices."""

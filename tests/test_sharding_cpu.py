@@ -64,3 +64,21 @@ def test_network_simulation_single_process():
     sim = importlib.import_module(PKG + ".simulation")
     cells = [{"cellID": i, "numTargets": 2} for i in range(3)]
     assert sim.networkSimulation(cells, cell_fn=_fake_cell) == [_fake_cell(c) for c in cells]
+
+
+def test_get_rmse_host_logic():
+    """sensing.postProcessing.getRMSE (getRMSE.m:1): first-match within rRes, NaN for unmatched estimates, NaN when empty."""
+    import importlib
+    import numpy as np
+    pp = importlib.import_module("5g_based_system_level_integrated_sensing_and_communication_simulator_b200.sensing.postProcessing")
+    params = {"rRes": 1.2, "antennaType": {"type": "ula"},
+              "tgtRealPos": [{"Range": 80.0, "Velocity": -12.0, "Elevation": 1.0, "Azimuth": 30.0},
+                             {"Range": 150.0, "Velocity": 5.0, "Elevation": 2.0, "Azimuth": -40.0}]}
+    res = [{"rngEst": [80.5, 149.4], "velEst": [-11.0, 5.5], "aziEst": [31.0, -40.0]},
+           {"rngEst": [300.0], "velEst": [0.0], "aziEst": [0.0]}]
+    out = pp.getRMSE(res, params)
+    assert np.allclose(out["rngRMSE"][:2], [0.5, 0.6]) and np.isnan(out["rngRMSE"][2])
+    assert np.allclose(out["velRMSE"][:2], [1.0, 0.5]) and np.allclose(out["aziRMSE"][:2], [1.0, 0.0])
+    assert np.all(np.isnan(out["eleRMSE"]))
+    empty = pp.getRMSE({"rngEst": [], "velEst": [], "aziEst": []}, params)
+    assert isinstance(empty, float) and np.isnan(empty)
