@@ -115,6 +115,7 @@ def _declare(lib):
         "isac_rdm_get_power": ([vp, i32, vp], C.c_int),
         "isac_rdm_cfar_host": ([vp, vp, vp, i32, i32, vp, vp, vp, vp], C.c_int),
         "isac_music_doa_host": ([vp, P(DoaConfig), vp, i32, P(i32), vp, P(i32), vp, vp], C.c_int),
+        "isac_ofdm_modulate_dev": ([vp, vp, i32, i32, i32, i32, i32, vp, f64, vp, P(C.c_int64)], C.c_int),
         "isac_doa_scan_host": ([vp, P(DoaConfig), i32, vp, i32, P(i32), vp, P(i32), vp, vp], C.c_int),
         "isac_sense_plan_create": ([vp, P(RdmConfig), P(DoaConfig), f64, f64, P(vp)], C.c_int),
         "isac_sense_plan_destroy": ([vp], C.c_int),
@@ -222,7 +223,7 @@ class Context:
         check(self.lib.isac_synchronize(self.handle), self.handle)
 
     PROF_SLOTS = ("rdm_range", "rdm_doppler", "cfar", "echo_demod", "covariance", "music", "pmi_sinr", "cdl",
-                  "prg_precode", "ul_tpmi")
+                  "prg_precode", "ul_tpmi", "ofdm_modulate")
 
     def profile_enable(self, on=True):
         check(self.lib.isac_profile_enable(self.handle, 1 if on else 0), self.handle)

@@ -5,6 +5,7 @@
 #include "rdm.cuh"
 #include "sense.cuh"
 #include "echo.cuh"
+#include "ofdm.cuh"
 #include "comm.cuh"
 #include "cdl.cuh"
 #include <cmath>
@@ -595,6 +596,19 @@ int isac_mono_static_sensing_dev(isac_ctx* h, const isac_echo_config* cfg, const
                                      c->stream);
     if (nSymOut) *nSymOut = n;
     return st;
+}
+
+int isac_ofdm_modulate_dev(isac_ctx* h, const void* txGrid, int32_t nSc, int32_t nSym, int32_t nAnts, int32_t nfft,
+                           int32_t symbolsPerSubframe, const int32_t* cpLengths, double scale, void* txWaveform, int64_t* T) {
+    if (!h || !cpLengths || symbolsPerSubframe < 1 || nSym < 1) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    OfdmConfig o{};
+    o.nSc = nSc; o.nSym = nSym; o.nAnts = nAnts; o.nfft = nfft;
+    o.symbolsPerSubframe = symbolsPerSubframe; o.cpLengths = cpLengths; o.scale = scale;
+    if (T) *T = ofdm_waveform_length(o);
+    if (!txWaveform) return ISAC_OK;  // size query
+    return ofdm_modulate_run(c, o, (const float2*)txGrid, (float2*)txWaveform, c->stream);
 }
 
 int isac_mono_static_sensing_host(isac_ctx* h, const isac_echo_config* cfg, const void* txHost, const void* noiseHost,

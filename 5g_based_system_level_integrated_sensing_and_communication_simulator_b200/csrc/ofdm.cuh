@@ -1,0 +1,20 @@
+// CP-OFDM modulation of the sensing transmit grid (gNBPhy.m:599): declarations shared with capi.cu.
+#pragma once
+#include "isac_common.cuh"
+
+namespace isac {
+
+constexpr int kOfdmMaxSymPerSubframe = 56;  // symbols per subframe up to 60 kHz subcarrier spacing
+
+struct OfdmConfig {
+    int nSc, nSym, nAnts, nfft;
+    int symbolsPerSubframe;  // length of cpLengths
+    const int* cpLengths;    // nrOFDMInfo.CyclicPrefixLengths of one subframe
+    double scale;            // signalAmp (gNBPhy.m:599)
+};
+
+long long ofdm_waveform_length(const OfdmConfig& c);
+// grid: device [nSc x nSym x nAnts] float2; wave: device [T x nAnts] float2, T = ofdm_waveform_length(c)
+int ofdm_modulate_run(Ctx* ctx, const OfdmConfig& c, const float2* grid, float2* wave, cudaStream_t st);
+
+}  // namespace isac

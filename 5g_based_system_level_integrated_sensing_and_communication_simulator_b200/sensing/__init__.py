@@ -6,7 +6,7 @@ import math
 import numpy as np
 
 from . import channelModels, detection, estimation, postProcessing  # noqa: F401
-from ._echo import monoStaticSensing  # noqa: F401
+from ._echo import monoStaticSensing, ofdmModulate  # noqa: F401
 
 LIGHTSPEED = 299792458.0   # physconst('Lightspeed')
 BOLTZMANN = 1.380649e-23   # physconst('Boltzmann')

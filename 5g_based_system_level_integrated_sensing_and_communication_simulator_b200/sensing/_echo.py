@@ -101,3 +101,37 @@ def monoStaticSensing(txWaveform, txDimension, carrierInfo, radarParams, targetL
     if dev_in:
         return out
     return out.cpu().numpy().transpose(2, 1, 0).copy()
+
+
+def ofdmModulate(carrierInfo, txGrid, scale=1.0):
+    """``txWaveform = scale * nrOFDMModulate(carrier, txGrid)`` -- the gNB PHY step that produces the waveform handed to
+    ``monoStaticSensing`` (reference +phyLayer/gNBPhy.m:599, accumulation for sensing at :604-612), on the device
+    (csrc/ofdm.cu).  Plain CP-OFDM: the toolbox's default windowing is not applied.
+
+    ``txGrid``: [nSc x nSym x nAnts] NumPy -> returns [T x nAnts] NumPy complex64;
+    torch CUDA [nAnts][nSym][nSc] -> torch CUDA [nAnts][T]."""
+    import torch
+    ctx = _lib.get_context(None)
+    num = ofdm_numerology(int(carrierInfo["NRBsDL"]), float(carrierInfo["SubcarrierSpacing"]))
+    cp = np.ascontiguousarray(num["CyclicPrefixLengths"], dtype=np.int32)
+    dev_in = _is_dev(txGrid)
+    if dev_in:
+        g_d = txGrid.contiguous()
+        nAnts, nSym, nSc = g_d.shape
+    else:
+        g = np.asarray(txGrid)
+        if g.ndim == 2:
+            g = g[:, :, None]
+        nSc, nSym, nAnts = g.shape
+        g_d = torch.from_numpy(np.ascontiguousarray(g.astype(np.complex64).transpose(2, 1, 0))).cuda()
+    if nSc != 12 * int(carrierInfo["NRBsDL"]):
+        raise _lib.IsacError(1, "txGrid must span 12*NRBsDL subcarriers")
+    T = C.c_int64()
+    args = (ctx.handle, _lib.ptr(g_d), nSc, nSym, nAnts, int(num["Nfft"]), int(cp.size), cp.ctypes.data, float(scale))
+    ctx.use_torch_stream()
+    _lib.check(ctx.lib.isac_ofdm_modulate_dev(*args, None, C.byref(T)), ctx.handle)
+    out = torch.empty((nAnts, T.value), dtype=torch.complex64, device=g_d.device)
+    _lib.check(ctx.lib.isac_ofdm_modulate_dev(*args, _lib.ptr(out), C.byref(T)), ctx.handle)
+    if dev_in:
+        return out
+    return out.cpu().numpy().T.copy()

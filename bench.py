@@ -317,12 +317,19 @@ def run_b200(args):
     value = cells * SUBFRAMES_PER_STEP * world / (ms_step * 1e-3)
 
     # ---- end-to-end through the host API (pinned host in, host results out) -------------------------
-    pin_wave = [torch.from_numpy(np.ascontiguousarray(host_wave[c % uniq].T)).pin_memory() for c in range(uniq)]
+    # Per step and cell the transmit GRID crosses PCIe (pinned -> device); the waveform the gNB PHY derives from it
+    # (txWaveform = signalAmp * nrOFDMModulate(txGrid), gNBPhy.m:599) is produced on the device by
+    # isac_ofdm_modulate_dev, then the simulation-level sensing pass (cellSimulation.m:191-197) runs and estResults come
+    # back to the host.  COMM results (PMI/RI/CQI/TPMI) land on the host inside comm.step().
     pin_grid = [torch.from_numpy(np.ascontiguousarray(host_grid[c % uniq].transpose(2, 1, 0))).pin_memory() for c in range(uniq)]
     # Two sets of device staging buffers: the copy stream fills set (s+1)%2 with the next step's inputs while the compute
     # stream works on set s%2, so PCIe traffic overlaps the COMM/sensing kernels of the step before.
-    stage_wave = [[torch.empty((nTx, T), dtype=torch.complex64, device="cuda") for _ in range(cells)] for _ in range(2)]
     stage_grid = [tx_grid_d, torch.empty_like(tx_grid_d)]
+    wave_d = [torch.empty((nTx, T), dtype=torch.complex64, device="cuda") for _ in range(cells)]
+    num = W.ofdm_numerology(int(car["NRBsDL"]), float(car["SubcarrierSpacing"]))
+    cp_len = np.ascontiguousarray(num["CyclicPrefixLengths"], dtype=np.int32)
+    amp = 10.0 ** ((cell["gNBTxPower"] - 30.0) / 20.0) * np.sqrt(num["Nfft"] ** 2 / (nSc * nTx))   # signalAmp (gNBPhy.m:596-599)
+    T_out = C.c_int64()
     copy_stream = torch.cuda.Stream()
     copied = [torch.cuda.Event(), torch.cuda.Event()]     # set s holds the inputs of its step
     consumed = [torch.cuda.Event(), torch.cuda.Event()]   # the sensing pass that read set s has been enqueued and finished
@@ -332,7 +339,6 @@ def run_b200(args):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[s])
             for c in range(cells):
-                stage_wave[s][c].copy_(pin_wave[c % uniq], non_blocking=True)
                 stage_grid[s][c].copy_(pin_grid[c % uniq], non_blocking=True)
             copied[s].record(copy_stream)
 
@@ -340,12 +346,14 @@ def run_b200(args):
         s = step % 2
         if not last:
             upload(step + 1)
-        comm.step(step)   # COMM results already land on the host (PMI/RI/CQI/TPMI); H is generated on the device
-        # simulation.cellSimulation's sensing pass (cellSimulation.m:191-197) per cell: txWave+txGrid in, estResults out
+        comm.step(step)
         ctx.use_torch_stream()
         torch.cuda.current_stream().wait_event(copied[s])
         for c in range(cells):
-            _lib.check(ctx.lib.isac_mono_static_sensing_dev(ctx.handle, C.byref(eargs.cfg), _lib.ptr(stage_wave[s][c]), None,
+            _lib.check(ctx.lib.isac_ofdm_modulate_dev(ctx.handle, _lib.ptr(stage_grid[s][c]), nSc, nSym, nTx, int(num["Nfft"]),
+                                                      int(cp_len.size), cp_len.ctypes.data, float(amp), _lib.ptr(wave_d[c]),
+                                                      C.byref(T_out)), ctx.handle)
+            _lib.check(ctx.lib.isac_mono_static_sensing_dev(ctx.handle, C.byref(eargs.cfg), _lib.ptr(wave_d[c]), None,
                                                             _lib.NOISE_PHILOX, 7919 * step + c, _lib.ptr(rx_grid_d[c]),
                                                             C.byref(nsym_out)), ctx.handle)
         plan.run_dev(rx_grid_d, stage_grid[s], cells)
@@ -358,6 +366,7 @@ def run_b200(args):
     upload(0)
     step_e2e(0, True)
     torch.cuda.synchronize()
+    assert T_out.value == T, (T_out.value, T)
     if world > 1:
         dist.barrier()
     t0 = time.time()
@@ -371,7 +380,8 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     e2e_value = cells * SUBFRAMES_PER_STEP * world * e2e_steps / t_e2e
-    h2d = cells * (T * nTx * 8 + nSc * nSym * nTx * 8)
+    n_est_e2e = [len(r["rngEst"]) for r in out]
+    h2d = cells * (nSc * nSym * nTx * 8)
     d2h = cells * (nTx * 4 + 64 * 8 + 16) + comm.d2h_bytes_per_step()  # detections/estimates + CSI / TPMI reports
 
     sampler.stop()
@@ -412,11 +422,14 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (MUSIC/CFAR compare in f64)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "cells_per_gpu": cells, "stages": stages,
-                       "l2_policy": "inputs (%.0f MB per step) larger than L2; no flush" % (h2d / 1e6),
+                       "l2_policy": "inputs (%.0f MB of waveforms + grids per step) larger than L2; no flush"
+                                    % (cells * (T * nTx * 8 + nSc * nSym * nTx * 8) / 1e6),
                        "rd_map_sets_per_sec": round(cells * world / (ms_step * 1e-3), 1),
                        "detections_sanity": n_est[:4]},
             "e2e": {"value": round(e2e_value, 2), "unit": "cell-subframes/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "api": "simulation-level sensing pass: pinned txWave/txGrid -> estResults"},
+                    "d2h_bytes_per_step": int(d2h), "api": "pinned txGrid -> device OFDM modulation (gNBPhy.m:599) -> simulation-level sensing pass "
+                           "(cellSimulation.m:191-197) -> estResults on the host; CSI/TPMI reports on the host",
+                    "detections_sanity": n_est_e2e[:4]},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": dict(roof.get("rdm_2dfft+cfar", {}),

@@ -213,6 +213,15 @@ int isac_mono_static_sensing_host(isac_ctx* ctx, const isac_echo_config* cfg, co
                                   const void* noiseHost, int32_t noiseMode, uint64_t seed, void* echoGridHost,
                                   int32_t* nSymOut);
 
+/* txWaveform = scale * nrOFDMModulate(carrier, txGrid)  (+phyLayer/gNBPhy.m:599; the grid / waveform pair the gNB PHY
+ * accumulates for sensing, gNBPhy.m:604-612) -- SURVEY 8(f) row 2: the step immediately before the sensing hot path.
+ * txGrid: device complex64 [nSc x nSym x nAnts]; txWaveform: device complex64 [T x nAnts] with
+ * T = sum_s (cpLengths[s mod symbolsPerSubframe] + nfft), returned in *T (call with txWaveform == NULL to query it).
+ * Plain CP-OFDM (IFFT + cyclic prefix): the toolbox's default raised-cosine windowing is not applied. */
+int isac_ofdm_modulate_dev(isac_ctx* ctx, const void* txGrid, int32_t nSc, int32_t nSym, int32_t nAnts, int32_t nfft,
+                           int32_t symbolsPerSubframe, const int32_t* cpLengths, double scale, void* txWaveform,
+                           int64_t* T);
+
 /* ---- K7-K10, K12: Type-I codebook, PMI / RI / CQI selection, UL TPMI selection, PRG precoding --------- */
 typedef struct {
     int32_t nPorts;                    /* csirs.NumCSIRSPorts                                  dlPMISelect.m:326 */

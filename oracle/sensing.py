@@ -188,6 +188,35 @@ def ofdm_demodulate(nrb, scs_khz, wave, cp_fraction=0.5):
     return grid
 
 
+def ofdm_modulate(nrb, scs_khz, grid, scale=1.0):
+    """``scale * nrOFDMModulate(carrier, grid)`` as called at gNBPhy.m:599 (the waveform the gNB PHY accumulates for
+    sensing, gNBPhy.m:604-612).
+
+    PARITY-UNPINNED (5G Toolbox): TS 38.211 5.3.1 CP-OFDM -- subcarrier k of the grid on FFT bin (k - nSc/2) mod Nfft,
+    ``ifft`` (1/Nfft), cyclic prefix = copy of the symbol's tail, symbols laid end to end from a subframe boundary.
+    The toolbox's default raised-cosine windowing with symbol overlap is NOT applied (its window length table is not
+    public); the result is the exact inverse of ``ofdm_demodulate`` above.  Returns [T x nAnts]."""
+    info = ofdm_info(nrb, scs_khz)
+    nfft = info["Nfft"]
+    grid = np.asarray(grid, dtype=np.complex128)
+    if grid.ndim == 2:
+        grid = grid[:, :, None]
+    nsc, nsym, nants = grid.shape
+    starts = ofdm_symbol_starts(info, nsym)
+    per = info["SymbolLengths"].size
+    T = int(starts[-1] + info["SymbolLengths"][(nsym - 1) % per])
+    wave = np.zeros((T, nants), dtype=np.complex128)
+    bins = np.mod(np.arange(nsc) - nsc // 2, nfft)
+    for s in range(nsym):
+        spec = np.zeros((nfft, nants), dtype=np.complex128)
+        spec[bins, :] = grid[:, s, :]
+        x = np.fft.ifft(spec, axis=0) * scale
+        cp = int(info["CyclicPrefixLengths"][s % per])
+        wave[starts[s]: starts[s] + cp, :] = x[nfft - cp:, :]
+        wave[starts[s] + cp: starts[s] + cp + nfft, :] = x
+    return wave
+
+
 # ----------------------------------------------------------------------------
 # a1: sensing.radarParams  (+sensing/radarParams.m:1-146)
 # ----------------------------------------------------------------------------

@@ -152,3 +152,20 @@ def test_upa_spectrum_is_normalised_per_azimuth_column():
     for spec in (S.music_doa(1, rp, Ra)[3], S.mvdr_bf(1, rp, Ra)[2], S.digital_bf(1, rp, Ra)[2]):
         assert spec.shape == (9, 12)
         assert np.allclose(spec.min(axis=0), 0.0) and (spec >= 0).all()
+
+
+def test_ofdm_modulate_is_the_inverse_of_demodulate():
+    """oracle nrOFDMModulate restatement (gNBPhy.m:599): demodulate(modulate(grid)) == grid for every CP pattern, and the
+    cyclic prefix is the symbol's tail (TS 38.211 5.3.1)."""
+    rng = np.random.default_rng(4)
+    for nrb, scs, nsym in ((24, 15, 17), (52, 30, 31), (6, 60, 57)):
+        nsc = 12 * nrb
+        grid = rng.standard_normal((nsc, nsym, 2)) + 1j * rng.standard_normal((nsc, nsym, 2))
+        wave = S.ofdm_modulate(nrb, scs, grid, 2.0)
+        info = S.ofdm_info(nrb, scs)
+        starts = S.ofdm_symbol_starts(info, nsym)
+        assert wave.shape[0] == starts[-1] + info["SymbolLengths"][(nsym - 1) % info["SymbolLengths"].size]
+        cp0 = int(info["CyclicPrefixLengths"][0])
+        assert np.allclose(wave[:cp0], wave[info["Nfft"]: info["Nfft"] + cp0])
+        back = S.ofdm_demodulate(nrb, scs, wave / 2.0)
+        assert np.abs(back - grid).max() < 1e-12

@@ -198,6 +198,26 @@ def test_music_upa_spectrum(P, nxy):
     assert err <= 1e-4
 
 
+@pytest.mark.parametrize("nrb_scs_sym", [(24, 15, 17), (52, 15, 30), (106, 30, 29), (273, 30, 28), (11, 15, 5), (6, 60, 57)])
+def test_ofdm_modulate_matches_oracle_and_round_trips(P, nrb_scs_sym):
+    """sensing.ofdmModulate (gNBPhy.m:599) vs the float64 oracle for every FFT size (128 .. 4096, odd symbol counts that
+    cross subframe boundaries), and the size-independent property demodulate(modulate(grid)) == grid."""
+    nrb, scs, nsym = nrb_scs_sym
+    rng = np.random.default_rng(nrb + nsym)
+    nsc, nants = 12 * nrb, 3
+    grid = (rng.standard_normal((nsc, nsym, nants)) + 1j * rng.standard_normal((nsc, nsym, nants))).astype(np.complex64)
+    car = {"NRBsDL": nrb, "SubcarrierSpacing": scs}
+    wave = P.sensing.ofdmModulate(car, grid, scale=37.5)
+    ref = S.ofdm_modulate(nrb, scs, grid, 37.5)
+    assert wave.shape == ref.shape
+    err = np.abs(wave - ref).max() / np.abs(ref).max()
+    print(nrb_scs_sym, "Nfft", S.ofdm_info(nrb, scs)["Nfft"], "T", wave.shape[0], "waveform err rel-to-peak", err)
+    assert err <= 1e-5   # fp32 IFFT against the float64 oracle
+    back = S.ofdm_demodulate(nrb, scs, wave.astype(np.complex128) / 37.5)
+    assert back.shape == grid.shape
+    assert np.abs(back - grid).max() / np.abs(grid).max() <= 1e-5
+
+
 @pytest.mark.parametrize("method", ["mvdrBF", "digitalBF"])
 def test_mvdr_and_beamscan_ula(P, method):
     """doaEstimation.mvdrBF / digitalBF, ULA branch (mvdrBF.m:57-89, digitalBF.m:57-90) vs the float64 oracle:
