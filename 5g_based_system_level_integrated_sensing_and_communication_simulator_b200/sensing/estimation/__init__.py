@@ -15,8 +15,10 @@ _plans = {}
 class SensePlan:
     """Device plan of the fft2D estimator (RDM + CFAR + covariance + MUSIC), see csrc/sense.cu."""
 
-    def __init__(self, radarEstParams, cfar, grid_shape, max_batch=1, device=None):
-        self.ctx = _lib.get_context(device)
+    def __init__(self, radarEstParams, cfar, grid_shape, max_batch=1, device=None, ctx=None):
+        # ctx: a dedicated library context (own stream / scratch buffers), e.g. to run the sensing pass on a second
+        # CUDA stream concurrently with the COMM kernels of the process-wide context
+        self.ctx = ctx if ctx is not None else _lib.get_context(device)
         lib = self.ctx.lib
         nSc, nSym, nAnts = grid_shape
         det = cfar["cfarDetector2D"]

@@ -262,17 +262,25 @@ def run_b200(args):
     tx_grid_d = torch.stack([to_dev_grid(host_grid[c % uniq]) for c in range(cells)])   # [cells][nAnts][nSym][nSc]
     tx_wave_d = [to_dev_wave(host_wave[c % uniq]) for c in range(cells)]                # each [nTx][T]
     rx_grid_d = torch.empty_like(tx_grid_d)
-    plan = est.SensePlan(rp, cf, (nSc, nSym, nTx), max_batch=cells, device=local)
+    # The sensing pass and the COMM slots of a cell are independent (cellSimulation.m runs the sensing pass after the slot
+    # loop on the accumulated Tx grid only).  The sensing chain has its own library context; in the end-to-end leg it is
+    # enqueued on its own CUDA stream so that its kernels fill the GPU while the host is busy with the (synchronising)
+    # CSI / TPMI report tails.
+    ctx_s = _lib.Context(local)
+    sense_stream = torch.cuda.Stream()
+    plan = est.SensePlan(rp, cf, (nSc, nSym, nTx), max_batch=cells, device=local, ctx=ctx_s)
     eargs = echo._EchoArgs(T, nTx, rp, los, car, nSym)
     import ctypes as C
     nsym_out = C.c_int32()
 
     def sensing_step_dev(step):
-        ctx.use_torch_stream()
+        # device-resident leg: ONE stream, so that the CUDA-event intervals around each kernel group (the live roofline
+        # figures) are not stretched by kernels of another stream competing for the SMs
+        ctx_s.use_torch_stream()
         for c in range(cells):
-            _lib.check(ctx.lib.isac_mono_static_sensing_dev(ctx.handle, C.byref(eargs.cfg), _lib.ptr(tx_wave_d[c]), None,
-                                                            _lib.NOISE_PHILOX, 7919 * step + c, _lib.ptr(rx_grid_d[c]),
-                                                            C.byref(nsym_out)), ctx.handle)
+            _lib.check(ctx_s.lib.isac_mono_static_sensing_dev(ctx_s.handle, C.byref(eargs.cfg), _lib.ptr(tx_wave_d[c]), None,
+                                                              _lib.NOISE_PHILOX, 7919 * step + c, _lib.ptr(rx_grid_d[c]),
+                                                              C.byref(nsym_out)), ctx_s.handle)
         plan.run_dev(rx_grid_d, tx_grid_d, cells)
 
     stages = ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa",
@@ -294,8 +302,9 @@ def run_b200(args):
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    ctx.profile_collect()
-    ctx.profile_enable(True)
+    for cx in (ctx, ctx_s):
+        cx.profile_collect()
+        cx.profile_enable(True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
@@ -307,7 +316,11 @@ def run_b200(args):
     t_wall1 = time.time()
     ms_total = e0.elapsed_time(e1)
     prof, launches = ctx.profile_collect()
-    ctx.profile_enable(False)
+    prof_s, launches_s = ctx_s.profile_collect()
+    prof.update(prof_s)                                         # disjoint kernel groups (sensing vs COMM)
+    launches += launches_s
+    for cx in (ctx, ctx_s):
+        cx.profile_enable(False)
     if world > 1:
         dist.barrier()
         t = torch.tensor([ms_total], device="cuda")
@@ -346,21 +359,24 @@ def run_b200(args):
         s = step % 2
         if not last:
             upload(step + 1)
-        comm.step(step)
-        ctx.use_torch_stream()
-        torch.cuda.current_stream().wait_event(copied[s])
-        for c in range(cells):
-            _lib.check(ctx.lib.isac_ofdm_modulate_dev(ctx.handle, _lib.ptr(stage_grid[s][c]), nSc, nSym, nTx, int(num["Nfft"]),
-                                                      int(cp_len.size), cp_len.ctypes.data, float(amp), _lib.ptr(wave_d[c]),
-                                                      C.byref(T_out)), ctx.handle)
-            _lib.check(ctx.lib.isac_mono_static_sensing_dev(ctx.handle, C.byref(eargs.cfg), _lib.ptr(wave_d[c]), None,
-                                                            _lib.NOISE_PHILOX, 7919 * step + c, _lib.ptr(rx_grid_d[c]),
-                                                            C.byref(nsym_out)), ctx.handle)
-        plan.run_dev(rx_grid_d, stage_grid[s], cells)
-        consumed[s].record(torch.cuda.current_stream())
-        return plan.collect(cells)   # D2H of detections / estimates (synchronises)
+        with torch.cuda.stream(sense_stream):
+            ctx_s.use_torch_stream()
+            sense_stream.wait_event(copied[s])
+            for c in range(cells):
+                _lib.check(ctx_s.lib.isac_ofdm_modulate_dev(ctx_s.handle, _lib.ptr(stage_grid[s][c]), nSc, nSym, nTx,
+                                                            int(num["Nfft"]), int(cp_len.size), cp_len.ctypes.data, float(amp),
+                                                            _lib.ptr(wave_d[c]), C.byref(T_out)), ctx_s.handle)
+                _lib.check(ctx_s.lib.isac_mono_static_sensing_dev(ctx_s.handle, C.byref(eargs.cfg), _lib.ptr(wave_d[c]), None,
+                                                                  _lib.NOISE_PHILOX, 7919 * step + c, _lib.ptr(rx_grid_d[c]),
+                                                                  C.byref(nsym_out)), ctx_s.handle)
+            plan.run_dev(rx_grid_d, stage_grid[s], cells)
+            consumed[s].record(sense_stream)
+        comm.step(step)              # CSI / TPMI reports land on the host (synchronising tails) while the sensing chain runs
+        with torch.cuda.stream(sense_stream):
+            return plan.collect(cells)   # D2H of detections / estimates (synchronises the sensing stream)
 
     e2e_steps = max(1, min(args.steps, 5))
+    torch.cuda.synchronize()
     for ev in consumed:
         ev.record(torch.cuda.current_stream())
     upload(0)
