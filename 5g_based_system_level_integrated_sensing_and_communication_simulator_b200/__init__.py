@@ -4,7 +4,8 @@ Host-side mirror of the reference's MATLAB package API for the one data-parallel
 repository accelerates:
 
     sensing.radarParams, sensing.monoStaticSensing, sensing.channelModels.basicRadarChannel,
-    sensing.detection.cfar2D, sensing.estimation.fft2D / music2D / doaEstimation.music,
+    sensing.detection.cfar2D, sensing.estimation.fft2D / music2D / doaEstimation.{music, mvdrBF, digitalBF},
+    sensing.ofdmModulate, sensing.postProcessing.getRMSE, networkTopology.blockages.city.checkLoS,
     communication.phyLayer.{dlPMISelect, riSelect, cqiSelect, pmiSelect, precodedSINR,
     sinrPerSubband, prgPrecode}, communication.pmiType1SinglePanelCodebook,
     simulation.cellSimulation (hot-path driver).
@@ -20,12 +21,12 @@ The directory name starts with a digit, so import it with
 """
 from . import _lib  # noqa: F401  (does not load the .so until first use)
 
-__all__ = ["_lib", "sensing", "communication", "simulation", "workloads"]
+__all__ = ["_lib", "sensing", "communication", "simulation", "networkTopology", "workloads"]
 __version__ = "0.1.0"
 
 
 def __getattr__(name):
     import importlib
-    if name in ("sensing", "communication", "simulation", "workloads", "build"):
+    if name in ("sensing", "communication", "simulation", "networkTopology", "workloads", "build"):
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

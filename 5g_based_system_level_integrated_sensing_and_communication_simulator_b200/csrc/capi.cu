@@ -6,6 +6,7 @@
 #include "sense.cuh"
 #include "echo.cuh"
 #include "ofdm.cuh"
+#include "los.cuh"
 #include "comm.cuh"
 #include "cdl.cuh"
 #include <cmath>
@@ -83,6 +84,9 @@ struct isac_ctx {
 };
 struct isac_rdm_plan {
     RdmPlan* p;
+};
+struct isac_city {
+    CityPlan* p;
 };
 struct isac_sense_plan {
     SensePlan* p;
@@ -596,6 +600,54 @@ int isac_mono_static_sensing_dev(isac_ctx* h, const isac_echo_config* cfg, const
                                      c->stream);
     if (nSymOut) *nSymOut = n;
     return st;
+}
+
+// ---- city layout: LoS / blockage ---------------------------------------------------------------
+int isac_city_create(isac_ctx* h, int32_t nWalls, const int32_t* wallOffsets, const double* corners, isac_city** out) {
+    if (!h || !out) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(h->c.device);
+    CityPlan* p = nullptr;
+    int st = city_plan_create(&h->c, nWalls, wallOffsets, corners, &p);
+    if (st) return st;
+    *out = new isac_city{p};
+    return ISAC_OK;
+}
+
+int isac_city_destroy(isac_city* c) {
+    if (!c) return ISAC_OK;
+    if (c->p) {
+        cudaSetDevice(c->p->ctx->device);
+        cudaStreamSynchronize(c->p->ctx->stream);
+        city_plan_destroy(c->p);
+    }
+    delete c;
+    return ISAC_OK;
+}
+
+int isac_city_check_los_dev(isac_city* c, int32_t nLinks, const double* uePos, const double* antPos, int32_t nAnt, int32_t* los) {
+    if (!c || !c->p || (nAnt != 1 && nAnt != nLinks)) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(c->p->ctx->device);
+    return city_check_los(c->p, nLinks, uePos, antPos, nAnt == 1 ? 0 : 3, los, c->p->ctx->stream);
+}
+
+int isac_city_check_los_host(isac_city* c, int32_t nLinks, const double* uePos, const double* antPos, int32_t nAnt, int32_t* los) {
+    if (!c || !c->p || !uePos || !antPos || !los || nLinks < 1 || (nAnt != 1 && nAnt != nLinks)) return ISAC_ERR_INVALID_ARG;
+    Ctx* x = c->p->ctx;
+    cudaSetDevice(x->device);
+    const size_t bU = sizeof(double) * 3 * (size_t)nLinks, bA = sizeof(double) * 3 * (size_t)nAnt, bL = sizeof(int32_t) * (size_t)nLinks;
+    void* d = nullptr;
+    int st = ctx_scratch(x, 18, bU + bA + bL, &d);
+    if (st) return st;
+    double* dU = (double*)d;
+    double* dA = (double*)((char*)d + bU);
+    int* dL = (int*)((char*)d + bU + bA);
+    ISAC_CUDA_CHECK(x, cudaMemcpyAsync(dU, uePos, bU, cudaMemcpyHostToDevice, x->stream));
+    ISAC_CUDA_CHECK(x, cudaMemcpyAsync(dA, antPos, bA, cudaMemcpyHostToDevice, x->stream));
+    st = city_check_los(c->p, nLinks, dU, dA, nAnt == 1 ? 0 : 3, dL, x->stream);
+    if (st) return st;
+    ISAC_CUDA_CHECK(x, cudaMemcpyAsync(los, dL, bL, cudaMemcpyDeviceToHost, x->stream));
+    ISAC_CUDA_CHECK(x, cudaStreamSynchronize(x->stream));
+    return ISAC_OK;
 }
 
 int isac_ofdm_modulate_dev(isac_ctx* h, const void* txGrid, int32_t nSc, int32_t nSym, int32_t nAnts, int32_t nfft,

@@ -222,6 +222,22 @@ int isac_ofdm_modulate_dev(isac_ctx* ctx, const void* txGrid, int32_t nSc, int32
                            int32_t symbolsPerSubframe, const int32_t* cpLengths, double scale, void* txWaveform,
                            int64_t* T);
 
+/* ---- LoS / blockage geometry of the city layout ---------------------------------------------------
+ * losDecision = simuLayout.checkLoS(uePos, antPos)  (+networkTopology/+blockages/openStreetMapCity.m:67; call sites
+ * +simulation/networkSimulation.m:138 (UEs) and :154 (targets), one MATLAB call per link) for a whole batch of links.
+ * A city is the list of wall polygons of its buildings (building.m:61-73: one 4-corner wall per floor-plan edge plus the
+ * ceiling); corners: host double [3 x nCorners] column-major, walls concatenated, wallOffsets[nWalls+1] (first = 0).
+ * Link i is blocked when the winding number of the user projected along the link onto any wall plane exceeds 0.1
+ * (wallBlockage.m:121-127, :178-222).  uePos [3 x nLinks]; antPos [3 x nAnt], nAnt == nLinks (element-wise pairs) or 1
+ * (one antenna for all links); los[i] = 1 for line of sight, 0 for blocked. */
+typedef struct isac_city isac_city;
+int isac_city_create(isac_ctx* ctx, int32_t nWalls, const int32_t* wallOffsets, const double* corners, isac_city** city);
+int isac_city_destroy(isac_city* city);
+int isac_city_check_los_host(isac_city* city, int32_t nLinks, const double* uePos, const double* antPos, int32_t nAnt,
+                             int32_t* los);
+int isac_city_check_los_dev(isac_city* city, int32_t nLinks, const double* uePos, const double* antPos, int32_t nAnt,
+                            int32_t* los);   /* device pointers, results stay on the device */
+
 /* ---- K7-K10, K12: Type-I codebook, PMI / RI / CQI selection, UL TPMI selection, PRG precoding --------- */
 typedef struct {
     int32_t nPorts;                    /* csirs.NumCSIRSPorts                                  dlPMISelect.m:326 */

@@ -14,6 +14,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+from oracle import geometry as OG  # noqa: E402
 from oracle import cdl as OCDL  # noqa: E402
 from oracle import comm as OC  # noqa: E402
 from oracle import sensing as OS  # noqa: E402
@@ -110,7 +111,45 @@ def make_cdl():
     np.savez_compressed(os.path.join(HERE, "cdl_c.npz"), **out)
 
 
+def city_links(fp_flat, fp_off, heights, seed=5, n=1500):
+    """Seeded link set over the city's bounding box: users / targets at street level and on roofs, gNB-like antennas."""
+    rng = np.random.default_rng(seed)
+    lo, hi = fp_flat.min(axis=1), fp_flat.max(axis=1)
+    ue = np.column_stack([rng.uniform(lo[0] - 20, hi[0] + 20, n), rng.uniform(lo[1] - 20, hi[1] + 20, n),
+                          rng.choice([1.5, 1.5, 1.5, 12.0, 40.0], n)])
+    ant = np.column_stack([rng.uniform(lo[0], hi[0], n), rng.uniform(lo[1], hi[1], n), rng.uniform(20.0, 45.0, n)])
+    # degenerate / boundary cases: a user exactly on a building corner (winding "invalid" rule), a link parallel to the
+    # ceilings (division by zero -> NaN -> not blocked by that wall), coincident user and antenna
+    ue[0] = [fp_flat[0, 0], fp_flat[1, 0], 0.0]
+    ue[1, 2] = ant[1, 2] = heights[0]
+    ue[2] = ant[2]
+    return ue, ant
+
+
+def make_city():
+    """Condense the reference's cached city (its only data fixture: dataFiles/blockages/OSM_city.json, the file
+    city.loadCityFromFile reads, city.m:116-143) and freeze the oracle's LoS decisions for a seeded link set."""
+    import json
+    src = "/root/reference/dataFiles/blockages/OSM_city.json"
+    if not os.path.exists(src):
+        print("skipping osm_city.npz: the reference tree is not mounted")
+        return
+    b = json.load(open(src))["buildings"]
+    fps = [np.asarray(x["floorPlan"], dtype=np.float64) for x in b]
+    heights = np.array([float(x["height"]) for x in b])
+    fp_off = np.zeros(len(fps) + 1, dtype=np.int64)
+    fp_off[1:] = np.cumsum([f.shape[1] for f in fps])
+    fp_flat = np.concatenate(fps, axis=1)
+    ue, ant = city_links(fp_flat, fp_off, heights)
+    los = OG.check_los(list(zip(fps, heights)), ue, ant)
+    los_one = OG.check_los(list(zip(fps, heights)), ue, ant[7:8])
+    np.savez_compressed(os.path.join(HERE, "osm_city.npz"), fp_flat=fp_flat, fp_off=fp_off, heights=heights, ue=ue, ant=ant,
+                        los=los, los_one_antenna=los_one)
+    print("osm_city: %d buildings, %d links, %.1f %% LoS" % (len(fps), los.size, 100.0 * los.mean()))
+
+
 if __name__ == "__main__":
+    make_city()
     make_sensing()
     make_comm()
     make_cdl()
