@@ -115,6 +115,10 @@ def _declare(lib):
         "isac_rdm_get_power": ([vp, i32, vp], C.c_int),
         "isac_rdm_cfar_host": ([vp, vp, vp, i32, i32, vp, vp, vp, vp], C.c_int),
         "isac_music_doa_host": ([vp, P(DoaConfig), vp, i32, P(i32), vp, P(i32), vp, vp], C.c_int),
+        "isac_dev_malloc": ([vp, C.c_uint64, P(vp)], C.c_int),
+        "isac_dev_free": ([vp, vp], C.c_int),
+        "isac_memcpy_h2d": ([vp, vp, vp, C.c_uint64], C.c_int),
+        "isac_memcpy_d2h": ([vp, vp, vp, C.c_uint64], C.c_int),
         "isac_city_create": ([vp, i32, vp, vp, P(vp)], C.c_int),
         "isac_city_destroy": ([vp], C.c_int),
         "isac_city_check_los_host": ([vp, i32, vp, vp, i32, vp], C.c_int),

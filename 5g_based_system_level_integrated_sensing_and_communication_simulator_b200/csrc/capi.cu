@@ -602,6 +602,38 @@ int isac_mono_static_sensing_dev(isac_ctx* h, const isac_echo_config* cfg, const
     return st;
 }
 
+// ---- device-memory helpers for gateways that drive `_dev` entry points (MEX: no CUDA runtime in the gateway) --------
+int isac_dev_malloc(isac_ctx* h, uint64_t bytes, void** dptr) {
+    if (!h || !dptr) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(h->c.device);
+    ISAC_CUDA_CHECK(&h->c, cudaMalloc(dptr, bytes ? (size_t)bytes : 1));
+    return ISAC_OK;
+}
+
+int isac_dev_free(isac_ctx* h, void* dptr) {
+    if (!h) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(h->c.device);
+    ISAC_CUDA_CHECK(&h->c, cudaStreamSynchronize(h->c.stream));
+    ISAC_CUDA_CHECK(&h->c, cudaFree(dptr));
+    return ISAC_OK;
+}
+
+int isac_memcpy_h2d(isac_ctx* h, void* dst, const void* src, uint64_t bytes) {
+    if (!h || (!dst && bytes) || (!src && bytes)) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(h->c.device);
+    ISAC_CUDA_CHECK(&h->c, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, h->c.stream));
+    ISAC_CUDA_CHECK(&h->c, cudaStreamSynchronize(h->c.stream));   // the host buffer may be pageable / reused by the caller
+    return ISAC_OK;
+}
+
+int isac_memcpy_d2h(isac_ctx* h, void* dst, const void* src, uint64_t bytes) {
+    if (!h || (!dst && bytes) || (!src && bytes)) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(h->c.device);
+    ISAC_CUDA_CHECK(&h->c, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, h->c.stream));
+    ISAC_CUDA_CHECK(&h->c, cudaStreamSynchronize(h->c.stream));
+    return ISAC_OK;
+}
+
 // ---- city layout: LoS / blockage ---------------------------------------------------------------
 int isac_city_create(isac_ctx* h, int32_t nWalls, const int32_t* wallOffsets, const double* corners, isac_city** out) {
     if (!h || !out) return ISAC_ERR_INVALID_ARG;
@@ -665,7 +697,7 @@ int isac_ofdm_modulate_dev(isac_ctx* h, const void* txGrid, int32_t nSc, int32_t
 
 int isac_mono_static_sensing_host(isac_ctx* h, const isac_echo_config* cfg, const void* txHost, const void* noiseHost,
                                   int32_t noiseMode, uint64_t seed, void* echoHost, int32_t* nSymOut) {
-    if (!h || !txHost || !echoHost) return ISAC_ERR_INVALID_ARG;
+    if (!h || (!txHost && echoHost) || (!echoHost && !nSymOut)) return ISAC_ERR_INVALID_ARG;
     Ctx* c = &h->c;
     cudaSetDevice(c->device);
     EchoConfig e;
@@ -673,6 +705,10 @@ int isac_mono_static_sensing_host(isac_ctx* h, const isac_echo_config* cfg, cons
     int n = 0;
     int st = mono_static_sensing_run(c, e, nullptr, nullptr, 0, 0, nullptr, &n, c->stream);  // size query
     if (st) return st;
+    if (!echoHost) {  // echoGridHost == NULL: query nSymOut only (as the _dev entry point)
+        *nSymOut = n;
+        return ISAC_OK;
+    }
     const size_t wb = sizeof(float2) * (size_t)e.T * e.nTx, gb = sizeof(float2) * (size_t)e.nSc * n * e.nTx;
     void *dTx = nullptr, *dNz = nullptr, *dOut = nullptr;
     if ((st = ctx_scratch(c, 0, wb, &dTx))) return st;

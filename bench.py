@@ -266,7 +266,7 @@ def run_b200(args):
     # loop on the accumulated Tx grid only).  The sensing chain has its own library context; in the end-to-end leg it is
     # enqueued on its own CUDA stream so that its kernels fill the GPU while the host is busy with the (synchronising)
     # CSI / TPMI report tails.
-    ctx_s = _lib.Context(local)
+    ctx_s = _lib.Context(local) if args.sense_ctx == "own" else ctx
     sense_stream = torch.cuda.Stream()
     plan = est.SensePlan(rp, cf, (nSc, nSym, nTx), max_batch=cells, device=local, ctx=ctx_s)
     eargs = echo._EchoArgs(T, nTx, rp, los, car, nSym)
@@ -316,9 +316,12 @@ def run_b200(args):
     t_wall1 = time.time()
     ms_total = e0.elapsed_time(e1)
     prof, launches = ctx.profile_collect()
-    prof_s, launches_s = ctx_s.profile_collect()
-    prof.update(prof_s)                                         # disjoint kernel groups (sensing vs COMM)
-    launches += launches_s
+    if ctx_s is not ctx:
+        prof_s, launches_s = ctx_s.profile_collect()
+        prof.update(prof_s)                                     # disjoint kernel groups (sensing vs COMM)
+        launches += launches_s
+    if os.environ.get("ISAC_BENCH_DEBUG"):
+        print("prof", {k: (round(v[0], 3), v[1]) for k, v in prof.items()}, "ms_total", round(ms_total, 3), file=sys.stderr)
     for cx in (ctx, ctx_s):
         cx.profile_enable(False)
     if world > 1:
@@ -559,6 +562,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells-per-gpu", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--sense-ctx", default="own", choices=["own", "shared"],
+                    help="library context of the sensing chain: its own (second stream in the e2e leg) or the COMM one")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 3:

@@ -4,7 +4,7 @@
  * xds0112/5G_based_System_level_Integrated_Sensing_and_Communication_Simulator.
  * The reference has no FFI layer: its boundary is the MATLAB package namespace, so every entry
  * point below names the reference function (file:line, relative to the reference root) whose
- * arithmetic it replaces.  MEX gateways (matlab/mex/*.cpp) and the Python host mirror
+ * arithmetic it replaces.  MEX gateways (the .cpp files of matlab/mex) and the Python host mirror
  * (5g_based_..._b200/) bind exactly these symbols.
  *
  * Conventions
@@ -52,11 +52,17 @@ int isac_use_own_stream(isac_ctx* ctx);
 int isac_synchronize(isac_ctx* ctx);
 /* CUDA-event timing of kernel groups on the launching stream (bench.py's live roofline) and the number
  * of kernels this library launched.  Slots: 0 rdm_range, 1 rdm_doppler, 2 cfar, 3 echo_demod, 4 covariance,
- * 5 music, 6 pmi_sinr, 7 cdl, 8 prg_precode, 9 ul_tpmi (16 slots).  collect() synchronises and resets. */
+ * 5 music, 6 pmi_sinr, 7 cdl, 8 prg_precode, 9 ul_tpmi, 10 ofdm_modulate (16 slots).  collect() synchronises and resets. */
 #define ISAC_PROF_SLOTS 16
 int isac_profile_enable(isac_ctx* ctx, int32_t on);
 int isac_profile_collect(isac_ctx* ctx, double* msPerSlot, int32_t* countPerSlot, int64_t* launches);
 const char* isac_version(void);
+/* Device-memory helpers for gateways that drive `_dev` entry points without linking the CUDA runtime themselves (the MEX
+ * files of matlab/mex): allocation on the context's device, blocking copies ordered on the context's stream. */
+int isac_dev_malloc(isac_ctx* ctx, uint64_t bytes, void** devPtr);
+int isac_dev_free(isac_ctx* ctx, void* devPtr);
+int isac_memcpy_h2d(isac_ctx* ctx, void* devDst, const void* hostSrc, uint64_t bytes);
+int isac_memcpy_d2h(isac_ctx* ctx, void* hostDst, const void* devSrc, uint64_t bytes);
 
 /* ---- K3+K4: 2D-FFT range-Doppler map + 2D CA-CFAR ---------------------------------------------
  * Replaces sensing.estimation.fft2D's vectorised core (+sensing/+estimation/fft2D.m:37-46, :59-63)
@@ -209,6 +215,7 @@ int isac_radar_channel_dev(isac_ctx* ctx, const isac_echo_config* cfg, const voi
 int isac_mono_static_sensing_dev(isac_ctx* ctx, const isac_echo_config* cfg, const void* txWaveform,
                                  const void* noise, int32_t noiseMode, uint64_t seed, void* echoGrid,
                                  int32_t* nSymOut);
+/* host buffers; echoGridHost == NULL queries *nSymOut as above */
 int isac_mono_static_sensing_host(isac_ctx* ctx, const isac_echo_config* cfg, const void* txWaveformHost,
                                   const void* noiseHost, int32_t noiseMode, uint64_t seed, void* echoGridHost,
                                   int32_t* nSymOut);
@@ -243,7 +250,7 @@ typedef struct {
     int32_t nPorts;                    /* csirs.NumCSIRSPorts                                  dlPMISelect.m:326 */
     int32_t N1, N2, O1, O2;            /* PanelDimensions, OverSamplingFactors (TS 38.214 Table 5.2.2.2.1-2)  :604-644 */
     int32_t codebookMode;              /* reportConfig.CodebookMode (1|2)                       :583-590 */
-    int32_t nSizeBWP, nStartBWP;       /* reportConfig.NSizeBWP / NStartBWP (relative to the carrier start)  :536-569 */
+    int32_t nSizeBWP, nStartBWP;       /* reportConfig.NSizeBWP / NStartBWP (CRB index; subbands split at NStartBWP mod SubbandSize)  :536-569 */
     int32_t subbandSize;               /* reportConfig.SubbandSize (0 when not applicable)      :705-742 */
     int32_t pmiSubband, cqiSubband;    /* PMIMode / CQIMode == 'Subband'                         :683-688, cqiSelect.m:865 */
     int32_t K, L;                      /* carrier.NSizeGrid*12, carrier.SymbolsPerSlot          :829-831 */

@@ -1,0 +1,7 @@
+function [L, aziEst, eleEst] = music(numDets, radarEstParams, Ra)
+%MUSIC Drop-in for sensing.estimation.doaEstimation.music (+sensing/+estimation/+doaEstimation/music.m:1).
+% UPA arrays: the reference's peak picker (tools.find2DPeaks) does not exist, so aziEst / eleEst come back empty there.
+    cfg = sensing.estimation.isacDoaConfig(radarEstParams);
+    [L, aziEst] = isac_doa_mex(cfg, 0, numDets, double(Ra)); %#ok<ASGLU>
+    eleEst = NaN(size(aziEst));                        % ULA: no elevation estimate (music.m:104)
+end

@@ -1,0 +1,7 @@
+function [aziEst, eleEst] = mvdrBF(numDets, radarEstParams, Ra)
+%MVDRBF Drop-in for sensing.estimation.doaEstimation.mvdrBF (+sensing/+estimation/+doaEstimation/mvdrBF.m:1).
+% UPA arrays: the reference's peak picker (tools.find2DPeaks) does not exist, so aziEst / eleEst come back empty there.
+    cfg = sensing.estimation.isacDoaConfig(radarEstParams);
+    [L, aziEst] = isac_doa_mex(cfg, 1, numDets, double(Ra)); %#ok<ASGLU>
+    eleEst = NaN(size(aziEst));                        % ULA: no elevation estimate (music.m:104)
+end

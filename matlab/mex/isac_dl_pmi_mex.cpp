@@ -1,0 +1,48 @@
+/* [i1, i2, sinrPerRE, sinrPerSubband, W, reK, reL] = isac_dl_pmi_mex(cfg, nLayers, H, nVar)
+ *   cfg : struct built by matlab/+communication/+phyLayer/dlPMISelect.m from the validated reportConfig
+ *   H   : single complex [K x L x nRx x P];  nVar: double scalar
+ *   i1 [3x1], i2 [nSB x 1] (1-based, NaN = not reported); sinrPerRE [nRE x nLayers x i2 x i11 x i12 x i13] at the CSI-RS REs
+ *   (reK, reL: their 1-based subscripts); sinrPerSubband [nSB x nLayers x ...]; W complex double [P x nLayers x ...]
+ * Marshals communication.phyLayer.dlPMISelect (+communication/+phyLayer/dlPMISelect.m:1). */
+#include "isac_mex_common.h"
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs != 4) mexErrMsgIdAndTxt("isac:dlPMISelect:nargin", "four inputs required");
+    const char* fn = "dlPMISelect";
+    const mxArray* H = prhs[2];
+    require_csingle(H, fn, "H");
+    const int nLayers = (int)mxGetScalar(prhs[1]);
+    const double nVar = mxGetScalar(prhs[3]);
+    CsiCfg cs(prhs[0], dim_of(H, 2));
+    if (dim_of(H, 0) != cs.c.K || dim_of(H, 1) != cs.c.L || dim_of(H, 3) != cs.c.nPorts)
+        mexErrMsgIdAndTxt("nr5g:hDLPMISelect:InvalidChannelDims", "H must be K-by-L-by-nRxAnts-by-NumCSIRSPorts");
+    isac_pmi_plan* plan = nullptr;   /* a production gateway caches the plan per report configuration */
+    isac_mex_check(isac_pmi_plan_create(isac_mex_ctx(), &cs.c, nLayers, 1, &plan), fn);
+    int32_t dims[4] = {0, 0, 0, 0}, nSB = 0, nCqiSB = 0, nRE = 0;
+    isac_mex_check(isac_pmi_plan_info(plan, dims, &nSB, &nCqiSB, &nRE, nullptr, nullptr), fn);
+    std::vector<int32_t> reK(nRE), reL(nRE);
+    isac_mex_check(isac_pmi_plan_info(plan, dims, &nSB, &nCqiSB, &nRE, reK.data(), reL.data()), fn);
+    const size_t nCand = (size_t)dims[0] * dims[1] * dims[2] * dims[3];
+    std::vector<double> i1(3), i2(nSB), S((size_t)nRE * nLayers * nCand), Sb((size_t)nSB * nLayers * nCand);
+    int rc;
+    {
+        DevBuf Hd(mxGetComplexSingles(H), mxGetNumberOfElements(H) * sizeof(mxComplexSingle), fn);
+        rc = isac_dl_pmi_select_dev(plan, Hd.p, &nVar, 1);
+        if (!rc) rc = isac_dl_pmi_collect(plan, 1, i1.data(), i2.data(), nullptr);
+        if (!rc) rc = isac_dl_pmi_get_info(plan, 1, S.data(), Sb.data());
+    }
+    isac_pmi_plan_destroy(plan);
+    isac_mex_check(rc, fn);
+    std::vector<double> W(2 * (size_t)cs.c.nPorts * nLayers * nCand);
+    int32_t wd[4];
+    isac_mex_check(isac_type1sp_codebook(&cs.c, nLayers, 0, wd, W.data()), fn);   /* dlPMISelect.m:853 */
+    const std::vector<mwSize> tail = {(mwSize)dims[0], (mwSize)dims[1], (mwSize)dims[2], (mwSize)dims[3]};
+    auto with_tail = [&](mwSize a, mwSize b) { std::vector<mwSize> d = {a, b}; d.insert(d.end(), tail.begin(), tail.end()); return d; };
+    plhs[0] = double_array({3, 1}, i1.data());
+    if (nlhs > 1) plhs[1] = double_array({(mwSize)nSB, 1}, i2.data());
+    if (nlhs > 2) plhs[2] = double_array(with_tail((mwSize)nRE, (mwSize)nLayers), S.data());
+    if (nlhs > 3) plhs[3] = double_array(with_tail((mwSize)nSB, (mwSize)nLayers), Sb.data());
+    if (nlhs > 4) plhs[4] = complex_double_array(with_tail((mwSize)cs.c.nPorts, (mwSize)nLayers), W.data());
+    if (nlhs > 5) { std::vector<double> v(reK.begin(), reK.end()); plhs[5] = double_array({(mwSize)nRE, 1}, v.data()); }
+    if (nlhs > 6) { std::vector<double> v(reL.begin(), reL.end()); plhs[6] = double_array({(mwSize)nRE, 1}, v.data()); }
+}

@@ -3,7 +3,6 @@
  *   grids : single complex [nSc x nSym x nAnts]
  * Marshals sensing.estimation.fft2D (+sensing/+estimation/fft2D.m:1) onto isac_fft2d_host. */
 #include "isac_mex_common.h"
-#include <vector>
 
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (nrhs != 3) mexErrMsgIdAndTxt("isac:fft2d:nargin", "three inputs required");
@@ -20,11 +19,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     r.cutRow0 = (int32_t)cr[0]; r.cutRow1 = (int32_t)cr[1]; r.cutCol0 = (int32_t)cc[0]; r.cutCol1 = (int32_t)cc[1];
     r.guardRows = r.guardCols = 2; r.trainRows = r.trainCols = 1;      /* cfar2D.m:32-33 */
     r.maxBatch = 1; r.pfa = field_scalar(cfg, "Pfa"); r.kaiserBeta = 3.0;   /* fft2D.m:135 */
-    isac_doa_config a = {};
-    a.isUpa = (int32_t)field_scalar(cfg, "isUpa"); a.nAnts = (int32_t)field_scalar(cfg, "nAnts");
-    a.nX = (int32_t)field_scalar(cfg, "nX"); a.nY = (int32_t)field_scalar(cfg, "nY"); a.d = 0.5;
-    a.aGran = field_scalar(cfg, "aGran"); a.aMax = field_scalar(cfg, "aMax");
-    a.eGran = field_scalar(cfg, "eGran"); a.eMax = field_scalar(cfg, "eMax");
+    isac_doa_config a = doa_from_cfg(cfg);
     isac_sense_plan* plan = nullptr;   /* a production gateway caches the plan per configuration */
     isac_mex_check(isac_sense_plan_create(isac_mex_ctx(), &r, &a, field_scalar(cfg, "rRes"), field_scalar(cfg, "vRes"), &plan), "fft2D");
     const int maxOut = 4096;
@@ -37,10 +32,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     isac_mex_check(st, "fft2D");   /* zero detections -> error, like findpeaks(...,'NPeaks',0) (music.m:102) */
     const char* names[] = {"rngEst", "velEst", "aziEst", "eleEst"};
     plhs[0] = mxCreateStructMatrix(1, 1, 4, names);
-    auto row = [](const double* v, int n) { mxArray* m = mxCreateDoubleMatrix(1, n, mxREAL); for (int i = 0; i < n; ++i) mxGetDoubles(m)[i] = v[i]; return m; };
-    mxSetField(plhs[0], 0, "rngEst", row(rng.data(), nR));
-    mxSetField(plhs[0], 0, "velEst", row(vel.data(), nV));
-    mxSetField(plhs[0], 0, "aziEst", row(azi.data(), nA));
+    mxSetField(plhs[0], 0, "rngEst", row_vector(rng.data(), nR));
+    mxSetField(plhs[0], 0, "velEst", row_vector(vel.data(), nV));
+    mxSetField(plhs[0], 0, "aziEst", row_vector(azi.data(), nA));
     mxArray* ele = mxCreateDoubleMatrix(1, nA, mxREAL);
     for (int i = 0; i < nA; ++i) mxGetDoubles(ele)[i] = mxGetNaN();   /* music.m:104 */
     mxSetField(plhs[0], 0, "eleEst", ele);
