@@ -119,6 +119,10 @@ def _declare(lib):
         "isac_dev_free": ([vp, vp], C.c_int),
         "isac_memcpy_h2d": ([vp, vp, vp, C.c_uint64], C.c_int),
         "isac_memcpy_d2h": ([vp, vp, vp, C.c_uint64], C.c_int),
+        "isac_chest_plan_create": ([vp, i32, i32, i32, i32, C.c_int64, vp, vp, i32, i32, i32, i32, i32, P(vp)], C.c_int),
+        "isac_chest_plan_destroy": ([vp], C.c_int),
+        "isac_channel_estimate_dev": ([vp, vp, i32, vp, vp], C.c_int),
+        "isac_chest_get_nvar": ([vp, i32, vp], C.c_int),
         "isac_city_create": ([vp, i32, vp, vp, P(vp)], C.c_int),
         "isac_city_destroy": ([vp], C.c_int),
         "isac_city_check_los_host": ([vp, i32, vp, vp, i32, vp], C.c_int),
@@ -231,7 +235,7 @@ class Context:
         check(self.lib.isac_synchronize(self.handle), self.handle)
 
     PROF_SLOTS = ("rdm_range", "rdm_doppler", "cfar", "echo_demod", "covariance", "music", "pmi_sinr", "cdl",
-                  "prg_precode", "ul_tpmi", "ofdm_modulate")
+                  "prg_precode", "ul_tpmi", "ofdm_modulate", "channel_estimate")
 
     def profile_enable(self, on=True):
         check(self.lib.isac_profile_enable(self.handle, 1 if on else 0), self.handle)

@@ -1,5 +1,6 @@
 """``+communication/+phyLayer`` mirror (hot-path functions): dlPMISelect, riSelect, cqiSelect, pmiSelect,
-precodedSINR, sinrPerSubband, prgPrecode, maxPUSCHPrecodingMatrixIndicator.
+precodedSINR, sinrPerSubband, prgPrecode, maxPUSCHPrecodingMatrixIndicator, and nrChannelEstimate (the toolbox call
+right before them, uePhy.m:897 / gNBPhy.m:1030).
 
 MATLAB configuration objects are plain dicts with the same field names:
   carrier      : NSizeGrid, NStartGrid (0), SymbolsPerSlot (14)
@@ -469,3 +470,73 @@ def prgPrecode(siz, nstartgrid, portsym, portind, F):
     _lib.check(ctx.lib.isac_prg_precode_dev(ctx.handle, int(siz[0]), int(siz[1]), int(nstartgrid), _lib.ptr(ps_d), _lib.ptr(pi_d),
                                             nre, nu, _lib.ptr(F_d), P, nprg, _lib.ptr(out_s), _lib.ptr(out_i)), ctx.handle)
     return (out_s.cpu().numpy().reshape((nre, P), order="F"), out_i.cpu().numpy().astype(np.int64).reshape((nre, P), order="F"))
+
+
+# ---- channel estimation ----------------------------------------------------------------------------
+class ChannelEstimator:
+    """Device plan of ``nrChannelEstimate`` for one reference-signal layout (csrc/chest.cu).
+
+    refInd / refSym follow the toolbox convention (1-based column-major linear indices into the K x L x nPorts grid, any
+    array shape).  ``run_dev`` keeps everything on the device: rxGrid [batch][nRx][L][K] -> Hest [batch][P][nRx][L][K]
+    (== MATLAB K x L x nRx x P x batch), the layout dlPMISelect / riSelect / cqiSelect / csiReport / pmiSelectBatch consume."""
+
+    def __init__(self, K, L, nRx, nPorts, refInd, refSym, CDMLengths=(1, 1), AveragingWindow=(0, 0), max_batch=1,
+                 device=None, ctx=None):
+        self.ctx = ctx if ctx is not None else _lib.get_context(device)
+        self.K, self.L, self.nRx, self.P, self.max_batch = int(K), int(L), int(nRx), int(nPorts), int(max_batch)
+        ind = np.ascontiguousarray(np.asarray(refInd).reshape(-1, order="F"), dtype=np.int32)
+        sym = np.ascontiguousarray(np.asarray(refSym).reshape(-1, order="F"), dtype=np.complex64)
+        if ind.size != sym.size:
+            raise ValueError("refInd and refSym disagree in size")
+        h = C.c_void_p()
+        _lib.check(self.ctx.lib.isac_chest_plan_create(self.ctx.handle, self.K, self.L, self.nRx, self.P, ind.size, _lib.ptr(ind),
+                                                       _lib.ptr(sym), int(CDMLengths[0]), int(CDMLengths[1]),
+                                                       int(AveragingWindow[0]), int(AveragingWindow[1]), self.max_batch,
+                                                       C.byref(h)), self.ctx.handle)
+        self.handle = h
+
+    def run_dev(self, rx_dev, batch=1, H_out=None, sync=True):
+        """rx_dev: torch CUDA complex64 [batch][nRx][L][K].  -> (Hest torch [batch][P][nRx][L][K], nVar [batch] or None)."""
+        import torch
+        if H_out is None:
+            H_out = torch.empty((batch, self.P, self.nRx, self.L, self.K), dtype=torch.complex64, device=rx_dev.device)
+        nvar = np.zeros(batch) if sync else None
+        self.ctx.use_torch_stream()
+        _lib.check(self.ctx.lib.isac_channel_estimate_dev(self.handle, _lib.ptr(rx_dev), int(batch), _lib.ptr(H_out),
+                                                          _lib.ptr(nvar)), self.ctx.handle)
+        return H_out, nvar
+
+    def nvar(self, batch=1):
+        out = np.zeros(batch)
+        _lib.check(self.ctx.lib.isac_chest_get_nvar(self.handle, int(batch), _lib.ptr(out)), self.ctx.handle)
+        return out
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.isac_chest_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nrChannelEstimate(rxGrid, refInd, refSym, nPorts=None, CDMLengths=(1, 1), AveragingWindow=(0, 0)):
+    """``[Hest, nVar] = nrChannelEstimate(rxGrid, refInd, refSym, 'CDMLengths', cdmLen, 'AveragingWindow', win)`` as the
+    reference calls it (uePhy.m:897, gNBPhy.m:1030).  rxGrid: NumPy [K x L x nRx]; returns Hest [K x L x nRx x P] complex64
+    and the scalar noise-variance estimate.  nPorts defaults to the port count implied by max(refInd)."""
+    import torch
+    rx = np.asarray(rxGrid)
+    if rx.ndim == 2:
+        rx = rx[:, :, None]
+    K, L, R = rx.shape
+    ind = np.asarray(refInd)
+    P = int(nPorts) if nPorts else int((int(ind.max()) - 1) // (K * L) + 1)
+    est = ChannelEstimator(K, L, R, P, refInd, refSym, CDMLengths, AveragingWindow, 1)
+    rx_d = torch.from_numpy(np.ascontiguousarray(rx.astype(np.complex64).transpose(2, 1, 0))).cuda(est.ctx.device)[None]
+    H, nvar = est.run_dev(rx_d, 1)
+    out = H[0].permute(3, 2, 1, 0).cpu().numpy()       # [K, L, R, P]
+    est.close()
+    return out, float(nvar[0])

@@ -6,6 +6,7 @@
 #include "sense.cuh"
 #include "echo.cuh"
 #include "ofdm.cuh"
+#include "chest.cuh"
 #include "los.cuh"
 #include "comm.cuh"
 #include "cdl.cuh"
@@ -1195,6 +1196,50 @@ int isac_cdl_generate_dev(isac_cdl_channel* ch, int32_t K, double scsHz, int32_t
     Ctx* c = ch->ctx;
     cudaSetDevice(c->device);
     return cdl_generate(c, ch->rays, K, scsHz, L, symTime, t0, (float2*)H, c->stream);
+}
+
+// ---- channel estimation ---------------------------------------------------------
+struct isac_chest_plan {
+    ChestPlan* p;
+};
+
+int isac_chest_plan_create(isac_ctx* h, int32_t K, int32_t L, int32_t nRx, int32_t nPorts, int64_t nRef, const int32_t* refInd,
+                           const void* refSym, int32_t cdmFd, int32_t cdmTd, int32_t avgF, int32_t avgT, int32_t maxBatch,
+                           isac_chest_plan** out) {
+    if (!h || !out) return ISAC_ERR_INVALID_ARG;
+    *out = nullptr;
+    cudaSetDevice(h->c.device);
+    ChestConfig c{K, L, nRx, nPorts, cdmFd, cdmTd, avgF, avgT, maxBatch};
+    ChestPlan* p = nullptr;
+    const int st = chest_plan_create(&h->c, c, (long long)nRef, refInd, (const float2*)refSym, &p);
+    if (st) return st;
+    *out = new isac_chest_plan{p};
+    return ISAC_OK;
+}
+
+int isac_chest_plan_destroy(isac_chest_plan* plan) {
+    if (!plan) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(plan->p->ctx->device);
+    cudaStreamSynchronize(plan->p->ctx->stream);
+    chest_plan_destroy(plan->p);
+    delete plan;
+    return ISAC_OK;
+}
+
+int isac_channel_estimate_dev(isac_chest_plan* plan, const void* rxGrid, int32_t batch, void* Hest, double* nVar) {
+    if (!plan) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(plan->p->ctx->device);
+    return chest_run(plan->p, (const float2*)rxGrid, batch, (float2*)Hest, nVar, plan->p->ctx->stream);
+}
+
+int isac_chest_get_nvar(isac_chest_plan* plan, int32_t batch, double* nVar) {
+    if (!plan || !nVar || batch < 1 || batch > plan->p->cfg.maxBatch) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = plan->p->ctx;
+    cudaSetDevice(c->device);
+    ISAC_CUDA_CHECK(c, cudaMemcpyAsync(plan->p->h_nvar, plan->p->d_nvar, sizeof(double) * batch, cudaMemcpyDeviceToHost, c->stream));
+    ISAC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < batch; ++b) nVar[b] = plan->p->h_nvar[b];
+    return ISAC_OK;
 }
 
 }  // extern "C"

@@ -90,7 +90,7 @@ void ctx_fft_tw(Ctx* ctx, int N, const float2** tw1, const float2** tw2);
 // live roofline figure) and a counter of this library's kernel launches.
 enum ProfSlot : int {
     kProfRdmRange = 0, kProfRdmDoppler = 1, kProfCfar = 2, kProfEcho = 3, kProfCov = 4, kProfMusic = 5,
-    kProfPmi = 6, kProfCdl = 7, kProfPrecode = 8, kProfUlPmi = 9, kProfOfdmMod = 10, kProfSlots = 16
+    kProfPmi = 6, kProfCdl = 7, kProfPrecode = 8, kProfUlPmi = 9, kProfOfdmMod = 10, kProfChest = 11, kProfSlots = 16
 };
 int prof_begin(Ctx* ctx, int slot, cudaStream_t st);  // returns a record index (or -1 when disabled)
 void prof_end(Ctx* ctx, int rec, cudaStream_t st);

@@ -43,7 +43,25 @@ struct RdmDev {
     long long totalCols;  // M * nAnts * batch
     int* ticketR;         // work counters of the persistent kernels (zeroed per run): columns / Doppler tiles are handed
     int* ticketD;         // out in order, so every SM stays busy until the last item
+    int hints;            // L2 eviction priorities, 2 bits each (0 normal, 1 evict_first, 2 evict_last): [1:0] rx/tx bulk loads,
+                          // [3:2] range-profile stores, [5:4] range-profile tile loads, [7:6] power-map stores; bit 8: discard the
+                          // range-profile lines of a tile from L2 once the Doppler kernel has staged them (no write-back)
 };
+
+// L2 eviction-priority policy for ld/st/bulk-copy cache hints
+__device__ __forceinline__ unsigned long long l2_policy(int kind) {
+    unsigned long long pol;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_hint(float2* p, float2 v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(float* p, float v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------
 // Kernel A: range IFFT
@@ -111,6 +129,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+__device__ __forceinline__ void tma_load_1d_hint(void* dst, const void* src, unsigned bytes, unsigned long long* bar,
+                                                 unsigned long long pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
 }
 
 template <int R1, int R2>
@@ -229,14 +256,15 @@ rdm_range4096_lean_kernel(const RdmDev p) {
     const float2* const sRx = stageRx + tf;
     const float2* const sTx = stageTx + tf;
     const int M = p.M, nSym = p.nSym, half = p.nSym / 2;
+    const unsigned long long polIn = l2_policy(p.hints & 3), polOut = l2_policy((p.hints >> 2) & 3);
     auto issue = [&](int col) {  // thread 0: fetch the rx and tx columns of `col`
         const int sp = col % M, page = col / M;
         int s = sp + half;
         if (s >= nSym) s -= nSym;  // ifftshift on the symbol axis (fft2D.m:44)
         const size_t off = ((size_t)page * nSym + s) * (size_t)nSc;
         mbar_expect_tx(&bar, 2 * colBytes);
-        tma_load_1d(stageRx, p.rx + off, colBytes, &bar);
-        tma_load_1d(stageTx, p.tx + off, colBytes, &bar);
+        tma_load_1d_hint(stageRx, p.rx + off, colBytes, &bar, polIn);
+        tma_load_1d_hint(stageTx, p.tx + off, colBytes, &bar, polIn);
     };
     if (tf == 0) {
         mbar_init(&bar, 1);
@@ -296,7 +324,7 @@ rdm_range4096_lean_kernel(const RdmDev p) {
         }
         float2* __restrict__ out = p.inter + (size_t)col * N + tf;
 #pragma unroll
-        for (int d = 0; d < 16; ++d) out[NT * d] = v[d];
+        for (int d = 0; d < 16; ++d) st_hint(out + NT * d, v[d], polOut);
         col = nxt;
     }
 }
@@ -310,11 +338,12 @@ rdm_range4096_lean_kernel(const RdmDev p) {
 // buffers per CTA suffice and 3 CTAs fit per SM.  Twiddles sit in shared memory.  Epilogue: |X|^2 times the per-row
 // scale w2[(n - N/2) mod N]^2 / (N F) (fft2D.m:44-46, :61), written at the Doppler index rotated by F/2 (fftshift).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar,
+                                            unsigned long long pol) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+        "[%4], %5;" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol)
         : "memory");
 }
 
@@ -336,10 +365,12 @@ rdm_doppler256_tma_kernel(const RdmDev p, const int nPages, const __grid_constan
     }
     const float2* const tw = tws + tf;  // + (c-1)*16
     const int nA = (M - tf + 15) >> 4;  // valid first-pass inputs: a*16 + tf < M
+    const unsigned long long polIn = l2_policy((p.hints >> 4) & 3), polOut = l2_policy((p.hints >> 6) & 3);
+    const bool discard = (p.hints >> 8) & 1;
     auto issue = [&](int tile, int s) {  // thread 0: one 2-D tensor copy [M symbols x 16 rows] -> buffer s
         const int page = tile / tilesPerPage, row0 = (tile - page * tilesPerPage) * RT;
         mbar_expect_tx(&bar[s], (unsigned)M * RT * (unsigned)sizeof(float2));
-        tma_load_2d(buf0 + s * TILE, &interMap, row0, page * M, &bar[s]);
+        tma_load_2d(buf0 + s * TILE, &interMap, row0, page * M, &bar[s], polIn);
     };
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -370,6 +401,10 @@ rdm_doppler256_tma_kernel(const RdmDev p, const int nPages, const __grid_constan
         const float sc = __ldg(p.win2 + n);  // per-row power scale (see rdm_plan_create)
         mbar_wait(&bar[s], (phase >> s) & 1u);
         phase ^= 1u << s;
+        if (discard && tid < M) {  // the staged tile is the only consumer of these 128-byte lines: drop them without write-back
+            const float2* line = p.inter + ((size_t)page * M + tid) * nIFFT + (n - nl);
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(line) : "memory");
+        }
         float2 v[16];
 #pragma unroll
         for (int a = 0; a < 16; ++a) v[a] = (a < nA) ? buf[a * TILE / 16] : make_float2(0.f, 0.f);
@@ -392,7 +427,7 @@ rdm_doppler256_tma_kernel(const RdmDev p, const int nPages, const __grid_constan
 #pragma unroll
         for (int d = 0; d < 16; ++d) {
             const int q = tf + 16 * ((d + 8) & 15);  // Doppler-axis fftshift (fft2D.m:46) as an output rotation
-            out[(size_t)q * nIFFT] = (v[d].x * v[d].x + v[d].y * v[d].y) * sc;  // abs(rdm).^2 (fft2D.m:61)
+            st_hint(out + (size_t)q * nIFFT, (v[d].x * v[d].x + v[d].y * v[d].y) * sc, polOut);  // abs(rdm).^2 (fft2D.m:61)
         }
         tile = nxt;
     }
@@ -667,6 +702,7 @@ int rdm_plan_create(Ctx* ctx, const RdmConfig& c, RdmPlan** out) {
     }
     cudaMemcpy(p->d_rowScale, f2.data(), sizeof(float) * c.nIFFT, cudaMemcpyHostToDevice);
     if (const char* e = getenv("ISAC_RDM_PDL")) p->pdl = atoi(e) != 0;
+    if (const char* e = getenv("ISAC_RDM_HINTS")) p->hints = (int)strtol(e, nullptr, 0);
     p->hasInterMap = c.nFFT == 256 && c.nIFFT % 16 == 0 && p->M <= 256 &&
                      make_inter_tensor_map(&p->interMap, p->d_inter, c.nIFFT, p->M, c.nAnts);
     *out = p;
@@ -900,6 +936,7 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
         d.nFFT = c.nFFT;
         d.M = p->M;
         d.totalCols = (long long)p->M * c.nAnts;
+        d.hints = p->hints;
         d.ticketR = p->d_tickets + 2 * b;
         d.ticketD = p->d_tickets + 2 * b + 1;
         cudaError_t e = cudaSuccess;

@@ -39,6 +39,9 @@ struct RdmPlan {
     CUtensorMap interMap{};      // 2-D TMA view of d_inter for the bulk-staged Doppler kernel (nFFT = 256)
     bool hasInterMap = false;
     bool pdl = true;             // programmatic dependent launch between the range and Doppler kernels of a batch (ISAC_RDM_PDL=0 disables)
+    int hints = 0x149;           // L2 eviction priorities of the lean pipeline (RdmDev::hints; ISAC_RDM_HINTS overrides): rx/tx loads and
+                                 // power-map stores evict_first, range-profile stores evict_last, staged range-profile lines discarded
+                                 // (measured 155.7 -> 147.3 us per chain of 4 cfg2 map-sets; gpurun_out/c15_hints.log)
     const float* lastPow = nullptr; // power map used by the last run (plan-owned or caller's)
     int lastBatch = 0;
     int variant = 0;             // N = 4096 pipelines: 0 lean persistent TMA range kernel (raw IFFT) + bulk-staged

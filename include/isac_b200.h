@@ -52,7 +52,7 @@ int isac_use_own_stream(isac_ctx* ctx);
 int isac_synchronize(isac_ctx* ctx);
 /* CUDA-event timing of kernel groups on the launching stream (bench.py's live roofline) and the number
  * of kernels this library launched.  Slots: 0 rdm_range, 1 rdm_doppler, 2 cfar, 3 echo_demod, 4 covariance,
- * 5 music, 6 pmi_sinr, 7 cdl, 8 prg_precode, 9 ul_tpmi, 10 ofdm_modulate (16 slots).  collect() synchronises and resets. */
+ * 5 music, 6 pmi_sinr, 7 cdl, 8 prg_precode, 9 ul_tpmi, 10 ofdm_modulate, 11 channel_estimate (16 slots).  collect() synchronises and resets. */
 #define ISAC_PROF_SLOTS 16
 int isac_profile_enable(isac_ctx* ctx, int32_t on);
 int isac_profile_collect(isac_ctx* ctx, double* msPerSlot, int32_t* countPerSlot, int64_t* launches);
@@ -372,6 +372,26 @@ int isac_cdl_generate_dev(isac_cdl_channel* ch, int32_t K, double scsHz, int32_t
 int isac_cdl_set_kernel(isac_cdl_channel* ch, int32_t legacyMma);
 int isac_cdl_generate_batch_dev(isac_cdl_channel* const* ch, int32_t n, int32_t K, double scsHz, int32_t L,
                                 const double* symTime, const double* t0, void* H);
+
+/* ---- channel estimation from reference signals ------------------------------------------------
+ * [Hest, nVar] = nrChannelEstimate(rxGrid, refInd, refSym, 'CDMLengths', [FD TD] [, 'AveragingWindow', [F T]]) -- the 5G
+ * Toolbox call the reference makes right before the COMM hot path (+communication/+phyLayer/uePhy.m:897 CSI-RS with
+ * cdmLen from :889-895; gNBPhy.m:1030 SRS with 'AveragingWindow',[0 7]; uePhy.m:836 / gNBPhy.m:935 DM-RS).
+ * LS estimates at the reference REs, CDM despreading (block means), optional F x T moving average over blocks (0 or 1 =
+ * none; the toolbox's automatic window is not reproduced), linear interpolation with constant extrapolation in frequency
+ * then time, nVar from second differences of the despread estimates (algorithm: oracle/chest.py; PARITY-UNPINNED).
+ * refInd: host int32 [nRef], 1-based column-major linear indices into the K x L x nPorts grid; refSym: host complex64
+ * [nRef].  Every port needs the same number of reference subcarriers on each of its reference symbols. */
+typedef struct isac_chest_plan isac_chest_plan;
+int isac_chest_plan_create(isac_ctx* ctx, int32_t K, int32_t L, int32_t nRx, int32_t nPorts, int64_t nRef,
+                           const int32_t* refInd, const void* refSym, int32_t cdmFd, int32_t cdmTd, int32_t avgF,
+                           int32_t avgT, int32_t maxBatch, isac_chest_plan** plan);
+int isac_chest_plan_destroy(isac_chest_plan* plan);
+/* rxGrid: device complex64 [K x L x nRx x batch]; Hest: device complex64 [K x L x nRx x nPorts x batch] (the layout
+ * isac_dl_pmi_select_dev / isac_csi_report_dev / isac_ul_pmi_select_batch_dev consume); nVar: host double [batch], or NULL
+ * to enqueue without synchronising (fetch later with isac_chest_get_nvar). */
+int isac_channel_estimate_dev(isac_chest_plan* plan, const void* rxGrid, int32_t batch, void* Hest, double* nVar);
+int isac_chest_get_nvar(isac_chest_plan* plan, int32_t batch, double* nVar);   /* synchronises the stream */
 
 #ifdef __cplusplus
 }

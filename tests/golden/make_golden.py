@@ -16,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import geometry as OG  # noqa: E402
 from oracle import cdl as OCDL  # noqa: E402
+from oracle import chest as OCH  # noqa: E402
 from oracle import comm as OC  # noqa: E402
 from oracle import sensing as OS  # noqa: E402
 
@@ -111,6 +112,28 @@ def make_cdl():
     np.savez_compressed(os.path.join(HERE, "cdl_c.npz"), **out)
 
 
+def chest_case(seed=21, nrb=24, R=2, snr_db=25.0):
+    """4-port CSI-RS row 5 (setupCSIRS.m:8-10) through a smooth frequency-selective channel + AWGN -> rxGrid."""
+    K, L, P = 12 * nrb, 14, 4
+    ind, sym, cdm = OCH.csirs_row5_layout(nrb, 1, 0, seed=seed)
+    rng = np.random.default_rng(seed)
+    taps = (rng.standard_normal((3, R, P)) + 1j * rng.standard_normal((3, R, P))) * np.array([1.0, 0.5, 0.25])[:, None, None]
+    k = np.arange(K)[:, None, None, None]
+    H = sum(taps[t][None, None] * np.exp(-2j * np.pi * k * t * 3 / 1024.0) for t in range(3)) * np.ones((1, L, 1, 1))
+    sig = 10 ** (-snr_db / 20)
+    noise = sig / np.sqrt(2) * (rng.standard_normal((K, L, R)) + 1j * rng.standard_normal((K, L, R)))
+    rx = OCH.apply_channel(H, ind, sym, noise)
+    return K, L, R, P, ind, sym, cdm, H, rx, sig ** 2
+
+
+def make_chest():
+    K, L, R, P, ind, sym, cdm, H, rx, nv = chest_case()
+    He, nve = OCH.channel_estimate(rx, ind, sym, P, cdm)
+    Ha, nva = OCH.channel_estimate(rx, ind, sym, P, cdm, (3, 1))
+    np.savez_compressed(os.path.join(HERE, "chest_small.npz"), Hest=He.astype(np.complex64), nVar=nve,
+                        Hest_avg=Ha.astype(np.complex64), nVar_avg=nva, nVar_true=nv)
+
+
 def city_links(fp_flat, fp_off, heights, seed=5, n=1500):
     """Seeded link set over the city's bounding box: users / targets at street level and on roofs, gNB-like antennas."""
     rng = np.random.default_rng(seed)
@@ -150,6 +173,7 @@ def make_city():
 
 if __name__ == "__main__":
     make_city()
+    make_chest()
     make_sensing()
     make_comm()
     make_cdl()
