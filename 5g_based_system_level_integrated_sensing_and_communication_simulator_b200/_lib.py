@@ -155,6 +155,8 @@ def _declare(lib):
         "isac_ri_select_dev": ([vp, vp, vp, i32, vp, vp, vp], C.c_int),
         "isac_cqi_select_dev": ([vp, i32, vp, vp, i32, vp, i32, vp, P(i32), vp, vp, vp], C.c_int),
         "isac_csi_report_dev": ([vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, P(i32)], C.c_int),
+        "isac_csi_report_enqueue_dev": ([vp, vp, vp, i32], C.c_int),
+        "isac_csi_report_finish": ([vp, vp, i32, i32, vp, vp, vp, vp, P(i32)], C.c_int),
         "isac_ul_pmi_select_dev": ([vp, i32, vp, i32, i32, i32, i32, f64, i32, i32, vp, vp, vp, P(i32), P(i32), P(i32)],
                                    C.c_int),
         "isac_ul_pmi_select_batch_dev": ([vp, i32, vp, i32, i32, i32, i32, f64, i32, i32, i32, vp, vp, P(i32), P(i32), vp], C.c_int),

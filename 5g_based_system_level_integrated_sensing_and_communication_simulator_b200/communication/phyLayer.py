@@ -312,9 +312,33 @@ def cqiSelect(carrier, csirs, reportConfig, nLayers, H, nVar, SINRTable):
     return cqi, {"i1": i1, "i2": i2}, {"SINRPerSubbandPerCW": sb}
 
 
-def csiReport(carrier, csirs, reportConfig, H, nVar, SINRTable, rankCap=4):
-    """Fused UE CSI report of uePhy.phyRxProcessing (uePhy.m:900-907): ``rank = min(riSelect(...), 4)`` followed
-    by ``cqiSelect`` at that rank.  Returns (rank, PMISet, CQI)."""
+class PendingCsiReport:
+    """A CSI report whose kernels are enqueued (csiReportEnqueue); ``finish()`` waits for its results only -- work enqueued
+    on the stream in between keeps the GPU busy during the host-side RI / CQI tails."""
+
+    def __init__(self, ctx, plan, Hd, B, nSB, nC, table, rankCap):
+        self.ctx, self.plan, self.Hd, self.B, self.nSB, self.nC = ctx, plan, Hd, B, nSB, nC    # Hd kept alive until finish()
+        self.table, self.rankCap = table, int(rankCap)
+
+    def finish(self):
+        B = self.B
+        RI = np.zeros(B)
+        i1 = np.zeros((3, B), order="F")
+        i2 = np.zeros((self.nSB, B), order="F")
+        cqi = np.zeros(((self.nC + 1) * 2 * B))
+        rows = C.c_int32()
+        _lib.check(self.ctx.lib.isac_csi_report_finish(self.plan, _lib.ptr(self.table), self.table.size, self.rankCap, _lib.ptr(RI),
+                                                       _lib.ptr(i1), _lib.ptr(i2), _lib.ptr(cqi), C.byref(rows)), self.ctx.handle)
+        cqi = cqi[: rows.value * 2 * B].reshape((rows.value, 2, B), order="F")
+        self.Hd = None
+        if B == 1:
+            return float(RI[0]), {"i1": i1[:, 0], "i2": i2[:, 0]}, cqi[..., 0]
+        return RI, {"i1": i1, "i2": i2}, cqi
+
+
+def csiReportEnqueue(carrier, csirs, reportConfig, H, nVar, SINRTable, rankCap=4):
+    """First half of csiReport: launches the SINR / selection kernels of every valid rank and the D2H copy of their results
+    on the current torch stream and returns without synchronising (isac_csi_report_enqueue_dev)."""
     Hd, K, L, R, P, B = _h_to_dev(H)
     cs = _csi_struct(carrier, csirs, reportConfig, R)
     nv = _nvar(nVar, B)
@@ -322,18 +346,15 @@ def csiReport(carrier, csirs, reportConfig, H, nVar, SINRTable, rankCap=4):
     nSB = len(_subband_sizes(cs.v["PMIMode"], cs.v))
     nC = len(_subband_sizes(cs.v["CQIMode"], cs.v))
     table = np.ascontiguousarray(SINRTable, dtype=np.float64)
-    RI = np.zeros(B)
-    i1 = np.zeros((3, B), order="F")
-    i2 = np.zeros((nSB, B), order="F")
-    cqi = np.zeros(((nC + 1) * 2 * B))
-    rows = C.c_int32()
     ctx.use_torch_stream()
-    _lib.check(ctx.lib.isac_csi_report_dev(plan, _lib.ptr(Hd), _lib.ptr(nv), B, _lib.ptr(table), table.size, int(rankCap),
-                                           _lib.ptr(RI), _lib.ptr(i1), _lib.ptr(i2), _lib.ptr(cqi), C.byref(rows)), ctx.handle)
-    cqi = cqi[: rows.value * 2 * B].reshape((rows.value, 2, B), order="F")
-    if B == 1:
-        return float(RI[0]), {"i1": i1[:, 0], "i2": i2[:, 0]}, cqi[..., 0]
-    return RI, {"i1": i1, "i2": i2}, cqi
+    _lib.check(ctx.lib.isac_csi_report_enqueue_dev(plan, _lib.ptr(Hd), _lib.ptr(nv), B), ctx.handle)
+    return PendingCsiReport(ctx, plan, Hd, B, nSB, nC, table, rankCap)
+
+
+def csiReport(carrier, csirs, reportConfig, H, nVar, SINRTable, rankCap=4):
+    """Fused UE CSI report of uePhy.phyRxProcessing (uePhy.m:900-907): ``rank = min(riSelect(...), 4)`` followed
+    by ``cqiSelect`` at that rank.  Returns (rank, PMISet, CQI)."""
+    return csiReportEnqueue(carrier, csirs, reportConfig, H, nVar, SINRTable, rankCap).finish()
 
 
 def maxPUSCHPrecodingMatrixIndicator(nlayers, nports):

@@ -742,6 +742,12 @@ struct isac_csi_plan {
     char* d_arena = nullptr;    // selection results of all ranks, contiguous -> one D2H copy per report
     char* h_arena = nullptr;    // pinned
     size_t arenaBytes = 0;
+    // a report enqueued by ri_enqueue and not yet finished (isac_csi_report_enqueue_dev / _finish)
+    cudaEvent_t ready = nullptr;   // recorded behind the D2H copy of the arena
+    const float2* pendH = nullptr;
+    std::vector<double> pendNVar;
+    int pendBatch = 0;             // 0 = nothing pending
+    bool pendLaunched = false;     // false: nothing reportable (riSelect.m:235-245), no kernels were enqueued
 };
 
 static CsiConfig to_csi_config(const isac_csi_config* c) {
@@ -897,6 +903,7 @@ int isac_csi_plan_destroy(isac_csi_plan* pl) {
     cudaStreamSynchronize(pl->ctx->stream);
     cudaFree(pl->d_arena);
     if (pl->h_arena) cudaFreeHost(pl->h_arena);
+    if (pl->ready) cudaEventDestroy(pl->ready);
     for (int r = 0; r < kMaxLayers; ++r)
         if (pl->byRank[r]) pmi_plan_destroy(pl->byRank[r]);
     delete pl;
@@ -911,9 +918,34 @@ int isac_csi_plan_set_kernel(isac_csi_plan* pl, int32_t direct) {
 }
 
 // riSelect.m:254-294 for a batch; keeps every evaluated rank's results for the fused report
-static int ri_select_batch(isac_csi_plan* pl, const float2* H, const double* nVar, int batch, std::vector<double>& RI,
-                           std::vector<PmiResult>& chosen, std::vector<std::vector<PmiResult>>& all) {
+// Kernels of every valid rank + the asynchronous D2H copy of the selection arena; no synchronisation.
+static int ri_enqueue(isac_csi_plan* pl, const float2* H, const double* nVar, int batch) {
     Ctx* c = pl->ctx;
+    const int maxRank = pl->cfg.nRx < pl->cfg.nPorts ? pl->cfg.nRx : pl->cfg.nPorts;
+    pl->pendH = H;
+    pl->pendNVar.assign(nVar, nVar + batch);
+    pl->pendBatch = batch;
+    pl->pendLaunched = false;
+    std::vector<PmiPlan*> plans;
+    for (int r = 1; r <= maxRank && r <= kMaxLayers; ++r)
+        if (pl->cfg.riRestriction[r - 1]) plans.push_back(pl->byRank[r - 1]);
+    if (plans.empty() || (pl->byRank[0] && pl->byRank[0]->reK.empty())) return kOk;  // riSelect.m:235-245
+    int st = pmi_select_run_multi(plans.data(), (int)plans.size(), H, nVar, batch, c->stream);
+    if (st) { pl->pendBatch = 0; return st; }
+    if (!pl->ready) ISAC_CUDA_CHECK(c, cudaEventCreateWithFlags(&pl->ready, cudaEventDisableTiming));
+    ISAC_CUDA_CHECK(c, cudaMemcpyAsync(pl->h_arena, pl->d_arena, pl->arenaBytes, cudaMemcpyDeviceToHost, c->stream));
+    ISAC_CUDA_CHECK(c, cudaEventRecord(pl->ready, c->stream));  // one copy + one wait for all ranks
+    pl->pendLaunched = true;
+    return kOk;
+}
+
+// Waits for the arena of the pending report (not for work enqueued behind it) and runs the host-side rank selection.
+static int ri_finish(isac_csi_plan* pl, std::vector<double>& RI, std::vector<PmiResult>& chosen,
+                     std::vector<std::vector<PmiResult>>& all) {
+    Ctx* c = pl->ctx;
+    const int batch = pl->pendBatch;
+    if (batch < 1) { set_error(c, "csi report: nothing enqueued"); return kErrInvalidArg; }
+    pl->pendBatch = 0;
     const int maxRank = pl->cfg.nRx < pl->cfg.nPorts ? pl->cfg.nRx : pl->cfg.nPorts;
     all.assign(kMaxLayers, {});
     std::vector<int> valid;
@@ -922,18 +954,11 @@ static int ri_select_batch(isac_csi_plan* pl, const float2* H, const double* nVa
     RI.assign(batch, NAN);
     chosen.assign(batch, PmiResult());
     const int nSB = pl->byRank[0] ? pl->byRank[0]->nSB : 1;
-    if (valid.empty() || (pl->byRank[0] && pl->byRank[0]->reK.empty())) {  // riSelect.m:235-245
+    if (!pl->pendLaunched) {  // riSelect.m:235-245
         for (auto& r : chosen) { r.allNaN = true; r.i2.assign(nSB, NAN); }
         return kOk;
     }
-    {
-        std::vector<PmiPlan*> plans;
-        for (int r : valid) plans.push_back(pl->byRank[r - 1]);
-        int st = pmi_select_run_multi(plans.data(), (int)plans.size(), H, nVar, batch, c->stream);
-        if (st) return st;
-    }
-    ISAC_CUDA_CHECK(c, cudaMemcpyAsync(pl->h_arena, pl->d_arena, pl->arenaBytes, cudaMemcpyDeviceToHost, c->stream));
-    ISAC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));  // one copy + one synchronisation for all ranks
+    ISAC_CUDA_CHECK(c, cudaEventSynchronize(pl->ready));
     for (int r : valid) {
         int st = pmi_select_collect_finish(pl->byRank[r - 1], batch, all[r - 1]);
         if (st) return st;
@@ -957,6 +982,12 @@ static int ri_select_batch(isac_csi_plan* pl, const float2* H, const double* nVa
         }
     }
     return kOk;
+}
+
+static int ri_select_batch(isac_csi_plan* pl, const float2* H, const double* nVar, int batch, std::vector<double>& RI,
+                           std::vector<PmiResult>& chosen, std::vector<std::vector<PmiResult>>& all) {
+    const int st = ri_enqueue(pl, H, nVar, batch);
+    return st ? st : ri_finish(pl, RI, chosen, all);
 }
 
 int isac_ri_select_dev(isac_csi_plan* pl, const void* H, const double* nVar, int32_t batch, double* RI, double* i1, double* i2) {
@@ -1015,16 +1046,27 @@ int isac_cqi_select_dev(isac_csi_plan* pl, int32_t nLayers, const void* H, const
     return ISAC_OK;
 }
 
-int isac_csi_report_dev(isac_csi_plan* pl, const void* H, const double* nVar, int32_t batch, const double* table,
-                        int32_t tableLen, int32_t rankCap, double* RI, double* i1, double* i2, double* cqi, int32_t* cqiRows) {
-    if (!pl || !H || !nVar || !table || !RI) return ISAC_ERR_INVALID_ARG;
+int isac_csi_report_enqueue_dev(isac_csi_plan* pl, const void* H, const double* nVar, int32_t batch) {
+    if (!pl || !H || !nVar) return ISAC_ERR_INVALID_ARG;
     Ctx* c = pl->ctx;
     cudaSetDevice(c->device);
     if (batch < 1 || batch > pl->maxBatch) { set_error(c, "csi report: batch out of range"); return ISAC_ERR_INVALID_ARG; }
+    if (pl->pendBatch) { set_error(c, "csi report: the previous report of this plan has not been finished"); return ISAC_ERR_INVALID_ARG; }
+    return ri_enqueue(pl, (const float2*)H, nVar, batch);
+}
+
+int isac_csi_report_finish(isac_csi_plan* pl, const double* table, int32_t tableLen, int32_t rankCap, double* RI, double* i1,
+                           double* i2, double* cqi, int32_t* cqiRows) {
+    if (!pl || !table || !RI) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = pl->ctx;
+    cudaSetDevice(c->device);
+    const float2* H = pl->pendH;
+    const std::vector<double> nVar = pl->pendNVar;
+    const int batch = pl->pendBatch;
     std::vector<double> ri;
     std::vector<PmiResult> chosen;
     std::vector<std::vector<PmiResult>> all;
-    int st = ri_select_batch(pl, (const float2*)H, nVar, batch, ri, chosen, all);
+    int st = ri_finish(pl, ri, chosen, all);
     if (st) return st;
     PmiPlan* p0 = pl->byRank[0];
     const int rowsOut = (pl->cfg.cqiSubband && p0->nCqiSB > 1) ? p0->nCqiSB + 1 : 1;
@@ -1035,8 +1077,7 @@ int isac_csi_report_dev(isac_csi_plan* pl, const void* H, const double* nVar, in
         if (rankCap > 0 && rank > rankCap) rank = rankCap;  // uePhy.m:901
         if (std::isnan(ri[b])) RI[b] = NAN; else RI[b] = rank;
         if (all[rank - 1].empty()) {  // rank not scored by the RI loop (restricted): evaluate it now
-            std::vector<PmiResult> tmp;
-            if ((st = pmi_select_run(pl->byRank[rank - 1], (const float2*)H, nVar, batch, c->stream))) return st;
+            if ((st = pmi_select_run(pl->byRank[rank - 1], H, nVar.data(), batch, c->stream))) return st;
             if ((st = pmi_select_collect(pl->byRank[rank - 1], batch, all[rank - 1]))) return st;
         }
         const PmiResult& pr = all[rank - 1][b];
@@ -1046,6 +1087,13 @@ int isac_csi_report_dev(isac_csi_plan* pl, const void* H, const double* nVar, in
         put_pmi(pr, p0->nSB, rank, i1 ? i1 + 3 * b : nullptr, i2 ? i2 + (size_t)p0->nSB * b : nullptr, nullptr);
     }
     return ISAC_OK;
+}
+
+int isac_csi_report_dev(isac_csi_plan* pl, const void* H, const double* nVar, int32_t batch, const double* table,
+                        int32_t tableLen, int32_t rankCap, double* RI, double* i1, double* i2, double* cqi, int32_t* cqiRows) {
+    if (!pl || !H || !nVar || !table || !RI) return ISAC_ERR_INVALID_ARG;
+    const int st = isac_csi_report_enqueue_dev(pl, H, nVar, batch);
+    return st ? st : isac_csi_report_finish(pl, table, tableLen, rankCap, RI, i1, i2, cqi, cqiRows);
 }
 
 int isac_precoded_sinr_host(isac_ctx* h, const void* H, int32_t nRx, int32_t nPorts, double sigma, const void* W, int32_t nLayers,

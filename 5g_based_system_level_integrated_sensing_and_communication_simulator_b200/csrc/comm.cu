@@ -337,14 +337,18 @@ __global__ void __launch_bounds__(128) pmi_subband_kernel(const __grid_constant_
         const double* __restrict__ s = rk.S + ((long long)b * p.nRE * nu + l) * nCand + c;
         double acc = 0.0, plain = 0.0;
         bool any = false;
-#pragma unroll 4
-        for (int e = e0; e < e1; ++e) {
-            const double v = s[(long long)e * nu * nCand];
-            if (!isnan(v)) {
-                acc += p.reW[e] * v;
-                plain += v;   // un-weighted partial of sum(SINRPerRE,[1 2 3],'omitnan') (dlPMISelect.m:444)
-                any = true;
-            }
+        // 16 independent loads in flight per thread (one 16-PRB subband = 16 CSI-RS REs); the sums keep the RE order
+        for (int eb = e0; eb < e1; eb += 16) {
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (eb + j < e1) ? __ldcs(s + (long long)(eb + j) * nu * nCand) : NAN;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (!isnan(v[j])) {
+                    acc += p.reW[min(eb + j, e1 - 1)] * v[j];
+                    plain += v[j];   // un-weighted partial of sum(SINRPerRE,[1 2 3],'omitnan') (dlPMISelect.m:444)
+                    any = true;
+                }
         }
         const long long o = (((long long)b * p.nSB + sb) * nu + l) * nCand + c;
         rk.sub[o] = any ? acc : NAN;

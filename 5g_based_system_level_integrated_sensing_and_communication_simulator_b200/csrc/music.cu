@@ -49,9 +49,9 @@ __device__ __forceinline__ double2 cis2pi(double t) {  // exp(2*pi*j*t)
 // ------------------------------------------------------------------------------------------
 // K5: antenna covariance, deterministic two-stage reduction
 // ------------------------------------------------------------------------------------------
-constexpr int kCovBI = 4, kCovBJ = 8, kCovThreads = 256;
+constexpr int kCovBI = 4, kCovBJ = 4, kCovThreads = 256;  // 4x4 blocks of the upper triangle: 16 float64 accumulators per thread
 
-__global__ void __launch_bounds__(kCovThreads)
+__global__ void __launch_bounds__(kCovThreads, 2)
 cov_partial_kernel(const float2* __restrict__ rx, long long N, int nAnts, int jBlocks, int chunks, double2* __restrict__ part) {
     const int chunk = blockIdx.x, pair = blockIdx.y, b = blockIdx.z;
     const int ib = pair / jBlocks, jb = pair % jBlocks;
@@ -83,9 +83,9 @@ cov_partial_kernel(const float2* __restrict__ rx, long long N, int nAnts, int jB
             for (int i = 0; i < kCovBI; ++i)
 #pragma unroll
                 for (int j = 0; j < kCovBJ; ++j) {
-                    // conj(xi) * xj
-                    acc[i][j].x += xi[i].x * xj[j].x + xi[i].y * xj[j].y;
-                    acc[i][j].y += xi[i].x * xj[j].y - xi[i].y * xj[j].x;
+                    // acc += conj(xi) * xj as 4 DFMA (the sum-of-products form costs DMUL + DFMA + DADD per part)
+                    acc[i][j].x = fma(xi[i].x, xj[j].x, fma(xi[i].y, xj[j].y, acc[i][j].x));
+                    acc[i][j].y = fma(xi[i].x, xj[j].y, fma(-xi[i].y, xj[j].x, acc[i][j].y));
                 }
         }
     }

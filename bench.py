@@ -187,8 +187,12 @@ class CommWorkload:
         self.out_ind = torch.empty(cells * self.pdsch[2] * Pp, dtype=torch.int32, device=dev)
         self.slot_t = 0.5e-3
 
-    def step(self, step):
+    def step(self, step, fillers=()):
+        """One frame of COMM work.  `fillers`: up to four callables, one per CSI-RS occasion, that enqueue independent work
+        (the bench passes pieces of the cell's sensing pass) behind the report's kernels before the host blocks on the
+        report's results -- the GPU then stays busy during the host-side RI / CQI tails."""
         lib, ctx, C = self.ctx.lib, self.ctx, self.C
+        fillers = list(fillers)
         ptr, check = self._lib.ptr, self._lib.check
         ctx.use_torch_stream()
         frame_t0 = 0.010 * step
@@ -202,9 +206,12 @@ class CommWorkload:
                 self.t0_dl[:] = frame_t0 + slot * self.slot_t
                 check(lib.isac_cdl_generate_batch_dev(self.dl_handles, self.nb, self.K, self.SCS, 14, ptr(self.sym_t), ptr(self.t0_dl),
                                                       ptr(self.H)), ctx.handle)
-                check(lib.isac_csi_report_dev(self.csi_plan, ptr(self.H), ptr(self.nvar), self.nb, ptr(self.table),
-                                              self.table.size, 4, ptr(self.RI), ptr(self.i1), ptr(self.i2), ptr(self.cqi),
-                                              C.byref(self.rows)), ctx.handle)
+                check(lib.isac_csi_report_enqueue_dev(self.csi_plan, ptr(self.H), ptr(self.nvar), self.nb), ctx.handle)
+                if fillers:
+                    fillers.pop(0)()
+                    ctx.use_torch_stream()
+                check(lib.isac_csi_report_finish(self.csi_plan, ptr(self.table), self.table.size, 4, ptr(self.RI), ptr(self.i1),
+                                                 ptr(self.i2), ptr(self.cqi), C.byref(self.rows)), ctx.handle)
             if slot in srs:                       # SRS occasion: UL channel of the 4 UEs of the group + TPMI selection
                 grp = srs[slot]
                 self.t0_ul[:] = frame_t0 + slot * self.slot_t
@@ -273,23 +280,28 @@ def run_b200(args):
     import ctypes as C
     nsym_out = C.c_int32()
 
-    def sensing_step_dev(step):
+    def sensing_pieces(step):
         # device-resident leg: ONE stream, so that the CUDA-event intervals around each kernel group (the live roofline
-        # figures) are not stretched by kernels of another stream competing for the SMs
-        ctx_s.use_torch_stream()
-        for c in range(cells):
-            _lib.check(ctx_s.lib.isac_mono_static_sensing_dev(ctx_s.handle, C.byref(eargs.cfg), _lib.ptr(tx_wave_d[c]), None,
-                                                              _lib.NOISE_PHILOX, 7919 * step + c, _lib.ptr(rx_grid_d[c]),
-                                                              C.byref(nsym_out)), ctx_s.handle)
-        plan.run_dev(rx_grid_d, tx_grid_d, cells)
+        # figures) are not stretched by kernels of another stream competing for the SMs.  The sensing pass of the frame is
+        # enqueued in three pieces behind the kernels of the first three CSI reports (CommWorkload.step `fillers`): it is
+        # independent of the COMM slots (cellSimulation.m:191-197 runs it on the accumulated Tx grid only).
+        def echo(c0, c1):
+            def run():
+                ctx_s.use_torch_stream()
+                for c in range(c0, c1):
+                    _lib.check(ctx_s.lib.isac_mono_static_sensing_dev(ctx_s.handle, C.byref(eargs.cfg), _lib.ptr(tx_wave_d[c]),
+                                                                      None, _lib.NOISE_PHILOX, 7919 * step + c,
+                                                                      _lib.ptr(rx_grid_d[c]), C.byref(nsym_out)), ctx_s.handle)
+            return run
+        half = (cells + 1) // 2
+        return [echo(0, half), echo(half, cells), lambda: plan.run_dev(rx_grid_d, tx_grid_d, cells)]
 
     stages = ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa",
               "cdl_dl_generate", "csi_report(ri+pmi+cqi)", "cdl_ul_generate", "ul_tpmi_select", "prg_precode"]
     comm = CommWorkload(P, cells, local)
 
     def step_dev(step):
-        sensing_step_dev(step)
-        comm.step(step)
+        comm.step(step, sensing_pieces(step))
 
     # ---- device-resident timing ----------------------------------------------------------------
     for i in range(args.warmup):

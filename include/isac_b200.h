@@ -313,6 +313,15 @@ int isac_csi_report_dev(isac_csi_plan* plan, const void* H, const double* nVar, 
                         int32_t tableLen, int32_t rankCap, double* RI, double* i1, double* i2, double* cqi,
                         int32_t* cqiRows);
 
+/* The same report in two halves, so that the caller can enqueue independent work (the next slot's precoding, the sensing
+ * chain, another cell) behind the report's kernels before blocking: _enqueue_dev launches the kernels of every valid rank and
+ * the D2H copy of the selection results without synchronising; _finish waits for that copy only (not for work enqueued
+ * later on the stream) and runs the host-side RI / CQI tails.  One report may be pending per plan; H must stay valid until
+ * _finish returns. */
+int isac_csi_report_enqueue_dev(isac_csi_plan* plan, const void* H, const double* nVar, int32_t batch);
+int isac_csi_report_finish(isac_csi_plan* plan, const double* sinrTable, int32_t tableLen, int32_t rankCap, double* RI,
+                           double* i1, double* i2, double* cqi, int32_t* cqiRows);
+
 /* sinr = communication.phyLayer.precodedSINR(H,sigma,W) (precodedSINR.m:11-18) for `batch` REs that share W:
  * H host complex128 [nRx x nPorts x batch], W host complex128 [nPorts x nLayers], sinr host double [batch]
  * (LMMSE SINR summed over the layers).  nLayers <= 8, sigma > 0. */

@@ -160,6 +160,15 @@ def test_ri_cqi_and_fused_report(PH, n_ports, panel, n_rx, snr):
     assert rk == rank
     assert np.array_equal(pmf["i1"], pmc_o["i1"]) and np.array_equal(pmf["i2"], pmc_o["i2"], equal_nan=True)
     assert np.array_equal(cqf[:, : cqi_o.shape[1]], cqi_o, equal_nan=True)
+    # the same report in two halves, with unrelated work enqueued on the stream in between (isac_csi_report_enqueue_dev/_finish)
+    import torch
+    pend = PH.csiReportEnqueue(carrier, csirs, rc, H, n_var, table, rankCap=4)
+    junk = torch.randn(1 << 22, device="cuda").cumsum(0)
+    rk2, pmf2, cqf2 = pend.finish()
+    assert rk2 == rk and np.array_equal(pmf2["i1"], pmf["i1"]) and np.array_equal(pmf2["i2"], pmf["i2"], equal_nan=True)
+    assert np.array_equal(cqf2, cqf, equal_nan=True) and bool(torch.isfinite(junk[-1]))
+    with pytest.raises(Exception):
+        pend.finish()                      # nothing pending any more
     # 8-layer CQI has two codewords
     if n_rx == 8:
         cqi_o8, _, _, _ = C.cqi_select(ocfg, re_k, re_l, 8, H, n_var, table)
