@@ -169,3 +169,33 @@ def test_ofdm_modulate_is_the_inverse_of_demodulate():
         assert np.allclose(wave[:cp0], wave[info["Nfft"]: info["Nfft"] + cp0])
         back = S.ofdm_demodulate(nrb, scs, wave / 2.0)
         assert np.abs(back - grid).max() < 1e-12
+
+
+def test_vectorised_comm_oracle_equals_loop_faithful_oracle():
+    """oracle/comm.py holds two restatements of the CSI path: the loop nest of the reference (dl_pmi_select / ri_select /
+    cqi_select) and a vectorised one (sinr_per_re_vectorized / csi_report_vectorized) used for the CPU baseline and for the
+    full-size GPU parity tests (tests/test_cfg23_gpu.py).  They must agree."""
+    from oracle import comm as OC
+    rng = np.random.default_rng(77)
+    for n_ports, panel, n_rx in ((4, (2, 1), 2), (8, (2, 2), 4)):
+        nrb = 24
+        cfg = OC.report_config(n_ports, panel, nrb, 0, 1, "Subband", "Subband", 4)
+        re_k, re_l = OC.csirs_first_port_res(nrb, 1, 0)
+        H = (rng.standard_normal((12 * nrb, 14, n_rx, n_ports)) + 1j * rng.standard_normal((12 * nrb, 14, n_rx, n_ports))) / np.sqrt(2)
+        H = H + np.roll(H, 1, axis=0)
+        for nu in (1, 2):
+            _, info = OC.dl_pmi_select(cfg, re_k, re_l, nu, H, 0.05)
+            Sv, Wv = OC.sinr_per_re_vectorized(cfg, re_k, re_l, nu, H, 0.05)
+            S = info["SINRPerRE"]
+            assert S.shape == Sv.shape and np.array_equal(np.isnan(S), np.isnan(Sv))
+            m = ~np.isnan(S)
+            assert np.abs(S[m] - Sv[m]).max() <= 1e-10 * np.abs(S[m]).max()
+        table = np.array([-3.46, 1.54, 6.54, 11.05, 13.54, 16.04, 17.54, 20.04, 22.04, 24.43, 26.93, 27.43, 29.43, 32.43, 35.43])
+        ri, pm = OC.ri_select(cfg, re_k, re_l, H, 0.05)
+        rank = int(min(ri, 4))
+        cqi, pmc, _, _ = OC.cqi_select(cfg, re_k, re_l, rank, H, 0.05, table)
+        rv, pmv, cqv = OC.csi_report_vectorized(cfg, re_k, re_l, H, 0.05, table, rank_cap=4)
+        assert rv == rank and np.array_equal(pmv["i1"], pmc["i1"]) and np.array_equal(pmv["i2"], pmc["i2"], equal_nan=True)
+        d = cqv[1:] - cqv[:1]       # absolute subband CQIs -> differential report format (cqiSelect.m:656-677)
+        off = np.where(np.isnan(d), np.nan, np.where(d == 0, 0, np.where(d == 1, 1, np.where(d >= 2, 2, 3))))
+        assert np.array_equal(np.vstack([cqv[:1], off]), cqi[:, : cqv.shape[1]], equal_nan=True)
