@@ -49,7 +49,7 @@ def _check_power(P_gpu, P_ref):
     assert err_l2 <= 1e-5
 
 
-@pytest.mark.parametrize("name", ["tiny", "cfg1"])
+@pytest.mark.parametrize("name", ["tiny", "cfg1", "cfg2"])   # cfg2 = BASELINE config 2 at full size (3276 x 168 x 8 -> 4096 x 256)
 def test_rdm_power_and_cfar_match_oracle(gpu, workloads, name):
     rp, cf, rx, tx = _scenario(workloads, name)
     plan = _plan(rp, cf, rx.shape)

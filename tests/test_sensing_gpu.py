@@ -32,7 +32,7 @@ def _rel_rms(a, b):
     return np.abs(a - b).max() / np.sqrt(np.mean(np.abs(b) ** 2))
 
 
-@pytest.mark.parametrize("name", ["tiny", "cfg1"])
+@pytest.mark.parametrize("name", ["tiny", "cfg1", "cfg2"])   # cfg2 = BASELINE config 2 at full size (3276 x 168 x 8 -> 4096 x 256)
 def test_mono_static_sensing_matches_oracle(P, workloads, name):
     cell, car, wave, rp, grid, txw, noise = _setup(workloads, name)
     txw32, nz32 = txw.astype(np.complex64), noise.astype(np.complex64)
@@ -81,7 +81,7 @@ def test_generated_noise_statistics(P, workloads):
     assert abs(np.mean(d.real * d.imag)) < 0.03 * expect
 
 
-@pytest.mark.parametrize("name", ["tiny", "cfg1"])
+@pytest.mark.parametrize("name", ["tiny", "cfg1", "cfg2"])   # cfg2 = BASELINE config 2 at full size (3276 x 168 x 8 -> 4096 x 256)
 def test_fft2d_estimator_matches_oracle(P, workloads, name):
     cell, car, wave, rp, grid, txw, noise = _setup(workloads, name)
     rx = S.mono_static_sensing(txw, grid.shape, car, rp, cell["targetLoSConditions"], noise).astype(np.complex64)
