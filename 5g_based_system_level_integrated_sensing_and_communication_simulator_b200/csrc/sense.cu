@@ -68,13 +68,66 @@ int sense_plan_create(Ctx* ctx, const RdmConfig& rc, const DoaConfig& doa, doubl
     SALLOC(ctx, p->d_order, sizeof(int) * n, sense_plan_destroy(p));
     cudaMemset(p->d_status, 0, sizeof(int) * B);
     cudaMemset(p->d_nPeaks, 0, sizeof(int) * B);
+    p->detCap = r->nCut < 512 ? r->nCut : 512;
+    const size_t pages = n * B;
+    const size_t stageBytes = sizeof(int) * (pages + 3 * B + (size_t)kMaxPeaks * B) + (sizeof(int2) + sizeof(float)) * (size_t)p->detCap * pages + 16;  // + alignment pad of the int2 section
+    if (cudaMallocHost((void**)&p->h_stage, stageBytes) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming) != cudaSuccess) {
+        set_error(ctx, "sense_plan_create: pinned staging allocation failed");
+        sense_plan_destroy(p);
+        return kErrCuda;
+    }
     *out = p;
+    return kOk;
+}
+
+// pinned staging layout (see SensePlan::h_stage)
+struct StageView {
+    int *cnt, *L, *nPk, *stt, *pk;
+    int2* det;
+    float* peak;
+};
+static StageView stage_view(const SensePlan* p) {
+    const size_t B = p->rdm->cfg.maxBatch, pages = (size_t)p->rdm->cfg.nAnts * B;
+    StageView v;
+    v.cnt = reinterpret_cast<int*>(p->h_stage);
+    v.L = v.cnt + pages;
+    v.nPk = v.L + B;
+    v.stt = v.nPk + B;
+    v.pk = v.stt + B;
+    v.det = reinterpret_cast<int2*>(v.pk + (size_t)kMaxPeaks * B + ((pages + 3 * B + (size_t)kMaxPeaks * B) & 1));  // 8-byte aligned
+    v.peak = reinterpret_cast<float*>(v.det + (size_t)p->detCap * pages);
+    return v;
+}
+
+// D2H copies of everything collect needs, enqueued behind the chain; `ready` marks their completion
+static int stage_results(SensePlan* p, int batch, cudaStream_t st) {
+    RdmPlan* r = p->rdm;
+    Ctx* ctx = r->ctx;
+    const int pages = r->cfg.nAnts * batch;
+    StageView v = stage_view(p);
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(v.cnt, r->d_detCount, sizeof(int32_t) * pages, cudaMemcpyDeviceToHost, st));
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(v.L, p->d_L, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    if (!p->doa.isUpa) {
+        ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(v.nPk, p->d_nPeaks, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+        ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(v.stt, p->d_status, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+        ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(v.pk, p->d_peakLoc, sizeof(int) * kMaxPeaks * batch, cudaMemcpyDeviceToHost, st));
+    }
+    // first detCap detections of every page: pages are nCut entries apart on the device, detCap apart in the staging buffer
+    ISAC_CUDA_CHECK(ctx, cudaMemcpy2DAsync(v.det, sizeof(int2) * p->detCap, r->d_det, sizeof(int2) * r->nCut, sizeof(int2) * p->detCap,
+                                           pages, cudaMemcpyDeviceToHost, st));
+    ISAC_CUDA_CHECK(ctx, cudaMemcpy2DAsync(v.peak, sizeof(float) * p->detCap, r->d_peak, sizeof(float) * r->nCut,
+                                           sizeof(float) * p->detCap, pages, cudaMemcpyDeviceToHost, st));
+    ISAC_CUDA_CHECK(ctx, cudaEventRecord(p->ready, st));
+    p->stagedBatch = batch;
     return kOk;
 }
 
 void sense_plan_destroy(SensePlan* p) {
     if (!p) return;
     if (p->rdm) rdm_plan_destroy(p->rdm);
+    if (p->h_stage) cudaFreeHost(p->h_stage);
+    if (p->ready) cudaEventDestroy(p->ready);
     cudaFree(p->d_Ra);
     cudaFree(p->d_w);
     cudaFree(p->d_V);
@@ -113,8 +166,9 @@ int sense_fft2d_run(SensePlan* p, const float2* rx, const float2* tx, int batch,
         LSource ls{};
         ls.rowmask = r->d_rowmask;
         ls.rowWords = r->rowWords;
-        return music_doa_ula(ctx, p->d_w, p->d_V, n, batch, p->doa, ls, p->d_L, p->d_P, p->d_PdB, p->d_peakLoc,
-                             p->d_nPeaks, p->d_status, st);  // music.m:73-104
+        s = music_doa_ula(ctx, p->d_w, p->d_V, n, batch, p->doa, ls, p->d_L, p->d_P, p->d_PdB, p->d_peakLoc,
+                          p->d_nPeaks, p->d_status, st);  // music.m:73-104
+        return s ? s : stage_results(p, batch, st);
     }
     // UPA (music.m:31-63): spectrum only, the reference's peak picker (tools.find2DPeaks) does not exist
     popcount_L_kernel<<<batch, 32, 0, st>>>(r->d_rowmask, r->rowWords, p->d_L);
@@ -148,7 +202,7 @@ int sense_fft2d_run(SensePlan* p, const float2* rx, const float2* tx, int batch,
                           p->d_PdB + (size_t)b * p->specLen, st);
         if (s) return s;
     }
-    return kOk;
+    return stage_results(p, batch, st);
 }
 
 int sense_fft2d_collect(SensePlan* p, int batch, std::vector<Fft2dResult>& out) {
@@ -156,34 +210,35 @@ int sense_fft2d_collect(SensePlan* p, int batch, std::vector<Fft2dResult>& out) 
     Ctx* ctx = r->ctx;
     const RdmConfig& c = r->cfg;
     cudaStream_t st = ctx->stream;
-    const int nA = c.nAnts, pages = nA * batch;
-    std::vector<int32_t> cnt(pages);
-    std::vector<int> L(batch), nPk(batch), stt(batch), pk((size_t)kMaxPeaks * batch);
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(cnt.data(), r->d_detCount, sizeof(int32_t) * pages, cudaMemcpyDeviceToHost, st));
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(L.data(), p->d_L, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
-    if (!p->doa.isUpa) {
-        ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(nPk.data(), p->d_nPeaks, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
-        ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(stt.data(), p->d_status, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
-        ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(pk.data(), p->d_peakLoc, sizeof(int) * kMaxPeaks * batch,
-                                             cudaMemcpyDeviceToHost, st));
+    const int nA = c.nAnts;
+    if (batch < 1 || batch > p->stagedBatch) {
+        set_error(ctx, "fft2D collect: no staged run covers this batch (call isac_fft2d_dev first)");
+        return kErrInvalidArg;
     }
-    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    ISAC_CUDA_CHECK(ctx, cudaEventSynchronize(p->ready));  // the staged copies only, not work enqueued behind them
+    const StageView v = stage_view(p);
     out.assign(batch, Fft2dResult());
-    std::vector<int2> det;
-    std::vector<float> peak;
+    std::vector<int2> detBig;
+    std::vector<float> peakBig;
     for (int b = 0; b < batch; ++b) {
         Fft2dResult& res = out[b];
         std::vector<double> allR, allV;
         for (int a = 0; a < nA; ++a) {
-            const int pg = b * nA + a, n = cnt[pg];
+            const int pg = b * nA + a, n = v.cnt[pg];
             if (n <= 0) continue;
-            det.resize(n);
-            peak.resize(n);
-            ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(det.data(), r->d_det + (size_t)r->nCut * pg, sizeof(int2) * n,
-                                                 cudaMemcpyDeviceToHost, st));
-            ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(peak.data(), r->d_peak + (size_t)r->nCut * pg, sizeof(float) * n,
-                                                 cudaMemcpyDeviceToHost, st));
-            ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+            const int2* det = v.det + (size_t)p->detCap * pg;
+            const float* peak = v.peak + (size_t)p->detCap * pg;
+            if (n > p->detCap) {  // more detections than the staged prefix: fetch this page directly
+                detBig.resize(n);
+                peakBig.resize(n);
+                ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(detBig.data(), r->d_det + (size_t)r->nCut * pg, sizeof(int2) * n,
+                                                     cudaMemcpyDeviceToHost, st));
+                ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(peakBig.data(), r->d_peak + (size_t)r->nCut * pg, sizeof(float) * n,
+                                                     cudaMemcpyDeviceToHost, st));
+                ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+                det = detBig.data();
+                peak = peakBig.data();
+            }
             std::vector<int> idx(n);
             std::iota(idx.begin(), idx.end(), 0);
             std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return peak[x] > peak[y]; });  // fft2D.m:89
@@ -200,11 +255,11 @@ int sense_fft2d_collect(SensePlan* p, int batch, std::vector<Fft2dResult>& out) 
         };
         res.rngEst = uniq(allR);
         res.velEst = uniq(allV);
-        res.L = L[b];
-        res.status = p->doa.isUpa ? 0 : stt[b];
+        res.L = v.L[b];
+        res.status = p->doa.isUpa ? 0 : v.stt[b];
         if (!p->doa.isUpa && res.status == 0)
-            for (int i = 0; i < nPk[b]; ++i)
-                res.aziEst.push_back((double)(pk[(size_t)b * kMaxPeaks + i] - 1) * p->doa.aGran - p->doa.aMax / 2.0);  // music.m:103
+            for (int i = 0; i < v.nPk[b]; ++i)
+                res.aziEst.push_back((double)(v.pk[(size_t)b * kMaxPeaks + i] - 1) * p->doa.aGran - p->doa.aMax / 2.0);  // music.m:103
     }
     return kOk;
 }

@@ -23,6 +23,15 @@ struct SensePlan {
     int* d_status = nullptr;   // [maxBatch]
     int* d_order = nullptr;    // large-array eigen order [nAnts]
     int specLen = 0;
+    // Results of the last run staged in pinned memory by copies enqueued behind the chain (sense_fft2d_run), so that
+    // sense_fft2d_collect waits on `ready` only -- not on work enqueued later on the stream -- and never copies again:
+    //   counts [pages] | L [B] | nPeaks [B] | status [B] | peakLoc [kMaxPeaks x B] | det [detCap x pages] | peak [detCap x pages]
+    // Only the first detCap detections of every (antenna, map-set) page are staged; a page with more falls back to a
+    // direct copy in collect.
+    char* h_stage = nullptr;
+    int detCap = 0;
+    cudaEvent_t ready = nullptr;
+    int stagedBatch = 0;       // batch of the staged run (0 = nothing staged)
 };
 
 int sense_plan_create(Ctx* ctx, const RdmConfig& rc, const DoaConfig& doa, double rRes, double vRes, SensePlan** out);
