@@ -27,6 +27,7 @@ struct EchoDev {
     const float2* tx;      // [T x nTx]
     const float2* noise;   // [T x nAnts] standard normals, or nullptr
     const float2* steer;   // [nAnts x nTgt] float2 (device) when it does not fit the inline table
+    const float2* beamed;  // [T x nTgt] u_i[m] = sum_t tx[m,t] a_i[t] from echo_beamform_kernel, or nullptr (gather in place)
     FftTw tw;
     float2* out;           // [nSc x nSymOut x nAnts]
     long long T;
@@ -82,7 +83,8 @@ __device__ __forceinline__ float2 target_sample(const EchoDev& p, int i, long lo
     const long long m = n - p.shift[i];
     if (n >= p.T || m < 0) return make_float2(0.f, 0.f);
     float2 u = make_float2(0.f, 0.f);
-    for (int t = 0; t < p.nTx; ++t) {
+    if (p.beamed) u = __ldg(p.beamed + (long long)i * p.T + m);
+    else for (int t = 0; t < p.nTx; ++t) {
         const float2 x = __ldg(p.tx + (long long)t * p.T + m);
         const float2 at = a[t];
         u.x += x.x * at.x - x.y * at.y;
@@ -92,6 +94,36 @@ __device__ __forceinline__ float2 target_sample(const EchoDev& p, int i, long lo
     float s, c;
     sincospif(2.0f * ph, &s, &c);
     return cmul(cmul(u, make_float2(c, s)), p.beta[i]);
+}
+
+// Pass 0: transmit beamforming of every target stream, u_i[m] = sum_t tx[m,t] a_i[t] (basicRadarChannel.m:51 rank-1 spatial
+// response, a_t == a_r).  One thread per sample: the nTx antenna streams are read ONCE (coalesced along m) for all targets;
+// pass 1 then reads one beamformed stream per (symbol, target) instead of gathering nTx streams per target.
+template <int NTG>   // NTG = nTgt rounded up to a power of two: the per-target loops unroll without dead predicated work
+__global__ void __launch_bounds__(256)
+echo_beamform_kernel(const EchoDev p, float2* __restrict__ U) {
+    __shared__ float2 steerS[kEchoInlineSteer];
+    for (int i = threadIdx.x; i < p.nAnts * p.nTgt && i < kEchoInlineSteer; i += blockDim.x)
+        steerS[i] = p.steerInline ? p.steerTab[i] : p.steer[i];
+    __syncthreads();
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= p.T) return;
+    float2 u[NTG];
+#pragma unroll
+    for (int i = 0; i < NTG; ++i) u[i] = make_float2(0.f, 0.f);
+    for (int t = 0; t < p.nTx; ++t) {
+        const float2 x = ld_stream(p.tx + (long long)t * p.T + m);
+#pragma unroll
+        for (int i = 0; i < NTG; ++i)
+            if (i < p.nTgt) {   // same accumulation order over t as the in-place gather of target_sample
+                const float2 at = steerS[i * p.nAnts + t];
+                u[i].x += x.x * at.x - x.y * at.y;
+                u[i].y += x.x * at.y + x.y * at.x;
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < NTG; ++i)
+        if (i < p.nTgt) U[(long long)i * p.T + m] = u[i];
 }
 
 // Pass 1: one CTA per (OFDM symbol, stream).  Streams 0..nTgt-1 are the target waveforms w_i; with an explicit noise
@@ -139,47 +171,62 @@ echo_stream_fft_kernel(const EchoDev p, float2* __restrict__ W) {
     }
 }
 
-// Pass 2: echoGrid[k,s,r] = ramp_s[k] * ( sum_i a_i[r] W_i[k,s] + noise ), zero beyond the demodulated symbols
+// Pass 2: echoGrid[k,s,r] = ramp_s[k] * ( sum_i a_i[r] W_i[k,s] + noise ), zero beyond the demodulated symbols.
+// One thread per (subcarrier, symbol) loops over the receive antennas: the nTgt stream spectra and the phase ramp are
+// fetched / evaluated once for all antennas, and one Philox call feeds two antennas.
+template <int NTG>
 __global__ void __launch_bounds__(256)
 echo_combine_kernel(const EchoDev p, const float2* __restrict__ W, int NF) {
     __shared__ float2 steerS[kEchoInlineSteer];
+    const bool steerInSmem = p.steerInline || p.nAnts * p.nTgt <= kEchoInlineSteer;
     for (int i = threadIdx.x; i < p.nAnts * p.nTgt && i < kEchoInlineSteer; i += blockDim.x)
         steerS[i] = p.steerInline ? p.steerTab[i] : p.steer[i];
     __syncthreads();
-    const int s = blockIdx.y, r = blockIdx.z;
+    const int s = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= p.nSc) return;
-    float2* __restrict__ o = p.out + ((long long)r * p.nSymOut + s) * p.nSc + k;
+    float2* __restrict__ o = p.out + (long long)s * p.nSc + k;      // + r * nSymOut * nSc
+    const long long page = (long long)p.nSymOut * p.nSc;
     if (s >= p.nSymRx) {  // zero padding up to txDimension(2) (monoStaticSensing.m:19-21)
-        *o = make_float2(0.f, 0.f);
+        for (int r = 0; r < p.nAnts; ++r) o[r * page] = make_float2(0.f, 0.f);
         return;
     }
+    float2 w[NTG];
+#pragma unroll
+    for (int i = 0; i < NTG; ++i)
+        w[i] = i < p.nTgt ? __ldcs(W + ((size_t)i * p.nSymRx + s) * p.nSc + k) : make_float2(0.f, 0.f);
     const int cp = p.cpTab[s % p.symPer];
     const int off = cp / 2, half = p.nSc / 2;
-    float2 acc = make_float2(0.f, 0.f);
-    for (int i = 0; i < p.nTgt; ++i) {
-        const float2 w = W[((size_t)i * p.nSymRx + s) * p.nSc + k];
-        const float2 ar = p.steerInline || p.nAnts * p.nTgt <= kEchoInlineSteer ? steerS[i * p.nAnts + r] : p.steer[i * p.nAnts + r];
-        acc.x += w.x * ar.x - w.y * ar.y;
-        acc.y += w.x * ar.y + w.y * ar.x;
-    }
-    if (p.noiseMode == 1) {
-        const float2 z = W[((size_t)(p.nTgt + r) * p.nSymRx + s) * p.nSc + k];
-        acc.x += p.noiseSigma * z.x;
-        acc.y += p.noiseSigma * z.y;
-    } else if (p.noiseMode == 2) {
-        const uint4 ctr = make_uint4((unsigned)k, (unsigned)s, (unsigned)r, 0x15ACu);
-        const uint4 rn = philox4x32(ctr, make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
-        const float2 g = gauss_pair(rn.x, rn.y);
-        const float sc = p.noiseSigma * sqrtf((float)NF);
-        acc.x += sc * g.x;
-        acc.y += sc * g.y;
-    }
     // undo the early FFT window start: exp(+2 pi j kk (cp - off)/Nfft), kk = k - nSc/2
     const float rampStep = (float)(cp - off) / (float)NF;  // cycles per subcarrier index
     float sn, cs;
     sincospif(2.0f * rampStep * (float)(k - half), &sn, &cs);
-    *o = cmul(acc, make_float2(cs, sn));
+    const float2 ramp = make_float2(cs, sn);
+    const float sc = p.noiseSigma * sqrtf((float)NF);
+    uint4 rn = make_uint4(0u, 0u, 0u, 0u);
+    for (int r = 0; r < p.nAnts; ++r) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NTG; ++i)
+            if (i < p.nTgt) {
+                const float2 ar = steerInSmem ? steerS[i * p.nAnts + r] : p.steer[i * p.nAnts + r];
+                acc.x += w[i].x * ar.x - w[i].y * ar.y;
+                acc.y += w[i].x * ar.y + w[i].y * ar.x;
+            }
+        if (p.noiseMode == 1) {
+            const float2 z = __ldcs(W + ((size_t)(p.nTgt + r) * p.nSymRx + s) * p.nSc + k);
+            acc.x += p.noiseSigma * z.x;
+            acc.y += p.noiseSigma * z.y;
+        } else if (p.noiseMode == 2) {
+            if ((r & 1) == 0)   // one counter block = four uniforms = two complex normals (antennas r, r+1)
+                rn = philox4x32(make_uint4((unsigned)k, (unsigned)s, (unsigned)(r >> 1), 0x15ACu),
+                                make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
+            const float2 g = (r & 1) ? gauss_pair(rn.z, rn.w) : gauss_pair(rn.x, rn.y);
+            acc.x += sc * g.x;
+            acc.y += sc * g.y;
+        }
+        o[r * page] = cmul(acc, ramp);
+    }
 }
 
 // basicRadarChannel alone: rxWaveform [T x nAnts]
@@ -314,8 +361,20 @@ static cudaError_t launch_echo(const EchoDev& d, float2* W, cudaStream_t st) {
     auto k = echo_stream_fft_kernel<R1, R2>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int streams = d.nTgt + (d.noiseMode == 1 ? d.nAnts : 0);
-    if (d.nSymRx > 0 && streams > 0) k<<<dim3(d.nSymRx, streams), G::NT, smem, st>>>(d, W);
-    echo_combine_kernel<<<dim3((d.nSc + 255) / 256, d.nSymOut, d.nAnts), 256, 0, st>>>(d, W, G::N);
+    const dim3 gB((unsigned)((d.T + 255) / 256)), gC((d.nSc + 255) / 256, d.nSymOut);
+    float2* U = const_cast<float2*>(d.beamed);
+#define ISAC_ECHO_NTG(NTG_)                                                                   \
+    do {                                                                                   \
+        if (U) echo_beamform_kernel<NTG_><<<gB, 256, 0, st>>>(d, U);                           \
+        if (d.nSymRx > 0 && streams > 0) k<<<dim3(d.nSymRx, streams), G::NT, smem, st>>>(d, W); \
+        echo_combine_kernel<NTG_><<<gC, 256, 0, st>>>(d, W, G::N);                             \
+    } while (0)
+    if (d.nTgt <= 1) ISAC_ECHO_NTG(1);
+    else if (d.nTgt <= 2) ISAC_ECHO_NTG(2);
+    else if (d.nTgt <= 4) ISAC_ECHO_NTG(4);
+    else if (d.nTgt <= 8) ISAC_ECHO_NTG(8);
+    else ISAC_ECHO_NTG(16);
+#undef ISAC_ECHO_NTG
     return cudaGetLastError();
 }
 
@@ -361,6 +420,11 @@ int mono_static_sensing_run(Ctx* ctx, const EchoConfig& c, const float2* tx, con
     void* dW = nullptr;   // stream spectra between the two passes
     const size_t streams = (size_t)d.nTgt + (noiseMode == 1 ? d.nAnts : 0);
     if ((s = ctx_scratch(ctx, 17, sizeof(float2) * (streams ? streams : 1) * (nSymRx ? nSymRx : 1) * c.nSc, &dW))) return s;
+    void* dU = nullptr;   // beamformed target streams (pass 0) when the steering table fits shared memory
+    if (d.nAnts * d.nTgt <= kEchoInlineSteer) {
+        if ((s = ctx_scratch(ctx, 18, sizeof(float2) * (size_t)d.nTgt * c.T, &dU))) return s;
+    }
+    d.beamed = (const float2*)dU;
     cudaError_t e;
     const int pr = prof_begin(ctx, kProfEcho, st);
     switch (c.nfft) {
@@ -372,7 +436,7 @@ int mono_static_sensing_run(Ctx* ctx, const EchoConfig& c, const float2* tx, con
         default: e = launch_echo<16, 16>(d, (float2*)dW, st); break;
     }
     prof_end(ctx, pr, st);
-    count_launches(ctx, 2);
+    count_launches(ctx, dU ? 3 : 2);
     ISAC_CUDA_CHECK(ctx, e);
     return kOk;
 }
