@@ -330,6 +330,97 @@ rdm_range4096_lean_kernel(const RdmDev p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Kernel A-direct (N = 4096): direct-load persistent range IFFT.  As the lean kernel but without the shared-memory stage:
+// every thread fetches its NJ rx / tx samples of the column with coalesced streaming loads straight into registers (thread tf
+// owns n = tf + 256 j, so a warp reads 256 contiguous bytes per load).  That removes the stage's write + read (42 % of the lean
+// kernel's shared-memory traffic) and shrinks the CTA to 48 KB of shared memory; the load latency is hidden by the other CTAs
+// of the SM instead of by a prefetch.  MINB = CTAs per SM the register budget is sized for.
+// ------------------------------------------------------------------------------------------
+template <int NJ, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+rdm_range4096_direct_kernel(const RdmDev p) {
+    constexpr int N = 4096, NT = 256, S1 = 257;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    float2* fftbuf = reinterpret_cast<float2*>(smraw);
+    float2* tw2s = fftbuf + 16 * S1;                       // [15][16]
+    float* w1s = reinterpret_cast<float*>(tw2s + 240);    // [NJ*256], zero beyond nSc
+    __shared__ int sNext;
+    const int tf = threadIdx.x;
+    const int nSc = p.nSc;
+    if (tf < 240) tw2s[tf] = __ldg(p.twR.tw2 + tf);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int n = tf + NT * j;
+        w1s[n] = (n < nSc) ? __ldg(p.win1 + n) : 0.f;
+    }
+    float2 tw1r[15];
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) tw1r[k1 - 1] = __ldg(p.twR.tw1 + (k1 - 1) * NT + tf);
+    const float* const w1 = w1s + tf;
+    const float2* const tw2 = tw2s + (tf & 15);
+    float2* const f1 = fftbuf + tf;
+    float2* const f2 = fftbuf + (tf >> 4) * S1 + (tf & 15);
+    const float2* const f3 = fftbuf + (tf & 15) * S1 + (tf >> 4) * 16;
+    const int M = p.M, nSym = p.nSym, half = p.nSym / 2;
+    const unsigned long long polOut = l2_policy((p.hints >> 2) & 3);
+    const int total = (int)p.totalCols;
+    const bool lastRow = tf + NT * (NJ - 1) < nSc;   // the last register row is only partly inside the grid
+    if (tf == 0) sNext = atomicAdd(p.ticketR, 1);
+    __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;");
+    int col = sNext;
+    bool mustWait = true;
+    while (col < total) {
+        const int sp = col % M, page = col / M;
+        int sy = sp + half;
+        if (sy >= nSym) sy -= nSym;  // ifftshift on the symbol axis (fft2D.m:44)
+        const size_t off = ((size_t)page * nSym + sy) * (size_t)nSc + tf;
+        const float2* __restrict__ rx = p.rx + off;
+        const float2* __restrict__ tx = p.tx + off;
+        float2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (j < NJ) {
+                const bool in = j < NJ - 1 || lastRow;
+                const float2 a = in ? ld_stream(rx + NT * j) : make_float2(0.f, 0.f);
+                const float2 b = in ? ld_stream(tx + NT * j) : make_float2(0.f, 0.f);
+                v[j] = pk_scale(pk_cmulc(a, b), w1[NT * j]);  // rx.*conj(tx).*rngWin (fft2D.m:37,43)
+            } else {
+                v[j] = make_float2(0.f, 0.f);
+            }
+        }
+        __syncthreads();   // the previous column's pass-3 loads are done (fftbuf reuse) and its sNext has been read
+        if (tf == 0) sNext = atomicAdd(p.ticketR, 1);
+        dft16<+1>(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) v[k1] = pk_cmul(v[k1], tw1r[k1 - 1]);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) f1[k1 * S1] = v[k1];
+        __syncthreads();
+#pragma unroll
+        for (int a2 = 0; a2 < 16; ++a2) v[a2] = f2[a2 * 16];
+        dft16<+1>(v);
+#pragma unroll
+        for (int c = 1; c < 16; ++c) v[c] = pk_cmul(v[c], tw2[(c - 1) * 16]);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) f2[c * 16] = v[c];
+        __syncthreads();
+        const int nxt = sNext;   // written behind the first barrier of this column
+#pragma unroll
+        for (int b2 = 0; b2 < 16; ++b2) v[b2] = f3[b2];
+        dft16<+1>(v);
+        if (mustWait) {  // first column only: everything above overlapped the tail of the preceding grid
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            mustWait = false;
+        }
+        float2* __restrict__ out = p.inter + (size_t)col * N + tf;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) st_hint(out + NT * d, v[d], polOut);
+        col = nxt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Kernel B' (F = 256): persistent Doppler FFT with bulk-copy staging.  One 256-thread CTA walks tiles of 16
 // consecutive range rows of one antenna page; the [M symbols x 16 rows] input tile of the NEXT tile is fetched from
 // the (L2-resident) range profiles by ONE 2-D tensor copy (cp.async.bulk.tensor, one mbarrier per buffer) while
@@ -777,6 +868,22 @@ static cudaError_t launch_range_lean_nj(const RdmDev& d, int numSMs, bool pdl, c
     if (blocks > d.totalCols) blocks = d.totalCols;
     return launch_ex(k, (unsigned)blocks, 256, smem, st, pdl, d);
 }
+template <int NJ, int MINB>
+static cudaError_t launch_range_direct_nj(const RdmDev& d, int numSMs, bool pdl, cudaStream_t st) {
+    const size_t smem = sizeof(float2) * (16 * 257 + 240) + sizeof(float) * NJ * 256;
+    auto k = rdm_range4096_direct_kernel<NJ, MINB>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    long long blocks = (long long)MINB * numSMs;
+    if (blocks > d.totalCols) blocks = d.totalCols;
+    return launch_ex(k, (unsigned)blocks, 256, smem, st, pdl, d);
+}
+static cudaError_t launch_range_direct(const RdmDev& d, int numSMs, int minb, bool pdl, cudaStream_t st) {
+    if (d.nSc <= 13 * 256 && d.nSc > 12 * 256)
+        return minb >= 4 ? launch_range_direct_nj<13, 4>(d, numSMs, pdl, st)
+                         : minb == 3 ? launch_range_direct_nj<13, 3>(d, numSMs, pdl, st) : launch_range_direct_nj<13, 2>(d, numSMs, pdl, st);
+    return minb >= 3 ? launch_range_direct_nj<16, 3>(d, numSMs, pdl, st) : launch_range_direct_nj<16, 2>(d, numSMs, pdl, st);
+}
 static cudaError_t launch_range_lean(const RdmDev& d, int numSMs, bool pdl, cudaStream_t st) {
     return d.nSc <= 13 * 256 ? launch_range_lean_nj<13>(d, numSMs, pdl, st) : launch_range_lean_nj<16>(d, numSMs, pdl, st);
 }
@@ -951,7 +1058,13 @@ int rdm_run(RdmPlan* p, const float2* rx, const float2* tx, int batch, float* po
                     if (p->variant == 0 || p->variant == 3) {
                         d.win2 = p->d_rowScale;  // raw range profiles: window / scale / centring move to the Doppler kernel
                         // PDL edge Doppler(b-1) -> range(b): only behind this plan's own bulk-staged Doppler kernel
-                        e = launch_range_lean(d, ctx_num_sms(ctx), p->pdl && b > 0 && prevTmaDoppler, st);
+                        static const int directMinb = getenv("ISAC_RDM_DIRECT") ? atoi(getenv("ISAC_RDM_DIRECT")) : 0;
+                        if (directMinb >= 2 && c.nSc > 15 * 256)   // experimental direct-load range kernel (NJ = 16 row guard)
+                            e = launch_range_direct(d, ctx_num_sms(ctx), directMinb, p->pdl && b > 0 && prevTmaDoppler, st);
+                        else if (directMinb >= 2 && c.nSc > 12 * 256 && c.nSc <= 13 * 256)
+                            e = launch_range_direct(d, ctx_num_sms(ctx), directMinb, p->pdl && b > 0 && prevTmaDoppler, st);
+                        else
+                            e = launch_range_lean(d, ctx_num_sms(ctx), p->pdl && b > 0 && prevTmaDoppler, st);
                         raw = true;
                     } else {
                         e = launch_range_tma(d, ctx_num_sms(ctx), st);
