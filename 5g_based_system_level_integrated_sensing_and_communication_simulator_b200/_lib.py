@@ -160,6 +160,8 @@ def _declare(lib):
         "isac_ul_pmi_select_dev": ([vp, i32, vp, i32, i32, i32, i32, f64, i32, i32, vp, vp, vp, P(i32), P(i32), P(i32)],
                                    C.c_int),
         "isac_ul_pmi_select_batch_dev": ([vp, i32, vp, i32, i32, i32, i32, f64, i32, i32, i32, vp, vp, P(i32), P(i32), vp], C.c_int),
+        "isac_ul_pmi_select_batch_enqueue_dev": ([vp, i32, vp, i32, i32, i32, i32, f64, i32, i32], C.c_int),
+        "isac_ul_pmi_select_batch_finish": ([vp, i32, vp, vp, P(i32), P(i32), vp], C.c_int),
         "isac_cdl_generate_batch_dev": ([vp, i32, i32, f64, i32, vp, vp, vp], C.c_int),
         "isac_prg_precode_dev": ([vp, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, vp, vp], C.c_int),
         "isac_prg_precode_batch_dev": ([vp, i32, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, vp, vp], C.c_int),

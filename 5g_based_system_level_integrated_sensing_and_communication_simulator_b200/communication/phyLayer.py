@@ -406,28 +406,47 @@ def pmiSelect(nlayers, hest, noiseest, bandSize):
     return pmi[:n].copy(), sinr[: n * nT].reshape((n, nT), order="F"), idx[: 2 * n].reshape((n, 2), order="F")
 
 
-def pmiSelectBatch(nlayers, hest, noiseest, bandSize):
-    """pmiSelect for a batch of estimates resident on the device: hest torch complex64 [batch][nPorts][nRx][nSym][K].
-    Returns (pmi [nSB x batch], sinr [nSB x nTPMI x batch], none [batch]); one synchronisation for the batch."""
+class PendingPmiSelect:
+    """A batched pmiSelect whose kernels are enqueued (pmiSelectBatchEnqueue); ``finish()`` waits for its results only."""
+
+    def __init__(self, ctx, hd, B, P, K, nlayers, bandSize):
+        self.ctx, self.hd, self.B = ctx, hd, B      # hd kept alive until finish()
+        self.max_sb = int(math.ceil(K / 12 / bandSize)) + 1
+        self.nT = maxPUSCHPrecodingMatrixIndicator(nlayers, P) + 1
+
+    def finish(self):
+        B, max_sb, nT = self.B, self.max_sb, self.nT
+        pmi = np.zeros(max_sb * B)
+        sinr = np.zeros(max_sb * nT * B)
+        none = np.zeros(B, dtype=np.int32)
+        nSB, nTo = C.c_int32(), C.c_int32()
+        _lib.check(self.ctx.lib.isac_ul_pmi_select_batch_finish(self.ctx.handle, max_sb, _lib.ptr(pmi), _lib.ptr(sinr), C.byref(nSB),
+                                                                C.byref(nTo), _lib.ptr(none)), self.ctx.handle)
+        self.hd = None
+        n = nSB.value
+        pmi = pmi.reshape((max_sb, B), order="F")[:n].copy()
+        sinr = np.stack([sinr.reshape((max_sb * nT, B), order="F")[: n * nT, b].reshape((n, nT), order="F") for b in range(B)], axis=2)
+        pmi[:, none != 0] = np.nan
+        sinr[:, :, none != 0] = np.nan
+        return pmi, sinr, none
+
+
+def pmiSelectBatchEnqueue(nlayers, hest, noiseest, bandSize):
+    """First half of pmiSelectBatch: kernels + asynchronous result copy on the current torch stream, no synchronisation
+    (isac_ul_pmi_select_batch_enqueue_dev).  One report may be pending per context."""
     hd = hest.contiguous()
     B, P, R, Ls, K = hd.shape
     ctx = _lib.get_context(None)
-    max_sb = int(math.ceil(K / 12 / bandSize)) + 1
-    nT = maxPUSCHPrecodingMatrixIndicator(nlayers, P) + 1
-    pmi = np.zeros(max_sb * B)
-    sinr = np.zeros(max_sb * nT * B)
-    none = np.zeros(B, dtype=np.int32)
-    nSB, nTo = C.c_int32(), C.c_int32()
     ctx.use_torch_stream()
-    _lib.check(ctx.lib.isac_ul_pmi_select_batch_dev(ctx.handle, int(nlayers), _lib.ptr(hd), K, Ls, R, P, float(noiseest),
-                                                    int(bandSize), B, max_sb, _lib.ptr(pmi), _lib.ptr(sinr), C.byref(nSB),
-                                                    C.byref(nTo), _lib.ptr(none)), ctx.handle)
-    n = nSB.value
-    pmi = pmi.reshape((max_sb, B), order="F")[:n].copy()
-    sinr = np.stack([sinr.reshape((max_sb * nT, B), order="F")[: n * nT, b].reshape((n, nT), order="F") for b in range(B)], axis=2)
-    pmi[:, none != 0] = np.nan
-    sinr[:, :, none != 0] = np.nan
-    return pmi, sinr, none
+    _lib.check(ctx.lib.isac_ul_pmi_select_batch_enqueue_dev(ctx.handle, int(nlayers), _lib.ptr(hd), K, Ls, R, P, float(noiseest),
+                                                            int(bandSize), B), ctx.handle)
+    return PendingPmiSelect(ctx, hd, B, P, K, nlayers, bandSize)
+
+
+def pmiSelectBatch(nlayers, hest, noiseest, bandSize):
+    """pmiSelect for a batch of estimates resident on the device: hest torch complex64 [batch][nPorts][nRx][nSym][K].
+    Returns (pmi [nSB x batch], sinr [nSB x nTPMI x batch], none [batch]); one synchronisation for the batch."""
+    return pmiSelectBatchEnqueue(nlayers, hest, noiseest, bandSize).finish()
 
 
 def precodedSINR(H, sigma, W):

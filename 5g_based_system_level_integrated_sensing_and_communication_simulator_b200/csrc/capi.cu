@@ -1136,15 +1136,9 @@ int isac_ul_pmi_select_dev(isac_ctx* h, int32_t nLayers, const void* hest, int32
     return ISAC_OK;
 }
 
-int isac_ul_pmi_select_batch_dev(isac_ctx* h, int32_t nLayers, const void* hest, int32_t K, int32_t nSym, int32_t nRx, int32_t nPorts,
-                                 double noiseEst, int32_t bandSize, int32_t batch, int32_t maxSB, double* pmi, double* sinr,
-                                 int32_t* nSB, int32_t* nTPMI, int32_t* none) {
-    if (!h || !hest || !nSB || !nTPMI || !none) return ISAC_ERR_INVALID_ARG;
-    Ctx* c = &h->c;
-    cudaSetDevice(c->device);
-    std::vector<UlPmiResult> r;
-    int st = ul_pmi_select_batch(c, nLayers, (const float2*)hest, K, nSym, nRx, nPorts, noiseEst, bandSize, batch, r, c->stream);
-    if (st) return st;
+static int ul_batch_outputs(Ctx* c, const std::vector<UlPmiResult>& r, int32_t maxSB, double* pmi, double* sinr, int32_t* nSB,
+                            int32_t* nTPMI, int32_t* none) {
+    const int batch = (int)r.size();
     *nSB = r[0].nSB; *nTPMI = r[0].nTPMI;
     if (r[0].nSB > maxSB) { set_error(c, "pmiSelect: maxSB too small"); return ISAC_ERR_CAPACITY; }
     for (int b = 0; b < batch; ++b) {
@@ -1154,6 +1148,37 @@ int isac_ul_pmi_select_batch_dev(isac_ctx* h, int32_t nLayers, const void* hest,
         if (sinr) std::memcpy(sinr + (size_t)maxSB * r[0].nTPMI * b, r[b].sinr.data(), sizeof(double) * r[b].sinr.size());
     }
     return ISAC_OK;
+}
+
+int isac_ul_pmi_select_batch_dev(isac_ctx* h, int32_t nLayers, const void* hest, int32_t K, int32_t nSym, int32_t nRx, int32_t nPorts,
+                                 double noiseEst, int32_t bandSize, int32_t batch, int32_t maxSB, double* pmi, double* sinr,
+                                 int32_t* nSB, int32_t* nTPMI, int32_t* none) {
+    if (!h || !hest || !nSB || !nTPMI || !none) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    std::vector<UlPmiResult> r;
+    int st = ul_pmi_select_batch(c, nLayers, (const float2*)hest, K, nSym, nRx, nPorts, noiseEst, bandSize, batch, r, c->stream);
+    if (st) return st;
+    return ul_batch_outputs(c, r, maxSB, pmi, sinr, nSB, nTPMI, none);
+}
+
+int isac_ul_pmi_select_batch_enqueue_dev(isac_ctx* h, int32_t nLayers, const void* hest, int32_t K, int32_t nSym, int32_t nRx,
+                                         int32_t nPorts, double noiseEst, int32_t bandSize, int32_t batch) {
+    if (!h || !hest) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    return ul_pmi_select_batch_enqueue(c, nLayers, (const float2*)hest, K, nSym, nRx, nPorts, noiseEst, bandSize, batch, c->stream);
+}
+
+int isac_ul_pmi_select_batch_finish(isac_ctx* h, int32_t maxSB, double* pmi, double* sinr, int32_t* nSB, int32_t* nTPMI,
+                                    int32_t* none) {
+    if (!h || !nSB || !nTPMI || !none) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    std::vector<UlPmiResult> r;
+    int st = ul_pmi_select_batch_finish(c, r);
+    if (st) return st;
+    return ul_batch_outputs(c, r, maxSB, pmi, sinr, nSB, nTPMI, none);
 }
 
 int isac_prg_precode_dev(isac_ctx* h, int32_t K, int32_t Lsym, int32_t nStartGrid, const void* portsym, const int32_t* portind,

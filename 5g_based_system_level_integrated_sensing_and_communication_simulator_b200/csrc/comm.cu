@@ -1200,11 +1200,38 @@ int ul_pmi_select_run(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int
     return s;
 }
 
+// A UL report whose kernels and result copy are enqueued but whose host tail has not run yet (one per context)
+struct UlPending {
+    Ctx* ctx = nullptr;
+    bool active = false, launched = false;
+    int batch = 0, nSB = 0, nT = 0;
+    UlPmiResult proto;
+    double* hBands = nullptr;   // pinned [nSB x nT x batch]
+    size_t hBytes = 0;
+    cudaEvent_t ready = nullptr;
+};
+static std::vector<UlPending*> g_ulPending;
+static UlPending* ul_pending(Ctx* ctx) {
+    for (UlPending* u : g_ulPending)
+        if (u->ctx == ctx) return u;
+    UlPending* u = new UlPending();
+    u->ctx = ctx;
+    g_ulPending.push_back(u);
+    return u;
+}
+
 int ul_pmi_select_batch(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int R, int P, double noiseEst, int bandSize,
                         int batch, std::vector<UlPmiResult>& outs, cudaStream_t st) {
+    const int s = ul_pmi_select_batch_enqueue(ctx, nu, hest, K, nSym, R, P, noiseEst, bandSize, batch, st);
+    return s ? s : ul_pmi_select_batch_finish(ctx, outs);
+}
+
+int ul_pmi_select_batch_enqueue(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int R, int P, double noiseEst, int bandSize,
+                                int batch, cudaStream_t st) {
     if (batch < 1) { set_error(ctx, "pmiSelect: batch < 1"); return kErrInvalidArg; }
-    outs.assign(batch, UlPmiResult());
-    UlPmiResult& out = outs[0];
+    UlPending* pend = ul_pending(ctx);
+    if (pend->active) { set_error(ctx, "pmiSelect: the previous enqueued report has not been finished"); return kErrInvalidArg; }
+    UlPmiResult out;
     if (!hest || K < 12 || nSym < 1 || R < 1 || R > 16 || bandSize < 1) {
         set_error(ctx, "pmiSelect: invalid argument");
         return kErrInvalidArg;
@@ -1225,9 +1252,11 @@ int ul_pmi_select_batch(Ctx* ctx, int nu, const float2* hest, int K, int nSym, i
     }
     out.subbandIndices.resize((size_t)nSB * 2);
     for (int i = 0; i < nSB; ++i) { out.subbandIndices[i] = lo[i]; out.subbandIndices[nSB + i] = hi[i]; }
+    pend->batch = batch; pend->nSB = nSB; pend->nT = nT; pend->launched = false;
     if (noiseEst == 0.0) {  // pmiSelect.m:39
         out.none = true;
-        for (int b = 1; b < batch; ++b) outs[b] = out;
+        pend->proto = out;
+        pend->active = true;
         return kOk;
     }
     // the PUSCH codebook of (nu, P) and the band limits are uploaded once per context and cached
@@ -1269,14 +1298,35 @@ int ul_pmi_select_batch(Ctx* ctx, int nu, const float2* hest, int K, int nSym, i
     prof_end(ctx, pr, st);
     count_launches(ctx, 2);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
-    std::vector<double> all((size_t)nSB * nT * batch);
-    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(all.data(), dB, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, st));
-    ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    const UlPmiResult proto = out;
+    const size_t bytes = sizeof(double) * (size_t)nSB * nT * batch;
+    if (pend->hBytes < bytes) {
+        if (pend->hBands) cudaFreeHost(pend->hBands);
+        pend->hBands = nullptr;
+        pend->hBytes = 0;
+        ISAC_CUDA_CHECK(ctx, cudaMallocHost((void**)&pend->hBands, bytes));
+        pend->hBytes = bytes;
+    }
+    if (!pend->ready) ISAC_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&pend->ready, cudaEventDisableTiming));
+    ISAC_CUDA_CHECK(ctx, cudaMemcpyAsync(pend->hBands, dB, bytes, cudaMemcpyDeviceToHost, st));
+    ISAC_CUDA_CHECK(ctx, cudaEventRecord(pend->ready, st));
+    pend->proto = out;
+    pend->launched = true;
+    pend->active = true;
+    return kOk;
+}
+
+// Waits for the band SINRs of the enqueued report only (not for work enqueued behind it) and runs the host tail.
+int ul_pmi_select_batch_finish(Ctx* ctx, std::vector<UlPmiResult>& outs) {
+    UlPending* pend = ul_pending(ctx);
+    if (!pend->active) { set_error(ctx, "pmiSelect: nothing enqueued"); return kErrInvalidArg; }
+    pend->active = false;
+    const int batch = pend->batch, nSB = pend->nSB, nT = pend->nT;
+    outs.assign(batch, pend->proto);
+    if (!pend->launched) return kOk;   // zero noise estimate: every report is "none" (pmiSelect.m:39,60-64)
+    ISAC_CUDA_CHECK(ctx, cudaEventSynchronize(pend->ready));
     for (int b = 0; b < batch; ++b) {
         UlPmiResult& o = outs[b];
-        o = proto;
-        const double* bands = all.data() + (size_t)b * nSB * nT;
+        const double* bands = pend->hBands + (size_t)b * nSB * nT;
         // "no channel estimates" <=> every band is 0/0 (pmiSelect.m:39,60-64)
         bool any = false;
         for (size_t i = 0; i < (size_t)nSB * nT; ++i) any |= !std::isnan(bands[i]);

@@ -126,6 +126,10 @@ int ul_pmi_select_run(Ctx* ctx, int nLayers, const float2* hest, int K, int nSym
 // `batch` independent estimates stacked along a 5th dimension (one synchronisation for all of them)
 int ul_pmi_select_batch(Ctx* ctx, int nLayers, const float2* hest, int K, int nSym, int nRx, int P, double noiseEst,
                         int bandSize, int batch, std::vector<UlPmiResult>& out, cudaStream_t st);
+// the same in two halves: kernels + async result copy (no synchronisation) / wait for that copy + host tail
+int ul_pmi_select_batch_enqueue(Ctx* ctx, int nLayers, const float2* hest, int K, int nSym, int nRx, int P, double noiseEst,
+                                int bandSize, int batch, cudaStream_t st);
+int ul_pmi_select_batch_finish(Ctx* ctx, std::vector<UlPmiResult>& out);
 
 // precodedSINR (precodedSINR.m:11-18) for `batch` REs sharing W: H [nRx x P x batch], W [P x nLayers] complex128 (device)
 int precoded_sinr_run(Ctx* ctx, const double2* H, int R, int P, double sigma, const double2* W, int nLayers, int batch,

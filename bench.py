@@ -198,6 +198,7 @@ class CommWorkload:
         ctx.use_torch_stream()
         frame_t0 = 0.010 * step
         srs = {3: 0, 4: 1, 11: 0, 12: 1, 19: 0}   # UEs 0-3 at slots 3, 11, 19, UEs 4-7 at slots 4, 12 (period 8, offset 3 + floor(ue/4))
+        ul_pending = False
         for slot in range(20):                    # slot order of the frame (TDD DDDSU @30 kHz); the GPU's cells advance together
             if slot % 5 < 3:                      # DL slot: PDSCH + DM-RS precoding of every cell (gNBPhy.m:822,826)
                 for sym, ind, nre in (self.pdsch, self.dmrs):
@@ -213,15 +214,22 @@ class CommWorkload:
                     ctx.use_torch_stream()
                 check(lib.isac_csi_report_finish(self.csi_plan, ptr(self.table), self.table.size, 4, ptr(self.RI), ptr(self.i1),
                                                  ptr(self.i2), ptr(self.cqi), C.byref(self.rows)), ctx.handle)
+            if ul_pending:                        # TPMI results of the previous slot's SRS occasion: their kernels ran behind
+                ul_pending = False                #   this slot's precoding launches, so the host only collects here
+                check(lib.isac_ul_pmi_select_batch_finish(ctx.handle, self.ul_pmi.size // self.nul, ptr(self.ul_pmi), ptr(self.ul_sinr),
+                                                          C.byref(self.ul_n[0]), C.byref(self.ul_n[1]), ptr(self.ul_none)), ctx.handle)
             if slot in srs:                       # SRS occasion: UL channel of the 4 UEs of the group + TPMI selection
                 grp = srs[slot]
                 self.t0_ul[:] = frame_t0 + slot * self.slot_t
                 check(lib.isac_cdl_generate_batch_dev(self.ul_handles[grp], self.nul, self.K, self.SCS, 1, ptr(self.sym13), ptr(self.t0_ul),
                                                       ptr(self.hest)), ctx.handle)
                 self.hest.mul_(self.comb)                                   # comb-4 SRS REs only (setupSRS.m:11-18)
-                check(lib.isac_ul_pmi_select_batch_dev(ctx.handle, 2, ptr(self.hest), self.K, 1, 8, 2, 0.05, 16, self.nul,
-                                                       self.ul_pmi.size // self.nul, ptr(self.ul_pmi), ptr(self.ul_sinr),
-                                                       C.byref(self.ul_n[0]), C.byref(self.ul_n[1]), ptr(self.ul_none)), ctx.handle)
+                check(lib.isac_ul_pmi_select_batch_enqueue_dev(ctx.handle, 2, ptr(self.hest), self.K, 1, 8, 2, 0.05, 16, self.nul),
+                      ctx.handle)
+                ul_pending = True
+        if ul_pending:                            # SRS occasion in the frame's last slot
+            check(lib.isac_ul_pmi_select_batch_finish(ctx.handle, self.ul_pmi.size // self.nul, ptr(self.ul_pmi), ptr(self.ul_sinr),
+                                                      C.byref(self.ul_n[0]), C.byref(self.ul_n[1]), ptr(self.ul_none)), ctx.handle)
 
     def d2h_bytes_per_step(self):
         return 4 * (self.RI.nbytes + self.i1.nbytes + self.i2.nbytes + self.cqi.nbytes) + 5 * (self.ul_pmi.nbytes + self.ul_sinr.nbytes)

@@ -338,6 +338,13 @@ int isac_ul_pmi_select_dev(isac_ctx* ctx, int32_t nLayers, const void* hest, int
 int isac_ul_pmi_select_batch_dev(isac_ctx* ctx, int32_t nLayers, const void* hest, int32_t K, int32_t nSym, int32_t nRx,
                                  int32_t nPorts, double noiseEst, int32_t bandSize, int32_t batch, int32_t maxSB, double* pmi,
                                  double* sinr, int32_t* nSB, int32_t* nTPMI, int32_t* none);
+/* The batched report in two halves (as isac_csi_report_enqueue_dev / _finish): _enqueue_dev launches the kernels and the copy
+ * of the band SINRs without synchronising, _finish waits for that copy only and runs the host-side TPMI selection.  One
+ * report may be pending per context. */
+int isac_ul_pmi_select_batch_enqueue_dev(isac_ctx* ctx, int32_t nLayers, const void* hest, int32_t K, int32_t nSym, int32_t nRx,
+                                         int32_t nPorts, double noiseEst, int32_t bandSize, int32_t batch);
+int isac_ul_pmi_select_batch_finish(isac_ctx* ctx, int32_t maxSB, double* pmi, double* sinr, int32_t* nSB, int32_t* nTPMI,
+                                    int32_t* none);
 /* [antsym,antind] = communication.phyLayer.prgPrecode(siz,nstartgrid,portsym,portind,F) (prgPrecode.m:53).
  * portsym complex64 / portind int32 (1-based) [NRE x nLayers], F complex64 [nLayers x P x NPRG] (device);
  * antsym complex64 / antind int32 [NRE x P] (device). */

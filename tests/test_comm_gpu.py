@@ -218,6 +218,13 @@ def test_ul_pmi_select_batch(PH):
     hd = torch.from_numpy(np.ascontiguousarray(hest.transpose(0, 4, 3, 2, 1))).cuda()
     pmi_b, sinr_b, none = PH.pmiSelectBatch(nu, hd, 0.05, band)
     assert list(none) == [0, 0, 0, 1, 0]
+    pend = PH.pmiSelectBatchEnqueue(nu, hd, 0.05, band)       # the same report in two halves with unrelated work in between
+    junk = torch.randn(1 << 20, device="cuda").sum()
+    pmi_e, sinr_e, none_e = pend.finish()
+    assert np.array_equal(pmi_e, pmi_b, equal_nan=True) and np.array_equal(sinr_e, sinr_b, equal_nan=True)
+    assert list(none_e) == list(none) and bool(torch.isfinite(junk))
+    with pytest.raises(Exception):
+        pend.finish()
     for b in range(B):
         r = PH.pmiSelect(nu, hest[b], 0.05, band)
         if b == 3:
