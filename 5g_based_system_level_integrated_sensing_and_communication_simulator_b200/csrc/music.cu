@@ -67,6 +67,7 @@ cov_partial_kernel(const float2* __restrict__ rx, long long N, int nAnts, int jB
         const long long per = (N + chunks - 1) / chunks;
         const long long t0 = (long long)chunk * per;
         const long long t1 = (t0 + per < N) ? t0 + per : N;
+#pragma unroll 2
         for (long long t = t0 + threadIdx.x; t < t1; t += kCovThreads) {
             double2 xi[kCovBI], xj[kCovBJ];
 #pragma unroll
@@ -106,10 +107,11 @@ cov_partial_kernel(const float2* __restrict__ rx, long long N, int nAnts, int jB
     }
 }
 
-__global__ void cov_final_kernel(const double2* __restrict__ part, int nAnts, int jBlocks, int nPairs, int chunks,
-                                 double invN, double2* __restrict__ Ra) {
+// one warp per matrix entry: the lanes stride over the chunk partials, then a fixed-order shuffle reduction (deterministic)
+__global__ void __launch_bounds__(256) cov_final_kernel(const double2* __restrict__ part, int nAnts, int jBlocks, int nPairs,
+                                                        int chunks, double invN, double2* __restrict__ Ra) {
     const int b = blockIdx.y;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (idx >= nAnts * nAnts) return;
     const int i = idx % nAnts, j = idx / nAnts;
     const int ii = i <= j ? i : j, jj = i <= j ? j : i;  // take (ii,jj) from the upper triangle
@@ -118,8 +120,11 @@ __global__ void cov_final_kernel(const double2* __restrict__ part, int nAnts, in
     const int pair = ib * jBlocks + jb;
     const int e = (ii - ib * kCovBI) * kCovBJ + (jj - jb * kCovBJ);
     double2 s = make_double2(0.0, 0.0);
-    for (int c = 0; c < chunks; ++c)
+    for (int c = lane; c < chunks; c += 32)
         s = zadd(s, part[(((long long)b * nPairs + pair) * chunks + c) * (kCovBI * kCovBJ) + e]);
+    s.x = warp_sum(s.x);
+    s.y = warp_sum(s.y);
+    if (lane) return;
     s.x *= invN;
     s.y *= invN;
     if (i > j) s.y = -s.y;
@@ -134,7 +139,11 @@ int cov_antenna(Ctx* ctx, const float2* rx, long long N, int nAnts, int batch, d
     }
     const int iBlocks = (nAnts + kCovBI - 1) / kCovBI, jBlocks = (nAnts + kCovBJ - 1) / kCovBJ;
     const int nPairs = iBlocks * jBlocks;
-    int chunks = (4 * ctx->numSMs) / (nPairs * batch);
+    // one full wave of CTAs that do work (2 per SM, launch bounds): only the block pairs touching the upper triangle count
+    int needed = 0;
+    for (int ib = 0; ib < iBlocks; ++ib)
+        for (int jb = 0; jb < jBlocks; ++jb) needed += (jb * kCovBJ + kCovBJ - 1 >= ib * kCovBI);
+    int chunks = (2 * ctx->numSMs) / (needed * batch);
     if (chunks < 1) chunks = 1;
     const long long maxChunks = (N + kCovThreads - 1) / kCovThreads;
     if (chunks > maxChunks) chunks = (int)maxChunks;
@@ -145,7 +154,7 @@ int cov_antenna(Ctx* ctx, const float2* rx, long long N, int nAnts, int batch, d
     const int pr = prof_begin(ctx, kProfCov, st);
     cov_partial_kernel<<<grid, kCovThreads, 0, st>>>(rx, N, nAnts, jBlocks, chunks, (double2*)part);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
-    dim3 g2((nAnts * nAnts + 255) / 256, batch);
+    dim3 g2((nAnts * nAnts + 7) / 8, batch);   // 8 warps = 8 entries per CTA
     cov_final_kernel<<<g2, 256, 0, st>>>((const double2*)part, nAnts, jBlocks, nPairs, chunks, 1.0 / (double)N, Ra);
     prof_end(ctx, pr, st);
     count_launches(ctx, 2);
