@@ -23,3 +23,25 @@ def cfar2D(radaParams):
     detector = {"Method": "CA", "ThresholdFactor": "Auto", "ProbabilityFalseAlarm": float(radaParams["Pfa"]),
                 "OutputFormat": "Detection index", "GuardBandSize": (2, 2), "TrainingBandSize": (1, 1)}
     return {"CUTIdx": CUTIdx, "cfarDetector2D": detector, "rngIdx": rngIdx, "dopIdx": dopIdx}
+
+
+def getPd(Pfa, snrdB, nPulses=1):
+    """``Pd = sensing.detection.getPd(Pfa, snrdB, nPulses)`` (reference +sensing/+detection/getPd.m:1): detection probability
+    over the SNR grid ``snrdB`` for every false-alarm probability in ``Pfa``; returns ``Pd[len(snrdB), len(Pfa)]`` like
+    ``rocpfa`` (the reference's figure is not drawn).
+
+    ``rocpfa(Pfa,'MaxSNR',..,'MinSNR',..,'NumPoints',..,'NumPulses',N)`` is a closed Phased Array System Toolbox function;
+    with its default signal type ('NonfluctuatingCoherent') it evaluates the textbook receiver operating characteristic of a
+    non-fluctuating target in complex white Gaussian noise with coherent detection, N pulses integrated coherently
+    (PARITY-UNPINNED against the toolbox):   Pd = 1/2 erfc( erfcinv(2 Pfa) - sqrt(N * SNR) ).
+    The SNR points are ``linspace(snrdB(1), snrdB(end), numel(snrdB))`` exactly as the reference passes them (getPd.m:9-12),
+    i.e. a non-uniform ``snrdB`` is resampled uniformly, as in the reference.  Host-only, as in the reference."""
+    from math import sqrt
+    from scipy.special import erfc, erfcinv
+    pfa = np.atleast_1d(np.asarray(Pfa, dtype=np.float64)).ravel()
+    snr_in = np.atleast_1d(np.asarray(snrdB, dtype=np.float64)).ravel()
+    if snr_in.size < 1 or np.any(pfa <= 0) or np.any(pfa >= 1) or nPulses < 1:
+        raise ValueError("getPd: Pfa must lie in (0,1), snrdB must be non-empty and nPulses >= 1")
+    snr_db = np.linspace(snr_in[0], snr_in[-1], snr_in.size)
+    snr = 10.0 ** (snr_db / 10.0)
+    return 0.5 * erfc(erfcinv(2.0 * pfa)[None, :] - np.sqrt(float(nPulses) * snr)[:, None])

@@ -199,3 +199,20 @@ def test_vectorised_comm_oracle_equals_loop_faithful_oracle():
         d = cqv[1:] - cqv[:1]       # absolute subband CQIs -> differential report format (cqiSelect.m:656-677)
         off = np.where(np.isnan(d), np.nan, np.where(d == 0, 0, np.where(d == 1, 1, np.where(d >= 2, 2, 3))))
         assert np.array_equal(np.vstack([cqv[:1], off]), cqi[:, : cqv.shape[1]], equal_nan=True)
+
+
+def test_get_pd_receiver_operating_characteristic():
+    """sensing.detection.getPd (getPd.m:1 -> rocpfa, NonfluctuatingCoherent): closed-form known answers."""
+    import importlib
+    det = importlib.import_module("5g_based_system_level_integrated_sensing_and_communication_simulator_b200.sensing.detection")
+    snr = np.linspace(-40.0, 30.0, 71)
+    pd = det.getPd([1e-3, 1e-6, 1e-9], snr, 1)
+    assert pd.shape == (71, 3)
+    assert np.allclose(pd[0], [1e-3, 1e-6, 1e-9], rtol=0.1)          # no signal: Pd -> Pfa
+    assert np.all(pd[-1] > 1 - 1e-12)                                # strong signal: Pd -> 1
+    assert np.all(np.diff(pd, axis=0) >= 0) and np.all(np.diff(pd, axis=1) <= 0)   # monotone in SNR and in Pfa
+    # Pd = 1/2 where sqrt(N SNR) = erfcinv(2 Pfa); N pulses shift the curve by 10 log10 N dB
+    from scipy.special import erfcinv
+    s_half = 20 * np.log10(erfcinv(2e-6))
+    assert abs(float(det.getPd(1e-6, [s_half, s_half], 1)[0, 0]) - 0.5) < 1e-12
+    assert abs(float(det.getPd(1e-6, [s_half - 10 * np.log10(16.0)] * 2, 16)[0, 0]) - 0.5) < 1e-12
