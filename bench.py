@@ -187,6 +187,21 @@ class CommWorkload:
         self.out_sym = torch.empty(cells * self.pdsch[2] * Pp, dtype=torch.complex64, device=dev)
         self.out_ind = torch.empty(cells * self.pdsch[2] * Pp, dtype=torch.int32, device=dev)
         self.slot_t = 0.5e-3
+        # argument tuples of the per-slot calls, marshalled once (every buffer is allocated above and reused each frame):
+        # the precoding kernels take ~13 us, so per-call pointer marshalling in Python would leave the GPU waiting
+        ptr = self._lib.ptr
+        h = self.ctx.handle
+        self.prg_args = [(h, self.K, 14, 0, ptr(sym), ptr(ind), nre, 2, ptr(self.F), 8, self.nprg, self.cells, ptr(self.out_sym),
+                          ptr(self.out_ind)) for sym, ind, nre in (self.pdsch, self.dmrs)]
+        self.cdl_dl_args = (self.dl_handles, self.nb, self.K, self.SCS, 14, ptr(self.sym_t), ptr(self.t0_dl), ptr(self.H))
+        self.cdl_ul_args = [(self.ul_handles[g], self.nul, self.K, self.SCS, 1, ptr(self.sym13), ptr(self.t0_ul), ptr(self.hest))
+                            for g in range(2)]
+        self.csi_enq_args = (self.csi_plan, ptr(self.H), ptr(self.nvar), self.nb)
+        self.csi_fin_args = (self.csi_plan, ptr(self.table), self.table.size, 4, ptr(self.RI), ptr(self.i1), ptr(self.i2),
+                             ptr(self.cqi), C.byref(self.rows))
+        self.ul_enq_args = (h, 2, ptr(self.hest), self.K, 1, 8, 2, 0.05, 16, self.nul)
+        self.ul_fin_args = (h, self.ul_pmi.size // self.nul, ptr(self.ul_pmi), ptr(self.ul_sinr), C.byref(self.ul_n[0]),
+                            C.byref(self.ul_n[1]), ptr(self.ul_none))
 
     def step(self, step, fillers=()):
         """One frame of COMM work.  `fillers`: up to four callables, one per CSI-RS occasion, that enqueue independent work
@@ -201,35 +216,27 @@ class CommWorkload:
         ul_pending = False
         for slot in range(20):                    # slot order of the frame (TDD DDDSU @30 kHz); the GPU's cells advance together
             if slot % 5 < 3:                      # DL slot: PDSCH + DM-RS precoding of every cell (gNBPhy.m:822,826)
-                for sym, ind, nre in (self.pdsch, self.dmrs):
-                    check(lib.isac_prg_precode_batch_dev(ctx.handle, self.K, 14, 0, ptr(sym), ptr(ind), nre, 2, ptr(self.F), 8, self.nprg,
-                                                         self.cells, ptr(self.out_sym), ptr(self.out_ind)), ctx.handle)
+                for a in self.prg_args:
+                    check(lib.isac_prg_precode_batch_dev(*a), ctx.handle)
             if slot % 5 == 2:                     # CSI-RS occasion (period 5 slots): channel of all UEs + fused RI/PMI/CQI report
                 self.t0_dl[:] = frame_t0 + slot * self.slot_t
-                check(lib.isac_cdl_generate_batch_dev(self.dl_handles, self.nb, self.K, self.SCS, 14, ptr(self.sym_t), ptr(self.t0_dl),
-                                                      ptr(self.H)), ctx.handle)
-                check(lib.isac_csi_report_enqueue_dev(self.csi_plan, ptr(self.H), ptr(self.nvar), self.nb), ctx.handle)
+                check(lib.isac_cdl_generate_batch_dev(*self.cdl_dl_args), ctx.handle)
+                check(lib.isac_csi_report_enqueue_dev(*self.csi_enq_args), ctx.handle)
                 if fillers:
                     fillers.pop(0)()
                     ctx.use_torch_stream()
-                check(lib.isac_csi_report_finish(self.csi_plan, ptr(self.table), self.table.size, 4, ptr(self.RI), ptr(self.i1),
-                                                 ptr(self.i2), ptr(self.cqi), C.byref(self.rows)), ctx.handle)
+                check(lib.isac_csi_report_finish(*self.csi_fin_args), ctx.handle)
             if ul_pending:                        # TPMI results of the previous slot's SRS occasion: their kernels ran behind
                 ul_pending = False                #   this slot's precoding launches, so the host only collects here
-                check(lib.isac_ul_pmi_select_batch_finish(ctx.handle, self.ul_pmi.size // self.nul, ptr(self.ul_pmi), ptr(self.ul_sinr),
-                                                          C.byref(self.ul_n[0]), C.byref(self.ul_n[1]), ptr(self.ul_none)), ctx.handle)
+                check(lib.isac_ul_pmi_select_batch_finish(*self.ul_fin_args), ctx.handle)
             if slot in srs:                       # SRS occasion: UL channel of the 4 UEs of the group + TPMI selection
-                grp = srs[slot]
                 self.t0_ul[:] = frame_t0 + slot * self.slot_t
-                check(lib.isac_cdl_generate_batch_dev(self.ul_handles[grp], self.nul, self.K, self.SCS, 1, ptr(self.sym13), ptr(self.t0_ul),
-                                                      ptr(self.hest)), ctx.handle)
+                check(lib.isac_cdl_generate_batch_dev(*self.cdl_ul_args[srs[slot]]), ctx.handle)
                 self.hest.mul_(self.comb)                                   # comb-4 SRS REs only (setupSRS.m:11-18)
-                check(lib.isac_ul_pmi_select_batch_enqueue_dev(ctx.handle, 2, ptr(self.hest), self.K, 1, 8, 2, 0.05, 16, self.nul),
-                      ctx.handle)
+                check(lib.isac_ul_pmi_select_batch_enqueue_dev(*self.ul_enq_args), ctx.handle)
                 ul_pending = True
         if ul_pending:                            # SRS occasion in the frame's last slot
-            check(lib.isac_ul_pmi_select_batch_finish(ctx.handle, self.ul_pmi.size // self.nul, ptr(self.ul_pmi), ptr(self.ul_sinr),
-                                                      C.byref(self.ul_n[0]), C.byref(self.ul_n[1]), ptr(self.ul_none)), ctx.handle)
+            check(lib.isac_ul_pmi_select_batch_finish(*self.ul_fin_args), ctx.handle)
 
     def d2h_bytes_per_step(self):
         return 4 * (self.RI.nbytes + self.i1.nbytes + self.i2.nbytes + self.cqi.nbytes) + 5 * (self.ul_pmi.nbytes + self.ul_sinr.nbytes)
