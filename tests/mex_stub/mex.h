@@ -1,7 +1,9 @@
-/* Minimal stand-in for MATLAB's mex.h (R2018a interleaved-complex API) -- DECLARATIONS ONLY.
- * MATLAB is not available in the build image, so the gateways under matlab/mex cannot be compiled into MEX files here;
- * tests/test_mex_sources_cpu.py runs `g++ -fsyntax-only` on each of them against this header and include/isac_b200.h so
- * that every call into the C ABI is at least type-checked.  Nothing links against this file. */
+/* Minimal stand-in for MATLAB's mex.h (R2018a interleaved-complex API).
+ * MATLAB is not available in the build image, so the gateways under matlab/mex cannot be compiled into MEX files here.
+ * tests/test_mex_sources_cpu.py type-checks each of them against this header and include/isac_b200.h, and
+ * tests/test_mex_mock_*.py build them together with mex_mock.cpp (a small functional implementation of these functions on a
+ * plain C struct) into shared objects, so that the gateways are linked against libisac_b200.so and EXECUTED end to end --
+ * on the CPU up to the "no CUDA device" error, on a B200 against the Python mirror's results. */
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -15,6 +17,9 @@ typedef struct { double real, imag; } mxComplexDouble;
 typedef enum { mxREAL = 0, mxCOMPLEX = 1 } mxComplexity;
 typedef enum { mxLOGICAL_CLASS = 3, mxDOUBLE_CLASS = 6, mxSINGLE_CLASS = 7, mxUINT8_CLASS = 9, mxINT32_CLASS = 12, mxUINT64_CLASS = 15 } mxClassID;
 
+#ifdef __cplusplus
+extern "C" {
+#endif
 bool mxIsSingle(const mxArray*);
 bool mxIsDouble(const mxArray*);
 bool mxIsComplex(const mxArray*);
@@ -47,3 +52,7 @@ double mxGetNaN(void);
 void mexErrMsgIdAndTxt(const char*, const char*, ...);
 int mexAtExit(void (*)(void));
 void mexLock(void);
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]);
+#ifdef __cplusplus
+}
+#endif

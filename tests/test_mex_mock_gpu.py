@@ -1,0 +1,168 @@
+"""The MEX gateways of matlab/mex EXECUTED on the GPU through a functional mock of MATLAB's mx/mex API (tests/mexmock.py):
+each gateway is fed the struct its .m shim builds and its outputs are compared with the Python mirror of the same
+reference function (which the parity tests check against the oracle).  This exercises the marshalling code itself --
+field names, dimension handling, 1-based indices, NaN conventions, device-buffer helpers -- which no MATLAB here can run."""
+import importlib
+
+import numpy as np
+import pytest
+
+import mexmock as M
+from oracle import chest as OCH  # noqa: F401  (test infrastructure import check only)
+from oracle import sensing as S
+
+PKG = "5g_based_system_level_integrated_sensing_and_communication_simulator_b200"
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P(gpu):
+    return importlib.import_module(PKG)
+
+
+def _doa_fields(rp):
+    ant = rp["antennaType"]
+    upa = ant["type"] == "upa"
+    return {"isUpa": float(upa), "nAnts": 0.0 if upa else float(ant["nV"] * ant["p"]), "nX": float(ant["nV"]) if upa else 0.0,
+            "nY": float(ant.get("nH", 0)) if upa else 0.0, "aGran": float(rp["azimuthScanGranularity"]),
+            "aMax": float(rp["azimuthScanScale"]), "eGran": float(rp["elevationScanGranularity"]),
+            "eMax": float(rp["elevationScanScale"])}
+
+
+def test_ul_pmi_gateway(P):
+    ph = P.communication.phyLayer
+    rng = np.random.default_rng(3)
+    K, R, Pn, nu, band = 24 * 12, 4, 4, 2, 4
+    hest = np.zeros((K, 1, R, Pn), np.complex64)
+    sc = np.arange(1, K, 4)
+    hest[sc, 0] = ((rng.standard_normal((sc.size, R, Pn)) + 1j * rng.standard_normal((sc.size, R, Pn))) / np.sqrt(2)).astype(np.complex64)
+    pmi, sinr, sb = M.call("isac_ul_pmi_mex", 3, float(nu), hest, 0.05, float(band))
+    rp, rs, rsb = ph.pmiSelect(nu, hest, 0.05, band)
+    assert np.array_equal(pmi.ravel(), np.asarray(rp).ravel(), equal_nan=True)
+    assert np.array_equal(sinr, rs, equal_nan=True) and np.array_equal(sb, rsb)
+    none = M.call("isac_ul_pmi_mex", 3, float(nu), np.zeros_like(hest), 0.05, float(band))   # no estimate -> scalar NaNs
+    assert all(x.shape == (1, 1) and np.isnan(x[0, 0]) for x in none)
+
+
+def test_prg_precode_gateway(P):
+    ph = P.communication.phyLayer
+    rng = np.random.default_rng(8)
+    nrb, L, nu, Pn, nprg = 24, 14, 2, 8, 6
+    K = 12 * nrb
+    pos = rng.choice(K * L, size=500, replace=False)
+    portind = np.stack([pos + 1 + K * L * j for j in range(nu)], axis=1).astype(np.int32)
+    portsym = (rng.standard_normal((500, nu)) + 1j * rng.standard_normal((500, nu))).astype(np.complex64)
+    F = (rng.standard_normal((nu, Pn, nprg)) + 1j * rng.standard_normal((nu, Pn, nprg))).astype(np.complex64)
+    sym, ind = M.call("isac_prg_precode_mex", 2, np.array([K, L, Pn], float), 0.0, portsym, portind, F)
+    rs, ri = ph.prgPrecode((K, L, Pn), 0, portsym, portind, F)
+    assert np.array_equal(sym, rs) and np.array_equal(ind, ri)
+
+
+def test_doa_gateway(P):
+    rng = np.random.default_rng(5)
+    n, N = 16, 2000
+    rp = {"antennaType": {"type": "ula", "nV": 8, "p": 2, "d": 0.5}, "azimuthScanScale": 360, "azimuthScanGranularity": 1,
+          "elevationScanScale": 180, "elevationScanGranularity": 1}
+    A = np.exp(-2j * np.pi * np.arange(n)[:, None] * 0.5 * S.sind(np.array([-35.0, 12.0, 48.0]))[None, :])
+    X = A @ (rng.standard_normal((3, N)) + 1j * rng.standard_normal((3, N))) + 0.3 * (rng.standard_normal((n, N)) + 1j * rng.standard_normal((n, N)))
+    Ra = X @ X.conj().T / N
+    for method, fn in ((0, "music"), (1, "mvdrBF"), (2, "digitalBF")):
+        L, azi, PdB = M.call("isac_doa_mex", 3, _doa_fields(rp), float(method), 3.0, Ra)
+        ref = getattr(P.sensing.estimation.doaEstimation, fn)(3, rp, Ra, return_spectrum=True)
+        azr, spec = (ref[1], ref[3]) if fn == "music" else (ref[0], ref[2])
+        assert int(L[0, 0]) == 3 and np.array_equal(azi.ravel(), azr) and np.array_equal(PdB.ravel(), np.asarray(spec).ravel())
+    L, azi, _ = M.call("isac_doa_mex", 3, _doa_fields(rp), 0.0, np.zeros((0, 0)), Ra)      # numDets = []: eigen-gap rule
+    Lr, azr, _ = P.sensing.estimation.doaEstimation.music(None, rp, Ra)
+    assert int(L[0, 0]) == Lr and np.array_equal(azi.ravel(), azr)
+    with pytest.raises(M.MexError) as e:                                                      # zero sources: findpeaks errors
+        M.call("isac_doa_mex", 3, _doa_fields(rp), 0.0, 0.0, Ra)
+    assert e.value.identifier == "isac:doa:status7"
+
+
+def test_fft2d_and_mono_static_gateways(P):
+    W = P.workloads
+    cell, car, wave = W.cell_config("tiny")
+    rp = P.sensing.radarParams(cell, car, wave)
+    cf = P.sensing.detection.cfar2D(rp)
+    grid, txw = W.sensing_tx("tiny", 1)
+    noise = W.std_normal_complex(txw.shape, 2).astype(np.complex64)
+    txw32, grid32 = txw.astype(np.complex64), grid.astype(np.complex64)
+    num = W.ofdm_numerology(int(car["NRBsDL"]), float(car["SubcarrierSpacing"]))
+    nT = int(rp["nTargets"])
+    ecfg = {"fc": float(rp["fc"]), "fs": float(rp["fs"]), "N0": float(rp["N0"]), "range": np.asarray(rp["range"], float).reshape(nT),
+            "velocity": np.asarray(rp["velocity"], float).reshape(nT),
+            "largeScaleFading": np.asarray(rp["largeScaleFading"], float).reshape(nT),
+            "steeringVec": np.asarray(rp["RxSteeringVec"], np.complex128).reshape(txw.shape[1], nT),
+            "los": np.asarray(cell["targetLoSConditions"], np.int32).reshape(nT), "nfft": float(num["Nfft"]),
+            "nSc": float(12 * int(car["NRBsDL"])), "nSymTx": float(grid.shape[1]),
+            "cpLengths": np.asarray(num["CyclicPrefixLengths"], np.int32)}
+    echo = M.call("isac_mono_static_mex", 1, ecfg, txw32, np.array([7], np.uint64), noise)
+    ref = P.sensing.monoStaticSensing(txw32, grid.shape, car, rp, cell["targetLoSConditions"], noise=noise)
+    assert echo.dtype == np.complex64 and echo.shape == ref.shape and np.array_equal(echo, ref)
+    fcfg = {"nIFFT": float(rp["nIFFT"]), "nFFT": float(rp["nFFT"]), "rRes": float(rp["rRes"]), "vRes": float(rp["vRes"]),
+            "cutRows": np.array([cf["CUTIdx"][0].min(), cf["CUTIdx"][0].max()], float).reshape(1, 2),
+            "cutCols": np.array([cf["CUTIdx"][1].min(), cf["CUTIdx"][1].max()], float).reshape(1, 2), "Pfa": float(rp["Pfa"])}
+    fcfg.update(_doa_fields(rp))
+    est = M.call("isac_fft2d_mex", 1, fcfg, echo, grid32)
+    r = P.sensing.estimation.fft2D(rp, cf, echo, grid32)
+    for k in ("rngEst", "velEst", "aziEst"):
+        assert np.array_equal(est[k].ravel(), r[k]), k
+    assert est["eleEst"].size == r["eleEst"].size and np.all(np.isnan(est["eleEst"]))
+
+
+def test_music2d_gateway(P):
+    rng = np.random.default_rng(21)
+    nSc, nSym, nA, scs, fc = 96, 40, 4, 30.0, 3.5e9
+    lam = S.LIGHTSPEED / fc
+    Tsri = 1 / (scs * 1e3) + 5e-6
+    rp = {"fc": fc, "Tsri": Tsri, "cfarEstZone": np.array([[50.0, 300.0], [-50.0, 50.0]]),
+          "antennaType": {"type": "ula", "nV": 2, "p": 2, "d": 0.5}, "azimuthScanScale": 360, "azimuthScanGranularity": 1,
+          "elevationScanScale": 180, "elevationScanGranularity": 1}
+    tx = np.exp(2j * np.pi * rng.random((nSc, nSym, nA)))
+    k, l = np.arange(nSc)[:, None], np.arange(nSym)[None, :]
+    H = sum(a * np.exp(-2j * np.pi * scs * 1e3 * 2 * r * k / S.LIGHTSPEED) * np.exp(2j * np.pi * Tsri * 2 * v * l / lam)
+            for r, v, a in ((120.0, 10.0, 1.0), (210.5, -22.5, 0.7)))
+    rx = np.stack([(H * np.exp(-2j * np.pi * a * 0.5 * S.sind(25.0))) * tx[:, :, a] for a in range(nA)], axis=2)
+    rx = (rx + 0.05 * (rng.standard_normal(rx.shape) + 1j * rng.standard_normal(rx.shape))).astype(np.complex64)
+    tx = tx.astype(np.complex64)
+    cfg = {"scsHz": scs * 1e3, "fc": fc, "Tsri": Tsri, "rMax": 300.0, "vZone": 50.0}
+    cfg.update(_doa_fields(rp))
+    est = M.call("isac_music2d_mex", 1, cfg, rx, tx)
+    ref = P.sensing.estimation.music2D(rp, {"scs": scs}, rx, tx)
+    for key in ("rngEst", "velEst", "aziEst", "PrmusicdB", "PvmusicdB"):
+        assert np.array_equal(est[key].ravel(), np.asarray(ref[key]).ravel()), key
+
+
+def test_dl_pmi_and_csi_report_gateways(P):
+    ph = P.communication.phyLayer
+    rng = np.random.default_rng(30)
+    nrb, R, Pn, sbs = 24, 4, 8, 4
+    K = 12 * nrb
+    H = ((rng.standard_normal((K, 14, R, Pn)) + 1j * rng.standard_normal((K, 14, R, Pn))) / np.sqrt(2)).astype(np.complex64)
+    H = (H + np.roll(H, 1, axis=0)).astype(np.complex64)
+    carrier = {"NSizeGrid": nrb, "NStartGrid": 0, "SymbolsPerSlot": 14}
+    csirs = {"NumCSIRSPorts": Pn, "NumRB": nrb, "RBOffset": 0, "SubcarrierLocations": 1, "SymbolLocations": 0, "Density": "one"}
+    rc = {"NSizeBWP": nrb, "NStartBWP": 0, "PanelDimensions": (2, 2), "CodebookMode": 1, "PMIMode": "Subband", "CQIMode": "Subband",
+          "SubbandSize": sbs}
+    pm, info = ph.dlPMISelect(carrier, csirs, rc, 2, H, 0.1)
+    cfg = {"nPorts": float(Pn), "N1": 2.0, "N2": 2.0, "O1": 4.0, "O2": 4.0, "codebookMode": 1.0, "nSizeBWP": float(nrb),
+           "nStartBWP": 0.0, "subbandSize": float(sbs), "pmiSubband": 1.0, "cqiSubband": 1.0, "K": float(K), "L": 14.0,
+           "subsetRestriction": np.ones(64, np.uint8), "i2Restriction": np.ones(16, np.uint8), "riRestriction": np.ones(8, np.uint8),
+           "reK": info["reK"].astype(np.int32), "reL": info["reL"].astype(np.int32)}
+    i1, i2, S_re, S_sb, Wm, reK, reL = M.call("isac_dl_pmi_mex", 7, cfg, 2.0, H, 0.1)
+    assert np.array_equal(i1.ravel(), pm["i1"]) and np.array_equal(i2.ravel(), pm["i2"], equal_nan=True)
+    assert S_re.shape == info["SINRPerRE"].shape and np.array_equal(S_re, info["SINRPerRE"], equal_nan=True)
+    assert np.array_equal(S_sb, info["SINRPerSubband"], equal_nan=True)
+    assert np.array_equal(Wm, info["W"]) and np.array_equal(reK.ravel(), info["reK"]) and np.array_equal(reL.ravel(), info["reL"])
+    table = np.asarray(P.communication.setupSINRtoCQIMappingTable()["downlinkSINR90pc"], float)
+    rk, pmr, cq = ph.csiReport(carrier, csirs, rc, H, 0.1, table, rankCap=4)
+    RI, i1, i2, CQI = M.call("isac_csi_report_mex", 4, cfg, H, 0.1, table, 4.0, 0.0)         # mode 0: fused report
+    assert RI[0, 0] == rk and np.array_equal(i1.ravel(), pmr["i1"]) and np.array_equal(i2.ravel(), pmr["i2"], equal_nan=True)
+    assert np.array_equal(CQI, cq, equal_nan=True)
+    ri_ref, pm_ri = ph.riSelect(carrier, csirs, rc, H, 0.1)
+    RI, i1, i2, _ = M.call("isac_csi_report_mex", 4, cfg, H, 0.1, table, 0.0, 1.0)           # mode 1: riSelect
+    assert RI[0, 0] == ri_ref and np.array_equal(i1.ravel(), pm_ri["i1"]) and np.array_equal(i2.ravel(), pm_ri["i2"], equal_nan=True)
+    cq_ref, pm_cq, _ = ph.cqiSelect(carrier, csirs, rc, 3, H, 0.1, table)
+    _, i1, i2, CQI = M.call("isac_csi_report_mex", 4, cfg, H, 0.1, table, 0.0, 2.0, 3.0)     # mode 2: cqiSelect at rank 3
+    assert np.array_equal(i1.ravel(), pm_cq["i1"]) and np.array_equal(i2.ravel(), pm_cq["i2"], equal_nan=True)
+    assert np.array_equal(CQI[:, : cq_ref.shape[1]], cq_ref, equal_nan=True)
