@@ -8,7 +8,6 @@ import numpy as np
 import pytest
 
 import mexmock as M
-from oracle import chest as OCH  # noqa: F401  (test infrastructure import check only)
 from oracle import sensing as S
 
 PKG = "5g_based_system_level_integrated_sensing_and_communication_simulator_b200"
