@@ -114,7 +114,8 @@ def build_cell_inputs(W, seed):
 class CommWorkload:
     """COMM share of one cfg2 cell-frame (20 slots @30 kHz, 8 UEs, 8x8, 273 PRB, CDL-C):
     4 CSI-RS occasions (period 5 slots, setupCSIRS.m:11) x 8 UEs: CDL channel matrix + fused RI/PMI/CQI report;
-    20 SRS occasions (period 8 slots, setupSRS.m:13; 2.5 per UE per frame): UL CDL + TPMI selection;
+    20 SRS occasions (period 8 slots, setupSRS.m:13; 2.5 per UE per frame): UL CDL + TPMI selection over the full band
+    (the reference hands pmiSelect the interpolated estimate of the SRS symbol, gNBPhy.m:1030-1035);
     12 DL slots: PRG precoding of a full-band 2-layer PDSCH (12 symbols) and its DM-RS."""
 
     N_UE, NRB, SCS = 8, 273, 30e3
@@ -151,9 +152,6 @@ class CommWorkload:
         self.H = torch.empty((self.nb, 8, 8, 14, K), dtype=torch.complex64, device=dev)       # [cell*ue][P][R][L][K]
         self.nul = cells * 4                                                # 4 UEs share an SRS slot (setupSRS.m:13)
         self.hest = torch.empty((self.nul, 2, 8, 1, K), dtype=torch.complex64, device=dev)    # [cell*ue][P][R][1][K]
-        comb = torch.zeros(K, dtype=torch.complex64, device=dev)
-        comb[1::4] = 1.0
-        self.comb = comb
         self.nvar = np.full(self.nb, 10 ** (-15 / 10))
         nSB = (self.NRB + 15) // 16
         self.RI = np.zeros(self.nb)
@@ -232,7 +230,8 @@ class CommWorkload:
             if slot in srs:                       # SRS occasion: UL channel of the 4 UEs of the group + TPMI selection
                 self.t0_ul[:] = frame_t0 + slot * self.slot_t
                 check(lib.isac_cdl_generate_batch_dev(*self.cdl_ul_args[srs[slot]]), ctx.handle)
-                self.hest.mul_(self.comb)                                   # comb-4 SRS REs only (setupSRS.m:11-18)
+                # pmiSelect sees the INTERPOLATED estimate of the SRS symbol, i.e. every subcarrier of the band
+                # (Hest(:,srsSymbols,:,:) out of nrChannelEstimate, gNBPhy.m:1030-1035), not only the comb-4 REs
                 check(lib.isac_ul_pmi_select_batch_enqueue_dev(*self.ul_enq_args), ctx.handle)
                 ul_pending = True
         if ul_pending:                            # SRS occasion in the frame's last slot
@@ -523,9 +522,7 @@ def _oracle_comm_sample(seed, n_reports=2):
     for i in range(max(1, round(n_reports * 20 / 32))):
         rays = OCd.build_rays(2, 300e-9, 5.0, (1, 1, 2), (1, 4, 2), True, False, seed * 100 + 50 + i)
         h = OCd.frequency_response(rays, K, 30e3, t_sym[13:14])
-        mask = np.zeros(K)
-        mask[1::4] = 1
-        OCm.pmi_select(2, h * mask[:, None, None, None], 0.05, 16)
+        OCm.pmi_select(2, h, 0.05, 16)                      # full band, as on the GPU leg
     return time.time() - t0
 
 
