@@ -15,6 +15,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _library_built():
+    """The tests bind the in-tree libisac_b200.so: build it (nvcc cross-compiles without a GPU) when a fresh checkout has none."""
+    build = importlib.import_module(PKG_NAME + ".build")
+    if not os.path.exists(build.LIB_PATH):
+        build.build_library(verbose=False)
+    assert os.path.exists(build.LIB_PATH)
+
+
 @pytest.fixture(scope="session")
 def pkg():
     return importlib.import_module(PKG_NAME)
