@@ -140,6 +140,7 @@ def _declare(lib):
                               P(i32)], C.c_int),
         "isac_antenna_covariance_dev": ([vp, vp, C.c_int64, i32, vp], C.c_int),
         "isac_type1sp_codebook": ([P(CsiConfig), i32, i32, P(i32), vp], C.c_int),
+        "isac_type1mp_codebook": ([P(CsiConfig), i32, i32, P(i32), vp], C.c_int),
         "isac_pusch_codebook": ([i32, i32, P(i32), vp], C.c_int),
         "isac_pmi_plan_create": ([vp, P(CsiConfig), i32, i32, P(vp)], C.c_int),
         "isac_pmi_plan_destroy": ([vp], C.c_int),

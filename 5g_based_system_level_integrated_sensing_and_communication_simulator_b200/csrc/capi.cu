@@ -775,6 +775,18 @@ int isac_type1sp_codebook(const isac_csi_config* cfg, int32_t nLayers, int32_t v
     return ISAC_OK;
 }
 
+int isac_type1mp_codebook(const isac_csi_config* cfg, int32_t nPanels, int32_t nLayers, int32_t dims[9], double* W) {
+    if (!cfg || !dims) return ISAC_ERR_INVALID_ARG;
+    CsiConfig c = to_csi_config(cfg);
+    int d[9];
+    std::vector<std::complex<double>> w;
+    const int st = type1mp_codebook(nullptr, c, nPanels, nLayers, d, W ? &w : nullptr);
+    if (st) return st;
+    for (int i = 0; i < 9; ++i) dims[i] = d[i];
+    if (W) std::memcpy(W, w.data(), sizeof(std::complex<double>) * w.size());
+    return ISAC_OK;
+}
+
 int isac_pusch_codebook(int32_t nLayers, int32_t nPorts, int32_t* nTPMI, double* W) {
     if (!nTPMI) return ISAC_ERR_INVALID_ARG;
     CodebookTable t;

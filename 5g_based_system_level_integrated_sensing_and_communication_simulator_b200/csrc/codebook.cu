@@ -393,6 +393,95 @@ int build_pusch_table(Ctx* ctx, int nu, int P, CodebookTable& t) {
     return kOk;
 }
 
+// getPMIType1MultiPanelCodebook (dlPMISelect.m:1351-1772; TS 38.214 Tables 5.2.2.2.2-1..-6) as the explicit array the
+// reference returns: W [P x nu x i20 x i21 x i22 x i11 x i12 x i13 x i141 x i142 x i143], restricted precoders all zero.
+// Every column is a "+" column  [c_g v ;  c_g phi_n v]_g  or a "-" column  [c_g v ; -c_g phi_n v]_g  over the Ng panels g,
+// with c_0 = 1 and c_g = phi(i14g) in codebook mode 1; mode 2 (Ng = 2): panel 1 carries a(i141) b(i21) v on the first and
+// +-a(i142) b(i22) v on the second polarisation.  Layers: [+v], [+v, -v'], [+v, +v', -v], [+v, +v', -v, -v'] with
+// v' = v_{l+k1, m+k2} (k tables :1518-1536 for two layers, :1615-1636 for three and four).  Pure host code.
+int type1mp_codebook(Ctx* ctx, const CsiConfig& c, int Ng, int nu, int dims[9], std::vector<cd>* W) {
+    const int N1 = c.N1, N2 = c.N2, O1 = c.O1, O2 = c.O2, mode = c.codebookMode;
+    if ((Ng != 2 && Ng != 4) || (mode != 1 && mode != 2) || (mode == 2 && Ng != 2) || nu < 1 || nu > 4 || N1 < 1 || N2 < 1) {
+        set_error(ctx, "nr5g:dlPMISelect:InvalidPanelDimensions");
+        return kErrInvalidArg;
+    }
+    const int P = 2 * Ng * N1 * N2, Pb = N1 * N2;
+    const int n11 = N1 * O1, n12 = N2 * O2, n141 = 4;
+    const int n142 = mode == 1 ? (Ng == 2 ? 1 : 4) : 4, n143 = mode == 1 ? (Ng == 2 ? 1 : 4) : 1;
+    const int n21 = mode == 1 ? 1 : 2, n22 = n21;
+    std::vector<int> k1, k2;
+    int n20 = 2;
+    if (nu == 1) { n20 = 4; k1 = {0}; k2 = {0}; }
+    else if (nu == 2) {
+        if (N1 > N2 && N2 > 1) { k1 = {0, O1, 0, 2 * O1}; k2 = {0, 0, O2, 0}; }
+        else if (N1 == N2) { k1 = {0, O1, 0, O1}; k2 = {0, 0, O2, O2}; }
+        else if (N1 == 2 && N2 == 1) { k1 = {0, O1}; k2 = {0, 0}; }
+        else { k1 = {0, O1, 2 * O1, 3 * O1}; k2 = {0, 0, 0, 0}; }
+    } else {
+        if (N1 == 2 && N2 == 1) { k1 = {O1}; k2 = {0}; }
+        else if (N1 == 4 && N2 == 1) { k1 = {O1, 2 * O1, 3 * O1}; k2 = {0, 0, 0}; }
+        else if (N1 == 8 && N2 == 1) { k1 = {O1, 2 * O1, 3 * O1, 4 * O1}; k2 = {0, 0, 0, 0}; }
+        else if (N1 == 2 && N2 == 2) { k1 = {O1, 0, O1}; k2 = {0, O2, O2}; }
+        else if (N1 == 4 && N2 == 2) { k1 = {O1, 0, O1, 2 * O1}; k2 = {0, O2, O2, 0}; }
+        else { set_error(ctx, "nr5g:dlPMISelect:InvalidPanelDimensions"); return kErrInvalidArg; }
+    }
+    const int n13 = (int)k1.size();
+    const int d[9] = {n20, n21, n22, n11, n12, n13, n141, n142, n143};
+    for (int i = 0; i < 9; ++i) dims[i] = d[i];
+    if (!W) return kOk;
+    size_t nCand = 1;
+    for (int i = 0; i < 9; ++i) nCand *= (size_t)d[i];
+    W->assign((size_t)P * nu * nCand, cd(0, 0));
+    const double s = 1.0 / std::sqrt((double)nu * P);
+    const cd A0(std::sqrt(0.5), std::sqrt(0.5)), B0(std::sqrt(0.5), -std::sqrt(0.5));   // a(x) = A0 phi(x), b(x) = B0 phi(x)
+    auto vlm = [&](int l, int m, std::vector<cd>& v) {   // getVlm: N2 fastest
+        v.resize(Pb);
+        for (int a1 = 0; a1 < N1; ++a1)
+            for (int a2 = 0; a2 < N2; ++a2) {
+                const double ang = 2.0 * M_PI * ((double)l * a1 / (O1 * N1) + (double)m * a2 / (O2 * N2));
+                v[a1 * N2 + a2] = cd(std::cos(ang), std::sin(ang));
+            }
+    };
+    std::vector<cd> v, vp;
+    size_t ci = 0;   // MATLAB linear order over [i20 i21 i22 i11 i12 i13 i141 i142 i143]: walk it with nested loops, last index outermost
+    for (int i143 = 0; i143 < n143; ++i143)
+     for (int i142 = 0; i142 < n142; ++i142)
+      for (int i141 = 0; i141 < n141; ++i141)
+       for (int i13 = 0; i13 < n13; ++i13)
+        for (int i12 = 0; i12 < n12; ++i12)
+         for (int i11 = 0; i11 < n11; ++i11) {
+            const int bit = N2 * O2 * i11 + i12;
+            const bool restricted = c.subsetRestriction && bit < n11 * n12 && !c.subsetRestriction[bit];
+            if (!restricted) { vlm(i11, i12, v); vlm(i11 + k1[i13], i12 + k2[i13], vp); }
+            for (int i22 = 0; i22 < n22; ++i22)
+             for (int i21 = 0; i21 < n21; ++i21)
+              for (int i20 = 0; i20 < n20; ++i20, ++ci) {
+                if (restricted) continue;
+                const cd fn = phi(i20);
+                cd first[4], second[4];   // per panel: coefficient of the first / second polarisation block of a "+" column
+                if (mode == 1) {
+                    const cd cg[4] = {cd(1, 0), phi(i141), phi(i142), phi(i143)};
+                    for (int g = 0; g < Ng; ++g) { first[g] = cg[g]; second[g] = cg[g] * fn; }
+                } else {
+                    first[0] = cd(1, 0); second[0] = fn;
+                    first[1] = A0 * phi(i141) * B0 * phi(i21); second[1] = A0 * phi(i142) * B0 * phi(i22);
+                }
+                for (int j = 0; j < nu; ++j) {
+                    const bool prime = (nu == 2 && j == 1) || (nu >= 3 && (j == 1 || j == 3));
+                    const bool minus = (nu == 2 && j == 1) || (nu >= 3 && j >= 2);
+                    const std::vector<cd>& x = prime ? vp : v;
+                    cd* col = W->data() + ((size_t)ci * nu + j) * P;
+                    for (int g = 0; g < Ng; ++g)
+                        for (int q = 0; q < Pb; ++q) {
+                            col[(2 * g) * Pb + q] = s * first[g] * x[q];
+                            col[(2 * g + 1) * Pb + q] = (minus ? -s : s) * second[g] * x[q];
+                        }
+                }
+              }
+         }
+    return kOk;
+}
+
 void materialize_codebook(const CodebookTable& t, std::vector<cd>& W) {
     const int nc = t.nCand();
     W.assign((size_t)t.P * t.nLayers * nc, cd(0, 0));

@@ -52,6 +52,9 @@ enum CodebookVariant { kVariantUE = 0, kVariantGNB = 1 };
 
 // getPMIType1SinglePanelCodebook (dlPMISelect.m:853-1349) / pmiType1SinglePanelCodebook.m:46-554
 int build_type1sp_table(Ctx* ctx, const CsiConfig& c, int nLayers, int variant, CodebookTable& t);
+// getPMIType1MultiPanelCodebook (dlPMISelect.m:1351-1772): dims = [i20 i21 i22 i11 i12 i13 i141 i142 i143] lengths, W (may be
+// nullptr) = explicit [P x nLayers x prod(dims)] array, column-major, restricted precoders zero
+int type1mp_codebook(Ctx* ctx, const CsiConfig& c, int nPanels, int nLayers, int dims[9], std::vector<std::complex<double>>* W);
 // nrPUSCHCodebook(nlayers,nports,tpmi).' for tpmi = 0..maxTPMI as an explicit table (pmiSelect.m:45)
 int build_pusch_table(Ctx* ctx, int nLayers, int nPorts, CodebookTable& t);
 // W[P x nLayers x nCand] complex128, column-major (restricted candidates all zero)

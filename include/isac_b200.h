@@ -268,6 +268,12 @@ typedef struct {
  * including that copy's deviations).  dims = [i2 i11 i12 i13] lengths; W complex128 [P x nLayers x prod(dims)]
  * (NULL to query dims).  Pure host code: works without a GPU. */
 int isac_type1sp_codebook(const isac_csi_config* cfg, int32_t nLayers, int32_t variant, int32_t dims[4], double* W);
+/* Wmp = getPMIType1MultiPanelCodebook(reportConfig,nLayers) (dlPMISelect.m:1351; TS 38.214 Tables 5.2.2.2.2-1..-6) for
+ * PanelDimensions = [nPanels N1 N2] (nPanels = Ng in {2,4}; codebook mode 2 only with Ng = 2; nLayers <= 4).
+ * dims = [i20 i21 i22 i11 i12 i13 i141 i142 i143] lengths; W complex128 [P x nLayers x prod(dims)] with P = 2*Ng*N1*N2
+ * (NULL to query dims).  Uses cfg->N1, N2, O1, O2, codebookMode, subsetRestriction.  Pure host code.  The PMI / RI / CQI
+ * selection entry points below cover Type1SinglePanel only (the shipped configuration never sets CodebookType). */
+int isac_type1mp_codebook(const isac_csi_config* cfg, int32_t nPanels, int32_t nLayers, int32_t dims[9], double* W);
 /* nrPUSCHCodebook(nlayers,nports,tpmi).' for tpmi = 0..maxTPMI (pmiSelect.m:45; TS 38.211 Tables 6.3.1.5-1..7);
  * W complex128 [nPorts x nLayers x nTPMI] (NULL to query nTPMI). */
 int isac_pusch_codebook(int32_t nLayers, int32_t nPorts, int32_t* nTPMI, double* W);

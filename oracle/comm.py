@@ -315,6 +315,79 @@ def type1_single_panel_codebook(cfg, n_layers, variant="ue"):
 # ----------------------------------------------------------------------------------------------
 # SINR
 # ----------------------------------------------------------------------------------------------
+def type1_multi_panel_codebook(cfg, n_panels, n_layers):
+    """getPMIType1MultiPanelCodebook (dlPMISelect.m:1351-1772): TS 38.214 Tables 5.2.2.2.2-1..-6, written out table by
+    table like the reference.  ``cfg``: N1, N2, O1, O2, CodebookMode, CodebookSubsetRestriction, i2Restriction;
+    ``n_panels`` = Ng in {2, 4} (mode 2 only with Ng = 2).
+    -> W [P, nLayers, i20, i21, i22, i11, i12, i13, i141, i142, i143] complex128, restricted precoders all zero."""
+    Ng, N1, N2, O1, O2 = int(n_panels), cfg["N1"], cfg["N2"], cfg["O1"], cfg["O2"]
+    mode = cfg["CodebookMode"]
+    if Ng not in (2, 4) or (mode == 2 and Ng != 2) or not 1 <= n_layers <= 4:
+        raise ValueError("nr5g:dlPMISelect:InvalidPanelDimensions")
+    P = 2 * Ng * N1 * N2                                                       # :1385
+    phi = lambda x: np.exp(1j * np.pi * x / 2)                                 # :1390-1392
+    a = lambda x: np.exp(1j * np.pi / 4 + 1j * np.pi * x / 2)
+    b = lambda x: np.exp(-1j * np.pi / 4 + 1j * np.pi * x / 2)
+    n11, n12, n141 = N1 * O1, N2 * O2, 4                                       # :1396-1400
+    if mode == 1:                                                              # :1405-1419
+        n142, n143 = (1, 1) if Ng == 2 else (4, 4)
+        n21 = n22 = 1
+    else:
+        n142, n143, n21, n22 = 4, 1, 2, 2
+    if n_layers == 1:                                                          # :1424-1426
+        n13, n20, k1, k2 = 1, 4, [0], [0]
+    elif n_layers == 2:                                                        # :1518-1536 (Table 5.2.2.2.1-3)
+        n20 = 2
+        if N1 > N2 and N2 > 1:
+            k1, k2 = [0, O1, 0, 2 * O1], [0, 0, O2, 0]
+        elif N1 == N2:
+            k1, k2 = [0, O1, 0, O1], [0, 0, O2, O2]
+        elif N1 == 2 and N2 == 1:
+            k1, k2 = [0, O1], [0, 0]
+        else:
+            k1, k2 = [0, O1, 2 * O1, 3 * O1], [0, 0, 0, 0]
+        n13 = len(k1)
+    else:                                                                      # :1615-1636 (Table 5.2.2.2.2-2)
+        n20 = 2
+        tab = {(2, 1): ([O1], [0]), (4, 1): ([O1, 2 * O1, 3 * O1], [0, 0, 0]), (8, 1): ([O1, 2 * O1, 3 * O1, 4 * O1], [0] * 4),
+               (2, 2): ([O1, 0, O1], [0, O2, O2]), (4, 2): ([O1, 0, O1, 2 * O1], [0, O2, O2, 0])}
+        if (N1, N2) not in tab:
+            raise ValueError("nr5g:dlPMISelect:InvalidPanelDimensions")
+        k1, k2 = tab[(N1, N2)]
+        n13 = len(k1)
+    W = np.zeros((P, n_layers, n20, n21, n22, n11, n12, n13, n141, n142, n143), dtype=np.complex128)
+    csr = cfg.get("CodebookSubsetRestriction", np.ones(n11 * n12))
+    i2r = cfg.get("i2Restriction", np.ones(16))
+    for i11 in range(n11):
+        for i12 in range(n12):
+            for i13 in range(n13):
+                if _restricted(csr, N2 * O2 * i11 + i12, None, i2r)[0]:      # only v_lm restriction applies (:1434, :1546)
+                    continue
+                v = _vlm(N1, N2, O1, O2, i11, i12)
+                vp = _vlm(N1, N2, O1, O2, i11 + k1[i13], i12 + k2[i13])
+                for i141 in range(n141):
+                    for i142 in range(n142):
+                        for i143 in range(n143):
+                            for i20 in range(n20):
+                                for i21 in range(n21):
+                                    for i22 in range(n22):
+                                        if mode == 1:
+                                            fn = phi(i20)
+                                            cp = [1.0, phi(i141)] if Ng == 2 else [1.0, phi(i141), phi(i142), phi(i143)]
+                                            plus = lambda x: np.concatenate([np.concatenate([c * x, c * fn * x]) for c in cp])
+                                            minus = lambda x: np.concatenate([np.concatenate([c * x, -c * fn * x]) for c in cp])
+                                        else:                                   # Ng = 2, mode 2 (:1489-1508 etc.)
+                                            fn = phi(i20)
+                                            c1, c2 = a(i141) * b(i21), a(i142) * b(i22)
+                                            plus = lambda x: np.concatenate([x, fn * x, c1 * x, c2 * x])
+                                            minus = lambda x: np.concatenate([x, -fn * x, c1 * x, -c2 * x])
+                                        cols = {1: [plus(v)], 2: [plus(v), minus(vp)], 3: [plus(v), plus(vp), minus(v)],
+                                                4: [plus(v), plus(vp), minus(v), minus(vp)]}[n_layers]
+                                        W[:, :, i20, i21, i22, i11, i12, i13, i141, i142, i143] = (
+                                            np.stack(cols, axis=1) / np.sqrt(n_layers * P))
+    return W
+
+
 def precoded_sinr_dl(H, n_var, W):
     """getPrecodedSINR (dlPMISelect.m:1825-1834): per-layer LMMSE SINR."""
     nu = W.shape[1]

@@ -94,3 +94,68 @@ def test_matlab_round4_and_subbands():
     assert C.subband_info("Subband", 3, 50, 8) == (7, [5, 8, 8, 8, 8, 8, 5])
     assert C.subband_info("Wideband", 0, 52, 4) == (1, [52])
     assert C.subband_info("Subband", 0, 20, 4) == (1, [20])
+
+
+# ---- Type-I multi-panel codebooks (dlPMISelect.m:1351-1772) ---------------------------------------------------------------
+_MP_CASES = [((2, 2, 1), 1, 1), ((2, 2, 1), 1, 2), ((2, 2, 1), 2, 1), ((2, 2, 1), 2, 3), ((2, 4, 1), 1, 4), ((2, 2, 2), 2, 2),
+             ((4, 2, 1), 1, 1), ((4, 2, 1), 1, 3), ((4, 2, 2), 1, 2), ((2, 4, 2), 2, 4), ((2, 8, 1), 1, 3)]
+
+
+@pytest.mark.parametrize("panel,mode,nu", _MP_CASES)
+def test_multi_panel_codebook_host_builder_equals_oracle(panel, mode, nu):
+    import importlib
+    com = importlib.import_module(PKG + ".communication")
+    Ng, N1, N2 = panel
+    O1, O2 = com._MP_PANELS[panel]
+    rng = np.random.default_rng(sum(panel) + 10 * mode + nu)
+    csr = (rng.random(N1 * O1 * N2 * O2) > 0.15).astype(int)
+    csr[rng.integers(csr.size)] = 0                    # at least one restricted beam
+    csr[(np.flatnonzero(csr == 0)[0] + 1) % csr.size] = 1   # and at least one allowed
+    W = com.pmiType1MultiPanelCodebook({"PanelDimensions": panel, "CodebookMode": mode, "CodebookSubsetRestriction": csr}, nu)
+    Wo = C.type1_multi_panel_codebook({"N1": N1, "N2": N2, "O1": O1, "O2": O2, "CodebookMode": mode,
+                                        "CodebookSubsetRestriction": csr}, Ng, nu)
+    assert W.shape == Wo.shape
+    assert np.abs(W - Wo).max() <= 1e-14
+    # restricted precoders are all zero, every other one has orthogonal columns of power 1/nu
+    G = np.einsum("pa...,pb...->ab...", W.conj(), W)
+    live = np.abs(W).sum(axis=(0, 1)) > 0
+    assert live.any() and (~live).any()
+    for a in range(nu):
+        for b in range(nu):
+            assert np.allclose(G[a, b][live], 1.0 / nu if a == b else 0.0, atol=1e-13)
+
+
+def test_multi_panel_codebook_known_matrices():
+    """The written-out matrices of the reference for single index sets (dlPMISelect.m:1447-1470, :1590-1607, :1680-1700)."""
+    phi = lambda x: np.exp(1j * np.pi * x / 2)
+    a = lambda x: np.exp(1j * np.pi / 4 + 1j * np.pi * x / 2)
+    b = lambda x: np.exp(-1j * np.pi / 4 + 1j * np.pi * x / 2)
+    # Ng = 2, mode 1, two layers (Table 5.2.2.2.2-4)
+    cfg = {"N1": 2, "N2": 2, "O1": 4, "O2": 4, "CodebookMode": 1}
+    W = C.type1_multi_panel_codebook(cfg, 2, 2)
+    i20, i11, i12, i13, i141 = 1, 5, 3, 3, 2
+    v, vp = C._vlm(2, 2, 4, 4, i11, i12), C._vlm(2, 2, 4, 4, i11 + 4, i12 + 4)      # N1 == N2: k1 = [0 O1 0 O1], k2 = [0 0 O2 O2]
+    fn, fp = phi(i20), phi(i141)
+    ref = np.block([[v[:, None], vp[:, None]], [fn * v[:, None], -fn * vp[:, None]], [fp * v[:, None], fp * vp[:, None]],
+                    [fn * fp * v[:, None], -fn * fp * vp[:, None]]]) / np.sqrt(2 * 16)
+    assert np.abs(W[:, :, i20, 0, 0, i11, i12, i13, i141, 0, 0] - ref).max() <= 1e-15
+    # Ng = 4, mode 1, one layer (Table 5.2.2.2.2-3)
+    cfg = {"N1": 2, "N2": 1, "O1": 4, "O2": 1, "CodebookMode": 1}
+    W = C.type1_multi_panel_codebook(cfg, 4, 1)
+    i20, i11, p1, p2, p3 = 3, 6, 1, 2, 3
+    v = C._vlm(2, 1, 4, 1, i11, 0)
+    fn = phi(i20)
+    ref = np.concatenate([v, fn * v, phi(p1) * v, fn * phi(p1) * v, phi(p2) * v, fn * phi(p2) * v, phi(p3) * v, fn * phi(p3) * v]) / 4.0
+    assert np.abs(W[:, 0, i20, 0, 0, i11, 0, 0, p1, p2, p3] - ref).max() <= 1e-15
+    # Ng = 2, mode 2, three layers (Table 5.2.2.2.2-5)
+    cfg = {"N1": 4, "N2": 1, "O1": 4, "O2": 1, "CodebookMode": 2}
+    W = C.type1_multi_panel_codebook(cfg, 2, 3)
+    i20, i21, i22, i11, i13, p1, p2 = 1, 1, 0, 9, 2, 3, 1
+    v, vp = C._vlm(4, 1, 4, 1, i11, 0), C._vlm(4, 1, 4, 1, i11 + 3 * 4, 0)          # (N1,N2) = (4,1): k1 = O1*(1:3)
+    fn, c1, c2 = phi(i20), a(p1) * b(i21), a(p2) * b(i22)
+    col = lambda x, s: np.concatenate([x, s * fn * x, c1 * x, s * c2 * x])
+    ref = np.stack([col(v, 1), col(vp, 1), col(v, -1)], axis=1) / np.sqrt(3 * 16)
+    assert np.abs(W[:, :, i20, i21, i22, i11, 0, i13, p1, p2, 0] - ref).max() <= 1e-15
+    assert W.shape == (16, 3, 2, 2, 2, 16, 1, 3, 4, 4, 1)
+    with pytest.raises(ValueError):
+        C.type1_multi_panel_codebook(cfg, 4, 1)        # mode 2 exists for two panels only
