@@ -76,7 +76,7 @@ class CsiConfig(C.Structure):
         ("codebookMode", C.c_int32), ("nSizeBWP", C.c_int32), ("nStartBWP", C.c_int32), ("subbandSize", C.c_int32),
         ("pmiSubband", C.c_int32), ("cqiSubband", C.c_int32), ("K", C.c_int32), ("L", C.c_int32), ("nRx", C.c_int32),
         ("subsetRestriction", C.c_void_p), ("i2Restriction", C.c_void_p), ("riRestriction", C.c_uint8 * 8),
-        ("nRE", C.c_int32), ("reK", C.c_void_p), ("reL", C.c_void_p),
+        ("nRE", C.c_int32), ("reK", C.c_void_p), ("reL", C.c_void_p), ("nPanels", C.c_int32),
     ]
 
 
@@ -141,12 +141,14 @@ def _declare(lib):
         "isac_antenna_covariance_dev": ([vp, vp, C.c_int64, i32, vp], C.c_int),
         "isac_type1sp_codebook": ([P(CsiConfig), i32, i32, P(i32), vp], C.c_int),
         "isac_type1mp_codebook": ([P(CsiConfig), i32, i32, P(i32), vp], C.c_int),
+        "isac_type1mp_codebook_from_table": ([P(CsiConfig), i32, i32, P(i32), vp], C.c_int),
         "isac_pusch_codebook": ([i32, i32, P(i32), vp], C.c_int),
         "isac_pmi_plan_create": ([vp, P(CsiConfig), i32, i32, P(vp)], C.c_int),
         "isac_pmi_plan_destroy": ([vp], C.c_int),
         "isac_precoded_sinr_host": ([vp, vp, i32, i32, f64, vp, i32, i32, vp], C.c_int),
         "isac_pmi_plan_set_kernel": ([vp, i32], C.c_int),
         "isac_csi_plan_set_kernel": ([vp, i32], C.c_int),
+        "isac_pmi_plan_mp_dims": ([vp, P(i32)], C.c_int),
         "isac_pmi_plan_info": ([vp, P(i32), P(i32), P(i32), P(i32), vp, vp], C.c_int),
         "isac_dl_pmi_select_dev": ([vp, vp, vp, i32], C.c_int),
         "isac_dl_pmi_collect": ([vp, i32, vp, vp, vp], C.c_int),

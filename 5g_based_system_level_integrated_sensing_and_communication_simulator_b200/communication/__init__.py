@@ -18,17 +18,16 @@ def pmiType1SinglePanelCodebook(reportConfig, nLayers):
     return phyLayer._codebook(reportConfig, nLayers, variant=1)
 
 
-# TS 38.214 Table 5.2.2.2.2-1: (Ng, N1, N2) -> (O1, O2)   (dlPMISelect.m:629-644)
-_MP_PANELS = {(2, 2, 1): (4, 1), (2, 4, 1): (4, 1), (4, 2, 1): (4, 1), (2, 2, 2): (4, 4), (2, 8, 1): (4, 1), (4, 4, 1): (4, 1),
-              (2, 4, 2): (4, 4), (4, 2, 2): (4, 4)}
+_MP_PANELS = phyLayer._MP_PANELS   # TS 38.214 Table 5.2.2.2.2-1: (Ng, N1, N2) -> (O1, O2)   (dlPMISelect.m:629-644)
 
 
-def pmiType1MultiPanelCodebook(reportConfig, nLayers):
+def pmiType1MultiPanelCodebook(reportConfig, nLayers, from_table=False):
     """``Wmp = getPMIType1MultiPanelCodebook(reportConfig,nLayers)`` (reference +communication/+phyLayer/dlPMISelect.m:1351-1772,
     TS 38.214 Tables 5.2.2.2.2-1..-6).  ``reportConfig``: PanelDimensions = (Ng, N1, N2), CodebookMode (2 only with Ng = 2),
     optional OverSamplingFactors and CodebookSubsetRestriction (N1*O1*N2*O2 bits).
     Returns Wmp[P, nLayers, i20, i21, i22, i11, i12, i13, i141, i142, i143] complex128 (host code, isac_type1mp_codebook).
-    The PMI / RI / CQI selection functions cover Type1SinglePanel only."""
+    ``from_table`` materialises the array from the beam / co-phasing table the SINR kernels read instead (consistency check).
+    Selection over it: ``communication.phyLayer.dlPMISelect`` with a three-element PanelDimensions."""
     import ctypes as C
     Ng, N1, N2 = (int(x) for x in reportConfig["PanelDimensions"])
     if (Ng, N1, N2) not in _MP_PANELS:
@@ -42,12 +41,13 @@ def pmiType1MultiPanelCodebook(reportConfig, nLayers):
                          codebookMode=int(reportConfig.get("CodebookMode", 1)),
                          subsetRestriction=csr.ctypes.data if csr is not None else None)
     lib = _lib.load()
+    fn = lib.isac_type1mp_codebook_from_table if from_table else lib.isac_type1mp_codebook
     dims = (C.c_int32 * 9)()
-    st = lib.isac_type1mp_codebook(C.byref(cfg), Ng, int(nLayers), dims, None)
+    st = fn(C.byref(cfg), Ng, int(nLayers), dims, None)
     if st:
         raise _lib.IsacError(st, "type-1 multi-panel codebook: invalid configuration")
     W = np.zeros((2 * Ng * N1 * N2, int(nLayers)) + tuple(int(x) for x in dims), dtype=np.complex128, order="F")
-    st = lib.isac_type1mp_codebook(C.byref(cfg), Ng, int(nLayers), dims, _lib.ptr(W))
+    st = fn(C.byref(cfg), Ng, int(nLayers), dims, _lib.ptr(W))
     if st:
         raise _lib.IsacError(st, "type-1 multi-panel codebook")
     return W

@@ -19,6 +19,9 @@ import numpy as np
 
 from .. import _lib
 
+# TS 38.214 Table 5.2.2.2.2-1: (Ng, N1, N2) -> (O1, O2)
+_MP_PANELS = {(2, 2, 1): (4, 1), (2, 4, 1): (4, 1), (4, 2, 1): (4, 1), (2, 2, 2): (4, 4), (2, 8, 1): (4, 1), (4, 4, 1): (4, 1),
+              (2, 4, 2): (4, 4), (4, 2, 2): (4, 4)}
 _PANELS = {(2, 1): (4, 1), (2, 2): (4, 4), (4, 1): (4, 1), (3, 2): (4, 4), (6, 1): (4, 1), (4, 2): (4, 4), (8, 1): (4, 1),
            (4, 3): (4, 4), (6, 2): (4, 4), (12, 1): (4, 1), (4, 4): (4, 4), (8, 2): (4, 4), (16, 1): (4, 1)}
 
@@ -26,8 +29,9 @@ _PANELS = {(2, 1): (4, 1), (2, 2): (4, 4), (4, 1): (4, 1), (3, 2): (4, 4), (6, 1
 def _validate_report_config(carrier, n_ports, reportConfig):
     """validateInputs of dlPMISelect.m:511-795 (Type1SinglePanel); raises ValueError with the reference's ids."""
     rc = dict(reportConfig)
-    if rc.get("CodebookType", "Type1SinglePanel") != "Type1SinglePanel":
-        raise NotImplementedError("Type1MultiPanel codebooks are outside the built hot path (DESIGN.md)")
+    multi = rc.get("CodebookType", "Type1SinglePanel") == "Type1MultiPanel"
+    if rc.get("CodebookType", "Type1SinglePanel") not in ("Type1SinglePanel", "Type1MultiPanel"):
+        raise ValueError("nr5g:dlPMISelect:InvalidCodebookType")
     nsize = rc.get("NSizeBWP") or carrier["NSizeGrid"]
     nstart = rc.get("NStartBWP")
     nstart = carrier.get("NStartGrid", 0) if nstart is None else nstart
@@ -37,7 +41,17 @@ def _validate_report_config(carrier, n_ports, reportConfig):
         raise ValueError("nr5g:dlPMISelect:InvalidBWPLimits")
     mode = int(rc.get("CodebookMode", 1))
     N1 = N2 = O1 = O2 = 1
-    if n_ports > 2:
+    Ng = 0
+    if multi:                                           # dlPMISelect.m:629-644 (TS 38.214 Table 5.2.2.2.2-1)
+        if "PanelDimensions" not in rc or len(rc["PanelDimensions"]) != 3:
+            raise ValueError("nr5g:dlPMISelect:PanelDimensionsMissing")
+        Ng, N1, N2 = (int(x) for x in rc["PanelDimensions"])
+        if (Ng, N1, N2) not in _MP_PANELS or 2 * Ng * N1 * N2 != n_ports:
+            raise ValueError("nr5g:dlPMISelect:InvalidPanelDimensions")
+        if mode == 2 and Ng != 2:
+            raise ValueError("nr5g:dlPMISelect:InvalidCodebookMode")
+        O1, O2 = _MP_PANELS[(Ng, N1, N2)]
+    elif n_ports > 2:
         if "PanelDimensions" not in rc:
             raise ValueError("nr5g:dlPMISelect:PanelDimensionsMissing")
         N1, N2 = (int(x) for x in rc["PanelDimensions"])
@@ -64,7 +78,7 @@ def _validate_report_config(carrier, n_ports, reportConfig):
     i2r = np.ones(16, dtype=np.uint8) if rc.get("i2Restriction") is None else np.ascontiguousarray(rc["i2Restriction"], dtype=np.uint8)
     rir = np.ones(8, dtype=np.uint8) if rc.get("RIRestriction") is None else np.ascontiguousarray(rc["RIRestriction"], dtype=np.uint8)
     return dict(NSizeBWP=int(nsize), NStartBWP=int(nstart), CodebookMode=mode, N1=N1, N2=N2, O1=O1, O2=O2,
-                PMIMode=pmi_mode, CQIMode=cqi_mode, SubbandSize=nsb, csr=csr, i2r=i2r, rir=rir)
+                PMIMode=pmi_mode, CQIMode=cqi_mode, SubbandSize=nsb, csr=csr, i2r=i2r, rir=rir, Ng=Ng)
 
 
 def _csirs_res(carrier, csirs, v):
@@ -99,11 +113,11 @@ class _Csi:
             K=int(carrier["NSizeGrid"]) * 12, L=int(carrier.get("SymbolsPerSlot", 14)), nRx=int(n_rx),
             subsetRestriction=v["csr"].ctypes.data, i2Restriction=v["i2r"].ctypes.data,
             riRestriction=(C.c_uint8 * 8)(*[int(x) for x in v["rir"]]),
-            nRE=int(re_k.size), reK=re_k.ctypes.data, reL=re_l.ctypes.data)
+            nRE=int(re_k.size), reK=re_k.ctypes.data, reL=re_l.ctypes.data, nPanels=int(v.get("Ng", 0)))
 
     def key(self):
         v = self.v
-        return (self.cfg.nPorts, v["N1"], v["N2"], v["CodebookMode"], v["NSizeBWP"], v["NStartBWP"], v["SubbandSize"],
+        return (self.cfg.nPorts, v.get("Ng", 0), v["N1"], v["N2"], v["CodebookMode"], v["NSizeBWP"], v["NStartBWP"], v["SubbandSize"],
                 v["PMIMode"], v["CQIMode"], self.cfg.K, self.cfg.L, self.cfg.nRx, v["csr"].tobytes(), v["i2r"].tobytes(),
                 v["rir"].tobytes(), self.re_k.tobytes(), self.re_l.tobytes())
 
@@ -182,7 +196,13 @@ def _pmi_plan(cs, nLayers, batch):
     return ctx, ent[0]
 
 
+def _single_panel_only(cs, what):
+    if int(cs.v.get("Ng", 0)) >= 2:
+        raise NotImplementedError(f"{what}: Type1MultiPanel reports are covered by dlPMISelect only (DESIGN.md section 6)")
+
+
 def _csi_plan(cs, batch):
+    _single_panel_only(cs, "riSelect / cqiSelect / csiReport")
     ctx = _lib.get_context(None)
     key = cs.key()
     ent = _csi_plans.get(key)
@@ -232,6 +252,40 @@ def dlPMISelect(carrier, csirs, reportConfig, nLayers, H, nVar=1e-10, full_grid=
     i2 = np.zeros((nSB.value, B), order="F")
     _lib.check(lib.isac_dl_pmi_collect(plan, B, _lib.ptr(i1), _lib.ptr(i2), None), ctx.handle)
     nCand = int(np.prod(d))
+    Ng = int(cs.v.get("Ng", 0))
+    if Ng >= 2:
+        # Type1MultiPanel (dlPMISelect.m:1351-1772): the plan keeps the 9-D index set [i20 i21 i22 | i11 i12 i13 i141 i142 i143]
+        # flattened in MATLAB linear order (i2 = i20,i21,i22; i13' = i13,i141,i142,i143); un-flatten it here
+        if nLayers > 4:
+            raise ValueError("nr5g:hDLPMISelect:InvalidNumLayers")
+        from . import pmiType1MultiPanelCodebook
+        mp = (C.c_int32 * 7)()
+        _lib.check(lib.isac_pmi_plan_mp_dims(plan, mp), ctx.handle)
+        mp = [int(x) for x in mp]
+        full = (mp[0], mp[1], mp[2], d[1], d[2], mp[3], mp[4], mp[5], mp[6])
+        W = pmiType1MultiPanelCodebook({"PanelDimensions": (Ng, cs.v["N1"], cs.v["N2"]), "CodebookMode": cs.v["CodebookMode"],
+                                        "CodebookSubsetRestriction": cs.v["csr"]}, nLayers)
+        S = np.zeros((nRE.value, nLayers, nCand, B), order="F")
+        Sb = np.zeros((nSB.value, nLayers, nCand, B), order="F")
+        _lib.check(lib.isac_dl_pmi_get_info(plan, B, _lib.ptr(S), _lib.ptr(Sb)), ctx.handle)
+        S = S.reshape((nRE.value, nLayers) + full + (B,), order="F")
+        Sb = Sb.reshape((nSB.value, nLayers) + full + (B,), order="F")
+        i1o = np.full((6, B), np.nan, order="F")
+        i2o = np.full((3, nSB.value, B), np.nan, order="F")
+        for b in range(B):
+            if not np.any(np.isnan(i1[:, b])):
+                i13f = int(i1[2, b]) - 1
+                i1o[:, b] = [i1[0, b], i1[1, b]] + [x + 1 for x in np.unravel_index(i13f, tuple(mp[3:7]), order="F")]
+            for sb in range(nSB.value):
+                if not np.isnan(i2[sb, b]):
+                    i2o[:, sb, b] = [x + 1 for x in np.unravel_index(int(i2[sb, b]) - 1, tuple(mp[0:3]), order="F")]
+        if full_grid:
+            g = np.full((cs.cfg.nSizeBWP * 12, L, nLayers) + full + (B,), np.nan)
+            g[reK - 1, reL - 1] = S
+            S = g
+        if B == 1:
+            i1o, i2o, S, Sb = i1o[:, 0], i2o[:, :, 0], S[..., 0], Sb[..., 0]
+        return {"i1": i1o, "i2": i2o}, {"SINRPerRE": S, "SINRPerSubband": Sb, "W": W, "reK": reK, "reL": reL}
     W = _codebook({**reportConfig, "NumCSIRSPorts": P}, nLayers, 0) if P > 1 else np.ones((1, 1, 1, 1, 1, 1), complex)
     if nRE.value and np.any(W):
         S = np.zeros((nRE.value, nLayers, nCand, B), order="F")

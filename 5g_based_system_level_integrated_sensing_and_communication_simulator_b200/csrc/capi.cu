@@ -758,6 +758,7 @@ static CsiConfig to_csi_config(const isac_csi_config* c) {
     o.subsetRestriction = c->subsetRestriction; o.i2Restriction = c->i2Restriction;
     std::memcpy(o.riRestriction, c->riRestriction, 8);
     o.nRE = c->nRE; o.reK = c->reK; o.reL = c->reL;
+    o.nPanels = c->nPanels;
     return o;
 }
 
@@ -784,6 +785,24 @@ int isac_type1mp_codebook(const isac_csi_config* cfg, int32_t nPanels, int32_t n
     if (st) return st;
     for (int i = 0; i < 9; ++i) dims[i] = d[i];
     if (W) std::memcpy(W, w.data(), sizeof(std::complex<double>) * w.size());
+    return ISAC_OK;
+}
+
+int isac_type1mp_codebook_from_table(const isac_csi_config* cfg, int32_t nPanels, int32_t nLayers, int32_t dims[9], double* W) {
+    if (!cfg || !dims) return ISAC_ERR_INVALID_ARG;
+    CsiConfig c = to_csi_config(cfg);
+    c.nPanels = nPanels;
+    c.nPorts = 2 * nPanels * c.N1 * c.N2;
+    CodebookTable t;
+    const int st = build_type1mp_table(nullptr, c, nLayers, t);
+    if (st) return st;
+    const int d[9] = {t.mp[0], t.mp[1], t.mp[2], t.n11, t.n12, t.mp[3], t.mp[4], t.mp[5], t.mp[6]};
+    for (int i = 0; i < 9; ++i) dims[i] = d[i];
+    if (W) {
+        std::vector<std::complex<double>> w;
+        materialize_codebook(t, w);
+        std::memcpy(W, w.data(), sizeof(std::complex<double>) * w.size());
+    }
     return ISAC_OK;
 }
 
@@ -824,7 +843,13 @@ int isac_pmi_plan_destroy(isac_pmi_plan* pl) {
 
 int isac_pmi_plan_set_kernel(isac_pmi_plan* pl, int32_t direct) {
     if (!pl || !pl->p) return ISAC_ERR_INVALID_ARG;
-    pl->p->direct = direct != 0;
+    pl->p->direct = direct != 0 || pl->p->cfg.nPanels >= 2;   // Type1MultiPanel plans always run the direct kernel
+    return ISAC_OK;
+}
+
+int isac_pmi_plan_mp_dims(const isac_pmi_plan* pl, int32_t mpDims[7]) {
+    if (!pl || !pl->p || !mpDims) return ISAC_ERR_INVALID_ARG;
+    for (int i = 0; i < 7; ++i) mpDims[i] = pl->p->tab.mp[i];
     return ISAC_OK;
 }
 
@@ -874,6 +899,10 @@ int isac_dl_pmi_get_info(isac_pmi_plan* pl, int32_t batch, double* sinrPerRE, do
 }
 
 int isac_csi_plan_create(isac_ctx* h, const isac_csi_config* cfg, int32_t maxBatch, isac_csi_plan** out) {
+    if (h && cfg && cfg->nPanels >= 2) {   // RI / CQI reports: Type1SinglePanel only (dlPMISelect covers Type1MultiPanel)
+        set_error(&h->c, "csi_plan_create: Type1MultiPanel reports are supported by the dlPMISelect entry points only");
+        return ISAC_ERR_UNSUPPORTED;
+    }
     if (!h || !cfg || !out) return ISAC_ERR_INVALID_ARG;
     cudaSetDevice(h->c.device);
     isac_csi_plan* pl = new isac_csi_plan();

@@ -55,6 +55,7 @@ struct Builder {
         LayerDesc& d = t.layers[ci * t.nLayers + j];
         d.beam = b;
         d.coef[0] = c0; d.coef[1] = c1; d.coef[2] = c2; d.coef[3] = c3;
+        for (int b = 4; b < kMaxBlocks; ++b) d.coef[b] = 0.0;
     }
 };
 
@@ -476,6 +477,85 @@ int type1mp_codebook(Ctx* ctx, const CsiConfig& c, int Ng, int nu, int dims[9], 
                             col[(2 * g) * Pb + q] = s * first[g] * x[q];
                             col[(2 * g + 1) * Pb + q] = (minus ? -s : s) * second[g] * x[q];
                         }
+                }
+              }
+         }
+    return kOk;
+}
+
+int build_type1mp_table(Ctx* ctx, const CsiConfig& c, int nu, CodebookTable& t) {
+    t = CodebookTable();
+    const int Ng = c.nPanels, N1 = c.N1, N2 = c.N2, O1 = c.O1, O2 = c.O2, mode = c.codebookMode;
+    int d[9];
+    int st = type1mp_codebook(ctx, c, Ng, nu, d, nullptr);   // validates the configuration, returns the index-set lengths
+    if (st) return st;
+    if (2 * Ng * N1 * N2 != c.nPorts) { set_error(ctx, "nr5g:dlPMISelect:InvalidPanelDimensions"); return kErrInvalidArg; }
+    const int n20 = d[0], n21 = d[1], n22 = d[2], n11 = d[3], n12 = d[4], n13 = d[5], n141 = d[6], n142 = d[7], n143 = d[8];
+    std::vector<int> k1, k2;   // same tables as type1mp_codebook
+    if (nu == 1) { k1 = {0}; k2 = {0}; }
+    else if (nu == 2) {
+        if (N1 > N2 && N2 > 1) { k1 = {0, O1, 0, 2 * O1}; k2 = {0, 0, O2, 0}; }
+        else if (N1 == N2) { k1 = {0, O1, 0, O1}; k2 = {0, 0, O2, O2}; }
+        else if (N1 == 2 && N2 == 1) { k1 = {0, O1}; k2 = {0, 0}; }
+        else { k1 = {0, O1, 2 * O1, 3 * O1}; k2 = {0, 0, 0, 0}; }
+    } else {
+        if (N1 == 2 && N2 == 1) { k1 = {O1}; k2 = {0}; }
+        else if (N1 == 4 && N2 == 1) { k1 = {O1, 2 * O1, 3 * O1}; k2 = {0, 0, 0}; }
+        else if (N1 == 8 && N2 == 1) { k1 = {O1, 2 * O1, 3 * O1, 4 * O1}; k2 = {0, 0, 0, 0}; }
+        else if (N1 == 2 && N2 == 2) { k1 = {O1, 0, O1}; k2 = {0, O2, O2}; }
+        else { k1 = {O1, 0, O1, 2 * O1}; k2 = {0, O2, O2, 0}; }
+    }
+    t.P = c.nPorts;
+    t.nLayers = nu;
+    t.NB = 2 * Ng;
+    t.Pb = N1 * N2;
+    t.nBeams = n11 * n12;
+    t.scale = 1.0 / std::sqrt((double)nu * t.P);
+    t.beams.resize((size_t)t.nBeams * t.Pb);
+    for (int l = 0; l < n11; ++l)
+        for (int m = 0; m < n12; ++m)
+            for (int a1 = 0; a1 < N1; ++a1)
+                for (int a2 = 0; a2 < N2; ++a2) {   // getVlm: N2 fastest
+                    const double ang = 2.0 * M_PI * ((double)l * a1 / (O1 * N1) + (double)m * a2 / (O2 * N2));
+                    t.beams[(size_t)(l * n12 + m) * t.Pb + a1 * N2 + a2] = cd(std::cos(ang), std::sin(ang));
+                }
+    Builder B{c, t, N1, N2, O1, O2, t.P};
+    B.alloc(n20 * n21 * n22, n11, n12, n13 * n141 * n142 * n143);
+    const int mp[7] = {n20, n21, n22, n13, n141, n142, n143};
+    for (int i = 0; i < 7; ++i) t.mp[i] = mp[i];
+    const cd A0(std::sqrt(0.5), std::sqrt(0.5)), B0(std::sqrt(0.5), -std::sqrt(0.5));
+    for (int i143 = 0; i143 < n143; ++i143)
+     for (int i142 = 0; i142 < n142; ++i142)
+      for (int i141 = 0; i141 < n141; ++i141)
+       for (int i13 = 0; i13 < n13; ++i13)
+        for (int i12 = 0; i12 < n12; ++i12)
+         for (int i11 = 0; i11 < n11; ++i11) {
+            if (B.restrictedLM({N2 * O2 * i11 + i12})) continue;   // only the v_lm restriction applies (:1434)
+            const int bv = B.beam(i11, i12), bvp = B.beam(i11 + k1[i13], i12 + k2[i13]);
+            const int i13f = i13 + n13 * (i141 + n141 * (i142 + n142 * i143));
+            for (int i22 = 0; i22 < n22; ++i22)
+             for (int i21 = 0; i21 < n21; ++i21)
+              for (int i20 = 0; i20 < n20; ++i20) {
+                const size_t ci = B.cand(i20 + n20 * (i21 + n21 * i22), i11, i12, i13f);
+                t.valid[ci] = 1;
+                const cd fn = phi(i20);
+                cd first[4], second[4];
+                if (mode == 1) {
+                    const cd cg[4] = {cd(1, 0), phi(i141), phi(i142), phi(i143)};
+                    for (int g = 0; g < Ng; ++g) { first[g] = cg[g]; second[g] = cg[g] * fn; }
+                } else {
+                    first[0] = cd(1, 0); second[0] = fn;
+                    first[1] = A0 * phi(i141) * B0 * phi(i21); second[1] = A0 * phi(i142) * B0 * phi(i22);
+                }
+                for (int j = 0; j < nu; ++j) {
+                    const bool prime = (nu == 2 && j == 1) || (nu >= 3 && (j == 1 || j == 3));
+                    const bool minus = (nu == 2 && j == 1) || (nu >= 3 && j >= 2);
+                    LayerDesc& ld = t.layers[ci * nu + j];
+                    ld.beam = prime ? bvp : bv;
+                    for (int g = 0; g < Ng; ++g) {
+                        ld.coef[2 * g] = first[g];
+                        ld.coef[2 * g + 1] = minus ? -second[g] : second[g];
+                    }
                 }
               }
          }

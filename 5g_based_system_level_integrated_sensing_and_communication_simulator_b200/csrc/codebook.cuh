@@ -9,7 +9,8 @@ namespace isac {
 
 constexpr int kMaxLayers = 8;
 constexpr int kMaxPmiBatch = 32;  // UEs per PMI launch (their noise variances travel as kernel parameters)
-constexpr int kMaxBlocks = 4;  // column blocks of a precoder: 2 (v_lm ; phi v_lm), 4 (vbar: 1, theta, phi, phi*theta) or P (explicit W, P <= 4)
+constexpr int kMaxBlocks = 8;  // column blocks of a precoder: 2 (v_lm ; phi v_lm), 4 (vbar: 1, theta, phi, phi*theta), P (explicit W, P <= 4)
+                               // or 2*Ng (multi-panel: both polarisations of every panel)
 
 // Mirrors isac_csi_config of include/isac_b200.h (validated reportConfig of dlPMISelect.m:511-851)
 struct CsiConfig {
@@ -28,6 +29,7 @@ struct CsiConfig {
     int nRE;
     const int* reK;             // 1-based CSI-RS RE subscripts relative to the BWP (validateInputs :797-833)
     const int* reL;
+    int nPanels;                // Ng of a Type1MultiPanel report (PanelDimensions = [Ng N1 N2]); 0 or 1 = Type1SinglePanel
 };
 
 // One precoder column = scale * [coef[0]*v ; coef[1]*v ; ...] with v = beams[beam]
@@ -45,6 +47,9 @@ struct CodebookTable {
     std::vector<uint8_t> valid;                     // [nCand] 0 = restricted (all-zero W)
     std::vector<LayerDesc> layers;                  // [nCand][nLayers]
     std::vector<double> candScale;                  // [nCand] per-candidate factor (explicit codebooks), else empty
+    // Type1MultiPanel: the reference's 9-D index set [i20 i21 i22 | i11 i12 i13 i141 i142 i143] is walked in MATLAB linear order,
+    // so it is stored flattened as n2 = i20*i21*i22 and n13 = i13*i141*i142*i143; mp = {i20,i21,i22,i13,i141,i142,i143} lengths
+    int mp[7] = {0, 0, 0, 0, 0, 0, 0};
     int nCand() const { return n2 * n11 * n12 * n13; }
 };
 
@@ -52,6 +57,9 @@ enum CodebookVariant { kVariantUE = 0, kVariantGNB = 1 };
 
 // getPMIType1SinglePanelCodebook (dlPMISelect.m:853-1349) / pmiType1SinglePanelCodebook.m:46-554
 int build_type1sp_table(Ctx* ctx, const CsiConfig& c, int nLayers, int variant, CodebookTable& t);
+// getPMIType1MultiPanelCodebook (dlPMISelect.m:1351-1772) as a beam / co-phasing table (2*Ng blocks per column), flattened
+// index set (see CodebookTable::mp); c.nPanels = Ng
+int build_type1mp_table(Ctx* ctx, const CsiConfig& c, int nLayers, CodebookTable& t);
 // getPMIType1MultiPanelCodebook (dlPMISelect.m:1351-1772): dims = [i20 i21 i22 i11 i12 i13 i141 i142 i143] lengths, W (may be
 // nullptr) = explicit [P x nLayers x prod(dims)] array, column-major, restricted precoders zero
 int type1mp_codebook(Ctx* ctx, const CsiConfig& c, int nPanels, int nLayers, int dims[9], std::vector<std::complex<double>>* W);

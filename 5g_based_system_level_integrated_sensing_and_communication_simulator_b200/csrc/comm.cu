@@ -522,8 +522,10 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
     p->cfg.nRE = (int)p->reK.size();
     p->cfg.reK = p->reK.data();
     p->cfg.reL = p->reL.data();
-    int s = build_type1sp_table(ctx, p->cfg, nLayers, kVariantUE, p->tab);
+    const bool multiPanel = p->cfg.nPanels >= 2;
+    int s = multiPanel ? build_type1mp_table(ctx, p->cfg, nLayers, p->tab) : build_type1sp_table(ctx, p->cfg, nLayers, kVariantUE, p->tab);
     if (s) { delete p; return s; }
+    if (multiPanel) p->direct = true;   // the Gram-pair dictionary is sized for the single-panel column structure
     subband_info(p->cfg.pmiSubband != 0, p->cfg.nStartBWP, p->cfg.nSizeBWP, p->cfg.subbandSize, p->sbSizes);
     subband_info(p->cfg.cqiSubband != 0, p->cfg.nStartBWP, p->cfg.nSizeBWP, p->cfg.subbandSize, p->cqiSbSizes);
     p->nSB = (int)p->sbSizes.size();

@@ -261,6 +261,7 @@ typedef struct {
     int32_t nRE;                       /* CSI-RS REs kept by validateInputs (port 1, lowest RE of each CDM group)  :797-833 */
     const int32_t* reK;                /* 1-based subcarrier subscripts relative to the BWP     :352-356 */
     const int32_t* reL;                /* 1-based OFDM symbol subscripts */
+    int32_t nPanels;                   /* Type1MultiPanel: Ng of PanelDimensions = [Ng N1 N2] (nPorts = 2*Ng*N1*N2); 0 / 1 = Type1SinglePanel */
 } isac_csi_config;
 
 /* W = getPMIType1SinglePanelCodebook(reportConfig,nLayers) (dlPMISelect.m:853; variant 0) or
@@ -271,9 +272,11 @@ int isac_type1sp_codebook(const isac_csi_config* cfg, int32_t nLayers, int32_t v
 /* Wmp = getPMIType1MultiPanelCodebook(reportConfig,nLayers) (dlPMISelect.m:1351; TS 38.214 Tables 5.2.2.2.2-1..-6) for
  * PanelDimensions = [nPanels N1 N2] (nPanels = Ng in {2,4}; codebook mode 2 only with Ng = 2; nLayers <= 4).
  * dims = [i20 i21 i22 i11 i12 i13 i141 i142 i143] lengths; W complex128 [P x nLayers x prod(dims)] with P = 2*Ng*N1*N2
- * (NULL to query dims).  Uses cfg->N1, N2, O1, O2, codebookMode, subsetRestriction.  Pure host code.  The PMI / RI / CQI
- * selection entry points below cover Type1SinglePanel only (the shipped configuration never sets CodebookType). */
+ * (NULL to query dims).  Uses cfg->N1, N2, O1, O2, codebookMode, subsetRestriction.  Pure host code.  Selection over it:
+ * isac_pmi_plan_create with cfg->nPanels = Ng (dlPMISelect); the RI / CQI report entry points cover Type1SinglePanel only. */
 int isac_type1mp_codebook(const isac_csi_config* cfg, int32_t nPanels, int32_t nLayers, int32_t dims[9], double* W);
+/* The same array materialised from the beam / co-phasing table the SINR kernels read (consistency check of that table). */
+int isac_type1mp_codebook_from_table(const isac_csi_config* cfg, int32_t nPanels, int32_t nLayers, int32_t dims[9], double* W);
 /* nrPUSCHCodebook(nlayers,nports,tpmi).' for tpmi = 0..maxTPMI (pmiSelect.m:45; TS 38.211 Tables 6.3.1.5-1..7);
  * W complex128 [nPorts x nLayers x nTPMI] (NULL to query nTPMI). */
 int isac_pusch_codebook(int32_t nLayers, int32_t nPorts, int32_t* nTPMI, double* W);
@@ -286,6 +289,11 @@ int isac_pmi_plan_destroy(isac_pmi_plan* plan);
  * 1 = direct form (H*W per candidate).  Same results to rounding; the direct form is the fallback for codebooks whose
  * pair dictionary does not fit in shared memory. */
 int isac_pmi_plan_set_kernel(isac_pmi_plan* plan, int32_t direct);
+/* Type1MultiPanel plans (cfg->nPanels = Ng >= 2, nLayers <= 4, dlPMISelect.m:1351-1772) keep the reference's 9-D index set
+ * [i20 i21 i22 | i11 i12 i13 i141 i142 i143] flattened in MATLAB linear order: dims[0] = i20*i21*i22, dims[3] =
+ * i13*i141*i142*i143, and PMISet comes back flattened likewise (i2 per subband; i1 = [i11 i12 i13']); mpDims = {i20, i21, i22,
+ * i13, i141, i142, i143} lengths un-flatten it (all zero for a single-panel plan).  They run the direct SINR kernel. */
+int isac_pmi_plan_mp_dims(const isac_pmi_plan* plan, int32_t mpDims[7]);
 /* dims = [i2 i11 i12 i13]; REs sorted by subcarrier as the plan stores them (reKs/reLs may be NULL) */
 int isac_pmi_plan_info(const isac_pmi_plan* plan, int32_t dims[4], int32_t* nSB, int32_t* nCqiSB, int32_t* nRE,
                        int32_t* reKs, int32_t* reLs);

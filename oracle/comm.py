@@ -407,7 +407,34 @@ def precoded_sinr_ul(H, sigma, W):
 # ----------------------------------------------------------------------------------------------
 # a9: dlPMISelect
 # ----------------------------------------------------------------------------------------------
-def dl_pmi_select(cfg, re_k, re_l, n_layers, H, n_var=1e-10, K=None, L=14, compact=True):
+def dl_pmi_select_multi_panel(cfg, n_panels, re_k, re_l, n_layers, H, n_var=1e-10):
+    """dlPMISelect with CodebookType = 'Type1MultiPanel' (dlPMISelect.m:385-501, multi-panel branches).  The reference walks its
+    9-D index set [i20 i21 i22 | i11 i12 i13 i141 i142 i143] in MATLAB linear order (find(...,1) at :455 and :489), so the
+    selection equals the single-panel selection on the array flattened to [i20*i21*i22, i11, i12, i13*i141*i142*i143].
+    -> PMISet {i1 [6], i2 [3 x nSB]} (:456-457, :489), info with the 9-D SINR arrays."""
+    Wmp = type1_multi_panel_codebook(cfg, n_panels, n_layers)
+    P, nu = Wmp.shape[:2]
+    d = Wmp.shape[2:]
+    flat = (d[0] * d[1] * d[2], d[3], d[4], d[5] * d[6] * d[7] * d[8])
+    pm, info = dl_pmi_select(dict(cfg, NumCSIRSPorts=P), re_k, re_l, n_layers, H, n_var,
+                             W_override=np.asfortranarray(Wmp).reshape((P, nu) + flat, order="F"))
+    n_sb = pm["i2"].size
+    i1 = np.full(6, np.nan)
+    if not np.any(np.isnan(pm["i1"])):
+        i1[:2] = pm["i1"][:2]
+        i1[2:] = [x + 1 for x in np.unravel_index(int(pm["i1"][2]) - 1, d[5:9], order="F")]
+    i2 = np.full((3, n_sb), np.nan)
+    for sb in range(n_sb):
+        if not np.isnan(pm["i2"][sb]):
+            i2[:, sb] = [x + 1 for x in np.unravel_index(int(pm["i2"][sb]) - 1, d[0:3], order="F")]
+    out = {"W": Wmp}
+    for key in ("SINRPerRE", "SINRPerSubband"):
+        a = info[key]
+        out[key] = None if a is None else np.asfortranarray(a).reshape(a.shape[:2] + tuple(d), order="F")
+    return {"i1": i1, "i2": i2}, out
+
+
+def dl_pmi_select(cfg, re_k, re_l, n_layers, H, n_var=1e-10, K=None, L=14, compact=True, W_override=None):
     """``[PMISet,info] = dlPMISelect(carrier,csirs,reportConfig,nLayers,H,nVar)`` (dlPMISelect.m:307-509),
     Type1SinglePanel.  ``re_k/re_l``: 1-based CSI-RS RE subscripts relative to the BWP (validateInputs :797-833).
     ``compact``: info['SINRPerRE'] is [nRE, nLayers, i2, i11, i12, i13] at the CSI-RS REs instead of the
@@ -415,7 +442,10 @@ def dl_pmi_select(cfg, re_k, re_l, n_layers, H, n_var=1e-10, K=None, L=14, compa
     n_var = max(float(n_var), 1e-10)                                                    # :846-848
     n_sb, sb_sizes = subband_info(cfg["PMIMode"], cfg["NStartBWP"], cfg["NSizeBWP"], cfg["SubbandSize"])
     P = cfg["NumCSIRSPorts"]
-    W = np.ones((1, 1, 1, 1, 1, 1), complex) if P == 1 else type1_single_panel_codebook(cfg, n_layers, "ue")
+    if W_override is not None:
+        W = W_override
+    else:
+        W = np.ones((1, 1, 1, 1, 1, 1), complex) if P == 1 else type1_single_panel_codebook(cfg, n_layers, "ue")
     _, _, n2, n11, n12, n13 = W.shape
     sizes = (n2, n11, n12, n13)
     re_k = np.asarray(re_k, dtype=int)

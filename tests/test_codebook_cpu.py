@@ -116,6 +116,10 @@ def test_multi_panel_codebook_host_builder_equals_oracle(panel, mode, nu):
                                         "CodebookSubsetRestriction": csr}, Ng, nu)
     assert W.shape == Wo.shape
     assert np.abs(W - Wo).max() <= 1e-14
+    # the beam / co-phasing table the SINR kernels read (2*Ng blocks per column, flattened index set) materialises to the same array
+    Wt = com.pmiType1MultiPanelCodebook({"PanelDimensions": panel, "CodebookMode": mode, "CodebookSubsetRestriction": csr}, nu,
+                                        from_table=True)
+    assert Wt.shape == Wo.shape and np.abs(Wt - Wo).max() <= 1e-14
     # restricted precoders are all zero, every other one has orthogonal columns of power 1/nu
     G = np.einsum("pa...,pb...->ab...", W.conj(), W)
     live = np.abs(W).sum(axis=(0, 1)) > 0
