@@ -10,7 +10,11 @@ function [cfg, rc] = isacCsiConfig(carrier, csirs, reportConfig, nLayers, H, nVa
     rir = ones(1, 8);
     if isfield(rc, 'RIRestriction') && ~isempty(rc.RIRestriction), rir(1:numel(rc.RIRestriction)) = rc.RIRestriction; end
     cqiSubband = isfield(rc, 'CQIMode') && strcmpi(rc.CQIMode, 'Subband');
-    cfg = struct('nPorts', csirs.NumCSIRSPorts(1), 'N1', rc.PanelDimensions(1), 'N2', rc.PanelDimensions(2), ...
+    nPanels = 0; pd = rc.PanelDimensions;
+    if isfield(rc, 'CodebookType') && strcmpi(rc.CodebookType, 'Type1MultiPanel')   % PanelDimensions = [Ng N1 N2] (:629-644)
+        nPanels = pd(1); pd = pd(2:3);
+    end
+    cfg = struct('nPanels', nPanels, 'nPorts', csirs.NumCSIRSPorts(1), 'N1', pd(1), 'N2', pd(2), ...
                  'O1', rc.OverSamplingFactors(1), 'O2', rc.OverSamplingFactors(2), 'codebookMode', rc.CodebookMode, ...
                  'nSizeBWP', rc.NSizeBWP, 'nStartBWP', rc.NStartBWP, 'subbandSize', max([rc.SubbandSize 0]), ...
                  'pmiSubband', double(strcmpi(rc.PMIMode, 'Subband')), 'cqiSubband', double(cqiSubband), ...

@@ -145,5 +145,7 @@ struct CsiCfg {
         for (int i = 0; i < 8; ++i) c.riRestriction[i] = i < (int)rir.size() ? rir[i] : 1;   /* riSelect.m:440-447 */
         reK = field_int32s(cfg, "reK"); reL = field_int32s(cfg, "reL");
         c.nRE = (int32_t)reK.size(); c.reK = reK.data(); c.reL = reL.data();
+        const mxArray* np = mxGetField(cfg, 0, "nPanels");   /* optional: Ng of a Type1MultiPanel report (dlPMISelect.m:629-644) */
+        c.nPanels = np ? (int32_t)mxGetScalar(np) : 0;
     }
 };

@@ -165,3 +165,33 @@ def test_dl_pmi_and_csi_report_gateways(P):
     _, i1, i2, CQI = M.call("isac_csi_report_mex", 4, cfg, H, 0.1, table, 0.0, 2.0, 3.0)     # mode 2: cqiSelect at rank 3
     assert np.array_equal(i1.ravel(), pm_cq["i1"]) and np.array_equal(i2.ravel(), pm_cq["i2"], equal_nan=True)
     assert np.array_equal(CQI[:, : cq_ref.shape[1]], cq_ref, equal_nan=True)
+
+
+def test_dl_pmi_gateway_multi_panel(P):
+    """Type1MultiPanel through the gateway: flattened outputs + mpDims, un-flattened here as the .m shim does."""
+    ph = P.communication.phyLayer
+    rng = np.random.default_rng(31)
+    nrb, R, panel, nu = 24, 4, (2, 2, 1), 2
+    Pn, K = 8, 12 * nrb
+    H = ((rng.standard_normal((K, 14, R, Pn)) + 1j * rng.standard_normal((K, 14, R, Pn))) / np.sqrt(2)).astype(np.complex64)
+    carrier = {"NSizeGrid": nrb, "NStartGrid": 0, "SymbolsPerSlot": 14}
+    csirs = {"NumCSIRSPorts": Pn, "NumRB": nrb, "RBOffset": 0, "SubcarrierLocations": 1, "SymbolLocations": 0, "Density": "one"}
+    rc = {"CodebookType": "Type1MultiPanel", "PanelDimensions": panel, "CodebookMode": 2, "NSizeBWP": nrb, "NStartBWP": 0,
+          "PMIMode": "Subband", "CQIMode": "Wideband", "SubbandSize": 8}
+    pm, info = ph.dlPMISelect(carrier, csirs, rc, nu, H, 0.1)
+    cfg = {"nPanels": 2.0, "nPorts": float(Pn), "N1": 2.0, "N2": 1.0, "O1": 4.0, "O2": 1.0, "codebookMode": 2.0, "nSizeBWP": float(nrb),
+           "nStartBWP": 0.0, "subbandSize": 8.0, "pmiSubband": 1.0, "cqiSubband": 0.0, "K": float(K), "L": 14.0,
+           "subsetRestriction": np.ones(8, np.uint8), "i2Restriction": np.ones(16, np.uint8), "riRestriction": np.ones(8, np.uint8),
+           "reK": info["reK"].astype(np.int32), "reL": info["reL"].astype(np.int32)}
+    i1, i2, S_re, S_sb, Wm, reK, reL, mp = M.call("isac_dl_pmi_mex", 8, cfg, float(nu), H, 0.1)
+    mp = [int(x) for x in mp.ravel()]
+    full = tuple(mp[0:3]) + S_re.shape[3:5] + tuple(mp[3:7])
+    assert S_re.ndim == 6 and np.prod(full) == np.prod(S_re.shape[2:])
+    assert np.array_equal(S_re.reshape(S_re.shape[:2] + full, order="F"), info["SINRPerRE"], equal_nan=True)
+    assert np.array_equal(S_sb.reshape(S_sb.shape[:2] + full, order="F"), info["SINRPerSubband"], equal_nan=True)
+    assert np.array_equal(Wm.reshape(Wm.shape[:2] + full, order="F"), info["W"])
+    i1 = i1.ravel()
+    i1u = [i1[0], i1[1]] + [x + 1 for x in np.unravel_index(int(i1[2]) - 1, tuple(mp[3:7]), order="F")]
+    assert np.array_equal(i1u, pm["i1"])
+    for sb, v in enumerate(i2.ravel()):
+        assert np.array_equal([x + 1 for x in np.unravel_index(int(v) - 1, tuple(mp[0:3]), order="F")], pm["i2"][:, sb])
