@@ -164,7 +164,8 @@ def _h_to_dev(H):
     if a.ndim == 4:
         a = a[..., None]
     K, L, R, P, B = a.shape
-    t = torch.from_numpy(np.ascontiguousarray(a.astype(np.complex64).transpose(4, 3, 2, 1, 0))).cuda()
+    dev = _lib.get_context(None).device        # host arrays go to the device of the default context (LOCAL_RANK)
+    t = torch.from_numpy(np.ascontiguousarray(a.astype(np.complex64).transpose(4, 3, 2, 1, 0))).to(f"cuda:{dev}")
     return t, K, L, R, P, B
 
 
@@ -177,17 +178,22 @@ def setSinrKernel(direct):
     (isac_pmi_plan_set_kernel).  Both give the same results to rounding; exposed for the parity tests."""
     global _direct_kernel
     _direct_kernel = bool(direct)
+    lib = _lib.get_context(None).lib
     for ent in _pmi_plans.values():
-        _lib.get_context(None).lib.isac_pmi_plan_set_kernel(ent[0], int(_direct_kernel))
+        lib.isac_pmi_plan_set_kernel(ent[0], int(_direct_kernel))
     for ent in _csi_plans.values():
-        _lib.get_context(None).lib.isac_csi_plan_set_kernel(ent[0], int(_direct_kernel))
+        lib.isac_csi_plan_set_kernel(ent[0], int(_direct_kernel))
 
 
-def _pmi_plan(cs, nLayers, batch):
-    ctx = _lib.get_context(None)
-    key = cs.key() + (nLayers,)
+def _pmi_plan(cs, nLayers, batch, device=None):
+    """Cached isac_pmi_plan of (report configuration, rank) on `device` (the device H lives on); a plan that is too small
+    for the batch is destroyed before its replacement takes the cache slot."""
+    ctx = _lib.get_context(device)
+    key = cs.key() + (nLayers, ctx.device)
     ent = _pmi_plans.get(key)
     if ent is None or ent[1] < batch:
+        if ent is not None:
+            ctx.lib.isac_pmi_plan_destroy(ent[0])
         h = C.c_void_p()
         _lib.check(ctx.lib.isac_pmi_plan_create(ctx.handle, C.byref(cs.cfg), int(nLayers), int(batch), C.byref(h)), ctx.handle)
         ctx.lib.isac_pmi_plan_set_kernel(h, int(_direct_kernel))
@@ -201,12 +207,14 @@ def _single_panel_only(cs, what):
         raise NotImplementedError(f"{what}: Type1MultiPanel reports are covered by dlPMISelect only (DESIGN.md section 6)")
 
 
-def _csi_plan(cs, batch):
+def _csi_plan(cs, batch, device=None):
     _single_panel_only(cs, "riSelect / cqiSelect / csiReport")
-    ctx = _lib.get_context(None)
-    key = cs.key()
+    ctx = _lib.get_context(device)
+    key = cs.key() + (ctx.device,)
     ent = _csi_plans.get(key)
     if ent is None or ent[1] < batch:
+        if ent is not None:
+            ctx.lib.isac_csi_plan_destroy(ent[0])
         h = C.c_void_p()
         _lib.check(ctx.lib.isac_csi_plan_create(ctx.handle, C.byref(cs.cfg), int(batch), C.byref(h)), ctx.handle)
         ctx.lib.isac_csi_plan_set_kernel(h, int(_direct_kernel))
@@ -238,7 +246,7 @@ def dlPMISelect(carrier, csirs, reportConfig, nLayers, H, nVar=1e-10, full_grid=
     if nLayers > min(R, P):
         raise ValueError("nr5g:hDLPMISelect:InvalidNumLayers")
     nv = _nvar(nVar, B)
-    ctx, plan = _pmi_plan(cs, int(nLayers), B)
+    ctx, plan = _pmi_plan(cs, int(nLayers), B, Hd.device.index)
     lib = ctx.lib
     dims = (C.c_int32 * 4)()
     nSB, nC, nRE = C.c_int32(), C.c_int32(), C.c_int32()
@@ -312,7 +320,7 @@ def riSelect(carrier, csirs, reportConfig, H, nVar=1e-10):
     Hd, K, L, R, P, B = _h_to_dev(H)
     cs = _csi_struct(carrier, csirs, reportConfig, R)
     nv = _nvar(nVar, B)
-    ctx, plan = _csi_plan(cs, B)
+    ctx, plan = _csi_plan(cs, B, Hd.device.index)
     nSB = len(_subband_sizes(cs.v["PMIMode"], cs.v))
     RI = np.zeros(B)
     i1 = np.zeros((3, B), order="F")
@@ -344,7 +352,7 @@ def cqiSelect(carrier, csirs, reportConfig, nLayers, H, nVar, SINRTable):
     Hd, K, L, R, P, B = _h_to_dev(H)
     cs = _csi_struct(carrier, csirs, reportConfig, R)
     nv = _nvar(nVar, B)
-    ctx, plan = _csi_plan(cs, B)
+    ctx, plan = _csi_plan(cs, B, Hd.device.index)
     nSB = len(_subband_sizes(cs.v["PMIMode"], cs.v))
     nC = len(_subband_sizes(cs.v["CQIMode"], cs.v))
     rows_full = nC + 1 if nC > 1 else 1
@@ -396,7 +404,7 @@ def csiReportEnqueue(carrier, csirs, reportConfig, H, nVar, SINRTable, rankCap=4
     Hd, K, L, R, P, B = _h_to_dev(H)
     cs = _csi_struct(carrier, csirs, reportConfig, R)
     nv = _nvar(nVar, B)
-    ctx, plan = _csi_plan(cs, B)
+    ctx, plan = _csi_plan(cs, B, Hd.device.index)
     nSB = len(_subband_sizes(cs.v["PMIMode"], cs.v))
     nC = len(_subband_sizes(cs.v["CQIMode"], cs.v))
     table = np.ascontiguousarray(SINRTable, dtype=np.float64)

@@ -192,6 +192,9 @@ int isac_destroy(isac_ctx* h) {
     for (int i = 0; i < Ctx::kScratchSlots; ++i)
         if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->d_twiddle) cudaFree(c->d_twiddle);
+    if (c->ulFree) c->ulFree(c->ulState);
+    for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t e : c->eventPool) cudaEventDestroy(e);
     if (c->ownStream) cudaStreamDestroy(c->ownStream);
     delete h;
     return ISAC_OK;
@@ -912,8 +915,10 @@ int isac_csi_plan_create(isac_ctx* h, const isac_csi_config* cfg, int32_t maxBat
     for (int r = 0; r < kMaxLayers; ++r) pl->byRank[r] = nullptr;
     const int maxRank = pl->cfg.nRx < pl->cfg.nPorts ? pl->cfg.nRx : pl->cfg.nPorts;  // riSelect.m:222
     PmiShared* share = nullptr;  // ranks built from the same beams share one Gram-pair dictionary -> one fused SINR launch
+    // report plans never return SINRPerRE: subband sums are accumulated inside the SINR kernel (ISAC_PMI_FUSED=0: per-RE path)
+    const bool fused = !(getenv("ISAC_PMI_FUSED") && atoi(getenv("ISAC_PMI_FUSED")) == 0);
     for (int r = 1; r <= maxRank && r <= kMaxLayers; ++r) {
-        int st = pmi_plan_create(&h->c, pl->cfg, r, maxBatch, &pl->byRank[r - 1], share);
+        int st = pmi_plan_create(&h->c, pl->cfg, r, maxBatch, &pl->byRank[r - 1], share, fused);
         if (!st && !share) share = pl->byRank[r - 1]->sh;
         if (st) {
             isac_csi_plan_destroy(pl);
@@ -1112,11 +1117,23 @@ int isac_csi_report_finish(isac_csi_plan* pl, const double* table, int32_t table
     PmiPlan* p0 = pl->byRank[0];
     const int rowsOut = (pl->cfg.cqiSubband && p0->nCqiSB > 1) ? p0->nCqiSB + 1 : 1;
     if (cqiRows) *cqiRows = rowsOut;
+    const bool launched = pl->pendLaunched;
     for (int b = 0; b < batch; ++b) {
         RI[b] = ri[b];
-        int rank = std::isnan(ri[b]) ? 1 : (int)ri[b];
-        if (rankCap > 0 && rank > rankCap) rank = rankCap;  // uePhy.m:901
-        if (std::isnan(ri[b])) RI[b] = NAN; else RI[b] = rank;
+        if (!launched) {   // no CSI-RS RE in the BWP / every rank restricted: all-NaN report (riSelect.m:235-245, cqiSelect.m:636-650)
+            if (i1) for (int q = 0; q < 3; ++q) i1[3 * b + q] = NAN;
+            if (i2) for (int sb = 0; sb < p0->nSB; ++sb) i2[(size_t)p0->nSB * b + sb] = NAN;
+            if (cqi) for (int q = 0; q < 2 * rowsOut; ++q) cqi[(size_t)2 * rowsOut * b + q] = NAN;
+            continue;
+        }
+        // rank = min(riSelect(..), rankCap) (uePhy.m:901-903): MATLAB's min ignores NaN, so a NaN RI proceeds with the cap
+        int rank = std::isnan(ri[b]) ? (rankCap > 0 ? rankCap : 1) : (int)ri[b];
+        if (rankCap > 0 && rank > rankCap) rank = rankCap;
+        if (!std::isnan(ri[b])) RI[b] = rank;
+        if (rank < 1 || rank > kMaxLayers || !pl->byRank[rank - 1]) {
+            set_error(c, "nr5g:hDLPMISelect:InvalidNumLayers");
+            return ISAC_ERR_INVALID_ARG;
+        }
         if (all[rank - 1].empty()) {  // rank not scored by the RI loop (restricted): evaluate it now
             if ((st = pmi_select_run(pl->byRank[rank - 1], H, nVar.data(), batch, c->stream))) return st;
             if ((st = pmi_select_collect(pl->byRank[rank - 1], batch, all[rank - 1]))) return st;

@@ -13,6 +13,7 @@
 // conditioning of HW, float32 cannot hold 1e-5 here), Cholesky, diag(A^-1), sinr_l = 1/(nVar [A^-1]_ll) - 1.
 #include "comm.cuh"
 #include "ctx.cuh"
+#include "sinr_core.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -34,59 +35,6 @@ struct PmiDev {
     double scale;
     double nVar[kMaxPmiBatch];  // per UE, already clipped at 1e-10 (dlPMISelect.m:846-848)
 };
-
-__device__ __forceinline__ double round4(double x) { return copysign(floor(fabs(x) * 1e4 + 0.5) / 1e4, x); }
-
-#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))   /* packed lower triangle, i >= j: stays in registers */
-
-// A (packed lower triangle of (HW)'(HW)) -> sinr_l = 1/(nVar [ (A + nVar I)^-1 ]_ll) - 1, l = 0..NU-1, written with stride
-// (dlPMISelect.m:1831-1833).  Cholesky A = L L^H in place, then [A^-1]_cc = || L^-1 e_c ||^2.
-template <int NU>
-__device__ __forceinline__ void chol_sinr(double2 (&A)[NU * (NU + 1) / 2], double nVar, double* __restrict__ out, long long stride) {
-    // every loop runs 0..NU with a compile-time guard, so each one unrolls on its own (trip counts that depend on an
-    // outer induction variable made the unroller fall back to local memory for some NU)
-#pragma unroll
-    for (int i = 0; i < NU; ++i) A[TRI(i, i)].x += nVar;
-#pragma unroll
-    for (int j = 0; j < NU; ++j) {
-        double d = A[TRI(j, j)].x;
-#pragma unroll
-        for (int k = 0; k < NU; ++k)
-            if (k < j) d = fma(-A[TRI(j, k)].x, A[TRI(j, k)].x, fma(-A[TRI(j, k)].y, A[TRI(j, k)].y, d));
-        // store 1/L_jj on the diagonal (MUFU seed + Newton instead of sqrt and two divisions)
-        const double inv = fast_rsqrt(d);
-        A[TRI(j, j)] = make_double2(inv, 0.0);
-#pragma unroll
-        for (int i = 0; i < NU; ++i) {
-            if (i > j) {
-                double2 s = A[TRI(i, j)];
-#pragma unroll
-                for (int k = 0; k < NU; ++k)
-                    if (k < j) s = zfmsc(s, A[TRI(i, k)], A[TRI(j, k)]);
-                A[TRI(i, j)] = make_double2(s.x * inv, s.y * inv);
-            }
-        }
-    }
-#pragma unroll
-    for (int cc = 0; cc < NU; ++cc) {
-        double2 x[NU];
-        x[cc] = make_double2(A[TRI(cc, cc)].x, 0.0);  // diagonal holds 1/L_cc
-        double nrm = x[cc].x * x[cc].x;
-#pragma unroll
-        for (int i = 0; i < NU; ++i) {
-            if (i > cc) {
-                double2 s = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int k = 0; k < NU; ++k)
-                    if (k >= cc && k < i) s = zfma(s, A[TRI(i, k)], x[k]);
-                const double inv = -A[TRI(i, i)].x;
-                x[i] = make_double2(s.x * inv, s.y * inv);
-                nrm = fma(x[i].x, x[i].x, fma(x[i].y, x[i].y, nrm));
-            }
-        }
-        out[(long long)cc * stride] = fast_rcp(nVar * nrm) - 1.0;
-    }
-}
 
 template <int NU>
 __global__ void __launch_bounds__(128)
@@ -485,7 +433,7 @@ static void partition_res(const std::vector<int>& k, const std::vector<int>& l, 
     start[nSB] = e;
 }
 
-int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, PmiPlan** out, PmiShared* share) {
+int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, PmiPlan** out, PmiShared* share, bool fused) {
     if (maxBatch < 1 || cin.nRx < 1 || cin.nPorts < 1 || cin.K < 12 || cin.L < 1 || cin.nRE < 0) {
         set_error(ctx, "pmi_plan_create: invalid configuration");
         return kErrInvalidArg;
@@ -499,6 +447,7 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
     p->cfg = cin;
     p->nLayers = nLayers;
     p->maxBatch = maxBatch;
+    p->fused = fused;
     if (cin.subsetRestriction) {
         const int n = cin.nPorts > 2 ? cin.N1 * cin.O1 * cin.N2 * cin.O2 : 6;
         p->csr.assign(cin.subsetRestriction, cin.subsetRestriction + n);
@@ -534,6 +483,12 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
     std::vector<double> w, cw;
     partition_res(p->reK, p->reL, p->sbSizes, sbStart, w);
     partition_res(p->reK, p->reL, p->cqiSbSizes, cqiStart, cw);
+    p->sbStartH = sbStart; p->cqiStartH = cqiStart; p->wH = w; p->cwH = cw;
+    p->uniformW = true;
+    for (int i = 0; i < p->nSB; ++i)
+        for (int e = sbStart[i]; e < sbStart[i + 1]; ++e) p->uniformW = p->uniformW && w[e] == w[sbStart[i]];
+    for (int i = 0; i < p->nCqiSB; ++i)
+        for (int e = cqiStart[i]; e < cqiStart[i + 1]; ++e) p->uniformW = p->uniformW && cw[e] == cw[cqiStart[i]];
     p->sbHasRE.resize(p->nSB);
     for (int i = 0; i < p->nSB; ++i) p->sbHasRE[i] = sbStart[i + 1] > sbStart[i];
     p->cqiSbHasRE.resize(p->nCqiSB);
@@ -676,9 +631,11 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
     const size_t B = maxBatch, nRE = p->reK.size() ? p->reK.size() : 1;
     cudaError_t e = cudaSuccess;
     auto A = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes ? bytes : 8); };
-    A((void**)&p->d_S, sizeof(double) * nCand * nu * nRE * B);
-    A((void**)&p->d_total, sizeof(double) * nCand * nu * p->nSB * B);  // plain per-subband sums
-    A((void**)&p->d_sub, sizeof(double) * nCand * nu * p->nSB * B);
+    if (!fused) {   // fused report plans allocate these on the first launch that needs them (pmi_plan_legacy_buffers)
+        A((void**)&p->d_S, sizeof(double) * nCand * nu * nRE * B);
+        A((void**)&p->d_total, sizeof(double) * nCand * nu * p->nSB * B);  // plain per-subband sums
+        A((void**)&p->d_sub, sizeof(double) * nCand * nu * p->nSB * B);
+    }
     // selection results of the plan: one arena (sel | sinrSel | sinrWb, laid out for maxBatch) -> one D2H copy
     p->resOff[0] = 0;
     p->resOff[1] = (sizeof(int) * (4 + p->nSB) * B + 15) / 16 * 16;
@@ -694,6 +651,17 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
         return kErrCuda;
     }
     *out = p;
+    return kOk;
+}
+
+// SINRPerRE / per-subband arrays of the per-RE kernels, for plans that were created without them
+static int pmi_plan_legacy_buffers(PmiPlan* p) {
+    if (p->d_S) return kOk;
+    Ctx* ctx = p->ctx;
+    const size_t nCand = p->tab.nCand(), nu = p->nLayers, nRE = p->reK.size() ? p->reK.size() : 1, B = p->maxBatch;
+    ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)&p->d_S, sizeof(double) * nCand * nu * nRE * B));
+    ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)&p->d_total, sizeof(double) * nCand * nu * p->nSB * B));
+    ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)&p->d_sub, sizeof(double) * nCand * nu * p->nSB * B));
     return kOk;
 }
 
@@ -719,6 +687,8 @@ void pmi_plan_destroy(PmiPlan* p) {
     cudaFree(p->d_reCqiSb); cudaFree(p->d_reCqiW); cudaFree(p->d_S); cudaFree(p->d_total); cudaFree(p->d_sub);
     if (p->ownsRes) cudaFree(p->d_res);
     cudaFree(p->d_ent); cudaFree(p->d_invScale2);
+    cudaFree(p->d_chunkRe0); cudaFree(p->d_chunkN); cudaFree(p->d_sbChunk); cudaFree(p->d_cqiChunk);
+    cudaFree(p->d_sbW); cudaFree(p->d_cqiSbW); cudaFree(p->d_part);
     if (p->sh && --p->sh->refs == 0) {
         cudaFree(p->sh->d_pairs);
         cudaFree(p->sh->d_pal);
@@ -768,7 +738,7 @@ static size_t pair_smem_bytes(const PmiShared* sh, int R) {
 }
 
 // (re-)upload the dictionary when ranks were added since the last launch
-static int pair_sync_dict(Ctx* ctx, PmiShared* sh, cudaStream_t st) {
+int pair_sync_dict(Ctx* ctx, PmiShared* sh, cudaStream_t st) {
     if (sh->upPairs == sh->pairs.size() && sh->upPal == sh->pal.size() && sh->upCp == sh->cpTerms.size()) return kOk;
     ISAC_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
     cudaFree(sh->d_pairs);
@@ -819,8 +789,31 @@ int pmi_select_run_multi(PmiPlan* const* plans, int n, const float2* H, const do
     }
     if (live.empty()) return kOk;
     const int pr = prof_begin(ctx, kProfPmi, st);
-    // SINR of every candidate: one fused launch per dictionary, the direct kernel for the rest
     std::vector<char> done(live.size(), 0);
+    // report plans: SINR search with the subband accumulation fused in + selection from the chunk partials (comm_fused.cu)
+    for (size_t i = 0; i < live.size(); ++i) {
+        PmiPlan* p = live[i];
+        PmiShared* sh = p->sh;
+        int T, mb;
+        if (done[i] || !p->fused || !p->uniformW || p->direct || !sh || !sh->ok || !pmi_fused_pick(sh, p->cfg.nRx, &T, &mb)) continue;
+        std::vector<PmiPlan*> grp;
+        for (size_t j = i; j < live.size(); ++j) {
+            PmiPlan* q = live[j];
+            if (done[j] || !q->fused || !q->uniformW || q->direct || q->sh != sh || q->reK != p->reK || q->reL != p->reL ||
+                q->sbSizes != p->sbSizes || q->cqiSbSizes != p->cqiSbSizes)
+                continue;
+            grp.push_back(q);
+            done[j] = 2;
+        }
+        int s = pmi_fused_run(grp.data(), (int)grp.size(), H, nv, batch, st);
+        if (s) return s;
+    }
+    for (size_t i = 0; i < live.size(); ++i)
+        if (done[i] != 2) {
+            int s = pmi_plan_legacy_buffers(live[i]);
+            if (s) return s;
+        }
+    // SINR of every candidate: one fused launch per dictionary, the direct kernel for the rest
     for (size_t i = 0; i < live.size(); ++i) {
         if (done[i]) continue;
         PmiPlan* p = live[i];
@@ -862,7 +855,7 @@ int pmi_select_run_multi(PmiPlan* const* plans, int n, const float2* H, const do
         count_launches(ctx, 1);
     }
     // subband means + selection: one launch each for the plans that share the RE partition (all ranks of a CSI plan)
-    std::fill(done.begin(), done.end(), 0);
+    for (size_t i = 0; i < live.size(); ++i) done[i] = done[i] == 2 ? 2 : 0;
     for (size_t i = 0; i < live.size(); ++i) {
         if (done[i]) continue;
         PmiPlan* p = live[i];
@@ -969,6 +962,10 @@ int pmi_get_sinr_arrays(PmiPlan* p, int batch, double* sinrPerRE, double* sinrPe
     Ctx* ctx = p->ctx;
     cudaStream_t st = ctx->stream;
     const size_t nCand = p->tab.nCand(), nu = p->nLayers, nRE = p->reK.size();
+    if (!p->d_S && nRE) {
+        set_error(ctx, "SINRPerRE / SINRPerSubband are kept by dlPMISelect plans only (report plans never store them)");
+        return kErrUnsupported;
+    }
     // device layout [cand][layer][RE|SB][batch] -> host MATLAB layout [RE|SB x layer x cand x batch]
     auto fetch = [&](const double* dsrc, size_t n3, double* dst) -> int {
         std::vector<double> tmp(nCand * nu * n3 * batch);
@@ -1202,24 +1199,33 @@ int ul_pmi_select_run(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int
     return s;
 }
 
-// A UL report whose kernels and result copy are enqueued but whose host tail has not run yet (one per context)
+// UL state of one context: the report whose kernels and result copy are enqueued but whose host tail has not run yet,
+// and the uploaded PUSCH codebooks / band limits.  Owned by the context (Ctx::ulState) and freed with it, so that a
+// context created later at the same address (MEX mexAtExit + re-create, another device) never inherits stale buffers.
+struct UlCache { int nu, P, K, band; double2* dW; int* dIdx; };
 struct UlPending {
-    Ctx* ctx = nullptr;
     bool active = false, launched = false;
     int batch = 0, nSB = 0, nT = 0;
     UlPmiResult proto;
     double* hBands = nullptr;   // pinned [nSB x nT x batch]
     size_t hBytes = 0;
     cudaEvent_t ready = nullptr;
+    std::vector<UlCache> cache;
 };
-static std::vector<UlPending*> g_ulPending;
+static void ul_state_free(void* s) {
+    UlPending* u = static_cast<UlPending*>(s);
+    if (!u) return;
+    if (u->hBands) cudaFreeHost(u->hBands);
+    if (u->ready) cudaEventDestroy(u->ready);
+    for (UlCache& e : u->cache) { cudaFree(e.dW); cudaFree(e.dIdx); }
+    delete u;
+}
 static UlPending* ul_pending(Ctx* ctx) {
-    for (UlPending* u : g_ulPending)
-        if (u->ctx == ctx) return u;
-    UlPending* u = new UlPending();
-    u->ctx = ctx;
-    g_ulPending.push_back(u);
-    return u;
+    if (!ctx->ulState) {
+        ctx->ulState = new UlPending();
+        ctx->ulFree = ul_state_free;
+    }
+    return static_cast<UlPending*>(ctx->ulState);
 }
 
 int ul_pmi_select_batch(Ctx* ctx, int nu, const float2* hest, int K, int nSym, int R, int P, double noiseEst, int bandSize,
@@ -1262,17 +1268,16 @@ int ul_pmi_select_batch_enqueue(Ctx* ctx, int nu, const float2* hest, int K, int
         return kOk;
     }
     // the PUSCH codebook of (nu, P) and the band limits are uploaded once per context and cached
-    struct UlCache { Ctx* ctx; int nu, P, K, band; double2* dW; int* dIdx; };
-    static std::vector<UlCache> cache;
+    std::vector<UlCache>& cache = pend->cache;
     UlCache* uc = nullptr;
     for (auto& e : cache)
-        if (e.ctx == ctx && e.nu == nu && e.P == P && e.K == K && e.band == bandSize) uc = &e;
+        if (e.nu == nu && e.P == P && e.K == K && e.band == bandSize) uc = &e;
     if (!uc) {
         std::vector<std::complex<double>> Wc;
         materialize_codebook(t, Wc);  // [P][nu][nT]
         std::vector<double2> Wd(Wc.size());
         for (size_t i = 0; i < Wc.size(); ++i) Wd[i] = make_double2(Wc[i].real(), Wc[i].imag());
-        UlCache e{ctx, nu, P, K, bandSize, nullptr, nullptr};
+        UlCache e{nu, P, K, bandSize, nullptr, nullptr};
         ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)&e.dW, sizeof(double2) * Wd.size()));
         ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)&e.dIdx, sizeof(int) * 2 * nSB));
         ISAC_CUDA_CHECK(ctx, cudaMemcpy(e.dW, Wd.data(), sizeof(double2) * Wd.size(), cudaMemcpyHostToDevice));

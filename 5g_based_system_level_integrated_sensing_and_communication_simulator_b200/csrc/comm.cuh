@@ -84,9 +84,25 @@ struct PmiPlan {
     void* pin = nullptr;            // pinned staging of the selection results
     size_t pinBytes = 0;
     std::vector<uint8_t> sbHasRE, cqiSbHasRE;
+    // fused report path (comm_fused.cu): subband sums accumulated inside the SINR kernel, SINRPerRE never stored
+    bool fused = false;             // requested by the owner (RI / CQI report plans); dlPMISelect plans keep SINRPerRE for `info`
+    bool uniformW = false;          // the mean-of-means weights are uniform inside every PMI and CQI subband
+    std::vector<int> sbStartH, cqiStartH;   // host copies of d_sbStart / d_cqiStart
+    std::vector<double> wH, cwH;            // host copies of d_reW / d_reCqiW
+    int fG = 0, nChunks = 0;        // REs per chunk the chunk tables were built for, number of chunks
+    int* d_chunkRe0 = nullptr; int* d_chunkN = nullptr;
+    int* d_sbChunk = nullptr; int* d_cqiChunk = nullptr;    // [nSB+1] / [nCqiSB+1] chunk ranges
+    double* d_sbW = nullptr; double* d_cqiSbW = nullptr;   // per-subband RE weight
+    double* d_part = nullptr;       // [maxBatch][nChunks][nLayers][nCand] chunk partial sums
 };
 
-int pmi_plan_create(Ctx* ctx, const CsiConfig& cfg, int nLayers, int maxBatch, PmiPlan** out, PmiShared* share = nullptr);
+int pmi_plan_create(Ctx* ctx, const CsiConfig& cfg, int nLayers, int maxBatch, PmiPlan** out, PmiShared* share = nullptr,
+                    bool fused = false);
+// fused report path (comm_fused.cu)
+int pair_sync_dict(Ctx* ctx, PmiShared* sh, cudaStream_t st);
+int pmi_fused_pick(const PmiShared* sh, int R, int* threads, int* minb);
+int pmi_plan_prepare_fused(PmiPlan* p, int G);
+int pmi_fused_run(PmiPlan* const* grp, int n, const float2* H, const double* nVar, int batch, cudaStream_t st);
 void pmi_plan_destroy(PmiPlan* p);
 void pmi_plan_use_arena(PmiPlan* p, char* dev, char* host);
 // H: device complex64 [K x L x nRx x P x batch]; nVar: host [batch]

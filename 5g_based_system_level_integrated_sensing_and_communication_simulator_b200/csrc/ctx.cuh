@@ -25,6 +25,9 @@ struct Ctx {
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> eventPool;
     long long launches = 0;
+    // per-context state of the UL TPMI path (pending report + codebook / band-limit cache, comm.cu); freed by isac_destroy
+    void* ulState = nullptr;
+    void (*ulFree)(void*) = nullptr;
 };
 
 // grow-only pinned host / device scratch buffers owned by the context

@@ -27,7 +27,8 @@ struct SensePlan {
     // sense_fft2d_collect waits on `ready` only -- not on work enqueued later on the stream -- and never copies again:
     //   counts [pages] | L [B] | nPeaks [B] | status [B] | peakLoc [kMaxPeaks x B] | det [detCap x pages] | peak [detCap x pages]
     // Only the first detCap detections of every (antenna, map-set) page are staged; a page with more falls back to a
-    // direct copy in collect.
+    // direct copy in collect -- valid because the next run of the SAME plan may only be enqueued after collect (one staging
+    // buffer, one device detection list per plan; include/isac_b200.h states the contract).
     char* h_stage = nullptr;
     int detCap = 0;
     cudaEvent_t ready = nullptr;

@@ -155,7 +155,10 @@ isac_rdm_plan* isac_sense_plan_rdm(isac_sense_plan* plan);
 int isac_fft2d_dev(isac_sense_plan* plan, const void* rxGrid, const void* txGrid, int32_t batch, float* rdPower);
 /* fetch estResults of the last run: for map-set b, rngEst[b*maxOut + i], i < nRng[b] (unique,'stable'
  * of the per-antenna peak-sorted lists, fft2D.m:89-102); velEst likewise; aziEst[b*ISAC_MAX_PEAKS+i];
- * status[b] = ISAC_ERR_NUM_DETS_ZERO when nothing was detected (reference: error -> senResults = NaN). */
+ * status[b] = ISAC_ERR_NUM_DETS_ZERO when nothing was detected (reference: error -> senResults = NaN).
+ * Waits only for the result copies staged behind that run, so OTHER work (another plan's kernels, CSI reports) may
+ * already be enqueued behind it; the next isac_fft2d_dev of the SAME plan must come after this call (one staging
+ * buffer and one detection list per plan). */
 int isac_fft2d_collect(isac_sense_plan* plan, int32_t batch, int32_t maxOut, double* rngEst, int32_t* nRng,
                        double* velEst, int32_t* nVel, double* aziEst, int32_t* nAzi, int32_t* L,
                        int32_t* status);

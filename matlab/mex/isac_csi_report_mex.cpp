@@ -5,6 +5,9 @@
  *   H: single complex [K x L x nRx x P]; CQI [cqiRows x 2] (second codeword column NaN when nLayers <= 4). */
 #include "isac_mex_common.h"
 
+static PlanCache<isac_csi_plan> g_plans(isac_csi_plan_destroy);
+static void drop_plans(void) { g_plans.clear(); }
+
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (nrhs < 6) mexErrMsgIdAndTxt("isac:csiReport:nargin", "six or seven inputs required");
     const char* fn = "csiReport";
@@ -16,8 +19,14 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     const int mode = (int)mxGetScalar(prhs[5]);
     const int nLayers = nrhs > 6 ? (int)mxGetScalar(prhs[6]) : 0;
     CsiCfg cs(prhs[0], dim_of(H, 2));
-    isac_csi_plan* plan = nullptr;
-    isac_mex_check(isac_csi_plan_create(isac_mex_ctx(), &cs.c, 1, &plan), fn);
+    isac_ctx* ctx = isac_mex_ctx();
+    g_plan_cleanup = drop_plans;
+    const std::string key = cs.key();
+    isac_csi_plan* plan = g_plans.find(key);          /* one plan per report configuration, reused by every later call */
+    if (!plan) {
+        isac_mex_check(isac_csi_plan_create(ctx, &cs.c, 1, &plan), fn);
+        g_plans.put(key, plan);
+    }
     const int nSBmax = cs.c.nSizeBWP + 1;          /* upper bound on the subband count */
     std::vector<double> RI(1, mxGetNaN()), i1(3), i2(nSBmax), cqi(2 * (size_t)(nSBmax + 1), mxGetNaN()), sinrCW(2 * (size_t)(nSBmax + 1));
     int32_t cqiRows = 0;
@@ -34,7 +43,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
             rc = isac_csi_report_dev(plan, Hd.p, &nVar, 1, mxGetDoubles(tab), (int32_t)mxGetNumberOfElements(tab), rankCap, RI.data(),
                                      i1.data(), i2.data(), cqi.data(), &cqiRows);
     }
-    isac_csi_plan_destroy(plan);
+    if (rc) g_plans.drop(plan);
     isac_mex_check(rc, fn);
     int nSB = 1;                                   /* PMI subbands of the report (dlPMISelect.m:465-501) */
     if (cs.c.pmiSubband && cs.c.subbandSize > 0 && cs.c.nSizeBWP >= 24)   /* first subband ends on a SubbandSize boundary */

@@ -9,6 +9,9 @@
  * Marshals communication.phyLayer.dlPMISelect (+communication/+phyLayer/dlPMISelect.m:1). */
 #include "isac_mex_common.h"
 
+static PlanCache<isac_pmi_plan> g_plans(isac_pmi_plan_destroy);
+static void drop_plans(void) { g_plans.clear(); }
+
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (nrhs != 4) mexErrMsgIdAndTxt("isac:dlPMISelect:nargin", "four inputs required");
     const char* fn = "dlPMISelect";
@@ -19,8 +22,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     CsiCfg cs(prhs[0], dim_of(H, 2));
     if (dim_of(H, 0) != cs.c.K || dim_of(H, 1) != cs.c.L || dim_of(H, 3) != cs.c.nPorts)
         mexErrMsgIdAndTxt("nr5g:hDLPMISelect:InvalidChannelDims", "H must be K-by-L-by-nRxAnts-by-NumCSIRSPorts");
-    isac_pmi_plan* plan = nullptr;   /* a production gateway caches the plan per report configuration */
-    isac_mex_check(isac_pmi_plan_create(isac_mex_ctx(), &cs.c, nLayers, 1, &plan), fn);
+    isac_ctx* ctx = isac_mex_ctx();
+    g_plan_cleanup = drop_plans;
+    std::string key = cs.key();
+    key_add(key, nLayers);
+    isac_pmi_plan* plan = g_plans.find(key);          /* one plan per (report configuration, rank) */
+    if (!plan) {
+        isac_mex_check(isac_pmi_plan_create(ctx, &cs.c, nLayers, 1, &plan), fn);
+        g_plans.put(key, plan);
+    }
     int32_t dims[4] = {0, 0, 0, 0}, nSB = 0, nCqiSB = 0, nRE = 0;
     isac_mex_check(isac_pmi_plan_info(plan, dims, &nSB, &nCqiSB, &nRE, nullptr, nullptr), fn);
     std::vector<int32_t> reK(nRE), reL(nRE);
@@ -36,7 +46,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         if (!rc) rc = isac_dl_pmi_collect(plan, 1, i1.data(), i2.data(), nullptr);
         if (!rc) rc = isac_dl_pmi_get_info(plan, 1, S.data(), Sb.data());
     }
-    isac_pmi_plan_destroy(plan);
+    if (rc) g_plans.drop(plan);
     isac_mex_check(rc, fn);
     std::vector<double> W(2 * (size_t)cs.c.nPorts * nLayers * nCand);
     int32_t wd[9];

@@ -10,8 +10,10 @@
 #include <vector>
 
 static isac_ctx* g_ctx = nullptr;
+static void (*g_plan_cleanup)(void) = nullptr;   /* set by the gateway that caches plans: they go before the context */
 
 static void isac_mex_cleanup(void) {
+    if (g_plan_cleanup) g_plan_cleanup();
     if (g_ctx) { isac_destroy(g_ctx); g_ctx = nullptr; }
 }
 
@@ -30,6 +32,49 @@ static void isac_mex_check(int st, const char* fn) {
     if (st == ISAC_OK) return;
     const std::string id = std::string("isac:") + fn + ":status" + std::to_string(st);
     mexErrMsgIdAndTxt(id.c_str(), "%s", isac_last_error(g_ctx));
+}
+
+/* Plans cached per configuration for the life of the MEX file (the context is mexLock'ed): the simulator calls a gateway
+ * once per slot / CSI-RS occasion with the same configuration, and creating a plan uploads codebook tables, builds the
+ * Gram-pair dictionary and allocates the device arenas.  Keyed by the serialised configuration; at most kMax plans are
+ * kept (least recently used goes first). */
+template <class Plan>
+struct PlanCache {
+    struct Entry { std::string key; Plan* plan; };
+    static const size_t kMax = 8;
+    std::vector<Entry> entries;
+    int (*destroy)(Plan*);
+    explicit PlanCache(int (*d)(Plan*)) : destroy(d) {}
+    Plan* find(const std::string& key) {
+        for (size_t i = 0; i < entries.size(); ++i)
+            if (entries[i].key == key) {
+                Entry hit = entries[i];
+                entries.erase(entries.begin() + i);
+                entries.push_back(hit);          /* most recently used at the back */
+                return hit.plan;
+            }
+        return nullptr;
+    }
+    void put(const std::string& key, Plan* plan) {
+        if (entries.size() >= kMax) { destroy(entries.front().plan); entries.erase(entries.begin()); }
+        entries.push_back(Entry{key, plan});
+    }
+    void drop(Plan* plan) {                       /* a plan that returned an error is not reused */
+        for (size_t i = 0; i < entries.size(); ++i)
+            if (entries[i].plan == plan) { destroy(plan); entries.erase(entries.begin() + i); return; }
+    }
+    void clear() {
+        for (Entry& e : entries) destroy(e.plan);
+        entries.clear();
+    }
+};
+template <class T>
+static void key_add(std::string& k, const T& v) { k.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
+template <class T>
+static void key_add(std::string& k, const std::vector<T>& v) {
+    const size_t n = v.size();
+    key_add(k, n);
+    if (n) k.append(reinterpret_cast<const char*>(v.data()), n * sizeof(T));
 }
 
 static const mxArray* field(const mxArray* s, const char* name) {
@@ -147,5 +192,15 @@ struct CsiCfg {
         c.nRE = (int32_t)reK.size(); c.reK = reK.data(); c.reL = reL.data();
         const mxArray* np = mxGetField(cfg, 0, "nPanels");   /* optional: Ng of a Type1MultiPanel report (dlPMISelect.m:629-644) */
         c.nPanels = np ? (int32_t)mxGetScalar(np) : 0;
+    }
+    /* serialised configuration: the key of the gateways' plan caches */
+    std::string key() const {
+        std::string k;
+        const int32_t f[] = {c.nPorts, c.N1, c.N2, c.O1, c.O2, c.codebookMode, c.nSizeBWP, c.nStartBWP, c.subbandSize, c.pmiSubband,
+                             c.cqiSubband, c.K, c.L, c.nRx, c.nPanels};
+        for (int32_t v : f) key_add(k, v);
+        for (int i = 0; i < 8; ++i) key_add(k, c.riRestriction[i]);
+        key_add(k, csr); key_add(k, i2r); key_add(k, reK); key_add(k, reL);
+        return k;
     }
 };

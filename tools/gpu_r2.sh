@@ -1,0 +1,49 @@
+#!/bin/bash
+# One entry point for the round-2 GPU calls: tools/gpu_r2.sh <step> ; outputs under gpurun_out/r2_<step>*
+set -u
+mkdir -p gpurun_out
+step=$1
+case $step in
+pmi1)
+  (timeout 900 python -m pytest tests/test_comm_gpu.py tests/test_cfg23_gpu.py tests/test_golden_gpu.py tests/test_chest_gpu.py tests/test_mex_mock_gpu.py -m gpu -q -x 2>&1 | tail -15) > gpurun_out/r2_pmi1_tests.log
+  cat gpurun_out/r2_pmi1_tests.log
+  for v in "ISAC_PMI_FUSED=0" "ISAC_PAIR_G=1" "ISAC_PAIR_G=2" "ISAC_PAIR_G=2 ISAC_PAIR_T=256" "ISAC_PAIR_G=4" "ISAC_PAIR_G=4 ISAC_PAIR_T=384"; do
+    env $v timeout 300 python tools/dev_pmi_variants.py 2>&1 | tail -3
+  done > gpurun_out/r2_pmi1_variants.log
+  cat gpurun_out/r2_pmi1_variants.log
+  ;;
+pmi2)
+  for v in "ISAC_PAIR_G=1" "ISAC_PAIR_G=4" "ISAC_PAIR_G=4 ISAC_PAIR_T=384"; do
+    echo "== $v"
+    env $v timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pmi_ -s 8 -c 4 --csv python tools/dev_pmi_variants.py 2>/dev/null | grep -E "pmi_" | awk -F'","' '{print $5, $NF}' | cut -c1-160
+  done > gpurun_out/r2_pmi2_launches.log 2>&1
+  cat gpurun_out/r2_pmi2_launches.log
+  ISAC_PAIR_G=4 ISAC_PAIR_T=384 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pmi_pair_fused -s 4 -c 1 -o gpurun_out/r2_pmi2_fused python tools/dev_pmi_variants.py > /dev/null 2>&1
+  ls -la gpurun_out/
+  ;;
+pmi3)
+  (timeout 900 python -m pytest tests/test_comm_gpu.py tests/test_cfg23_gpu.py tests/test_golden_gpu.py -m gpu -q -x 2>&1 | tail -5) > gpurun_out/r2_pmi3_tests.log
+  cat gpurun_out/r2_pmi3_tests.log
+  for v in "ISAC_PMI_FUSED=0" "ISAC_PAIR_G=1" "ISAC_PAIR_G=4" "ISAC_PAIR_G=4 ISAC_PAIR_T=384"; do
+    env $v timeout 300 python tools/dev_pmi_variants.py 2>&1 | tail -2 | head -1
+    env $v timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pmi_ -s 8 -c 3 --csv python tools/dev_pmi_variants.py 2>/dev/null | grep -E "pmi_" | awk -F'","' '{print $5, $NF}' | cut -c1-160
+  done > gpurun_out/r2_pmi3_variants.log 2>&1
+  cat gpurun_out/r2_pmi3_variants.log
+  ;;
+pmi4)
+  (timeout 900 python -m pytest tests/test_comm_gpu.py tests/test_cfg23_gpu.py tests/test_golden_gpu.py -m gpu -q -x 2>&1 | tail -5) > gpurun_out/r2_pmi4_tests.log
+  cat gpurun_out/r2_pmi4_tests.log
+  for v in "ISAC_PAIR_G=1" "ISAC_PAIR_G=2" "ISAC_PAIR_G=4" "ISAC_PAIR_G=4 ISAC_PAIR_T=384" "ISAC_PAIR_G=4 ISAC_PAIR_T=384 ISAC_PAIR_BP=0"; do
+    env $v timeout 300 python tools/dev_pmi_variants.py 2>&1 | tail -2 | head -1
+    env $v timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pmi_ -s 8 -c 2 --csv python tools/dev_pmi_variants.py 2>/dev/null | grep -E "pmi_" | awk -F'","' '{print $5, $NF}' | cut -c1-160
+  done > gpurun_out/r2_pmi4_variants.log 2>&1
+  cat gpurun_out/r2_pmi4_variants.log
+  ;;
+full)
+  (timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -8) > gpurun_out/r2_full_tests.log
+  cat gpurun_out/r2_full_tests.log
+  timeout 600 python bench.py > gpurun_out/r2_full_bench.json 2> gpurun_out/r2_full_bench.err
+  tail -n 3 gpurun_out/r2_full_bench.err; cat gpurun_out/r2_full_bench.json | cut -c1-1500
+  ;;
+*) echo "unknown step $step"; exit 1;;
+esac
