@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import channelModels, phyLayer  # noqa: F401
+from . import channelModels, pathlossModels, phyLayer  # noqa: F401
 from .phyLayer import _csi_struct, _validate_report_config
 from .. import _lib
 

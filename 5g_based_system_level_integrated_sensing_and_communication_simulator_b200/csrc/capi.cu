@@ -10,6 +10,7 @@
 #include "los.cuh"
 #include "comm.cuh"
 #include "cdl.cuh"
+#include "link.cuh"
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -728,6 +729,41 @@ int isac_mono_static_sensing_host(isac_ctx* h, const isac_echo_config* cfg, cons
     ISAC_CUDA_CHECK(c, cudaMemcpyAsync(echoHost, dOut, gb, cudaMemcpyDeviceToHost, c->stream));
     ISAC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     if (nSymOut) *nSymOut = n;
+    return ISAC_OK;
+}
+
+// ---- link budget -------------------------------------------------------------------------------
+int isac_pathloss_host(isac_ctx* h, int32_t scenario, double fcHz, int32_t nLinks, const double* bsPos, const double* uePos,
+                       const int32_t* los, double* plDb) {
+    if (!h) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(h->c.device);
+    return pathloss_run(&h->c, scenario, fcHz, nLinks, bsPos, uePos, los, plDb, h->c.stream);
+}
+
+int isac_link_budget_dev(isac_ctx* h, void* H, int64_t elemsPerLink, int32_t nLinks, const double* plDb, double rxGainDb) {
+    if (!h) return ISAC_ERR_INVALID_ARG;
+    cudaSetDevice(h->c.device);
+    return link_scale_run(&h->c, (float2*)H, elemsPerLink, nLinks, plDb, rxGainDb, h->c.stream);
+}
+
+int isac_thermal_noise_power(double noiseFigureDb, double temperatureK, double sampleRate, double* Nt) {
+    if (!Nt || !(sampleRate > 0.0)) return ISAC_ERR_INVALID_ARG;
+    const double nf = std::pow(10.0, noiseFigureDb / 10.0);
+    *Nt = 1.380649e-23 * (temperatureK + 290.0 * (nf - 1.0)) * sampleRate;   // uePhy.m:945-947
+    return ISAC_OK;
+}
+
+int isac_dft_channel_matrix(int32_t nTx, int32_t nRx, double* H) {
+    if (nTx < 1 || nRx < 1 || !H) return ISAC_ERR_INVALID_ARG;
+    const int m = nTx > nRx ? nTx : nRx;
+    // the rows (or columns) of the truncated DFT matrix stay orthogonal with norm sqrt(m): its 2-norm is sqrt(m)
+    const double inv = 1.0 / std::sqrt((double)m), w = -2.0 * 3.14159265358979323846 / m;
+    for (int r = 0; r < nRx; ++r)
+        for (int t = 0; t < nTx; ++t) {
+            const double ph = w * (double)((long long)t * r % m);
+            H[2 * (t + (size_t)nTx * r)] = std::cos(ph) * inv;
+            H[2 * (t + (size_t)nTx * r) + 1] = std::sin(ph) * inv;
+        }
     return ISAC_OK;
 }
 

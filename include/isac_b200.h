@@ -406,6 +406,26 @@ int isac_cdl_set_kernel(isac_cdl_channel* ch, int32_t legacyMma);
 int isac_cdl_generate_batch_dev(isac_cdl_channel* const* ch, int32_t n, int32_t K, double scsHz, int32_t L,
                                 const double* symTime, const double* t0, void* H);
 
+/* ---- link budget of the channel application step (SURVEY 8(a) row a16 tail, 8(f) row 4) --------------------------------
+ * pathLoss = communication.pathlossModels.config5GNRModels(scenario, fc, los, bsPosition, uePosition)
+ *   (+communication/+pathlossModels/config5GNRModels.m:27-36 -> nrPathLoss: TR 38.901 Table 7.4.1-1, no shadow fading,
+ *   EnvironmentHeight 1 m, BuildingHeight 5 m, StreetWidth 20 m) and configFreeSpaceModel (configFreeSpaceModel.m:1-8),
+ * for nLinks links at once (call sites uePhy.m:743-747, gNBPhy.m:852-856).  bsPos / uePos: host double [nLinks x 3] row-major
+ * (x, y, z of each link); los: host int32 [nLinks] (ignored for ISAC_PL_FSPL); plDb: host double [nLinks].
+ * Identical positions give 0 dB (config5GNRModels.m:32-33).  The InF-* scenarios are not built (ISAC_ERR_INVALID_ARG). */
+enum { ISAC_PL_UMA = 0, ISAC_PL_UMI = 1, ISAC_PL_RMA = 2, ISAC_PL_INH = 3, ISAC_PL_FSPL = 4 };
+int isac_pathloss_host(isac_ctx* ctx, int32_t scenario, double fcHz, int32_t nLinks, const double* bsPos, const double* uePos,
+                       const int32_t* los, double* plDb);
+/* rxWaveform = db2mag(-pathLoss)*rxWaveform; applyRxGain (uePhy.m:748-751, :935-940) on the frequency-domain channel matrices
+ * of nLinks links: H device complex64 [elemsPerLink x nLinks], scaled in place by 10^((rxGainDb - plDb[link])/20). */
+int isac_link_budget_dev(isac_ctx* ctx, void* H, int64_t elemsPerLink, int32_t nLinks, const double* plDb, double rxGainDb);
+/* applyThermalNoise (uePhy.m:942-950, gNBPhy.m:1100-1108): Nt = k (T + 290 (10^(NF/10) - 1)) fs in watts -- the noise variance
+ * per complex sample (and, with the unitary OFDM demodulation scaling, per resource element).  Pure host code. */
+int isac_thermal_noise_power(double noiseFigureDb, double temperatureK, double sampleRate, double* Nt);
+/* Channel matrix used when no CDL model is attached (uePhy.m:735-739): H = fft(eye(max(nTx,nRx))); H = H(1:nTx,1:nRx)/norm(H).
+ * H: host complex128 [nTx x nRx] column-major.  Pure host code. */
+int isac_dft_channel_matrix(int32_t nTx, int32_t nRx, double* H);
+
 /* ---- channel estimation from reference signals ------------------------------------------------
  * [Hest, nVar] = nrChannelEstimate(rxGrid, refInd, refSym, 'CDMLengths', [FD TD] [, 'AveragingWindow', [F T]]) -- the 5G
  * Toolbox call the reference makes right before the COMM hot path (+communication/+phyLayer/uePhy.m:897 CSI-RS with

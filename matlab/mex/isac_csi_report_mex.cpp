@@ -1,8 +1,10 @@
-/* [RI, i1, i2, CQI] = isac_csi_report_mex(cfg, H, nVar, SINRTable, rankCap, mode [, nLayers])
+/* [RI, i1, i2, CQI, SINRPerSubbandPerCW] = isac_csi_report_mex(cfg, H, nVar, SINRTable, rankCap, mode [, nLayers])
  *   mode 0: fused UE report (uePhy.m:900-907): RI = min(riSelect(..), rankCap), then cqiSelect at that rank
  *   mode 1: [RI,PMISet] = riSelect(carrier,csirs,reportConfig,H,nVar)            (riSelect.m:1; CQI = [])
  *   mode 2: [CQI,PMISet] = cqiSelect(carrier,csirs,reportConfig,nLayers,H,nVar,SINRTable) (cqiSelect.m:1; RI = nLayers)
- *   H: single complex [K x L x nRx x P]; CQI [cqiRows x 2] (second codeword column NaN when nLayers <= 4). */
+ *   H: single complex [K x L x nRx x P]; CQI [cqiRows x 2] (second codeword column NaN when nLayers <= 4).
+ *   SINRPerSubbandPerCW (mode 2 only, else []): [rows x 2] linear SINR per codeword, wideband value first when there is more
+ *   than one CQI subband (cqiSelect.m:610-633). */
 #include "isac_mex_common.h"
 
 static PlanCache<isac_csi_plan> g_plans(isac_csi_plan_destroy);
@@ -52,4 +54,11 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (nlhs > 1) plhs[1] = double_array({3, 1}, i1.data());
     if (nlhs > 2) plhs[2] = double_array({(mwSize)nSB, 1}, i2.data());
     if (nlhs > 3) plhs[3] = double_array({(mwSize)cqiRows, 2}, cqi.data());
+    if (nlhs > 4) {
+        int nCqiSB = 1;                            /* CQI subbands: the same partition rule with the CQI mode */
+        if (cs.c.cqiSubband && cs.c.subbandSize > 0 && cs.c.nSizeBWP >= 24)
+            nCqiSB = (cs.c.nStartBWP % cs.c.subbandSize + cs.c.nSizeBWP + cs.c.subbandSize - 1) / cs.c.subbandSize;
+        const int rowsFull = nCqiSB > 1 ? nCqiSB + 1 : 1;
+        plhs[4] = mode == 2 ? double_array({(mwSize)rowsFull, 2}, sinrCW.data()) : mxCreateDoubleMatrix(0, 0, mxREAL);
+    }
 }

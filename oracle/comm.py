@@ -759,42 +759,57 @@ def sinr_per_re_vectorized(cfg, re_k, re_l, n_layers, H, n_var):
     return S.reshape((Hs.shape[0], n_layers) + sizes, order="F"), W
 
 
-def csi_report_vectorized(cfg, re_k, re_l, H, n_var, sinr_table, rank_cap=4):
-    """riSelect + cqiSelect (uePhy.m:900-907) using the vectorised SINR kernel; selection logic identical to
-    dl_pmi_select / ri_select / cqi_select above (they are re-used through a monkey-patched SINR array)."""
+def pmi_at_rank_vectorized(cfg, re_k, re_l, r, H, n_var):
+    """dlPMISelect at rank r (dlPMISelect.m:385-501) from the vectorised SINR array: (PMISet, SINRPerSubband at the reported
+    PMI [nSB x r]).  Same selection logic as dl_pmi_select above."""
     re_k = np.asarray(re_k, int)
-    re_l = np.asarray(re_l, int)
     n_sb, sb_sizes = subband_info(cfg["PMIMode"], cfg["NStartBWP"], cfg["NSizeBWP"], cfg["SubbandSize"])
+    S, _ = sinr_per_re_vectorized(cfg, re_k, re_l, r, H, n_var)
+    sizes = S.shape[2:]
+    total = matlab_round4(np.nansum(S, axis=(0, 1)))
+    lin = int(np.flatnonzero(total.reshape(-1, order="F") == total.max())[0])
+    i2, i11, i12, i13 = np.unravel_index(lin, sizes, order="F")
+    i2s, sel = np.full(n_sb, np.nan), np.full((n_sb, r), np.nan)
+    start = 0
+    for sb in range(n_sb):
+        m = (re_k >= start * 12 + 1) & (re_k <= (start + sb_sizes[sb]) * 12)
+        if m.any():
+            sub = np.nanmean(S[m][:, :, :, i11, i12, i13], axis=0)           # [nu, n2] (single CSI-RS symbol)
+            t = matlab_round4(np.nansum(sub, axis=0))
+            i2s[sb] = int(np.argmax(t)) + 1
+            sel[sb] = sub[:, int(i2s[sb]) - 1]
+        start += sb_sizes[sb]
+    return {"i1": np.array([i11 + 1, i12 + 1, i13 + 1.0]), "i2": i2s}, sel
+
+
+def cqi_from_subband_sinr(sel, rank, sinr_table):
+    """cqiSelect.m:610-653 from SINRPerSubband at the reported PMI: per-codeword sums (nrLayerDemap), wideband row = mean over
+    the subbands when there is more than one, CQI look-up.  Returns absolute CQIs [rows x nCW]."""
+    n_sb = sel.shape[0]
+    n_cw = int(math.ceil(rank / 4))
+    cw = np.stack([layer_demap_sums(sel[s]) if not np.any(np.isnan(sel[s])) else np.full(n_cw, np.nan) for s in range(n_sb)])
+    full = np.vstack([np.nanmean(cw, axis=0), cw]) if n_sb > 1 else cw
+    return np.vectorize(lambda x: get_cqi(x, sinr_table))(full)
+
+
+def csi_report_vectorized(cfg, re_k, re_l, H, n_var, sinr_table, rank_cap=4, return_all=False):
+    """riSelect + cqiSelect (uePhy.m:900-907) using the vectorised SINR kernel; selection logic identical to
+    dl_pmi_select / ri_select / cqi_select above.  return_all: also the unclipped RI and every rank's (PMISet, SINR)."""
     R, P = H.shape[2], H.shape[3]
     best, RI, keep = -np.inf, np.nan, {}
     for r in range(1, min(R, P) + 1):
         if not cfg["RIRestriction"][r - 1]:
             continue
-        S, W = sinr_per_re_vectorized(cfg, re_k, re_l, r, H, n_var)
-        sizes = S.shape[2:]
-        total = matlab_round4(np.nansum(S, axis=(0, 1)))
-        lin = int(np.flatnonzero(total.reshape(-1, order="F") == total.max())[0])
-        i2, i11, i12, i13 = np.unravel_index(lin, sizes, order="F")
-        i2s, sel = np.full(n_sb, np.nan), np.full((n_sb, r), np.nan)
-        start = 0
-        for sb in range(n_sb):
-            m = (re_k >= start * 12 + 1) & (re_k <= (start + sb_sizes[sb]) * 12)
-            if m.any():
-                sub = np.nanmean(S[m][:, :, :, i11, i12, i13], axis=0)           # [nu, n2] (single CSI-RS symbol)
-                t = matlab_round4(np.nansum(sub, axis=0))
-                i2s[sb] = int(np.argmax(t)) + 1
-                sel[sb] = sub[:, int(i2s[sb]) - 1]
-            start += sb_sizes[sb]
+        pm, sel = pmi_at_rank_vectorized(cfg, re_k, re_l, r, H, n_var)
         with np.errstate(invalid="ignore"):
             layer = np.nanmean(sel * r, axis=0)
         tot_r = np.sum(layer[layer >= 1])
-        keep[r] = ({"i1": np.array([i11 + 1, i12 + 1, i13 + 1.0]), "i2": i2s}, sel)
+        keep[r] = (pm, sel)
         if tot_r > best + 0.1:
             best, RI = tot_r, r
     rank = int(min(RI, rank_cap))
     pm, sel = keep[rank]
-    n_cw = int(math.ceil(rank / 4))
-    cw = np.stack([layer_demap_sums(sel[s]) if not np.any(np.isnan(sel[s])) else np.full(n_cw, np.nan) for s in range(n_sb)])
-    full = np.vstack([np.nanmean(cw, axis=0), cw]) if n_sb > 1 else cw
-    cq = np.vectorize(lambda x: get_cqi(x, sinr_table))(full)
+    cq = cqi_from_subband_sinr(sel, rank, sinr_table)
+    if return_all:
+        return rank, pm, cq, RI, keep
     return rank, pm, cq

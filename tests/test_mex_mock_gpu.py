@@ -195,3 +195,95 @@ def test_dl_pmi_gateway_multi_panel(P):
     assert np.array_equal(i1u, pm["i1"])
     for sb, v in enumerate(i2.ravel()):
         assert np.array_equal([x + 1 for x in np.unravel_index(int(v) - 1, tuple(mp[0:3]), order="F")], pm["i2"][:, sb])
+
+
+def test_radar_channel_gateway(P):
+    """sensing.channelModels.basicRadarChannel through its gateway, incl. the all-NLoS error the reference turns into an
+    empty waveform (basicRadarChannel.m:59-64)."""
+    W = P.workloads
+    cell, car, wave = W.cell_config("tiny")
+    rp = P.sensing.radarParams(cell, car, wave)
+    _, txw = W.sensing_tx("tiny", 1)
+    noise = W.std_normal_complex(txw.shape, 2).astype(np.complex64)
+    txw32 = txw.astype(np.complex64)
+    nT = int(rp["nTargets"])
+    cfg = {"fc": float(rp["fc"]), "fs": float(rp["fs"]), "N0": float(rp["N0"]), "range": np.asarray(rp["range"], float).reshape(nT),
+           "velocity": np.asarray(rp["velocity"], float).reshape(nT),
+           "largeScaleFading": np.asarray(rp["largeScaleFading"], float).reshape(nT),
+           "steeringVec": np.asarray(rp["RxSteeringVec"], np.complex128).reshape(txw.shape[1], nT),
+           "los": np.asarray(cell["targetLoSConditions"], np.int32).reshape(nT)}
+    rx = M.call("isac_radar_channel_mex", 1, cfg, txw32, np.array([0], np.uint64), noise)
+    ref = P.sensing.channelModels.basicRadarChannel(txw32, rp, cell["targetLoSConditions"], noise=noise)
+    assert rx.dtype == np.complex64 and rx.shape == ref.shape and np.array_equal(rx, ref)
+    with pytest.raises(M.MexError) as e:
+        M.call("isac_radar_channel_mex", 1, dict(cfg, los=np.zeros(nT, np.int32)), txw32, np.array([0], np.uint64), noise)
+    assert e.value.identifier == "isac:basicRadarChannel:status6"
+
+
+def test_precoded_sinr_and_codebook_gateways(P):
+    ph = P.communication.phyLayer
+    rng = np.random.default_rng(12)
+    R, Pn, nu, B = 4, 4, 2, 37
+    H = (rng.standard_normal((R, Pn, B)) + 1j * rng.standard_normal((R, Pn, B))) / np.sqrt(2)
+    Wc = ph.puschCodebook(nu, Pn)[:, :, 3]
+    got = M.call("isac_precoded_sinr_mex", 1, H, 0.3, Wc)
+    ref = np.asarray(ph.precodedSINR(H, 0.3, Wc)).ravel()
+    assert got.shape == (B, 1) and np.array_equal(got.ravel(), ref)
+    one = M.call("isac_precoded_sinr_mex", 1, H[:, :, 0], 0.3, Wc)          # the reference's per-RE call (pmiSelect.m:52)
+    assert one.shape == (1, 1) and one[0, 0] == ref[0]
+    # gNB-side codebook copy (pmiType1SinglePanelCodebook.m), 16 ports rank 3: the copy's missing i13 index is reproduced
+    rc = {"PanelDimensions": (4, 2), "OverSamplingFactors": (4, 4), "CodebookMode": 1}
+    cfg = {"nPorts": 16.0, "N1": 4.0, "N2": 2.0, "O1": 4.0, "O2": 4.0, "codebookMode": 1.0, "nSizeBWP": 1.0, "nStartBWP": 0.0,
+           "subbandSize": 0.0, "pmiSubband": 0.0, "cqiSubband": 0.0, "K": 12.0, "L": 14.0, "subsetRestriction": np.zeros(0, np.uint8),
+           "i2Restriction": np.zeros(0, np.uint8), "riRestriction": np.ones(8, np.uint8), "reK": np.zeros(0, np.int32),
+           "reL": np.zeros(0, np.int32)}
+    for nl in (1, 3):
+        Wg = M.call("isac_codebook_mex", 1, cfg, float(nl), 1.0)
+        Wr = P.communication.pmiType1SinglePanelCodebook(rc, nl)
+        assert Wg.shape == Wr.shape and np.array_equal(Wg, Wr)
+    with pytest.raises(M.MexError) as e:
+        M.call("isac_codebook_mex", 1, dict(cfg, N1=3.0), 1.0, 1.0)           # 2*N1*N2 != nPorts
+    assert e.value.identifier == "isac:pmiType1SinglePanelCodebook:config"
+
+
+def test_cdl_gateway(P):
+    """communication.channelModels.cdlChannelMatrix: the gateway returns the same H as the Python mirror's channel object."""
+    cm = importlib.import_module(PKG + ".communication.channelModels")
+    K, scs = 24 * 12, 30e3
+    num = P.workloads.ofdm_numerology(24, 30)
+    st = np.ascontiguousarray(P.workloads.symbol_starts(num, 14) / num["SampleRate"], dtype=np.float64)
+    cfg = {"profile": 2.0, "delaySpread": 300e-9, "fc": 3.5e9, "maxDoppler": 5.0, "txSize": np.array([1, 4, 2], np.int32),
+           "rxSize": np.array([1, 1, 2], np.int32), "txPattern38901": 1.0, "rxPattern38901": 0.0, "seed": 73.0}
+    H = M.call("isac_cdl_mex", 1, cfg, float(K), scs, st.reshape(1, -1), 0.002)
+    ch = cm.CDLChannel("CDL-C", TransmitAntennaArraySize=(1, 4, 2), ReceiveAntennaArraySize=(1, 1, 2), Seed=73)
+    ref = ch.generate(K, scs, st, 0.002).cpu().numpy().transpose(3, 2, 1, 0)      # [nTx][nRx][L][K] -> [K x L x nRx x nTx]
+    assert H.dtype == np.complex64 and H.shape == ref.shape == (K, 14, 2, 8) and np.array_equal(H, ref)
+    H2 = M.call("isac_cdl_mex", 1, cfg, float(K), scs, st.reshape(1, -1), 0.002)  # second call: cached channel, same realisation
+    assert np.array_equal(H, H2)
+
+
+def test_cqi_gateway_info_output_and_plan_reuse(P):
+    """Mode 2 of the report gateway returns SINRPerSubbandPerCW for CQIInfo (cqiSelect.m:685); repeated calls with one
+    configuration reuse the cached plan and give identical results."""
+    ph = P.communication.phyLayer
+    rng = np.random.default_rng(33)
+    nrb, R, Pn, sbs = 24, 4, 8, 4
+    K = 12 * nrb
+    H = ((rng.standard_normal((K, 14, R, Pn)) + 1j * rng.standard_normal((K, 14, R, Pn))) / np.sqrt(2)).astype(np.complex64)
+    carrier = {"NSizeGrid": nrb, "NStartGrid": 0, "SymbolsPerSlot": 14}
+    csirs = {"NumCSIRSPorts": Pn, "NumRB": nrb, "RBOffset": 0, "SubcarrierLocations": 1, "SymbolLocations": 0, "Density": "one"}
+    rc = {"NSizeBWP": nrb, "NStartBWP": 0, "PanelDimensions": (2, 2), "CodebookMode": 1, "PMIMode": "Subband", "CQIMode": "Subband",
+          "SubbandSize": sbs}
+    _, info = ph.dlPMISelect(carrier, csirs, rc, 1, H, 0.1)
+    cfg = {"nPorts": float(Pn), "N1": 2.0, "N2": 2.0, "O1": 4.0, "O2": 4.0, "codebookMode": 1.0, "nSizeBWP": float(nrb),
+           "nStartBWP": 0.0, "subbandSize": float(sbs), "pmiSubband": 1.0, "cqiSubband": 1.0, "K": float(K), "L": 14.0,
+           "subsetRestriction": np.ones(64, np.uint8), "i2Restriction": np.ones(16, np.uint8), "riRestriction": np.ones(8, np.uint8),
+           "reK": info["reK"].astype(np.int32), "reL": info["reL"].astype(np.int32)}
+    table = np.asarray(P.communication.setupSINRtoCQIMappingTable()["downlinkSINR90pc"], float)
+    cq_ref, pm_ref, ci = ph.cqiSelect(carrier, csirs, rc, 2, H, 0.1, table)
+    outs = [M.call("isac_csi_report_mex", 5, cfg, H, 0.1, table, 0.0, 2.0, 2.0) for _ in range(3)]
+    for _, i1, i2, CQI, sbcw in outs:
+        assert np.array_equal(i1.ravel(), pm_ref["i1"]) and np.array_equal(i2.ravel(), pm_ref["i2"], equal_nan=True)
+        assert np.array_equal(CQI[:, :1], cq_ref, equal_nan=True)
+        assert sbcw.shape == (nrb // sbs + 1, 2)
+        assert np.array_equal(sbcw[:, :1], np.asarray(ci["SINRPerSubbandPerCW"]).reshape(-1, 1), equal_nan=True)

@@ -17,7 +17,8 @@ GATEWAYS = sorted(glob.glob(os.path.join(MEX, "*_mex.cpp")))
 def test_gateways_present():
     names = {os.path.basename(g) for g in GATEWAYS}
     assert {"isac_fft2d_mex.cpp", "isac_mono_static_mex.cpp", "isac_dl_pmi_mex.cpp", "isac_csi_report_mex.cpp",
-            "isac_ul_pmi_mex.cpp", "isac_prg_precode_mex.cpp", "isac_doa_mex.cpp", "isac_music2d_mex.cpp"} <= names
+            "isac_ul_pmi_mex.cpp", "isac_prg_precode_mex.cpp", "isac_doa_mex.cpp", "isac_music2d_mex.cpp",
+            "isac_radar_channel_mex.cpp", "isac_precoded_sinr_mex.cpp", "isac_codebook_mex.cpp", "isac_cdl_mex.cpp"} <= names
     text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     for n in re.findall(r"isac_\w+_mex\.cpp", text):
         assert n in names, f"INTEGRATION.md names {n}, which does not exist"
@@ -48,8 +49,58 @@ def test_shims_call_existing_gateways():
     shims = glob.glob(os.path.join(ROOT, "matlab", "+*", "**", "*.m"), recursive=True)
     assert shims
     for m in shims:
-        if os.path.basename(m).startswith("isac"):      # configuration helpers shared by the shims
-            continue
+        if os.path.basename(m).startswith("isac") or os.path.basename(m) == "validateDLPMIInputs.m":
+            continue                                    # configuration / validation helpers shared by the shims
         called = set(re.findall(r"\b(isac_\w+_mex)\b", open(m).read()))
         assert called, f"{m} calls no gateway"
         assert called <= names, (m, sorted(called - names))
+
+
+def _reference_functions():
+    """Package-qualified names of every function / class file of the reference (committed list; re-derived and compared when
+    the reference tree is mounted, so the list cannot go stale)."""
+    listed = set(open(os.path.join(ROOT, "tests", "golden", "reference_functions.txt")).read().split())
+    ref = "/root/reference"
+    if os.path.isdir(ref):
+        found = set()
+        for root, _, files in os.walk(ref):
+            parts = [p for p in os.path.relpath(root, ref).split(os.sep) if p != "."]
+            if parts and not all(p[0] in "+@" for p in parts):
+                continue
+            pk = ".".join(p[1:] for p in parts if p.startswith("+"))
+            found |= {(pk + "." if pk else "") + f[:-2] for f in files if f.endswith(".m")}
+        assert found == listed, "tests/golden/reference_functions.txt is stale"
+    return listed
+
+
+def _shim_functions():
+    out = set()
+    base = os.path.join(ROOT, "matlab")
+    for m in glob.glob(os.path.join(base, "+*", "**", "*.m"), recursive=True):
+        parts = os.path.relpath(m, base).split(os.sep)
+        out.add(".".join(p[1:] for p in parts[:-1]) + "." + parts[-1][:-2])
+    return out
+
+
+def test_every_function_a_shim_calls_exists():
+    """A shim may call (a) a gateway of matlab/mex, (b) a package function shipped under matlab/, (c) a package function of
+    the reference, (d) MATLAB / toolbox functions (unqualified names).  A package-qualified call that resolves to neither
+    tree would fail in MATLAB with 'Undefined function' (round-1 finding: validateDLPMIInputs)."""
+    known = _reference_functions() | _shim_functions()
+    shims = glob.glob(os.path.join(ROOT, "matlab", "+*", "**", "*.m"), recursive=True)
+    assert shims
+    for m in shims:
+        code = "\n".join(line.split("%")[0] for line in open(m).read().splitlines())   # strip comments
+        for call in re.findall(r"\b((?:communication|sensing|simulation|networkTopology|parameters|tools)(?:\.\w+)+)\s*\(", code):
+            assert call in known, f"{os.path.relpath(m, ROOT)} calls {call}, which exists neither under matlab/ nor in the reference"
+
+
+def test_kept_signatures_have_a_shim():
+    """Every kept-API function of SURVEY 8(b) whose arithmetic moved to the device has a same-named shim."""
+    shims = _shim_functions()
+    for name in ("sensing.monoStaticSensing", "sensing.channelModels.basicRadarChannel", "sensing.estimation.fft2D",
+                 "sensing.estimation.music2D", "sensing.estimation.doaEstimation.music", "communication.phyLayer.dlPMISelect",
+                 "communication.phyLayer.riSelect", "communication.phyLayer.cqiSelect", "communication.phyLayer.pmiSelect",
+                 "communication.phyLayer.precodedSINR", "communication.phyLayer.prgPrecode",
+                 "communication.pmiType1SinglePanelCodebook", "communication.phyLayer.validateDLPMIInputs"):
+        assert name in shims, name

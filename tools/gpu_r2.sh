@@ -45,5 +45,9 @@ full)
   timeout 600 python bench.py > gpurun_out/r2_full_bench.json 2> gpurun_out/r2_full_bench.err
   tail -n 3 gpurun_out/r2_full_bench.err; cat gpurun_out/r2_full_bench.json | cut -c1-1500
   ;;
+t1)
+  (timeout 1500 python -m pytest tests/test_cfg3_full_gpu.py tests/test_mex_mock_gpu.py -m gpu -q -x 2>&1 | tail -25) > gpurun_out/r2_t1_tests.log
+  cat gpurun_out/r2_t1_tests.log
+  ;;
 *) echo "unknown step $step"; exit 1;;
 esac
