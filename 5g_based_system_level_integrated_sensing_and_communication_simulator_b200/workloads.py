@@ -137,3 +137,104 @@ def std_normal_complex(shape, seed: int) -> np.ndarray:
     """randn(size)+1j*randn(size) stand-in (basicRadarChannel.m:68) with a fixed NumPy seed."""
     rng = np.random.default_rng(seed)
     return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 5: the openStreetMapCity scenario scaled to 19 gNBs / 100 UEs / 20 moving targets
+# ---------------------------------------------------------------------------------------------------------------------
+RADIO = {
+    # the shipped scenario's radio (+scenarios/openStreetMapCity.m:44-62): 100 MHz @ 30 kHz -> 273 PRB, 8-element dual-polarised
+    # ULA (16 Tx), 2-antenna UEs, row-5 CSI-RS (4 ports, setupCSIRS.m:8), 2-port SRS (setupSRS.m:18), one frame = 20 slots
+    "shipped": dict(nrb=273, scs=30, nV=8, p=2, ue_ants=2, csirs_ports=4, panel=(2, 1), subband=16, num_slots=20),
+    # same structure at 24 PRB / 15 kHz / 4 Tx for tests whose oracle has to finish in seconds
+    "small": dict(nrb=24, scs=15, nV=2, p=2, ue_ants=2, csirs_ports=4, panel=(2, 1), subband=4, num_slots=10),
+}
+
+
+def hex_gnb_positions(num_cells: int, radius: float, roi, height: float) -> np.ndarray:
+    """gNB sites of the reference's hexagonal layout (+networkTopology/+wraparound/generateWrapAround.m:94-150,
+    getgNBPositions): lattice points (i*1.5r, j*r*sqrt(3)/2) with i + j even inside the region of interest, in the
+    reference's loop order (i outer, j inner), truncated to ``num_cells``.  Returns [n x 3]."""
+    xw, yw = roi[0] / 2.0, roi[1] / 2.0
+    dx, dy = 1.5 * radius, radius * math.sqrt(3.0) / 2.0
+    mx, my = math.ceil(xw / dx), math.ceil(yw / dy)
+    out = []
+    for i in range(-mx, mx + 1):
+        for j in range(-my, my + 1):
+            if (i + j) % 2 == 0 and abs(i * dx) <= xw and abs(j * dy) <= yw:
+                out.append([i * dx, j * dy, height])
+    if len(out) < num_cells:
+        raise ValueError(f"the region of interest holds only {len(out)} sites of radius {radius}")
+    return np.asarray(out[:num_cells], dtype=np.float64)
+
+
+def scenario_cfg5(seed: int = 5, n_gnb: int = 19, n_ue: int = 100, n_targets: int = 20, radius: float = 80.0,
+                  radio: str = "shipped", roi=(500.0, 760.0)) -> dict:
+    """BASELINE config 5: ``n_gnb`` hexagonally placed gNBs inside the cached OSM city's extent (the shipped scenario places
+    its single gNB inside the same city, +scenarios/openStreetMapCity.m:20-43), ``n_ue`` UEs attached to the nearest site,
+    ``n_targets`` targets moving on straight lines, each attached to the gNB it was dropped around (attachedTargets is static
+    in the reference, openStreetMapCity.m:41).  Deterministic in ``seed``; nothing depends on how cells are later sharded."""
+    rng = np.random.default_rng(seed)
+    gnb = hex_gnb_positions(n_gnb, radius, roi, 25.0)
+    ue = np.column_stack([rng.uniform(-roi[0] / 2, roi[0] / 2, n_ue), rng.uniform(-roi[1] / 2, roi[1] / 2, n_ue), np.full(n_ue, 1.5)])
+    ue_cell = np.argmin(((ue[:, None, :2] - gnb[None, :, :2]) ** 2).sum(axis=2), axis=1)
+    tgt_cell = rng.integers(0, n_gnb, n_targets)
+    rr, az = rng.uniform(60.0, 180.0, n_targets), np.deg2rad(rng.uniform(-60.0, 60.0, n_targets))
+    tgt = gnb[tgt_cell] + np.column_stack([rr * np.cos(az), rr * np.sin(az), np.zeros(n_targets)])
+    tgt[:, 2] = 1.5
+    speed, head = rng.uniform(2.0, 15.0, n_targets), rng.uniform(0, 2 * np.pi, n_targets)
+    vel = np.column_stack([speed * np.cos(head), speed * np.sin(head), np.zeros(n_targets)])
+    load = rng.uniform(0.5, 1.0, (n_gnb, 64))                 # DL load of cell c in frame f (fraction of the Tx power radiated)
+    return {"gnb": gnb, "ue": ue, "ue_cell": ue_cell, "target0": tgt, "target_vel": vel, "target_cell": tgt_cell,
+            "rcs": np.ones(n_targets), "radio": radio, "seed": seed, "load": load, "frame_time": 10e-3,
+            "fc": 3.5e9, "txPower": 46.0, "rxGainUE": 0.0, "noiseFigureUE": 9.0, "scenario": "UMa"}
+
+
+def cfg5_target_state(scn: dict, frame: int):
+    """Positions of every target at the start of CPI ``frame`` and their radial velocities towards the attached gNB
+    (positive = receding, the sign convention of radarParams.velocity, basicRadarChannel.m:25)."""
+    pos = scn["target0"] + scn["target_vel"] * (frame * scn["frame_time"])
+    los_vec = pos - scn["gnb"][scn["target_cell"]]
+    unit = los_vec / np.linalg.norm(los_vec, axis=1, keepdims=True)
+    return pos, (scn["target_vel"] * unit).sum(axis=1)
+
+
+def cfg5_cell_params(scn: dict, cell: int, frame: int, ue_los=None, tgt_los=None) -> tuple[dict, dict, dict]:
+    """(cellSimuParams, carrierInfo, waveInfo) of one cell for CPI ``frame``: the fields
+    +simulation/assignCellSimulationParameters.m:27-101 flattens for cellSimulation, plus the UE list of the cell.
+    ``ue_los`` / ``tgt_los``: LoS flags of ALL UEs / targets of the scenario towards their own gNB (checkLoS,
+    networkSimulation.m:138,154); default all LoS."""
+    r = RADIO[scn["radio"]]
+    num = ofdm_numerology(r["nrb"], r["scs"])
+    pos, radial = cfg5_target_state(scn, frame)
+    ti = np.flatnonzero(scn["target_cell"] == cell)
+    ui = np.flatnonzero(scn["ue_cell"] == cell)
+    n_ants = r["nV"] * r["p"]
+    cellp = {
+        "cellID": int(cell), "frame": int(frame),
+        "numTargets": int(ti.size), "targetIDs": ti, "targetPosition": pos[ti].reshape(-1, 3),
+        "gNBPosition": scn["gnb"][cell],
+        "numDLSlots": 3, "tddPattern": list("DDDSU"), "numSlots": r["num_slots"],
+        "gNBTxAnts": n_ants, "dlCarrierFreq": scn["fc"],
+        "gNBNoiseFigure": 6.0, "gNBTemperature": 290.0, "gNBTxPower": scn["txPower"], "gNBRxGain": 25.5,
+        "rcs": scn["rcs"][ti], "velocity": radial[ti],
+        "gNBSenAntenna": {"type": "ula", "nV": r["nV"], "p": r["p"], "d": 0.5},
+        "detectionArea": np.array([[50.0, 500.0], [-50.0, 50.0]]), "Pfa": 1e-9,
+        "targetLoSConditions": (np.ones(ti.size, dtype=np.int64) if tgt_los is None else np.asarray(tgt_los)[ti].astype(np.int64)),
+        "ueIDs": ui, "uePosition": scn["ue"][ui].reshape(-1, 3),
+        "ueLoSConditions": (np.ones(ui.size, dtype=np.int64) if ue_los is None else np.asarray(ue_los)[ui].astype(np.int64)),
+        "ueTxAnts": r["ue_ants"], "radio": scn["radio"], "txLoad": float(scn["load"][cell, frame % scn["load"].shape[1]]),
+    }
+    carrier = {"SubcarrierSpacing": r["scs"], "NRBsDL": r["nrb"]}
+    wave = {"SampleRate": num["SampleRate"], "SymbolsPerSlot": 14, "Nfft": num["Nfft"],
+            "SlotsPerSubframe": num["SlotsPerSubframe"], "SymbolLengths": num["SymbolLengths"],
+            "CyclicPrefixLengths": num["CyclicPrefixLengths"]}
+    cellp["carrierInfo"], cellp["waveInfo"] = carrier, wave
+    return cellp, carrier, wave
+
+
+def cfg5_sensing_grid(scn: dict, cell: int, frame: int) -> np.ndarray:
+    """senTxGrid of a cell-CPI: unit QPSK on every RE of the DL symbols of the frame, seeded by (scenario, cell, frame)."""
+    r = RADIO[scn["radio"]]
+    nsym = 14 * int(round(3 / 5 * r["num_slots"]))
+    return qpsk_grid(12 * r["nrb"], nsym, r["nV"] * r["p"], 1_000_003 * scn["seed"] + 1009 * cell + frame)

@@ -49,5 +49,9 @@ t1)
   (timeout 1500 python -m pytest tests/test_cfg3_full_gpu.py tests/test_mex_mock_gpu.py -m gpu -q -x 2>&1 | tail -25) > gpurun_out/r2_t1_tests.log
   cat gpurun_out/r2_t1_tests.log
   ;;
+t2)
+  (timeout 1700 python -m pytest tests/test_cfg5_gpu.py tests/test_link_gpu.py -m gpu -q 2>&1 | tail -40) > gpurun_out/r2_t2_tests.log
+  cat gpurun_out/r2_t2_tests.log
+  ;;
 *) echo "unknown step $step"; exit 1;;
 esac
