@@ -344,7 +344,7 @@ rdm_range4096_direct_kernel(const RdmDev p) {
     float2* fftbuf = reinterpret_cast<float2*>(smraw);
     float2* tw2s = fftbuf + 16 * S1;                       // [15][16]
     float* w1s = reinterpret_cast<float*>(tw2s + 240);    // [NJ*256], zero beyond nSc
-    __shared__ int sNext;
+    __shared__ int sNext, sNext2;
     const int tf = threadIdx.x;
     const int nSc = p.nSc;
     if (tf < 240) tw2s[tf] = __ldg(p.twR.tw2 + tf);
@@ -365,7 +365,21 @@ rdm_range4096_direct_kernel(const RdmDev p) {
     const unsigned long long polOut = l2_policy((p.hints >> 2) & 3);
     const int total = (int)p.totalCols;
     const bool lastRow = tf + NT * (NJ - 1) < nSc;   // the last register row is only partly inside the grid
-    if (tf == 0) sNext = atomicAdd(p.ticketR, 1);
+    const bool pf = (p.hints >> 9) & 1;   // bit 9: bulk-prefetch the rx / tx columns of the ticket after next into L2
+    auto prefetch = [&](int c) {          // thread 0
+        const int sp = c % M, page = c / M;
+        int sy = sp + half;
+        if (sy >= nSym) sy -= nSym;
+        const size_t off = ((size_t)page * nSym + sy) * (size_t)nSc;
+        const unsigned bytes = (unsigned)nSc * (unsigned)sizeof(float2);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.rx + off), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.tx + off), "r"(bytes) : "memory");
+    };
+    if (tf == 0) {
+        sNext = atomicAdd(p.ticketR, 1);
+        sNext2 = atomicAdd(p.ticketR, 1);
+        if (pf && sNext2 < total) prefetch(sNext2);
+    }
     __syncthreads();
     asm volatile("griddepcontrol.launch_dependents;");
     int col = sNext;
@@ -390,7 +404,12 @@ rdm_range4096_direct_kernel(const RdmDev p) {
             }
         }
         __syncthreads();   // the previous column's pass-3 loads are done (fftbuf reuse) and its sNext has been read
-        if (tf == 0) sNext = atomicAdd(p.ticketR, 1);
+        if (tf == 0) {     // this CTA's columns: col (running), sNext2 (next, already prefetched), a fresh ticket (prefetched now)
+            sNext = sNext2;
+            const int t2 = atomicAdd(p.ticketR, 1);
+            sNext2 = t2;
+            if (pf && t2 < total) prefetch(t2);
+        }
         dft16<+1>(v);
 #pragma unroll
         for (int k1 = 1; k1 < 16; ++k1) v[k1] = pk_cmul(v[k1], tw1r[k1 - 1]);
@@ -674,6 +693,82 @@ __global__ void __launch_bounds__(1024) cfar2d_compact_kernel(const CfarDev p, i
             const int row = p.row0 + i % p.nCutRows, col = p.col0 + i / p.nCutRows;
             o[off] = make_int2(row + 1, col + 1);
             pk[off] = P[(long long)col * p.nIFFT + row];
+            ++off;
+        }
+    if (threadIdx.x == blockDim.x - 1) detCount[page] = warpTot[31];
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel C+D fused: one CTA per (antenna, map) page.  The CUT rectangle plus its training halo ((nCutRows + 2 hr) x
+// (nCutCols + 2 hc) cells: 376 x 29 at 273 PRB) is staged once in shared memory with coalesced loads along the range axis,
+// every thread decides a contiguous run of CUTs from the staged tile (the training cells are added in float64 in exactly
+// the order of the stand-alone decision kernels, so the decisions are bit-identical), the run counts are scanned across the
+// CTA with warp shuffles and the detections are written in CUT order.  One launch instead of two, no flag array, and the
+// 24 training loads of a CUT come from shared memory instead of L2.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) cfar2d_fused_kernel(const CfarDev p, int2* det, float* peak, int32_t* detCount) {
+    extern __shared__ float tile[];   // [tileCols][tileRows], range fastest
+    __shared__ int warpTot[32];
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the power map of the preceding grid (programmatic dependent launch)
+    const long long page = blockIdx.x;
+    const int tr = p.nCutRows + 2 * p.hr, nCutCols = p.nCut / p.nCutRows, tc = nCutCols + 2 * p.hc;
+    const float* __restrict__ P = p.pow + page * (long long)p.nFFT * p.nIFFT + (long long)(p.col0 - p.hc) * p.nIFFT + (p.row0 - p.hr);
+    for (int i = threadIdx.x; i < tr * tc; i += blockDim.x) {
+        const int r = i % tr, c = i / tr;
+        tile[i] = __ldcg(P + (long long)c * p.nIFFT + r);
+    }
+    __syncthreads();
+    const int per = (p.nCut + blockDim.x - 1) / blockDim.x;
+    const int lo = threadIdx.x * per, hi = min(lo + per, p.nCut);
+    unsigned long long mask = 0ull;   // per <= 64 (checked by the launcher)
+    int cnt = 0;
+    for (int i = lo; i < hi; ++i) {
+        const int r = i % p.nCutRows + p.hr, c = i / p.nCutRows + p.hc;   // tile coordinates of the CUT
+        double acc = 0.0;
+        for (int dc = -p.hc; dc <= p.hc; ++dc) {
+            const float* __restrict__ col = tile + (c + dc) * tr + r;
+            const bool colInGuard = (dc >= -p.gc && dc <= p.gc);
+            for (int dr = -p.hr; dr <= p.hr; ++dr) {
+                if (colInGuard && dr >= -p.gr && dr <= p.gr) continue;
+                acc = acc + (double)col[dr];
+            }
+        }
+        const bool d = (double)tile[c * tr + r] > p.alpha * (acc / p.nTrain);   // strict (CFARDetector2D)
+        if (d) {
+            mask |= 1ull << (i - lo);
+            ++cnt;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) warpTot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warpTot[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += v;
+        }
+        warpTot[lane] = w;  // inclusive totals of the warps
+    }
+    __syncthreads();
+    int off = incl - cnt + (warp ? warpTot[warp - 1] : 0);
+    int2* __restrict__ o = det + page * (long long)p.nCut;
+    float* __restrict__ pk = peak + page * (long long)p.nCut;
+    for (int i = lo; i < hi; ++i)
+        if ((mask >> (i - lo)) & 1ull) {
+            const int rr = i % p.nCutRows, cc = i / p.nCutRows;
+            const int row = p.row0 + rr, col = p.col0 + cc;
+            o[off] = make_int2(row + 1, col + 1);
+            pk[off] = tile[(cc + p.hc) * tr + rr + p.hr];
+            atomicOr(p.rowmask + (page / p.nAnts) * p.rowWords + (row >> 5), 1u << (row & 31));
             ++off;
         }
     if (threadIdx.x == blockDim.x - 1) detCount[page] = warpTot[31];
@@ -983,6 +1078,23 @@ static int rdm_cfar_launch(RdmPlan* p, const float* pow, int batch, bool chained
     if (!chained) {
         ISAC_CUDA_CHECK(ctx, cudaMemsetAsync(p->d_rowmask, 0, sizeof(uint32_t) * (size_t)p->rowWords * batch, st));
         pr = prof_begin(ctx, kProfCfar, st);
+    }
+    // fused decision + compaction kernel (opt-in, ISAC_CFAR_FUSED=1): measured SLOWER than the two-kernel path inside the chain
+    // (+27 us per chain at 1 and 4 map-sets, profiles/r2_rdm_experiments.txt), so the wide one-thread-per-CUT decision kernel
+    // followed by the per-page compaction stays the default
+    static const int fusedOff = getenv("ISAC_CFAR_FUSED") ? atoi(getenv("ISAC_CFAR_FUSED")) == 0 : 1;
+    const size_t tileBytes = sizeof(float) * (size_t)(p->nCutRows + 2 * d.hr) * (size_t)(p->nCutCols + 2 * d.hc);
+    if (!fusedOff && tileBytes <= 200 * 1024 && (p->nCut + 1023) / 1024 <= 64) {
+        cudaFuncSetAttribute(cfar2d_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileBytes);
+        // same shared-memory carve-out as the range / Doppler kernels of the chain: a different one makes the SMs drain first
+        cudaFuncSetAttribute(cfar2d_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        ISAC_CUDA_CHECK(ctx, launch_ex(cfar2d_fused_kernel, (unsigned)(p->cfg.nAnts * batch), 1024, tileBytes, st, chained && p->pdl, d,
+                                       p->d_det, p->d_peak, p->d_detCount));
+        if (!chained) prof_end(ctx, pr, st);
+        count_launches(ctx, 1);
+        p->lastPow = pow;
+        p->lastBatch = batch;
+        return kOk;
     }
     const long long blocks = (d.total + 255) / 256;
     const bool ref7 = d.gr == 2 && d.gc == 2 && d.hr == 3 && d.hc == 3;

@@ -107,6 +107,9 @@ class HotPath:
             from .networkTopology import blockages
             self.city = blockages.city(city_buildings, device=self.device)
         self._channels = {}
+        self._pl_cache = {}
+        self._xgain = {}
+        self._grids = {}            # per cell: (pinned host senTxGrid [nAnts][nSym][nSc], NumPy view of it)
         self.keep_H = None          # tests: a list that receives (cellID, occasion, H after the link budget, nVar)
         self.maxUE = int(np.bincount(scn["ue_cell"], minlength=scn["gnb"].shape[0]).max())
 
@@ -136,15 +139,23 @@ class HotPath:
         through the UMa path loss of that link (LoS from the city) and the UE's Rx gain.  No reference counterpart (cells are
         independent there, networkSimulation.m:57-60): an extension named by BASELINE.json, off by default in the parity tests."""
         ue = np.asarray(cellp["uePosition"]).reshape(-1, 3)
-        others = summary[summary[:, 0] != cellp["cellID"]]
-        if ue.shape[0] == 0 or others.shape[0] == 0:
-            return np.zeros(ue.shape[0])
-        uu = np.repeat(ue, others.shape[0], axis=0)
-        bb = np.tile(others[:, 1:4], (ue.shape[0], 1))
-        los = self.city.checkLoS(uu, bb) if self.city is not None else np.ones(uu.shape[0], bool)
-        pl = self.pl.config5GNRModels(self.scn["scenario"], self.scn["fc"], los.astype(np.int32), bb, uu, device=self.device)
-        pw = np.tile(others[:, 4], ue.shape[0]) * 10 ** ((self.scn["rxGainUE"] - np.atleast_1d(pl)) / 10.0)
-        return pw.reshape(ue.shape[0], others.shape[0]).sum(axis=1)
+        if ue.shape[0] == 0:
+            return np.zeros(0)
+        c = int(cellp["cellID"])
+        g = self._xgain.get(c)
+        if g is None:   # linear gains UE <- every gNB site: the sites, the UEs and the city are static, so one device pass per cell
+            gnb = self.scn["gnb"]
+            uu = np.repeat(ue, gnb.shape[0], axis=0)
+            bb = np.tile(gnb, (ue.shape[0], 1))
+            los = self.city.checkLoS(uu, bb) if self.city is not None else np.ones(uu.shape[0], bool)
+            pl = self.pl.config5GNRModels(self.scn["scenario"], self.scn["fc"], los.astype(np.int32), bb, uu, device=self.device)
+            g = 10 ** ((self.scn["rxGainUE"] - np.atleast_1d(pl)) / 10.0)
+            g = g.reshape(ue.shape[0], gnb.shape[0])
+            self._xgain[c] = g
+        p_re = np.zeros(self.scn["gnb"].shape[0])
+        p_re[summary[:, 0].astype(int)] = summary[:, 4]
+        p_re[c] = 0.0                                   # the own cell is the signal, not interference
+        return g @ p_re
 
     # -- COMM ----------------------------------------------------------------------------------------------------------
     def _channel(self, ue_id, los, uplink):
@@ -178,40 +189,77 @@ class HotPath:
 
     def comm_frame(self, cellp, interf=None):
         """COMM share of one frame of one cell.  Returns the comResults record (arrays indexed by the cell's UE order)."""
-        ue_ids = np.asarray(cellp["ueIDs"], int)
-        n = ue_ids.size
-        nOcc, nSB = len(self.csi_slots), self.nSB
-        rec = {"ueIDs": ue_ids, "RI": np.full((nOcc, n), np.nan), "i1": np.full((nOcc, 3, n), np.nan), "i2": np.full((nOcc, nSB, n), np.nan),
-               "CQI": np.full((nOcc, n), np.nan), "ulPMI": np.full((len(self.srs_slots), nSB, n), np.nan), "precodeEnergy": np.nan}
-        if n == 0:
-            return rec
-        scn, los = self.scn, np.asarray(cellp["ueLoSConditions"]).astype(bool)
-        ue = np.asarray(cellp["uePosition"]).reshape(-1, 3)
-        frame_t0 = cellp["frame"] * scn["frame_time"]
-        pl_db = np.atleast_1d(self.pl.config5GNRModels(scn["scenario"], scn["fc"], los.astype(np.int32), cellp["gNBPosition"], ue,
-                                                       device=self.device))
-        p_port = 10 ** ((scn["txPower"] - 30.0) / 10.0) * cellp["txLoad"] / (self.K * self.r["csirs_ports"])   # W per RE and port
-        nvar = self.noise_re + (np.zeros(n) if interf is None else np.asarray(interf))
-        last = None
-        for o, slot in enumerate(self.csi_slots):
-            H = self._batch(ue_ids, los, False, frame_t0 + slot * self.slot_dur, self.sym_t)
-            self.pl.applyPathLossAndRxGain(H, pl_db - 10 * np.log10(p_port), scn["rxGainUE"])       # uePhy.m:743-751
-            if self.keep_H is not None:
-                self.keep_H.append((cellp["cellID"], o, H.cpu().numpy(), nvar.copy()))
-            RI, pm, cq = self.ph.csiReport(self.carrier, self.csirs, self.rc, H, nvar, self.table, rankCap=4)   # uePhy.m:900-907
-            RI, i1, i2, cq = np.atleast_1d(RI), np.asarray(pm["i1"]).reshape(3, n), np.asarray(pm["i2"]).reshape(nSB, n), np.asarray(cq)
-            rec["RI"][o], rec["i1"][o], rec["i2"][o] = RI, i1, i2
-            rec["CQI"][o] = cq.reshape(cq.shape[0], -1, n)[0, 0]
-            last = (RI, i1, i2)
-        p_ul = 10 ** ((23.0 - 30.0) / 10.0) / (self.K * 2)                                            # 23 dBm UE, 2 SRS ports
-        for o, slot in enumerate(self.srs_slots):
-            Hul = self._batch(ue_ids, los, True, frame_t0 + slot * self.slot_dur, self.sym_t[13:14])
-            self.pl.applyPathLossAndRxGain(Hul, pl_db - 10 * np.log10(p_ul), cellp["gNBRxGain"])    # gNBPhy.m:852-860
-            pmi, _, none = self.ph.pmiSelectBatch(2, Hul, self.noise_re_gnb, self.r["subband"])      # gNBPhy.m:1035, rank 2 (cellSimulation.m:16)
-            pmi = np.asarray(pmi).reshape(-1, n)
-            rec["ulPMI"][o, : pmi.shape[0]] = np.where(np.asarray(none).reshape(1, n) != 0, np.nan, pmi)
-        rec["precodeEnergy"] = self._precode_scheduled(cellp, last)
-        return rec
+        return self.comm_frames([cellp], [interf])[0]
+
+    def _path_loss(self, cellp):
+        """UMa path loss of the cell's UE links (uePhy.m:743-747); UEs and the city are static, so one device call per cell."""
+        key = (int(cellp["cellID"]), tuple(np.asarray(cellp["ueLoSConditions"]).astype(int).tolist()))
+        pl = self._pl_cache.get(key)
+        if pl is None:
+            ue = np.asarray(cellp["uePosition"]).reshape(-1, 3)
+            pl = np.atleast_1d(self.pl.config5GNRModels(self.scn["scenario"], self.scn["fc"], np.asarray(key[1], np.int32),
+                                                       cellp["gNBPosition"], ue, device=self.device))
+            self._pl_cache[key] = pl
+        return pl
+
+    def comm_frames(self, cellps, interfs=None):
+        """COMM share of one frame for several cells at once: the UEs of all cells that report in the same slot go through the
+        CDL generator, the link budget and the fused report together (batches of up to 32 UEs, the library's limit) -- the
+        per-UE results do not depend on who shares the batch, so the records are the same as cell by cell."""
+        interfs = interfs if interfs is not None else [None] * len(cellps)
+        scn, nSB, nOcc, nSrs = self.scn, self.nSB, len(self.csi_slots), len(self.srs_slots)
+        recs, ues = [], []          # ues: (cell index, position in the cell, ue id, los, path loss, nVar, txLoad)
+        for ci, (cellp, interf) in enumerate(zip(cellps, interfs)):
+            ue_ids = np.asarray(cellp["ueIDs"], int)
+            n = ue_ids.size
+            recs.append({"ueIDs": ue_ids, "RI": np.full((nOcc, n), np.nan), "i1": np.full((nOcc, 3, n), np.nan),
+                         "i2": np.full((nOcc, nSB, n), np.nan), "CQI": np.full((nOcc, n), np.nan),
+                         "ulPMI": np.full((nSrs, nSB, n), np.nan), "precodeEnergy": np.nan})
+            if n == 0:
+                continue
+            los = np.asarray(cellp["ueLoSConditions"]).astype(bool)
+            pl_db = self._path_loss(cellp)
+            nvar = self.noise_re + (np.zeros(n) if interf is None else np.asarray(interf))
+            for q in range(n):
+                ues.append((ci, q, int(ue_ids[q]), bool(los[q]), float(pl_db[q]), float(nvar[q]), float(cellp["txLoad"]),
+                            float(cellp["gNBRxGain"])))
+        if not ues:
+            return recs
+        frame_t0 = cellps[0]["frame"] * scn["frame_time"]
+        p_tx = 10 ** ((scn["txPower"] - 30.0) / 10.0) / (self.K * self.r["csirs_ports"])                # W per RE and port at full load
+        p_ul = 10 ** ((23.0 - 30.0) / 10.0) / (self.K * 2)                                               # 23 dBm UE, 2 SRS ports
+        for c0 in range(0, len(ues), 32):
+            grp = ues[c0: c0 + 32]
+            ids, los = [g[2] for g in grp], [g[3] for g in grp]
+            pl = np.array([g[4] for g in grp])
+            nvar = np.array([g[5] for g in grp])
+            load = np.array([g[6] for g in grp])
+            for o, slot in enumerate(self.csi_slots):
+                H = self._batch(ids, los, False, frame_t0 + slot * self.slot_dur, self.sym_t)
+                self.pl.applyPathLossAndRxGain(H, pl - 10 * np.log10(p_tx * load), scn["rxGainUE"])    # uePhy.m:743-751
+                if self.keep_H is not None:
+                    self.keep_H.append(([cellps[g[0]]["cellID"] for g in grp], o, H.cpu().numpy(), nvar.copy()))
+                RI, pm, cq = self.ph.csiReport(self.carrier, self.csirs, self.rc, H, nvar, self.table, rankCap=4)   # uePhy.m:900-907
+                m = len(grp)
+                RI, i1, i2 = np.atleast_1d(RI), np.asarray(pm["i1"]).reshape(3, m), np.asarray(pm["i2"]).reshape(nSB, m)
+                cq = np.asarray(cq).reshape(np.asarray(cq).shape[0], -1, m)
+                for j, g in enumerate(grp):
+                    r = recs[g[0]]
+                    r["RI"][o, g[1]], r["i1"][o, :, g[1]], r["i2"][o, :, g[1]], r["CQI"][o, g[1]] = RI[j], i1[:, j], i2[:, j], cq[0, 0, j]
+            rxg = grp[0][7]
+            for o, slot in enumerate(self.srs_slots):
+                Hul = self._batch(ids, los, True, frame_t0 + slot * self.slot_dur, self.sym_t[13:14])
+                self.pl.applyPathLossAndRxGain(Hul, pl - 10 * np.log10(p_ul), rxg)                      # gNBPhy.m:852-860
+                pmi, _, none = self.ph.pmiSelectBatch(2, Hul, self.noise_re_gnb, self.r["subband"])     # gNBPhy.m:1035, rank 2 (cellSimulation.m:16)
+                pmi = np.asarray(pmi).reshape(-1, len(grp))
+                pmi = np.where(np.asarray(none).reshape(1, -1) != 0, np.nan, pmi)
+                for j, g in enumerate(grp):
+                    recs[g[0]]["ulPMI"][o, : pmi.shape[0], g[1]] = pmi[:, j]
+        for ci, cellp in enumerate(cellps):
+            r = recs[ci]
+            if r["ueIDs"].size:
+                r["precodeEnergy"] = self._precode_scheduled(cellp, (r["RI"][-1], r["i1"][-1], r["i2"][-1]))
+        return recs
 
     def _precode_scheduled(self, cellp, last):
         """PDSCH of the first UE of the cell precoded per PRG with the gNB-side codebook at its reported PMI
@@ -244,15 +292,24 @@ class HotPath:
         carrier, wave = cellp["carrierInfo"], cellp["waveInfo"]
         rp = self.sensing.radarParams(cellp, carrier, wave)
         cf = self.sensing.detection.cfar2D(rp)
-        grid = self.W.cfg5_sensing_grid(self.scn, cellp["cellID"], cellp["frame"]) if tx_grid is None else tx_grid
-        g_d = torch.from_numpy(np.ascontiguousarray(grid.astype(np.complex64).transpose(2, 1, 0))).to(f"cuda:{self.device}")
-        nsc, ntx = grid.shape[0], grid.shape[2]
+        if tx_grid is None:        # the cell's Tx payload: generated once, kept in pinned host memory, uploaded every CPI
+            ent = self._grids.get(int(cellp["cellID"]))
+            if ent is None:
+                g = self.W.cfg5_sensing_grid(self.scn, cellp["cellID"])
+                ent = (torch.from_numpy(np.ascontiguousarray(g.astype(np.complex64).transpose(2, 1, 0))).pin_memory(), g.shape)
+                self._grids[int(cellp["cellID"])] = ent
+            g_d = ent[0].to(f"cuda:{self.device}", non_blocking=True)
+            shape = ent[1]
+        else:
+            g_d = torch.from_numpy(np.ascontiguousarray(tx_grid.astype(np.complex64).transpose(2, 1, 0))).to(f"cuda:{self.device}")
+            shape = tx_grid.shape
+        nsc, ntx = shape[0], shape[2]
         amp = 10.0 ** ((cellp["gNBTxPower"] - 30.0) / 20.0) * np.sqrt(wave["Nfft"] ** 2 / (nsc * ntx))   # signalAmp (gNBPhy.m:599)
         w_d = self.sensing.ofdmModulate(carrier, g_d, amp)
         seed = 9_000_011 * self.scn["seed"] + 1019 * cellp["cellID"] + cellp["frame"]
         try:
             nz = None if noise is None else torch.from_numpy(np.ascontiguousarray(noise.astype(np.complex64).T)).to(w_d.device)
-            rx = self.sensing.monoStaticSensing(w_d, grid.shape, carrier, rp, cellp["targetLoSConditions"], noise=nz,
+            rx = self.sensing.monoStaticSensing(w_d, shape, carrier, rp, cellp["targetLoSConditions"], noise=nz,
                                                 seed=None if noise is not None else seed)
             return self.sensing.estimation.fft2D(rp, cf, rx, g_d)
         except _lib.IsacError:
@@ -289,7 +346,7 @@ def pack_record(hp, com, sen):
     return np.concatenate([[float(n), com["precodeEnergy"]], ue.ravel(), s])
 
 
-def networkFrames(scn, n_frames, city_buildings=None, device=None, interference=False, group=None, hp=None, on_frame=None):
+def networkFrames(scn, n_frames, city_buildings=None, device=None, interference=False, group=None, hp=None, on_frame=None, frame0=0):
     """``n_frames`` frames of every cell of the scenario, cells block-cyclic over the ranks of ``group`` (reference:
     the serial cell loop of networkSimulation.m:57-60).  Per frame: (optional) all-gather of the per-cell transmit summaries for
     the interference term, the cells of this rank, all-gather of their fixed-size records.  Returns records[frame] =
@@ -322,16 +379,15 @@ def networkFrames(scn, n_frames, city_buildings=None, device=None, interference=
         return full
 
     records = []
-    for f in range(n_frames):
+    for f in range(frame0, frame0 + n_frames):
         ue_los, tgt_los = hp.los_flags(f)
         summary = None
         if interference:
             summary = gather(hp.tx_summary(mine, f), 5)
-        rows = []
-        for c in mine:
-            cellp, _, _ = hp.W.cfg5_cell_params(scn, c, f, ue_los, tgt_los)
-            com, sen = cellFrame(hp, cellp, summary)
-            rows.append(pack_record(hp, com, sen))
+        cellps = [hp.W.cfg5_cell_params(scn, c, f, ue_los, tgt_los)[0] for c in mine]
+        interfs = [hp.interference(cp, summary) if summary is not None else None for cp in cellps]
+        coms = hp.comm_frames(cellps, interfs) if cellps else []
+        rows = [pack_record(hp, com, hp.sensing_cpi(cp)) for cp, com in zip(cellps, coms)]
         width = len(rows[0]) if rows else len(pack_record(hp, hp.comm_frame({"ueIDs": np.zeros(0, int)}), float("nan")))
         local = np.stack(rows) if rows else np.zeros((0, width))
         records.append(gather(local, width))

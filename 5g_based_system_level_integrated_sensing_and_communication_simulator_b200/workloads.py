@@ -233,8 +233,9 @@ def cfg5_cell_params(scn: dict, cell: int, frame: int, ue_los=None, tgt_los=None
     return cellp, carrier, wave
 
 
-def cfg5_sensing_grid(scn: dict, cell: int, frame: int) -> np.ndarray:
-    """senTxGrid of a cell-CPI: unit QPSK on every RE of the DL symbols of the frame, seeded by (scenario, cell, frame)."""
+def cfg5_sensing_grid(scn: dict, cell: int) -> np.ndarray:
+    """senTxGrid of a cell's CPI: unit QPSK on every RE of the DL symbols of a frame, seeded by (scenario, cell); the same
+    payload is transmitted every frame (what changes from CPI to CPI are the targets, the noise and the channels)."""
     r = RADIO[scn["radio"]]
     nsym = 14 * int(round(3 / 5 * r["num_slots"]))
-    return qpsk_grid(12 * r["nrb"], nsym, r["nV"] * r["p"], 1_000_003 * scn["seed"] + 1009 * cell + frame)
+    return qpsk_grid(12 * r["nrb"], nsym, r["nV"] * r["p"], 1_000_003 * scn["seed"] + 1009 * cell)

@@ -32,8 +32,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "5g_based_system_level_integrated_sensing_and_communication_simulator_b200"
-SUBFRAMES_PER_STEP = 10
-WORKLOAD = "cfg2: 1 gNB, 8 UE, 4 targets, 8x8, 273 PRB @30 kHz, 1 frame (168 DL symbols) per cell per step"
+SUBFRAMES_PER_FRAME = 10
+WORKLOAD = "cfg2: 1 gNB, 8 UE, 4 targets, 8x8, 273 PRB @30 kHz, frames of 168 DL symbols per cell"
+STAGES = ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa", "cdl_dl_generate", "csi_report(ri+pmi+cqi)",
+          "cdl_ul_generate", "ul_tpmi_select", "prg_precode"]
+# measured sustained DFMA rate of one B200 (tools/micro/fp64_peak.cu, profiles/r2_fp64_peak.txt): the roofline of the PMI / SINR
+# group, which runs its Cholesky factorisations on the FP64 pipe
+FP64_PEAK_TFLOPS = 32.8
+# FP64 flops of one 32-UE cfg2 CSI report (8 ports (2,2), ranks 1-8, 273 REs): DFMA = 2, DMUL / DADD = 1, thread-level counts
+# of the SASS instructions executed (ncu source page of profiles/r2_pmi_fused_v2_summary.txt, scaled by UEs / 32)
+PMI_FLOPS_PER_UE_REPORT = 2.39e8
+
+
+def bench_config(cells, frames):
+    """The `config` object of the JSON line -- identical for the B200 arm and the reference arm."""
+    return {"workload": WORKLOAD, "cells_per_gpu": cells, "frames_per_step": frames, "stages": STAGES,
+            "l2_policy": "inputs (waveforms + grids of all cells, 330 MB per frame at 4 cells) larger than L2; no flush"}
 
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch group from the committed ncu capture
@@ -310,12 +324,13 @@ def run_b200(args):
         half = (cells + 1) // 2
         return [echo(0, half), echo(half, cells), lambda: plan.run_dev(rx_grid_d, tx_grid_d, cells)]
 
-    stages = ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa",
-              "cdl_dl_generate", "csi_report(ri+pmi+cqi)", "cdl_ul_generate", "ul_tpmi_select", "prg_precode"]
     comm = CommWorkload(P, cells, local)
 
+    F = args.frames_per_step
+
     def step_dev(step):
-        comm.step(step, sensing_pieces(step))
+        for f in range(F):                 # one step = F consecutive frames of every cell (a >= 1 s timed region at the default K)
+            comm.step(step * F + f, sensing_pieces(step * F + f))
 
     # ---- device-resident timing ----------------------------------------------------------------
     for i in range(args.warmup):
@@ -356,7 +371,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = cells * SUBFRAMES_PER_STEP * world / (ms_step * 1e-3)
+    value = cells * SUBFRAMES_PER_FRAME * F * world / (ms_step * 1e-3)
 
     # ---- end-to-end through the host API (pinned host in, host results out) -------------------------
     # Per step and cell the transmit GRID crosses PCIe (pinned -> device); the waveform the gNB PHY derives from it
@@ -415,7 +430,7 @@ def run_b200(args):
         comm.step(step, [echo(0, half, True), echo(half, cells, False), chain])   # CSI / TPMI reports land on the host
         return plan.collect(cells)   # D2H of detections / estimates (synchronises)
 
-    e2e_steps = max(1, args.steps)    # same K as the device-resident leg: the pipeline fill (first upload) is paid once
+    e2e_steps = max(1, args.steps) * F   # frames: the same K steps of F frames as the device-resident leg
     torch.cuda.synchronize()
     for ev in consumed:
         ev.record(torch.cuda.current_stream())
@@ -435,10 +450,35 @@ def run_b200(args):
         t = torch.tensor([t_e2e], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
-    e2e_value = cells * SUBFRAMES_PER_STEP * world * e2e_steps / t_e2e
+    e2e_value = cells * SUBFRAMES_PER_FRAME * world * e2e_steps / t_e2e
     n_est_e2e = [len(r["rngEst"]) for r in out]
-    h2d = cells * (nSc * nSym * nTx * 8)
-    d2h = cells * (nTx * 4 + 64 * 8 + 16) + comm.d2h_bytes_per_step()  # detections/estimates + CSI / TPMI reports
+    h2d = F * cells * (nSc * nSym * nTx * 8)
+    d2h = F * (cells * (nTx * 4 + 64 * 8 + 16) + comm.d2h_bytes_per_step())  # detections/estimates + CSI / TPMI reports
+
+    # ---- the drop-in cost of the CSI functions: H of one CSI-RS occasion from PINNED HOST memory ---------------------------
+    # dlPMISelect / riSelect / cqiSelect take H as a host array (uePhy.m:897-907: Hest comes out of nrChannelEstimate on the host);
+    # through the MEX / _host path every occasion's H (8 bytes x K x 14 x nRx x P per UE) crosses PCIe before the report runs.
+    host_h = None
+    if not args.skip_host_h:
+        Hpin = torch.empty(comm.H.shape, dtype=torch.complex64).pin_memory()
+        Hpin.copy_(comm.H)
+        Hdev = torch.empty_like(comm.H)
+        ph = importlib.import_module(PKG + ".communication.phyLayer")
+        torch.cuda.synchronize()
+        reps = 3
+        t0h = time.time()
+        for _ in range(reps):
+            Hdev.copy_(Hpin, non_blocking=True)
+            ph.csiReport(comm.carrier, comm.csirs, comm.rc, Hdev, comm.nvar, comm.table, rankCap=4)
+        torch.cuda.synchronize()
+        t_occ = (time.time() - t0h) / reps
+        frame_s = t_e2e / e2e_steps
+        # a frame has 4 occasions; their H transfers replace the device CDL generation of the e2e leg
+        host_h = {"ms_per_occasion": round(t_occ * 1e3, 2), "h2d_bytes_per_occasion": int(Hpin.numel() * 8),
+                  "pcie_GBps": round(Hpin.numel() * 8 / t_occ / 1e9, 1),
+                  "value_if_every_occasion_crossed_pcie": round(cells * SUBFRAMES_PER_FRAME * world / (frame_s + 4 * t_occ), 1),
+                  "note": "one CSI-RS occasion (%d UEs): pinned host H -> device -> fused RI/PMI/CQI report -> host; the MATLAB drop-in "
+                          "pays this per occasion, the device-resident pipeline (CDL or channel estimation on the GPU) does not" % comm.nb}
 
     sampler.stop()
     clocks = sampler.summary(t_wall0, t_wall1)
@@ -462,6 +502,14 @@ def run_b200(args):
     dom = max(groups, key=lambda k: groups[k][0])
     roof = {}
     for name, (ms, n) in groups.items():
+        if name == "pmi_sinr" and n and ms > 0:   # FP64-pipe bound: Cholesky / inverse-diagonal of every candidate in float64
+            ach = PMI_FLOPS_PER_UE_REPORT * comm.nb / (ms / n * 1e-3) / 1e12
+            roof[name] = {"bound": "fp64", "achieved": round(ach, 2), "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                          "frac": round(ach / FP64_PEAK_TFLOPS, 4), "avg_launch_us": round(ms / n * 1e3, 2),
+                          "share_of_step": round(ms / ms_total, 4),
+                          "peak_source": "measured DFMA rate (tools/micro/fp64_peak.cu, profiles/r2_fp64_peak.txt)",
+                          "fp64_pipe_pct_ncu": 34.1, "ncu": "profiles/r2_pmi_fused_v2_summary.txt"}
+            continue
         if n and ms > 0 and name not in alg:
             roof[name] = {"bound": "latency/alu", "avg_launch_us": round(ms / n * 1e3, 2), "share_of_step": round(ms / ms_total, 4)}
             continue
@@ -477,16 +525,15 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (MUSIC/CFAR compare in f64)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "cells_per_gpu": cells, "stages": stages,
-                       "l2_policy": "inputs (%.0f MB of waveforms + grids per step) larger than L2; no flush"
-                                    % (cells * (T * nTx * 8 + nSc * nSym * nTx * 8) / 1e6),
-                       "rd_map_sets_per_sec": round(cells * world / (ms_step * 1e-3), 1),
-                       "rd_map_sets_per_sec_rdm_kernels": round(cells * world / (rdm_ms / max(rdm_n, 1) * 1e-3), 1) if rdm_ms > 0 else None,
-                       "detections_sanity": n_est[:4]},
+            "config": bench_config(cells, F),
+            "details": {"rd_map_sets_per_sec": round(cells * F * world / (ms_step * 1e-3), 1),
+                        "rd_map_sets_per_sec_rdm_kernels": round(cells * world / (rdm_ms / max(rdm_n, 1) * 1e-3), 1) if rdm_ms > 0 else None,
+                        "detections_sanity": n_est[:4], "timed_region_s": round(ms_total * 1e-3, 3),
+                        "input_bytes_per_frame": int(cells * (T * nTx * 8 + nSc * nSym * nTx * 8))},
             "e2e": {"value": round(e2e_value, 2), "unit": "cell-subframes/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "api": "pinned txGrid -> device OFDM modulation (gNBPhy.m:599) -> simulation-level sensing pass "
                            "(cellSimulation.m:191-197) -> estResults on the host; CSI/TPMI reports on the host",
-                    "detections_sanity": n_est_e2e[:4]},
+                    "detections_sanity": n_est_e2e[:4], "host_H_occasion": host_h},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": dict(roof.get("rdm_2dfft+cfar", {}),
@@ -495,108 +542,237 @@ def run_b200(args):
             "roofline_all": roof, "dominant_group": dom,
         }
         if args.cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(sample_cells=1)
+            line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------
-def _oracle_comm_sample(seed, n_reports=2):
-    """`n_reports` UE CSI reports (+ proportional UL/precoding work) of the cfg2 COMM share on the CPU.
-    Uses the vectorised NumPy restatement (best-effort CPU variant of BASELINE.md).  Returns seconds."""
-    from oracle import comm as OCm
+def run_cfg5(args):
+    """--workload cfg5: BASELINE config 5 (openStreetMapCity scenario: 19 gNBs, 100 UEs, 20 moving targets, shipped 273-PRB radio)
+    through simulation.networkFrames.  STRONG scaling: the 19 cells are sharded block-cyclic over the N ranks (3,3,3,2,2,2,2,2 at
+    N = 8); per frame the ranks all-gather the per-cell transmit summaries (inter-cell interference term) and the fixed-size
+    per-cell records over NCCL -- both collectives are INSIDE the timed region.  One step = one frame of all 19 cells."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P = importlib.import_module(PKG)
+    sim = importlib.import_module(PKG + ".simulation")
+    W = P.workloads
+    scn = W.scenario_cfg5(radio=args.cfg5_radio)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "osm_city.npz"))
+    off = z["fp_off"]
+    buildings = [(z["fp_flat"][:, off[i]:off[i + 1]], float(z["heights"][i])) for i in range(off.size - 1)]
+    hp = sim.HotPath(scn, device=local, city_buildings=buildings)
+    ctx = hp.ctx
+    n_cells = scn["gnb"].shape[0]
+    frame = [0]
+
+    def run(n):
+        recs = sim.networkFrames(scn, n, interference=True, hp=hp, frame0=frame[0])
+        frame[0] += n
+        return recs
+
+    run(max(1, args.warmup))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ctx.profile_collect()
+    ctx.profile_enable(True)
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    recs = run(args.steps)                       # host results of every cell on every rank: this IS the end-to-end path
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    _, launches = ctx.profile_collect()
+    ctx.profile_enable(False)
+    t = t_wall1 - t_wall0
+    if world > 1:
+        dist.barrier()
+        tt = torch.tensor([t, float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt[1:], op=dist.ReduceOp.SUM)
+        t, launches = float(tt[0].item()), int(tt[1].item())
+    sampler.stop()
+    value = n_cells * SUBFRAMES_PER_FRAME * args.steps / t
+    r = W.RADIO[scn["radio"]]
+    nsym = 14 * int(round(3 / 5 * r["num_slots"]))
+    h2d = sum(12 * r["nrb"] * nsym * r["nV"] * r["p"] * 8 for c in range(n_cells) if (scn["target_cell"] == c).any())
+    if rank == 0:
+        det = int(sum(x[:, -(4 + 2 * sim.REC_RNG + sim.REC_AZI)].sum() for x in recs))
+        line = {"metric": "cell_subframes_per_sec", "value": round(value, 2), "unit": "cell-subframes/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t / args.steps * 1e3, 3), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32 (PMI / MUSIC / CFAR compare in f64)", "data": "synthetic",
+                "config": {"workload": "cfg5: openStreetMapCity scenario, 19 gNB / 100 UE / 20 moving targets, %d PRB, one frame of all "
+                                       "cells per step, cells sharded over the GPUs" % r["nrb"],
+                           "cells": n_cells, "shard_sizes": [len(sim.shard_cells(n_cells, world, q)) for q in range(world)],
+                           "collectives_in_timed_region": ["all_gather(tx summaries [cells x 5] f64)", "all_gather(records [cells x %d] f64)" % recs[0].shape[1]],
+                           "l2_policy": "every cell-frame streams fresh grids / waveforms (> L2 per rank at the shipped radio); no flush"},
+                "e2e": {"value": round(value, 2), "unit": "cell-subframes/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(recs[0].size * 8),
+                        "api": "simulation.networkFrames: host scenario in, per-cell host records of every cell out (timed with the host clock, "
+                               "max over ranks); `value` is this same end-to-end figure -- the driver has no device-only leg"},
+                "gpu_launches": int(launches), "clocks": sampler.summary(t_wall0, t_wall1),
+                "details": {"cell_frames_with_detections": det, "frames": args.steps}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arms: the float64 NumPy restatement of the reference (oracle/), WHOLE cell-frames, no extrapolation.
+# One cfg2 cell-frame = the task list below in slot order (TDD DDDSU @30 kHz): per DL slot the PDSCH and DM-RS precoding, per
+# CSI-RS occasion the channel + fused RI/PMI/CQI report of each of the 8 UEs, per SRS occasion the UL channel + TPMI selection of
+# each of its 4 UEs, and at the end of the frame the sensing pass (echo synthesis + demodulation, fft2D).  Every task is
+# stateless (its inputs derive from the seed), so tasks can be spread over processes and over the steps of a run.
+# ----------------------------------------------------------------------------------------------
+_TABLE = np.array([-3.46, 1.54, 6.54, 11.05, 13.54, 16.04, 17.54, 20.04, 22.04, 24.43, 26.93, 27.43, 29.43, 32.43, 35.43])
+
+
+def cell_frame_tasks():
+    tasks = []
+    srs = {3, 4, 11, 12, 19}
+    for slot in range(20):
+        if slot % 5 < 3:
+            tasks += [("prg", slot, 0), ("prg", slot, 1)]
+        if slot % 5 == 2:
+            tasks += [("csi", slot, u) for u in range(8)]
+        if slot in srs:
+            tasks += [("srs", slot, u) for u in range(4)]
+    tasks.append(("sense", 20, 0))
+    return tasks
+
+
+def run_task(task, seed):
+    """Execute one task of a cell-frame on the CPU.  Returns (seconds, fft2D seconds or 0)."""
     from oracle import cdl as OCd
-    rng = np.random.default_rng(seed)
+    from oracle import comm as OCm
+    kind, slot, u = task
     nrb, K = 273, 273 * 12
-    cfg = OCm.report_config(8, (2, 2), nrb, 0, 1, "Subband", "Subband", 16)
-    re_k, re_l = OCm.csirs_first_port_res(nrb, 1, 0)
-    table = np.array([-3.46, 1.54, 6.54, 11.05, 13.54, 16.04, 17.54, 20.04, 22.04, 24.43, 26.93, 27.43, 29.43, 32.43, 35.43])
     t_sym = np.arange(14) * 35.7e-6
     t0 = time.time()
-    for i in range(n_reports):
-        rays = OCd.build_rays(2, 300e-9, 5.0, (1, 4, 2), (2, 2, 2), True, False, seed * 100 + i)
+    t_fft = 0.0
+    if kind == "csi":
+        cfg = OCm.report_config(8, (2, 2), nrb, 0, 1, "Subband", "Subband", 16)
+        re_k, re_l = OCm.csirs_first_port_res(nrb, 1, 0)
+        rays = OCd.build_rays(2, 300e-9, 5.0, (1, 4, 2), (2, 2, 2), True, False, seed * 1000 + slot * 10 + u)
         H = OCd.frequency_response(rays, K, 30e3, t_sym)
-        OCm.csi_report_vectorized(cfg, re_k, re_l, H, 10 ** -1.5, table)
-    # UL: 20/32 SRS occasions per CSI report
-    for i in range(max(1, round(n_reports * 20 / 32))):
-        rays = OCd.build_rays(2, 300e-9, 5.0, (1, 1, 2), (1, 4, 2), True, False, seed * 100 + 50 + i)
+        OCm.csi_report_vectorized(cfg, re_k, re_l, H, 10 ** -1.5, _TABLE)
+    elif kind == "srs":
+        rays = OCd.build_rays(2, 300e-9, 5.0, (1, 1, 2), (1, 4, 2), True, False, seed * 1000 + 500 + slot * 10 + u)
         h = OCd.frequency_response(rays, K, 30e3, t_sym[13:14])
         OCm.pmi_select(2, h, 0.05, 16)                      # full band, as on the GPU leg
-    return time.time() - t0
+    elif kind == "prg":
+        rng = np.random.default_rng(seed * 1000 + slot * 2 + u)
+        L, nu, P, nprg = 14, 2, 8, 137
+        ks, syms = (np.arange(K), np.arange(2, 14)) if u == 0 else (np.arange(0, K, 2), np.array([2]))   # PDSCH / DM-RS
+        pos = (ks[:, None] + K * syms[None, :]).T.reshape(-1)
+        ind = np.stack([pos + 1 + K * L * j for j in range(nu)], axis=1)
+        sym = rng.standard_normal((pos.size, nu)) + 1j * rng.standard_normal((pos.size, nu))
+        Fm = rng.standard_normal((nu, P, nprg)) + 1j * rng.standard_normal((nu, P, nprg))
+        OCm.prg_precode((K, L, P), 0, sym, ind, Fm)
+    else:
+        from oracle import sensing as S
+        W = importlib.import_module(PKG + ".workloads")
+        cell, car, wave = W.cell_config("cfg2")
+        rp = S.radar_params(cell, car, wave)
+        grid, txw = W.sensing_tx("cfg2", seed)              # input generation (QPSK grid + OFDM modulation) is not timed
+        noise = W.std_normal_complex(txw.shape, seed + 1)
+        cf = S.cfar2d_config(rp)
+        t0 = time.time()
+        rx = S.mono_static_sensing(txw, grid.shape, car, rp, cell["targetLoSConditions"], noise)
+        t1 = time.time()
+        S.fft2d(rp, cf, rx, grid)
+        t_fft = time.time() - t1
+    return time.time() - t0, t_fft
 
 
-def _oracle_cell_frame(seed, split=False):
-    """One cfg2 cell-frame of sensing work on the CPU (float64 oracle).  Returns seconds (and the fft2D share if `split`)."""
-    from oracle import sensing as S
-    W = importlib.import_module(PKG + ".workloads")
-    cell, car, wave = W.cell_config("cfg2")
-    rp = S.radar_params(cell, car, wave)
-    grid, txw = W.sensing_tx("cfg2", seed)
-    noise = W.std_normal_complex(txw.shape, seed + 1)
-    cf = S.cfar2d_config(rp)
-    t0 = time.time()
-    rx = S.mono_static_sensing(txw, grid.shape, car, rp, cell["targetLoSConditions"], noise)
-    t1 = time.time()
-    S.fft2d(rp, cf, rx, grid)
-    t2 = time.time()
-    return (t2 - t0, t2 - t1) if split else t2 - t0
+def _run_tasks(arg):
+    tasks, seed = arg
+    tot, fft = 0.0, 0.0
+    for t in tasks:
+        a, b = run_task(t, seed)
+        tot += a
+        fft += b
+    return tot, fft
 
 
-def _cell_frame_seconds(seed, n_reports=2):
-    """Bounded CPU sample of one cfg2 cell-frame: the whole sensing share + n_reports of the 32 CSI reports (and the
-    proportional SRS work), the COMM part extrapolated linearly to the full frame."""
-    ts = _oracle_cell_frame(seed)
-    tc = _oracle_comm_sample(seed, n_reports) * (32.0 / n_reports)
-    return ts + tc, ts, tc
+def _warm(_):
+    """Imports + one small report: the pool's processes are ready before the timed region."""
+    from oracle import comm as OCm
+    rng = np.random.default_rng(0)
+    cfg = OCm.report_config(4, (2, 1), 24, 0, 1, "Subband", "Subband", 4)
+    re_k, re_l = OCm.csirs_first_port_res(24, 1, 0)
+    H = rng.standard_normal((288, 14, 2, 4)) + 1j * rng.standard_normal((288, 14, 2, 4))
+    OCm.csi_report_vectorized(cfg, re_k, re_l, H, 0.1, _TABLE)
+    return 0
 
 
-def cpu_baseline(sample_cells=1):
-    ts, t_fft2d = _oracle_cell_frame(11, split=True)
-    tc = _oracle_comm_sample(11, 2) * (32.0 / 2)
-    t = ts + tc
-    return {"value": round(SUBFRAMES_PER_STEP / t, 3), "unit": "cell-subframes/s", "cores": 1, "kind": "port",
-            "rd_map_sets_per_sec": round(1.0 / t_fft2d, 3),
-            "sample": f"1 cfg2 cell-frame: full sensing share ({ts:.1f} s, of which fft2D = 2D-FFT + CFAR + MUSIC on one map-set "
-                      f"{t_fft2d:.1f} s) + 2 of its 32 UE CSI reports and 1 of its 20 SRS reports, extrapolated linearly ({tc:.1f} s); "
-                      "NumPy float64 restatement of the reference (not MATLAB)"}
+def cpu_baseline():
+    """One WHOLE cfg2 cell-frame on the host cores: its 77 tasks dealt round-robin to one process per core."""
+    from concurrent.futures import ProcessPoolExecutor
+    workers = max(1, min(os.cpu_count() or 1, 8))
+    tasks = cell_frame_tasks()
+    order = sorted(range(len(tasks)), key=lambda i: (tasks[i][0] != "sense", tasks[i][0] != "csi"))   # long tasks first
+    parts = [[tasks[i] for i in order[w::workers]] for w in range(workers)]
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        list(ex.map(_warm, range(workers)))
+        t0 = time.time()
+        res = list(ex.map(_run_tasks, [(pt, 11) for pt in parts]))
+        wall = time.time() - t0
+    t_fft = sum(r[1] for r in res)
+    return {"value": round(SUBFRAMES_PER_FRAME / wall, 3), "unit": "cell-subframes/s", "cores": workers, "kind": "port",
+            "rd_map_sets_per_sec": round(1.0 / t_fft, 3) if t_fft > 0 else None,
+            "sample": f"1 whole cfg2 cell-frame (32 CSI reports, 20 SRS reports, 24 precoding calls, sensing pass) in {wall:.1f} s wall "
+                      f"on {workers} processes ({sum(r[0] for r in res):.1f} core-seconds; fft2D of its one map-set {t_fft:.1f} s on one "
+                      "core); NumPy float64 restatement of the reference (MATLAB cannot run here), nothing extrapolated"}
 
 
 def run_reference(args):
+    """--impl reference: `workers` whole cell-frames over the K timed steps -- step s executes the s-th K-quantile of every
+    frame's task list (in slot order), so the run as a whole executes complete cell-frames and nothing is extrapolated."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from concurrent.futures import ProcessPoolExecutor
-    cores = os.cpu_count() or 1
-    workers = max(1, min(cores, 8))
-    per_step = workers  # one (sampled) cell-frame per worker per step
+    workers = max(1, min(os.cpu_count() or 1, 8))
+    tasks = cell_frame_tasks()
+    K = max(1, args.steps)
+    bounds = [round(i * len(tasks) / K) for i in range(K + 1)]
     with ProcessPoolExecutor(max_workers=workers) as ex:
-        for _ in range(args.warmup and 1):
-            list(ex.map(_cell_frame_seconds, range(workers)))
+        for _ in range(args.warmup):
+            list(ex.map(_warm, range(workers)))
         t0 = time.time()
-        res = []
-        for s in range(args.steps):
-            res += list(ex.map(_cell_frame_seconds, [100 * s + i for i in range(per_step)]))
+        core_s, t_fft = 0.0, 0.0
+        for sidx in range(K):
+            chunk = tasks[bounds[sidx]: bounds[sidx + 1]]
+            res = list(ex.map(_run_tasks, [(chunk, 100 + w) for w in range(workers)]))
+            core_s += sum(r[0] for r in res)
+            t_fft += sum(r[1] for r in res)
         wall = time.time() - t0
-    # Every worker ran the whole sensing share of a cell-frame (ts) and 2 of its 32 CSI reports + 1 of its 20 SRS reports
-    # (tc / 16 of measured time, tc = the linear extrapolation to the full COMM share): the time-weighted fraction of a
-    # cell-frame's CPU work that was actually executed scales the MEASURED wall clock to whole cell-frames.
-    frac = float(np.mean([(ts + tc / 16.0) / (ts + tc) for _, ts, tc in res]))
-    value = per_step * SUBFRAMES_PER_STEP * args.steps * frac / wall
+    value = workers * SUBFRAMES_PER_FRAME / wall
+    cells = args.cells_per_gpu
     line = {"impl": "reference", "metric": "cell_subframes_per_sec", "value": round(value, 3), "unit": "cell-subframes/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(wall / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": round(wall / K * 1e3, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "cells_per_step": per_step,
-                       "stages": ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa", "cdl_dl_generate",
-                                  "csi_report(ri+pmi+cqi)", "cdl_ul_generate", "ul_tpmi_select"],
-                       "note": "bounded sample: per step every worker executes the full sensing share and 2 of the 32 CSI reports "
-                               "(+ 1 of the 20 SRS reports) of one cell-frame = %.1f %% of a cell-frame's CPU work (time-weighted); "
-                               "value = cells x 10 subframes x that fraction / measured wall time" % (100.0 * frac)},
+            "config": bench_config(cells, args.frames_per_step),
+            "details": {"cell_frames_executed": workers, "core_seconds": round(core_s, 1),
+                        "rd_map_sets_per_sec_one_core": round(workers / t_fft, 3) if t_fft > 0 else None,
+                        "note": "bounded sample of the workload: %d whole cell-frames (one per process) spread over the %d timed steps; "
+                                "value = cell-frames x 10 subframes / measured wall time" % (workers, K)},
             "cpu_baseline": {"value": round(value, 3), "unit": "cell-subframes/s", "cores": workers, "kind": "port",
-                             "sample": f"{per_step} sampled cfg2 cell-frames per step over {workers} processes ({100.0 * frac:.1f} % of "
-                                       "each executed, wall-clock scaled); NumPy float64 restatement of the reference (MATLAB "
-                                       "cannot run here)"},
+                             "sample": f"{workers} whole cfg2 cell-frames over {workers} processes in {wall:.1f} s wall; NumPy float64 "
+                                       "restatement of the reference (MATLAB cannot run here), nothing extrapolated"},
             "e2e": {"value": round(value, 3), "unit": "cell-subframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -608,14 +784,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells-per-gpu", type=int, default=4)
+    ap.add_argument("--frames-per-step", type=int, default=10,
+                    help="frames of every cell per step (cfg2): 10 frames x 4 cells = 400 cell-subframes per step, a >= 1 s timed region at K = 20")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
+                    help="cfg2 (default): weak scaling, cells_per_gpu cells per GPU; cfg5: the 19-cell openStreetMapCity scenario, strong scaling")
+    ap.add_argument("--cfg5-radio", default="shipped", choices=["shipped", "small"])
+    ap.add_argument("--skip-host-h", action="store_true", help="skip the host-resident-H occasion measurement of the e2e object")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--sense-ctx", default="own", choices=["own", "shared"],
                     help="library context of the sensing chain: its own (second stream in the e2e leg) or the COMM one")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.steps > 3:
-            args.steps = 3  # bounded sample: each step is `workers` cell-frames of float64 NumPy work
         run_reference(args)
+        return
+    if args.workload == "cfg5":
+        run_cfg5(args)
         return
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 or int(os.environ.get("RANK", "0")) > 0:
         args.cpu_baseline = args.cpu_baseline and int(os.environ.get("WORLD_SIZE", "1")) == 1

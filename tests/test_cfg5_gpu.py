@@ -131,7 +131,8 @@ def test_cfg5_one_cell_against_the_oracle(world1):
     r = W.RADIO["small"]
     ocfg = OC.report_config(r["csirs_ports"], r["panel"], r["nrb"], 0, 1, "Subband", "Subband", r["subband"])
     re_k, re_l = OC.csirs_first_port_res(r["nrb"], 1, 0)
-    for _, o, H, nvar in kept:
+    for cells_of, o, H, nvar in kept:
+        assert set(cells_of) == {cell}
         for u in range(H.shape[0]):
             Hm = H[u].transpose(3, 2, 1, 0)                                # [P][R][L][K] -> [K x L x R x P]
             rank, pmo, cqo = OC.csi_report_vectorized(ocfg, re_k, re_l, Hm, nvar[u], hp.table, rank_cap=4)
@@ -139,7 +140,7 @@ def test_cfg5_one_cell_against_the_oracle(world1):
             assert np.array_equal(com["i1"][o, :, u], pmo["i1"]) and np.array_equal(com["i2"][o, :, u], pmo["i2"], equal_nan=True)
             assert com["CQI"][o, u] == cqo[0, 0]
     # SENSING: explicit noise tensor (MATLAB's randn cannot be reproduced), oracle on the same grid / waveform
-    grid = W.cfg5_sensing_grid(scn, cell, frame)
+    grid = W.cfg5_sensing_grid(scn, cell)
     amp = 10.0 ** ((cellp["gNBTxPower"] - 30.0) / 20.0) * np.sqrt(wave["Nfft"] ** 2 / (grid.shape[0] * grid.shape[2]))
     txw = (amp * W.ofdm_modulate(grid, r["nrb"], r["scs"])).astype(np.complex64)
     noise = W.std_normal_complex(txw.shape, 77).astype(np.complex64)

@@ -53,5 +53,20 @@ t2)
   (timeout 1700 python -m pytest tests/test_cfg5_gpu.py tests/test_link_gpu.py -m gpu -q 2>&1 | tail -40) > gpurun_out/r2_t2_tests.log
   cat gpurun_out/r2_t2_tests.log
   ;;
+b1)
+  timeout 900 python bench.py > gpurun_out/r2_b1_bench.json 2> gpurun_out/r2_b1_bench.err; tail -n 5 gpurun_out/r2_b1_bench.err; cut -c1-3000 gpurun_out/r2_b1_bench.json
+  timeout 900 python bench.py --workload cfg5 --steps 5 --warmup 2 > gpurun_out/r2_b1_cfg5.json 2> gpurun_out/r2_b1_cfg5.err; tail -n 5 gpurun_out/r2_b1_cfg5.err; cut -c1-2000 gpurun_out/r2_b1_cfg5.json
+  ;;
+b2)
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --workload cfg5 --steps 5 --warmup 2 > gpurun_out/r2_b2_cfg5_n2.json 2> gpurun_out/r2_b2_cfg5_n2.err; tail -n 5 gpurun_out/r2_b2_cfg5_n2.err; cut -c1-2000 gpurun_out/r2_b2_cfg5_n2.json
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_b2_cfg2_n2.json 2> gpurun_out/r2_b2_cfg2_n2.err; tail -n 3 gpurun_out/r2_b2_cfg2_n2.err; cut -c1-600 gpurun_out/r2_b2_cfg2_n2.json
+  ;;
+rdm1)
+  (timeout 600 python -m pytest tests/test_rdm_gpu.py tests/test_sensing_gpu.py tests/test_golden_gpu.py tests/test_properties_gpu.py -m gpu -q -x 2>&1 | tail -5) > gpurun_out/r2_rdm1_tests.log; cat gpurun_out/r2_rdm1_tests.log
+  for v in "ISAC_CFAR_FUSED=0" "ISAC_CFAR_FUSED=1" "ISAC_RDM_DIRECT=2 ISAC_RDM_HINTS=0x349" "ISAC_RDM_DIRECT=3 ISAC_RDM_HINTS=0x349" "ISAC_RDM_DIRECT=4 ISAC_RDM_HINTS=0x349" "ISAC_RDM_DIRECT=3"; do
+    echo "== $v"; env $v timeout 300 python tools/dev_rdm_bench.py 0 2>&1 | grep "variant=0"
+  done > gpurun_out/r2_rdm1_variants.log 2>&1
+  cat gpurun_out/r2_rdm1_variants.log
+  ;;
 *) echo "unknown step $step"; exit 1;;
 esac
