@@ -13,7 +13,7 @@ class CDLChannel:
     H[K x L x nRx x nTx] that nrChannelEstimate would hand to riSelect/cqiSelect (uePhy.m:897-907).
     Statistical parity only (see csrc/cdl.cu)."""
 
-    PROFILES = {"CDL-A": 0, "CDL-C": 2, "CDL-D": 3}
+    PROFILES = {"CDL-A": 0, "CDL-B": 1, "CDL-C": 2, "CDL-D": 3, "CDL-E": 4}
 
     def __init__(self, DelayProfile="CDL-D", DelaySpread=300e-9, CarrierFrequency=3.5e9, MaximumDopplerShift=5.0,
                  TransmitAntennaArraySize=(1, 8, 2), ReceiveAntennaArraySize=(1, 1, 2), TransmitElement="38.901",

@@ -379,7 +379,7 @@ int isac_prg_precode_batch_dev(isac_ctx* ctx, int32_t K, int32_t Lsym, int32_t n
  * configured at +parameters/+channelModels/+communication/cdl.m:48-88, profile chosen by
  * communication.channelModels.updateCDLModels.m:7-15).  Statistical parity only (toolbox RNG stream). */
 typedef struct {
-    int32_t profile;         /* 0 CDL-A, 2 CDL-C, 3 CDL-D                    cdl.m:58 / updateCDLModels.m:11-13 */
+    int32_t profile;         /* 0 CDL-A, 1 CDL-B, 2 CDL-C, 3 CDL-D, 4 CDL-E      cdl.m:58 / updateCDLModels.m:11-13 */
     double delaySpread;      /* channel.DelaySpread = 300e-9                 cdl.m:59 */
     double fc;               /* channel.CarrierFrequency                     cdl.m:60 */
     double maxDoppler;       /* MaximumDopplerShift (toolbox default 5 Hz) */

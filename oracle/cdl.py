@@ -42,7 +42,24 @@ CDL_D = np.array([
     [2.596, -21.9, 13, 163, 97.5, 79.4], [1.775, -22.9, 34.6, -137, 98.5, 78.2], [4.042, -27.8, -64.5, 74.5, 88.4, 73.6],
     [7.937, -23.6, -32.9, 127.7, 91.3, 78.3], [9.424, -24.8, 52.6, -119.6, 103.8, 87], [9.708, -30.0, -132.1, -9.1, 80.3, 70.6],
     [12.525, -27.7, 77.2, -83.8, 86.5, 72.9]])
-PROFILES = {0: (CDL_A, (5, 11, 3, 3), 10.0, None), 2: (CDL_C, (2, 15, 3, 7), 7.0, None), 3: (CDL_D, (5, 8, 3, 3), 11.0, -0.2)}
+# TR 38.901 Tables 7.7.1-2 (CDL-B) and 7.7.1-5 (CDL-E; first row = Rayleigh part of the LOS cluster, specular path -0.03 dB)
+CDL_B = np.array([
+    [0.0000, 0, 9.3, -173.3, 105.8, 78.9], [0.1072, -2.2, 9.3, -173.3, 105.8, 78.9], [0.2155, -4, 9.3, -173.3, 105.8, 78.9],
+    [0.2095, -3.2, -34.1, 125.5, 115.3, 63.3], [0.2870, -9.8, -65.4, -88.0, 119.3, 59.9], [0.2986, -1.2, -11.4, 155.1, 103.2, 67.5],
+    [0.3752, -3.4, -11.4, 155.1, 103.2, 67.5], [0.5055, -5.2, -11.4, 155.1, 103.2, 67.5], [0.3681, -7.6, -67.2, -89.8, 118.2, 82.6],
+    [0.3697, -3, 52.5, 132.1, 102.0, 66.3], [0.5700, -8.9, -72, -83.6, 100.4, 61.6], [0.5283, -9, 74.3, 95.3, 98.3, 58.0],
+    [1.1021, -4.8, -52.2, 103.7, 103.4, 78.2], [1.2756, -5.7, -50.5, -87.8, 102.5, 82.0], [1.5474, -7.5, 61.4, -92.5, 101.4, 62.4],
+    [1.7842, -1.9, 30.6, -139.1, 103.0, 78.0], [2.0169, -7.6, -72.5, -90.6, 100.0, 60.9], [2.8294, -12.2, -90.6, 58.6, 115.2, 82.9],
+    [3.0219, -9.8, -77.6, -79.0, 100.5, 60.8], [3.6187, -11.4, -82.6, 65.8, 119.6, 57.3], [4.1067, -14.9, -103.6, 52.7, 118.7, 59.9],
+    [4.2790, -9.2, 75.6, 88.7, 117.8, 60.1], [4.7834, -11.3, -77.6, -60.4, 115.7, 62.3]])
+CDL_E = np.array([
+    [0, -22.03, 0, -180, 99.6, 80.4], [0.5133, -15.8, 57.5, 18.2, 104.2, 80.4], [0.5440, -18.1, 57.5, 18.2, 104.2, 80.4],
+    [0.5630, -19.8, 57.5, 18.2, 104.2, 80.4], [0.5440, -22.9, -20.1, 101.8, 99.4, 80.8], [0.7112, -22.4, 16.2, 112.9, 100.8, 86.3],
+    [1.9092, -18.6, 9.3, -155.5, 98.8, 82.7], [1.9293, -20.8, 9.3, -155.5, 98.8, 82.7], [1.9589, -22.6, 9.3, -155.5, 98.8, 82.7],
+    [2.6426, -22.3, 19, -143.3, 100.8, 82.9], [3.7136, -25.6, 32.7, -94.7, 96.4, 88], [5.4524, -20.2, 0.5, 147, 98.9, 81],
+    [12.0034, -29.8, 55.9, -36.2, 95.6, 88.6], [20.6519, -29.2, 57.6, -26, 104.6, 78.3]])
+PROFILES = {0: (CDL_A, (5, 11, 3, 3), 10.0, None), 1: (CDL_B, (10, 22, 3, 7), 8.0, None), 2: (CDL_C, (2, 15, 3, 7), 7.0, None),
+            3: (CDL_D, (5, 8, 3, 3), 11.0, -0.2), 4: (CDL_E, (5, 11, 3, 7), 8.0, -0.03)}
 
 
 class SplitMix64:

@@ -11,7 +11,7 @@ PKG = "5g_based_system_level_integrated_sensing_and_communication_simulator_b200
 
 
 def test_oracle_pdp_and_k_factor():
-    for prof in (0, 2, 3):
+    for prof in (0, 1, 2, 3, 4):
         r = OC.build_rays(prof, 300e-9, 5.0, (1, 1, 1), (1, 1, 1), False, False, 7)
         # single vertical isotropic element: |g_m|^2 summed per cluster == normalised cluster power
         pw = np.array([np.sum(np.abs(r["g"][r["cluster"] == n][:20]) ** 2) for n in range(r["tau"].size)])
@@ -21,13 +21,19 @@ def test_oracle_pdp_and_k_factor():
     d = OC.build_rays(3, 300e-9, 5.0, (1, 1, 1), (1, 1, 1), False, False, 1)
     assert abs(10 * np.log10(d["plos"] / d["power"][0]) - 13.3) < 1e-9          # CDL-D K-factor (Table 7.7.1-4)
     assert abs(np.abs(d["g"][-1, 0, 0]) ** 2 - d["plos"]) < 1e-12
+    e = OC.build_rays(4, 300e-9, 5.0, (1, 1, 1), (1, 1, 1), False, False, 1)
+    assert abs(10 * np.log10(e["plos"] / e["power"][0]) - 22.0) < 1e-9          # CDL-E K-factor (Table 7.7.1-5)
     assert OC.CDL_A.shape == (23, 6) and OC.CDL_C.shape == (24, 6) and OC.CDL_D.shape == (13, 6)
+    assert OC.CDL_B.shape == (23, 6) and OC.CDL_E.shape == (14, 6)
+    # the strongest cluster of every NLOS table is at 0 dB; mean delays (power-weighted, normalised) of the tables
+    assert OC.CDL_A[:, 1].max() == 0 and OC.CDL_B[:, 1].max() == 0 and OC.CDL_C[:, 1].max() == 0
     assert abs(OC.pattern38901(90.0, 0.0) - 10 ** 0.8) < 1e-12 and abs(OC.pattern38901(90.0, 180.0) - 10 ** (-2.2)) < 1e-12
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("prof,name,tx,rx", [(3, "CDL-D", (1, 4, 2), (1, 1, 2)), (0, "CDL-A", (1, 8, 2), (1, 1, 2)),
-                                             (2, "CDL-C", (1, 4, 2), (2, 2, 2))])
+                                             (2, "CDL-C", (1, 4, 2), (2, 2, 2)), (1, "CDL-B", (1, 4, 2), (1, 1, 2)),
+                                             (4, "CDL-E", (1, 2, 2), (1, 2, 2))])
 def test_cdl_rays_and_frequency_response(gpu, prof, name, tx, rx):
     cm = importlib.import_module(PKG + ".communication.channelModels")
     ch = cm.CDLChannel(DelayProfile=name, TransmitAntennaArraySize=tx, ReceiveAntennaArraySize=rx, Seed=1234)
