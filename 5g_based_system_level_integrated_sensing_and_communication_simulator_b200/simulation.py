@@ -241,6 +241,15 @@ class HotPath:
                     self.keep_H.append(([cellps[g[0]]["cellID"] for g in grp], o, H.cpu().numpy(), nvar.copy()))
                 RI, pm, cq = self.ph.csiReport(self.carrier, self.csirs, self.rc, H, nvar, self.table, rankCap=4)   # uePhy.m:900-907
                 m = len(grp)
+                if scn.get("sinr_grid"):   # BASELINE config 3: the per-PRB SINR grid at the reported rank (info.SINRPerRE, dlPMISelect.m:505)
+                    ranks = np.atleast_1d(RI)
+                    for nu in sorted({int(x) for x in ranks if not np.isnan(x)}):
+                        sel = [j for j in range(m) if ranks[j] == nu]
+                        _, info = self.ph.dlPMISelect(self.carrier, self.csirs, self.rc, nu, H[sel], nvar[sel])
+                        S = np.asarray(info["SINRPerRE"])
+                        S = S.reshape(S.shape + (1,)) if len(sel) == 1 else S
+                        for q, j in enumerate(sel):
+                            recs[grp[j][0]].setdefault("sinrGridSum", np.zeros(len(recs[grp[j][0]]["ueIDs"])))[grp[j][1]] = np.nansum(S[..., q])
                 RI, i1, i2 = np.atleast_1d(RI), np.asarray(pm["i1"]).reshape(3, m), np.asarray(pm["i2"]).reshape(nSB, m)
                 cq = np.asarray(cq).reshape(np.asarray(cq).shape[0], -1, m)
                 for j, g in enumerate(grp):
@@ -326,9 +335,10 @@ def pack_record(hp, com, sen):
     """Fixed-size float64 record of a cell-frame (NaN padded) -- what the ranks exchange."""
     n, U = com["ueIDs"].size, hp.maxUE
     nOcc, nSB, nSrs = com["RI"].shape[0], hp.nSB, com["ulPMI"].shape[0]
-    ue = np.full((U, 1 + nOcc * (5 + nSB) + nSrs * nSB), np.nan)
+    ue = np.full((U, 2 + nOcc * (5 + nSB) + nSrs * nSB), np.nan)
+    grid = com.get("sinrGridSum")
     for q in range(n):
-        row = [float(com["ueIDs"][q])]
+        row = [float(com["ueIDs"][q]), np.nan if grid is None else float(grid[q])]   # checksum of the per-PRB SINR grid (cfg3)
         for o in range(nOcc):
             row += [com["RI"][o, q], *com["i1"][o, :, q], com["CQI"][o, q], *com["i2"][o, :, q]]
         for o in range(nSrs):

@@ -148,6 +148,9 @@ RADIO = {
     "shipped": dict(nrb=273, scs=30, nV=8, p=2, ue_ants=2, csirs_ports=4, panel=(2, 1), subband=16, num_slots=20),
     # same structure at 24 PRB / 15 kHz / 4 Tx for tests whose oracle has to finish in seconds
     "small": dict(nrb=24, scs=15, nV=2, p=2, ue_ants=2, csirs_ports=4, panel=(2, 1), subband=4, num_slots=10),
+    # BASELINE config 3: 64-element gNB array virtualised onto 32 CSI-RS ports (4,4) -- the largest Type-I port count
+    # (dlPMISelect.m:623-626) --, 4-antenna UEs, 273 PRB; the 16-element Rx sub-array serves the 2-port SRS
+    "cfg3": dict(nrb=273, scs=30, nV=8, p=2, ue_ants=4, csirs_ports=32, panel=(4, 4), subband=16, num_slots=20),
 }
 
 
@@ -239,3 +242,22 @@ def cfg5_sensing_grid(scn: dict, cell: int) -> np.ndarray:
     r = RADIO[scn["radio"]]
     nsym = 14 * int(round(3 / 5 * r["num_slots"]))
     return qpsk_grid(12 * r["nrb"], nsym, r["nV"] * r["p"], 1_000_003 * scn["seed"] + 1009 * cell)
+
+
+def scenario_cfg3(seed: int = 3, ue_per_cell: int = 4, radius: float = 500.0) -> dict:
+    """BASELINE config 3: 7 hexagonal cells (centre + first ring of the reference's lattice, generateWrapAround.m:94-150,
+    radius 500 m), ``ue_per_cell`` UEs dropped uniformly in each cell, 32-port Type-I reports + the per-PRB SINR grid; no radar
+    targets (the configuration is about the COMM half).  Same structure as scenario_cfg5."""
+    rng = np.random.default_rng(seed)
+    dx, dy = 1.5 * radius, radius * math.sqrt(3.0) / 2.0
+    sites = [(0, 0)] + [(i, j) for i, j in ((0, 2), (1, 1), (1, -1), (0, -2), (-1, -1), (-1, 1))]
+    gnb = np.array([[i * dx, j * dy, 25.0] for i, j in sites])
+    n_ue = 7 * ue_per_cell
+    ue_cell = np.repeat(np.arange(7), ue_per_cell)
+    rr, az = radius * 0.9 * np.sqrt(rng.uniform(0.01, 1.0, n_ue)), rng.uniform(0, 2 * np.pi, n_ue)
+    ue = gnb[ue_cell] + np.column_stack([rr * np.cos(az), rr * np.sin(az), np.zeros(n_ue)])
+    ue[:, 2] = 1.5
+    return {"gnb": gnb, "ue": ue, "ue_cell": ue_cell, "target0": np.zeros((0, 3)), "target_vel": np.zeros((0, 3)),
+            "target_cell": np.zeros(0, dtype=int), "rcs": np.zeros(0), "radio": "cfg3", "seed": seed,
+            "load": rng.uniform(0.5, 1.0, (7, 64)), "frame_time": 10e-3, "fc": 3.5e9, "txPower": 46.0, "rxGainUE": 0.0,
+            "noiseFigureUE": 9.0, "scenario": "UMa", "sinr_grid": True}

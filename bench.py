@@ -565,10 +565,17 @@ def run_cfg5(args):
     P = importlib.import_module(PKG)
     sim = importlib.import_module(PKG + ".simulation")
     W = P.workloads
-    scn = W.scenario_cfg5(radio=args.cfg5_radio)
-    z = np.load(os.path.join(ROOT, "tests", "golden", "osm_city.npz"))
-    off = z["fp_off"]
-    buildings = [(z["fp_flat"][:, off[i]:off[i + 1]], float(z["heights"][i])) for i in range(off.size - 1)]
+    if args.workload == "cfg3":      # BASELINE config 3: 7-cell hex, 4 UE/cell, 32-port Type-I reports + per-PRB SINR grid, no city
+        scn, buildings = W.scenario_cfg3(), None
+        wl = ("cfg3: 7-cell hex, 4 UE/cell, 64-element array on 32 CSI-RS ports (4,4), Type-I reports of every rank + per-PRB SINR "
+              "grid, 273 PRB, one frame of all cells per step, cells sharded over the GPUs")
+    else:
+        scn = W.scenario_cfg5(radio=args.cfg5_radio)
+        z = np.load(os.path.join(ROOT, "tests", "golden", "osm_city.npz"))
+        off = z["fp_off"]
+        buildings = [(z["fp_flat"][:, off[i]:off[i + 1]], float(z["heights"][i])) for i in range(off.size - 1)]
+        wl = ("cfg5: openStreetMapCity scenario, 19 gNB / 100 UE / 20 moving targets, %d PRB, one frame of all cells per step, "
+              "cells sharded over the GPUs" % W.RADIO[scn["radio"]]["nrb"])
     hp = sim.HotPath(scn, device=local, city_buildings=buildings)
     ctx = hp.ctx
     n_cells = scn["gnb"].shape[0]
@@ -612,9 +619,7 @@ def run_cfg5(args):
         line = {"metric": "cell_subframes_per_sec", "value": round(value, 2), "unit": "cell-subframes/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t / args.steps * 1e3, 3), "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32 (PMI / MUSIC / CFAR compare in f64)", "data": "synthetic",
-                "config": {"workload": "cfg5: openStreetMapCity scenario, 19 gNB / 100 UE / 20 moving targets, %d PRB, one frame of all "
-                                       "cells per step, cells sharded over the GPUs" % r["nrb"],
-                           "cells": n_cells, "shard_sizes": [len(sim.shard_cells(n_cells, world, q)) for q in range(world)],
+                "config": {"workload": wl, "cells": n_cells, "shard_sizes": [len(sim.shard_cells(n_cells, world, q)) for q in range(world)],
                            "collectives_in_timed_region": ["all_gather(tx summaries [cells x 5] f64)", "all_gather(records [cells x %d] f64)" % recs[0].shape[1]],
                            "l2_policy": "every cell-frame streams fresh grids / waveforms (> L2 per rank at the shipped radio); no flush"},
                 "e2e": {"value": round(value, 2), "unit": "cell-subframes/s", "h2d_bytes_per_step": int(h2d),
@@ -786,8 +791,9 @@ def main():
     ap.add_argument("--cells-per-gpu", type=int, default=4)
     ap.add_argument("--frames-per-step", type=int, default=10,
                     help="frames of every cell per step (cfg2): 10 frames x 4 cells = 400 cell-subframes per step, a >= 1 s timed region at K = 20")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"],
-                    help="cfg2 (default): weak scaling, cells_per_gpu cells per GPU; cfg5: the 19-cell openStreetMapCity scenario, strong scaling")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
+                    help="cfg2 (default): weak scaling, cells_per_gpu cells per GPU; cfg3 / cfg5: the 7-cell 32-port and the 19-cell "
+                         "openStreetMapCity scenarios, strong scaling (cells sharded over the GPUs)")
     ap.add_argument("--cfg5-radio", default="shipped", choices=["shipped", "small"])
     ap.add_argument("--skip-host-h", action="store_true", help="skip the host-resident-H occasion measurement of the e2e object")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
@@ -797,7 +803,7 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    if args.workload == "cfg5":
+    if args.workload in ("cfg3", "cfg5"):
         run_cfg5(args)
         return
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 or int(os.environ.get("RANK", "0")) > 0:

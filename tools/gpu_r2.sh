@@ -68,5 +68,10 @@ rdm1)
   done > gpurun_out/r2_rdm1_variants.log 2>&1
   cat gpurun_out/r2_rdm1_variants.log
   ;;
+b3)
+  (timeout 900 python -m pytest tests/test_cfg5_gpu.py tests/test_cdl.py -m gpu -q 2>&1 | tail -5)
+  timeout 900 python bench.py --workload cfg3 --steps 5 --warmup 2 > gpurun_out/r2_b3_cfg3.json 2> gpurun_out/r2_b3_cfg3.err; tail -n 5 gpurun_out/r2_b3_cfg3.err; cut -c1-1500 gpurun_out/r2_b3_cfg3.json
+  timeout 900 python bench.py --workload cfg5 --steps 10 --warmup 3 > gpurun_out/r2_b3_cfg5.json 2> gpurun_out/r2_b3_cfg5.err; tail -n 5 gpurun_out/r2_b3_cfg5.err; cut -c1-300 gpurun_out/r2_b3_cfg5.json
+  ;;
 *) echo "unknown step $step"; exit 1;;
 esac
