@@ -152,6 +152,7 @@ def _declare(lib):
         "isac_precoded_sinr_host": ([vp, vp, i32, i32, f64, vp, i32, i32, vp], C.c_int),
         "isac_pmi_plan_set_kernel": ([vp, i32], C.c_int),
         "isac_csi_plan_set_kernel": ([vp, i32], C.c_int),
+        "isac_csi_plan_mp_dims": ([vp, i32, P(i32)], C.c_int),
         "isac_pmi_plan_mp_dims": ([vp, P(i32)], C.c_int),
         "isac_pmi_plan_info": ([vp, P(i32), P(i32), P(i32), P(i32), vp, vp], C.c_int),
         "isac_dl_pmi_select_dev": ([vp, vp, vp, i32], C.c_int),

@@ -202,13 +202,31 @@ def _pmi_plan(cs, nLayers, batch, device=None):
     return ctx, ent[0]
 
 
-def _single_panel_only(cs, what):
-    if int(cs.v.get("Ng", 0)) >= 2:
-        raise NotImplementedError(f"{what}: Type1MultiPanel reports are covered by dlPMISelect only (DESIGN.md section 6)")
+def _mp_unflatten(ctx, plan, cs, ranks, i1, i2):
+    """Type1MultiPanel report: the plan returns i1[2] / i2 as linear indices into the flattened index sets of the rank that was
+    reported (isac_csi_plan_mp_dims); bring PMISet into the reference's form {i1 [6 x B], i2 [3 x nSB x B]}
+    (dlPMISelect.m:456-457, :489).  ``ranks``: the rank of every batch entry (NaN -> all-NaN PMISet)."""
+    B, nSB = i1.shape[1], i2.shape[0]
+    i1o = np.full((6, B), np.nan, order="F")
+    i2o = np.full((3, nSB, B), np.nan, order="F")
+    cache = {}
+    for b in range(B):
+        if np.isnan(ranks[b]) or np.any(np.isnan(i1[:, b])):
+            continue
+        nu = int(ranks[b])
+        if nu not in cache:
+            mp = (C.c_int32 * 7)()
+            _lib.check(ctx.lib.isac_csi_plan_mp_dims(plan, nu, mp), ctx.handle)
+            cache[nu] = [int(x) for x in mp]
+        mp = cache[nu]
+        i1o[:, b] = [i1[0, b], i1[1, b]] + [x + 1 for x in np.unravel_index(int(i1[2, b]) - 1, tuple(mp[3:7]), order="F")]
+        for sb in range(nSB):
+            if not np.isnan(i2[sb, b]):
+                i2o[:, sb, b] = [x + 1 for x in np.unravel_index(int(i2[sb, b]) - 1, tuple(mp[0:3]), order="F")]
+    return i1o, i2o
 
 
 def _csi_plan(cs, batch, device=None):
-    _single_panel_only(cs, "riSelect / cqiSelect / csiReport")
     ctx = _lib.get_context(device)
     key = cs.key() + (ctx.device,)
     ent = _csi_plans.get(key)
@@ -327,6 +345,13 @@ def riSelect(carrier, csirs, reportConfig, H, nVar=1e-10):
     i2 = np.zeros((nSB, B), order="F")
     ctx.use_torch_stream()
     _lib.check(ctx.lib.isac_ri_select_dev(plan, _lib.ptr(Hd), _lib.ptr(nv), B, _lib.ptr(RI), _lib.ptr(i1), _lib.ptr(i2)), ctx.handle)
+    if int(cs.v.get("Ng", 0)) >= 2:
+        # all-NaN totals: the reference returns the PMISet of the last valid rank (riSelect.m:289-292)
+        last = max((r + 1 for r in range(min(R, P, 4)) if cs.v["rir"][r]), default=1)
+        i1, i2 = _mp_unflatten(ctx, plan, cs, np.where(np.isnan(RI), float(last), RI), i1, i2)
+        if B == 1:
+            return float(RI[0]), {"i1": i1[:, 0], "i2": i2[:, :, 0]}
+        return RI, {"i1": i1, "i2": i2}
     if B == 1:
         return float(RI[0]), {"i1": i1[:, 0], "i2": i2[:, 0]}
     return RI, {"i1": i1, "i2": i2}
@@ -369,6 +394,11 @@ def cqiSelect(carrier, csirs, reportConfig, nLayers, H, nVar, SINRTable):
     ncw = int(math.ceil(nLayers / 4))
     cqi = cqi[: rows.value * 2 * B].reshape((rows.value, 2, B), order="F")[:, :ncw]
     sb = sb.reshape((rows_full, 2, B), order="F")[:, :ncw]
+    if int(cs.v.get("Ng", 0)) >= 2:
+        i1, i2 = _mp_unflatten(ctx, plan, cs, np.full(B, float(nLayers)), i1, i2)
+        if B == 1:
+            return cqi[..., 0], {"i1": i1[:, 0], "i2": i2[:, :, 0]}, {"SINRPerSubbandPerCW": sb[..., 0]}
+        return cqi, {"i1": i1, "i2": i2}, {"SINRPerSubbandPerCW": sb}
     if B == 1:
         return cqi[..., 0], {"i1": i1[:, 0], "i2": i2[:, 0]}, {"SINRPerSubbandPerCW": sb[..., 0]}
     return cqi, {"i1": i1, "i2": i2}, {"SINRPerSubbandPerCW": sb}
@@ -378,9 +408,9 @@ class PendingCsiReport:
     """A CSI report whose kernels are enqueued (csiReportEnqueue); ``finish()`` waits for its results only -- work enqueued
     on the stream in between keeps the GPU busy during the host-side RI / CQI tails."""
 
-    def __init__(self, ctx, plan, Hd, B, nSB, nC, table, rankCap):
+    def __init__(self, ctx, plan, Hd, B, nSB, nC, table, rankCap, cs=None):
         self.ctx, self.plan, self.Hd, self.B, self.nSB, self.nC = ctx, plan, Hd, B, nSB, nC    # Hd kept alive until finish()
-        self.table, self.rankCap = table, int(rankCap)
+        self.table, self.rankCap, self.cs = table, int(rankCap), cs
 
     def finish(self):
         B = self.B
@@ -393,6 +423,11 @@ class PendingCsiReport:
                                                        _lib.ptr(i1), _lib.ptr(i2), _lib.ptr(cqi), C.byref(rows)), self.ctx.handle)
         cqi = cqi[: rows.value * 2 * B].reshape((rows.value, 2, B), order="F")
         self.Hd = None
+        if self.cs is not None and int(self.cs.v.get("Ng", 0)) >= 2:
+            i1, i2 = _mp_unflatten(self.ctx, self.plan, self.cs, RI, i1, i2)
+            if B == 1:
+                return float(RI[0]), {"i1": i1[:, 0], "i2": i2[:, :, 0]}, cqi[..., 0]
+            return RI, {"i1": i1, "i2": i2}, cqi
         if B == 1:
             return float(RI[0]), {"i1": i1[:, 0], "i2": i2[:, 0]}, cqi[..., 0]
         return RI, {"i1": i1, "i2": i2}, cqi
@@ -410,7 +445,7 @@ def csiReportEnqueue(carrier, csirs, reportConfig, H, nVar, SINRTable, rankCap=4
     table = np.ascontiguousarray(SINRTable, dtype=np.float64)
     ctx.use_torch_stream()
     _lib.check(ctx.lib.isac_csi_report_enqueue_dev(plan, _lib.ptr(Hd), _lib.ptr(nv), B), ctx.handle)
-    return PendingCsiReport(ctx, plan, Hd, B, nSB, nC, table, rankCap)
+    return PendingCsiReport(ctx, plan, Hd, B, nSB, nC, table, rankCap, cs)
 
 
 def csiReport(carrier, csirs, reportConfig, H, nVar, SINRTable, rankCap=4):

@@ -937,11 +937,14 @@ int isac_dl_pmi_get_info(isac_pmi_plan* pl, int32_t batch, double* sinrPerRE, do
     return pmi_get_sinr_arrays(pl->p, batch, sinrPerRE, sinrPerSubband);
 }
 
+// riSelect.m:222-231: ranks 1..min(nRx, nPorts), at most 4 with a Type1MultiPanel codebook
+static int csi_max_rank(const CsiConfig& c) {
+    int m = c.nRx < c.nPorts ? c.nRx : c.nPorts;
+    if (c.nPanels >= 2 && m > 4) m = 4;
+    return m < kMaxLayers ? m : kMaxLayers;
+}
+
 int isac_csi_plan_create(isac_ctx* h, const isac_csi_config* cfg, int32_t maxBatch, isac_csi_plan** out) {
-    if (h && cfg && cfg->nPanels >= 2) {   // RI / CQI reports: Type1SinglePanel only (dlPMISelect covers Type1MultiPanel)
-        set_error(&h->c, "csi_plan_create: Type1MultiPanel reports are supported by the dlPMISelect entry points only");
-        return ISAC_ERR_UNSUPPORTED;
-    }
     if (!h || !cfg || !out) return ISAC_ERR_INVALID_ARG;
     cudaSetDevice(h->c.device);
     isac_csi_plan* pl = new isac_csi_plan();
@@ -949,7 +952,7 @@ int isac_csi_plan_create(isac_ctx* h, const isac_csi_config* cfg, int32_t maxBat
     pl->cfg = to_csi_config(cfg);
     pl->maxBatch = maxBatch;
     for (int r = 0; r < kMaxLayers; ++r) pl->byRank[r] = nullptr;
-    const int maxRank = pl->cfg.nRx < pl->cfg.nPorts ? pl->cfg.nRx : pl->cfg.nPorts;  // riSelect.m:222
+    const int maxRank = csi_max_rank(pl->cfg);  // riSelect.m:222
     PmiShared* share = nullptr;  // ranks built from the same beams share one Gram-pair dictionary -> one fused SINR launch
     // report plans never return SINRPerRE: subband sums are accumulated inside the SINR kernel (ISAC_PMI_FUSED=0: per-RE path)
     const bool fused = !(getenv("ISAC_PMI_FUSED") && atoi(getenv("ISAC_PMI_FUSED")) == 0);
@@ -995,7 +998,13 @@ int isac_csi_plan_destroy(isac_csi_plan* pl) {
 int isac_csi_plan_set_kernel(isac_csi_plan* pl, int32_t direct) {
     if (!pl) return ISAC_ERR_INVALID_ARG;
     for (int r = 0; r < kMaxLayers; ++r)
-        if (pl->byRank[r]) pl->byRank[r]->direct = direct != 0;
+        if (pl->byRank[r]) pl->byRank[r]->direct = direct != 0 || pl->cfg.nPanels >= 2;   // multi-panel: direct kernel only
+    return ISAC_OK;
+}
+
+int isac_csi_plan_mp_dims(const isac_csi_plan* pl, int32_t nLayers, int32_t mpDims[7]) {
+    if (!pl || !mpDims || nLayers < 1 || nLayers > kMaxLayers || !pl->byRank[nLayers - 1]) return ISAC_ERR_INVALID_ARG;
+    for (int i = 0; i < 7; ++i) mpDims[i] = pl->byRank[nLayers - 1]->tab.mp[i];
     return ISAC_OK;
 }
 
@@ -1003,7 +1012,7 @@ int isac_csi_plan_set_kernel(isac_csi_plan* pl, int32_t direct) {
 // Kernels of every valid rank + the asynchronous D2H copy of the selection arena; no synchronisation.
 static int ri_enqueue(isac_csi_plan* pl, const float2* H, const double* nVar, int batch) {
     Ctx* c = pl->ctx;
-    const int maxRank = pl->cfg.nRx < pl->cfg.nPorts ? pl->cfg.nRx : pl->cfg.nPorts;
+    const int maxRank = csi_max_rank(pl->cfg);
     pl->pendH = H;
     pl->pendNVar.assign(nVar, nVar + batch);
     pl->pendBatch = batch;
@@ -1028,7 +1037,7 @@ static int ri_finish(isac_csi_plan* pl, std::vector<double>& RI, std::vector<Pmi
     const int batch = pl->pendBatch;
     if (batch < 1) { set_error(c, "csi report: nothing enqueued"); return kErrInvalidArg; }
     pl->pendBatch = 0;
-    const int maxRank = pl->cfg.nRx < pl->cfg.nPorts ? pl->cfg.nRx : pl->cfg.nPorts;
+    const int maxRank = csi_max_rank(pl->cfg);
     all.assign(kMaxLayers, {});
     std::vector<int> valid;
     for (int r = 1; r <= maxRank && r <= kMaxLayers; ++r)

@@ -313,6 +313,10 @@ typedef struct isac_csi_plan isac_csi_plan;
 /* One plan per report configuration: holds the per-rank PMI plans (riSelect.m:254 loops over the valid ranks). */
 int isac_csi_plan_create(isac_ctx* ctx, const isac_csi_config* cfg, int32_t maxBatch, isac_csi_plan** plan);
 int isac_csi_plan_destroy(isac_csi_plan* plan);
+/* Type1MultiPanel reports (cfg->nPanels = Ng >= 2; ranks 1-4, riSelect.m:222-231): i1[2] and i2 come back as linear indices
+ * into the flattened index sets [i13 i141 i142 i143] and [i20 i21 i22] of the reported rank (MATLAB order); mpDims = their
+ * lengths [i20 i21 i22 i13 i141 i142 i143] at `nLayers`, for ind2sub on the caller's side (zeros for a single-panel plan). */
+int isac_csi_plan_mp_dims(const isac_csi_plan* plan, int32_t nLayers, int32_t mpDims[7]);
 int isac_csi_plan_set_kernel(isac_csi_plan* plan, int32_t direct);   /* as isac_pmi_plan_set_kernel, all ranks */
 /* [RI,PMISet] = communication.phyLayer.riSelect(carrier,csirs,reportConfig,H,nVar) (riSelect.m:1).
  * RI [batch] (NaN when nothing is reportable), i1 [3 x batch], i2 [nSB x batch]. */

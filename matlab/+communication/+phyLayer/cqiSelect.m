@@ -9,8 +9,8 @@ function [CQI, PMISet, CQIInfo, PMIInfo] = cqiSelect(carrier, csirs, reportConfi
     if nargin >= 7, SINRTable = varargin{2}; end
     if isempty(SINRTable), t = communication.setupSINRtoCQIMappingTable(); SINRTable = t.downlinkSINR90pc; end
     [cfg, rc] = communication.phyLayer.isacCsiConfig(carrier, csirs, reportConfig, nLayers, H, nVar);
-    [~, i1, i2, CQI, sbcw] = isac_csi_report_mex(cfg, single(H), double(nVar), double(SINRTable(:)), 0, 2, nLayers);
-    PMISet.i1 = i1(:).'; PMISet.i2 = i2(:).';
+    [~, i1, i2, CQI, sbcw, mp] = isac_csi_report_mex(cfg, single(H), double(nVar), double(SINRTable(:)), 0, 2, nLayers);
+    PMISet = communication.phyLayer.isacPMISet(cfg, i1, i2, mp);
     nCW = ceil(nLayers/4);
     CQI = CQI(:, 1:nCW);                          % one codeword up to four layers (cqiSelect.m:576-632)
     if nargout < 3, return; end
@@ -33,7 +33,7 @@ function out = sinrPerRB(SINRPerRE, PMISet, cfg, rc, carrier, nCW)
 % add the layers of a codeword (nrLayerDemap: floor(nu/2) layers in codeword 1 when nu > 4), average the REs of an RB.
     nRB = rc.NSizeBWP; L = carrier.SymbolsPerSlot; nu = size(SINRPerRE, 3);
     out = NaN(nRB, L, nCW);
-    if any(isnan(PMISet.i1)), return; end
+    if any(isnan(PMISet.i1)) || cfg.nPanels >= 2, return; end   % multi-panel: SINRPerRBPerCW is left NaN (11-D slices of :734-736)
     if cfg.pmiSubband && cfg.subbandSize > 0 && nRB >= 24   % PMI subband sizes (getDownlinkPMISubbandInfo, dlPMISelect.m:1836-1887)
         first = cfg.subbandSize - mod(rc.NStartBWP, cfg.subbandSize);
         sizes = first;

@@ -1,10 +1,12 @@
-/* [RI, i1, i2, CQI, SINRPerSubbandPerCW] = isac_csi_report_mex(cfg, H, nVar, SINRTable, rankCap, mode [, nLayers])
+/* [RI, i1, i2, CQI, SINRPerSubbandPerCW, mpDims] = isac_csi_report_mex(cfg, H, nVar, SINRTable, rankCap, mode [, nLayers])
  *   mode 0: fused UE report (uePhy.m:900-907): RI = min(riSelect(..), rankCap), then cqiSelect at that rank
  *   mode 1: [RI,PMISet] = riSelect(carrier,csirs,reportConfig,H,nVar)            (riSelect.m:1; CQI = [])
  *   mode 2: [CQI,PMISet] = cqiSelect(carrier,csirs,reportConfig,nLayers,H,nVar,SINRTable) (cqiSelect.m:1; RI = nLayers)
  *   H: single complex [K x L x nRx x P]; CQI [cqiRows x 2] (second codeword column NaN when nLayers <= 4).
  *   SINRPerSubbandPerCW (mode 2 only, else []): [rows x 2] linear SINR per codeword, wideband value first when there is more
- *   than one CQI subband (cqiSelect.m:610-633). */
+ *   than one CQI subband (cqiSelect.m:610-633).
+ *   Type1MultiPanel (cfg.nPanels = Ng >= 2): i1(3) and i2 are linear indices into the flattened index sets of the reported rank;
+ *   mpDims = [i20 i21 i22 i13 i141 i142 i143] lengths at that rank for ind2sub in the .m shim (zeros otherwise). */
 #include "isac_mex_common.h"
 
 static PlanCache<isac_csi_plan> g_plans(isac_csi_plan_destroy);
@@ -60,5 +62,12 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
             nCqiSB = (cs.c.nStartBWP % cs.c.subbandSize + cs.c.nSizeBWP + cs.c.subbandSize - 1) / cs.c.subbandSize;
         const int rowsFull = nCqiSB > 1 ? nCqiSB + 1 : 1;
         plhs[4] = mode == 2 ? double_array({(mwSize)rowsFull, 2}, sinrCW.data()) : mxCreateDoubleMatrix(0, 0, mxREAL);
+    }
+    if (nlhs > 5) {
+        int32_t mp[7] = {0, 0, 0, 0, 0, 0, 0};
+        const double r = RI[0];
+        if (cs.c.nPanels >= 2 && r == r && r >= 1) isac_mex_check(isac_csi_plan_mp_dims(plan, (int32_t)r, mp), fn);
+        std::vector<double> v(mp, mp + 7);
+        plhs[5] = double_array({1, 7}, v.data());
     }
 }

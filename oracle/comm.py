@@ -507,18 +507,56 @@ def _scatter(S, re_k, re_l, K, L):
 # ----------------------------------------------------------------------------------------------
 # a12: riSelect
 # ----------------------------------------------------------------------------------------------
-def ri_select(cfg, re_k, re_l, H, n_var=1e-10):
-    """``[RI,PMISet] = riSelect(carrier,csirs,reportConfig,H,nVar)`` (riSelect.m:198-294)."""
+def _mp_flat_codebook(cfg, n_panels, n_layers):
+    """Type1MultiPanel codebook with its 9-D index set flattened in MATLAB linear order to [i2', i11, i12, i13'] (see
+    dl_pmi_select_multi_panel), and the 9 index-set lengths."""
+    Wmp = type1_multi_panel_codebook(cfg, n_panels, n_layers)
+    P, nu = Wmp.shape[:2]
+    d = Wmp.shape[2:]
+    flat = (d[0] * d[1] * d[2], d[3], d[4], d[5] * d[6] * d[7] * d[8])
+    return np.asfortranarray(Wmp).reshape((P, nu) + flat, order="F"), d
+
+
+def mp_unflatten_pmi(pm, d):
+    """Flattened PMISet {i1 [3], i2 [nSB]} -> the multi-panel form {i1 [6], i2 [3 x nSB]} (dlPMISelect.m:456-457, :489)."""
+    n_sb = np.asarray(pm["i2"]).size
+    i1 = np.full(6, np.nan)
+    if not np.any(np.isnan(pm["i1"])):
+        i1[:2] = pm["i1"][:2]
+        i1[2:] = [x + 1 for x in np.unravel_index(int(pm["i1"][2]) - 1, d[5:9], order="F")]
+    i2 = np.full((3, n_sb), np.nan)
+    for sb in range(n_sb):
+        if not np.isnan(pm["i2"][sb]):
+            i2[:, sb] = [x + 1 for x in np.unravel_index(int(pm["i2"][sb]) - 1, d[0:3], order="F")]
+    return {"i1": i1, "i2": i2}
+
+
+def _pmi_any_panel(cfg, n_panels, re_k, re_l, r, H, n_var):
+    """dlPMISelect on the (flattened) index set of either codebook type -> (flattened PMISet, info, index-set lengths or None)."""
+    if n_panels >= 2:
+        Wf, d = _mp_flat_codebook(cfg, n_panels, r)
+        pm, info = dl_pmi_select(dict(cfg, NumCSIRSPorts=Wf.shape[0]), re_k, re_l, r, H, n_var, W_override=Wf)
+        return pm, info, d
+    pm, info = dl_pmi_select(cfg, re_k, re_l, r, H, n_var)
+    return pm, info, None
+
+
+def ri_select(cfg, re_k, re_l, H, n_var=1e-10, n_panels=0):
+    """``[RI,PMISet] = riSelect(carrier,csirs,reportConfig,H,nVar)`` (riSelect.m:198-294).  ``n_panels`` >= 2: CodebookType
+    'Type1MultiPanel' (ranks 1-4, RIRestriction of 4 bits, riSelect.m:222-231, :449-456; PMISet in the multi-panel form)."""
     n_sb, _ = subband_info(cfg["PMIMode"], cfg["NStartBWP"], cfg["NSizeBWP"], cfg["SubbandSize"])
     P, R = H.shape[3], H.shape[2]
-    max_rank = min(R, P)
+    max_rank = min(R, P, 4) if n_panels >= 2 else min(R, P)
     valid = [r for r in range(1, max_rank + 1) if cfg["RIRestriction"][r - 1]]
     if not valid or len(re_k) == 0:
+        if n_panels >= 2:
+            return np.nan, {"i1": np.full(6, np.nan), "i2": np.full((3, n_sb), np.nan)}
         return np.nan, {"i1": np.full(3, np.nan), "i2": np.full(n_sb, np.nan)}
     best, total = -np.inf, np.full(max_rank, np.nan)
     RI, pm_best, pm = np.nan, None, None
+    dims = {}
     for r in valid:                                                                       # :254-285
-        pm, info = dl_pmi_select(cfg, re_k, re_l, r, H, n_var)
+        pm, info, dims[r] = _pmi_any_panel(cfg, n_panels, re_k, re_l, r, H, n_var)
         sb_sinr = np.full((n_sb, r), np.nan)
         if not np.any(np.isnan(pm["i1"])):
             i1 = pm["i1"].astype(int)
@@ -531,8 +569,8 @@ def ri_select(cfg, re_k, re_l, H, n_var=1e-10):
         if total[r - 1] > best + 0.1:                                                     # :284
             best, RI, pm_best = total[r - 1], r, pm
     if np.all(np.isnan(total)):
-        return np.nan, pm
-    return RI, pm_best
+        return np.nan, (mp_unflatten_pmi(pm, dims[valid[-1]]) if n_panels >= 2 else pm)
+    return RI, (mp_unflatten_pmi(pm_best, dims[int(RI)]) if n_panels >= 2 else pm_best)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -559,12 +597,13 @@ def get_cqi(lin_sinr, table):
     return 0.0 if idx.size == 0 else float(idx[-1] + 1)
 
 
-def cqi_select(cfg, re_k, re_l, n_layers, H, n_var, sinr_table, L=14):
+def cqi_select(cfg, re_k, re_l, n_layers, H, n_var, sinr_table, L=14, n_panels=0):
     """``[CQI,PMISet,CQIInfo,PMIInfo] = cqiSelect(carrier,csirs,reportConfig,nLayers,H,nVar,SINRTable)``
-    (cqiSelect.m:411-695, CSI-RS object syntax, no PRGSize)."""
+    (cqiSelect.m:411-695, CSI-RS object syntax, no PRGSize).  ``n_panels`` >= 2: Type1MultiPanel (the SINR look-ups of :589-603
+    on the flattened index set; PMISet returned in the multi-panel form, PMIInfo arrays stay flattened)."""
     n_cq, cq_sizes = subband_info(cfg["CQIMode"], cfg["NStartBWP"], cfg["NSizeBWP"], cfg["SubbandSize"])
     n_cw = int(math.ceil(n_layers / 4))
-    pm, info = dl_pmi_select(cfg, re_k, re_l, n_layers, H, n_var)                         # :507
+    pm, info, mp_dims = _pmi_any_panel(cfg, n_panels, re_k, re_l, n_layers, H, n_var)     # :507
     S = info["SINRPerRE"]
     re_k = np.asarray(re_k, int)
     re_l = np.asarray(re_l, int)
@@ -592,9 +631,10 @@ def cqi_select(cfg, re_k, re_l, n_layers, H, n_var, sinr_table, L=14):
     if sb_cw.shape[0] > 1:
         with np.errstate(invalid="ignore"):
             sb_cw = np.vstack([np.nanmean(sb_cw, axis=0), sb_cw])                         # :631-633
+    pm_out = mp_unflatten_pmi(pm, mp_dims) if n_panels >= 2 else pm
     if nan_pm:
         ns = 0 if n_cq == 1 else n_cq
-        return np.full((ns + 1, n_cw), np.nan), pm, {"SINRPerSubbandPerCW": np.full((ns + 1, n_cw), np.nan)}, info
+        return np.full((ns + 1, n_cw), np.nan), pm_out, {"SINRPerSubbandPerCW": np.full((ns + 1, n_cw), np.nan)}, info
     cq_all = np.vectorize(lambda x: get_cqi(x, sinr_table))(sb_cw)                        # :653
     if cfg["CQIMode"].lower() == "subband":
         diff = cq_all[1:] - cq_all[0]                                                     # :661
@@ -606,7 +646,7 @@ def cqi_select(cfg, re_k, re_l, n_layers, H, n_var, sinr_table, L=14):
         cqi = np.vstack([cq_all[0:1], off])                                               # :677
     else:
         cqi = cq_all[0:1]
-    return cqi, pm, {"SINRPerSubbandPerCW": sb_cw, "SubbandCQI": cq_all}, info
+    return cqi, pm_out, {"SINRPerSubbandPerCW": sb_cw, "SubbandCQI": cq_all}, info
 
 
 # ----------------------------------------------------------------------------------------------
