@@ -128,6 +128,8 @@ def _declare(lib):
         "isac_city_check_los_host": ([vp, i32, vp, vp, i32, vp], C.c_int),
         "isac_city_check_los_dev": ([vp, i32, vp, vp, i32, vp], C.c_int),
         "isac_ofdm_modulate_dev": ([vp, vp, i32, i32, i32, i32, i32, vp, f64, vp, P(C.c_int64)], C.c_int),
+        "isac_ofdm_modulate_ex_dev": ([vp, vp, i32, i32, i32, C.c_int64, i32, i32, vp, f64, i32, i32, vp, C.c_int64, C.c_int64,
+                                       P(C.c_int64)], C.c_int),
         "isac_pathloss_host": ([vp, i32, f64, i32, vp, vp, vp, vp], C.c_int),
         "isac_link_budget_dev": ([vp, vp, C.c_int64, i32, vp, f64], C.c_int),
         "isac_thermal_noise_power": ([f64, f64, f64, P(f64)], C.c_int),

@@ -700,6 +700,26 @@ int isac_ofdm_modulate_dev(isac_ctx* h, const void* txGrid, int32_t nSc, int32_t
     return ofdm_modulate_run(c, o, (const float2*)txGrid, (float2*)txWaveform, c->stream);
 }
 
+int isac_ofdm_modulate_ex_dev(isac_ctx* h, const void* txGrid, int32_t nSc, int32_t nSym, int32_t nAnts, int64_t gridStride, int32_t nfft,
+                              int32_t symbolsPerSubframe, const int32_t* cpLengths, double scale, int32_t windowing, int32_t symPhase,
+                              void* txWaveform, int64_t waveStride, int64_t sampleOffset, int64_t* T) {
+    if (!h || !cpLengths || symbolsPerSubframe < 1 || nSym < 1) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    OfdmConfig o{};
+    o.nSc = nSc; o.nSym = nSym; o.nAnts = nAnts; o.nfft = nfft;
+    o.symbolsPerSubframe = symbolsPerSubframe; o.cpLengths = cpLengths; o.scale = scale;
+    o.windowing = windowing; o.symPhase = symPhase; o.gridStride = gridStride; o.waveStride = waveStride; o.sampleOffset = sampleOffset;
+    const long long len = ofdm_waveform_length(o);
+    if (T) *T = len;
+    if (!txWaveform) return ISAC_OK;  // size query
+    if (waveStride > 0 && sampleOffset + len > waveStride) {
+        set_error(c, "ofdmModulate: the block does not fit in the destination buffer");
+        return ISAC_ERR_CAPACITY;
+    }
+    return ofdm_modulate_run(c, o, (const float2*)txGrid, (float2*)txWaveform, c->stream);
+}
+
 int isac_mono_static_sensing_host(isac_ctx* h, const isac_echo_config* cfg, const void* txHost, const void* noiseHost,
                                   int32_t noiseMode, uint64_t seed, void* echoHost, int32_t* nSymOut) {
     if (!h || (!txHost && echoHost) || (!echoHost && !nSymOut)) return ISAC_ERR_INVALID_ARG;

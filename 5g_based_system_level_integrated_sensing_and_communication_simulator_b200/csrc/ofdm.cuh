@@ -11,6 +11,12 @@ struct OfdmConfig {
     int symbolsPerSubframe;  // length of cpLengths
     const int* cpLengths;    // nrOFDMInfo.CyclicPrefixLengths of one subframe
     double scale;            // signalAmp (gNBPhy.m:599)
+    // extended form (isac_ofdm_modulate_ex_dev): a block of symbols written into resident buffers
+    int windowing = 0;       // raised-cosine window / overlap length in samples (0: plain CP-OFDM)
+    int symPhase = 0;        // position of the block's first symbol in the subframe's CP pattern
+    long long gridStride = 0;   // symbols per antenna page of the SOURCE grid (0: nSym)
+    long long waveStride = 0;   // samples per antenna of the DESTINATION buffer (0: the block's own length)
+    long long sampleOffset = 0; // first sample of the block in the destination buffer
 };
 
 long long ofdm_waveform_length(const OfdmConfig& c);

@@ -103,10 +103,60 @@ def monoStaticSensing(txWaveform, txDimension, carrierInfo, radarParams, targetL
     return out.cpu().numpy().transpose(2, 1, 0).copy()
 
 
-def ofdmModulate(carrierInfo, txGrid, scale=1.0):
+class SensingTxAccumulator:
+    """Device-resident ``senTxGrid`` / ``senTxWave`` of the gNB PHY's sensing tap (reference +phyLayer/gNBPhy.m:604-612): the
+    reference appends every DL slot's grid and waveform with ``cat`` (O(n^2) copying over a run); here the buffers are
+    allocated once for ``maxSymbols`` symbols and ``append(slotGrid, slotInSubframe)`` writes the slot's grid and its OFDM
+    waveform (``scale * nrOFDMModulate``, optional windowing) straight to their place (isac_ofdm_modulate_ex_dev)."""
+
+    def __init__(self, carrierInfo, nTx, maxSymbols, scale=1.0, windowing=0, device=None):
+        import torch
+        self.ctx = _lib.get_context(device)
+        self.num = ofdm_numerology(int(carrierInfo["NRBsDL"]), float(carrierInfo["SubcarrierSpacing"]))
+        self.nSc, self.nTx, self.maxSym = 12 * int(carrierInfo["NRBsDL"]), int(nTx), int(maxSymbols)
+        self.scale, self.windowing = float(scale), int(windowing)
+        self.cp = np.ascontiguousarray(self.num["CyclicPrefixLengths"], dtype=np.int32)
+        # capacity in samples: a run of whole slots never needs more than maxSymbols worst-case symbol lengths
+        self.maxT = int(self.maxSym * (self.num["Nfft"] + int(self.cp.max())))
+        dev = f"cuda:{self.ctx.device}"
+        self.senTxGrid = torch.zeros((self.nTx, self.maxSym, self.nSc), dtype=torch.complex64, device=dev)
+        self.senTxWave = torch.zeros((self.nTx, self.maxT), dtype=torch.complex64, device=dev)
+        self.nSym, self.T = 0, 0
+
+    def append(self, slotGrid, slotInSubframe=0):
+        """``slotGrid``: [nSc x nSymSlot x nTx] NumPy or torch CUDA [nTx][nSymSlot][nSc]; ``slotInSubframe`` selects the slot's
+        place in the subframe's cyclic-prefix pattern (the long prefixes sit at the start of every half subframe)."""
+        import torch
+        if _is_dev(slotGrid):
+            g = slotGrid
+        else:
+            g = torch.from_numpy(np.ascontiguousarray(np.asarray(slotGrid).astype(np.complex64).transpose(2, 1, 0))).to(self.senTxGrid.device)
+        nTx, n, nSc = g.shape
+        if nTx != self.nTx or nSc != self.nSc or self.nSym + n > self.maxSym:
+            raise _lib.IsacError(8, "SensingTxAccumulator: slot grid does not fit (shape or capacity)")
+        self.senTxGrid[:, self.nSym: self.nSym + n] = g                     # obj.senTxGrid = cat(2, obj.senTxGrid, txGrid)
+        T = C.c_int64()
+        src = self.senTxGrid[0, self.nSym]                                  # block start; antenna pages maxSym symbols apart
+        self.ctx.use_torch_stream()
+        _lib.check(self.ctx.lib.isac_ofdm_modulate_ex_dev(self.ctx.handle, _lib.ptr(src), self.nSc, n, self.nTx, self.maxSym,
+                                                          int(self.num["Nfft"]), int(self.cp.size), self.cp.ctypes.data, self.scale,
+                                                          self.windowing, int(slotInSubframe) * 14, _lib.ptr(self.senTxWave), self.maxT,
+                                                          self.T, C.byref(T)), self.ctx.handle)
+        self.nSym += n
+        self.T += T.value                                                   # obj.senTxWave = cat(1, obj.senTxWave, txWaveform)
+
+    def grid(self):
+        return self.senTxGrid[:, : self.nSym]
+
+    def wave(self):
+        return self.senTxWave[:, : self.T]
+
+
+def ofdmModulate(carrierInfo, txGrid, scale=1.0, windowing=0):
     """``txWaveform = scale * nrOFDMModulate(carrier, txGrid)`` -- the gNB PHY step that produces the waveform handed to
     ``monoStaticSensing`` (reference +phyLayer/gNBPhy.m:599, accumulation for sensing at :604-612), on the device
-    (csrc/ofdm.cu).  Plain CP-OFDM: the toolbox's default windowing is not applied.
+    (csrc/ofdm.cu).  ``windowing`` = N > 0 samples applies the raised-cosine windowing / overlap of nrOFDMModulate's 'Windowing'
+    argument (documented scheme, PARITY-UNPINNED); the default 0 is plain CP-OFDM.
 
     ``txGrid``: [nSc x nSym x nAnts] NumPy -> returns [T x nAnts] NumPy complex64;
     torch CUDA [nAnts][nSym][nSc] -> torch CUDA [nAnts][T]."""
@@ -127,11 +177,19 @@ def ofdmModulate(carrierInfo, txGrid, scale=1.0):
     if nSc != 12 * int(carrierInfo["NRBsDL"]):
         raise _lib.IsacError(1, "txGrid must span 12*NRBsDL subcarriers")
     T = C.c_int64()
-    args = (ctx.handle, _lib.ptr(g_d), nSc, nSym, nAnts, int(num["Nfft"]), int(cp.size), cp.ctypes.data, float(scale))
     ctx.use_torch_stream()
-    _lib.check(ctx.lib.isac_ofdm_modulate_dev(*args, None, C.byref(T)), ctx.handle)
-    out = torch.empty((nAnts, T.value), dtype=torch.complex64, device=g_d.device)
-    _lib.check(ctx.lib.isac_ofdm_modulate_dev(*args, _lib.ptr(out), C.byref(T)), ctx.handle)
+    if windowing:
+        def call(dst, stride):
+            return ctx.lib.isac_ofdm_modulate_ex_dev(ctx.handle, _lib.ptr(g_d), nSc, nSym, nAnts, 0, int(num["Nfft"]), int(cp.size),
+                                                     cp.ctypes.data, float(scale), int(windowing), 0, dst, stride, 0, C.byref(T))
+        _lib.check(call(None, 0), ctx.handle)
+        out = torch.empty((nAnts, T.value), dtype=torch.complex64, device=g_d.device)
+        _lib.check(call(_lib.ptr(out), T.value), ctx.handle)
+    else:
+        args = (ctx.handle, _lib.ptr(g_d), nSc, nSym, nAnts, int(num["Nfft"]), int(cp.size), cp.ctypes.data, float(scale))
+        _lib.check(ctx.lib.isac_ofdm_modulate_dev(*args, None, C.byref(T)), ctx.handle)
+        out = torch.empty((nAnts, T.value), dtype=torch.complex64, device=g_d.device)
+        _lib.check(ctx.lib.isac_ofdm_modulate_dev(*args, _lib.ptr(out), C.byref(T)), ctx.handle)
     if dev_in:
         return out
     return out.cpu().numpy().T.copy()

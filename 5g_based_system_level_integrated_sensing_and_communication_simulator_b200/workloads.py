@@ -47,9 +47,12 @@ def qpsk_grid(nsc: int, nsym: int, nants: int, seed: int) -> np.ndarray:
     return np.exp(1j * (np.pi / 4 + np.pi / 2 * b))
 
 
-def ofdm_modulate(grid: np.ndarray, nrb: int, scs_khz: float) -> np.ndarray:
-    """Plain CP-OFDM modulation (IFFT + cyclic prefix, no windowing) of [nSc x nSym x nAnts]
-    -> [T x nAnts]; symbol timing starts at a subframe boundary like nrOFDMDemodulate assumes."""
+def ofdm_modulate(grid: np.ndarray, nrb: int, scs_khz: float, windowing: int = 0) -> np.ndarray:
+    """CP-OFDM modulation (IFFT + cyclic prefix) of [nSc x nSym x nAnts] -> [T x nAnts]; symbol timing starts at a subframe
+    boundary like nrOFDMDemodulate assumes.  ``windowing`` = N > 0: the documented W-OLA scheme of nrOFDMModulate's 'Windowing'
+    argument (PARITY-UNPINNED): each symbol's cyclic extension grows by N samples in front of its prefix, that head is shaped
+    by the rising raised cosine p[i] = 0.5 (1 - sin(pi (N + 1 - 2 i) / (2 N))), i = 1..N, the last N samples of the symbol
+    before it by the falling one (1 - p), and the two overlap-add; the first symbol has nothing in front of it."""
     num = ofdm_numerology(nrb, scs_khz)
     nfft = num["Nfft"]
     nsc, nsym, nants = grid.shape
@@ -65,6 +68,14 @@ def ofdm_modulate(grid: np.ndarray, nrb: int, scs_khz: float) -> np.ndarray:
         st = int(starts[s])
         wave[st: st + cp, :] = td[nfft - cp:, s, :]
         wave[st + cp: st + cp + nfft, :] = td[:, s, :]
+    if windowing > 0:
+        N = int(windowing)
+        rise = 0.5 * (1.0 - np.sin(np.pi * (N + 1 - 2 * np.arange(1, N + 1)) / (2 * N)))[:, None]
+        for s in range(1, nsym):
+            cp = int(num["CyclicPrefixLengths"][s % num["CyclicPrefixLengths"].size])
+            st = int(starts[s])
+            head = td[nfft - cp - N: nfft - cp, s, :]
+            wave[st - N: st, :] = (1.0 - rise) * wave[st - N: st, :] + rise * head
     return wave
 
 

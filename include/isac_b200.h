@@ -227,7 +227,7 @@ int isac_mono_static_sensing_host(isac_ctx* ctx, const isac_echo_config* cfg, co
  * accumulates for sensing, gNBPhy.m:604-612) -- SURVEY 8(f) row 2: the step immediately before the sensing hot path.
  * txGrid: device complex64 [nSc x nSym x nAnts]; txWaveform: device complex64 [T x nAnts] with
  * T = sum_s (cpLengths[s mod symbolsPerSubframe] + nfft), returned in *T (call with txWaveform == NULL to query it).
- * Plain CP-OFDM (IFFT + cyclic prefix): the toolbox's default raised-cosine windowing is not applied. */
+ * Plain CP-OFDM (IFFT + cyclic prefix); isac_ofdm_modulate_ex_dev adds the raised-cosine windowing and block placement. */
 int isac_ofdm_modulate_dev(isac_ctx* ctx, const void* txGrid, int32_t nSc, int32_t nSym, int32_t nAnts, int32_t nfft,
                            int32_t symbolsPerSubframe, const int32_t* cpLengths, double scale, void* txWaveform,
                            int64_t* T);
@@ -409,6 +409,17 @@ int isac_cdl_generate_dev(isac_cdl_channel* ch, int32_t K, double scsHz, int32_t
 int isac_cdl_set_kernel(isac_cdl_channel* ch, int32_t legacyMma);
 int isac_cdl_generate_batch_dev(isac_cdl_channel* const* ch, int32_t n, int32_t K, double scsHz, int32_t L,
                                 const double* symTime, const double* t0, void* H);
+
+/* The same step for a BLOCK of symbols written into resident buffers -- the device form of the sensing tap of the gNB PHY,
+ * which appends every DL slot's grid and waveform to senTxGrid / senTxWave (gNBPhy.m:604-612: cat per slot, O(n^2) copying):
+ * txGrid: device complex64, antenna pages `gridStride` symbols apart (0: nSym), block starts at the pointer passed;
+ * the block's waveform goes to txWaveform[sampleOffset ...] of a buffer with `waveStride` samples per antenna (0: the block's
+ * own length); symPhase = index of the block's first symbol in the subframe's CP pattern (14 * slot-in-subframe for whole
+ * slots); windowing = N >= 0 samples of raised-cosine shaping / overlap with the symbol in front (nrOFDMModulate 'Windowing';
+ * the head of the block's first symbol is folded into whatever the buffer already holds in front of it).  *T = block length. */
+int isac_ofdm_modulate_ex_dev(isac_ctx* ctx, const void* txGrid, int32_t nSc, int32_t nSym, int32_t nAnts, int64_t gridStride,
+                              int32_t nfft, int32_t symbolsPerSubframe, const int32_t* cpLengths, double scale, int32_t windowing,
+                              int32_t symPhase, void* txWaveform, int64_t waveStride, int64_t sampleOffset, int64_t* T);
 
 /* ---- link budget of the channel application step (SURVEY 8(a) row a16 tail, 8(f) row 4) --------------------------------
  * pathLoss = communication.pathlossModels.config5GNRModels(scenario, fc, los, bsPosition, uePosition)

@@ -188,14 +188,17 @@ def ofdm_demodulate(nrb, scs_khz, wave, cp_fraction=0.5):
     return grid
 
 
-def ofdm_modulate(nrb, scs_khz, grid, scale=1.0):
+def ofdm_modulate(nrb, scs_khz, grid, scale=1.0, windowing=0):
     """``scale * nrOFDMModulate(carrier, grid)`` as called at gNBPhy.m:599 (the waveform the gNB PHY accumulates for
     sensing, gNBPhy.m:604-612).
 
     PARITY-UNPINNED (5G Toolbox): TS 38.211 5.3.1 CP-OFDM -- subcarrier k of the grid on FFT bin (k - nSc/2) mod Nfft,
     ``ifft`` (1/Nfft), cyclic prefix = copy of the symbol's tail, symbols laid end to end from a subframe boundary.
-    The toolbox's default raised-cosine windowing with symbol overlap is NOT applied (its window length table is not
-    public); the result is the exact inverse of ``ofdm_demodulate`` above.  Returns [T x nAnts]."""
+    ``windowing`` = N > 0 samples: the W-OLA scheme documented for the 'Windowing' argument -- the symbol's cyclic extension
+    grows by N samples in front of its prefix, that head is shaped by p[i] = 0.5 (1 - sin(pi (N + 1 - 2 i) / (2 N))), i = 1..N,
+    the last N samples of the symbol before it by 1 - p, and the two are added (waveform length unchanged; the first symbol
+    has nothing in front of it).  The toolbox's DEFAULT window length (a table over SCS and NRB) is not public, so the default
+    here is N = 0, the exact inverse of ``ofdm_demodulate`` above.  Returns [T x nAnts]."""
     info = ofdm_info(nrb, scs_khz)
     nfft = info["Nfft"]
     grid = np.asarray(grid, dtype=np.complex128)
@@ -212,6 +215,11 @@ def ofdm_modulate(nrb, scs_khz, grid, scale=1.0):
         spec[bins, :] = grid[:, s, :]
         x = np.fft.ifft(spec, axis=0) * scale
         cp = int(info["CyclicPrefixLengths"][s % per])
+        if windowing > 0 and s > 0:
+            N = int(windowing)
+            rise = 0.5 * (1.0 - np.sin(np.pi * (N + 1 - 2 * np.arange(1, N + 1)) / (2 * N)))[:, None]
+            st = int(starts[s])
+            wave[st - N: st, :] = (1.0 - rise) * wave[st - N: st, :] + rise * x[nfft - cp - N: nfft - cp, :]
         wave[starts[s]: starts[s] + cp, :] = x[nfft - cp:, :]
         wave[starts[s] + cp: starts[s] + cp + nfft, :] = x
     return wave

@@ -218,6 +218,36 @@ def test_ofdm_modulate_matches_oracle_and_round_trips(P, nrb_scs_sym):
     assert np.abs(back - grid).max() / np.abs(grid).max() <= 1e-5
 
 
+def test_ofdm_windowing_and_slot_accumulation(P):
+    """nrOFDMModulate with a window (documented W-OLA scheme) vs the oracle, and the device-resident sensing tap
+    (gNBPhy.m:604-612): appending DL slots one by one gives the same senTxGrid / senTxWave as modulating them in one piece --
+    with the window folded across the slot boundaries."""
+    echo = importlib.import_module(PKG + ".sensing._echo")
+    nrb, scs = 52, 30
+    rng = np.random.default_rng(5)
+    nsc, nants, nslots = 12 * nrb, 4, 5
+    grid = (rng.standard_normal((nsc, 14 * nslots, nants)) + 1j * rng.standard_normal((nsc, 14 * nslots, nants))).astype(np.complex64)
+    car = {"NRBsDL": nrb, "SubcarrierSpacing": scs}
+    for N in (0, 18, 72):
+        ref = S.ofdm_modulate(nrb, scs, grid, 3.0, windowing=N)
+        wave = P.sensing.ofdmModulate(car, grid, scale=3.0, windowing=N)
+        assert wave.shape == ref.shape
+        assert np.abs(wave - ref).max() / np.abs(ref).max() <= 1e-5, N
+        acc = echo.SensingTxAccumulator(car, nants, 14 * nslots, scale=3.0, windowing=N)
+        for sl in range(nslots):
+            acc.append(grid[:, 14 * sl: 14 * (sl + 1)], slotInSubframe=sl % 2)      # 30 kHz: two slots per subframe
+        assert acc.nSym == 14 * nslots and acc.T == ref.shape[0]
+        assert np.array_equal(acc.grid().cpu().numpy().transpose(2, 1, 0), grid)
+        got = acc.wave().cpu().numpy().T
+        assert np.abs(got - ref).max() / np.abs(ref).max() <= 1e-5, N
+    if True:   # the window changes only the N samples in front of every symbol but the first
+        plain, win = S.ofdm_modulate(nrb, scs, grid, 3.0), S.ofdm_modulate(nrb, scs, grid, 3.0, windowing=18)
+        changed = np.flatnonzero(np.abs(plain - win).max(axis=1) > 0)
+        assert changed.size <= 18 * (14 * nslots - 1) and changed.size > 0
+    with pytest.raises(Exception):
+        P.sensing.ofdmModulate(car, grid, scale=1.0, windowing=400)                  # longer than the cyclic prefix
+
+
 @pytest.mark.parametrize("method", ["mvdrBF", "digitalBF"])
 def test_mvdr_and_beamscan_ula(P, method):
     """doaEstimation.mvdrBF / digitalBF, ULA branch (mvdrBF.m:57-89, digitalBF.m:57-90) vs the float64 oracle:
