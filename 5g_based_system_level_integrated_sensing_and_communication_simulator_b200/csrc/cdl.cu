@@ -460,21 +460,25 @@ cdl_response_umma_kernel(const float2* __restrict__ Call, const CdlBatch bt, int
     }
     // E[k0+row, n] = exp(-2 pi j f tau_n), once per CTA (shared by all column tiles): the phase f*tau is reduced to
     // [0,1) in float64, the sine/cosine of the reduced phase are float32 (as accurate as the fp32 operand they feed)
-    for (int i = threadIdx.x; i < kCdlMaxCl * kUmmaM; i += blockDim.x) {
-        const int n = i / kUmmaM, row = i % kUmmaM;
-        float er = 0.f, ei = 0.f;
-        if (n < nCl) {
-            const double c = ((double)(k0 + row) - (double)(K / 2)) * scs * tau[n];
-            sincospif(-2.0f * (float)(c - floor(c)), &ei, &er);
+    for (int i = threadIdx.x; i < (kCdlMaxCl / 4) * kUmmaM; i += blockDim.x) {   // item = (4 consecutive clusters, row): 16-byte stores
+        const int g = i / kUmmaM, row = i % kUmmaM;
+        unsigned eh[4], el[4], ih[4], il[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int n = g * 4 + kk;
+            float er = 0.f, ei = 0.f;
+            if (n < nCl) {
+                const double c = ((double)(k0 + row) - (double)(K / 2)) * scs * tau[n];
+                sincospif(-2.0f * (float)(c - floor(c)), &ei, &er);
+            }
+            split_tf32(er, eh[kk], el[kk]);
+            split_tf32(ei, ih[kk], il[kk]);
         }
-        unsigned h, l;
-        const int o = (n >> 3) * 4096 + umma_off(row, n & 7);
-        split_tf32(er, h, l);
-        *(unsigned*)(sm + 0 * kUmmaTileBytes + o) = h;
-        *(unsigned*)(sm + 1 * kUmmaTileBytes + o) = l;
-        split_tf32(ei, h, l);
-        *(unsigned*)(sm + 2 * kUmmaTileBytes + o) = h;
-        *(unsigned*)(sm + 3 * kUmmaTileBytes + o) = l;
+        const int o = (g >> 1) * 4096 + umma_off(row, (g & 1) * 4);
+        *(uint4*)(sm + 0 * kUmmaTileBytes + o) = make_uint4(eh[0], eh[1], eh[2], eh[3]);
+        *(uint4*)(sm + 1 * kUmmaTileBytes + o) = make_uint4(el[0], el[1], el[2], el[3]);
+        *(uint4*)(sm + 2 * kUmmaTileBytes + o) = make_uint4(ih[0], ih[1], ih[2], ih[3]);
+        *(uint4*)(sm + 3 * kUmmaTileBytes + o) = make_uint4(il[0], il[1], il[2], il[3]);
     }
     // instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kUmmaN >> 3) << 17) | ((unsigned)(kUmmaM >> 4) << 24);
@@ -485,13 +489,22 @@ cdl_response_umma_kernel(const float2* __restrict__ Call, const CdlBatch bt, int
     const int colHalf = (warp >> 2) * 64;
     const int nTiles = (int)((J + kUmmaN - 1) / kUmmaN);
     constexpr int kCPer = kCdlMaxCl * kUmmaN / 256;   // C elements per thread and tile (12)
+    // Work item of the operand fill = (group of 4 consecutive clusters, column): its four hi (lo) words are one 16-byte row of a
+    // core matrix, so each thread issues ONE 128-bit shared-memory store per operand array and item instead of four scattered
+    // 32-bit ones (the 32-bit stores of a warp hit 8 banks four times over: 75 % of the kernel's shared-memory wavefronts were
+    // conflicts, profiles/r1_cdl_umma_v1_summary.txt).  Item i = threadIdx.x + q*256: group g = i / 128, column i % 128.
+    constexpr int kItems = kCPer / 4;                 // 3 items of 4 clusters per thread
     float2 cnext[kCPer];
     auto fetch_c = [&](long long j0) {   // global loads of one column tile of C (zero beyond nCl / J)
 #pragma unroll
-        for (int q = 0; q < kCPer; ++q) {
-            const int i = threadIdx.x + q * 256, n = i / kUmmaN, col = i % kUmmaN;
+        for (int q = 0; q < kItems; ++q) {
+            const int i = threadIdx.x + q * 256, g = i / kUmmaN, col = i % kUmmaN;
             const long long j = j0 + col;
-            cnext[q] = (n < nCl && j < J) ? __ldg(C + (size_t)n * J + j) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int n = g * 4 + kk;
+                cnext[q * 4 + kk] = (n < nCl && j < J) ? __ldg(C + (size_t)n * J + j) : make_float2(0.f, 0.f);
+            }
         }
     };
     fetch_c(0);
@@ -500,16 +513,18 @@ cdl_response_umma_kernel(const float2* __restrict__ Call, const CdlBatch bt, int
         // C tile split into TF32 hi/lo; the previous tile's MMAs have completed (barrier wait below), its loads were
         // issued before that wait so their latency hides behind the tensor work
 #pragma unroll
-        for (int q = 0; q < kCPer; ++q) {
-            const int i = threadIdx.x + q * 256, n = i / kUmmaN, col = i % kUmmaN;
-            unsigned h, l;
-            const int o = (n >> 3) * 4096 + umma_off(col, n & 7);
-            split_tf32(cnext[q].x, h, l);
-            *(unsigned*)(sm + 4 * kUmmaTileBytes + o) = h;
-            *(unsigned*)(sm + 5 * kUmmaTileBytes + o) = l;
-            split_tf32(cnext[q].y, h, l);
-            *(unsigned*)(sm + 6 * kUmmaTileBytes + o) = h;
-            *(unsigned*)(sm + 7 * kUmmaTileBytes + o) = l;
+        for (int q = 0; q < kItems; ++q) {
+            const int i = threadIdx.x + q * 256, g = i / kUmmaN, col = i % kUmmaN;
+            uint4 rh, rl, ih, il;
+            split_tf32(cnext[q * 4 + 0].x, rh.x, rl.x); split_tf32(cnext[q * 4 + 1].x, rh.y, rl.y);
+            split_tf32(cnext[q * 4 + 2].x, rh.z, rl.z); split_tf32(cnext[q * 4 + 3].x, rh.w, rl.w);
+            split_tf32(cnext[q * 4 + 0].y, ih.x, il.x); split_tf32(cnext[q * 4 + 1].y, ih.y, il.y);
+            split_tf32(cnext[q * 4 + 2].y, ih.z, il.z); split_tf32(cnext[q * 4 + 3].y, ih.w, il.w);
+            const int o = (g >> 1) * 4096 + umma_off(col, (g & 1) * 4);   // clusters 4g..4g+3: k-step g/2, k = 0..3 or 4..7
+            *(uint4*)(sm + 4 * kUmmaTileBytes + o) = rh;
+            *(uint4*)(sm + 5 * kUmmaTileBytes + o) = rl;
+            *(uint4*)(sm + 6 * kUmmaTileBytes + o) = ih;
+            *(uint4*)(sm + 7 * kUmmaTileBytes + o) = il;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

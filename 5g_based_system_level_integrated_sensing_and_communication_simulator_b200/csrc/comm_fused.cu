@@ -46,6 +46,16 @@ struct FusedDev {
     double nVar[kMaxPmiBatch];
 };
 
+// Slot of RE e inside the G-wide group of table entry `id`: XOR-swizzled with the entry's index so that lanes which read the
+// SAME e of DIFFERENT entries (the table-building stages) spread over all eight 16-byte bank groups, while the G lanes that read
+// one entry (the candidate stage) still touch one contiguous 16*G-byte segment.
+template <int G>
+__device__ __forceinline__ int swz(int id, int e) {
+    if (G == 4) return e ^ ((id >> 1) & 3);
+    if (G == 2) return e ^ ((id >> 2) & 1);
+    return 0;
+}
+
 template <int NU, int G>
 __device__ __noinline__ void fused_rank_eval(const FusedRank rk, const double2* __restrict__ Gt, double nVar, double* __restrict__ part,
                                              int nValid) {
@@ -79,7 +89,7 @@ __device__ __noinline__ void fused_rank_eval(const FusedRank rk, const double2* 
                         const int t = w * 8 + u;
                         if (t < NT) {   // bit 15: the pair is stored as (j,i) -> conjugate
                             const uint32_t id = (q[u >> 1] >> ((u & 1) * 16)) & 0xffffu;
-                            const double2 g = Gt[(id & 0x7fffu) * G + e];
+                            const double2 g = Gt[(id & 0x7fffu) * G + swz<G>((int)(id & 0x7fffu), e)];
                             A[t] = make_double2(g.x, (id & 0x8000u) ? -g.y : g.y);
                         }
                     }
@@ -143,36 +153,52 @@ pmi_pair_fused_kernel(const __grid_constant__ FusedDev p) {
             const double2* __restrict__ hr = Hs + (size_t)(r * P + blk * p.Pb) * G + e;
             double2 acc = make_double2(0.0, 0.0);
             for (int q = 0; q < p.Pb; ++q) acc = zfma(acc, hr[q * G], __ldg(bv + q));
-            Bf[((size_t)r * nAtoms + a) * G + e] = acc;
+            Bf[((size_t)r * nAtoms + a) * G + swz<G>(a, e)] = acc;
         }
     }
     __syncthreads();
-    // 2. atom Gram pairs Gm[pi][e] = <Bf[a], Bf[a']>
-    for (int i = threadIdx.x; i < p.nPairs * G; i += T) {
-        const int e = i % G, pi = i / G;
+    // 2. atom Gram pairs Gm[pi][e] = <Bf[a], Bf[a']>: one thread per pair, the G REs inside (the pair word is decoded once)
+    for (int pi = threadIdx.x; pi < p.nPairs; pi += T) {
         const uint32_t w = __ldg(p.pairs + pi);
-        const double2* __restrict__ pa = Bf + (size_t)(w & 0xffffu) * G + e;
-        const double2* __restrict__ pb = Bf + (size_t)(w >> 16) * G + e;
-        double2 acc = make_double2(0.0, 0.0);
-        for (int r = 0; r < R; ++r, pa += (size_t)nAtoms * G, pb += (size_t)nAtoms * G) acc = zfmac(acc, *pb, *pa);  // conj(Bf[a]) Bf[a']
-        Gm[i] = acc;
+        const int a0 = (int)(w & 0xffffu), a1 = (int)(w >> 16);
+        const double2* __restrict__ pa = Bf + (size_t)a0 * G;
+        const double2* __restrict__ pb = Bf + (size_t)a1 * G;
+        double2 acc[G];
+#pragma unroll
+        for (int e = 0; e < G; ++e) acc[e] = make_double2(0.0, 0.0);
+        for (int r = 0; r < R; ++r, pa += (size_t)nAtoms * G, pb += (size_t)nAtoms * G) {
+#pragma unroll
+            for (int e = 0; e < G; ++e) acc[e] = zfmac(acc[e], pb[swz<G>(a1, e)], pa[swz<G>(a0, e)]);  // conj(Bf[a]) Bf[a']
+        }
+#pragma unroll
+        for (int e = 0; e < G; ++e) Gm[(size_t)pi * G + swz<G>(pi, e)] = acc[e];
     }
     __syncthreads();
-    // 3. column-pair table Gt[q][e] = sum_t pal[.] Gm[.][e]
+    // 3. column-pair table Gt[q][e] = sum_t pal[.] Gm[.][e]: one thread per column pair, its terms decoded once for the G REs;
+    //    the conjugation flag flips the sign bit of the imaginary part
     const uint4* __restrict__ cpt = reinterpret_cast<const uint4*>(p.cpTerms);
-    for (int i = threadIdx.x; i < p.nCP * G; i += T) {
-        const int e = i % G, q = i / G;
-        double2 acc = make_double2(0.0, 0.0);
+    for (int q = threadIdx.x; q < p.nCP; q += T) {
+        double2 acc[G];
+#pragma unroll
+        for (int e = 0; e < G; ++e) acc[e] = make_double2(0.0, 0.0);
         for (int t = 0; t < p.cpT / 4; ++t) {
             const uint4 v = __ldg(cpt + (size_t)t * p.nCP + q);
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const double2 g = Gm[(w4[u] & 0x7fffu) * G + e];
-                acc = zfma(acc, make_double2(g.x, (w4[u] & 0x8000u) ? -g.y : g.y), pal[w4[u] >> 16]);
+                const double2 c = pal[w4[u] >> 16];
+                const int pid = (int)(w4[u] & 0x7fffu);
+                const double2* __restrict__ gm = Gm + (size_t)pid * G;
+                const long long flip = (long long)(w4[u] & 0x8000u) << 48;   // bit 15 -> bit 63
+#pragma unroll
+                for (int e = 0; e < G; ++e) {
+                    const double2 g = gm[swz<G>(pid, e)];
+                    acc[e] = zfma(acc[e], make_double2(g.x, __longlong_as_double(__double_as_longlong(g.y) ^ flip)), c);
+                }
             }
         }
-        Gt[i] = acc;
+#pragma unroll
+        for (int e = 0; e < G; ++e) Gt[(size_t)q * G + swz<G>(q, e)] = acc[e];
     }
     __syncthreads();
     // 4. every (candidate, RE) item of every rank

@@ -73,5 +73,13 @@ b3)
   timeout 900 python bench.py --workload cfg3 --steps 5 --warmup 2 > gpurun_out/r2_b3_cfg3.json 2> gpurun_out/r2_b3_cfg3.err; tail -n 5 gpurun_out/r2_b3_cfg3.err; cut -c1-1500 gpurun_out/r2_b3_cfg3.json
   timeout 900 python bench.py --workload cfg5 --steps 10 --warmup 3 > gpurun_out/r2_b3_cfg5.json 2> gpurun_out/r2_b3_cfg5.err; tail -n 5 gpurun_out/r2_b3_cfg5.err; cut -c1-300 gpurun_out/r2_b3_cfg5.json
   ;;
+prof)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:pmi_pair_fused -s 4 -c 1 -o gpurun_out/r2_prof_pmi python tools/dev_pmi_variants.py > /dev/null 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:cdl_response_umma -s 2 -c 1 -o gpurun_out/r2_prof_cdl python tools/profile_comm.py > /dev/null 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:rdm_range4096_lean|rdm_doppler256_tma|cfar2d" -s 16 -c 4 -o gpurun_out/r2_prof_rdm python tools/profile_rdm.py 4 0 > /dev/null 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:echo_|cov_" -s 8 -c 6 -o gpurun_out/r2_prof_misc python tools/profile_misc.py > /dev/null 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2_prof_bench_launches.csv python bench.py --steps 1 --warmup 1 --frames-per-step 1 --no-cpu-baseline --skip-host-h > gpurun_out/r2_prof_bench_under_ncu.json 2> /dev/null
+  ls -la gpurun_out | tail -8
+  ;;
 *) echo "unknown step $step"; exit 1;;
 esac
