@@ -711,6 +711,16 @@ def _run_tasks(arg):
     return tot, fft
 
 
+def _init_worker():
+    """One BLAS / OpenMP thread per worker process: the pool already runs one process per core, nested threading only makes the
+    processes fight over them."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1)
+    except Exception:
+        pass
+
+
 def _warm(_):
     """Imports + one small report: the pool's processes are ready before the timed region."""
     from oracle import comm as OCm
@@ -729,7 +739,7 @@ def cpu_baseline():
     tasks = cell_frame_tasks()
     order = sorted(range(len(tasks)), key=lambda i: (tasks[i][0] != "sense", tasks[i][0] != "csi"))   # long tasks first
     parts = [[tasks[i] for i in order[w::workers]] for w in range(workers)]
-    with ProcessPoolExecutor(max_workers=workers) as ex:
+    with ProcessPoolExecutor(max_workers=workers, initializer=_init_worker) as ex:
         list(ex.map(_warm, range(workers)))
         t0 = time.time()
         res = list(ex.map(_run_tasks, [(pt, 11) for pt in parts]))
@@ -753,7 +763,7 @@ def run_reference(args):
     tasks = cell_frame_tasks()
     K = max(1, args.steps)
     bounds = [round(i * len(tasks) / K) for i in range(K + 1)]
-    with ProcessPoolExecutor(max_workers=workers) as ex:
+    with ProcessPoolExecutor(max_workers=workers, initializer=_init_worker) as ex:
         for _ in range(args.warmup):
             list(ex.map(_warm, range(workers)))
         t0 = time.time()

@@ -81,5 +81,12 @@ prof)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2_prof_bench_launches.csv python bench.py --steps 1 --warmup 1 --frames-per-step 1 --no-cpu-baseline --skip-host-h > gpurun_out/r2_prof_bench_under_ncu.json 2> /dev/null
   ls -la gpurun_out | tail -8
   ;;
+scale)
+  N=$2
+  run() { timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 bench.py --gpus $N "${@:3}" > gpurun_out/r2_scale_$2_n$N.json 2> gpurun_out/r2_scale_$2_n$N.err; tail -n 1 gpurun_out/r2_scale_$2_n$N.json | cut -c1-400; }
+  run 29521 cfg5 --workload cfg5 --steps 20 --warmup 5
+  run 29522 cfg3 --workload cfg3 --steps 10 --warmup 3
+  if [ "${3:-}" = "cfg2" ]; then run 29523 cfg2 --steps 10 --warmup 3 --no-cpu-baseline; fi
+  ;;
 *) echo "unknown step $step"; exit 1;;
 esac
