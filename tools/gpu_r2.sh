@@ -39,6 +39,21 @@ pmi4)
   done > gpurun_out/r2_pmi4_variants.log 2>&1
   cat gpurun_out/r2_pmi4_variants.log
   ;;
+pmiq)
+  (timeout 900 python -m pytest tests/test_comm_gpu.py tests/test_golden_gpu.py tests/test_multipanel_gpu.py -m gpu -q -x 2>&1 | tail -5) > gpurun_out/r2_pmiq_tests.log
+  cat gpurun_out/r2_pmiq_tests.log
+  for v in ${PMIQ_VARIANTS:-"ISAC_PAIR_ASC=0,ISAC_PAIR_RR=0" "ISAC_PAIR_ASC=1,ISAC_PAIR_RR=0" "ISAC_PAIR_ASC=1,ISAC_PAIR_RR=1" "ISAC_PAIR_ASC=0,ISAC_PAIR_RR=1" "ISAC_PAIR_UNIT=1100" "ISAC_PAIR_UNIT=2200" "ISAC_PAIR_UNIT=1"}; do
+    v=${v//,/ }
+    echo "== $v"
+    env $v timeout 300 python tools/dev_pmi_variants.py 2>&1 | tail -2 | head -1
+    env $v timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pmi_ -s 8 -c 2 --csv python tools/dev_pmi_variants.py 2>/dev/null | grep -E "pmi_" | awk -F'","' '{print $5, $NF}' | cut -c1-160
+  done > gpurun_out/r2_pmiq_variants.log 2>&1
+  cat gpurun_out/r2_pmiq_variants.log
+  ;;
+profpmi)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:pmi_pair_fused -s 4 -c 1 -o gpurun_out/r2_prof_pmi_${TAG:-x} python tools/dev_pmi_variants.py > /dev/null 2>&1
+  ls -la gpurun_out/*.ncu-rep
+  ;;
 full)
   (timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -8) > gpurun_out/r2_full_tests.log
   cat gpurun_out/r2_full_tests.log
