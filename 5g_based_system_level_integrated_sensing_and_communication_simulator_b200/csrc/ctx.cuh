@@ -7,7 +7,7 @@ namespace isac {
 
 struct Ctx {
     static constexpr int kPinnedSlots = 8;
-    static constexpr int kScratchSlots = 24;
+    static constexpr int kScratchSlots = 26;
     int device = 0;
     int numSMs = 0;
     int ccMajor = 0;

@@ -48,10 +48,11 @@ struct EchoDev {
 };
 
 // Philox4x32-10
+template <int ROUNDS = 10>
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < ROUNDS; ++i) {
         const unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
         const unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
         ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -67,6 +68,16 @@ __device__ __forceinline__ float2 gauss_pair(unsigned a, unsigned b) {
     float s, c;
     sincospif(2.0f * u2, &s, &c);
     return make_float2(r * c, r * s);
+}
+// Box-Muller on the special-function unit (lg2 / sqrt / sin / cos approximations, absolute error ~1e-6 of a unit-variance
+// sample): the frequency-domain noise of the production path draws 2 nAnts normals per resource element, which made
+// echo_combine_kernel ALU-bound with the accurate forms above.
+__device__ __forceinline__ float2 gauss_pair_fast(unsigned a, unsigned b) {
+    const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;  // (0,1)
+    const float ang = ((float)b + 0.5f) * 1.4629180792671596e-9f;   // 2 pi u2
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(u1)));   // sqrt(-2 ln u1)
+    return make_float2(r * __cosf(ang), r * __sinf(ang));
 }
 
 // noise sample after the receive mixer: z[n] * exp(-2 pi j fc Ts n)   (basicRadarChannel.m:69,73-74)
@@ -219,9 +230,9 @@ echo_combine_kernel(const EchoDev p, const float2* __restrict__ W, int NF) {
             acc.y += p.noiseSigma * z.y;
         } else if (p.noiseMode == 2) {
             if ((r & 1) == 0)   // one counter block = four uniforms = two complex normals (antennas r, r+1)
-                rn = philox4x32(make_uint4((unsigned)k, (unsigned)s, (unsigned)(r >> 1), 0x15ACu),
-                                make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
-            const float2 g = (r & 1) ? gauss_pair(rn.z, rn.w) : gauss_pair(rn.x, rn.y);
+                rn = philox4x32<7>(make_uint4((unsigned)k, (unsigned)s, (unsigned)(r >> 1), 0x15ACu),   // Philox4x32-7 (crush-resistant)
+                                   make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
+            const float2 g = (r & 1) ? gauss_pair_fast(rn.z, rn.w) : gauss_pair_fast(rn.x, rn.y);
             acc.x += sc * g.x;
             acc.y += sc * g.y;
         }

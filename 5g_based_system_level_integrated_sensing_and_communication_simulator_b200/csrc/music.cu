@@ -132,10 +132,124 @@ __global__ void __launch_bounds__(256) cov_final_kernel(const double2* __restric
     Ra[(long long)b * nAnts * nAnts + idx] = s;
 }
 
+// Arrays of up to 8 elements (the sensing arrays of the shipped scenarios): ONE pass over the grid.  Every thread keeps the whole
+// upper triangle (NA(NA+1)/2 complex float64 accumulators) and walks its share of the samples two at a time with 128-bit
+// streaming loads -- 2 NA loads in flight per thread and iteration, each antenna stream read exactly once, coalesced -- instead
+// of one CTA set per 4x4 block pair re-reading the streams of its rows and columns.  One CTA per SM (a single wave); the chunk
+// partials are added in chunk order by the CTA that finishes last (ticket counter), so the result does not depend on the
+// scheduling and no second launch is needed.
+template <int NA>
+__global__ void __launch_bounds__(kCovThreads, 1)
+cov_full_kernel(const float2* __restrict__ rx, long long N, int nAnts, int chunks, double2* __restrict__ part,
+                unsigned* __restrict__ tickets, double invN, double2* __restrict__ Ra) {
+    constexpr int NT = NA * (NA + 1) / 2;
+    const int chunk = blockIdx.x, b = blockIdx.y;
+    double2 acc[NT];
+#pragma unroll
+    for (int e = 0; e < NT; ++e) acc[e] = make_double2(0.0, 0.0);
+    const float2* __restrict__ base = rx + (long long)b * nAnts * N;
+    const long long nP = N >> 1;   // sample pairs (N even: checked on the host)
+    const long long per = (nP + chunks - 1) / chunks;
+    const long long u0 = (long long)chunk * per, u1 = (u0 + per < nP) ? u0 + per : nP;
+    // software pipeline: the loads of the next sample pair are issued right after the current pair has been widened to float64,
+    // so their latency runs behind the 8 NT fused multiply-adds of the current pair
+    auto fetch = [&](long long u, float4 (&v)[NA]) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+            v[a] = (a < nAnts && u < u1) ? __ldcs(reinterpret_cast<const float4*>(base + (long long)a * N) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 v[NA];
+    fetch(u0 + threadIdx.x, v);
+#pragma unroll 1
+    for (long long u = u0 + threadIdx.x; u < u1; u += kCovThreads) {
+        double2 xl[NA], xh[NA];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            xl[a] = make_double2((double)v[a].x, (double)v[a].y);
+            xh[a] = make_double2((double)v[a].z, (double)v[a].w);
+        }
+        fetch(u + kCovThreads, v);
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+#pragma unroll
+            for (int j = i; j < NA; ++j) {   // acc += conj(x_i) x_j, products of float32 values are exact in float64
+                double2& c = acc[i * NA - i * (i - 1) / 2 + (j - i)];
+                c.x = fma(xl[i].x, xl[j].x, fma(xl[i].y, xl[j].y, c.x));
+                c.y = fma(xl[i].x, xl[j].y, fma(-xl[i].y, xl[j].x, c.y));
+                c.x = fma(xh[i].x, xh[j].x, fma(xh[i].y, xh[j].y, c.x));
+                c.y = fma(xh[i].x, xh[j].y, fma(-xh[i].y, xh[j].x, c.y));
+            }
+    }
+    __shared__ double2 red[kCovThreads / 32][NT];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < NT; ++e) {
+        const double re = warp_sum(acc[e].x), im = warp_sum(acc[e].y);
+        if (lane == 0) red[warp][e] = make_double2(re, im);
+    }
+    __syncthreads();
+    if (threadIdx.x < NT) {
+        double2 s = make_double2(0.0, 0.0);
+        for (int w = 0; w < kCovThreads / 32; ++w) s = zadd(s, red[w][threadIdx.x]);
+        part[((long long)b * chunks + chunk) * NT + threadIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(tickets + b, 1u) == (unsigned)chunks - 1u;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // one warp per entry, the lanes stride over the chunk partials (independent loads), then a fixed-order shuffle tree: deterministic
+    for (int e = warp; e < NT; e += kCovThreads / 32) {
+        double2 s = make_double2(0.0, 0.0);
+        const double2* __restrict__ pb = part + (long long)b * chunks * NT + e;
+        for (int c = lane; c < chunks; c += 32) s = zadd(s, __ldcg(pb + (long long)c * NT));
+        s.x = warp_sum(s.x);
+        s.y = warp_sum(s.y);
+        int i = 0, r = e;
+        while (r >= NA - i) { r -= NA - i; ++i; }
+        const int j = i + r;
+        if (lane == 0 && i < nAnts && j < nAnts) {
+            s.x *= invN;
+            s.y *= invN;
+            if (i == j) s.y = 0.0;
+            Ra[(long long)b * nAnts * nAnts + i + (long long)j * nAnts] = s;
+            if (i != j) Ra[(long long)b * nAnts * nAnts + j + (long long)i * nAnts] = make_double2(s.x, -s.y);
+        }
+    }
+    if (threadIdx.x == 0) tickets[b] = 0u;   // ready for the next launch on this stream
+}
+
 int cov_antenna(Ctx* ctx, const float2* rx, long long N, int nAnts, int batch, double2* Ra, cudaStream_t st) {
     if (!rx || !Ra || N < 1 || nAnts < 1 || batch < 1) {
         set_error(ctx, "cov_antenna: invalid argument");
         return kErrInvalidArg;
+    }
+    if (nAnts <= 8 && (N & 1) == 0 && batch <= 1024 && (reinterpret_cast<uintptr_t>(rx) & 15) == 0) {   // single-pass kernel
+        const int NA = nAnts <= 2 ? 2 : (nAnts <= 4 ? 4 : 8), NT = NA * (NA + 1) / 2;
+        int chunks = ctx->numSMs / batch;
+        if (chunks < 1) chunks = 1;
+        const long long maxChunks = ((N >> 1) + kCovThreads - 1) / kCovThreads;
+        if (chunks > maxChunks) chunks = (int)maxChunks;
+        void* part = nullptr;
+        void* tick = nullptr;
+        int s = ctx_scratch(ctx, 8, sizeof(double2) * (size_t)batch * chunks * NT, &part);
+        if (s) return s;
+        static_assert(sizeof(unsigned) * 1024 <= 4096, "ticket slot");
+        const bool fresh = ctx->scratchBytes[24] < 4096;
+        if ((s = ctx_scratch(ctx, 24, 4096, &tick))) return s;
+        if (fresh) ISAC_CUDA_CHECK(ctx, cudaMemsetAsync(tick, 0, 4096, st));   // the kernels leave the counters at zero
+        dim3 grid(chunks, batch);
+        const int pr = prof_begin(ctx, kProfCov, st);
+        const double invN = 1.0 / (double)N;
+        if (NA == 2) cov_full_kernel<2><<<grid, kCovThreads, 0, st>>>(rx, N, nAnts, chunks, (double2*)part, (unsigned*)tick, invN, Ra);
+        else if (NA == 4) cov_full_kernel<4><<<grid, kCovThreads, 0, st>>>(rx, N, nAnts, chunks, (double2*)part, (unsigned*)tick, invN, Ra);
+        else cov_full_kernel<8><<<grid, kCovThreads, 0, st>>>(rx, N, nAnts, chunks, (double2*)part, (unsigned*)tick, invN, Ra);
+        prof_end(ctx, pr, st);
+        count_launches(ctx, 1);
+        ISAC_CUDA_CHECK(ctx, cudaGetLastError());
+        return kOk;
     }
     const int iBlocks = (nAnts + kCovBI - 1) / kCovBI, jBlocks = (nAnts + kCovBJ - 1) / kCovBJ;
     const int nPairs = iBlocks * jBlocks;

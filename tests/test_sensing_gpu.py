@@ -79,6 +79,18 @@ def test_generated_noise_statistics(P, workloads):
     assert abs(var / expect - 1) < 0.03
     assert abs(np.mean(d)) < 5 * np.sqrt(expect / d.size)
     assert abs(np.mean(d.real * d.imag)) < 0.03 * expect
+    # Gaussian shape (Box-Muller on the special-function unit): 4th moment of a complex normal = 2 var^2, tails present
+    assert abs(np.mean(np.abs(d) ** 4) / (2 * expect ** 2) - 1) < 0.08
+    x = np.concatenate([d.real, d.imag]) / np.sqrt(expect / 2)
+    assert abs(np.mean(np.abs(x) > 2.0) - 0.0455) < 0.006 and np.abs(x).max() > 3.5
+    # antennas, resource elements and seeds are independent draws
+    e = (g1 - g0)
+    a0, a1 = e[..., 0].ravel(), e[..., 1].ravel()
+    assert abs(np.vdot(a0, a1)) / (np.linalg.norm(a0) * np.linalg.norm(a1)) < 5 / np.sqrt(a0.size)
+    assert abs(np.vdot(a0[:-1], a0[1:])) / np.linalg.norm(a0) ** 2 < 5 / np.sqrt(a0.size)
+    g3 = P.sensing.monoStaticSensing(txw32, grid.shape, car, rp, cell["targetLoSConditions"], seed=8)
+    b0 = (g3 - g0)[..., 0].ravel()
+    assert abs(np.vdot(a0, b0)) / (np.linalg.norm(a0) * np.linalg.norm(b0)) < 5 / np.sqrt(a0.size)
 
 
 @pytest.mark.parametrize("name", ["tiny", "cfg1", "cfg2"])   # cfg2 = BASELINE config 2 at full size (3276 x 168 x 8 -> 4096 x 256)

@@ -54,6 +54,13 @@ profpmi)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:pmi_pair_fused -s 4 -c 1 -o gpurun_out/r2_prof_pmi_${TAG:-x} python tools/dev_pmi_variants.py > /dev/null 2>&1
   ls -la gpurun_out/*.ncu-rep
   ;;
+misc)
+  (timeout 900 python -m pytest tests/test_sensing_gpu.py tests/test_golden_gpu.py tests/test_cdl.py tests/test_properties_gpu.py tests/test_mex_mock_gpu.py -m gpu -q -x 2>&1 | tail -5) > gpurun_out/r2_misc_tests.log
+  cat gpurun_out/r2_misc_tests.log
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:echo_|cov_|eig_|music_|cdl_|prg_" -c 80 --csv python tools/profile_misc.py 2>/dev/null | grep -E "echo_|cov_|eig_|music_|cdl_|prg_" | awk -F'","' '{print $5, $NF}' | cut -c1-120 > gpurun_out/r2_misc_times.log
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:cdl_|prg_|ul_" -s 10 -c 40 --csv python tools/profile_comm.py 2>/dev/null | grep -E "cdl_|prg_|ul_" | awk -F'","' '{print $5, $NF}' | cut -c1-120 >> gpurun_out/r2_misc_times.log
+  sort gpurun_out/r2_misc_times.log | uniq -c | sort -k2 | head -60
+  ;;
 full)
   (timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -8) > gpurun_out/r2_full_tests.log
   cat gpurun_out/r2_full_tests.log
