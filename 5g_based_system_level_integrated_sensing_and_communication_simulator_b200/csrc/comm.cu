@@ -1355,44 +1355,56 @@ int ul_pmi_select_batch_finish(Ctx* ctx, std::vector<UlPmiResult>& outs) {
 // ------------------------------------------------------------------------------------------
 // PRG precoding (prgPrecode.m:53-144)
 // ------------------------------------------------------------------------------------------
-// One thread per (RE, antenna port).  The reference writes the layer symbols into a K x L x nLayers grid by linear
-// index (portgrid(indin) = symin, prgPrecode.m:131), multiplies every RE by F(:,:,prg) (:134) and reads the result back at
+// One thread per RE, looping over the antenna ports.  The reference writes the layer symbols into a K x L x nLayers grid by
+// linear index (portgrid(indin) = symin, prgPrecode.m:131), multiplies every RE by F(:,:,prg) (:134) and reads the result back at
 // the RE positions of the first layer (:139-144).  nrPDSCHIndices-style input has the same RE positions in every layer
 // column, so the symbol that lands at (position of row i, layer l) is symin(i,l): the kernel checks exactly that and
 // otherwise falls back to scanning the index list for the target linear index (last write wins; absent -> 0), which
-// reproduces the grid semantics for arbitrary indices without a scratch grid or a second pass.
+// reproduces the grid semantics for arbitrary indices without a scratch grid or a second pass.  The layer symbols, the index
+// arithmetic (a 64-bit modulo) and the PRG number are evaluated once per RE and reused for all P ports; every store of a warp
+// is one contiguous run along the RE axis.
 __global__ void __launch_bounds__(256)
 prg_precode_kernel(const float2* __restrict__ sym, const int* __restrict__ ind, int NRE, long long plane, int K, int nu,
                    const float2* __restrict__ F, int P, int NPRG, int nStartGrid, int Pd, float2* __restrict__ antsym,
                    int* __restrict__ antind) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)NRE * P) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NRE) return;
     // blockIdx.y: independent allocations of a batch (e.g. the cells of one slot), every array stacked along its last dim
     sym += (long long)blockIdx.y * NRE * nu;
     ind += (long long)blockIdx.y * NRE * nu;
     F += (long long)blockIdx.y * nu * P * NPRG;
     antsym += (long long)blockIdx.y * NRE * P;
     antind += (long long)blockIdx.y * NRE * P;
-    const int i = (int)(gid % NRE), p = (int)(gid / NRE);
-    const long long pos = ((long long)ind[i] - 1) % plane;  // RE position of the first layer's index
+    const long long i0 = (long long)ind[i] - 1;
+    const long long pos = (plane <= 0x7fffffffLL && i0 >= 0 && i0 <= 0xffffffffLL) ? (long long)((unsigned)i0 % (unsigned)plane)
+                                                                                  : i0 % plane;  // RE position of the first layer's index
     const int k = (int)(pos % K);
     const int prg = (nStartGrid + k / 12) / Pd;             // getPRGSet (prgPrecode.m:94-100), 0-based
-    float2 acc = make_float2(0.f, 0.f);
-    for (int l = 0; l < nu; ++l) {
-        const long long target = pos + plane * l + 1;
-        float2 x;
-        if ((long long)ind[i + (long long)NRE * l] == target) x = sym[i + (long long)NRE * l];
-        else {
-            x = make_float2(0.f, 0.f);
-            for (long long q = 0; q < (long long)NRE * nu; ++q)
-                if ((long long)ind[q] == target) x = sym[q];
+    float2 x[kMaxLayers];
+#pragma unroll
+    for (int l = 0; l < kMaxLayers; ++l) {
+        x[l] = make_float2(0.f, 0.f);
+        if (l < nu) {
+            const long long target = pos + plane * l + 1;
+            if ((long long)ind[i + (long long)NRE * l] == target) x[l] = sym[i + (long long)NRE * l];
+            else
+                for (long long q = 0; q < (long long)NRE * nu; ++q)
+                    if ((long long)ind[q] == target) x[l] = sym[q];
         }
-        const float2 f = __ldg(F + l + nu * (p + (long long)P * prg));
-        acc.x += x.x * f.x - x.y * f.y;                     // portgrid * F(:,:,prg) (prgPrecode.m:134)
-        acc.y += x.x * f.y + x.y * f.x;
     }
-    antsym[gid] = acc;
-    antind[gid] = (int)(pos + 1 + plane * p);
+    const float2* __restrict__ Fp = F + (long long)nu * P * prg;
+    for (int p = 0; p < P; ++p) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int l = 0; l < kMaxLayers; ++l)
+            if (l < nu) {
+                const float2 f = __ldg(Fp + l + nu * p);
+                acc.x += x[l].x * f.x - x[l].y * f.y;           // portgrid * F(:,:,prg) (prgPrecode.m:134)
+                acc.y += x[l].x * f.y + x[l].y * f.x;
+            }
+        antsym[i + (long long)NRE * p] = acc;
+        antind[i + (long long)NRE * p] = (int)(pos + 1 + plane * p);
+    }
 }
 
 int prg_precode_run(Ctx* ctx, int K, int Lsym, int nStartGrid, const float2* portsym, const int* portind, int NRE, int nu,
@@ -1407,8 +1419,7 @@ int prg_precode_run(Ctx* ctx, int K, int Lsym, int nStartGrid, const float2* por
     const int nrb = K / 12;
     const int Pd = (nrb + nStartGrid + NPRG - 1) / NPRG;  // Pd_BWP = ceil((NRB+nstartgrid)/NPRG)
     const int pr = prof_begin(ctx, kProfPrecode, st);
-    const long long m = (long long)NRE * P;
-    dim3 grid((unsigned)((m + 255) / 256), batch);
+    dim3 grid((unsigned)((NRE + 255) / 256), batch);
     prg_precode_kernel<<<grid, 256, 0, st>>>(portsym, portind, NRE, plane, K, nu, F, P, NPRG, nStartGrid, Pd, antsym, antind);
     prof_end(ctx, pr, st);
     count_launches(ctx, 1);
