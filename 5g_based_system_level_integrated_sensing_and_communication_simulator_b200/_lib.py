@@ -104,6 +104,7 @@ def _declare(lib):
         "isac_synchronize": ([vp], C.c_int),
         "isac_profile_enable": ([vp, i32], C.c_int),
         "isac_profile_collect": ([vp, vp, vp, vp], C.c_int),
+        "isac_profile_timeline": ([vp, vp, i32, vp, vp, vp, P(i32)], C.c_int),
         "isac_version": ([], C.c_char_p),
         "isac_rdm_plan_create": ([vp, P(RdmConfig), P(vp)], C.c_int),
         "isac_rdm_plan_destroy": ([vp], C.c_int),
@@ -262,6 +263,17 @@ class Context:
         check(self.lib.isac_profile_collect(self.handle, ptr(ms), ptr(cnt), C.byref(n)), self.handle)
         out = {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.PROF_SLOTS) if cnt[i]}
         return out, int(n.value)
+
+    def profile_timeline(self, base_event, max_rec=65536):
+        """[(slot name, begin_ms, end_ms)] of the kernel groups recorded since the last collect, relative to the torch CUDA
+        event ``base_event`` (call before ``profile_collect``, which clears the records)."""
+        slots = np.zeros(max_rec, dtype=np.int32)
+        t0 = np.zeros(max_rec)
+        t1 = np.zeros(max_rec)
+        n = C.c_int32()
+        check(self.lib.isac_profile_timeline(self.handle, C.c_void_p(base_event.cuda_event), max_rec, ptr(slots), ptr(t0), ptr(t1),
+                                             C.byref(n)), self.handle)
+        return [(self.PROF_SLOTS[slots[i]], float(t0[i]), float(t1[i])) for i in range(n.value)]
 
     def close(self):
         if self.handle:

@@ -248,6 +248,26 @@ int isac_profile_collect(isac_ctx* h, double* msPerSlot, int32_t* countPerSlot, 
     return ISAC_OK;
 }
 
+int isac_profile_timeline(isac_ctx* h, void* baseEvent, int32_t maxRec, int32_t* slots, double* beginMs, double* endMs, int32_t* nRec) {
+    if (!h || !baseEvent || !slots || !beginMs || !endMs || !nRec || maxRec < 0) return ISAC_ERR_INVALID_ARG;
+    Ctx* c = &h->c;
+    cudaSetDevice(c->device);
+    ISAC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    int n = 0;
+    for (auto& r : c->prof) {
+        if (n >= maxRec) break;
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, (cudaEvent_t)baseEvent, r.a) != cudaSuccess ||
+            cudaEventElapsedTime(&b, (cudaEvent_t)baseEvent, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+        slots[n] = r.slot;
+        beginMs[n] = (double)a;
+        endMs[n] = (double)b;
+        ++n;
+    }
+    *nRec = n;
+    return ISAC_OK;
+}
+
 int isac_synchronize(isac_ctx* h) {
     if (!h) return ISAC_ERR_INVALID_ARG;
     ISAC_CUDA_CHECK(&h->c, cudaStreamSynchronize(h->c.stream));
@@ -803,6 +823,11 @@ struct isac_csi_plan {
     size_t arenaBytes = 0;
     // a report enqueued by ri_enqueue and not yet finished (isac_csi_report_enqueue_dev / _finish)
     cudaEvent_t ready = nullptr;   // recorded behind the D2H copy of the arena
+    // host-side result records of the last report: kept between reports so that the per-UE vectors are reused, not reallocated
+    std::vector<double> riBuf;
+    std::vector<PmiResult> chosenBuf;
+    std::vector<std::vector<PmiResult>> allBuf;
+    bool scored[kMaxLayers] = {};   // ranks whose records in the `all` list of the last ri_finish are current
     const float2* pendH = nullptr;
     std::vector<double> pendNVar;
     int pendBatch = 0;             // 0 = nothing pending
@@ -1058,12 +1083,14 @@ static int ri_finish(isac_csi_plan* pl, std::vector<double>& RI, std::vector<Pmi
     if (batch < 1) { set_error(c, "csi report: nothing enqueued"); return kErrInvalidArg; }
     pl->pendBatch = 0;
     const int maxRank = csi_max_rank(pl->cfg);
-    all.assign(kMaxLayers, {});
+    all.resize(kMaxLayers);   // the per-UE records of an earlier report stay allocated (their vectors are overwritten in place)
+    for (int r = 0; r < kMaxLayers; ++r) pl->scored[r] = false;
     std::vector<int> valid;
     for (int r = 1; r <= maxRank && r <= kMaxLayers; ++r)
         if (pl->cfg.riRestriction[r - 1]) valid.push_back(r);
     RI.assign(batch, NAN);
-    chosen.assign(batch, PmiResult());
+    chosen.resize(batch);
+    for (auto& r : chosen) { r.allNaN = false; r.i1[0] = r.i1[1] = r.i1[2] = 0; r.i2.clear(); r.sinrSel.clear(); r.sinrWbSel.clear(); }
     const int nSB = pl->byRank[0] ? pl->byRank[0]->nSB : 1;
     if (!pl->pendLaunched) {  // riSelect.m:235-245
         for (auto& r : chosen) { r.allNaN = true; r.i2.assign(nSB, NAN); }
@@ -1073,6 +1100,7 @@ static int ri_finish(isac_csi_plan* pl, std::vector<double>& RI, std::vector<Pmi
     for (int r : valid) {
         int st = pmi_select_collect_finish(pl->byRank[r - 1], batch, all[r - 1]);
         if (st) return st;
+        pl->scored[r - 1] = true;
     }
     for (int b = 0; b < batch; ++b) {
         double best = -INFINITY;
@@ -1174,9 +1202,9 @@ int isac_csi_report_finish(isac_csi_plan* pl, const double* table, int32_t table
     const float2* H = pl->pendH;
     const std::vector<double> nVar = pl->pendNVar;
     const int batch = pl->pendBatch;
-    std::vector<double> ri;
-    std::vector<PmiResult> chosen;
-    std::vector<std::vector<PmiResult>> all;
+    std::vector<double>& ri = pl->riBuf;
+    std::vector<PmiResult>& chosen = pl->chosenBuf;
+    std::vector<std::vector<PmiResult>>& all = pl->allBuf;
     int st = ri_finish(pl, ri, chosen, all);
     if (st) return st;
     PmiPlan* p0 = pl->byRank[0];
@@ -1199,9 +1227,10 @@ int isac_csi_report_finish(isac_csi_plan* pl, const double* table, int32_t table
             set_error(c, "nr5g:hDLPMISelect:InvalidNumLayers");
             return ISAC_ERR_INVALID_ARG;
         }
-        if (all[rank - 1].empty()) {  // rank not scored by the RI loop (restricted): evaluate it now
+        if (!pl->scored[rank - 1]) {  // rank not scored by the RI loop (restricted): evaluate it now
             if ((st = pmi_select_run(pl->byRank[rank - 1], H, nVar.data(), batch, c->stream))) return st;
             if ((st = pmi_select_collect(pl->byRank[rank - 1], batch, all[rank - 1]))) return st;
+            pl->scored[rank - 1] = true;
         }
         const PmiResult& pr = all[rank - 1][b];
         CsiReport rep;

@@ -920,7 +920,8 @@ int pmi_select_collect_enqueue(PmiPlan* p, int batch, cudaStream_t st) {
 // parse the staged results; the caller has synchronised the stream after pmi_select_collect_enqueue
 int pmi_select_collect_finish(PmiPlan* p, int batch, std::vector<PmiResult>& out) {
     const int nu = p->nLayers, nSB = p->nSB, nC = p->nCqiSB;
-    out.assign(batch, PmiResult());
+    out.resize(batch);   // elements (and their vectors' capacity) survive when the caller keeps `out` between reports
+    for (auto& r : out) { r.allNaN = false; r.i1[0] = r.i1[1] = r.i1[2] = 0; }
     if (plan_all_nan(p)) {
         for (auto& r : out) {
             r.allNaN = true;

@@ -225,9 +225,12 @@ class CommWorkload:
         ctx.use_torch_stream()
         frame_t0 = 0.010 * step
         srs = {3: 0, 4: 1, 11: 0, 12: 1, 19: 0}   # UEs 0-3 at slots 3, 11, 19, UEs 4-7 at slots 4, 12 (period 8, offset 3 + floor(ue/4))
-        ul_pending = False
+        ul_pending = csi_pending = False
         for slot in range(20):                    # slot order of the frame (TDD DDDSU @30 kHz); the GPU's cells advance together
             if slot % 5 < 3:                      # DL slot: PDSCH + DM-RS precoding of every cell (gNBPhy.m:822,826)
+                if csi_pending:
+                    csi_pending = False
+                    check(lib.isac_csi_report_finish(*self.csi_fin_args), ctx.handle)
                 for a in self.prg_args:
                     check(lib.isac_prg_precode_batch_dev(*a), ctx.handle)
             if slot % 5 == 2:                     # CSI-RS occasion (period 5 slots): channel of all UEs + fused RI/PMI/CQI report
@@ -237,7 +240,9 @@ class CommWorkload:
                 if fillers:
                     fillers.pop(0)()
                     ctx.use_torch_stream()
-                check(lib.isac_csi_report_finish(*self.csi_fin_args), ctx.handle)
+                    check(lib.isac_csi_report_finish(*self.csi_fin_args), ctx.handle)
+                else:                             # nothing to put behind the report: collect it where it is first needed (the
+                    csi_pending = True            #   next DL slot's precoding), behind the S / U slots' SRS work
             if ul_pending:                        # TPMI results of the previous slot's SRS occasion: their kernels ran behind
                 ul_pending = False                #   this slot's precoding launches, so the host only collects here
                 check(lib.isac_ul_pmi_select_batch_finish(*self.ul_fin_args), ctx.handle)
@@ -248,6 +253,8 @@ class CommWorkload:
                 # (Hest(:,srsSymbols,:,:) out of nrChannelEstimate, gNBPhy.m:1030-1035), not only the comb-4 REs
                 check(lib.isac_ul_pmi_select_batch_enqueue_dev(*self.ul_enq_args), ctx.handle)
                 ul_pending = True
+        if csi_pending:                           # report of the frame's last occasion (its host tail runs behind slot 19's SRS kernels)
+            check(lib.isac_csi_report_finish(*self.csi_fin_args), ctx.handle)
         if ul_pending:                            # SRS occasion in the frame's last slot
             check(lib.isac_ul_pmi_select_batch_finish(*self.ul_fin_args), ctx.handle)
 
@@ -260,6 +267,37 @@ class CommWorkload:
         # (nul channels x 1 symbol x 8x2) batched generations of a step (8 bytes per channel coefficient)
         total = 4 * self.nb * 8 * K * 14 * 8 * 8 + 5 * self.nul * 8 * K * 1 * 8 * 2
         return {"cdl": total / 9.0}
+
+
+def write_timeline(path, base_event, contexts, ms_total, frames):
+    """Poor man's timeline of the timed region (no nsys in the image): the CUDA-event stamps of every kernel group, merged over
+    the contexts, with the idle gaps between consecutive groups and what ran on either side of them."""
+    rec = sorted((r for cx in contexts for r in cx.profile_timeline(base_event)), key=lambda r: r[1])
+    busy, gaps, by_pair, last_end, last_name = 0.0, [], {}, 0.0, "start"
+    for name, a, b in rec:
+        busy += b - a
+        g = a - last_end
+        if g > 0.002:
+            gaps.append((g, last_name, name, a))
+            k = (last_name, name)
+            by_pair[k] = (by_pair.get(k, (0.0, 0))[0] + g, by_pair.get(k, (0.0, 0))[1] + 1)
+        if b > last_end:
+            last_end, last_name = b, name
+    with open(path, "w") as f:
+        f.write("# bench.py --timeline: %d kernel groups over %d frames, %.3f ms timed, %.3f ms inside groups (%.1f %%), "
+                "%.3f ms in %d gaps > 2 us\n" % (len(rec), frames, ms_total, busy, 100 * busy / ms_total,
+                                                 sum(g[0] for g in gaps), len(gaps)))
+        f.write("# idle time by (group before, group after), per frame:\n")
+        for (a, b), (t, n) in sorted(by_pair.items(), key=lambda kv: -kv[1][0]):
+            f.write("#   %-14s -> %-14s %8.1f us/frame in %5.1f gaps/frame (mean %.1f us)\n" % (a, b, 1e3 * t / frames, n / frames, 1e3 * t / n))
+        f.write("# one frame in the middle of the region (begin_us, duration_us, gap_before_us, group):\n")
+        lo = ms_total * (frames // 2) / frames
+        hi = ms_total * (frames // 2 + 1) / frames
+        prev = None
+        for name, a, b in rec:
+            if a >= lo and a < hi:
+                f.write("%10.1f %8.1f %8.1f  %s\n" % (1e3 * (a - lo), 1e3 * (b - a), 1e3 * (a - prev) if prev is not None else 0.0, name))
+            prev = max(prev, b) if prev is not None else b
 
 
 def run_b200(args):
@@ -356,6 +394,8 @@ def run_b200(args):
     torch.cuda.synchronize()
     t_wall1 = time.time()
     ms_total = e0.elapsed_time(e1)
+    if args.timeline:
+        write_timeline(args.timeline, e0, [ctx] + ([ctx_s] if ctx_s is not ctx else []), ms_total, args.steps * F)
     prof, launches = ctx.profile_collect()
     if ctx_s is not ctx:
         prof_s, launches_s = ctx_s.profile_collect()
@@ -805,6 +845,7 @@ def main():
                     help="cfg2 (default): weak scaling, cells_per_gpu cells per GPU; cfg3 / cfg5: the 7-cell 32-port and the 19-cell "
                          "openStreetMapCity scenarios, strong scaling (cells sharded over the GPUs)")
     ap.add_argument("--cfg5-radio", default="shipped", choices=["shipped", "small"])
+    ap.add_argument("--timeline", default=None, help="write the CUDA-event timeline of the timed region (kernel groups and idle gaps) to this file")
     ap.add_argument("--skip-host-h", action="store_true", help="skip the host-resident-H occasion measurement of the e2e object")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--sense-ctx", default="own", choices=["own", "shared"],

@@ -56,6 +56,9 @@ int isac_synchronize(isac_ctx* ctx);
 #define ISAC_PROF_SLOTS 16
 int isac_profile_enable(isac_ctx* ctx, int32_t on);
 int isac_profile_collect(isac_ctx* ctx, double* msPerSlot, int32_t* countPerSlot, int64_t* launches);
+/* Tooling: begin / end time stamps (ms after `baseEvent`, a cudaEvent_t recorded on the same device) of every kernel group
+ * recorded since the last isac_profile_collect, in launch order -- the per-frame timeline bench.py --timeline prints. */
+int isac_profile_timeline(isac_ctx* ctx, void* baseEvent, int32_t maxRec, int32_t* slots, double* beginMs, double* endMs, int32_t* nRec);
 const char* isac_version(void);
 /* Device-memory helpers for gateways that drive `_dev` entry points without linking the CUDA runtime themselves (the MEX
  * files of matlab/mex): allocation on the context's device, blocking copies ordered on the context's stream. */

@@ -182,6 +182,29 @@ def test_covariance_and_music_doa(P, workloads):
     assert e.value.status == 7
 
 
+@pytest.mark.parametrize("n,N", [(1, 4096), (2, 30000), (3, 30001), (4, 1234), (5, 60000), (8, 550368), (8, 77), (8, 2), (9, 5000), (16, 9999)])
+def test_antenna_covariance_sizes(P, n, N):
+    """fft2D.m:106-107 covariance over array sizes on both sides of the single-pass kernel (<= 8 elements, even sample count),
+    odd sample counts and sample counts below one CTA; float64 accumulation of exact products, so the bar is 1e-12."""
+    import torch
+    _lib = importlib.import_module(PKG + "._lib")
+    rng = np.random.default_rng(100 * n + N % 97)
+    X = (rng.standard_normal((n, N)) + 1j * rng.standard_normal((n, N))).astype(np.complex64)
+    X[:, ::7] *= 30.0
+    Xd = X.astype(np.complex128)
+    Ra_ref = (Xd.conj() @ Xd.T) / N          # Ra(i,j) = mean(conj(x_i) x_j): the orientation isac_antenna_covariance_dev documents
+    ctx = _lib.get_context(0)
+    g_d = torch.from_numpy(np.ascontiguousarray(X)).cuda()
+    Ra = np.zeros((n, n), dtype=np.complex128, order="F")
+    ctx.use_torch_stream()
+    for rep in range(2):                      # second call: the ticket counters of the single-pass kernel were left at zero
+        Ra[:] = 0
+        _lib.check(ctx.lib.isac_antenna_covariance_dev(ctx.handle, _lib.ptr(g_d), N, n, _lib.ptr(Ra)), ctx.handle)
+        err = np.abs(Ra - Ra_ref).max() / np.abs(Ra_ref).max()
+        assert err <= 1e-12, (n, N, rep, err)
+        assert np.array_equal(Ra, Ra.conj().T) and np.all(Ra.imag[np.diag_indices(n)] == 0)
+
+
 @pytest.mark.parametrize("nxy", [(4, 4), (10, 9)])
 def test_music_upa_spectrum(P, nxy):
     """UPA branch (music.m:31-63): spectrum array parity (the reference's peak picker does not exist).
