@@ -61,6 +61,12 @@ misc)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:cdl_|prg_|ul_" -s 10 -c 40 --csv python tools/profile_comm.py 2>/dev/null | grep -E "cdl_|prg_|ul_" | awk -F'","' '{print $5, $NF}' | cut -c1-120 >> gpurun_out/r2_misc_times.log
   sort gpurun_out/r2_misc_times.log | uniq -c | sort -k2 | head -60
   ;;
+prof2)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:cdl_response_umma -s 9 -c 1 -o gpurun_out/r2_prof2_cdl_dl python tools/profile_comm.py > /dev/null 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:echo_|cov_|eig_small|prg_precode" -s 8 -c 6 -o gpurun_out/r2_prof2_misc python tools/profile_misc.py > /dev/null 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2_prof2_bench_launches.csv python bench.py --steps 1 --warmup 1 --frames-per-step 1 --no-cpu-baseline --skip-host-h > gpurun_out/r2_prof2_bench_under_ncu.json 2> /dev/null
+  ls -la gpurun_out | tail -6
+  ;;
 full)
   (timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -8) > gpurun_out/r2_full_tests.log
   cat gpurun_out/r2_full_tests.log
