@@ -56,6 +56,93 @@ __device__ __forceinline__ int swz(int id, int e) {
     return 0;
 }
 
+// Low ranks: E of the G REs of a candidate inside one thread (E = G for ranks 1-3, E = 2 for ranks 4-5).  For these ranks the
+// factorisation is a handful of flops and the lane-per-RE form spends its time on index decoding, validity loads and the shuffle
+// sums; here the index words are decoded once for E REs, the E independent factorisations interleave (instruction-level
+// parallelism where the lane-per-RE form had only 3 warps per scheduler to hide the float64 latency) and the chunk sum needs
+// fewer (or no) shuffles.  The sum keeps the order of the shuffle tree, (e0 + e1) + (e2 + e3), so all forms give identical bits.
+template <int NU, int G, int E>
+__device__ __noinline__ void fused_rank_eval_multi(const FusedRank rk, const double2* __restrict__ Gt, double nVar,
+                                                   double* __restrict__ part, int nValid) {
+    static_assert(G % E == 0 && (E == 1 || E == 2 || E == 4), "REs per thread");
+    constexpr int NT = NU * (NU + 1) / 2;
+    constexpr int NW = (NT + 7) / 8;
+    constexpr int LPC = G / E;   // lanes per candidate
+    const int nItems = rk.nCand * LPC;
+    for (int base = 0; base < nItems; base += blockDim.x) {   // warp-uniform trip count: every lane reaches the shuffles
+        const int item = base + threadIdx.x;
+        const bool act = item < nItems;
+        const int c = act ? item / LPC : 0, e0 = (item % LPC) * E;
+        if (item + (int)blockDim.x < nItems)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rk.ent + (size_t)((item + blockDim.x) / LPC) * rk.ntPad)));
+        double s[E][NU];
+        bool ok[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) ok[j] = false;
+        if (act) {
+            const uint4* __restrict__ ep = reinterpret_cast<const uint4*>(rk.ent + (size_t)c * rk.ntPad);
+            uint4 ev[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) ev[w] = __ldg(ep + w);
+            if (rk.valid[c]) {   // else: restricted precoder, contributes nothing (dlPMISelect.m:418)
+                double2 A[E][NT];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const uint32_t q[4] = {ev[w].x, ev[w].y, ev[w].z, ev[w].w};
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int t = w * 8 + u;
+                        if (t < NT) {
+                            const uint32_t id = (q[u >> 1] >> ((u & 1) * 16)) & 0xffffu;
+                            const int ix = (int)(id & 0x7fffu);
+                            const bool cj = (id & 0x8000u) != 0;
+#pragma unroll
+                            for (int j = 0; j < E; ++j) {
+                                const double2 g = Gt[ix * G + swz<G>(ix, e0 + j)];
+                                A[j][t] = make_double2(g.x, cj ? -g.y : g.y);
+                            }
+                        }
+                    }
+                }
+                const double nv = nVar * (rk.invScale2 ? rk.invScale2[c] : rk.invS2);
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    chol_sinr<NU>(A[j], nv, s[j], 1);
+                    ok[j] = e0 + j < nValid;
+#pragma unroll
+                    for (int l = 0; l < NU; ++l) ok[j] = ok[j] && (s[j][l] == s[j][l]);   // sum(...,'omitnan'): a NaN RE is skipped
+                }
+            }
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            cnt += ok[j] ? 1 : 0;
+            if (!ok[j]) {
+#pragma unroll
+                for (int l = 0; l < NU; ++l) s[j][l] = 0.0;
+            }
+        }
+        double tot[NU];
+#pragma unroll
+        for (int l = 0; l < NU; ++l) {
+            if (E == 4) tot[l] = (s[0][l] + s[1][l]) + (s[2][l] + s[3][l]);
+            else if (E == 2) tot[l] = s[0][l] + s[1][l];
+            else tot[l] = s[0][l];
+        }
+#pragma unroll
+        for (int o = 1; o < LPC; o <<= 1) {
+#pragma unroll
+            for (int l = 0; l < NU; ++l) tot[l] += __shfl_xor_sync(0xffffffffu, tot[l], o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if (act && e0 == 0) {
+#pragma unroll
+            for (int l = 0; l < NU; ++l) part[(size_t)l * rk.nCand + c] = cnt ? tot[l] : NAN;
+        }
+    }
+}
+
 template <int NU, int G>
 __device__ __noinline__ void fused_rank_eval(const FusedRank rk, const double2* __restrict__ Gt, double nVar, double* __restrict__ part,
                                              int nValid) {
@@ -209,10 +296,10 @@ pmi_pair_fused_kernel(const __grid_constant__ FusedDev p) {
         const FusedRank rk = p.rk[q];
         double* __restrict__ part = rk.part + ((size_t)b * p.nChunks + chunk) * rk.nu * (size_t)rk.nCand;
         switch (rk.nu) {
-            case 1: fused_rank_eval<1, G>(rk, Gt, nVar, part, nValid); break;
-            case 2: fused_rank_eval<2, G>(rk, Gt, nVar, part, nValid); break;
-            case 3: fused_rank_eval<3, G>(rk, Gt, nVar, part, nValid); break;
-            case 4: fused_rank_eval<4, G>(rk, Gt, nVar, part, nValid); break;
+            case 1: fused_rank_eval_multi<1, G, G>(rk, Gt, nVar, part, nValid); break;
+            case 2: fused_rank_eval_multi<2, G, G>(rk, Gt, nVar, part, nValid); break;
+            case 3: fused_rank_eval_multi<3, G, G>(rk, Gt, nVar, part, nValid); break;
+            case 4: fused_rank_eval_multi<4, G, (G > 2 ? 2 : G)>(rk, Gt, nVar, part, nValid); break;
             case 5: fused_rank_eval<5, G>(rk, Gt, nVar, part, nValid); break;
             case 6: fused_rank_eval<6, G>(rk, Gt, nVar, part, nValid); break;
             case 7: fused_rank_eval<7, G>(rk, Gt, nVar, part, nValid); break;
