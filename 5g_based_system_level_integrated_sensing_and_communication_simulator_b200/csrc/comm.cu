@@ -606,6 +606,7 @@ int pmi_plan_create(Ctx* ctx, const CsiConfig& cin, int nLayers, int maxBatch, P
                 for (int j = 0; j <= i; ++j)
                     ent[(size_t)c * ntPad + i * (i + 1) / 2 + j] = (uint16_t)(colpair_of(colId[i], colId[j]) & 0xffff);
         }
+        p->entH = ent;
         if ((s = upload(ctx, &p->d_ent, ent)) || (!is2.empty() && (s = upload(ctx, &p->d_invScale2, is2)))) {
             pmi_plan_destroy(p);
             return s;
@@ -686,7 +687,7 @@ void pmi_plan_destroy(PmiPlan* p) {
     cudaFree(p->d_valid); cudaFree(p->d_reK); cudaFree(p->d_reL); cudaFree(p->d_reSb); cudaFree(p->d_reW);
     cudaFree(p->d_reCqiSb); cudaFree(p->d_reCqiW); cudaFree(p->d_S); cudaFree(p->d_total); cudaFree(p->d_sub);
     if (p->ownsRes) cudaFree(p->d_res);
-    cudaFree(p->d_ent); cudaFree(p->d_invScale2);
+    cudaFree(p->d_ent); cudaFree(p->d_entF); cudaFree(p->d_invScale2);
     cudaFree(p->d_chunkRe0); cudaFree(p->d_chunkN); cudaFree(p->d_sbChunk); cudaFree(p->d_cqiChunk);
     cudaFree(p->d_sbW); cudaFree(p->d_cqiSbW); cudaFree(p->d_part);
     if (p->sh && --p->sh->refs == 0) {

@@ -73,6 +73,8 @@ struct PmiPlan {
     double* d_nVar = nullptr;       // [batch] (unused: nVar travels as a kernel parameter)
     PmiShared* sh = nullptr;        // Gram-pair dictionary (shared between the ranks of a CSI plan)
     uint16_t* d_ent = nullptr;      // [nCand][ntPad]: column-pair index of every packed lower-triangle entry
+    std::vector<uint16_t> entH;     // host copy
+    uint16_t* d_entF = nullptr;     // fused path: the same entries as table SLOT indices of RE 0, id * G + swizzle(id) (bit 15 kept)
     double* d_invScale2 = nullptr;  // [nCand] 1/scale^2 (explicit codebooks only)
     double invS2 = 1.0;             // 1/scale^2 of the rank
     int ntPad = 0;

@@ -24,7 +24,7 @@
 namespace isac {
 
 struct FusedRank {
-    const uint16_t* ent;     // [nCand][ntPad]: column-pair index of each packed lower-triangle entry (bit 15: conjugate)
+    const uint16_t* ent;     // [nCand][ntPad]: table slot (of RE 0) of each packed lower-triangle entry, id * G + swizzle(id) (bit 15: conjugate)
     const uint8_t* valid;
     const double* invScale2; // per candidate 1/scale^2 (explicit codebooks) or nullptr
     double* part;            // [batch][nChunks][nu][nCand] partial sums (NaN: nothing to add)
@@ -93,12 +93,12 @@ __device__ __noinline__ void fused_rank_eval_multi(const FusedRank rk, const dou
                     for (int u = 0; u < 8; ++u) {
                         const int t = w * 8 + u;
                         if (t < NT) {
-                            const uint32_t id = (q[u >> 1] >> ((u & 1) * 16)) & 0xffffu;
-                            const int ix = (int)(id & 0x7fffu);
+                            const uint32_t id = (q[u >> 1] >> ((u & 1) * 16)) & 0xffffu;   // slot of RE 0 | conjugate flag << 15
+                            const uint32_t ix = id & 0x7fffu;
                             const bool cj = (id & 0x8000u) != 0;
 #pragma unroll
                             for (int j = 0; j < E; ++j) {
-                                const double2 g = Gt[ix * G + swz<G>(ix, e0 + j)];
+                                const double2 g = Gt[ix ^ (uint32_t)(e0 + j)];            // the swizzle is an XOR of the low bits
                                 A[j][t] = make_double2(g.x, cj ? -g.y : g.y);
                             }
                         }
@@ -175,8 +175,8 @@ __device__ __noinline__ void fused_rank_eval(const FusedRank rk, const double2* 
                     for (int u = 0; u < 8; ++u) {
                         const int t = w * 8 + u;
                         if (t < NT) {   // bit 15: the pair is stored as (j,i) -> conjugate
-                            const uint32_t id = (q[u >> 1] >> ((u & 1) * 16)) & 0xffffu;
-                            const double2 g = Gt[(id & 0x7fffu) * G + swz<G>((int)(id & 0x7fffu), e)];
+                            const uint32_t id = (q[u >> 1] >> ((u & 1) * 16)) & 0xffffu;   // slot of RE 0 | conjugate flag << 15
+                            const double2 g = Gt[(id & 0x7fffu) ^ (uint32_t)e];              // slot of RE e: the swizzle is an XOR of the low bits
                             A[t] = make_double2(g.x, (id & 0x8000u) ? -g.y : g.y);
                         }
                     }
@@ -520,6 +520,15 @@ int pmi_plan_prepare_fused(PmiPlan* p, int G) {
     p->d_part = nullptr;
     const size_t n = (size_t)p->maxBatch * (nChunks ? nChunks : 1) * p->nLayers * p->tab.nCand();
     ISAC_CUDA_CHECK(ctx, cudaMalloc((void**)&p->d_part, sizeof(double) * n));
+    {   // index words of the candidate stage as slot numbers: slot(id, e) = (id * G + k(id)) ^ e with k = the swizzle of swz<G>
+        std::vector<uint16_t> ef(p->entH.size());
+        for (size_t i = 0; i < ef.size(); ++i) {
+            const uint32_t id = p->entH[i] & 0x7fffu;
+            const uint32_t k = G == 4 ? ((id >> 1) & 3u) : (G == 2 ? ((id >> 2) & 1u) : 0u);
+            ef[i] = (uint16_t)((id * (uint32_t)G + k) | (p->entH[i] & 0x8000u));
+        }
+        if ((s = upload_vec(ctx, &p->d_entF, ef))) return s;
+    }
     p->fG = G;
     p->nChunks = nChunks;
     return kOk;
@@ -540,6 +549,7 @@ int pmi_fused_pick(const PmiShared* sh, int R, int* threads, int* minb) {
         if (forceG && G != forceG) continue;
         const size_t b = fused_smem_bytes(sh, R, G);
         if (b > cap) continue;
+        if ((sh->cpTerms.size() / (sh->cpT ? sh->cpT : 1)) * (size_t)G > 0x8000u) continue;   // slot numbers are 15-bit
         int T = G == 4 ? 384 : 128, mb = G == 4 ? 1 : (G == 2 ? 2 : 3);
         if (G == 4 && forceT == 256) T = 256;
         if (G == 2 && forceT == 256) { T = 256; mb = 1; }
@@ -586,7 +596,7 @@ int pmi_fused_run(PmiPlan* const* grp, int n, const float2* H, const double* nv,
     for (int i = 0; i < n; ++i) {
         PmiPlan* q = grp[i];
         FusedRank& rk = d.rk[d.nRanks++];
-        rk.ent = q->d_ent; rk.valid = q->d_valid; rk.invScale2 = q->d_invScale2; rk.part = q->d_part; rk.invS2 = q->invS2;
+        rk.ent = q->d_entF; rk.valid = q->d_valid; rk.invScale2 = q->d_invScale2; rk.part = q->d_part; rk.invS2 = q->invS2;
         rk.nCand = q->tab.nCand(); rk.nu = q->nLayers; rk.ntPad = q->ntPad;
         FusedPostRank& pr = pd.rk[pd.nRanks++];
         const CodebookTable& t = q->tab;
