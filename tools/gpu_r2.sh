@@ -70,6 +70,7 @@ prof2)
 full)
   (timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -8) > gpurun_out/r2_full_tests.log
   cat gpurun_out/r2_full_tests.log
+  (timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3)
   timeout 600 python bench.py > gpurun_out/r2_full_bench.json 2> gpurun_out/r2_full_bench.err
   tail -n 3 gpurun_out/r2_full_bench.err; cat gpurun_out/r2_full_bench.json | cut -c1-1500
   ;;
