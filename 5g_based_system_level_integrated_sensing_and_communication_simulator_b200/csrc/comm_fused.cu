@@ -93,13 +93,13 @@ __device__ __noinline__ void fused_rank_eval_multi(const FusedRank rk, const dou
                     for (int u = 0; u < 8; ++u) {
                         const int t = w * 8 + u;
                         if (t < NT) {
-                            const uint32_t id = (q[u >> 1] >> ((u & 1) * 16)) & 0xffffu;   // slot of RE 0 | conjugate flag << 15
-                            const uint32_t ix = id & 0x7fffu;
-                            const bool cj = (id & 0x8000u) != 0;
+                            const uint32_t qq = q[u >> 1];                                   // two entries: slot of RE 0 | conjugate flag << 15
+                            const uint32_t ix = ((u & 1) ? (qq >> 16) : qq) & 0x7fffu;
+                            const uint32_t sgn = ((u & 1) ? qq : (qq << 16)) & 0x80000000u;  // the flag moved onto the sign bit
 #pragma unroll
                             for (int j = 0; j < E; ++j) {
                                 const double2 g = Gt[ix ^ (uint32_t)(e0 + j)];            // the swizzle is an XOR of the low bits
-                                A[j][t] = make_double2(g.x, cj ? -g.y : g.y);
+                                A[j][t] = make_double2(g.x, __hiloint2double(__double2hiint(g.y) ^ (int)sgn, __double2loint(g.y)));
                             }
                         }
                     }
@@ -175,9 +175,11 @@ __device__ __noinline__ void fused_rank_eval(const FusedRank rk, const double2* 
                     for (int u = 0; u < 8; ++u) {
                         const int t = w * 8 + u;
                         if (t < NT) {   // bit 15: the pair is stored as (j,i) -> conjugate
-                            const uint32_t id = (q[u >> 1] >> ((u & 1) * 16)) & 0xffffu;   // slot of RE 0 | conjugate flag << 15
-                            const double2 g = Gt[(id & 0x7fffu) ^ (uint32_t)e];              // slot of RE e: the swizzle is an XOR of the low bits
-                            A[t] = make_double2(g.x, (id & 0x8000u) ? -g.y : g.y);
+                            const uint32_t qq = q[u >> 1];                                   // two entries: slot of RE 0 | conjugate flag << 15
+                            const uint32_t slot = ((u & 1) ? (qq >> 16) : qq) & 0x7fffu;
+                            const uint32_t sgn = ((u & 1) ? qq : (qq << 16)) & 0x80000000u;  // the flag moved onto the sign bit
+                            const double2 g = Gt[slot ^ (uint32_t)e];                        // slot of RE e: the swizzle is an XOR of the low bits
+                            A[t] = make_double2(g.x, __hiloint2double(__double2hiint(g.y) ^ (int)sgn, __double2loint(g.y)));
                         }
                     }
                 }
