@@ -19,6 +19,7 @@
 #include "ctx.cuh"
 #include "sinr_core.cuh"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 namespace isac {
@@ -247,6 +248,7 @@ pmi_pair_fused_kernel(const __grid_constant__ FusedDev p) {
     }
     __syncthreads();
     // 2. atom Gram pairs Gm[pi][e] = <Bf[a], Bf[a']>: one thread per pair, the G REs inside (the pair word is decoded once)
+    //    (two threads per pair with half of the REs each -- 3 full rounds instead of 1.5 at 576 pairs -- measured slower)
     for (int pi = threadIdx.x; pi < p.nPairs; pi += T) {
         const uint32_t w = __ldg(p.pairs + pi);
         const int a0 = (int)(w & 0xffffu), a1 = (int)(w >> 16);
@@ -302,7 +304,7 @@ pmi_pair_fused_kernel(const __grid_constant__ FusedDev p) {
             case 2: fused_rank_eval_multi<2, G, G>(rk, Gt, nVar, part, nValid); break;
             case 3: fused_rank_eval_multi<3, G, G>(rk, Gt, nVar, part, nValid); break;
             case 4: fused_rank_eval_multi<4, G, (G > 2 ? 2 : G)>(rk, Gt, nVar, part, nValid); break;
-            case 5: fused_rank_eval<5, G>(rk, Gt, nVar, part, nValid); break;
+            case 5: fused_rank_eval_multi<5, G, (G > 2 ? 2 : G)>(rk, Gt, nVar, part, nValid); break;
             case 6: fused_rank_eval<6, G>(rk, Gt, nVar, part, nValid); break;
             case 7: fused_rank_eval<7, G>(rk, Gt, nVar, part, nValid); break;
             default: fused_rank_eval<8, G>(rk, Gt, nVar, part, nValid); break;
@@ -605,6 +607,15 @@ int pmi_fused_run(PmiPlan* const* grp, int n, const float2* H, const double* nv,
         pr.part = q->d_part; pr.sel = q->d_sel; pr.sinrSel = q->d_sinrSel; pr.sinrWb = q->d_sinrWb;
         pr.nCand = t.nCand(); pr.nu = q->nLayers; pr.n2 = t.n2; pr.n11 = t.n11; pr.n12 = t.n12; pr.n13 = t.n13;
         maxCand = std::max(maxCand, pr.nCand);
+    }
+    static const bool dbg = getenv("ISAC_PAIR_DEBUG") != nullptr;
+    if (dbg) {
+        static bool once = false;
+        if (!once) {
+            once = true;
+            fprintf(stderr, "[isac] fused report: G=%d T=%d atoms=%d pairs=%d colPairs=%d cpT=%d palette=%d chunks=%d smem=%zu ranks=%d\n", G, T,
+                    d.NB * d.nBeams, d.nPairs, d.nCP, d.cpT, d.nPal, d.nChunks, fused_smem_bytes(sh, d.R, G), d.nRanks);
+        }
     }
     const size_t smem = fused_smem_bytes(sh, d.R, G);
     if (smem > 227 * 1024 - 1024) { set_error(ctx, "pmi_fused_run: tables exceed shared memory"); return kErrCapacity; }
