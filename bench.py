@@ -40,7 +40,7 @@ STAGES = ["echo_demod", "rdm_2dfft", "cfar2d", "covariance", "music_doa", "cdl_d
 # group, which runs its Cholesky factorisations on the FP64 pipe
 FP64_PEAK_TFLOPS = 32.8
 # FP64 flops of one 32-UE cfg2 CSI report (8 ports (2,2), ranks 1-8, 273 REs): DFMA = 2, DMUL / DADD = 1, thread-level counts
-# of the SASS instructions executed (ncu source page of profiles/r2_pmi_fused_v2_summary.txt, scaled by UEs / 32)
+# of the SASS instructions executed (ncu source page of profiles/r2_pmi_fused_v3_summary.txt, scaled by UEs / 32)
 PMI_FLOPS_PER_UE_REPORT = 2.39e8
 
 
@@ -548,7 +548,7 @@ def run_b200(args):
                           "frac": round(ach / FP64_PEAK_TFLOPS, 4), "avg_launch_us": round(ms / n * 1e3, 2),
                           "share_of_step": round(ms / ms_total, 4),
                           "peak_source": "measured DFMA rate (tools/micro/fp64_peak.cu, profiles/r2_fp64_peak.txt)",
-                          "fp64_pipe_pct_ncu": 34.1, "ncu": "profiles/r2_pmi_fused_v2_summary.txt"}
+                          "fp64_pipe_pct_ncu": 36.0, "ncu": "profiles/r2_pmi_fused_v3_summary.txt"}
             continue
         if n and ms > 0 and name not in alg:
             roof[name] = {"bound": "latency/alu", "avg_launch_us": round(ms / n * 1e3, 2), "share_of_step": round(ms / ms_total, 4)}
