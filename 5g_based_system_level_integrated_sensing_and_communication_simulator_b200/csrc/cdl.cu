@@ -201,6 +201,9 @@ struct CdlBatch {
     double t0[kCdlMaxBatch];
 };
 
+// LPER = symbols per work item (compile time: a run-time bound on fully unrolled 16-symbol loops issued every predicated-off
+// iteration -- 9 of 16 at L = 14, 15 of 16 for the one-symbol SRS channels)
+template <int LPER>
 __global__ void __launch_bounds__(128)
 cdl_cluster_kernel(const CdlBatch bt, int nRay, int losRay, int nCl, int nRx, int nTx, int L, const CdlTimes tl,
                    float2* __restrict__ Call /*[batch][nCl][J]*/) {
@@ -224,30 +227,35 @@ cdl_cluster_kernel(const CdlBatch bt, int nRay, int losRay, int nCl, int nRx, in
     __syncthreads();
     // work item = (antenna pair us, symbol group): groups of symbols so that all 128 threads are busy when RT < 128
     const int groups = RT >= (int)blockDim.x ? 1 : (int)blockDim.x / RT;
-    const int lper = (L + groups - 1) / groups;
+    const int lper = LPER;   // == ceil(L / groups), chosen by the host
     for (int w = threadIdx.x; w < RT * groups; w += blockDim.x) {
         const int us = w % RT, grp = w / RT;
         const int u = us / nTx, sx = us % nTx;
         const int l0 = grp * lper, l1 = min(L, l0 + lper);
-        double re[kCdlMaxSym], im[kCdlMaxSym];
+        double re[LPER], im[LPER];
 #pragma unroll
-        for (int l = 0; l < kCdlMaxSym; ++l) re[l] = im[l] = 0.0;
-        // ray coefficients five at a time: the loads of a group are independent, so one global-memory latency covers five rays
-        // instead of one (the serial form spent 20 x a dependent shared -> global load chain per thread); same summation order
+        for (int l = 0; l < LPER; ++l) re[l] = im[l] = 0.0;
+        // ray coefficients five at a time, double-buffered: the loads of group k + 1 are in flight while group k is accumulated,
+        // so one global-memory latency is exposed per thread instead of one per ray (the serial form spent 20 x a dependent
+        // shared -> global load chain); same summation order
         constexpr int kGrp = 5;
-        for (int q0 = 0; q0 < cnt; q0 += kGrp) {
-            double2 gv[kGrp];
+        double2 gv[kGrp], gn[kGrp];
+        auto fetch = [&](int q0, double2 (&dst)[kGrp]) {
 #pragma unroll
             for (int u2 = 0; u2 < kGrp; ++u2)
-                gv[u2] = q0 + u2 < cnt ? __ldg(g + (size_t)rayIdx[q0 + u2] * RT + us) : make_double2(0.0, 0.0);
+                dst[u2] = q0 + u2 < cnt ? __ldg(g + (size_t)rayIdx[q0 + u2] * RT + us) : make_double2(0.0, 0.0);
+        };
+        fetch(0, gv);
+        for (int q0 = 0; q0 < cnt; q0 += kGrp) {
+            fetch(q0 + kGrp, gn);
 #pragma unroll
             for (int u2 = 0; u2 < kGrp; ++u2) {
                 const int q = q0 + u2;
                 if (q < cnt) {
 #pragma unroll
-                    for (int d = 0; d < kCdlMaxSym; ++d) {
+                    for (int d = 0; d < LPER; ++d) {
                         const int l = l0 + d;
-                        if (d < lper && l < l1) {
+                        if (l < l1) {
                             const double2 p = ph[l][q];
                             re[d] = fma(gv[u2].x, p.x, fma(-gv[u2].y, p.y, re[d]));
                             im[d] = fma(gv[u2].x, p.y, fma(gv[u2].y, p.x, im[d]));
@@ -255,12 +263,14 @@ cdl_cluster_kernel(const CdlBatch bt, int nRay, int losRay, int nCl, int nRx, in
                     }
                 }
             }
+#pragma unroll
+            for (int u2 = 0; u2 < kGrp; ++u2) gv[u2] = gn[u2];
         }
         // MATLAB order of H(k,l,u,s): j = l + L*(u + nRx*s)
 #pragma unroll
-        for (int d = 0; d < kCdlMaxSym; ++d) {
+        for (int d = 0; d < LPER; ++d) {
             const int l = l0 + d;
-            if (d < lper && l < l1)
+            if (l < l1)
                 C[(size_t)n * L * RT + l + (size_t)L * (u + (size_t)nRx * sx)] = make_float2((float)re[d], (float)im[d]);
         }
     }
@@ -676,7 +686,17 @@ int cdl_generate_batch(Ctx* ctx, CdlRays* const* rays, int n, int K, double scsH
         }
         const int pr = prof_begin(ctx, kProfCdl, st);
         dim3 g1(r0.nCl, nb);
-        cdl_cluster_kernel<<<g1, 128, 0, st>>>(bt, r0.nRay, losRay, r0.nCl, r0.nRx, r0.nTx, L, tl, (float2*)dC);
+        {
+            const int groups = RT >= 128 ? 1 : 128 / RT, lper = (L + groups - 1) / groups;   // as in the kernel
+#define ISAC_CDL_CLUSTER(N_) case N_: cdl_cluster_kernel<N_><<<g1, 128, 0, st>>>(bt, r0.nRay, losRay, r0.nCl, r0.nRx, r0.nTx, L, tl, (float2*)dC); break;
+            switch (lper) {
+                ISAC_CDL_CLUSTER(1) ISAC_CDL_CLUSTER(2) ISAC_CDL_CLUSTER(3) ISAC_CDL_CLUSTER(4) ISAC_CDL_CLUSTER(5) ISAC_CDL_CLUSTER(6)
+                ISAC_CDL_CLUSTER(7) ISAC_CDL_CLUSTER(8) ISAC_CDL_CLUSTER(9) ISAC_CDL_CLUSTER(10) ISAC_CDL_CLUSTER(11) ISAC_CDL_CLUSTER(12)
+                ISAC_CDL_CLUSTER(13) ISAC_CDL_CLUSTER(14) ISAC_CDL_CLUSTER(15)
+                default: cdl_cluster_kernel<16><<<g1, 128, 0, st>>>(bt, r0.nRay, losRay, r0.nCl, r0.nRx, r0.nTx, L, tl, (float2*)dC); break;
+            }
+#undef ISAC_CDL_CLUSTER
+        }
         dim3 grid((K + kCdlTK - 1) / kCdlTK, (unsigned)((J + kCdlTJ - 1) / kCdlTJ), nb);
         if (!legacyMma) {   // tcgen05 / TMEM path
             dim3 gu((K + kUmmaM - 1) / kUmmaM, nb);   // one CTA per (128-subcarrier tile, channel), looping over the column tiles
