@@ -1365,12 +1365,14 @@ int ul_pmi_select_batch_finish(Ctx* ctx, std::vector<UlPmiResult>& outs) {
 // reproduces the grid semantics for arbitrary indices without a scratch grid or a second pass.  The layer symbols, the index
 // arithmetic (a 64-bit modulo) and the PRG number are evaluated once per RE and reused for all P ports; every store of a warp
 // is one contiguous run along the RE axis.
+template <int NU>   // layers, compile time: a run-time bound on the unrolled layer loops issues every predicated-off iteration
 __global__ void __launch_bounds__(256)
-prg_precode_kernel(const float2* __restrict__ sym, const int* __restrict__ ind, int NRE, long long plane, int K, int nu,
+prg_precode_kernel(const float2* __restrict__ sym, const int* __restrict__ ind, int NRE, long long plane, int K,
                    const float2* __restrict__ F, int P, int NPRG, int nStartGrid, int Pd, float2* __restrict__ antsym,
                    int* __restrict__ antind) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NRE) return;
+    constexpr int nu = NU;
     // blockIdx.y: independent allocations of a batch (e.g. the cells of one slot), every array stacked along its last dim
     sym += (long long)blockIdx.y * NRE * nu;
     ind += (long long)blockIdx.y * NRE * nu;
@@ -1382,28 +1384,25 @@ prg_precode_kernel(const float2* __restrict__ sym, const int* __restrict__ ind, 
                                                                                   : i0 % plane;  // RE position of the first layer's index
     const int k = (int)(pos % K);
     const int prg = (nStartGrid + k / 12) / Pd;             // getPRGSet (prgPrecode.m:94-100), 0-based
-    float2 x[kMaxLayers];
+    float2 x[NU];
 #pragma unroll
-    for (int l = 0; l < kMaxLayers; ++l) {
+    for (int l = 0; l < NU; ++l) {
         x[l] = make_float2(0.f, 0.f);
-        if (l < nu) {
-            const long long target = pos + plane * l + 1;
-            if ((long long)ind[i + (long long)NRE * l] == target) x[l] = sym[i + (long long)NRE * l];
-            else
-                for (long long q = 0; q < (long long)NRE * nu; ++q)
-                    if ((long long)ind[q] == target) x[l] = sym[q];
-        }
+        const long long target = pos + plane * l + 1;
+        if ((long long)ind[i + (long long)NRE * l] == target) x[l] = sym[i + (long long)NRE * l];
+        else
+            for (long long q = 0; q < (long long)NRE * nu; ++q)
+                if ((long long)ind[q] == target) x[l] = sym[q];
     }
     const float2* __restrict__ Fp = F + (long long)nu * P * prg;
     for (int p = 0; p < P; ++p) {
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int l = 0; l < kMaxLayers; ++l)
-            if (l < nu) {
-                const float2 f = __ldg(Fp + l + nu * p);
-                acc.x += x[l].x * f.x - x[l].y * f.y;           // portgrid * F(:,:,prg) (prgPrecode.m:134)
-                acc.y += x[l].x * f.y + x[l].y * f.x;
-            }
+        for (int l = 0; l < NU; ++l) {
+            const float2 f = __ldg(Fp + l + nu * p);
+            acc.x += x[l].x * f.x - x[l].y * f.y;           // portgrid * F(:,:,prg) (prgPrecode.m:134)
+            acc.y += x[l].x * f.y + x[l].y * f.x;
+        }
         antsym[i + (long long)NRE * p] = acc;
         antind[i + (long long)NRE * p] = (int)(pos + 1 + plane * p);
     }
@@ -1422,7 +1421,12 @@ int prg_precode_run(Ctx* ctx, int K, int Lsym, int nStartGrid, const float2* por
     const int Pd = (nrb + nStartGrid + NPRG - 1) / NPRG;  // Pd_BWP = ceil((NRB+nstartgrid)/NPRG)
     const int pr = prof_begin(ctx, kProfPrecode, st);
     dim3 grid((unsigned)((NRE + 255) / 256), batch);
-    prg_precode_kernel<<<grid, 256, 0, st>>>(portsym, portind, NRE, plane, K, nu, F, P, NPRG, nStartGrid, Pd, antsym, antind);
+#define ISAC_PRG(N_) case N_: prg_precode_kernel<N_><<<grid, 256, 0, st>>>(portsym, portind, NRE, plane, K, F, P, NPRG, nStartGrid, Pd, antsym, antind); break;
+    switch (nu) {
+        ISAC_PRG(1) ISAC_PRG(2) ISAC_PRG(3) ISAC_PRG(4) ISAC_PRG(5) ISAC_PRG(6) ISAC_PRG(7) ISAC_PRG(8)
+        default: set_error(ctx, "prgPrecode: more than 8 layers"); return kErrInvalidArg;
+    }
+#undef ISAC_PRG
     prof_end(ctx, pr, st);
     count_launches(ctx, 1);
     ISAC_CUDA_CHECK(ctx, cudaGetLastError());
