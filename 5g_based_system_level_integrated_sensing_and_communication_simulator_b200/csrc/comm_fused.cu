@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kSelThreads) pmi_select_fused_kernel(const __g
     const size_t chunkStride = (size_t)nu * nCand;
     const double* __restrict__ part = p.part + (size_t)b * pd.nChunks * chunkStride;
     // totalSINR (dlPMISelect.m:444) = sum over every RE and layer, NaN skipped: the partials of candidate c are the rows
-    // (chunk, layer) of a [nChunks*nu][nCand] array; thread group g adds rows g, g + groups, ... (8 independent loads in
+    // (chunk, layer) of a [nChunks*nu][nCand] array; thread group g adds rows g, g + groups, ... (16 independent loads in
     // flight), then the groups are added in order -- a fixed summation order
     int span = 32;
     while (span < nCand && span < kSelThreads) span <<= 1;
@@ -356,6 +356,13 @@ __global__ void __launch_bounds__(kSelThreads) pmi_select_fused_kernel(const __g
         for (int c = threadIdx.x % span; c < nCand; c += span) {
             double tot = 0.0;
             int r = g;
+            for (; r + 15 * groups < rows; r += 16 * groups) {   // 16 loads in flight: a 384-candidate rank has one row group only
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = __ldcs(part + (size_t)(r + u * groups) * nCand + c);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) tot += (v[u] == v[u]) ? v[u] : 0.0;
+            }
             for (; r + 7 * groups < rows; r += 8 * groups) {
                 double v[8];
 #pragma unroll

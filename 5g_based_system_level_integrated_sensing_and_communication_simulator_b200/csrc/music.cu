@@ -301,11 +301,13 @@ __device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, doubl
                                                 double& s, double2& ph) {
     const double g2 = gamma.x * gamma.x + gamma.y * gamma.y;
     if (!(g2 > tol * tol * alpha * beta) || g2 == 0.0) return false;
-    const double g = sqrt(g2);
-    ph = make_double2(gamma.x / g, -gamma.y / g);  // e^{-i phi}
-    const double zeta = (beta - alpha) / (2.0 * g);
-    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    c = 1.0 / sqrt(1.0 + t * t);
+    // reciprocal square roots instead of sqrt + division: the rotation parameters sit on the serial path of every Jacobi step
+    // (one warp per column pair waits for them), and a rotation that is a few ulp off is corrected by the next sweep
+    const double ig = rsqrt(g2);
+    ph = make_double2(gamma.x * ig, -gamma.y * ig);  // e^{-i phi}
+    const double zeta = 0.5 * (beta - alpha) * ig;
+    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+    c = rsqrt(fma(t, t, 1.0));
     s = c * t;
     return true;
 }
