@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """bench.py — throughput of the B200-native ISAC hot path (contract: see the task statement).
 
-Metric (BASELINE.json): cell-subframes/sec.  One *step* = one 10 ms frame (10 subframes) of hot-path
-work for each of ``cells_per_gpu`` cells of BASELINE config 2 (1 gNB, 8 UE, 4 targets, 8x8,
-273 PRB @ 30 kHz, TDD DDDSU -> 168 DL symbols per frame):
+Metric (BASELINE.json): cell-subframes/sec.  One *step* = ``--frames-per-step`` (default 10) consecutive 10 ms frames
+(10 subframes each) of hot-path work for each of ``cells_per_gpu`` cells of BASELINE config 2 (1 gNB, 8 UE, 4 targets, 8x8,
+273 PRB @ 30 kHz, TDD DDDSU -> 168 DL symbols per frame), so the default K = 20 steps give a >= 1 s timed region:
     sensing : mono-static echo synthesis + OFDM demod of the frame's DL waveform (K1+K2),
               2D-FFT range-Doppler map + 2D CA-CFAR (K3+K4), antenna covariance + MUSIC DoA (K5+K6);
     comm    : per UE and CSI-RS occasion RI/PMI/CQI selection over the Type-I codebook (K7-K9), UL TPMI
